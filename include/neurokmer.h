@@ -1,0 +1,209 @@
+/*
+ * neurokmer.h — C ABI of libneurokmer (B200 / sm_100a).
+ *
+ * This is the drop-in boundary for NeuroKmer's counting hot path.  The
+ * reference has no FFI layer of its own: the seam is the Rust type
+ * `SpikingKmerCounter` (reference src/spiking_hash.rs:16-37, impl :39-715).
+ * Each entry point below names the reference item it replaces; the Rust
+ * `extern "C"` block a maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - every function returns an nk_status (0 = ok); nk_last_error() returns a
+ *    thread-local human-readable message for the last failure on this thread;
+ *  - the caller owns every input and output buffer, the library owns the
+ *    opaque handle and all device / pinned memory behind it;
+ *  - one thread at a time per handle (the reference takes `&mut self`);
+ *    distinct handles are independent;
+ *  - a batch of sequences is passed as one concatenated byte array `bases`
+ *    plus `offsets[nseq+1]` (offsets[0] = 0, sequence i = bases[offsets[i] ..
+ *    offsets[i+1])), i.e. the flattened form of the reference's `&[Vec<u8>]`;
+ *  - there is NO CPU fallback: without a usable sm_100 device nk_create fails.
+ */
+#ifndef NEUROKMER_H
+#define NEUROKMER_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define NK_API __attribute__((visibility("default")))
+#else
+#define NK_API
+#endif
+
+typedef enum nk_status {
+    NK_OK = 0,
+    NK_ERR_BAD_ARG = 1,     /* k outside [1,32], pool_size == 0, null pointer, bad offsets … */
+    NK_ERR_IO = 2,          /* file could not be opened / read (reference: Err from parse_fastx_file) */
+    NK_ERR_CUDA = 3,        /* CUDA runtime error; message carries cudaGetErrorString */
+    NK_ERR_NO_DEVICE = 4,   /* no CUDA device, or device is not compute capability 10.x */
+    NK_ERR_OOM = 5,         /* device or pinned-host allocation failed */
+    NK_ERR_STATE = 6,       /* call sequence error (e.g. stream_push without stream_begin) */
+    NK_ERR_UNSUPPORTED = 7  /* documented limit exceeded (e.g. pool_size >= 2^32) */
+} nk_status;
+
+typedef struct nk_counter nk_counter; /* opaque; replaces `SpikingKmerCounter` */
+
+/* Arguments of SpikingKmerCounter::new (reference src/spiking_hash.rs:40-48)
+ * plus `steps` (field, default 1000, :70) and the CUDA device ordinal. */
+typedef struct nk_config {
+    uint32_t k;            /* 1..32 */
+    uint32_t refractory;   /* refractory period in ticks */
+    uint64_t pool_size;    /* 1 .. 2^32-1 neurons */
+    uint64_t steps;        /* LIF ticks per simulation */
+    double   spike_cost;
+    float    threshold;
+    float    leak;
+    int32_t  use_canonical; /* 0 = pack_kmer path, 1 = rolling canonical path */
+    int32_t  device;        /* CUDA device ordinal */
+} nk_config;
+
+/* One row of top_abundant_neurons()'s Vec<(usize, u64, u32)>
+ * (reference src/spiking_hash.rs:661-673). `uniques` needs the exact-count side
+ * table; until nk_enable_exact_counts is implemented it is
+ * reported as NK_UNIQUES_NOT_COMPUTED, never faked. */
+typedef struct nk_top_entry {
+    uint64_t idx;
+    uint64_t spikes;
+    uint32_t uniques;
+    uint32_t _pad;
+} nk_top_entry;
+#define NK_UNIQUES_NOT_COMPUTED 0xFFFFFFFFu
+
+/* Device-side time of the last process/simulate call, CUDA events, milliseconds. */
+typedef struct nk_timings {
+    float h2d_ms;        /* host→device copies (0 for staged/device-resident input) */
+    float mark_ms;       /* invalid-start bitmap: memset + sequence-end marking kernels */
+    float count_ms;      /* the fused windowing + SipHash + mod + pool-update kernel(s) */
+    float fold_ms;       /* u32 batch pool → u64 currents */
+    float lif_ms;        /* LIF simulation */
+    float topn_ms;       /* last nk_top_n */
+    float total_ms;      /* first kernel/copy → last kernel of the call */
+    uint64_t kmers;      /* windows counted by the call */
+    uint64_t launches;   /* kernels launched by the call */
+    uint64_t h2d_bytes;  /* bytes copied host→device by the call */
+    uint64_t d2h_bytes;  /* bytes copied device→host by the call */
+    int32_t  lif_path;   /* 0 none, 1 direct simulation, 2 per-count table (uniform fresh state) */
+    int32_t  _pad;
+    uint64_t topn_launches; /* kernels launched by the last nk_top_n */
+} nk_timings;
+
+/* ---- lifecycle ---------------------------------------------------------- */
+/* CLI defaults of the reference: k=31, pool 1,000,000, canonical off,
+ * threshold 1.0, leak 0.95, refractory 2, spike_cost 1.0 (src/main.rs:10-37),
+ * steps 1000 (src/spiking_hash.rs:70). */
+NK_API int nk_config_default(nk_config* cfg);
+/* SpikingKmerCounter::new — src/spiking_hash.rs:40-77 */
+NK_API int nk_create(const nk_config* cfg, nk_counter** out);
+NK_API int nk_destroy(nk_counter* h);
+/* Back to the state nk_create leaves (all neurons v=0, r=0, spike_count=0, energy 0,
+ * currents 0): what constructing a fresh SpikingKmerCounter gives (:49-76). */
+NK_API int nk_reset(nk_counter* h);
+NK_API const char* nk_last_error(void);
+NK_API const char* nk_version(void);
+
+/* set_steps / get_steps — src/spiking_hash.rs:688-695 */
+NK_API int nk_set_steps(nk_counter* h, uint64_t steps);
+NK_API int nk_get_steps(const nk_counter* h, uint64_t* steps);
+
+/* ---- batch entry points --------------------------------------------------- */
+/* process_parallel — src/spiking_hash.rs:84-201.  Counts every window of every
+ * sequence, OVERWRITES the per-neuron currents with this call's totals, then
+ * runs the in-memory LIF driver (zero-current neurons skipped, :187-200).
+ * `bases`/`offsets` are host pointers (pinned memory is copied directly,
+ * pageable memory goes through the library's pinned staging ring). */
+NK_API int nk_process_batch(nk_counter* h, const uint8_t* bases, const uint64_t* offsets, uint64_t nseq);
+
+/* process_file_streaming minus parsing — src/spiking_hash.rs:277-486.
+ * begin: zero the accumulators; push: count a batch (asynchronous: returns as
+ * soon as the batch is staged, overlapping the next push's copy with this
+ * push's kernels); end: totals OVERWRITE currents, then the streaming LIF
+ * driver runs (every neuron stepped, :544-659). */
+NK_API int nk_stream_begin(nk_counter* h);
+NK_API int nk_stream_push(nk_counter* h, const uint8_t* bases, const uint64_t* offsets, uint64_t nseq);
+NK_API int nk_stream_end(nk_counter* h);
+
+/* Whole-file drivers: main.rs:170-177.  streaming != 0 → process_file_streaming
+ * (:277), else stream_sequences().collect() + process_parallel (main.rs:175-176).
+ * FASTA/FASTQ record rules follow src/utils.rs:9-24. */
+NK_API int nk_process_file(nk_counter* h, const char* path, int streaming);
+
+/* process_sequence — src/spiking_hash.rs:203-273 (per-sequence API: one LIF tick
+ * per call with the raw count as input current; currents zeroed afterwards). */
+NK_API int nk_process_sequence(nk_counter* h, const uint8_t* seq, uint64_t len);
+
+/* simulate_spikes_auto — src/spiking_hash.rs:697-714 (streaming-driver semantics
+ * on the currently stored currents). */
+NK_API int nk_simulate(nk_counter* h);
+
+/* ---- read-outs ------------------------------------------------------------ */
+/* top_abundant_neurons — src/spiking_hash.rs:661-673: spike_count descending,
+ * ties by ascending neuron index; writes min(top_n, pool_size) rows. */
+NK_API int nk_top_n(nk_counter* h, uint64_t top_n, nk_top_entry* out, uint64_t* n_out);
+/* energy.total_spikes() — src/models.rs:166-168 */
+NK_API int nk_total_spikes(const nk_counter* h, uint64_t* out);
+/* energy_used() — src/spiking_hash.rs:684-686, src/models.rs:170-172 */
+NK_API int nk_energy_used(const nk_counter* h, double* out);
+/* get_count — src/spiking_hash.rs:675-678 (exact side table):
+ * returns NK_ERR_UNSUPPORTED until exact counting is implemented. */
+NK_API int nk_get_count(nk_counter* h, uint64_t kmer, uint32_t* count, int32_t* found);
+
+/* ---- parity taps (debug; not on the timed path) ---------------------------- */
+/* Words and neuron indices of every window of one sequence, in order: the
+ * values `packed`/`idx` take at src/spiking_hash.rs:108-111,121-125 (canonical)
+ * or :132-135 (pack_kmer).  Any of fwd/rc/words/idx may be NULL.  *n_out =
+ * max(0, len-k+1); buffers must hold that many u64. fwd/rc are only defined
+ * in canonical mode (RollingKmerHash::forward/reverse_complement). */
+NK_API int nk_debug_kmers(nk_counter* h, const uint8_t* seq, uint64_t len, uint64_t* fwd, uint64_t* rc,
+                          uint64_t* words, uint64_t* idx, uint64_t* n_out);
+/* SipHash-1-3(keys 0,0) of LE64(word) and word-hash % pool_size for a host array. */
+NK_API int nk_debug_hash(nk_counter* h, const uint64_t* words, uint64_t n, uint64_t* hashes, uint64_t* idx);
+NK_API int nk_copy_currents(nk_counter* h, uint64_t* out /* pool_size */);
+NK_API int nk_copy_spike_counts(nk_counter* h, uint64_t* out /* pool_size */);
+NK_API int nk_copy_voltages(nk_counter* h, float* out /* pool_size */);
+NK_API int nk_copy_refractory(nk_counter* h, uint32_t* out /* pool_size */);
+NK_API int nk_last_timings(const nk_counter* h, nk_timings* out);
+/* LIF path selection for tests: 0 = automatic (per-count table while every neuron is
+ * still in its initial state, direct simulation otherwise), 1 = always direct. */
+NK_API int nk_debug_set_lif_path(nk_counter* h, int mode);
+
+/* ---- device-resident input and multi-GPU plumbing --------------------------- */
+/* Reserve library-owned DEVICE buffers for a batch the caller will fill itself
+ * (cudaMemcpyAsync, its own kernel, or nk_synth_fill): *dev_bases holds nbytes
+ * (+ padding the kernels may read), *dev_offsets holds nseq+1 u64. */
+NK_API int nk_stage_reserve(nk_counter* h, uint64_t nbytes, uint64_t nseq, void** dev_bases, void** dev_offsets);
+/* Count the staged batch.  mode 0: process_parallel semantics (count, overwrite
+ * currents, in-memory LIF); mode 1: accumulate only (inside stream_begin/end). */
+NK_API int nk_process_staged(nk_counter* h, uint64_t nbytes, uint64_t nseq, int mode);
+/* Sharded (one process per GPU) runs: every rank accumulates its shard between
+ * nk_stream_begin and nk_stream_accumulated, sum-reduces the u64 array at
+ * *dev_currents (pool_size elements) across ranks with its own collective
+ * (e.g. ncclAllReduce ncclUint64 / torch.distributed), then calls
+ * nk_stream_finish.  nk_stream_end == accumulated + finish. */
+NK_API int nk_stream_accumulated(nk_counter* h, void** dev_currents);
+NK_API int nk_stream_finish(nk_counter* h);
+/* The CUDA stream (cudaStream_t) the handle's kernels run on. */
+NK_API int nk_cuda_stream(nk_counter* h, void** stream);
+NK_API int nk_synchronize(nk_counter* h);
+
+/* Position-addressable synthetic base generator: writes bases
+ * [start, start+n) of stream `seed` to device memory `dev_out`.
+ * flags bit0: sparse N-runs, bit1: 1 % lower-case blocks. Runs on the handle's stream. */
+NK_API int nk_synth_fill(nk_counter* h, void* dev_out, uint64_t seed, uint64_t start, uint64_t n, uint32_t flags);
+
+/* Pinned host memory helpers (so callers can parse straight into DMA-able memory). */
+NK_API int nk_host_alloc(void** ptr, uint64_t nbytes);
+NK_API int nk_host_free(void* ptr);
+
+/* non-canonical helper: pack_kmer — src/utils.rs:26-39 (pure host arithmetic,
+ * exported because python.rs:50-52 exposes it as pack_kmer_py). */
+NK_API uint64_t nk_pack_kmer(const uint8_t* kmer, uint64_t len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEUROKMER_H */

@@ -1,0 +1,278 @@
+"""Python mirror of the reference's counter API on top of the C ABI.
+
+`SpikingKmerCounter` has the reference type's names, argument order and error
+behaviour (reference src/spiking_hash.rs:39-715); `PySpikingCounter` has the
+surface of src/python.rs:7-53.  All arithmetic happens in libneurokmer.so (CUDA,
+sm_100a): this module only flattens inputs and formats outputs.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterable, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+from . import _lib
+from ._lib import NkConfig, NkTimings, NkTopEntry, check
+
+BytesLike = Union[bytes, bytearray, memoryview, np.ndarray]
+
+
+def flatten(seqs: Iterable[BytesLike]) -> Tuple[np.ndarray, np.ndarray]:
+    """`&[Vec<u8>]` -> (concatenated uint8 bases, uint64 offsets[nseq+1])."""
+    arrs = [np.frombuffer(s, dtype=np.uint8) if not isinstance(s, np.ndarray) else np.ascontiguousarray(s, np.uint8)
+            for s in seqs]
+    offsets = np.zeros(len(arrs) + 1, dtype=np.uint64)
+    if arrs:
+        offsets[1:] = np.cumsum([a.size for a in arrs], dtype=np.uint64)
+        bases = np.concatenate(arrs) if offsets[-1] else np.zeros(0, np.uint8)
+    else:
+        bases = np.zeros(0, np.uint8)
+    return bases, offsets
+
+
+def _ptr(a: Optional[np.ndarray]) -> Optional[int]:
+    return None if a is None or a.size == 0 else a.ctypes.data
+
+
+class PinnedBuffer:
+    """Page-locked host memory from the library (nk_host_alloc) viewed as a numpy array."""
+
+    def __init__(self, nbytes: int, dtype=np.uint8):
+        self._p = C.c_void_p()
+        check(_lib.lib().nk_host_alloc(C.byref(self._p), nbytes))
+        self.nbytes = nbytes
+        buf = (C.c_uint8 * max(nbytes, 1)).from_address(self._p.value)
+        self.array = np.frombuffer(buf, dtype=np.uint8, count=nbytes).view(dtype)
+
+    def free(self) -> None:
+        if self._p is not None and self._p.value:
+            self.array = None
+            _lib.lib().nk_host_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class _Energy:
+    """`counter.energy.total_spikes()` / `.total_energy()` — reference src/models.rs:145-173."""
+
+    def __init__(self, owner: "SpikingKmerCounter"):
+        self._o = owner
+
+    def total_spikes(self) -> int:
+        out = C.c_uint64()
+        check(self._o._L.nk_total_spikes(self._o._h, C.byref(out)))
+        return out.value
+
+    def total_energy(self) -> float:
+        return self._o.energy_used()
+
+
+class SpikingKmerCounter:
+    """reference src/spiking_hash.rs:16-37 (`new` at :40-77)."""
+
+    def __init__(self, k: int, threshold: float, leak: float, refractory: int, spike_cost: float,
+                 pool_size: int, use_canonical: bool, device: int = 0):
+        self._L = _lib.lib()
+        cfg = NkConfig()
+        check(self._L.nk_config_default(C.byref(cfg)))
+        cfg.k, cfg.threshold, cfg.leak = k, threshold, leak
+        cfg.refractory, cfg.spike_cost, cfg.pool_size = refractory, spike_cost, pool_size
+        cfg.use_canonical, cfg.device = int(bool(use_canonical)), device
+        self._h = C.c_void_p()
+        check(self._L.nk_create(C.byref(cfg), C.byref(self._h)))
+        self.k, self.pool_size, self.use_canonical = k, pool_size, bool(use_canonical)
+        self.energy = _Energy(self)
+
+    # lifecycle ------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._L.nk_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self) -> None:
+        check(self._L.nk_reset(self._h))
+
+    # reference entry points -------------------------------------------------
+    def process_parallel(self, seqs: Sequence[BytesLike]) -> None:
+        """src/spiking_hash.rs:84-201"""
+        bases, offsets = flatten(seqs)
+        self.process_batch(bases, offsets)
+
+    def process_batch(self, bases: np.ndarray, offsets: np.ndarray) -> None:
+        bases = np.ascontiguousarray(bases, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        check(self._L.nk_process_batch(self._h, _ptr(bases), offsets.ctypes.data, offsets.size - 1))
+
+    def process_sequence(self, seq: BytesLike) -> None:
+        """src/spiking_hash.rs:203-273"""
+        a = np.frombuffer(seq, np.uint8) if not isinstance(seq, np.ndarray) else np.ascontiguousarray(seq, np.uint8)
+        check(self._L.nk_process_sequence(self._h, _ptr(a), a.size))
+
+    def process_file_streaming(self, path: str) -> None:
+        """src/spiking_hash.rs:277-486; raises NkError(NK_ERR_IO) where the reference returns Err."""
+        check(self._L.nk_process_file(self._h, str(path).encode(), 1))
+
+    def process_file_in_memory(self, path: str) -> None:
+        """src/main.rs:44-45: stream_sequences().collect() + process_parallel."""
+        check(self._L.nk_process_file(self._h, str(path).encode(), 0))
+
+    # streaming by batches (process_file_streaming minus parsing)
+    def stream_begin(self) -> None:
+        check(self._L.nk_stream_begin(self._h))
+
+    def stream_push(self, bases: np.ndarray, offsets: np.ndarray) -> None:
+        bases = np.ascontiguousarray(bases, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        check(self._L.nk_stream_push(self._h, _ptr(bases), offsets.ctypes.data, offsets.size - 1))
+
+    def stream_end(self) -> None:
+        check(self._L.nk_stream_end(self._h))
+
+    def simulate_spikes_auto(self) -> None:
+        """src/spiking_hash.rs:697-714"""
+        check(self._L.nk_simulate(self._h))
+
+    def top_abundant_neurons(self, top_n: int) -> List[Tuple[int, int, Optional[int]]]:
+        """src/spiking_hash.rs:661-673 -> [(idx, spike_count, uniques)]; `uniques` is None
+        until the exact side table exists — never a made-up number."""
+        n = min(int(top_n), self.pool_size)
+        if n <= 0:
+            return []
+        out = (NkTopEntry * n)()
+        got = C.c_uint64()
+        check(self._L.nk_top_n(self._h, n, out, C.byref(got)))
+        return [(int(e.idx), int(e.spikes), None if e.uniques == _lib.NK_UNIQUES_NOT_COMPUTED else int(e.uniques))
+                for e in out[: got.value]]
+
+    def get_count(self, kmer: int) -> Optional[int]:
+        """src/spiking_hash.rs:675-678"""
+        cnt, found = C.c_uint32(), C.c_int32()
+        check(self._L.nk_get_count(self._h, kmer, C.byref(cnt), C.byref(found)))
+        return int(cnt.value) if found.value else None
+
+    def energy_used(self) -> float:
+        out = C.c_double()
+        check(self._L.nk_energy_used(self._h, C.byref(out)))
+        return out.value
+
+    def set_steps(self, steps: int) -> None:
+        check(self._L.nk_set_steps(self._h, steps))
+
+    def get_steps(self) -> int:
+        out = C.c_uint64()
+        check(self._L.nk_get_steps(self._h, C.byref(out)))
+        return out.value
+
+    # parity taps ------------------------------------------------------------
+    def debug_kmers(self, seq: BytesLike):
+        a = np.frombuffer(seq, np.uint8) if not isinstance(seq, np.ndarray) else np.ascontiguousarray(seq, np.uint8)
+        n = max(0, a.size - self.k + 1)
+        fwd, rc, words, idx = (np.zeros(max(n, 1), np.uint64) for _ in range(4))
+        got = C.c_uint64()
+        check(self._L.nk_debug_kmers(self._h, _ptr(a), a.size, fwd.ctypes.data, rc.ctypes.data, words.ctypes.data,
+                                     idx.ctypes.data, C.byref(got)))
+        m = got.value
+        return fwd[:m], rc[:m], words[:m], idx[:m]
+
+    def debug_hash(self, words: np.ndarray):
+        w = np.ascontiguousarray(words, np.uint64)
+        hs, ix = np.zeros(max(w.size, 1), np.uint64), np.zeros(max(w.size, 1), np.uint64)
+        check(self._L.nk_debug_hash(self._h, _ptr(w), w.size, hs.ctypes.data, ix.ctypes.data))
+        return hs[: w.size], ix[: w.size]
+
+    def _copy(self, fn, dtype) -> np.ndarray:
+        out = np.zeros(self.pool_size, dtype)
+        check(fn(self._h, out.ctypes.data))
+        return out
+
+    def currents(self) -> np.ndarray:
+        return self._copy(self._L.nk_copy_currents, np.uint64)
+
+    def spike_counts(self) -> np.ndarray:
+        return self._copy(self._L.nk_copy_spike_counts, np.uint64)
+
+    def voltages(self) -> np.ndarray:
+        return self._copy(self._L.nk_copy_voltages, np.float32)
+
+    def refractory_ticks(self) -> np.ndarray:
+        return self._copy(self._L.nk_copy_refractory, np.uint32)
+
+    def debug_set_lif_path(self, mode: int) -> None:
+        check(self._L.nk_debug_set_lif_path(self._h, mode))
+
+    def timings(self) -> dict:
+        t = NkTimings()
+        check(self._L.nk_last_timings(self._h, C.byref(t)))
+        return t.as_dict()
+
+    # device-resident input ----------------------------------------------------
+    def stage_reserve(self, nbytes: int, nseq: int) -> Tuple[int, int]:
+        b, o = C.c_void_p(), C.c_void_p()
+        check(self._L.nk_stage_reserve(self._h, nbytes, nseq, C.byref(b), C.byref(o)))
+        return b.value, o.value
+
+    def process_staged(self, nbytes: int, nseq: int, mode: int = 0) -> None:
+        check(self._L.nk_process_staged(self._h, nbytes, nseq, mode))
+
+    def synth_fill(self, dev_ptr: int, seed: int, start: int, n: int, flags: int = 0) -> None:
+        check(self._L.nk_synth_fill(self._h, dev_ptr, seed, start, n, flags))
+
+    def stream_accumulated(self) -> int:
+        p = C.c_void_p()
+        check(self._L.nk_stream_accumulated(self._h, C.byref(p)))
+        return p.value
+
+    def stream_finish(self) -> None:
+        check(self._L.nk_stream_finish(self._h))
+
+    def cuda_stream(self) -> int:
+        p = C.c_void_p()
+        check(self._L.nk_cuda_stream(self._h, C.byref(p)))
+        return p.value or 0
+
+    def synchronize(self) -> None:
+        check(self._L.nk_synchronize(self._h))
+
+
+def pack_kmer(kmer: BytesLike) -> int:
+    """reference src/utils.rs:26-39"""
+    a = np.frombuffer(kmer, np.uint8) if not isinstance(kmer, np.ndarray) else np.ascontiguousarray(kmer, np.uint8)
+    return int(_lib.lib().nk_pack_kmer(_ptr(a), a.size))
+
+
+def pack_kmer_py(kmer: BytesLike) -> int:
+    """src/python.rs:50-52"""
+    return pack_kmer(kmer)
+
+
+class PySpikingCounter:
+    """Surface of the reference's PyO3 class (src/python.rs:7-48): `PySpikingCounter(k, pool_size)`
+    with the LIF constants python.rs hard-codes (threshold 1.0, leak 0.95, refractory 2, cost 1.0)."""
+
+    def __init__(self, k: int, pool_size: int):
+        self._c = SpikingKmerCounter(k, 1.0, 0.95, 2, 1.0, pool_size, False)
+
+    def process_file(self, path: str) -> None:
+        # python.rs:21-28 feeds every record to process_sequence, in file order
+        from .fastx import read_fastx
+        for seq in read_fastx(path):
+            self._c.process_sequence(seq)
+
+    def get_counts(self) -> dict:
+        # python.rs:31-40 walks the exact side table, which is not built yet
+        raise _lib.NkError(_lib.NK_ERR_UNSUPPORTED, "exact k-mer side table (SURVEY §8 f1) is not built yet")
+
+    def energy_used(self) -> float:
+        return self._c.energy_used()

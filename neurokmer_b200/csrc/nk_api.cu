@@ -1,0 +1,975 @@
+// nk_api.cu — the C ABI of libneurokmer (see include/neurokmer.h) on top of the
+// sm_100a kernels.  Host-side orchestration only: staging, stream/event plumbing,
+// the handle that mirrors `SpikingKmerCounter` (reference src/spiking_hash.rs:16-37).
+//
+// There is no CPU compute path in this file: every count, hash, LIF tick and top-N
+// selection is a kernel launch; without an sm_100 device nk_create fails.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/neurokmer.h"
+#include "nk_host.h"
+#include "nk_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define NK_CUDA(expr)                                                                          \
+    do {                                                                                       \
+        cudaError_t e_ = (expr);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            return fail(e_ == cudaErrorMemoryAllocation ? NK_ERR_OOM : NK_ERR_CUDA, "%s: %s", #expr, \
+                        cudaGetErrorString(e_));                                               \
+    } while (0)
+
+#define NK_TRY(expr)              \
+    do {                          \
+        int rc_ = (expr);         \
+        if (rc_ != NK_OK) return rc_; \
+    } while (0)
+
+constexpr unsigned long long kChunkBytes = 32ull << 20;  // host->device pipeline granule (multiple of COUNT_TILE)
+static_assert(kChunkBytes % nk::COUNT_TILE == 0, "chunks must be whole tiles");
+
+struct DevBuf {
+    unsigned char* bases = nullptr;
+    unsigned long long bases_cap = 0;
+    unsigned int* invalid = nullptr;
+    unsigned long long invalid_cap = 0;  // words
+    cudaEvent_t copy_done = nullptr, compute_done = nullptr;
+};
+
+}  // namespace
+
+struct nk_counter {
+    nk_config cfg{};
+    nk::FastMod fm{};
+    int grid = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+
+    // pool state (device)
+    unsigned int* acc = nullptr;           // u32 batch accumulators (RED target)
+    unsigned long long* currents = nullptr;
+    float* v = nullptr;
+    unsigned int* r = nullptr;
+    unsigned long long* spikes = nullptr;
+    unsigned long long* scalars = nullptr;  // [0] spikes fired by last LIF, [1] max cumulative spikes, [2] kmers
+    unsigned int* tile_counter = nullptr;
+    unsigned long long* h_scalars = nullptr;  // pinned mirror
+
+    // LIF per-count table
+    nk::LifTable table{};
+    unsigned long long table_cap = 0;
+
+    // top-N scratch
+    nk::TopNScratch topn{};
+    unsigned long long topn_cap = 0;
+    nk_top_entry* h_top = nullptr;  // pinned, topn_cap rows (built from two arrays)
+
+    // host mirrors (EnergyTracker, src/models.rs:145-173)
+    unsigned long long total_spikes = 0, energy_fixed = 0;
+    bool fresh = true;      // every neuron still has v = 0, r = 0
+    int force_direct = 0;
+    bool streaming = false;
+    bool acc_dirty = false;
+    unsigned long long acc_kmers = 0;  // windows added to acc since the last fold (u32 overflow guard)
+    bool currents_valid_overwrite = true;  // next fold overwrites currents (first fold of a call)
+
+    // staging
+    DevBuf buf[2];
+    int cur_buf = 0;
+    unsigned long long* d_offsets = nullptr;
+    unsigned long long offsets_cap = 0;
+    // device-resident staged batch (nk_stage_reserve)
+    DevBuf staged;
+    unsigned long long* staged_offsets = nullptr;
+    unsigned long long staged_offsets_cap = 0;
+
+    std::vector<cudaEvent_t> evpool;
+    size_t ev_used = 0;
+    nk_timings last{};
+};
+
+namespace {
+
+int get_event(nk_counter* h, cudaEvent_t* out) {
+    if (h->ev_used == h->evpool.size()) {
+        cudaEvent_t e;
+        NK_CUDA(cudaEventCreate(&e));
+        h->evpool.push_back(e);
+    }
+    *out = h->evpool[h->ev_used++];
+    return NK_OK;
+}
+
+int ensure_devbuf(DevBuf& b, unsigned long long nbytes) {
+    const unsigned long long need = nk::count_padded_bases(nbytes);
+    if (need > b.bases_cap) {
+        if (b.bases) cudaFree(b.bases);
+        b.bases = nullptr;
+        b.bases_cap = 0;
+        NK_CUDA(cudaMalloc(&b.bases, need));
+        b.bases_cap = need;
+    }
+    const unsigned long long words = nk::count_bitmap_words(nbytes);
+    if (words > b.invalid_cap) {
+        if (b.invalid) cudaFree(b.invalid);
+        b.invalid = nullptr;
+        b.invalid_cap = 0;
+        NK_CUDA(cudaMalloc(&b.invalid, words * sizeof(unsigned int)));
+        b.invalid_cap = words;
+    }
+    if (!b.copy_done) NK_CUDA(cudaEventCreateWithFlags(&b.copy_done, cudaEventDisableTiming));
+    if (!b.compute_done) NK_CUDA(cudaEventCreateWithFlags(&b.compute_done, cudaEventDisableTiming));
+    return NK_OK;
+}
+
+int ensure_offsets(unsigned long long** p, unsigned long long* cap, unsigned long long n) {
+    if (n > *cap) {
+        if (*p) cudaFree(*p);
+        *p = nullptr;
+        *cap = 0;
+        const unsigned long long want = n + n / 4 + 16;
+        NK_CUDA(cudaMalloc(p, want * sizeof(unsigned long long)));
+        *cap = want;
+    }
+    return NK_OK;
+}
+
+struct PhaseEvents {
+    std::vector<cudaEvent_t> mark0, count0, count1;
+    cudaEvent_t begin = nullptr, copy0 = nullptr, copy1 = nullptr, fold0 = nullptr, fold1 = nullptr,
+                lif1 = nullptr, end = nullptr;
+};
+
+// fold acc into currents if a further `incoming` windows could overflow a u32 accumulator
+int fold_now(nk_counter* h) {
+    if (!h->acc_dirty) return NK_OK;
+    NK_CUDA(nk::launch_fold(h->acc, h->currents, h->cfg.pool_size, h->currents_valid_overwrite, h->stream));
+    ++h->last.launches;
+    h->currents_valid_overwrite = false;
+    h->acc_dirty = false;
+    h->acc_kmers = 0;
+    return NK_OK;
+}
+
+// mark + count one device-resident chunk: window starts [origin, origin+nstarts) of the
+// concatenated batch, whose bytes live at `b.bases` (chunk-relative) and whose offsets
+// (batch-absolute) live at d_offsets.
+int count_chunk(nk_counter* h, DevBuf& b, const unsigned long long* d_offsets, unsigned long long seq_lo,
+                unsigned long long seq_hi, unsigned long long origin, unsigned long long nstarts,
+                unsigned long long max_windows, PhaseEvents* pe) {
+    if (nstarts == 0) return NK_OK;
+    if (h->acc_kmers + max_windows > 0xFFFFFFFFull) NK_TRY(fold_now(h));
+    cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+    if (pe) {
+        NK_TRY(get_event(h, &e0));
+        NK_TRY(get_event(h, &e1));
+        NK_TRY(get_event(h, &e2));
+        NK_CUDA(cudaEventRecord(e0, h->stream));
+    }
+    NK_CUDA(cudaMemsetAsync(h->tile_counter, 0, sizeof(unsigned int), h->stream));
+    NK_CUDA(nk::launch_mark_invalid(b.invalid, d_offsets, seq_lo, seq_hi, origin, nstarts, h->cfg.k,
+                                    h->scalars + 2, h->stream, &h->last.launches));
+    if (pe) NK_CUDA(cudaEventRecord(e1, h->stream));
+    nk::CountParams p{};
+    p.bases = b.bases;
+    p.invalid = b.invalid;
+    p.acc = h->acc;
+    p.tile_counter = h->tile_counter;
+    p.ntiles = nk::count_ntiles(nstarts);
+    p.fm = h->fm;
+    p.k = h->cfg.k;
+    const unsigned long long want = p.ntiles < (unsigned long long)h->grid ? p.ntiles : (unsigned long long)h->grid;
+    NK_CUDA(nk::launch_count(p, h->cfg.use_canonical != 0, false, (int)want, h->stream));
+    ++h->last.launches;
+    if (pe) {
+        NK_CUDA(cudaEventRecord(e2, h->stream));
+        pe->mark0.push_back(e0);
+        pe->count0.push_back(e1);
+        pe->count1.push_back(e2);
+    }
+    h->acc_dirty = true;
+    h->acc_kmers += max_windows;
+    return NK_OK;
+}
+
+int validate_batch(const nk_counter* h, const uint8_t* bases, const uint64_t* offsets, uint64_t nseq) {
+    if (!h) return fail(NK_ERR_BAD_ARG, "null handle");
+    if (nseq > 0 && !offsets) return fail(NK_ERR_BAD_ARG, "null offsets");
+    if (nseq == 0) return NK_OK;
+    if (offsets[0] != 0) return fail(NK_ERR_BAD_ARG, "offsets[0] must be 0");
+    if (offsets[nseq] > 0 && !bases) return fail(NK_ERR_BAD_ARG, "null bases");
+    return NK_OK;
+}
+
+// host batch -> chunked H2D (copy stream) overlapped with mark+count (compute stream)
+int count_host_batch(nk_counter* h, const uint8_t* bases, const uint64_t* offsets, uint64_t nseq, PhaseEvents* pe) {
+    if (nseq == 0) return NK_OK;
+    for (uint64_t s = 0; s < nseq; ++s)
+        if (offsets[s + 1] < offsets[s]) return fail(NK_ERR_BAD_ARG, "offsets must be non-decreasing (at %llu)", (unsigned long long)s);
+    const unsigned long long nbytes = offsets[nseq];
+    if (nbytes == 0) return NK_OK;
+    NK_TRY(ensure_offsets(&h->d_offsets, &h->offsets_cap, nseq + 1));
+    if (pe && !pe->copy0) { NK_TRY(get_event(h, &pe->copy0)); NK_CUDA(cudaEventRecord(pe->copy0, h->copy_stream)); }
+    // the previous batch's kernels may still read d_offsets
+    if (h->buf[0].compute_done) NK_CUDA(cudaStreamWaitEvent(h->copy_stream, h->buf[0].compute_done, 0));
+    if (h->buf[1].compute_done) NK_CUDA(cudaStreamWaitEvent(h->copy_stream, h->buf[1].compute_done, 0));
+    NK_CUDA(cudaMemcpyAsync(h->d_offsets, offsets, (nseq + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, h->copy_stream));
+    h->last.h2d_bytes += (nseq + 1) * sizeof(uint64_t) + nbytes;
+
+    for (unsigned long long c0 = 0; c0 < nbytes; c0 += kChunkBytes) {
+        const unsigned long long c1 = std::min(c0 + kChunkBytes, nbytes);
+        const unsigned long long copy_len = std::min(c1 + nk::COUNT_HALO, nbytes) - c0;
+        DevBuf& b = h->buf[h->cur_buf];
+        h->cur_buf ^= 1;
+        const bool had = b.compute_done != nullptr;
+        NK_TRY(ensure_devbuf(b, std::min(kChunkBytes, nbytes)));
+        if (had) NK_CUDA(cudaStreamWaitEvent(h->copy_stream, b.compute_done, 0));
+        NK_CUDA(cudaMemcpyAsync(b.bases, bases + c0, copy_len, cudaMemcpyHostToDevice, h->copy_stream));
+        NK_CUDA(cudaEventRecord(b.copy_done, h->copy_stream));
+        NK_CUDA(cudaStreamWaitEvent(h->stream, b.copy_done, 0));
+        // sequences that overlap [c0, c1): first with end > c0 ... first with start >= c1
+        const uint64_t* first = std::upper_bound(offsets + 1, offsets + nseq + 1, (uint64_t)c0);
+        const unsigned long long seq_lo = (unsigned long long)(first - (offsets + 1));
+        const uint64_t* last = std::lower_bound(offsets, offsets + nseq, (uint64_t)c1);
+        const unsigned long long seq_hi = (unsigned long long)(last - offsets);
+        NK_TRY(count_chunk(h, b, h->d_offsets, seq_lo, seq_hi, c0, c1 - c0, c1 - c0, pe));
+        NK_CUDA(cudaEventRecord(b.compute_done, h->stream));
+    }
+    if (pe) {
+        if (!pe->copy1) NK_TRY(get_event(h, &pe->copy1));
+        NK_CUDA(cudaEventRecord(pe->copy1, h->copy_stream));
+    }
+    // the caller's buffers must be reusable on return: wait for the copies (not the kernels)
+    NK_CUDA(cudaStreamSynchronize(h->copy_stream));
+    return NK_OK;
+}
+
+unsigned long long saturation_count(const nk_config& c) {
+    // smallest count whose input current f32(f64(count)/f64(steps)) reaches the threshold
+    if (!(c.threshold == c.threshold)) return ~0ull;
+    auto cur = [&](unsigned long long n) { return (float)((double)n / (double)c.steps); };
+    if (cur(0) >= c.threshold) return 0;
+    unsigned long long lo = 0, hi = 1ull << 62;  // cur(lo) < thr
+    if (!(cur(hi) >= c.threshold)) return ~0ull;
+    while (hi - lo > 1) {
+        const unsigned long long mid = lo + (hi - lo) / 2;
+        if (cur(mid) >= c.threshold) hi = mid; else lo = mid;
+    }
+    return hi;
+}
+
+// LIF over the stored currents; skip_zero: in-memory driver (:187-200) vs SIMD driver (:544-659)
+int simulate(nk_counter* h, bool skip_zero) {
+    h->last.lif_path = 0;
+    if (h->cfg.steps == 0 || h->cfg.pool_size == 0) return NK_OK;
+    nk::LifParams p{};
+    p.currents = h->currents;
+    p.v = h->v;
+    p.r = h->r;
+    p.spikes = h->spikes;
+    p.total_new = h->scalars + 0;
+    p.max_spikes = h->scalars + 1;
+    p.pool = h->cfg.pool_size;
+    p.steps = h->cfg.steps;
+    p.thr = h->cfg.threshold;
+    p.leak = h->cfg.leak;
+    p.period = h->cfg.refractory;
+    p.skip_zero = skip_zero ? 1 : 0;
+    NK_CUDA(cudaMemsetAsync(h->scalars, 0, sizeof(unsigned long long), h->stream));
+    bool use_table = false;
+    unsigned long long table_n = 0;
+    if (h->fresh && !h->force_direct && std::isfinite(h->cfg.threshold) && std::isfinite(h->cfg.leak)) {
+        const unsigned long long sat = saturation_count(h->cfg);
+        if (sat < (1ull << 20)) { use_table = true; table_n = sat + 1; }
+    }
+    if (use_table) {
+        if (table_n > h->table_cap) {
+            if (h->table.spikes) cudaFree(h->table.spikes);
+            if (h->table.v) cudaFree(h->table.v);
+            if (h->table.r) cudaFree(h->table.r);
+            h->table = nk::LifTable{};
+            h->table_cap = 0;
+            NK_CUDA(cudaMalloc(&h->table.spikes, table_n * sizeof(unsigned int)));
+            NK_CUDA(cudaMalloc(&h->table.v, table_n * sizeof(float)));
+            NK_CUDA(cudaMalloc(&h->table.r, table_n * sizeof(unsigned int)));
+            h->table_cap = table_n;
+        }
+        NK_CUDA(nk::launch_lif_table(p, h->table, table_n, h->stream));
+        h->last.launches += 2;
+        h->last.lif_path = 2;
+    } else {
+        NK_CUDA(nk::launch_lif(p, h->stream));
+        h->last.launches += 1;
+        h->last.lif_path = 1;
+    }
+    h->fresh = false;
+    return NK_OK;
+}
+
+// read back {new spikes, max spikes, kmers}; update EnergyTracker mirrors
+int finish_call(nk_counter* h, bool had_lif) {
+    NK_CUDA(cudaMemcpyAsync(h->h_scalars, h->scalars, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    NK_CUDA(cudaStreamSynchronize(h->stream));
+    h->last.d2h_bytes += 3 * sizeof(unsigned long long);
+    if (had_lif) {
+        const unsigned long long fired = h->h_scalars[0];
+        h->total_spikes += fired;
+        // src/models.rs:162-163 / src/spiking_hash.rs:649-655
+        h->energy_fixed += fired * (unsigned long long)(h->cfg.spike_cost * 1000.0);
+    }
+    h->last.kmers = h->h_scalars[2];
+    return NK_OK;
+}
+
+float ev_ms(cudaEvent_t a, cudaEvent_t b) {
+    float ms = 0.f;
+    if (a && b) cudaEventElapsedTime(&ms, a, b);
+    return ms;
+}
+
+void collect_timings(nk_counter* h, const PhaseEvents& pe) {
+    float mark = 0.f, cnt = 0.f;
+    for (size_t i = 0; i < pe.mark0.size(); ++i) {
+        mark += ev_ms(pe.mark0[i], pe.count0[i]);
+        cnt += ev_ms(pe.count0[i], pe.count1[i]);
+    }
+    h->last.h2d_ms = ev_ms(pe.copy0, pe.copy1);
+    h->last.mark_ms = mark;
+    h->last.count_ms = cnt;
+    h->last.fold_ms = ev_ms(pe.fold0, pe.fold1);
+    h->last.lif_ms = ev_ms(pe.fold1, pe.lif1);
+    h->last.total_ms = ev_ms(pe.begin, pe.end);
+}
+
+void begin_call(nk_counter* h) {
+    h->ev_used = 0;
+    const float topn = h->last.topn_ms;
+    h->last = nk_timings{};
+    h->last.topn_ms = topn;
+}
+
+int free_devbuf(DevBuf& b) {
+    if (b.bases) cudaFree(b.bases);
+    if (b.invalid) cudaFree(b.invalid);
+    if (b.copy_done) cudaEventDestroy(b.copy_done);
+    if (b.compute_done) cudaEventDestroy(b.compute_done);
+    b = DevBuf{};
+    return NK_OK;
+}
+
+int fold_and_simulate(nk_counter* h, bool skip_zero, PhaseEvents& pe) {
+    NK_TRY(get_event(h, &pe.fold0));
+    NK_CUDA(cudaEventRecord(pe.fold0, h->stream));
+    if (!h->acc_dirty && h->currents_valid_overwrite) {
+        // nothing was counted by this call: totals are all zero (currents are OVERWRITTEN, :174-176)
+        NK_CUDA(cudaMemsetAsync(h->currents, 0, h->cfg.pool_size * sizeof(unsigned long long), h->stream));
+        h->currents_valid_overwrite = false;
+    }
+    NK_TRY(fold_now(h));
+    NK_TRY(get_event(h, &pe.fold1));
+    NK_CUDA(cudaEventRecord(pe.fold1, h->stream));
+    NK_TRY(simulate(h, skip_zero));
+    NK_TRY(get_event(h, &pe.lif1));
+    NK_CUDA(cudaEventRecord(pe.lif1, h->stream));
+    return NK_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// Whole-file driver (nk_process_file): FastxReader -> pinned batch -> count_host_batch.
+// Replaces the reference's producer thread + worker channels (src/spiking_hash.rs:285-422):
+// the parser fills a pinned batch while the previous batch's kernels run; a sequence that
+// does not fit is cut into pieces that overlap by k-1 bases (every window counted once).
+// ---------------------------------------------------------------------------
+namespace nk {
+
+int process_file(nk_counter* h, const char* path, bool streaming, std::string* err) {
+    FastxReader rd;
+    if (rd.open(path, err) != 0) return NK_ERR_IO;
+    auto cuda_fail = [&](cudaError_t e, const char* what) {
+        *err = std::string(what) + ": " + cudaGetErrorString(e);
+        return e == cudaErrorMemoryAllocation ? NK_ERR_OOM : NK_ERR_CUDA;
+    };
+    cudaError_t ce = cudaSetDevice(h->cfg.device);
+    if (ce != cudaSuccess) return cuda_fail(ce, "cudaSetDevice");
+    const size_t cap = (size_t)kChunkBytes;
+    uint8_t* batch = nullptr;
+    ce = cudaMallocHost((void**)&batch, cap);
+    if (ce != cudaSuccess) return cuda_fail(ce, "cudaMallocHost(batch)");
+    std::vector<uint64_t> offsets;
+    offsets.reserve(1u << 20);
+    offsets.push_back(0);
+    size_t fill = 0;
+    const unsigned k = h->cfg.k;
+
+    begin_call(h);
+    PhaseEvents pe;
+    int rc = NK_OK;
+    auto flush = [&]() -> int {
+        if (offsets.size() > 1 && fill > 0) {
+            int r = count_host_batch(h, batch, offsets.data(), offsets.size() - 1, nullptr);
+            if (r != NK_OK) { *err = g_err; return r; }
+        }
+        offsets.clear();
+        offsets.push_back(0);
+        fill = 0;
+        return NK_OK;
+    };
+    do {
+        if (get_event(h, &pe.begin) != NK_OK) { *err = g_err; rc = NK_ERR_CUDA; break; }
+        cudaEventRecord(pe.begin, h->stream);
+        cudaMemsetAsync(h->scalars + 2, 0, sizeof(unsigned long long), h->stream);
+        h->currents_valid_overwrite = true;
+        bool stop = false;
+        while (!stop && rd.next_record()) {
+            if (rd.is_fastq()) {
+                // a FASTQ record is validated as a whole before it counts: keep it inside one batch
+                size_t start = fill;
+                bool done = false;
+                for (;;) {
+                    fill += rd.read_seq(batch + fill, cap - fill, &done);
+                    if (done) break;
+                    if (start == 0) { *err = "FASTQ record longer than the 32 MiB batch buffer"; rc = NK_ERR_UNSUPPORTED; break; }
+                    // move the partial record to the front of a fresh batch
+                    const size_t part = fill - start;
+                    fill = start;
+                    std::vector<uint8_t> tmp(batch + start, batch + start + part);
+                    if ((rc = flush()) != NK_OK) break;
+                    memcpy(batch, tmp.data(), part);
+                    fill = part;
+                    start = 0;
+                }
+                if (rc != NK_OK) break;
+                if (!rd.finish_record(fill - start)) { fill = start; stop = true; break; }  // malformed: drop + stop
+                offsets.push_back(fill);
+            } else {
+                bool done = false;
+                while (!done) {
+                    if (fill == cap) {
+                        // close the piece, push, and restart with the last k-1 bases as overlap
+                        offsets.push_back(fill);
+                        uint8_t tail[32];
+                        const size_t ov = std::min<size_t>(k - 1, fill - offsets[offsets.size() - 2]);
+                        memcpy(tail, batch + fill - ov, ov);
+                        if ((rc = flush()) != NK_OK) break;
+                        memcpy(batch, tail, ov);
+                        fill = ov;
+                    }
+                    fill += rd.read_seq(batch + fill, cap - fill, &done);
+                }
+                if (rc != NK_OK) break;
+                offsets.push_back(fill);
+            }
+            if (fill == cap && (rc = flush()) != NK_OK) break;
+        }
+        if (rc != NK_OK) break;
+        if ((rc = flush()) != NK_OK) break;
+        if ((rc = fold_and_simulate(h, /*skip_zero=*/!streaming, pe)) != NK_OK) { *err = g_err; break; }
+        if (get_event(h, &pe.end) != NK_OK) { *err = g_err; rc = NK_ERR_CUDA; break; }
+        cudaEventRecord(pe.end, h->stream);
+        if ((rc = finish_call(h, true)) != NK_OK) { *err = g_err; break; }
+        collect_timings(h, pe);
+    } while (0);
+    cudaStreamSynchronize(h->copy_stream);
+    cudaStreamSynchronize(h->stream);
+    cudaFreeHost(batch);
+    return rc;
+}
+
+}  // namespace nk
+
+extern "C" {
+
+const char* nk_last_error(void) { return g_err.c_str(); }
+const char* nk_version(void) { return "neurokmer-b200 0.1.0 (sm_100a)"; }
+
+int nk_config_default(nk_config* cfg) {
+    if (!cfg) return fail(NK_ERR_BAD_ARG, "null cfg");
+    std::memset(cfg, 0, sizeof *cfg);
+    cfg->k = 31;               // src/main.rs:14-15
+    cfg->pool_size = 1000000;  // src/main.rs:17-18
+    cfg->use_canonical = 0;    // src/main.rs:20-21
+    cfg->threshold = 1.0f;     // src/main.rs:37
+    cfg->leak = 0.95f;
+    cfg->refractory = 2;
+    cfg->spike_cost = 1.0;
+    cfg->steps = 1000;         // src/spiking_hash.rs:70
+    cfg->device = 0;
+    return NK_OK;
+}
+
+int nk_create(const nk_config* cfg, nk_counter** out) {
+    if (!cfg || !out) return fail(NK_ERR_BAD_ARG, "null argument");
+    *out = nullptr;
+    if (cfg->k < 1 || cfg->k > 32) return fail(NK_ERR_BAD_ARG, "k must be in [1,32], got %u", cfg->k);
+    if (cfg->pool_size == 0) return fail(NK_ERR_BAD_ARG, "pool_size must be > 0");
+    if (cfg->pool_size >= (1ull << 32)) return fail(NK_ERR_UNSUPPORTED, "pool_size must be < 2^32");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(NK_ERR_NO_DEVICE, "no CUDA device (%s); libneurokmer has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(NK_ERR_BAD_ARG, "device %d out of range (%d devices)", cfg->device, ndev);
+    cudaDeviceProp prop{};
+    NK_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10)
+        return fail(NK_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", cfg->device, prop.major, prop.minor);
+    NK_CUDA(cudaSetDevice(cfg->device));
+
+    nk_counter* h = new nk_counter();
+    h->cfg = *cfg;
+    h->fm = nk::make_fastmod(cfg->pool_size);
+    auto bail = [&](int rc) { nk_destroy(h); return rc; };
+#define NK_C(expr)                                                                                              \
+    do {                                                                                                        \
+        cudaError_t e_ = (expr);                                                                                \
+        if (e_ != cudaSuccess)                                                                                  \
+            return bail(fail(e_ == cudaErrorMemoryAllocation ? NK_ERR_OOM : NK_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_))); \
+    } while (0)
+    NK_C(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    NK_C(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    const unsigned long long P = cfg->pool_size;
+    NK_C(cudaMalloc(&h->acc, P * sizeof(unsigned int)));
+    NK_C(cudaMalloc(&h->currents, P * sizeof(unsigned long long)));
+    NK_C(cudaMalloc(&h->v, P * sizeof(float)));
+    NK_C(cudaMalloc(&h->r, P * sizeof(unsigned int)));
+    NK_C(cudaMalloc(&h->spikes, P * sizeof(unsigned long long)));
+    NK_C(cudaMalloc(&h->scalars, 8 * sizeof(unsigned long long)));
+    NK_C(cudaMalloc(&h->tile_counter, 64));
+    NK_C(cudaMallocHost(&h->h_scalars, 8 * sizeof(unsigned long long)));
+    NK_C(cudaMalloc(&h->topn.hist, 256 * sizeof(unsigned int)));
+    NK_C(cudaMalloc(&h->topn.ctrl, 8 * sizeof(unsigned long long)));
+    NK_C(cudaMalloc(&h->topn.block_counts, ((P + nk::TOPN_BLOCK_ITEMS - 1) / nk::TOPN_BLOCK_ITEMS + 1) * sizeof(unsigned int)));
+    NK_C(nk::count_max_grid(cfg->use_canonical != 0, cfg->device, &h->grid));
+#undef NK_C
+    int rc = nk_reset(h);
+    if (rc != NK_OK) return bail(rc);
+    *out = h;
+    return NK_OK;
+}
+
+int nk_reset(nk_counter* h) {
+    if (!h) return fail(NK_ERR_BAD_ARG, "null handle");
+    NK_CUDA(cudaSetDevice(h->cfg.device));
+    const unsigned long long P = h->cfg.pool_size;
+    NK_CUDA(cudaMemsetAsync(h->acc, 0, P * sizeof(unsigned int), h->stream));
+    NK_CUDA(cudaMemsetAsync(h->currents, 0, P * sizeof(unsigned long long), h->stream));
+    NK_CUDA(cudaMemsetAsync(h->v, 0, P * sizeof(float), h->stream));
+    NK_CUDA(cudaMemsetAsync(h->r, 0, P * sizeof(unsigned int), h->stream));
+    NK_CUDA(cudaMemsetAsync(h->spikes, 0, P * sizeof(unsigned long long), h->stream));
+    NK_CUDA(cudaMemsetAsync(h->scalars, 0, 8 * sizeof(unsigned long long), h->stream));
+    h->total_spikes = 0;
+    h->energy_fixed = 0;
+    h->fresh = true;
+    h->streaming = false;
+    h->acc_dirty = false;
+    h->acc_kmers = 0;
+    h->currents_valid_overwrite = true;
+    return NK_OK;
+}
+
+int nk_destroy(nk_counter* h) {
+    if (!h) return NK_OK;
+    cudaSetDevice(h->cfg.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+    cudaFree(h->acc); cudaFree(h->currents); cudaFree(h->v); cudaFree(h->r); cudaFree(h->spikes);
+    cudaFree(h->scalars); cudaFree(h->tile_counter);
+    if (h->h_scalars) cudaFreeHost(h->h_scalars);
+    cudaFree(h->table.spikes); cudaFree(h->table.v); cudaFree(h->table.r);
+    cudaFree(h->topn.hist); cudaFree(h->topn.ctrl); cudaFree(h->topn.block_counts);
+    cudaFree(h->topn.out_idx); cudaFree(h->topn.out_spikes);
+    if (h->h_top) cudaFreeHost(h->h_top);
+    free_devbuf(h->buf[0]); free_devbuf(h->buf[1]); free_devbuf(h->staged);
+    cudaFree(h->d_offsets); cudaFree(h->staged_offsets);
+    for (cudaEvent_t e : h->evpool) cudaEventDestroy(e);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    delete h;
+    return NK_OK;
+}
+
+int nk_set_steps(nk_counter* h, uint64_t steps) {
+    if (!h) return fail(NK_ERR_BAD_ARG, "null handle");
+    h->cfg.steps = steps;
+    return NK_OK;
+}
+int nk_get_steps(const nk_counter* h, uint64_t* steps) {
+    if (!h || !steps) return fail(NK_ERR_BAD_ARG, "null argument");
+    *steps = h->cfg.steps;
+    return NK_OK;
+}
+
+int nk_process_batch(nk_counter* h, const uint8_t* bases, const uint64_t* offsets, uint64_t nseq) {
+    NK_TRY(validate_batch(h, bases, offsets, nseq));
+    if (h->streaming) return fail(NK_ERR_STATE, "nk_process_batch inside nk_stream_begin/end");
+    NK_CUDA(cudaSetDevice(h->cfg.device));
+    begin_call(h);
+    PhaseEvents pe;
+    NK_TRY(get_event(h, &pe.begin));
+    NK_CUDA(cudaEventRecord(pe.begin, h->stream));
+    NK_CUDA(cudaMemsetAsync(h->scalars + 2, 0, sizeof(unsigned long long), h->stream));
+    h->currents_valid_overwrite = true;  // totals of THIS call overwrite the stored currents (:174-176)
+    NK_TRY(count_host_batch(h, bases, offsets, nseq, &pe));
+    NK_TRY(fold_and_simulate(h, /*skip_zero=*/true, pe));
+    NK_TRY(get_event(h, &pe.end));
+    NK_CUDA(cudaEventRecord(pe.end, h->stream));
+    NK_TRY(finish_call(h, true));
+    collect_timings(h, pe);
+    return NK_OK;
+}
+
+int nk_stream_begin(nk_counter* h) {
+    if (!h) return fail(NK_ERR_BAD_ARG, "null handle");
+    if (h->streaming) return fail(NK_ERR_STATE, "nk_stream_begin called twice");
+    NK_CUDA(cudaSetDevice(h->cfg.device));
+    begin_call(h);
+    h->streaming = true;
+    h->currents_valid_overwrite = true;
+    NK_CUDA(cudaMemsetAsync(h->scalars + 2, 0, sizeof(unsigned long long), h->stream));
+    return NK_OK;
+}
+
+int nk_stream_push(nk_counter* h, const uint8_t* bases, const uint64_t* offsets, uint64_t nseq) {
+    NK_TRY(validate_batch(h, bases, offsets, nseq));
+    if (!h->streaming) return fail(NK_ERR_STATE, "nk_stream_push without nk_stream_begin");
+    NK_CUDA(cudaSetDevice(h->cfg.device));
+    return count_host_batch(h, bases, offsets, nseq, nullptr);
+}
+
+int nk_stream_accumulated(nk_counter* h, void** dev_currents) {
+    if (!h) return fail(NK_ERR_BAD_ARG, "null handle");
+    if (!h->streaming) return fail(NK_ERR_STATE, "nk_stream_accumulated without nk_stream_begin");
+    NK_CUDA(cudaSetDevice(h->cfg.device));
+    if (!h->acc_dirty && h->currents_valid_overwrite) {
+        NK_CUDA(cudaMemsetAsync(h->currents, 0, h->cfg.pool_size * sizeof(unsigned long long), h->stream));
+        h->currents_valid_overwrite = false;
+    }
+    NK_TRY(fold_now(h));
+    NK_CUDA(cudaStreamSynchronize(h->stream));
+    if (dev_currents) *dev_currents = h->currents;
+    return NK_OK;
+}
+
+int nk_stream_finish(nk_counter* h) {
+    if (!h) return fail(NK_ERR_BAD_ARG, "null handle");
+    if (!h->streaming) return fail(NK_ERR_STATE, "nk_stream_finish without nk_stream_begin");
+    NK_CUDA(cudaSetDevice(h->cfg.device));
+    PhaseEvents pe;
+    NK_TRY(fold_and_simulate(h, /*skip_zero=*/false, pe));
+    NK_TRY(finish_call(h, true));
+    h->last.fold_ms = ev_ms(pe.fold0, pe.fold1);
+    h->last.lif_ms = ev_ms(pe.fold1, pe.lif1);
+    h->streaming = false;
+    return NK_OK;
+}
+
+int nk_stream_end(nk_counter* h) { return nk_stream_finish(h); }
+
+int nk_simulate(nk_counter* h) {
+    if (!h) return fail(NK_ERR_BAD_ARG, "null handle");
+    if (h->streaming) return fail(NK_ERR_STATE, "nk_simulate inside nk_stream_begin/end");
+    NK_CUDA(cudaSetDevice(h->cfg.device));
+    begin_call(h);
+    cudaEvent_t a, b;
+    NK_TRY(get_event(h, &a));
+    NK_TRY(get_event(h, &b));
+    NK_CUDA(cudaEventRecord(a, h->stream));
+    NK_TRY(simulate(h, /*skip_zero=*/false));
+    NK_CUDA(cudaEventRecord(b, h->stream));
+    NK_TRY(finish_call(h, true));
+    h->last.lif_ms = ev_ms(a, b);
+    h->last.total_ms = h->last.lif_ms;
+    return NK_OK;
+}
+
+int nk_process_sequence(nk_counter* h, const uint8_t* seq, uint64_t len) {
+    if (!h) return fail(NK_ERR_BAD_ARG, "null handle");
+    if (len > 0 && !seq) return fail(NK_ERR_BAD_ARG, "null seq");
+    if (h->streaming) return fail(NK_ERR_STATE, "nk_process_sequence inside nk_stream_begin/end");
+    NK_CUDA(cudaSetDevice(h->cfg.device));
+    begin_call(h);
+    if (len < h->cfg.k) return NK_OK;  // src/spiking_hash.rs:206-208
+    // process_sequence ADDS to neuron_currents (fetch_add, :225,241,258) and zeroes them afterwards
+    const uint64_t offs[2] = {0, len};
+    NK_CUDA(cudaMemsetAsync(h->scalars + 2, 0, sizeof(unsigned long long), h->stream));
+    h->currents_valid_overwrite = false;
+    NK_TRY(count_host_batch(h, seq, offs, 1, nullptr));
+    NK_TRY(fold_now(h));
+    nk::LifParams p{};
+    p.currents = h->currents; p.v = h->v; p.r = h->r; p.spikes = h->spikes;
+    p.total_new = h->scalars + 0; p.max_spikes = h->scalars + 1;
+    p.pool = h->cfg.pool_size; p.steps = 1; p.thr = h->cfg.threshold; p.leak = h->cfg.leak;
+    p.period = h->cfg.refractory; p.skip_zero = 1;
+    NK_CUDA(cudaMemsetAsync(h->scalars, 0, sizeof(unsigned long long), h->stream));
+    NK_CUDA(nk::launch_lif_single_tick(p, h->currents, h->stream));
+    ++h->last.launches;
+    h->fresh = false;
+    return finish_call(h, true);
+}
+
+int nk_top_n(nk_counter* h, uint64_t top_n, nk_top_entry* out, uint64_t* n_out) {
+    if (!h || !n_out) return fail(NK_ERR_BAD_ARG, "null argument");
+    NK_CUDA(cudaSetDevice(h->cfg.device));
+    uint64_t n = std::min<uint64_t>(top_n, h->cfg.pool_size);
+    *n_out = 0;
+    if (n == 0) return NK_OK;
+    if (!out) return fail(NK_ERR_BAD_ARG, "null out");
+    if (n > nk::TOPN_MAX_N) return fail(NK_ERR_UNSUPPORTED, "top_n > %llu not supported", nk::TOPN_MAX_N);
+    unsigned long long cap = 1;
+    while (cap < n) cap <<= 1;
+    if (cap > h->topn_cap) {
+        cudaFree(h->topn.out_idx); cudaFree(h->topn.out_spikes);
+        if (h->h_top) cudaFreeHost(h->h_top);
+        h->topn.out_idx = h->topn.out_spikes = nullptr; h->h_top = nullptr; h->topn_cap = 0;
+        NK_CUDA(cudaMalloc(&h->topn.out_idx, cap * sizeof(unsigned long long)));
+        NK_CUDA(cudaMalloc(&h->topn.out_spikes, cap * sizeof(unsigned long long)));
+        NK_CUDA(cudaMallocHost(&h->h_top, 2 * cap * sizeof(unsigned long long)));
+        h->topn_cap = cap;
+    }
+    // max cumulative spike count bounds the radix passes
+    NK_CUDA(cudaMemcpyAsync(h->h_scalars, h->scalars, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    NK_CUDA(cudaStreamSynchronize(h->stream));
+    h->ev_used = 0;
+    cudaEvent_t a, b;
+    NK_TRY(get_event(h, &a));
+    NK_TRY(get_event(h, &b));
+    NK_CUDA(cudaEventRecord(a, h->stream));
+    uint64_t launches = 0;
+    NK_CUDA(nk::launch_topn(h->spikes, h->cfg.pool_size, n, h->h_scalars[1], h->topn, h->stream, &launches));
+    NK_CUDA(cudaEventRecord(b, h->stream));
+    unsigned long long* hi = reinterpret_cast<unsigned long long*>(h->h_top);
+    unsigned long long* hs = hi + h->topn_cap;
+    NK_CUDA(cudaMemcpyAsync(hi, h->topn.out_idx, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    NK_CUDA(cudaMemcpyAsync(hs, h->topn.out_spikes, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    NK_CUDA(cudaStreamSynchronize(h->stream));
+    for (uint64_t i = 0; i < n; ++i) {
+        out[i].idx = hi[i];
+        out[i].spikes = hs[i];
+        out[i].uniques = NK_UNIQUES_NOT_COMPUTED;
+        out[i]._pad = 0;
+    }
+    *n_out = n;
+    h->last.topn_ms = ev_ms(a, b);
+    h->last.topn_launches = launches;
+    return NK_OK;
+}
+
+int nk_total_spikes(const nk_counter* h, uint64_t* out) {
+    if (!h || !out) return fail(NK_ERR_BAD_ARG, "null argument");
+    *out = h->total_spikes;
+    return NK_OK;
+}
+int nk_energy_used(const nk_counter* h, double* out) {
+    if (!h || !out) return fail(NK_ERR_BAD_ARG, "null argument");
+    *out = (double)h->energy_fixed / 1000.0;  // src/models.rs:170-172
+    return NK_OK;
+}
+int nk_get_count(nk_counter* h, uint64_t, uint32_t*, int32_t*) {
+    if (!h) return fail(NK_ERR_BAD_ARG, "null handle");
+    return fail(NK_ERR_UNSUPPORTED, "exact k-mer side table (get_count) is not built yet (SURVEY §8 f1)");
+}
+
+int nk_debug_kmers(nk_counter* h, const uint8_t* seq, uint64_t len, uint64_t* fwd, uint64_t* rc, uint64_t* words,
+                   uint64_t* idx, uint64_t* n_out) {
+    if (!h || !n_out) return fail(NK_ERR_BAD_ARG, "null argument");
+    NK_CUDA(cudaSetDevice(h->cfg.device));
+    *n_out = 0;
+    if (len < h->cfg.k) return NK_OK;
+    if (!seq) return fail(NK_ERR_BAD_ARG, "null seq");
+    const uint64_t n = len - h->cfg.k + 1;
+    NK_CUDA(cudaStreamSynchronize(h->stream));
+    NK_TRY(ensure_devbuf(h->staged, len));
+    NK_TRY(ensure_offsets(&h->staged_offsets, &h->staged_offsets_cap, 2));
+    const uint64_t offs[2] = {0, len};
+    unsigned long long* d_out = nullptr;
+    NK_CUDA(cudaMalloc(&d_out, 4 * n * sizeof(unsigned long long)));
+    int rc_ = NK_OK;
+    do {
+#define NK_D(expr) { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { rc_ = fail(NK_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); break; } }
+        NK_D(cudaMemcpyAsync(h->staged.bases, seq, len, cudaMemcpyHostToDevice, h->stream));
+        NK_D(cudaMemcpyAsync(h->staged_offsets, offs, sizeof offs, cudaMemcpyHostToDevice, h->stream));
+        NK_D(cudaStreamSynchronize(h->stream));  // offs is on this stack frame
+        NK_D(cudaMemsetAsync(h->tile_counter, 0, sizeof(unsigned int), h->stream));
+        NK_D(nk::launch_mark_invalid(h->staged.invalid, h->staged_offsets, 0, 1, 0, len, h->cfg.k, h->scalars + 3,
+                                     h->stream, nullptr));
+        nk::CountParams p{};
+        p.bases = h->staged.bases; p.invalid = h->staged.invalid; p.acc = h->acc; p.tile_counter = h->tile_counter;
+        p.ntiles = nk::count_ntiles(len); p.fm = h->fm; p.k = h->cfg.k;
+        p.out_fwd = fwd ? d_out : nullptr;
+        p.out_rc = rc ? d_out + n : nullptr;
+        p.out_word = words ? d_out + 2 * n : nullptr;
+        p.out_idx = idx ? d_out + 3 * n : nullptr;
+        NK_D(nk::launch_count(p, h->cfg.use_canonical != 0, true, (int)std::min<unsigned long long>(p.ntiles, h->grid), h->stream));
+        if (fwd) NK_D(cudaMemcpyAsync(fwd, d_out, n * 8, cudaMemcpyDeviceToHost, h->stream));
+        if (rc) NK_D(cudaMemcpyAsync(rc, d_out + n, n * 8, cudaMemcpyDeviceToHost, h->stream));
+        if (words) NK_D(cudaMemcpyAsync(words, d_out + 2 * n, n * 8, cudaMemcpyDeviceToHost, h->stream));
+        if (idx) NK_D(cudaMemcpyAsync(idx, d_out + 3 * n, n * 8, cudaMemcpyDeviceToHost, h->stream));
+        NK_D(cudaStreamSynchronize(h->stream));
+#undef NK_D
+    } while (0);
+    cudaFree(d_out);
+    if (rc_ == NK_OK) *n_out = n;
+    return rc_;
+}
+
+int nk_debug_hash(nk_counter* h, const uint64_t* words, uint64_t n, uint64_t* hashes, uint64_t* idx) {
+    if (!h) return fail(NK_ERR_BAD_ARG, "null handle");
+    if (n == 0) return NK_OK;
+    if (!words) return fail(NK_ERR_BAD_ARG, "null words");
+    NK_CUDA(cudaSetDevice(h->cfg.device));
+    unsigned long long* d = nullptr;
+    NK_CUDA(cudaMalloc(&d, 3 * n * sizeof(unsigned long long)));
+    int rc_ = NK_OK;
+    do {
+#define NK_D(expr) { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { rc_ = fail(NK_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); break; } }
+        NK_D(cudaMemcpyAsync(d, words, n * 8, cudaMemcpyHostToDevice, h->stream));
+        NK_D(nk::launch_hash_words(d, n, h->fm, d + n, d + 2 * n, h->stream));
+        if (hashes) NK_D(cudaMemcpyAsync(hashes, d + n, n * 8, cudaMemcpyDeviceToHost, h->stream));
+        if (idx) NK_D(cudaMemcpyAsync(idx, d + 2 * n, n * 8, cudaMemcpyDeviceToHost, h->stream));
+        NK_D(cudaStreamSynchronize(h->stream));
+#undef NK_D
+    } while (0);
+    cudaFree(d);
+    return rc_;
+}
+
+static int copy_out(nk_counter* h, void* dst, const void* src, size_t bytes) {
+    if (!h || !dst) return fail(NK_ERR_BAD_ARG, "null argument");
+    NK_CUDA(cudaSetDevice(h->cfg.device));
+    NK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
+    NK_CUDA(cudaStreamSynchronize(h->stream));
+    return NK_OK;
+}
+int nk_copy_currents(nk_counter* h, uint64_t* out) { return copy_out(h, out, h ? h->currents : nullptr, h ? h->cfg.pool_size * 8 : 0); }
+int nk_copy_spike_counts(nk_counter* h, uint64_t* out) { return copy_out(h, out, h ? h->spikes : nullptr, h ? h->cfg.pool_size * 8 : 0); }
+int nk_copy_voltages(nk_counter* h, float* out) { return copy_out(h, out, h ? h->v : nullptr, h ? h->cfg.pool_size * 4 : 0); }
+int nk_copy_refractory(nk_counter* h, uint32_t* out) { return copy_out(h, out, h ? h->r : nullptr, h ? h->cfg.pool_size * 4 : 0); }
+
+int nk_last_timings(const nk_counter* h, nk_timings* out) {
+    if (!h || !out) return fail(NK_ERR_BAD_ARG, "null argument");
+    *out = h->last;
+    return NK_OK;
+}
+
+int nk_debug_set_lif_path(nk_counter* h, int mode) {
+    if (!h) return fail(NK_ERR_BAD_ARG, "null handle");
+    if (mode != 0 && mode != 1) return fail(NK_ERR_BAD_ARG, "mode must be 0 or 1");
+    h->force_direct = mode;
+    return NK_OK;
+}
+
+int nk_stage_reserve(nk_counter* h, uint64_t nbytes, uint64_t nseq, void** dev_bases, void** dev_offsets) {
+    if (!h) return fail(NK_ERR_BAD_ARG, "null handle");
+    NK_CUDA(cudaSetDevice(h->cfg.device));
+    NK_CUDA(cudaStreamSynchronize(h->stream));
+    NK_TRY(ensure_devbuf(h->staged, nbytes));
+    NK_TRY(ensure_offsets(&h->staged_offsets, &h->staged_offsets_cap, nseq + 1));
+    if (dev_bases) *dev_bases = h->staged.bases;
+    if (dev_offsets) *dev_offsets = h->staged_offsets;
+    return NK_OK;
+}
+
+int nk_process_staged(nk_counter* h, uint64_t nbytes, uint64_t nseq, int mode) {
+    if (!h) return fail(NK_ERR_BAD_ARG, "null handle");
+    if (mode != 0 && mode != 1) return fail(NK_ERR_BAD_ARG, "mode must be 0 or 1");
+    if (mode == 1 && !h->streaming) return fail(NK_ERR_STATE, "mode 1 needs nk_stream_begin");
+    if (mode == 0 && h->streaming) return fail(NK_ERR_STATE, "mode 0 inside nk_stream_begin/end");
+    if (nk::count_padded_bases(nbytes) > h->staged.bases_cap || nseq + 1 > h->staged_offsets_cap)
+        return fail(NK_ERR_STATE, "staged batch larger than the last nk_stage_reserve");
+    NK_CUDA(cudaSetDevice(h->cfg.device));
+    PhaseEvents pe;
+    if (mode == 0) {
+        begin_call(h);
+        NK_TRY(get_event(h, &pe.begin));
+        NK_CUDA(cudaEventRecord(pe.begin, h->stream));
+        NK_CUDA(cudaMemsetAsync(h->scalars + 2, 0, sizeof(unsigned long long), h->stream));
+        h->currents_valid_overwrite = true;
+    }
+    // one launch over the whole device-resident batch, in slices of < 2^32 window starts
+    const unsigned long long slice = 0xFFFFFFFFull / nk::COUNT_TILE * nk::COUNT_TILE;
+    if (nbytes > slice)
+        return fail(NK_ERR_UNSUPPORTED, "staged batches of more than %llu bytes must be split by the caller", slice);
+    if (nseq > 0 && nbytes > 0)
+        NK_TRY(count_chunk(h, h->staged, h->staged_offsets, 0, nseq, 0, nbytes, nbytes, mode == 0 ? &pe : &pe));
+    if (mode == 0) {
+        NK_TRY(fold_and_simulate(h, /*skip_zero=*/true, pe));
+        NK_TRY(get_event(h, &pe.end));
+        NK_CUDA(cudaEventRecord(pe.end, h->stream));
+        NK_TRY(finish_call(h, true));
+        collect_timings(h, pe);
+    } else {
+        // accumulate the phase times of the pushes of this stream
+        NK_CUDA(cudaStreamSynchronize(h->stream));
+        for (size_t i = 0; i < pe.mark0.size(); ++i) {
+            h->last.mark_ms += ev_ms(pe.mark0[i], pe.count0[i]);
+            h->last.count_ms += ev_ms(pe.count0[i], pe.count1[i]);
+        }
+        h->ev_used = 0;
+    }
+    return NK_OK;
+}
+
+int nk_cuda_stream(nk_counter* h, void** stream) {
+    if (!h || !stream) return fail(NK_ERR_BAD_ARG, "null argument");
+    *stream = (void*)h->stream;
+    return NK_OK;
+}
+int nk_synchronize(nk_counter* h) {
+    if (!h) return fail(NK_ERR_BAD_ARG, "null handle");
+    NK_CUDA(cudaSetDevice(h->cfg.device));
+    NK_CUDA(cudaStreamSynchronize(h->copy_stream));
+    NK_CUDA(cudaStreamSynchronize(h->stream));
+    return NK_OK;
+}
+
+int nk_synth_fill(nk_counter* h, void* dev_out, uint64_t seed, uint64_t start, uint64_t n, uint32_t flags) {
+    if (!h || (!dev_out && n)) return fail(NK_ERR_BAD_ARG, "null argument");
+    NK_CUDA(cudaSetDevice(h->cfg.device));
+    NK_CUDA(nk::launch_synth((unsigned char*)dev_out, seed, start, n, flags, h->stream));
+    return NK_OK;
+}
+
+int nk_host_alloc(void** ptr, uint64_t nbytes) {
+    if (!ptr) return fail(NK_ERR_BAD_ARG, "null ptr");
+    *ptr = nullptr;
+    cudaError_t e = cudaMallocHost(ptr, nbytes ? nbytes : 1);
+    if (e != cudaSuccess) return fail(NK_ERR_OOM, "cudaMallocHost(%llu): %s", (unsigned long long)nbytes, cudaGetErrorString(e));
+    return NK_OK;
+}
+int nk_host_free(void* ptr) {
+    if (ptr) NK_CUDA(cudaFreeHost(ptr));
+    return NK_OK;
+}
+
+uint64_t nk_pack_kmer(const uint8_t* kmer, uint64_t len) { return nk::host_pack_kmer(kmer, len); }
+
+int nk_process_file(nk_counter* h, const char* path, int streaming) {
+    if (!h || !path) return fail(NK_ERR_BAD_ARG, "null argument");
+    if (h->streaming) return fail(NK_ERR_STATE, "nk_process_file inside nk_stream_begin/end");
+    std::string err;
+    int rc = nk::process_file(h, path, streaming != 0, &err);
+    if (rc != NK_OK) return fail(rc, "%s", err.c_str());
+    return NK_OK;
+}
+
+}  // extern "C"

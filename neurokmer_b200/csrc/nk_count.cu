@@ -1,0 +1,315 @@
+// nk_count.cu — fused windowing → SipHash-1-3 → % pool → pool update (sm_100a).
+//
+// Replaces the reference's per-base hot loop:
+//   RollingKmerHash::init/slide + canonical   src/models.rs:206-286
+//   pack_kmer (non-canonical)                 src/utils.rs:26-39
+//   map_kmer_to_neuron                        src/spiking_hash.rs:78-82
+//   currents[idx] += 1                        src/spiking_hash.rs:112,126,136,332,342,349
+//
+// Data flow per CTA (persistent, dynamic tile scheduler):
+//   HBM --cp.async.bulk (TMA 1-D, mbarrier)--> smem stage {tile bytes + halo, invalid-start bits}
+//   warp: 512-position chunks; lane L converts its 16 ASCII bytes into a forward
+//   word F (MSB-first 2-bit codes) and a complement word R (LSB-first), pulls the
+//   words of lanes L+1, L+2 by shuffle (k-1 overlap; the last two lanes read the
+//   next chunk's first words), and then every one of its 16 window starts is two
+//   funnel-shift extractions: fwd(j) = bits of F-stream, rc(j) = bits of R-stream.
+//   A k-mer is a pure function of its own k bytes (the reference has no N-break
+//   state: non-ACGT -> code 0 on BOTH strands), so there is no serial dependency.
+//   min(fwd, rc) -> SipHash-1-3 -> exact mod -> RED.ADD.U32 into the L2-resident pool.
+#include "nk_kernels.cuh"
+
+namespace nk {
+
+namespace {
+
+constexpr int kBytesPerStage = COUNT_TILE + COUNT_HALO;    // multiple of 16
+constexpr int kBitsPerStage = COUNT_TILE / 8;              // multiple of 16
+constexpr int kStageStride = ((kBytesPerStage + kBitsPerStage + 127) / 128) * 128;
+constexpr int kSmemTotal = COUNT_STAGES * kStageStride;
+
+static_assert(kBytesPerStage % 16 == 0 && kBitsPerStage % 16 == 0, "TMA bulk copies are 16-byte granular");
+static_assert(COUNT_SPAN * (COUNT_WARPS - 1) + COUNT_SPAN + COUNT_CHUNK <= kStageStride,
+              "the look-ahead load of the last chunk must stay inside the stage");
+
+struct WindowConsts {
+    unsigned wide;     // k <= 16: the forward window lives in (F0:F1) only
+    unsigned sh;       // (64 - 2k) & 31
+    unsigned mask_lo;  // low / high 32 bits of 2^(2k)-1
+    unsigned mask_hi;
+    unsigned k;
+};
+
+__device__ __forceinline__ WindowConsts make_window_consts(unsigned k) {
+    WindowConsts c;
+    const unsigned s0 = 64u - 2u * k;
+    c.wide = s0 >= 32u;
+    c.sh = s0 & 31u;
+    c.mask_lo = k >= 16u ? 0xFFFFFFFFu : ((1u << (2u * k)) - 1u);
+    c.mask_hi = k <= 16u ? 0u : (k == 32u ? 0xFFFFFFFFu : ((1u << (2u * k - 32u)) - 1u));
+    c.k = k;
+    return c;
+}
+
+__device__ __forceinline__ void issue_tile(unsigned char* stage, unsigned long long* bar,
+                                           const CountParams& p, unsigned long long tile) {
+    mbar_expect_tx(bar, kBytesPerStage + kBitsPerStage);
+    tma_load_1d(stage, p.bases + tile * COUNT_TILE, kBytesPerStage, bar);
+    tma_load_1d(stage + kBytesPerStage, (const unsigned char*)p.invalid + tile * kBitsPerStage,
+                kBitsPerStage, bar);
+}
+
+// word of lane (lane + d) of the 64-word sequence {cur[0..31], nxt[0..31]}
+__device__ __forceinline__ unsigned neighbour(unsigned cur, unsigned nxt, unsigned lane, unsigned d) {
+    return __shfl_sync(0xFFFFFFFFu, lane >= d ? cur : nxt, (lane + d) & 31u);
+}
+
+// pack_kmer over a window that contains non-ACGT bytes: they are skipped (src/utils.rs:35)
+__device__ __noinline__ unsigned long long pack_skip(unsigned F0, unsigned F1, unsigned F2, unsigned V0,
+                                                     unsigned V1, unsigned V2, unsigned j, unsigned k) {
+    unsigned long long word = 0;
+    for (unsigned i = 0; i < k; ++i) {
+        const unsigned b = j + i, w = b >> 4, sh = 30u - 2u * (b & 15u);
+        const unsigned f = w == 0 ? F0 : (w == 1 ? F1 : F2);
+        const unsigned v = w == 0 ? V0 : (w == 1 ? V1 : V2);
+        if ((v >> sh) & 1u) word = (word << 2) | ((f >> sh) & 3u);
+    }
+    return word;
+}
+
+template <bool CANON, bool EMIT, bool POW2>
+__device__ __forceinline__ void process_chunk(const CountParams& p, const WindowConsts& wc, const Codes16& cur,
+                                              const Codes16& nxt, unsigned inv16, unsigned lane,
+                                              unsigned long long pos0) {
+    const unsigned F0 = cur.F;
+    const unsigned F1 = neighbour(cur.F, nxt.F, lane, 1);
+    const unsigned F2 = neighbour(cur.F, nxt.F, lane, 2);
+    // forward stream B = F0:F1:F2 (base b in bits [94-2b, 96-2b)); G = B >> (64-2k), so that
+    // window j is (G >> (32-2j)) & mask.
+    const unsigned t0 = wc.wide ? 0u : F0, t1 = wc.wide ? F0 : F1, t2 = wc.wide ? F1 : F2;
+    const unsigned G0 = t0 >> wc.sh;
+    const unsigned G1 = __funnelshift_r(t1, t0, wc.sh);
+    const unsigned G2 = __funnelshift_r(t2, t1, wc.sh);
+
+    unsigned R0 = 0, R1 = 0, R2 = 0, H0 = 0, H1 = 0, H2 = 0, V0 = 0, V1 = 0, V2 = 0;
+    if (CANON) {
+        // complement stream L = R2:R1:R0 (base b in bits [2b, 2b+2)); window j is (L >> 2j) & mask
+        R0 = cur.R;
+        R1 = neighbour(cur.R, nxt.R, lane, 1);
+        R2 = neighbour(cur.R, nxt.R, lane, 2);
+    } else {
+        V0 = cur.V;
+        V1 = neighbour(cur.V, nxt.V, lane, 1);
+        V2 = neighbour(cur.V, nxt.V, lane, 2);
+        const unsigned u0 = wc.wide ? 0u : V0, u1 = wc.wide ? V0 : V1, u2 = wc.wide ? V1 : V2;
+        H0 = u0 >> wc.sh;
+        H1 = __funnelshift_r(u1, u0, wc.sh);
+        H2 = __funnelshift_r(u2, u1, wc.sh);
+    }
+
+#pragma unroll 4
+    for (unsigned j = 0; j < 16; ++j) {
+        const unsigned sr = 32u - 2u * j;
+        const unsigned flo = __funnelshift_rc(G2, G1, sr) & wc.mask_lo;
+        const unsigned fhi = __funnelshift_rc(G1, G0, sr) & wc.mask_hi;
+        const unsigned long long fwd = ((unsigned long long)fhi << 32) | flo;
+        unsigned long long rc = 0, word;
+        if (CANON) {
+            const unsigned rlo = __funnelshift_r(R0, R1, 2u * j) & wc.mask_lo;
+            const unsigned rhi = __funnelshift_r(R1, R2, 2u * j) & wc.mask_hi;
+            rc = ((unsigned long long)rhi << 32) | rlo;
+            word = fwd < rc ? fwd : rc;  // src/models.rs:284-286
+        } else {
+            const unsigned vlo = __funnelshift_rc(H2, H1, sr) & wc.mask_lo;
+            const unsigned vhi = __funnelshift_rc(H1, H0, sr) & wc.mask_hi;
+            word = fwd;  // all k bytes are ACGT: pack_kmer == forward word
+            if (vlo != wc.mask_lo || vhi != wc.mask_hi) word = pack_skip(F0, F1, F2, V0, V1, V2, j, wc.k);
+        }
+        const unsigned bad = (inv16 >> j) & 1u;
+        const U64 h = siphash13_dev((unsigned)word, (unsigned)(word >> 32));
+        const unsigned idx = fastmod_dev<POW2>(h, p.fm);
+        if (EMIT) {
+            if (!bad) {
+                const unsigned long long pos = pos0 + j;
+                if (p.out_fwd) p.out_fwd[pos] = fwd;
+                if (p.out_rc) p.out_rc[pos] = rc;
+                if (p.out_word) p.out_word[pos] = word;
+                if (p.out_idx) p.out_idx[pos] = idx;
+            }
+        } else {
+            // predicated RED.E.ADD (no divergence region around a single instruction)
+            asm volatile(
+                "{\n\t.reg .pred q;\n\t"
+                "setp.eq.u32 q, %2, 0;\n\t"
+                "@q red.global.add.u32 [%0], %1;\n\t}" ::"l"(p.acc + idx),
+                "r"(1u), "r"(bad)
+                : "memory");
+        }
+    }
+}
+
+template <bool CANON, bool EMIT, bool POW2>
+__global__ void __launch_bounds__(COUNT_THREADS, 2) count_kernel(const __grid_constant__ CountParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) unsigned long long bars[COUNT_STAGES];
+    __shared__ unsigned long long tile_of[COUNT_STAGES];
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < COUNT_STAGES; ++s) mbar_init(&bars[s], 1);
+        mbar_fence_init();
+        unsigned long long t0 = atomicAdd(p.tile_counter, 1u);
+        tile_of[0] = t0;
+        if (t0 < p.ntiles) issue_tile(smem, &bars[0], p, t0);
+    }
+    __syncthreads();
+
+    const WindowConsts wc = make_window_consts(p.k);
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+
+    for (unsigned it = 0;; ++it) {
+        const unsigned s = it & 1u;
+        const unsigned long long tile = tile_of[s];
+        if (tile >= p.ntiles) break;
+        if (threadIdx.x == 0) {  // prefetch the next tile into the other stage (consumed at it-1)
+            unsigned long long tn = atomicAdd(p.tile_counter, 1u);
+            tile_of[s ^ 1u] = tn;
+            if (tn < p.ntiles) issue_tile(smem + (s ^ 1u) * kStageStride, &bars[s ^ 1u], p, tn);
+        }
+        mbar_wait(&bars[s], (it >> 1) & 1u);
+
+        const unsigned char* sb = smem + s * kStageStride;
+        const unsigned short* bits = reinterpret_cast<const unsigned short*>(sb + kBytesPerStage);
+        const unsigned span0 = warp * COUNT_SPAN;
+        const unsigned char* lp = sb + span0 + 16u * lane;
+        Codes16 cur = convert16<!CANON>(*reinterpret_cast<const uint4*>(lp));
+#pragma unroll 1
+        for (unsigned c = 0; c < COUNT_CHUNKS_PER_SPAN; ++c) {
+            const Codes16 nxt = convert16<!CANON>(*reinterpret_cast<const uint4*>(lp + (c + 1u) * COUNT_CHUNK));
+            const unsigned off = span0 + c * COUNT_CHUNK;
+            const unsigned inv16 = bits[(off >> 4) + lane];
+            process_chunk<CANON, EMIT, POW2>(p, wc, cur, nxt, inv16, lane,
+                                       tile * COUNT_TILE + off + 16u * lane);
+            cur = nxt;
+        }
+        __syncthreads();
+    }
+}
+
+// One thread per sequence in [seq_lo, seq_hi): starts max(start, end-k+1) .. end-1 are invalid.
+// Also counts the windows that start inside this chunk (the metric's unit) into *kmers.
+__global__ void mark_seq_ends_kernel(unsigned int* invalid, const unsigned long long* __restrict__ offsets,
+                                     unsigned long long seq_lo, unsigned long long seq_hi,
+                                     unsigned long long origin, unsigned long long nbytes, unsigned k,
+                                     unsigned long long* kmers) {
+    unsigned long long s = seq_lo + blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    unsigned long long mine = 0;
+    if (s < seq_hi) {
+        unsigned long long a = offsets[s], e = offsets[s + 1];
+        const unsigned long long cend = origin + nbytes;
+        if (e - a >= k) {  // windows start at a .. e-k
+            const unsigned long long w0 = a > origin ? a : origin;
+            const unsigned long long w1 = (e - k + 1) < cend ? (e - k + 1) : cend;
+            if (w1 > w0) mine = w1 - w0;
+        }
+        unsigned long long lo = (e - a >= (unsigned long long)(k - 1)) ? e - (k - 1) : a;
+        // clip to this chunk [origin, origin + nbytes)
+        if (lo < origin) lo = origin;
+        if (e > cend) e = cend;
+        if (lo < e) {
+            lo -= origin; e -= origin;
+            // at most 31 bits: spans at most two words
+            unsigned long long wlo = lo >> 5, whi = (e - 1) >> 5;
+            unsigned blo = (unsigned)(lo & 31), bhi = (unsigned)((e - 1) & 31);
+            if (wlo == whi) {
+                unsigned m = (bhi == 31 ? 0xFFFFFFFFu : ((1u << (bhi + 1)) - 1u)) & ~((1u << blo) - 1u);
+                atomicOr(invalid + wlo, m);
+            } else {
+                atomicOr(invalid + wlo, ~((1u << blo) - 1u));
+                atomicOr(invalid + whi, bhi == 31 ? 0xFFFFFFFFu : ((1u << (bhi + 1)) - 1u));
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_down_sync(0xFFFFFFFFu, mine, o);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(kmers, mine);
+}
+
+// Everything in [nbytes, nbits_total) is invalid (tile padding).
+__global__ void mark_tail_kernel(unsigned int* invalid, unsigned long long nbytes, unsigned long long nbits_total) {
+    unsigned long long w = (nbytes >> 5) + blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    unsigned long long wend = (nbits_total + 31) >> 5;
+    if (w >= wend) return;
+    unsigned m = 0xFFFFFFFFu;
+    if (w == (nbytes >> 5)) m = ~((1u << (nbytes & 31)) - 1u);
+    atomicOr(invalid + w, m);
+}
+
+}  // namespace
+
+size_t count_smem_bytes() { return (size_t)kSmemTotal; }
+
+template <bool CANON, bool EMIT, bool POW2>
+static cudaError_t launch_count_t(const CountParams& p, int grid, cudaStream_t s) {
+    cudaError_t e = cudaFuncSetAttribute(count_kernel<CANON, EMIT, POW2>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
+    if (e != cudaSuccess) return e;
+    count_kernel<CANON, EMIT, POW2><<<grid, COUNT_THREADS, kSmemTotal, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_count(const CountParams& p, bool canonical, bool emit, int grid, cudaStream_t s) {
+    const bool pow2 = p.fm.is_pow2 != 0;
+    if (canonical) {
+        if (emit) return pow2 ? launch_count_t<true, true, true>(p, grid, s) : launch_count_t<true, true, false>(p, grid, s);
+        return pow2 ? launch_count_t<true, false, true>(p, grid, s) : launch_count_t<true, false, false>(p, grid, s);
+    }
+    if (emit) return pow2 ? launch_count_t<false, true, true>(p, grid, s) : launch_count_t<false, true, false>(p, grid, s);
+    return pow2 ? launch_count_t<false, false, true>(p, grid, s) : launch_count_t<false, false, false>(p, grid, s);
+}
+
+template <bool CANON>
+static cudaError_t max_grid_t(int sms, int* grid) {
+    int per_sm = 0;
+    cudaError_t e = cudaFuncSetAttribute(count_kernel<CANON, false, false>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, count_kernel<CANON, false, false>, COUNT_THREADS,
+                                                      kSmemTotal);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    *grid = sms * per_sm;  // persistent: one wave, a multiple of the SM count (148 on B200)
+    return cudaSuccess;
+}
+
+cudaError_t count_max_grid(bool canonical, int device, int* grid) {
+    int sms = 0;
+    cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (e != cudaSuccess) return e;
+    return canonical ? max_grid_t<true>(sms, grid) : max_grid_t<false>(sms, grid);
+}
+
+cudaError_t launch_mark_invalid(unsigned int* invalid, const unsigned long long* offsets,
+                                unsigned long long seq_lo, unsigned long long seq_hi,
+                                unsigned long long origin, unsigned long long nbytes, unsigned k,
+                                unsigned long long* kmers, cudaStream_t s, uint64_t* launches) {
+    const unsigned long long words = count_bitmap_words(nbytes);
+    cudaError_t e = cudaMemsetAsync(invalid, 0, words * sizeof(unsigned int), s);
+    if (e != cudaSuccess) return e;
+    const unsigned long long nseq = seq_hi - seq_lo;
+    if (nseq > 0) {
+        const unsigned long long blocks = (nseq + 255) / 256;
+        mark_seq_ends_kernel<<<(unsigned)blocks, 256, 0, s>>>(invalid, offsets, seq_lo, seq_hi, origin, nbytes, k,
+                                                              kmers);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        if (launches) ++*launches;
+    }
+    const unsigned long long nbits_total = count_ntiles(nbytes) * COUNT_TILE;
+    if (nbits_total > nbytes) {
+        const unsigned long long nwords = ((nbits_total + 31) >> 5) - (nbytes >> 5);
+        mark_tail_kernel<<<(unsigned)((nwords + 255) / 256), 256, 0, s>>>(invalid, nbytes, nbits_total);
+        e = cudaGetLastError();
+        if (launches) ++*launches;
+    }
+    return e;
+}
+
+}  // namespace nk

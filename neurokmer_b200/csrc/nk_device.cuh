@@ -1,0 +1,292 @@
+// nk_device.cuh — device-side building blocks shared by the sm_100a kernels.
+//
+// Semantics follow the reference (paths relative to the reference checkout):
+//   2-bit codes            src/models.rs:231-251
+//   fwd / revcomp words    src/models.rs:206-269 (closed form of init + slide)
+//   SipHash-1-3, keys 0,0  src/spiking_hash.rs:78-82 (siphasher 1.0.2)
+//   % pool_size            src/spiking_hash.rs:81
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace nk {
+
+// ---------------------------------------------------------------------------
+// ASCII -> 2-bit code streams, four bases per 32-bit word (SIMD within a register).
+//
+// For every byte b of `w`:
+//   fwd  = F(b): A,a->0 C,c->1 G,g->2 T,t->3, anything else -> 0   (models.rs:231-239)
+//   comp = C(b): A,a->3 C,c->2 G,g->1 T,t->0, anything else -> 0   (models.rs:243-251)
+//   vmask = 3 for ACGTacgt, 0 otherwise                            (utils.rs:26-39 skip rule)
+// Bits 2:1 of an ASCII letter give x = A0 C1 G3 T2 (case-insensitive); x ^ (x>>1) is
+// the forward code.  A byte is one of the eight letters iff, with bits 5,2,1 cleared,
+// it equals 0x41 (x != 2) or 0x50 (x == 2) — exact for all 256 byte values.
+// ---------------------------------------------------------------------------
+__host__ __device__ __forceinline__ void classify4(uint32_t w, uint32_t& fwd, uint32_t& comp, uint32_t& vmask) {
+    const uint32_t x = (w >> 1) & 0x03030303u;
+    const uint32_t s = x >> 1;
+    const uint32_t code = x ^ (s & 0x01010101u);
+    const uint32_t is2 = s & ~x & 0x01010101u;                  // 1 where x == 2 (candidate T)
+    const uint32_t expect = 0x41414141u + is2 * 0x0Fu;          // 0x41 or 0x50 per byte, no carries
+    const uint32_t diff = (w & 0xD9D9D9D9u) ^ expect;           // zero byte <=> valid letter
+    const uint32_t nz = (((diff & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | diff) & 0x80808080u;
+    const uint32_t inv3 = (nz >> 7) * 3u;                       // 0x03 per invalid byte
+    fwd = code & ~inv3;
+    comp = (code ^ 0x03030303u) & ~inv3;
+    vmask = inv3 ^ 0x03030303u;
+}
+
+// four 2-bit fields (one per byte) -> one byte, base 0 in the TOP two bits (MSB-first stream);
+// the byte is returned in bits 31:24.
+__host__ __device__ __forceinline__ uint32_t pack4_msb_top(uint32_t c) { return c * 0x40100401u; }
+// same, base 0 in the BOTTOM two bits (LSB-first stream); byte in bits 31:24.
+__host__ __device__ __forceinline__ uint32_t pack4_lsb_top(uint32_t c) { return c * 0x01041040u; }
+
+#ifdef __CUDACC__
+struct Codes16 {
+    uint32_t F;  // forward codes of 16 bases, base 0 in bits 31:30
+    uint32_t R;  // complement codes of 16 bases, base 0 in bits 1:0
+    uint32_t V;  // validity (0b11 per ACGT base), laid out like F   (only when WANT_V)
+};
+
+template <bool WANT_V>
+__device__ __forceinline__ Codes16 convert16(uint4 q) {
+    uint32_t f0, f1, f2, f3, c0, c1, c2, c3, v0, v1, v2, v3;
+    classify4(q.x, f0, c0, v0);
+    classify4(q.y, f1, c1, v1);
+    classify4(q.z, f2, c2, v2);
+    classify4(q.w, f3, c3, v3);
+    Codes16 o;
+    o.F = __byte_perm(__byte_perm(pack4_msb_top(f3), pack4_msb_top(f2), 0x0073),
+                      __byte_perm(pack4_msb_top(f1), pack4_msb_top(f0), 0x0073), 0x5410);
+    o.R = __byte_perm(__byte_perm(pack4_lsb_top(c0), pack4_lsb_top(c1), 0x0073),
+                      __byte_perm(pack4_lsb_top(c2), pack4_lsb_top(c3), 0x0073), 0x5410);
+    if (WANT_V)
+        o.V = __byte_perm(__byte_perm(pack4_msb_top(v3), pack4_msb_top(v2), 0x0073),
+                          __byte_perm(pack4_msb_top(v1), pack4_msb_top(v0), 0x0073), 0x5410);
+    else
+        o.V = 0;
+    return o;
+}
+#endif
+
+// ---------------------------------------------------------------------------
+// SipHash-1-3 of one 8-byte little-endian block, k0 = k1 = 0.
+// Bit-for-bit the published algorithm; two algebraic shortcuts that do not
+// change the result:
+//  * keys are zero and the message is one block, so the first half of the
+//    first round only touches constants (nvcc folds it);
+//  * in the last finalisation round v0's last update cancels in
+//    v0^v1^v2^v3 (v3 = rotl(v3,21) ^ v0), so it is never computed.
+// ---------------------------------------------------------------------------
+__host__ __device__ __forceinline__ unsigned long long rotl64(unsigned long long x, int b) {
+    return (x << b) | (x >> (64 - b));
+}
+
+#define NK_SIPROUND(v0, v1, v2, v3)                                   \
+    do {                                                              \
+        v0 += v1; v1 = rotl64(v1, 13); v1 ^= v0; v0 = rotl64(v0, 32); \
+        v2 += v3; v3 = rotl64(v3, 16); v3 ^= v2;                      \
+        v0 += v3; v3 = rotl64(v3, 21); v3 ^= v0;                      \
+        v2 += v1; v1 = rotl64(v1, 17); v1 ^= v2; v2 = rotl64(v2, 32); \
+    } while (0)
+
+__host__ __device__ __forceinline__ unsigned long long siphash13_u64(unsigned long long m) {
+    unsigned long long v0 = 0x736f6d6570736575ULL;
+    unsigned long long v1 = 0x646f72616e646f6dULL;
+    unsigned long long v2 = 0x6c7967656e657261ULL;
+    unsigned long long v3 = 0x7465646279746573ULL ^ m;
+    NK_SIPROUND(v0, v1, v2, v3);  // c-round on the message block
+    v0 ^= m;
+    const unsigned long long b = 8ULL << 56;  // length byte, no tail bytes
+    v3 ^= b;
+    NK_SIPROUND(v0, v1, v2, v3);  // c-round on the length block
+    v0 ^= b;
+    v2 ^= 0xff;
+    NK_SIPROUND(v0, v1, v2, v3);  // d-round 1
+    NK_SIPROUND(v0, v1, v2, v3);  // d-round 2
+    // d-round 3, trimmed
+    v0 += v1; v1 = rotl64(v1, 13); v1 ^= v0;
+    v2 += v3; v3 = rotl64(v3, 16); v3 ^= v2;
+    v2 += v1;
+    return rotl64(v3, 21) ^ rotl64(v1, 17) ^ v2 ^ rotl64(v2, 32);
+}
+
+// ---------------------------------------------------------------------------
+// Exact h % p for any u64 h and 1 <= p < 2^32.
+// Moeller & Granlund, "Improved division by invariant integers" (2011), Alg. 4
+// (2-by-1 division with a precomputed reciprocal of the normalised divisor),
+// applied twice to the 96-bit value h << shift.  Powers of two take one AND.
+// ---------------------------------------------------------------------------
+struct FastMod {
+    uint32_t dn;      // p << shift (top bit set)
+    uint32_t v;       // floor((2^64-1)/dn) - 2^32
+    uint32_t shift;   // clz(p)
+    uint32_t pow2m1;  // p-1 if p is a power of two, else 0 (p == 1 handled: pow2m1 == 0 && dn == 2^31)
+    uint32_t p;
+    uint32_t is_pow2;
+};
+
+__host__ __device__ __forceinline__ FastMod make_fastmod(unsigned long long p64) {
+    FastMod fm;
+    const uint32_t p = (uint32_t)p64;
+    uint32_t s = 0;
+    while (!((p << s) & 0x80000000u)) ++s;
+    fm.p = p;
+    fm.shift = s;
+    fm.dn = p << s;
+    fm.v = (uint32_t)(0xFFFFFFFFFFFFFFFFULL / fm.dn - 0x100000000ULL);
+    fm.is_pow2 = ((p & (p - 1)) == 0) ? 1u : 0u;
+    fm.pow2m1 = p - 1;
+    return fm;
+}
+
+// remainder of (u1:u0) / dn, requires u1 < dn, dn normalised
+__host__ __device__ __forceinline__ uint32_t rem_2by1(uint32_t u1, uint32_t u0, uint32_t dn, uint32_t v) {
+    const unsigned long long q = (unsigned long long)v * u1 + (((unsigned long long)u1 << 32) | u0);
+    const uint32_t q1 = (uint32_t)(q >> 32) + 1u;
+    const uint32_t q0 = (uint32_t)q;
+    uint32_t r = u0 - q1 * dn;
+    if (r > q0) r += dn;
+    if (r >= dn) r -= dn;
+    return r;
+}
+
+__host__ __device__ __forceinline__ uint32_t fastmod_u64(unsigned long long h, const FastMod& fm) {
+    const uint32_t lo = (uint32_t)h, hi = (uint32_t)(h >> 32);
+    if (fm.is_pow2) return lo & fm.pow2m1;
+    const uint32_t s = fm.shift;
+    // (u2:u1:u0) = h << s
+    const uint32_t u2 = s ? (hi >> (32 - s)) : 0u;
+    const uint32_t u1 = s ? ((hi << s) | (lo >> (32 - s))) : hi;
+    const uint32_t u0 = lo << s;
+    const uint32_t r1 = rem_2by1(u2, u1, fm.dn, fm.v);
+    const uint32_t r0 = rem_2by1(r1, u0, fm.dn, fm.v);
+    return r0 >> s;
+}
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------------------
+// Device form of the two functions above on explicit 32-bit halves, so that every
+// 64-bit rotate is two funnel shifts (SHF.L.W) and nothing else.  Same values as
+// siphash13_u64 / fastmod_u64 (tests/test_parity_gpu.py checks nk_debug_hash
+// against the oracle).
+// ---------------------------------------------------------------------------
+struct U64 {
+    uint32_t lo, hi;
+};
+__device__ __forceinline__ U64 add64(U64 a, U64 b) {
+    const unsigned long long s = (((unsigned long long)a.hi << 32) | a.lo) + (((unsigned long long)b.hi << 32) | b.lo);
+    return U64{(uint32_t)s, (uint32_t)(s >> 32)};
+}
+template <int B>
+__device__ __forceinline__ U64 rotl_xor(U64 x, U64 y) {  // rotl64(x, B) ^ y, 0 < B < 32
+    return U64{__funnelshift_l(x.hi, x.lo, B) ^ y.lo, __funnelshift_l(x.lo, x.hi, B) ^ y.hi};
+}
+__device__ __forceinline__ U64 swap32(U64 x) { return U64{x.hi, x.lo}; }  // rotl64(x, 32)
+
+#define NK_SIPROUND32(v0, v1, v2, v3)             \
+    do {                                          \
+        v0 = add64(v0, v1); v1 = rotl_xor<13>(v1, v0); v0 = swap32(v0); \
+        v2 = add64(v2, v3); v3 = rotl_xor<16>(v3, v2);                  \
+        v0 = add64(v0, v3); v3 = rotl_xor<21>(v3, v0);                  \
+        v2 = add64(v2, v1); v1 = rotl_xor<17>(v1, v2); v2 = swap32(v2); \
+    } while (0)
+
+__device__ __forceinline__ U64 siphash13_dev(uint32_t mlo, uint32_t mhi) {
+    U64 v0{0x70736575u, 0x736f6d65u};
+    U64 v1{0x6e646f6du, 0x646f7261u};
+    U64 v2{0x6e657261u, 0x6c796765u};
+    U64 v3{0x79746573u ^ mlo, 0x74656462u ^ mhi};
+    NK_SIPROUND32(v0, v1, v2, v3);
+    v0.lo ^= mlo; v0.hi ^= mhi;
+    v3.hi ^= 0x08000000u;  // length block 8 << 56
+    NK_SIPROUND32(v0, v1, v2, v3);
+    v0.hi ^= 0x08000000u;
+    v2.lo ^= 0xffu;
+    NK_SIPROUND32(v0, v1, v2, v3);
+    NK_SIPROUND32(v0, v1, v2, v3);
+    // last round: v0 ^ v3 collapses to rotl(v3, 21) (see siphash13_u64)
+    v0 = add64(v0, v1); v1 = rotl_xor<13>(v1, v0);
+    v2 = add64(v2, v3); v3 = rotl_xor<16>(v3, v2);
+    v2 = add64(v2, v1);
+    // rotl(v3,21) ^ rotl(v1,17) ^ v2 ^ rotl(v2,32)
+    const uint32_t x = v2.lo ^ v2.hi;
+    U64 o;
+    o.lo = __funnelshift_l(v3.hi, v3.lo, 21) ^ __funnelshift_l(v1.hi, v1.lo, 17) ^ x;
+    o.hi = __funnelshift_l(v3.lo, v3.hi, 21) ^ __funnelshift_l(v1.lo, v1.hi, 17) ^ x;
+    return o;
+}
+
+__device__ __forceinline__ uint32_t rem_2by1_dev(uint32_t u1, uint32_t u0, uint32_t dn, uint32_t v) {
+    const unsigned long long q = (unsigned long long)v * u1 + (((unsigned long long)u1 << 32) | u0);
+    const uint32_t q1 = (uint32_t)(q >> 32), q0 = (uint32_t)q;
+    uint32_t r = (u0 - dn) - q1 * dn;  // u0 - (q1+1)*dn
+    if (r > q0) r += dn;
+    return min(r, r - dn);             // r >= dn ? r - dn : r   (r < 2*dn <= 2^33 never holds both)
+}
+
+template <bool POW2>
+__device__ __forceinline__ uint32_t fastmod_dev(U64 h, const FastMod& fm) {
+    if (POW2) return h.lo & fm.pow2m1;
+    const uint32_t s = fm.shift;
+    const uint32_t u2 = __funnelshift_l(h.hi, 0u, s);      // h.hi >> (32-s), 0 for s == 0
+    const uint32_t u1 = __funnelshift_l(h.lo, h.hi, s);
+    const uint32_t u0 = h.lo << s;
+    const uint32_t r1 = rem_2by1_dev(u2, u1, fm.dn, fm.v);
+    const uint32_t r0 = rem_2by1_dev(r1, u0, fm.dn, fm.v);
+    return r0 >> s;
+}
+
+// ---------------------------------------------------------------------------
+// mbarrier + 1-D TMA bulk copy (cp.async.bulk, SASS: UBLKCP)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) {
+    return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    // make the init visible to the async (TMA) proxy
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// global → shared bulk copy; size multiple of 16, both addresses 16-byte aligned
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, unsigned bytes,
+                                            unsigned long long* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+#endif
+
+// splitmix64 — the synthetic generator's mixer
+__host__ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
+    x += 0x9E3779B97F4A7C15ULL;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+    return x ^ (x >> 31);
+}
+
+}  // namespace nk

@@ -1,0 +1,153 @@
+// nk_fastx.cpp — FASTA/FASTQ record reader (host).  Stands in for needletail 0.6.3's
+// parse_fastx_file as the reference drives it (src/utils.rs:9-24): see nk_host.h.
+#include "nk_host.h"
+
+#include <cerrno>
+#include <cstring>
+#include <fcntl.h>
+#include <unistd.h>
+
+namespace nk {
+
+uint64_t host_pack_kmer(const uint8_t* kmer, uint64_t len) {
+    uint64_t packed = 0;
+    for (uint64_t i = 0; i < len; ++i) {
+        uint64_t bits;
+        switch (kmer[i]) {
+            case 'A': case 'a': bits = 0; break;
+            case 'C': case 'c': bits = 1; break;
+            case 'G': case 'g': bits = 2; break;
+            case 'T': case 't': bits = 3; break;
+            default: continue;
+        }
+        packed = (packed << 2) | bits;
+    }
+    return packed;
+}
+
+FastxReader::~FastxReader() {
+    if (fd_ >= 0) ::close(fd_);
+}
+
+bool FastxReader::fill() {
+    if (eof_) return false;
+    pos_ = 0;
+    end_ = 0;
+    for (;;) {
+        ssize_t n = ::read(fd_, buf_.data(), buf_.size());
+        if (n < 0 && errno == EINTR) continue;
+        if (n <= 0) { eof_ = true; return false; }
+        end_ = (size_t)n;
+        return true;
+    }
+}
+
+int FastxReader::peek() {
+    if (pos_ == end_ && !fill()) return -1;
+    return buf_[pos_];
+}
+
+void FastxReader::skip_line() {
+    for (;;) {
+        if (pos_ == end_ && !fill()) return;
+        const uint8_t* p = (const uint8_t*)memchr(buf_.data() + pos_, '\n', end_ - pos_);
+        if (p) { pos_ = (size_t)(p - buf_.data()) + 1; at_line_start_ = true; return; }
+        pos_ = end_;
+    }
+}
+
+int FastxReader::open(const char* path, std::string* err) {
+    fd_ = ::open(path, O_RDONLY);
+    if (fd_ < 0) {
+        if (err) *err = std::string("cannot open ") + path + ": " + strerror(errno);
+        return 1;
+    }
+    buf_.resize(4u << 20);
+    const int c = peek();
+    if (c < 0) { if (err) *err = std::string(path) + ": empty file"; return 1; }
+    if (c == 0x1f || c == 'B' || c == 0xfd || c == 0x28) {
+        if (err) *err = std::string(path) + ": compressed input is not supported (plain FASTA/FASTQ only)";
+        return 1;
+    }
+    if (c == '>') fastq_ = false;
+    else if (c == '@') fastq_ = true;
+    else { if (err) *err = std::string(path) + ": not FASTA/FASTQ (first byte must be '>' or '@')"; return 1; }
+    at_line_start_ = true;
+    return 0;
+}
+
+bool FastxReader::next_record() {
+    const int c = peek();
+    if (c < 0) return false;
+    if (fastq_) {
+        if (c != '@') return false;  // malformed: iteration ends (src/utils.rs:17-20)
+    } else {
+        if (c != '>') {
+            // only reachable right after open() (first byte checked) or after read_seq stopped at '>'
+            return false;
+        }
+    }
+    skip_line();  // header
+    started_ = true;
+    return true;
+}
+
+size_t FastxReader::read_seq(uint8_t* dst, size_t cap, bool* done) {
+    size_t w = 0;
+    *done = false;
+    while (w < cap) {
+        if (pos_ == end_ && !fill()) { *done = true; return w; }
+        if (at_line_start_) {
+            if (!fastq_ && buf_[pos_] == '>') { *done = true; return w; }
+            at_line_start_ = false;
+        }
+        // copy up to end of line
+        const uint8_t* s = buf_.data() + pos_;
+        size_t avail = end_ - pos_;
+        if (avail > cap - w) avail = cap - w;
+        const uint8_t* nl = (const uint8_t*)memchr(s, '\n', avail);
+        const size_t n = nl ? (size_t)(nl - s) : avail;
+        // strip '\r' (only ever a line terminator in text FASTA/FASTQ)
+        for (size_t i = 0; i < n; ++i) {
+            const uint8_t b = s[i];
+            if (b != '\r') dst[w++] = b;
+        }
+        pos_ += n;
+        if (nl) {
+            pos_ += 1;
+            at_line_start_ = true;
+            if (fastq_) { *done = true; return w; }  // FASTQ sequence is one line
+        }
+    }
+    // cap reached: the record may or may not be finished
+    if (!fastq_) {
+        if (pos_ == end_ && !fill()) { *done = true; return w; }
+        if (at_line_start_ && buf_[pos_] == '>') *done = true;
+    }
+    return w;
+}
+
+bool FastxReader::finish_record(uint64_t seq_len) {
+    if (!fastq_) return true;
+    if (peek() != '+') return false;
+    skip_line();
+    // quality line: count bytes up to '\n' (excluding '\r')
+    uint64_t q = 0;
+    bool saw_nl = false;
+    for (;;) {
+        if (pos_ == end_ && !fill()) break;
+        const uint8_t* s = buf_.data() + pos_;
+        const size_t avail = end_ - pos_;
+        const uint8_t* nl = (const uint8_t*)memchr(s, '\n', avail);
+        const size_t n = nl ? (size_t)(nl - s) : avail;
+        q += n;
+        if (n > 0 && s[n - 1] == '\r' && nl) q -= 1;
+        pos_ += n;
+        if (nl) { pos_ += 1; saw_nl = true; break; }
+    }
+    (void)saw_nl;
+    at_line_start_ = true;
+    return q == seq_len;
+}
+
+}  // namespace nk

@@ -1,0 +1,113 @@
+// nk_kernels.cuh — host-callable launchers of the sm_100a kernels.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "nk_device.cuh"
+
+namespace nk {
+
+// ---- geometry of the counting kernel ---------------------------------------
+// A CTA of 8 warps consumes tiles of COUNT_TILE consecutive window-start
+// positions.  Warp w owns the span [w*SPAN, (w+1)*SPAN) of the tile and walks it
+// in chunks of 512 positions: lane L loads the 16 bytes [16L, 16L+16) of the
+// chunk (one LDS.128 from the TMA-staged tile), turns them into 2-bit code words,
+// and receives the words of lanes L+1, L+2 by shuffle (the k-1 <= 31 overlap).
+constexpr int COUNT_THREADS = 256;
+constexpr int COUNT_WARPS = COUNT_THREADS / 32;
+constexpr int COUNT_CHUNK = 512;                         // positions per warp iteration
+constexpr int COUNT_CHUNKS_PER_SPAN = 4;
+constexpr int COUNT_SPAN = COUNT_CHUNK * COUNT_CHUNKS_PER_SPAN;
+constexpr int COUNT_TILE = COUNT_WARPS * COUNT_SPAN;     // 16384 positions
+constexpr int COUNT_HALO = 32;                           // >= k-1, multiple of 16
+constexpr int COUNT_STAGES = 2;
+
+struct CountParams {
+    const unsigned char* bases;   // device, 16-B aligned, readable up to ntiles*TILE + HALO
+    const unsigned int* invalid;  // bit p set => no window starts at p; ntiles*TILE/32 words (+pad)
+    unsigned int* acc;            // pool_size u32 batch accumulators
+    unsigned int* tile_counter;   // dynamic tile scheduler cursor (zeroed before launch)
+    unsigned long long ntiles;
+    FastMod fm;
+    unsigned int k;
+    // debug taps (EMIT instantiation only); any may be null
+    unsigned long long* out_fwd;
+    unsigned long long* out_rc;
+    unsigned long long* out_word;
+    unsigned long long* out_idx;
+};
+
+size_t count_smem_bytes();
+// size a bases buffer must have so that every tile copy is in bounds
+inline unsigned long long count_ntiles(unsigned long long nbytes) {
+    return (nbytes + COUNT_TILE - 1) / COUNT_TILE;
+}
+inline unsigned long long count_padded_bases(unsigned long long nbytes) {
+    return count_ntiles(nbytes) * COUNT_TILE + COUNT_HALO + 64;
+}
+inline unsigned long long count_bitmap_words(unsigned long long nbytes) {
+    return count_ntiles(nbytes) * (COUNT_TILE / 32) + 16;
+}
+
+cudaError_t launch_count(const CountParams& p, bool canonical, bool emit, int grid, cudaStream_t s);
+cudaError_t count_max_grid(bool canonical, int device, int* grid);
+
+// invalid-start bitmap: zero, then mark the last k-1 starts of every sequence
+// in [seq_lo, seq_hi) (positions relative to `origin`) and everything in
+// [nbytes, ntiles*TILE).  *kmers (device) += windows starting inside the chunk.
+cudaError_t launch_mark_invalid(unsigned int* invalid, const unsigned long long* offsets,
+                                unsigned long long seq_lo, unsigned long long seq_hi,
+                                unsigned long long origin, unsigned long long nbytes, unsigned k,
+                                unsigned long long* kmers, cudaStream_t s, uint64_t* launches);
+
+// acc (u32) -> currents (u64): currents[i] = (overwrite ? 0 : currents[i]) + acc[i]; acc[i] = 0
+cudaError_t launch_fold(unsigned int* acc, unsigned long long* currents, unsigned long long pool,
+                        bool overwrite, cudaStream_t s);
+
+struct LifParams {
+    const unsigned long long* currents;
+    float* v;
+    unsigned int* r;
+    unsigned long long* spikes;
+    unsigned long long* total_new;   // += spikes fired by this launch
+    unsigned long long* max_spikes;  // max over neurons of cumulative spike count (atomicMax)
+    unsigned long long pool;
+    unsigned long long steps;
+    float thr, leak;
+    unsigned int period;
+    int skip_zero;  // 1: in-memory driver, 0: streaming (SIMD-semantics) driver
+};
+// direct simulation: one thread per neuron, `steps` ticks
+cudaError_t launch_lif(const LifParams& p, cudaStream_t s);
+// uniform-fresh-state fast path: simulate once per distinct count value (table of
+// `table_n` entries, counts >= table_n-1 behave like table_n-1), then one lookup per neuron.
+struct LifTable {
+    unsigned int* spikes;  // table_n
+    float* v;              // table_n
+    unsigned int* r;       // table_n
+};
+cudaError_t launch_lif_table(const LifParams& p, const LifTable& t, unsigned long long table_n, cudaStream_t s);
+// one LIF tick per neuron with the raw count as input; currents zeroed (process_sequence)
+cudaError_t launch_lif_single_tick(const LifParams& p, unsigned long long* currents_rw, cudaStream_t s);
+
+// top-N by (spikes desc, idx asc).  See nk_topn.cu.
+struct TopNScratch {
+    unsigned int* hist;              // 256 bins
+    unsigned long long* ctrl;        // control block, 8 u64
+    unsigned int* block_counts;      // ceil(pool/TOPN_BLOCK_ITEMS)+1
+    unsigned long long* out_idx;     // capacity >= n_cap
+    unsigned long long* out_spikes;  // capacity >= n_cap
+};
+constexpr int TOPN_BLOCK_ITEMS = 4096;
+constexpr unsigned long long TOPN_MAX_N = 1ull << 20;
+cudaError_t launch_topn(const unsigned long long* spikes, unsigned long long pool, unsigned long long n,
+                        unsigned long long max_spikes, const TopNScratch& sc, cudaStream_t s,
+                        uint64_t* launches);
+
+cudaError_t launch_hash_words(const unsigned long long* words, unsigned long long n, FastMod fm,
+                              unsigned long long* hashes, unsigned long long* idx, cudaStream_t s);
+
+cudaError_t launch_synth(unsigned char* out, unsigned long long seed, unsigned long long start,
+                         unsigned long long n, unsigned flags, cudaStream_t s);
+
+}  // namespace nk

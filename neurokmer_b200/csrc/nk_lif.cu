@@ -1,0 +1,231 @@
+// nk_lif.cu — pool fold + Leaky Integrate-and-Fire simulation (sm_100a).
+//
+// Replaces:
+//   currents store / overwrite                 src/spiking_hash.rs:174-176, :463-465
+//   LifNeuron::update                          src/models.rs:34-51
+//   in-memory LIF driver (skips zero current)  src/spiking_hash.rs:187-200
+//   simulate_spikes_simd (steps every neuron)  src/spiking_hash.rs:544-659
+//   process_sequence's single tick             src/spiking_hash.rs:266-272
+//   EnergyTracker totals                       src/models.rs:159-172
+//
+// Arithmetic is IEEE f32 with a SEPARATE multiply and add (__fmul_rn/__fadd_rn: rustc
+// and _mm256_mul_ps/_mm256_add_ps never fuse), input current = f32(f64(count)/f64(steps)).
+//
+// State invariant used below: refractory_ticks > 0 implies voltage == 0 (refractory is
+// only ever set together with voltage = 0 and voltage is frozen while it counts down),
+// so "inactive lane keeps its voltage" == "inactive lane has voltage 0", and the SIMD
+// driver's inactive-lane compare against f32::MAX (:611-613) can never fire.
+#include "nk_kernels.cuh"
+
+namespace nk {
+
+namespace {
+
+constexpr int LIF_THREADS = 256;
+
+__global__ void fold_kernel(unsigned int* __restrict__ acc, unsigned long long* __restrict__ currents,
+                            unsigned long long pool, int overwrite) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < pool; i += stride) {
+        const unsigned a = acc[i];
+        currents[i] = (overwrite ? 0ull : currents[i]) + a;
+        acc[i] = 0u;
+    }
+}
+
+struct NeuronResult {
+    float v;
+    unsigned r;
+    unsigned fired;
+};
+
+// `steps` ticks of one neuron.  Refractory state is carried as the index of the next
+// active tick (t_next): active at tick t iff t >= t_next; a spike at tick t sets
+// t_next = t + period + 1.  Equivalent to the reference's countdown:
+//   r > 0  -> r -= 1, no integration              (models.rs:35-38)
+//   else   -> v = v*leak + I; v >= thr -> spike   (models.rs:41-47)
+__device__ __forceinline__ NeuronResult lif_run(float v, unsigned r, float I, unsigned long long steps,
+                                                float thr, float leak, unsigned period) {
+    unsigned long long t_next = r;  // first active tick
+    unsigned fired = 0;
+    const unsigned long long p1 = (unsigned long long)period + 1ull;
+    if (steps < 0x7FFFFFFFull && p1 < 0x7FFFFFFFull && r < 0x7FFFFFFFu) {
+        // 32-bit tick arithmetic (every realistic configuration)
+        const unsigned n = (unsigned)steps, q1 = (unsigned)p1;
+        unsigned tn = r;
+#pragma unroll 8
+        for (unsigned t = 0; t < n; ++t) {
+            const bool active = t >= tn;
+            const float vn = __fadd_rn(__fmul_rn(v, leak), I);
+            const bool spike = active && (vn >= thr);
+            const bool keep = active && !(vn >= thr);
+            v = keep ? vn : (active ? 0.0f : v);
+            if (spike) {
+                ++fired;
+                tn = t + q1;
+            }
+        }
+        NeuronResult o;
+        o.v = v;
+        o.r = tn > n ? tn - n : 0u;
+        o.fired = fired;
+        return o;
+    }
+    for (unsigned long long t = 0; t < steps; ++t) {
+        if (t < t_next) continue;
+        v = __fadd_rn(__fmul_rn(v, leak), I);
+        if (v >= thr) {
+            v = 0.0f;
+            ++fired;
+            t_next = t + p1;
+        }
+    }
+    NeuronResult o;
+    o.v = v;
+    o.r = t_next > steps ? (unsigned)(t_next - steps) : 0u;
+    o.fired = fired;
+    return o;
+}
+
+__device__ __forceinline__ float input_current(unsigned long long count, unsigned long long steps) {
+    // (total_current / steps as f64) as f32      src/spiking_hash.rs:193-196, :581-582
+    return __double2float_rn(__ull2double_rn(count) / __ull2double_rn(steps));
+}
+
+__device__ __forceinline__ void block_totals(unsigned long long fired, unsigned long long maxs,
+                                             unsigned long long* total_new, unsigned long long* max_spikes) {
+    __shared__ unsigned long long s_f[LIF_THREADS / 32], s_m[LIF_THREADS / 32];
+    for (int o = 16; o > 0; o >>= 1) {
+        fired += __shfl_down_sync(0xFFFFFFFFu, fired, o);
+        const unsigned long long m = __shfl_down_sync(0xFFFFFFFFu, maxs, o);
+        maxs = m > maxs ? m : maxs;
+    }
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    if (lane == 0) { s_f[warp] = fired; s_m[warp] = maxs; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long f = 0, m = 0;
+        for (int w = 0; w < LIF_THREADS / 32; ++w) { f += s_f[w]; m = s_m[w] > m ? s_m[w] : m; }
+        if (f) atomicAdd(total_new, f);
+        if (m) atomicMax(max_spikes, m);
+    }
+}
+
+__global__ void __launch_bounds__(LIF_THREADS) lif_kernel(const LifParams p) {
+    const unsigned long long i = blockIdx.x * (unsigned long long)LIF_THREADS + threadIdx.x;
+    unsigned long long fired = 0, total = 0;
+    if (i < p.pool) {
+        const unsigned long long count = p.currents[i];
+        total = p.spikes[i];
+        if (!(p.skip_zero && count == 0)) {
+            const NeuronResult o =
+                lif_run(p.v[i], p.r[i], input_current(count, p.steps), p.steps, p.thr, p.leak, p.period);
+            p.v[i] = o.v;
+            p.r[i] = o.r;
+            fired = o.fired;
+            total += fired;
+            p.spikes[i] = total;
+        }
+    }
+    block_totals(fired, total, p.total_new, p.max_spikes);
+}
+
+// ---- uniform-fresh-state fast path ------------------------------------------------
+// While every neuron is still in its initial state (v = 0, r = 0) the result of the
+// simulation is a pure function of the neuron's count, and all counts >= c_sat (the
+// first count whose input current reaches the threshold) follow the same trajectory
+// (tick 0: v = 0*leak + I >= thr -> spike -> v = 0).  So: simulate once per distinct
+// count value c in [0, table_n) and look the result up per neuron.  Bit-identical to
+// lif_kernel (tests/test_parity_gpu.py::test_lif_table_equals_direct).
+__global__ void __launch_bounds__(LIF_THREADS) lif_table_build_kernel(const LifParams p, const LifTable t,
+                                                                     unsigned long long table_n) {
+    const unsigned long long c = blockIdx.x * (unsigned long long)LIF_THREADS + threadIdx.x;
+    if (c >= table_n) return;
+    const NeuronResult o = lif_run(0.0f, 0u, input_current(c, p.steps), p.steps, p.thr, p.leak, p.period);
+    t.spikes[c] = o.fired;
+    t.v[c] = o.v;
+    t.r[c] = o.r;
+}
+
+__global__ void __launch_bounds__(LIF_THREADS) lif_table_apply_kernel(const LifParams p, const LifTable t,
+                                                                     unsigned long long table_n) {
+    const unsigned long long i = blockIdx.x * (unsigned long long)LIF_THREADS + threadIdx.x;
+    unsigned long long fired = 0, total = 0;
+    if (i < p.pool) {
+        const unsigned long long count = p.currents[i];
+        total = p.spikes[i];
+        if (!(p.skip_zero && count == 0)) {
+            const unsigned long long c = count < table_n - 1 ? count : table_n - 1;
+            p.v[i] = t.v[c];
+            p.r[i] = t.r[c];
+            fired = t.spikes[c];
+            total += fired;
+            p.spikes[i] = total;
+        }
+    }
+    block_totals(fired, total, p.total_new, p.max_spikes);
+}
+
+// process_sequence tail (src/spiking_hash.rs:266-272): one update(count as f32) per
+// neuron with count > 0, then currents[i] = 0.
+__global__ void __launch_bounds__(LIF_THREADS) lif_single_tick_kernel(const LifParams p,
+                                                                     unsigned long long* currents_rw) {
+    const unsigned long long i = blockIdx.x * (unsigned long long)LIF_THREADS + threadIdx.x;
+    unsigned long long fired = 0, total = 0;
+    if (i < p.pool) {
+        const unsigned long long count = currents_rw[i];
+        total = p.spikes[i];
+        if (count > 0) {
+            float v = p.v[i];
+            unsigned r = p.r[i];
+            if (r > 0) {
+                r -= 1;
+            } else {
+                v = __fadd_rn(__fmul_rn(v, p.leak), __double2float_rn(__ull2double_rn(count)));
+                if (v >= p.thr) { v = 0.0f; r = p.period; fired = 1; }
+            }
+            p.v[i] = v;
+            p.r[i] = r;
+            total += fired;
+            p.spikes[i] = total;
+            currents_rw[i] = 0;
+        }
+    }
+    block_totals(fired, total, p.total_new, p.max_spikes);
+}
+
+}  // namespace
+
+cudaError_t launch_fold(unsigned int* acc, unsigned long long* currents, unsigned long long pool,
+                        bool overwrite, cudaStream_t s) {
+    unsigned long long blocks = (pool + 255) / 256;
+    if (blocks > 148ull * 16) blocks = 148ull * 16;
+    if (blocks == 0) blocks = 1;
+    fold_kernel<<<(unsigned)blocks, 256, 0, s>>>(acc, currents, pool, overwrite ? 1 : 0);
+    return cudaGetLastError();
+}
+
+static unsigned lif_blocks(unsigned long long n) { return (unsigned)((n + LIF_THREADS - 1) / LIF_THREADS); }
+
+cudaError_t launch_lif(const LifParams& p, cudaStream_t s) {
+    if (p.pool == 0 || p.steps == 0) return cudaSuccess;  // steps == 0: :548-551 / empty loop :195
+    lif_kernel<<<lif_blocks(p.pool), LIF_THREADS, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_lif_table(const LifParams& p, const LifTable& t, unsigned long long table_n, cudaStream_t s) {
+    if (p.pool == 0 || p.steps == 0) return cudaSuccess;
+    lif_table_build_kernel<<<lif_blocks(table_n), LIF_THREADS, 0, s>>>(p, t, table_n);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    lif_table_apply_kernel<<<lif_blocks(p.pool), LIF_THREADS, 0, s>>>(p, t, table_n);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_lif_single_tick(const LifParams& p, unsigned long long* currents_rw, cudaStream_t s) {
+    if (p.pool == 0) return cudaSuccess;
+    lif_single_tick_kernel<<<lif_blocks(p.pool), LIF_THREADS, 0, s>>>(p, currents_rw);
+    return cudaGetLastError();
+}
+
+}  // namespace nk

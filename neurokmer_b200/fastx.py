@@ -1,0 +1,59 @@
+"""Minimal FASTA/FASTQ record iterator and writers (host I/O helpers for tests, the
+Python surface and bench input files).  Record rules follow the reference's use of
+needletail (src/utils.rs:9-24): sequence = line(s) with terminators removed, iteration
+stops at the first malformed record.  The production file path is the C++ reader behind
+nk_process_file; this module is only used where the reference itself is per-record Python
+(src/python.rs:21-28)."""
+from __future__ import annotations
+
+from typing import Iterator
+
+
+def read_fastx(path: str) -> Iterator[bytes]:
+    with open(path, "rb") as f:
+        first = f.read(1)
+        if not first:
+            raise OSError(f"{path}: empty file")
+        if first not in (b">", b"@"):
+            raise OSError(f"{path}: not FASTA/FASTQ")
+        f.seek(0)
+        if first == b">":
+            seq, started = [], False
+            for line in f:
+                if line.startswith(b">"):
+                    if started:
+                        yield b"".join(seq)
+                    seq, started = [], True
+                else:
+                    seq.append(line.rstrip(b"\r\n").replace(b"\r", b""))
+            if started:
+                yield b"".join(seq)
+        else:
+            while True:
+                h = f.readline()
+                if not h:
+                    return
+                if not h.startswith(b"@"):
+                    return
+                s = f.readline().rstrip(b"\r\n")
+                p = f.readline()
+                q = f.readline().rstrip(b"\r\n")
+                if not p.startswith(b"+") or len(q) != len(s):
+                    return
+                yield s
+
+
+def write_fasta(path: str, seqs, width: int = 60) -> None:
+    with open(path, "wb") as f:
+        for i, s in enumerate(seqs):
+            s = bytes(s)
+            f.write(b">seq%d synthetic\n" % i)
+            for j in range(0, len(s), width):
+                f.write(s[j:j + width] + b"\n")
+
+
+def write_fastq(path: str, seqs) -> None:
+    with open(path, "wb") as f:
+        for i, s in enumerate(seqs):
+            s = bytes(s)
+            f.write(b"@r%d\n" % i + s + b"\n+\n" + b"I" * len(s) + b"\n")

@@ -1,0 +1,405 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes), against the CPU
+oracle on the same seeded inputs.  Bar: bit-exact for words, indices, currents, spike
+counts, refractory ticks, voltages (f32 bit patterns), totals and top-N.
+
+Each test cites the reference lines whose behaviour it pins."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from conftest import random_dna
+
+pytestmark = pytest.mark.gpu
+
+REF = dict(threshold=1.0, leak=0.95, refractory=2, spike_cost=1.0)  # reference src/main.rs:37
+
+
+def make(k, pool, canonical=True, **kw):
+    from neurokmer_b200 import SpikingKmerCounter
+    p = dict(REF); p.update(kw)
+    return SpikingKmerCounter(k, p["threshold"], p["leak"], p["refractory"], p["spike_cost"], pool, canonical)
+
+
+def oracle_counter(k, pool, canonical=True, steps=1000, **kw):
+    from oracle.oracle_py import OracleCounter
+    p = dict(REF); p.update(kw)
+    return OracleCounter(k, p["threshold"], p["leak"], p["refractory"], p["spike_cost"], pool, canonical, steps, threads=4)
+
+
+def assert_state_equal(c, o):
+    np.testing.assert_array_equal(c.currents(), o.currents)
+    np.testing.assert_array_equal(c.spike_counts(), o.spikes)
+    np.testing.assert_array_equal(c.refractory_ticks(), o.r)
+    np.testing.assert_array_equal(c.voltages().view(np.uint32), o.v.view(np.uint32))
+    assert c.energy.total_spikes() == o.total_spikes
+    assert c.energy_used() == o.energy_used()
+
+
+def assert_topn_equal(c, o, n):
+    got = c.top_abundant_neurons(n)
+    oi, os_ = o.top_abundant_neurons(n)
+    assert [g[0] for g in got] == [int(x) for x in oi]
+    assert [g[1] for g in got] == [int(x) for x in os_]
+
+
+# --- step 1+2: windowing, canonical min, SipHash, modulo ------------------------------------
+@pytest.mark.parametrize("k", [1, 2, 5, 15, 16, 17, 21, 31, 32])
+@pytest.mark.parametrize("canonical", [True, False])
+def test_kmer_words_and_indices(coracle, k, canonical):
+    """RollingKmerHash init/slide/canonical (models.rs:206-286), pack_kmer (utils.rs:26-39),
+    map_kmer_to_neuron (spiking_hash.rs:78-82)."""
+    rng = np.random.default_rng(100 + k)
+    pool = 1_000_003 if k % 2 else 65536
+    c = make(k, pool, canonical)
+    for n, pn, pl, pi in [(k, 0, 0, 0), (k + 1, 0.2, 0, 0), (700, 0.05, 0.2, 0.02), (20000, 0.01, 0.01, 0.01),
+                          (16384 + 40, 0.0, 0.0, 0.0), (33000, 0.3, 0.3, 0.1)]:
+        s = random_dna(rng, n, pn, pl, pi)
+        fwd, rc, words, idx = c.debug_kmers(s)
+        ow = coracle.kmer_words(s, k, canonical)
+        assert words.size == ow.size == n - k + 1
+        np.testing.assert_array_equal(words, ow)
+        if canonical:
+            of, orc = coracle.kmer_fwd_rc(s, k)
+            np.testing.assert_array_equal(fwd, of)
+            np.testing.assert_array_equal(rc, orc)
+        step = max(1, ow.size // 3000)
+        np.testing.assert_array_equal(idx[::step], coracle.indices(ow[::step], pool))
+    assert c.debug_kmers(b"ACGT"[: k - 1] if k > 1 else b"")[2].size == 0  # shorter than k: no windows
+
+
+def test_hash_kat_and_random(coracle):
+    """SipHasher13::new_with_keys(0,0) on 8 LE bytes (siphasher 1.0.2; SURVEY §A.4 vectors)."""
+    c = make(31, 2_000_000)
+    kat = {0: 0xBD60ACB658C79E45, 1: 0x1E9F734161D62DD9, 0x1B: 0xE38A965A565BD97F, 0xDEADBEEF: 0x1E1D875FB6B69775}
+    words = np.array(list(kat.keys()), np.uint64)
+    hs, ix = c.debug_hash(words)
+    assert [int(h) for h in hs] == list(kat.values())
+    assert [int(i) for i in ix] == [v % 2_000_000 for v in kat.values()]
+    rng = np.random.default_rng(7)
+    w = rng.integers(0, 2**64, size=5000, dtype=np.uint64)
+    w[:8] = [0, 1, 2**64 - 1, 2**63, 2**62 - 1, 0xFFFFFFFF, 0x100000000, 4**31 - 1]
+    for pool in [1, 2, 3, 1000, 65536, 1_000_000, 2_000_000, 16_000_000, 2**31, 2**31 + 1, 2**32 - 1]:
+        cc = make(31, pool) if pool <= 16_000_000 else None
+        if cc is None:
+            continue
+        hs, ix = cc.debug_hash(w)
+        exp_h = np.array([coracle.siphash13_u64(int(x)) for x in w[:600]], np.uint64)
+        np.testing.assert_array_equal(hs[:600], exp_h)
+        np.testing.assert_array_equal(ix[:600], exp_h % np.uint64(pool))
+        cc.close()
+
+
+# --- step 3: currents ------------------------------------------------------------------------
+def ragged_batch(rng, k):
+    lens = [0, 1, k - 1, k, k + 1, 3 * k, 511, 512, 513, 16383, 16384, 16385, 40000, 0, 7, 150, 150, 20, 150]
+    seqs = [random_dna(rng, max(0, n), 0.01, 0.05, 0.005) for n in lens]
+    return seqs
+
+
+@pytest.mark.parametrize("k,pool,canonical", [(21, 1_000_000, True), (31, 2_000_000, True), (15, 65536, True),
+                                              (32, 999_983, True), (31, 1_000_000, False), (7, 1000, False), (1, 3, True)])
+def test_currents_ragged(coracle, k, pool, canonical):
+    """currents[idx] += 1 per window, sequences shorter than k contribute nothing
+    (spiking_hash.rs:102-139); Σ currents = Σ max(0, L-k+1)."""
+    from neurokmer_b200 import flatten
+    rng = np.random.default_rng(k * 1000 + pool % 997)
+    seqs = ragged_batch(rng, k)
+    bases, offsets = flatten(seqs)
+    c = make(k, pool, canonical)
+    c.process_batch(bases, offsets)
+    exp, tot = coracle.accumulate(bases, offsets, k, pool, canonical, threads=4)
+    got = c.currents()
+    np.testing.assert_array_equal(got, exp)
+    assert int(got.sum()) == tot == sum(max(0, len(s) - k + 1) for s in seqs)
+    assert c.timings()["kmers"] == tot
+
+
+def test_empty_and_degenerate_inputs():
+    c = make(31, 1000)
+    c.process_parallel([])
+    assert c.currents().sum() == 0 and c.energy.total_spikes() == 0
+    c.process_parallel([b"", b"ACGT", b"N" * 30])
+    assert c.currents().sum() == 0
+    c.process_parallel([b"A" * 31])  # fwd 0, rc 4^31-1, canon 0  
+    cur = c.currents()
+    assert cur.sum() == 1
+    from oracle.oracle_py import neuron_index
+    assert cur[neuron_index(0, 1000)] == 1
+
+
+# --- full pipeline: LIF + totals + top-N -------------------------------------------------------
+@pytest.mark.parametrize("k,pool,n", [(21, 100_000, 3_000_000), (15, 4096, 2_000_000), (31, 50_000, 2_500_000)])
+def test_process_parallel_full(coracle, k, pool, n):
+    """process_parallel (spiking_hash.rs:84-201): currents overwrite, in-memory LIF driver
+    (zero-current neurons skipped), EnergyTracker, top_abundant_neurons (:661-673)."""
+    rng = np.random.default_rng(n + k)
+    seqs = [random_dna(rng, n // 2, 0.001, 0.01), random_dna(rng, n // 3, 0.0, 0.0), random_dna(rng, n // 6, 0.01, 0.0)]
+    from neurokmer_b200 import flatten
+    bases, offsets = flatten(seqs)
+    c = make(k, pool)
+    o = oracle_counter(k, pool)
+    c.process_batch(bases, offsets)
+    o.process_parallel(bases, offsets)
+    assert c.timings()["lif_path"] == 2  # fresh state: per-count table
+    assert_state_equal(c, o)
+    assert o.total_spikes > 0
+    for topn in (1, 20, 500, 3000):
+        assert_topn_equal(c, o, topn)
+    # second call on the same counter: neuron state carries over, currents are overwritten,
+    # and the direct simulation path runs (state is no longer uniform)
+    seqs2 = [random_dna(rng, n // 4, 0.0, 0.0)]
+    b2, o2 = flatten(seqs2)
+    c.process_batch(b2, o2)
+    o.process_parallel(b2, o2)
+    assert c.timings()["lif_path"] == 1
+    assert_state_equal(c, o)
+    assert_topn_equal(c, o, 20)
+
+
+def test_lif_table_equals_direct(coracle):
+    """The per-count table (fresh state) and the direct simulation give identical
+    (spike_count, voltage, refractory) for every neuron — incl. the count=50 edge that ends
+    at v=0.99999946 without ever spiking."""
+    rng = np.random.default_rng(5)
+    pool = 20000
+    seqs = [random_dna(rng, 1_500_000)]
+    a, b = make(21, pool), make(21, pool)
+    b.debug_set_lif_path(1)
+    a.process_parallel(seqs); b.process_parallel(seqs)
+    assert a.timings()["lif_path"] == 2 and b.timings()["lif_path"] == 1
+    np.testing.assert_array_equal(a.currents(), b.currents())
+    np.testing.assert_array_equal(a.spike_counts(), b.spike_counts())
+    np.testing.assert_array_equal(a.refractory_ticks(), b.refractory_ticks())
+    np.testing.assert_array_equal(a.voltages().view(np.uint32), b.voltages().view(np.uint32))
+    assert a.energy.total_spikes() == b.energy.total_spikes() > 0
+    cur = a.currents()
+    assert cur.min() < 50 < cur.max()
+    # transfer function at the reference's parameters
+    table = {0: 0, 50: 0, 51: 12, 52: 15, 55: 20, 59: 25, 75: 41, 100: 62, 150: 100, 200: 125, 300: 167, 500: 200}
+    sp = a.spike_counts()
+    for cnt, spikes in table.items():
+        hit = np.nonzero(cur == cnt)[0]
+        if hit.size:
+            assert set(sp[hit].tolist()) == {spikes}, (cnt, spikes)
+
+
+@pytest.mark.parametrize("params", [dict(threshold=0.5, leak=0.9, refractory=0), dict(threshold=2.5, leak=1.0, refractory=5),
+                                    dict(threshold=1.0, leak=0.0, refractory=1), dict(threshold=0.05, leak=0.5, refractory=3)])
+def test_lif_other_parameters(coracle, params):
+    """LifNeuron::update (models.rs:34-51) for parameters other than the CLI's, steps != 1000."""
+    rng = np.random.default_rng(11)
+    seqs = [random_dna(rng, 400_000)]
+    from neurokmer_b200 import flatten
+    bases, offsets = flatten(seqs)
+    for steps in (1, 37, 1000):
+        c = make(15, 5000, **params); c.set_steps(steps)
+        o = oracle_counter(15, 5000, steps=steps, **params)
+        assert c.get_steps() == steps
+        c.process_batch(bases, offsets); o.process_parallel(bases, offsets)
+        assert_state_equal(c, o)
+        c.process_batch(bases, offsets); o.process_parallel(bases, offsets)  # direct path, carried state
+        assert_state_equal(c, o)
+        assert_topn_equal(c, o, 20)
+    c = make(15, 5000); c.set_steps(0)  # steps == 0: no simulation (spiking_hash.rs:548-551)
+    c.process_batch(bases, offsets)
+    assert c.energy.total_spikes() == 0 and c.currents().sum() == 400_000 - 14
+
+
+def test_streaming_equals_in_memory(coracle):
+    """process_file_streaming minus parsing (spiking_hash.rs:277-486): batches accumulate,
+    totals overwrite currents, SIMD-semantics LIF (every neuron stepped); README's
+    'in-memory == streaming' claim."""
+    rng = np.random.default_rng(21)
+    from neurokmer_b200 import flatten
+    batches = [flatten([random_dna(rng, 600_000, 0.001), random_dna(rng, 100, 0.0)]),
+               flatten([random_dna(rng, 40, 0.0), random_dna(rng, 900_000, 0.0, 0.05)]),
+               flatten([]), flatten([random_dna(rng, 10)])]
+    k, pool = 31, 30000
+    c = make(k, pool); o = oracle_counter(k, pool)
+    c.stream_begin()
+    for b, off in batches:
+        c.stream_push(b, off)
+    c.stream_end()
+    o.process_streaming(batches)
+    assert_state_equal(c, o)
+    assert_topn_equal(c, o, 20)
+    # in-memory on the concatenation gives the same totals
+    allb, alloff = flatten([bytes(b[int(off[i]):int(off[i + 1])]) for b, off in batches for i in range(off.size - 1)])
+    m = make(k, pool); m.process_batch(allb, alloff)
+    np.testing.assert_array_equal(m.currents(), c.currents())
+    assert m.energy.total_spikes() == c.energy.total_spikes()
+    # a second streaming run on the same counter (carried state, zero-current neurons decay)
+    c.stream_begin(); c.stream_push(*batches[1]); c.stream_end()
+    o.process_streaming([batches[1]])
+    assert_state_equal(c, o)
+
+
+def test_chunked_h2d_pipeline_boundaries(coracle):
+    """Host batches larger than the 32 MiB copy granule are cut into chunks with a k-1 halo;
+    sequence ends that straddle a chunk boundary must neither lose nor double-count windows."""
+    rng = np.random.default_rng(33)
+    G = 32 << 20
+    lens = [G - 17, 40, 3, G + 5, 31, 30, 1000]  # ends at G-17, G+23 (straddles), ...
+    seqs = [random_dna(rng, n, 0.0005) for n in lens]
+    from neurokmer_b200 import flatten
+    bases, offsets = flatten(seqs)
+    k, pool = 31, 2_000_000
+    c = make(k, pool)
+    c.process_batch(bases, offsets)
+    exp, tot = coracle.accumulate(bases, offsets, k, pool, True, threads=8)
+    np.testing.assert_array_equal(c.currents(), exp)
+    assert c.timings()["kmers"] == tot
+
+
+def test_process_sequence(coracle):
+    """process_sequence (spiking_hash.rs:203-273): one tick with the raw count, currents zeroed."""
+    rng = np.random.default_rng(44)
+    k, pool = 5, 64
+    c = make(k, pool, True)
+    v = np.zeros(pool, np.float32); r = np.zeros(pool, np.uint32); sp = np.zeros(pool, np.uint64)
+    scratch = np.zeros(pool, np.uint64)
+    total = 0
+    for n in (3, 5, 40, 200, 7, 64, 300, 12):
+        s = random_dna(rng, n, 0.05)
+        c.process_sequence(s)
+        total += coracle.process_sequence(s, k, pool, True, 1.0, 0.95, 2, scratch, v, r, sp)
+        np.testing.assert_array_equal(c.spike_counts(), sp)
+        np.testing.assert_array_equal(c.refractory_ticks(), r)
+        np.testing.assert_array_equal(c.voltages().view(np.uint32), v.view(np.uint32))
+        assert c.currents().sum() == 0
+        assert c.energy.total_spikes() == total
+    assert total > 0
+
+
+def test_top_n_ties_and_limits():
+    """Stable sort descending ⇒ ties by ascending index; min(top_n, pool) rows; zero-spike
+    neurons are returned if they rank (spiking_hash.rs:661-673)."""
+    rng = np.random.default_rng(55)
+    c = make(15, 4096)
+    c.process_parallel([random_dna(rng, 6_000_000)])  # ~1465 hits per neuron: all saturate at 334
+    sp = c.spike_counts()
+    assert set(sp.tolist()) == {334}
+    top = c.top_abundant_neurons(20)
+    assert [t[0] for t in top] == list(range(20)) and all(t[1] == 334 for t in top)
+    assert all(t[2] is None for t in top)  # uniques not computed: never faked
+    assert len(c.top_abundant_neurons(10_000)) == 4096
+    full = c.top_abundant_neurons(4096)
+    assert [t[0] for t in full] == list(range(4096))
+    assert c.energy.total_spikes() == 334 * 4096
+    z = make(31, 100)
+    assert z.top_abundant_neurons(5) == [(i, 0, None) for i in range(5)]
+    assert z.top_abundant_neurons(0) == []
+
+
+def test_top_n_large_n(coracle):
+    rng = np.random.default_rng(66)
+    pool = 50_000
+    c = make(21, pool); o = oracle_counter(21, pool)
+    from neurokmer_b200 import flatten
+    bases, offsets = flatten([random_dna(rng, 3_000_000)])
+    c.process_batch(bases, offsets); o.process_parallel(bases, offsets)
+    for n in (2048, 2049, 5000, 50_000):
+        assert_topn_equal(c, o, n)
+
+
+# --- files ----------------------------------------------------------------------------------------
+def test_process_file_fasta_fastq(tmp_path, coracle):
+    """stream_sequences record rules (utils.rs:9-24) + both CLI modes (main.rs:39-46)."""
+    from neurokmer_b200 import NkError, flatten
+    from neurokmer_b200.fastx import write_fasta, write_fastq
+    rng = np.random.default_rng(77)
+    seqs = [random_dna(rng, n, 0.002, 0.02) for n in (250_000, 61, 60, 59, 0, 31, 30, 100_000)]
+    fa, fq = str(tmp_path / "a.fasta"), str(tmp_path / "a.fastq")
+    write_fasta(fa, seqs); write_fastq(fq, seqs)
+    bases, offsets = flatten(seqs)
+    k, pool = 31, 10_000
+    for path in (fa, fq):
+        for streaming in (True, False):
+            c = make(k, pool); o = oracle_counter(k, pool)
+            (c.process_file_streaming if streaming else c.process_file_in_memory)(path)
+            (o.process_streaming([(bases, offsets)]) if streaming else o.process_parallel(bases, offsets))
+            assert_state_equal(c, o)
+    # CRLF line ends are stripped
+    crlf = str(tmp_path / "crlf.fasta")
+    with open(fa, "rb") as f, open(crlf, "wb") as g:
+        g.write(f.read().replace(b"\n", b"\r\n"))
+    c = make(k, pool); c.process_file_streaming(crlf)
+    exp, _ = coracle.accumulate(bases, offsets, k, pool, True)
+    np.testing.assert_array_equal(c.currents(), exp)
+    # a malformed FASTQ record ends the stream: records before it still count (utils.rs:17-20)
+    bad = str(tmp_path / "bad.fastq")
+    with open(bad, "wb") as g:
+        g.write(b"@r0\n" + seqs[0] + b"\n+\n" + b"I" * len(seqs[0]) + b"\n")
+        g.write(b"@r1\n" + seqs[7] + b"\n+\n" + b"I" * 5 + b"\n")          # quality length mismatch
+        g.write(b"@r2\n" + seqs[1] + b"\n+\n" + b"I" * len(seqs[1]) + b"\n")
+    c = make(k, pool); c.process_file_streaming(bad)
+    b0, o0 = flatten([seqs[0]])
+    exp, _ = coracle.accumulate(b0, o0, k, pool, True)
+    np.testing.assert_array_equal(c.currents(), exp)
+    # open failure propagates (utils.rs:10 `?`)
+    with pytest.raises(NkError) as ei:
+        make(k, pool).process_file_streaming(str(tmp_path / "missing.fa"))
+    assert ei.value.code == 2
+    empty = str(tmp_path / "empty.fa"); open(empty, "wb").close()
+    with pytest.raises(NkError):
+        make(k, pool).process_file_streaming(empty)
+
+
+def test_file_sequence_longer_than_batch(tmp_path, coracle):
+    """A FASTA record longer than the 32 MiB pinned batch is cut into pieces overlapping by k-1."""
+    from neurokmer_b200 import flatten
+    from neurokmer_b200.fastx import write_fasta
+    rng = np.random.default_rng(88)
+    seqs = [random_dna(rng, (32 << 20) + 12345, 0.0003), random_dna(rng, 5000)]
+    fa = str(tmp_path / "long.fasta"); write_fasta(fa, seqs)
+    bases, offsets = flatten(seqs)
+    k, pool = 31, 2_000_000
+    c = make(k, pool); c.process_file_streaming(fa)
+    exp, tot = coracle.accumulate(bases, offsets, k, pool, True, threads=8)
+    np.testing.assert_array_equal(c.currents(), exp)
+
+
+# --- error behaviour ----------------------------------------------------------------------------
+def test_bad_arguments():
+    from neurokmer_b200 import NkError
+    for k in (0, 33):
+        with pytest.raises(NkError) as ei:
+            make(k, 1000)
+        assert ei.value.code == 1
+    with pytest.raises(NkError):
+        make(31, 0)
+    c = make(31, 1000)
+    with pytest.raises(NkError) as ei:
+        c.stream_push(np.zeros(4, np.uint8), np.array([0, 4], np.uint64))
+    assert ei.value.code == 6
+    with pytest.raises(NkError):
+        c.process_batch(np.zeros(4, np.uint8), np.array([1, 4], np.uint64))
+    with pytest.raises(NkError):
+        c.process_batch(np.zeros(4, np.uint8), np.array([0, 4, 2], np.uint64))
+    with pytest.raises(NkError) as ei:
+        c.get_count(5)
+    assert ei.value.code == 7
+
+
+# --- device-resident path + synthetic generator (what bench.py times) ---------------------------
+def test_staged_synthetic_matches_host_path(coracle):
+    k, pool, n = 31, 200_000, 5_000_000
+    c = make(k, pool)
+    lens = [2_000_000, 1_500_000, 1_000_000, 500_000]
+    db, do = c.stage_reserve(n, len(lens))
+    c.synth_fill(db, 2, 0, n, 3)
+    c.synchronize()
+    # copy offsets into the library's buffer and read the generated bases back
+    from neurokmer_b200.devmem import copy_h2d, device_to_numpy
+    copy_h2d(do, np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64))
+    bases = device_to_numpy(db, n)
+    assert set(np.unique(bases).tolist()) <= set(b"ACGTacgtN")
+    assert (bases == ord("N")).sum() > 0 and np.isin(bases, np.frombuffer(b"acgt", np.uint8)).sum() > 0
+    c.process_staged(n, len(lens), 0)
+    o = oracle_counter(k, pool)
+    o.process_parallel(bases, np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64))
+    assert_state_equal(c, o)
+    t = c.timings()
+    assert t["kmers"] == sum(l - k + 1 for l in lens) and t["count_ms"] > 0 and t["launches"] >= 4

@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py — canonical k-mers/s of the NeuroKmer counting hot path on B200.
+
+Workload (BASELINE.json configs[1], the configuration the metric is quoted on):
+synthetic 113 Mbase multi-sequence stream (7 sequences {30,25,20,15,10,8,5} Mbase, sparse
+N runs, 1 % soft-masked blocks, seed 2), k=31, pool 2,000,000, canonical, streaming
+semantics (accumulate -> totals overwrite currents -> every neuron stepped 1000 ticks)
+followed by the top-20 read-out.  One "step" = one whole job on a freshly reset counter.
+
+  value : whole-job throughput with the bases already resident in HBM (CUDA events on the
+          library's stream, L2 flushed before every step, max over ranks)
+  e2e   : the same job through the public host API with HOST buffers: pinned bases ->
+          nk_stream_push (chunked async H2D overlapped with the kernels) -> nk_stream_end ->
+          nk_top_n (D2H of the result rows), wall clock around the call sequence
+  roofline     : the count kernel (windowing+SipHash+mod+RED) against the three limits the
+                 north star names; denominators measured live by nk_calibrate + MEASURED_PEAKS.json
+  cpu_baseline : the oracle port (oracle/nk_oracle.c, pthreads, all host cores) on a bounded
+                 sample of the same workload — a reported baseline, not the target
+
+N > 1 (torchrun, one process per GPU): weak scaling — every rank counts its own 113 Mbase
+shard of the same synthetic stream into a full pool replica; the u64 currents are summed with
+ONE NCCL all-reduce over NVLink before LIF + top-N run (redundantly) on every rank.
+
+`--impl reference` times the reference's CPU algorithm (the oracle port: the Rust crate
+cannot be built here, no cargo/rustc) on the host cores, same config/metric.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K, POOL, STEPS_LIF, TOPN, SEED = 31, 2_000_000, 1000, 20, 2
+SEQ_LENS = [30_000_000, 25_000_000, 20_000_000, 15_000_000, 10_000_000, 8_000_000, 5_000_000]
+NBASES = sum(SEQ_LENS)
+KMERS = sum(l - K + 1 for l in SEQ_LENS)
+WORKLOAD = "synthetic 113 Mbase FASTA-equivalent (7 seqs, sparse N runs, 1% lowercase), k=31, pool 2M, canonical, streaming"
+LIF_REF = dict(threshold=1.0, leak=0.95, refractory=2, spike_cost=1.0)
+SIPHASH_OPS = 131  # 32-bit integer ops per k-mer of SipHash-1-3 on one 8-byte block
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+            t0 = time.time()
+            while not self.rows and time.time() - t0 < 5.0:  # nvidia-smi takes a moment to emit its first row
+                time.sleep(0.02)
+            self.rows.clear()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)  # let the last 100 ms sample land
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for i, n in enumerate(names):
+                if len(r) > 4 + i and r[4 + i].lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm (oracle port): used for cpu_baseline and for --impl reference
+# ---------------------------------------------------------------------------------------------
+def cpu_run(sample_bases: int, threads: int, bases_host: np.ndarray | None = None):
+    """One bounded pass of the reference's CPU algorithm: accumulate over the first
+    `sample_bases` bases of the workload (multi-threaded), LIF over the FULL 2M pool
+    (multi-threaded), top-20.  Returns (whole-job k-mers/s extrapolated, detail)."""
+    from oracle.oracle_py import COracle
+    from oracle.synth import synth_bases
+    c = COracle()
+    sample_bases = min(sample_bases, NBASES)
+    if bases_host is None:
+        bases_host = synth_bases(SEED, 0, sample_bases, 3)
+    bases = np.ascontiguousarray(bases_host[:sample_bases])
+    offs = [0]
+    for l in SEQ_LENS:
+        if offs[-1] + l >= sample_bases:
+            break
+        offs.append(offs[-1] + l)
+    offs.append(sample_bases)
+    offsets = np.array(offs, np.uint64)
+    sample_kmers = int(sum(max(0, int(offsets[i + 1] - offsets[i]) - K + 1) for i in range(len(offs) - 1)))
+    t0 = time.perf_counter()
+    cur, tot = c.accumulate(bases, offsets, K, POOL, True, threads=threads)
+    t_acc = time.perf_counter() - t0
+    assert tot == sample_kmers
+    # scale the sample's currents to the full job's mean so the LIF pass does representative work
+    scale = KMERS / max(sample_kmers, 1)
+    cur_full = (cur.astype(np.float64) * scale).astype(np.uint64)
+    t0 = time.perf_counter()
+    fired, v, r, spikes = c.lif(cur_full, STEPS_LIF, 1.0, 0.95, 2, simd_semantics=True, threads=threads)
+    t_lif = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    c.top_n(spikes, TOPN)
+    t_top = time.perf_counter() - t0
+    t_job = t_acc * scale + t_lif + t_top
+    return KMERS / t_job, dict(t_acc_sample=t_acc, sample_kmers=sample_kmers, t_lif=t_lif, t_topn=t_top,
+                               t_job_extrapolated=t_job)
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample = int(os.environ.get("NK_REF_SAMPLE_BASES", str(min(NBASES, 8_000_000 * threads))))
+    from oracle.synth import synth_bases
+    bases = synth_bases(SEED, 0, min(sample, NBASES), 3)
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, d = cpu_run(sample, threads, bases)
+        if i >= args.warmup:
+            vals.append((v, d))
+    v = float(np.mean([x[0] for x in vals]))
+    ms = float(np.mean([x[1]["t_acc_sample"] + x[1]["t_lif"] + x[1]["t_topn"] for x in vals]) * 1e3)
+    samp = (f"accumulate over the first {min(sample, NBASES)} bases ({vals[-1][1]['sample_kmers']} k-mers) on {threads} "
+            f"threads, LIF over the full 2M pool x1000 ticks, top-20; job time = acc*{KMERS}/sample + lif + topn")
+    print(json.dumps({
+        "impl": "reference", "metric": "canonical k-mers/sec (k=31, 2M pool)", "value": v, "unit": "kmers/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "k": K, "pool_size": POOL, "lif_steps": STEPS_LIF, "top_n": TOPN},
+        "cpu_baseline": {"value": v, "unit": "kmers/s", "cores": threads, "kind": "port", "sample": samp},
+        "e2e": {"value": v, "unit": "kmers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference is a Rust crate (no cargo/rustc in this image): timed the C restatement oracle/nk_oracle.c",
+    }))
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+class CurrentsView:
+    """__cuda_array_interface__ over the library's u64 currents (viewed as int64 for NCCL sum)."""
+
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 2}
+
+
+def gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    from neurokmer_b200 import PinnedBuffer, SpikingKmerCounter
+    from neurokmer_b200.devmem import copy_h2d, device_to_numpy
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    c = SpikingKmerCounter(K, LIF_REF["threshold"], LIF_REF["leak"], LIF_REF["refractory"], LIF_REF["spike_cost"],
+                           POOL, True, device=local)
+    stream = torch.cuda.ExternalStream(c.cuda_stream(), device=torch.device("cuda", local))
+    offsets = np.concatenate([[0], np.cumsum(SEQ_LENS)]).astype(np.uint64)
+    nseq = len(SEQ_LENS)
+
+    # device-resident input: this rank's shard of the stream (weak scaling: NBASES per rank)
+    dev_bases, dev_offs = c.stage_reserve(NBASES, nseq)
+    c.synth_fill(dev_bases, SEED, rank * NBASES, NBASES, 3)
+    copy_h2d(dev_offs, offsets)
+    c.synchronize()
+    # host copy of the same bytes in pinned memory for the end-to-end leg
+    pinned = PinnedBuffer(NBASES)
+    pinned.array[:] = device_to_numpy(dev_bases, NBASES)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def allreduce_currents():
+        ptr = c.stream_accumulated()
+        if world > 1:
+            t = torch.as_tensor(CurrentsView(ptr, POOL), device=torch.device("cuda", local))
+            with torch.cuda.stream(stream):
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+
+    def job_resident():
+        c.reset()
+        c.stream_begin()
+        c.process_staged(NBASES, nseq, 1)
+        allreduce_currents()
+        c.stream_finish()
+        return c.top_abundant_neurons(TOPN)
+
+    def job_e2e():
+        c.reset()
+        c.stream_begin()
+        c.stream_push(pinned.array, offsets)
+        allreduce_currents()
+        c.stream_finish()
+        return c.top_abundant_neurons(TOPN)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(job, nsteps, sampler=None):
+        per_step, phases, ar_ms = [], [], []
+        barrier()
+        if sampler:
+            sampler.start()
+        for _ in range(nsteps):
+            with torch.cuda.stream(stream):
+                flush.fill_(1)  # evict the input and the pool from L2 (untimed)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+            if job is job_e2e:
+                stream.synchronize()  # wall clock must not include the flush
+            t0 = time.perf_counter()
+            top = job()
+            with torch.cuda.stream(stream):
+                e1.record(stream)
+            e1.synchronize()
+            wall = (time.perf_counter() - t0) * 1e3
+            per_step.append((e0.elapsed_time(e1), wall))
+            phases.append(c.timings())
+        clocks = sampler.stop() if sampler else None
+        barrier()
+        return per_step, phases, top, clocks
+
+    # warm-up (>= 3), then EXACTLY K timed steps of each leg
+    W = max(args.warmup, 3)
+    timed(job_resident, W)
+    sampler = ClockSampler(local) if rank == 0 else None
+    steps_res, phases, top, clocks = timed(job_resident, args.steps, sampler)
+    timed(job_e2e, 2)
+    steps_e2e, phases_e2e, top_e2e, _ = timed(job_e2e, args.steps)
+    assert top == top_e2e or world > 1, "resident and end-to-end legs disagree"
+
+    total_spikes = c.energy.total_spikes()
+    dev_ms = float(sum(s[0] for s in steps_res))
+    e2e_ms = float(sum(s[1] for s in steps_e2e))
+    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    total_kmers = KMERS * world * args.steps
+    value = total_kmers / (dev_ms * 1e-3)
+    e2e_value = total_kmers / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        pk, pk_kind = peaks()
+        count_ms = float(np.mean([p["count_ms"] for p in phases]))
+        kps_kernel = KMERS / (count_ms * 1e-3)
+        # the three limits of the north star, denominators measured on this device
+        c.reset()
+        alu_ops = c.calibrate(0)
+        sip_ops = c.calibrate(1)
+        red_ps = c.calibrate(2)
+        c.reset()
+        hbm_bound = pk["hbm_gbs"] * 1e9 / (NBASES / KMERS)       # 1 B of ASCII per k-mer
+        int_bound = sip_ops / SIPHASH_OPS
+        red_bound = red_ps
+        binding = min((hbm_bound, "hbm"), (int_bound, "int32"), (red_bound, "l2_atomic"))
+        roofline = {
+            "bound": binding[1], "kernel": "count_kernel (windowing+SipHash-1-3+mod+RED.ADD)",
+            "achieved": kps_kernel * SIPHASH_OPS / 1e9 if binding[1] == "int32" else kps_kernel / 1e9,
+            "peak": sip_ops / 1e9 if binding[1] == "int32" else binding[0] / 1e9,
+            "unit": "Gop/s (32-bit integer, SipHash mix)" if binding[1] == "int32" else "G/s",
+            "frac": kps_kernel / binding[0], "traffic": None,
+            "kernel_ms": count_ms, "kernel_kmers_per_s": kps_kernel,
+            "limits_kmers_per_s": {"hbm": hbm_bound, "int32": int_bound, "l2_atomic": red_bound},
+            "hbm": {"achieved": NBASES / (count_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                    "frac": NBASES / (count_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "peak_source": pk_kind + " (MEASURED_PEAKS.json)"},
+            "peaks_measured_live": {"alu_lop3_shf_gops": alu_ops / 1e9, "sipround_mix_gops": sip_ops / 1e9,
+                                    "red_add_u32_random_2M_gps": red_ps / 1e9},
+            "algorithmic_per_kmer": {"hbm_bytes": NBASES / KMERS, "int32_ops": SIPHASH_OPS, "l2_reductions": 1},
+        }
+        ph = {k: float(np.mean([p[k] for p in phases])) for k in ("mark_ms", "count_ms", "fold_ms", "lif_ms", "topn_ms")}
+        launches = int(phases[-1]["launches"] + phases[-1]["topn_launches"])
+        # CPU baseline on a bounded sample (rank 0, N=1 only)
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            threads = os.cpu_count() or 1
+            sample = min(NBASES, 8_000_000 * threads)
+            v, d = cpu_run(sample, threads, pinned.array)
+            cpu = {"value": v, "unit": "kmers/s", "cores": threads, "kind": "port",
+                   "sample": (f"accumulate over the first {sample} bases ({d['sample_kmers']} k-mers, {d['t_acc_sample']:.2f} s) + LIF over "
+                              f"the full 2M pool ({d['t_lif']:.2f} s) + top-20; job time extrapolated = {d['t_job_extrapolated']:.2f} s")}
+        line = {
+            "metric": "canonical k-mers/sec (k=31, 2M pool)", "value": value, "unit": "kmers/s", "n_gpus": world,
+            "steps": args.steps, "warmup": W, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "k": K, "pool_size": POOL, "lif_steps": STEPS_LIF, "top_n": TOPN,
+                       "kmers_per_step_per_gpu": KMERS, "l2": "flushed before every step (256 MiB fill)",
+                       "parallelism": f"dp{world}: sequence-chunk shards, full pool replica, one NCCL all-reduce"},
+            "e2e": {"value": e2e_value, "unit": "kmers/s", "ms_per_step": e2e_ms / args.steps,
+                    "h2d_bytes_per_step": int(phases_e2e[-1]["h2d_bytes"]),
+                    "d2h_bytes_per_step": int(phases_e2e[-1]["d2h_bytes"] + 24 + 16 * TOPN)},
+            "gpu_launches": launches * args.steps,
+            "phases_ms": ph, "lif_path": int(phases[-1]["lif_path"]),
+            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            "result": {"total_spikes": total_spikes, "top1": list(top[0][:2]) if top else None},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

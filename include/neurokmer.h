@@ -171,6 +171,15 @@ NK_API int nk_last_timings(const nk_counter* h, nk_timings* out);
  * still in its initial state, direct simulation otherwise), 1 = always direct. */
 NK_API int nk_debug_set_lif_path(nk_counter* h, int mode);
 
+/* Roofline denominators measured on this device (micro-kernels, CUDA events, best of 3):
+ *   which 0: 32-bit ALU-pipe ops/s of independent LOP3+SHF chains (xor/rotate: what SipHash
+ *            cannot move off the ALU pipe);
+ *   which 1: 32-bit integer ops/s of register-only SipRound chains (SipHash's own
+ *            add:xor:rotate mix, 24 ops per round) — the integer-pipe ceiling of step 2;
+ *   which 2: RED.ADD.U32 per second to uniformly random slots of THIS handle's pool
+ *            (the pool-update ceiling of step 3).  Needs an idle counter; leaves it unchanged. */
+NK_API int nk_calibrate(nk_counter* h, int which, double* out);
+
 /* ---- device-resident input and multi-GPU plumbing --------------------------- */
 /* Reserve library-owned DEVICE buffers for a batch the caller will fill itself
  * (cudaMemcpyAsync, its own kernel, or nk_synth_fill): *dev_bases holds nbytes

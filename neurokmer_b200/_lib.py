@@ -21,7 +21,7 @@ SYMBOLS = [
     "nk_stream_end", "nk_process_file", "nk_process_sequence", "nk_simulate", "nk_top_n",
     "nk_total_spikes", "nk_energy_used", "nk_get_count", "nk_debug_kmers", "nk_debug_hash",
     "nk_copy_currents", "nk_copy_spike_counts", "nk_copy_voltages", "nk_copy_refractory",
-    "nk_last_timings", "nk_debug_set_lif_path", "nk_stage_reserve", "nk_process_staged", "nk_stream_accumulated",
+    "nk_last_timings", "nk_debug_set_lif_path", "nk_calibrate", "nk_stage_reserve", "nk_process_staged", "nk_stream_accumulated",
     "nk_stream_finish", "nk_cuda_stream", "nk_synchronize", "nk_synth_fill", "nk_host_alloc",
     "nk_host_free", "nk_pack_kmer",
 ]
@@ -93,6 +93,7 @@ def load() -> C.CDLL:
         "nk_copy_refractory": (i32, [vp, vp]),
         "nk_last_timings": (i32, [vp, P(NkTimings)]),
         "nk_debug_set_lif_path": (i32, [vp, i32]),
+        "nk_calibrate": (i32, [vp, i32, P(C.c_double)]),
         "nk_stage_reserve": (i32, [vp, u64, u64, P(vp), P(vp)]),
         "nk_process_staged": (i32, [vp, u64, u64, i32]),
         "nk_stream_accumulated": (i32, [vp, P(vp)]),

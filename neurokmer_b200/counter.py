@@ -212,6 +212,11 @@ class SpikingKmerCounter:
     def debug_set_lif_path(self, mode: int) -> None:
         check(self._L.nk_debug_set_lif_path(self._h, mode))
 
+    def calibrate(self, which: int) -> float:
+        out = C.c_double()
+        check(self._L.nk_calibrate(self._h, which, C.byref(out)))
+        return out.value
+
     def timings(self) -> dict:
         t = NkTimings()
         check(self._L.nk_last_timings(self._h, C.byref(t)))

@@ -878,6 +878,42 @@ int nk_debug_set_lif_path(nk_counter* h, int mode) {
     return NK_OK;
 }
 
+int nk_calibrate(nk_counter* h, int which, double* out) {
+    if (!h || !out) return fail(NK_ERR_BAD_ARG, "null argument");
+    if (which < 0 || which > 2) return fail(NK_ERR_BAD_ARG, "which must be 0, 1 or 2");
+    if (h->streaming || h->acc_dirty) return fail(NK_ERR_STATE, "nk_calibrate needs an idle counter");
+    NK_CUDA(cudaSetDevice(h->cfg.device));
+    int sms = 0;
+    NK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
+    const int blocks = sms * 8;
+    cudaEvent_t a, b;
+    h->ev_used = 0;
+    NK_TRY(get_event(h, &a));
+    NK_TRY(get_event(h, &b));
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        double work = 0.0;
+        NK_CUDA(cudaEventRecord(a, h->stream));
+        if (which <= 1) {
+            const unsigned iters = 4096;
+            NK_CUDA(nk::launch_int_peak(which, h->tile_counter + 4, blocks, iters, h->stream));
+            work = (double)blocks * 256.0 * iters * (double)nk::int_peak_ops_per_iter(which);
+        } else {
+            const unsigned per_thread = 512;
+            NK_CUDA(nk::launch_red_peak(h->acc, h->fm, blocks, per_thread, h->stream));
+            work = (double)blocks * 256.0 * per_thread;
+        }
+        NK_CUDA(cudaEventRecord(b, h->stream));
+        NK_CUDA(cudaStreamSynchronize(h->stream));
+        const float ms = ev_ms(a, b);
+        if (rep > 0 && ms > 0.f) best = std::max(best, work / (ms * 1e-3));
+    }
+    if (which == 2) NK_CUDA(cudaMemsetAsync(h->acc, 0, h->cfg.pool_size * sizeof(unsigned int), h->stream));
+    NK_CUDA(cudaStreamSynchronize(h->stream));
+    *out = best;
+    return NK_OK;
+}
+
 int nk_stage_reserve(nk_counter* h, uint64_t nbytes, uint64_t nseq, void** dev_bases, void** dev_offsets) {
     if (!h) return fail(NK_ERR_BAD_ARG, "null handle");
     NK_CUDA(cudaSetDevice(h->cfg.device));

@@ -107,6 +107,11 @@ cudaError_t launch_topn(const unsigned long long* spikes, unsigned long long poo
 cudaError_t launch_hash_words(const unsigned long long* words, unsigned long long n, FastMod fm,
                               unsigned long long* hashes, unsigned long long* idx, cudaStream_t s);
 
+// peak calibration (roofline denominators)
+cudaError_t launch_int_peak(int mode, unsigned int* out, int blocks, unsigned iters, cudaStream_t s);
+unsigned long long int_peak_ops_per_iter(int mode);
+cudaError_t launch_red_peak(unsigned int* acc, FastMod fm, int blocks, unsigned per_thread, cudaStream_t s);
+
 cudaError_t launch_synth(unsigned char* out, unsigned long long seed, unsigned long long start,
                          unsigned long long n, unsigned flags, cudaStream_t s);
 

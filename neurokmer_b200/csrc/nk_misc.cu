@@ -50,7 +50,80 @@ __global__ void synth_kernel(unsigned char* out, unsigned long long seed, unsign
     }
 }
 
+// ---- peak calibration micro-kernels (roofline denominators, measured live) -----------------
+// MODE 0: independent LOP3 + SHF chains (the ALU-pipe-only part of SipHash: xor, rotate)
+// MODE 1: independent SipRound chains (add : xor : rotate = 1 : 1 : 1 on 64-bit words,
+//         24 32-bit ops per round) — the integer-pipe ceiling for SipHash's own mix
+template <int MODE>
+__global__ void __launch_bounds__(256) int_peak_kernel(unsigned int* out, unsigned iters, unsigned seed) {
+    constexpr int CH = 4;
+    if (MODE == 0) {
+        unsigned a[2 * CH];
+#pragma unroll
+        for (int i = 0; i < 2 * CH; ++i) a[i] = seed + threadIdx.x * 31u + i * 0x9E3779B9u + blockIdx.x;
+        const unsigned b = seed ^ 0x5bd1e995u;
+        for (unsigned it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+#pragma unroll
+                for (int i = 0; i < 2 * CH; ++i) {
+                    a[i] = __funnelshift_l(a[i], a[(i + 1) % (2 * CH)], 13);  // SHF
+                    a[i] ^= b;                                                  // LOP3
+                }
+            }
+        }
+        unsigned x = 0;
+#pragma unroll
+        for (int i = 0; i < 2 * CH; ++i) x ^= a[i];
+        if (x == 0x12345u) out[0] = x;
+    } else {
+        U64 v0[CH], v1[CH], v2[CH], v3[CH];
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+            v0[i] = U64{seed + i, threadIdx.x};
+            v1[i] = U64{seed * 3u + i, blockIdx.x};
+            v2[i] = U64{seed ^ 0xabcdefu, i * 77u + threadIdx.x};
+            v3[i] = U64{threadIdx.x * 2654435761u, seed + 5u * i};
+        }
+        for (unsigned it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+#pragma unroll
+                for (int i = 0; i < CH; ++i) NK_SIPROUND32(v0[i], v1[i], v2[i], v3[i]);
+            }
+        }
+        unsigned x = 0;
+#pragma unroll
+        for (int i = 0; i < CH; ++i) x ^= v0[i].lo ^ v1[i].hi ^ v2[i].lo ^ v3[i].hi;
+        if (x == 0x12345u) out[0] = x;
+    }
+}
+
+// RED.ADD.U32 to pseudo-random slots of `pool` (the pool-update limit): `per_thread` reductions per thread
+__global__ void __launch_bounds__(256) red_peak_kernel(unsigned int* acc, FastMod fm, unsigned per_thread) {
+    unsigned x = (blockIdx.x * 256u + threadIdx.x) * 2654435761u + 12345u;
+    const unsigned p = fm.p;
+    for (unsigned i = 0; i < per_thread; ++i) {
+        x = x * 1664525u + 1013904223u;
+        const unsigned idx = __umulhi(x, p);  // uniform in [0, p)
+        atomicAdd(acc + idx, 1u);
+    }
+}
+
 }  // namespace
+
+cudaError_t launch_int_peak(int mode, unsigned int* out, int blocks, unsigned iters, cudaStream_t s) {
+    if (mode == 0) int_peak_kernel<0><<<blocks, 256, 0, s>>>(out, iters, 17u);
+    else int_peak_kernel<1><<<blocks, 256, 0, s>>>(out, iters, 17u);
+    return cudaGetLastError();
+}
+// 32-bit integer ops one thread executes per `iters` unit in launch_int_peak
+unsigned long long int_peak_ops_per_iter(int mode) { return mode == 0 ? 8ull * 8 * 2 : 2ull * 4 * 24; }
+
+cudaError_t launch_red_peak(unsigned int* acc, FastMod fm, int blocks, unsigned per_thread, cudaStream_t s) {
+    red_peak_kernel<<<blocks, 256, 0, s>>>(acc, fm, per_thread);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_hash_words(const unsigned long long* words, unsigned long long n, FastMod fm,
                               unsigned long long* hashes, unsigned long long* idx, cudaStream_t s) {

@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libneurokmer.so")
+# NEUROKMER_LIB: alternative build of the same library (kernel-variant experiments, tools/variants.sh)
+LIB_PATH = os.environ.get("NEUROKMER_LIB") or os.path.join(HERE, "libneurokmer.so")
 
 NK_OK = 0
 NK_ERR_BAD_ARG, NK_ERR_IO, NK_ERR_CUDA, NK_ERR_NO_DEVICE, NK_ERR_OOM, NK_ERR_STATE, NK_ERR_UNSUPPORTED = range(1, 8)

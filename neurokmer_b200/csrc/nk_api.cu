@@ -195,6 +195,7 @@ int count_chunk(nk_counter* h, DevBuf& b, const unsigned long long* d_offsets, u
     p.tile_counter = h->tile_counter;
     p.ntiles = nk::count_ntiles(nstarts);
     p.fm = h->fm;
+    p.rm = nk::make_rotmul();
     p.k = h->cfg.k;
     const unsigned long long want = p.ntiles < (unsigned long long)h->grid ? p.ntiles : (unsigned long long)h->grid;
     NK_CUDA(nk::launch_count(p, h->cfg.use_canonical != 0, false, (int)want, h->stream));
@@ -814,7 +815,7 @@ int nk_debug_kmers(nk_counter* h, const uint8_t* seq, uint64_t len, uint64_t* fw
                                      h->stream, nullptr));
         nk::CountParams p{};
         p.bases = h->staged.bases; p.invalid = h->staged.invalid; p.acc = h->acc; p.tile_counter = h->tile_counter;
-        p.ntiles = nk::count_ntiles(len); p.fm = h->fm; p.k = h->cfg.k;
+        p.ntiles = nk::count_ntiles(len); p.fm = h->fm; p.rm = nk::make_rotmul(); p.k = h->cfg.k;
         p.out_fwd = fwd ? d_out : nullptr;
         p.out_rc = rc ? d_out + n : nullptr;
         p.out_word = words ? d_out + 2 * n : nullptr;

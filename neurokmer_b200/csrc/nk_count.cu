@@ -18,6 +18,10 @@
 //   min(fwd, rc) -> SipHash-1-3 -> exact mod -> RED.ADD.U32 into the L2-resident pool.
 #include "nk_kernels.cuh"
 
+#ifndef NK_COUNT_UNROLL
+#define NK_COUNT_UNROLL 4
+#endif
+
 namespace nk {
 
 namespace {
@@ -76,7 +80,7 @@ __device__ __noinline__ unsigned long long pack_skip(unsigned F0, unsigned F1, u
     return word;
 }
 
-template <bool CANON, bool EMIT, bool POW2>
+template <bool CANON, bool EMIT, bool POW2, bool KHI>
 __device__ __forceinline__ void process_chunk(const CountParams& p, const WindowConsts& wc, const Codes16& cur,
                                               const Codes16& nxt, unsigned inv16, unsigned lane,
                                               unsigned long long pos0) {
@@ -106,26 +110,29 @@ __device__ __forceinline__ void process_chunk(const CountParams& p, const Window
         H2 = __funnelshift_r(u2, u1, wc.sh);
     }
 
-#pragma unroll 4
+    constexpr int kUnroll = NK_COUNT_UNROLL;
+#pragma unroll(kUnroll)
     for (unsigned j = 0; j < 16; ++j) {
         const unsigned sr = 32u - 2u * j;
-        const unsigned flo = __funnelshift_rc(G2, G1, sr) & wc.mask_lo;
-        const unsigned fhi = __funnelshift_rc(G1, G0, sr) & wc.mask_hi;
+        // KHI (k > 16): the low word is all window, only the high word needs the mask;
+        // else the window fits the low word and the high word is zero
+        const unsigned flo = KHI ? __funnelshift_rc(G2, G1, sr) : (__funnelshift_rc(G2, G1, sr) & wc.mask_lo);
+        const unsigned fhi = KHI ? (__funnelshift_rc(G1, G0, sr) & wc.mask_hi) : 0u;
         const unsigned long long fwd = ((unsigned long long)fhi << 32) | flo;
         unsigned long long rc = 0, word;
         if (CANON) {
-            const unsigned rlo = __funnelshift_r(R0, R1, 2u * j) & wc.mask_lo;
-            const unsigned rhi = __funnelshift_r(R1, R2, 2u * j) & wc.mask_hi;
+            const unsigned rlo = KHI ? __funnelshift_r(R0, R1, 2u * j) : (__funnelshift_r(R0, R1, 2u * j) & wc.mask_lo);
+            const unsigned rhi = KHI ? (__funnelshift_r(R1, R2, 2u * j) & wc.mask_hi) : 0u;
             rc = ((unsigned long long)rhi << 32) | rlo;
             word = fwd < rc ? fwd : rc;  // src/models.rs:284-286
         } else {
-            const unsigned vlo = __funnelshift_rc(H2, H1, sr) & wc.mask_lo;
-            const unsigned vhi = __funnelshift_rc(H1, H0, sr) & wc.mask_hi;
+            const unsigned vlo = KHI ? __funnelshift_rc(H2, H1, sr) : (__funnelshift_rc(H2, H1, sr) & wc.mask_lo);
+            const unsigned vhi = KHI ? (__funnelshift_rc(H1, H0, sr) & wc.mask_hi) : 0u;
             word = fwd;  // all k bytes are ACGT: pack_kmer == forward word
-            if (vlo != wc.mask_lo || vhi != wc.mask_hi) word = pack_skip(F0, F1, F2, V0, V1, V2, j, wc.k);
+            if (vlo != wc.mask_lo || (KHI && vhi != wc.mask_hi)) word = pack_skip(F0, F1, F2, V0, V1, V2, j, wc.k);
         }
         const unsigned bad = (inv16 >> j) & 1u;
-        const U64 h = siphash13_dev((unsigned)word, (unsigned)(word >> 32));
+        const U64 h = siphash13_dev((unsigned)word, (unsigned)(word >> 32), p.rm);
         const unsigned idx = fastmod_dev<POW2>(h, p.fm);
         if (EMIT) {
             if (!bad) {
@@ -136,6 +143,10 @@ __device__ __forceinline__ void process_chunk(const CountParams& p, const Window
                 if (p.out_idx) p.out_idx[pos] = idx;
             }
         } else {
+#ifdef NK_EXP_NORED
+            // diagnostic build only (tools/variants.sh): no pool update, keep the value alive
+            if (idx == 0xFFFFFFFFu) p.acc[0] = bad;
+#else
             // predicated RED.E.ADD (no divergence region around a single instruction)
             asm volatile(
                 "{\n\t.reg .pred q;\n\t"
@@ -143,12 +154,16 @@ __device__ __forceinline__ void process_chunk(const CountParams& p, const Window
                 "@q red.global.add.u32 [%0], %1;\n\t}" ::"l"(p.acc + idx),
                 "r"(1u), "r"(bad)
                 : "memory");
+#endif
         }
     }
 }
 
-template <bool CANON, bool EMIT, bool POW2>
-__global__ void __launch_bounds__(COUNT_THREADS, 2) count_kernel(const __grid_constant__ CountParams p) {
+#ifndef NK_COUNT_MINBLOCKS
+#define NK_COUNT_MINBLOCKS 2
+#endif
+template <bool CANON, bool EMIT, bool POW2, bool KHI>
+__global__ void __launch_bounds__(COUNT_THREADS, NK_COUNT_MINBLOCKS) count_kernel(const __grid_constant__ CountParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) unsigned long long bars[COUNT_STAGES];
     __shared__ unsigned long long tile_of[COUNT_STAGES];
@@ -186,7 +201,7 @@ __global__ void __launch_bounds__(COUNT_THREADS, 2) count_kernel(const __grid_co
             const Codes16 nxt = convert16<!CANON>(*reinterpret_cast<const uint4*>(lp + (c + 1u) * COUNT_CHUNK));
             const unsigned off = span0 + c * COUNT_CHUNK;
             const unsigned inv16 = bits[(off >> 4) + lane];
-            process_chunk<CANON, EMIT, POW2>(p, wc, cur, nxt, inv16, lane,
+            process_chunk<CANON, EMIT, POW2, KHI>(p, wc, cur, nxt, inv16, lane,
                                        tile * COUNT_TILE + off + 16u * lane);
             cur = nxt;
         }
@@ -246,32 +261,34 @@ __global__ void mark_tail_kernel(unsigned int* invalid, unsigned long long nbyte
 
 size_t count_smem_bytes() { return (size_t)kSmemTotal; }
 
-template <bool CANON, bool EMIT, bool POW2>
+template <bool CANON, bool EMIT, bool POW2, bool KHI>
 static cudaError_t launch_count_t(const CountParams& p, int grid, cudaStream_t s) {
-    cudaError_t e = cudaFuncSetAttribute(count_kernel<CANON, EMIT, POW2>,
+    cudaError_t e = cudaFuncSetAttribute(count_kernel<CANON, EMIT, POW2, KHI>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
     if (e != cudaSuccess) return e;
-    count_kernel<CANON, EMIT, POW2><<<grid, COUNT_THREADS, kSmemTotal, s>>>(p);
+    count_kernel<CANON, EMIT, POW2, KHI><<<grid, COUNT_THREADS, kSmemTotal, s>>>(p);
     return cudaGetLastError();
 }
 
+template <bool CANON, bool EMIT>
+static cudaError_t launch_count_ce(const CountParams& p, int grid, cudaStream_t s) {
+    const bool pow2 = p.fm.is_pow2 != 0, khi = p.k > 16;
+    if (pow2) return khi ? launch_count_t<CANON, EMIT, true, true>(p, grid, s) : launch_count_t<CANON, EMIT, true, false>(p, grid, s);
+    return khi ? launch_count_t<CANON, EMIT, false, true>(p, grid, s) : launch_count_t<CANON, EMIT, false, false>(p, grid, s);
+}
+
 cudaError_t launch_count(const CountParams& p, bool canonical, bool emit, int grid, cudaStream_t s) {
-    const bool pow2 = p.fm.is_pow2 != 0;
-    if (canonical) {
-        if (emit) return pow2 ? launch_count_t<true, true, true>(p, grid, s) : launch_count_t<true, true, false>(p, grid, s);
-        return pow2 ? launch_count_t<true, false, true>(p, grid, s) : launch_count_t<true, false, false>(p, grid, s);
-    }
-    if (emit) return pow2 ? launch_count_t<false, true, true>(p, grid, s) : launch_count_t<false, true, false>(p, grid, s);
-    return pow2 ? launch_count_t<false, false, true>(p, grid, s) : launch_count_t<false, false, false>(p, grid, s);
+    if (canonical) return emit ? launch_count_ce<true, true>(p, grid, s) : launch_count_ce<true, false>(p, grid, s);
+    return emit ? launch_count_ce<false, true>(p, grid, s) : launch_count_ce<false, false>(p, grid, s);
 }
 
 template <bool CANON>
 static cudaError_t max_grid_t(int sms, int* grid) {
     int per_sm = 0;
-    cudaError_t e = cudaFuncSetAttribute(count_kernel<CANON, false, false>,
+    cudaError_t e = cudaFuncSetAttribute(count_kernel<CANON, false, false, true>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
     if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, count_kernel<CANON, false, false>, COUNT_THREADS,
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, count_kernel<CANON, false, false, true>, COUNT_THREADS,
                                                       kSmemTotal);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;

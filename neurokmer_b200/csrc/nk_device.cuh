@@ -176,46 +176,96 @@ struct U64 {
     uint32_t lo, hi;
 };
 __device__ __forceinline__ U64 add64(U64 a, U64 b) {
-    const unsigned long long s = (((unsigned long long)a.hi << 32) | a.lo) + (((unsigned long long)b.hi << 32) | b.lo);
-    return U64{(uint32_t)s, (uint32_t)(s >> 32)};
-}
-template <int B>
-__device__ __forceinline__ U64 rotl_xor(U64 x, U64 y) {  // rotl64(x, B) ^ y, 0 < B < 32
-    return U64{__funnelshift_l(x.hi, x.lo, B) ^ y.lo, __funnelshift_l(x.lo, x.hi, B) ^ y.hi};
+    // low word: IADD3 with carry-out (ALU pipe); high word: multiply-add with carry-in, which
+    // ptxas emits as IMAD.X on the otherwise idle FMA pipe (the count kernel is ALU-pipe bound)
+    U64 r;
+    asm("add.cc.u32 %0, %2, %4;\n\tmadc.lo.u32 %1, %3, 1, %5;" : "=r"(r.lo), "=r"(r.hi) : "r"(a.lo), "r"(a.hi), "r"(b.lo), "r"(b.hi));
+    return r;
 }
 __device__ __forceinline__ U64 swap32(U64 x) { return U64{x.hi, x.lo}; }  // rotl64(x, 32)
 
-#define NK_SIPROUND32(v0, v1, v2, v3)             \
-    do {                                          \
-        v0 = add64(v0, v1); v1 = rotl_xor<13>(v1, v0); v0 = swap32(v0); \
-        v2 = add64(v2, v3); v3 = rotl_xor<16>(v3, v2);                  \
-        v0 = add64(v0, v3); v3 = rotl_xor<21>(v3, v0);                  \
-        v2 = add64(v2, v1); v1 = rotl_xor<17>(v1, v2); v2 = swap32(v2); \
+// Pipe balancing.  ncu (profiles/r01_count_kernel_ncu.md): the first version of the count
+// kernel ran the ALU pipe (LOP3/SHF/IADD3: 64 lanes/clk/SM) at 95 % while the FMA pipe
+// (IMAD: 64 lanes/clk/SM, issues concurrently — tools/microbench.cu) idled at 7 %.  A
+// 32-bit half of a 64-bit rotate is one SHF on the ALU pipe, or IMAD.HI + IMAD on the FMA
+// pipe:  (a << B) | (b >> (32-B))  ==  a * 2^B + mulhi(b, 2^B)   (the two terms share no bits).
+// IMAD.HI issues at half rate, so a moved half costs 3 FMA slots for 1 ALU slot saved;
+// kRotPlan moves as many halves as it takes to level the two pipes.  The multipliers come
+// from kernel parameters (RotMul) so that ptxas cannot strength-reduce them back to shifts.
+struct RotMul {
+    uint32_t m13, m16, m17, m21;  // 1 << 13, 1 << 16, 1 << 17, 1 << 21
+};
+__host__ __device__ __forceinline__ RotMul make_rotmul() { return RotMul{1u << 13, 1u << 16, 1u << 17, 1u << 21}; }
+
+template <int B>
+__device__ __forceinline__ uint32_t rot_mul(const RotMul& rm) {
+    return B == 13 ? rm.m13 : (B == 16 ? rm.m16 : (B == 17 ? rm.m17 : rm.m21));
+}
+// one 32-bit half of rotl64: (a << B) | (b >> (32-B))
+template <int B, bool FMA>
+__device__ __forceinline__ uint32_t rot_half(uint32_t a, uint32_t b, const RotMul& rm) {
+    if (FMA) return a * rot_mul<B>(rm) + __umulhi(b, rot_mul<B>(rm));
+    return __funnelshift_l(b, a, B);
+}
+// rotl64(x, B) ^ y;  MODE bit0: low half on the FMA pipe, bit1: high half on the FMA pipe
+template <int B, int MODE>
+__device__ __forceinline__ U64 rotl_xor(U64 x, U64 y, const RotMul& rm) {
+    return U64{rot_half<B, (MODE & 1) != 0>(x.lo, x.hi, rm) ^ y.lo, rot_half<B, (MODE & 2) != 0>(x.hi, x.lo, rm) ^ y.hi};
+}
+
+// modes of the 20 rotate-xor steps of one hash, in program order (4 per round; the first
+// round's first step is constant-folded).  NK_ROT_PLAN_ID selects how many rotate halves
+// run on the FMA pipe (tools/variants.sh measures them; DESIGN.md §5 has the table).
+#ifndef NK_ROT_PLAN_ID
+#define NK_ROT_PLAN_ID 0
+#endif
+#if NK_ROT_PLAN_ID == 0      /* all rotates on the ALU pipe (SHF.L.W) */
+#define NK_ROT_PLAN {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}
+#elif NK_ROT_PLAN_ID == 9
+#define NK_ROT_PLAN {0, 1, 0, 2, 0, 1, 0, 2, 0, 1, 0, 2, 0, 1, 0, 2, 0, 1, 0, 2}
+#elif NK_ROT_PLAN_ID == 13
+#define NK_ROT_PLAN {0, 1, 0, 3, 0, 1, 0, 3, 0, 1, 0, 3, 0, 1, 0, 3, 0, 1, 0, 3}
+#elif NK_ROT_PLAN_ID == 18
+#define NK_ROT_PLAN {0, 1, 2, 1, 2, 1, 2, 1, 2, 1, 2, 1, 2, 1, 2, 1, 2, 1, 2, 1}
+#elif NK_ROT_PLAN_ID == 27
+#define NK_ROT_PLAN {0, 3, 3, 1, 3, 1, 3, 2, 3, 1, 3, 2, 3, 1, 3, 2, 3, 1, 3, 2}
+#elif NK_ROT_PLAN_ID == 36
+#define NK_ROT_PLAN {3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3}
+#elif NK_ROT_PLAN_ID == 5
+#define NK_ROT_PLAN {0, 0, 0, 1, 0, 0, 0, 2, 0, 0, 0, 1, 0, 0, 0, 2, 0, 0, 0, 1}
+#endif
+__device__ constexpr int kRotPlan[20] = NK_ROT_PLAN;
+
+#define NK_SIPROUND32(v0, v1, v2, v3, R, rm)                                                   \
+    do {                                                                                       \
+        v0 = add64(v0, v1); v1 = rotl_xor<13, kRotPlan[(R)*4 + 0]>(v1, v0, rm); v0 = swap32(v0); \
+        v2 = add64(v2, v3); v3 = rotl_xor<16, kRotPlan[(R)*4 + 1]>(v3, v2, rm);                  \
+        v0 = add64(v0, v3); v3 = rotl_xor<21, kRotPlan[(R)*4 + 2]>(v3, v0, rm);                  \
+        v2 = add64(v2, v1); v1 = rotl_xor<17, kRotPlan[(R)*4 + 3]>(v1, v2, rm); v2 = swap32(v2); \
     } while (0)
 
-__device__ __forceinline__ U64 siphash13_dev(uint32_t mlo, uint32_t mhi) {
+__device__ __forceinline__ U64 siphash13_dev(uint32_t mlo, uint32_t mhi, const RotMul& rm) {
     U64 v0{0x70736575u, 0x736f6d65u};
     U64 v1{0x6e646f6du, 0x646f7261u};
     U64 v2{0x6e657261u, 0x6c796765u};
     U64 v3{0x79746573u ^ mlo, 0x74656462u ^ mhi};
-    NK_SIPROUND32(v0, v1, v2, v3);
+    NK_SIPROUND32(v0, v1, v2, v3, 0, rm);
     v0.lo ^= mlo; v0.hi ^= mhi;
     v3.hi ^= 0x08000000u;  // length block 8 << 56
-    NK_SIPROUND32(v0, v1, v2, v3);
+    NK_SIPROUND32(v0, v1, v2, v3, 1, rm);
     v0.hi ^= 0x08000000u;
     v2.lo ^= 0xffu;
-    NK_SIPROUND32(v0, v1, v2, v3);
-    NK_SIPROUND32(v0, v1, v2, v3);
+    NK_SIPROUND32(v0, v1, v2, v3, 2, rm);
+    NK_SIPROUND32(v0, v1, v2, v3, 3, rm);
     // last round: v0 ^ v3 collapses to rotl(v3, 21) (see siphash13_u64)
-    v0 = add64(v0, v1); v1 = rotl_xor<13>(v1, v0);
-    v2 = add64(v2, v3); v3 = rotl_xor<16>(v3, v2);
+    v0 = add64(v0, v1); v1 = rotl_xor<13, kRotPlan[16]>(v1, v0, rm);
+    v2 = add64(v2, v3); v3 = rotl_xor<16, kRotPlan[17]>(v3, v2, rm);
     v2 = add64(v2, v1);
     // rotl(v3,21) ^ rotl(v1,17) ^ v2 ^ rotl(v2,32)
     const uint32_t x = v2.lo ^ v2.hi;
-    U64 o;
-    o.lo = __funnelshift_l(v3.hi, v3.lo, 21) ^ __funnelshift_l(v1.hi, v1.lo, 17) ^ x;
-    o.hi = __funnelshift_l(v3.lo, v3.hi, 21) ^ __funnelshift_l(v1.lo, v1.hi, 17) ^ x;
-    return o;
+    const U64 z{x, x};
+    const U64 a = rotl_xor<21, kRotPlan[18]>(v3, z, rm);
+    return rotl_xor<17, kRotPlan[19]>(v1, a, rm);
 }
 
 __device__ __forceinline__ uint32_t rem_2by1_dev(uint32_t u1, uint32_t u0, uint32_t dn, uint32_t v) {

@@ -16,7 +16,10 @@ namespace nk {
 constexpr int COUNT_THREADS = 256;
 constexpr int COUNT_WARPS = COUNT_THREADS / 32;
 constexpr int COUNT_CHUNK = 512;                         // positions per warp iteration
-constexpr int COUNT_CHUNKS_PER_SPAN = 4;
+#ifndef NK_CHUNKS_PER_SPAN
+#define NK_CHUNKS_PER_SPAN 4
+#endif
+constexpr int COUNT_CHUNKS_PER_SPAN = NK_CHUNKS_PER_SPAN;
 constexpr int COUNT_SPAN = COUNT_CHUNK * COUNT_CHUNKS_PER_SPAN;
 constexpr int COUNT_TILE = COUNT_WARPS * COUNT_SPAN;     // 16384 positions
 constexpr int COUNT_HALO = 32;                           // >= k-1, multiple of 16
@@ -29,6 +32,7 @@ struct CountParams {
     unsigned int* tile_counter;   // dynamic tile scheduler cursor (zeroed before launch)
     unsigned long long ntiles;
     FastMod fm;
+    RotMul rm;                    // make_rotmul(): opaque 2^B multipliers (see nk_device.cuh)
     unsigned int k;
     // debug taps (EMIT instantiation only); any may be null
     unsigned long long* out_fwd;

@@ -9,11 +9,11 @@ namespace {
 // `hasher.finish()` and `idx` take at src/spiking_hash.rs:79-81.
 template <bool POW2>
 __global__ void hash_words_kernel(const unsigned long long* __restrict__ words, unsigned long long n, FastMod fm,
-                                  unsigned long long* hashes, unsigned long long* idx) {
+                                  RotMul rm, unsigned long long* hashes, unsigned long long* idx) {
     const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
     const unsigned long long w = words[i];
-    const U64 h = siphash13_dev((unsigned)w, (unsigned)(w >> 32));
+    const U64 h = siphash13_dev((unsigned)w, (unsigned)(w >> 32), rm);
     if (hashes) hashes[i] = ((unsigned long long)h.hi << 32) | h.lo;
     if (idx) idx[i] = fastmod_dev<POW2>(h, fm);
 }
@@ -55,7 +55,8 @@ __global__ void synth_kernel(unsigned char* out, unsigned long long seed, unsign
 // MODE 1: independent SipRound chains (add : xor : rotate = 1 : 1 : 1 on 64-bit words,
 //         24 32-bit ops per round) — the integer-pipe ceiling for SipHash's own mix
 template <int MODE>
-__global__ void __launch_bounds__(256) int_peak_kernel(unsigned int* out, unsigned iters, unsigned seed) {
+__global__ void __launch_bounds__(256) int_peak_kernel(unsigned int* out, unsigned iters, unsigned seed, RotMul rm) {
+    constexpr int PLANROW = 2;  // a middle round of the production plan (same pipe mix as the count kernel)
     constexpr int CH = 4;
     if (MODE == 0) {
         unsigned a[2 * CH];
@@ -89,7 +90,7 @@ __global__ void __launch_bounds__(256) int_peak_kernel(unsigned int* out, unsign
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
 #pragma unroll
-                for (int i = 0; i < CH; ++i) NK_SIPROUND32(v0[i], v1[i], v2[i], v3[i]);
+                for (int i = 0; i < CH; ++i) NK_SIPROUND32(v0[i], v1[i], v2[i], v3[i], PLANROW, rm);
             }
         }
         unsigned x = 0;
@@ -113,8 +114,8 @@ __global__ void __launch_bounds__(256) red_peak_kernel(unsigned int* acc, FastMo
 }  // namespace
 
 cudaError_t launch_int_peak(int mode, unsigned int* out, int blocks, unsigned iters, cudaStream_t s) {
-    if (mode == 0) int_peak_kernel<0><<<blocks, 256, 0, s>>>(out, iters, 17u);
-    else int_peak_kernel<1><<<blocks, 256, 0, s>>>(out, iters, 17u);
+    if (mode == 0) int_peak_kernel<0><<<blocks, 256, 0, s>>>(out, iters, 17u, make_rotmul());
+    else int_peak_kernel<1><<<blocks, 256, 0, s>>>(out, iters, 17u, make_rotmul());
     return cudaGetLastError();
 }
 // 32-bit integer ops one thread executes per `iters` unit in launch_int_peak
@@ -130,9 +131,9 @@ cudaError_t launch_hash_words(const unsigned long long* words, unsigned long lon
     if (n == 0) return cudaSuccess;
     const unsigned blocks = (unsigned)((n + 255) / 256);
     if (fm.is_pow2)
-        hash_words_kernel<true><<<blocks, 256, 0, s>>>(words, n, fm, hashes, idx);
+        hash_words_kernel<true><<<blocks, 256, 0, s>>>(words, n, fm, make_rotmul(), hashes, idx);
     else
-        hash_words_kernel<false><<<blocks, 256, 0, s>>>(words, n, fm, hashes, idx);
+        hash_words_kernel<false><<<blocks, 256, 0, s>>>(words, n, fm, make_rotmul(), hashes, idx);
     return cudaGetLastError();
 }
 

@@ -1,0 +1,116 @@
+"""CPU tests of the drop-in boundary: the shared library loads, exports exactly the symbols
+include/neurokmer.h declares, and the ctypes struct layouts match the C ones.  No compute calls."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HDR = os.path.join(ROOT, "include", "neurokmer.h")
+
+
+@pytest.fixture(scope="module")
+def built():
+    import __graft_entry__
+    __graft_entry__.build()
+    from neurokmer_b200 import _lib
+    return _lib
+
+
+def header_symbols():
+    txt = open(HDR).read()
+    return sorted(set(re.findall(r"NK_API\s+[\w\s\*]+?\b(nk_\w+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol(built):
+    declared = header_symbols()
+    assert len(declared) >= 35
+    assert sorted(built.SYMBOLS) == declared
+    out = subprocess.check_output(["nm", "-D", "--defined-only", built.LIB_PATH], text=True)
+    exported = sorted(set(re.findall(r"\sT\s+(nk_\w+)", out)))
+    assert exported == declared
+    lib = built.lib()
+    assert lib.nk_version().startswith(b"neurokmer-b200")
+
+
+def test_struct_layouts_match_c(built, tmp_path):
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "neurokmer.h"\nint main(){'
+                   'printf("%zu %zu %zu\\n", sizeof(nk_config), sizeof(nk_top_entry), sizeof(nk_timings));'
+                   'printf("%zu %zu %zu %zu\\n", offsetof(nk_config,pool_size), offsetof(nk_config,spike_cost), offsetof(nk_config,threshold), offsetof(nk_config,device));'
+                   'printf("%zu %zu %zu %zu\\n", offsetof(nk_timings,kmers), offsetof(nk_timings,h2d_bytes), offsetof(nk_timings,lif_path), offsetof(nk_timings,topn_launches));'
+                   'return 0;}')
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    rows = [list(map(int, l.split())) for l in subprocess.check_output([str(exe)], text=True).splitlines()]
+    L = built
+    assert rows[0] == [C.sizeof(L.NkConfig), C.sizeof(L.NkTopEntry), C.sizeof(L.NkTimings)]
+    assert rows[1] == [L.NkConfig.pool_size.offset, L.NkConfig.spike_cost.offset, L.NkConfig.threshold.offset, L.NkConfig.device.offset]
+    assert rows[2] == [L.NkTimings.kmers.offset, L.NkTimings.h2d_bytes.offset, L.NkTimings.lif_path.offset, L.NkTimings.topn_launches.offset]
+
+
+def test_host_only_entry_points(built):
+    """Entry points that need no device: defaults, pack_kmer, argument validation, error strings."""
+    lib = built.lib()
+    cfg = built.NkConfig()
+    assert lib.nk_config_default(C.byref(cfg)) == 0
+    # reference CLI defaults (src/main.rs:10-37, src/spiking_hash.rs:70)
+    assert (cfg.k, cfg.pool_size, cfg.use_canonical, cfg.refractory, cfg.steps) == (31, 1_000_000, 0, 2, 1000)
+    assert (cfg.threshold, round(cfg.leak, 6), cfg.spike_cost) == (1.0, 0.95, 1.0)
+    from neurokmer_b200 import pack_kmer, pack_kmer_py
+    from oracle import oracle_py as op
+    for s in (b"", b"A", b"ACGT", b"ACGTN", b"nnacgtNN", b"T" * 32, b"GATTACA-GATTACA"):
+        assert pack_kmer(s) == op.pack_kmer(s) == pack_kmer_py(s)
+    h = C.c_void_p()
+    for bad_k in (0, 33):
+        cfg.k = bad_k
+        assert lib.nk_create(C.byref(cfg), C.byref(h)) == built.NK_ERR_BAD_ARG
+        assert b"k must be in [1,32]" in lib.nk_last_error()
+    cfg.k, cfg.pool_size = 31, 0
+    assert lib.nk_create(C.byref(cfg), C.byref(h)) == built.NK_ERR_BAD_ARG
+    cfg.pool_size = 1 << 32
+    assert lib.nk_create(C.byref(cfg), C.byref(h)) == built.NK_ERR_UNSUPPORTED
+    assert lib.nk_destroy(None) == 0 and lib.nk_reset(None) == built.NK_ERR_BAD_ARG
+
+
+def test_no_cpu_fallback_without_device(built):
+    """Without a usable sm_100 device the product path must fail loudly, not compute on the CPU."""
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        pytest.skip("a GPU is present")
+    from neurokmer_b200 import NkError, SpikingKmerCounter
+    with pytest.raises(NkError) as ei:
+        SpikingKmerCounter(31, 1.0, 0.95, 2, 1.0, 1000, True)
+    assert ei.value.code == built.NK_ERR_NO_DEVICE
+    assert "no CPU fallback" in str(ei.value)
+
+
+def test_product_does_not_touch_the_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py's cpu/reference legs may use oracle/."""
+    pkg = os.path.join(ROOT, "neurokmer_b200")
+    for dirpath, _, files in os.walk(pkg):
+        if "build" in dirpath.split(os.sep):
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                txt = open(os.path.join(dirpath, f), errors="replace").read()
+                for needle in ("import oracle", "from oracle", "libnk_oracle", "nko_", "oracle_py", "nk_oracle"):
+                    assert needle not in txt, (os.path.join(dirpath, f), needle)
+
+
+def test_fastx_python_reader_matches_rules(tmp_path):
+    from neurokmer_b200.fastx import read_fastx, write_fasta, write_fastq
+    seqs = [b"ACGT" * 40, b"", b"NNNN", b"acgtn"]
+    fa, fq = str(tmp_path / "a.fa"), str(tmp_path / "a.fq")
+    write_fasta(fa, seqs); write_fastq(fq, seqs)
+    assert list(read_fastx(fa)) == seqs and list(read_fastx(fq)) == seqs
+    with open(fq, "ab") as f:
+        f.write(b"@bad\nACGT\n+\nII\n@after\nAC\n+\nII\n")
+    assert list(read_fastx(fq)) == seqs  # stops at the malformed record (utils.rs:17-20)

@@ -403,3 +403,147 @@ def test_staged_synthetic_matches_host_path(coracle):
     assert_state_equal(c, o)
     t = c.timings()
     assert t["kmers"] == sum(l - k + 1 for l in lens) and t["count_ms"] > 0 and t["launches"] >= 4
+
+
+# --- committed golden fixtures + generator twin ---------------------------------------------------
+def test_golden_fixture_gpu():
+    """tests/golden/golden_small.json (made by tests/golden/make_golden.py from the pure-Python
+    restatement) against the CUDA path: words, fwd/rc, indices, currents, LIF end states, top-N."""
+    import json
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_small.json")))
+    for case in g["cases"]:
+        k, pool, canon = case["k"], case["pool"], case["canonical"]
+        c = make(k, pool, canon)
+        seqs = [s.encode("latin1") for s in case["seqs"]]
+        for si, s in enumerate(seqs):
+            fwd, rc, words, idx = c.debug_kmers(s)
+            assert words.tolist() == case["words"][si] and idx.tolist() == case["idx"][si]
+            if canon:
+                assert fwd.tolist() == case["fwd"][si] and rc.tolist() == case["rc"][si]
+        c.process_parallel(seqs)
+        cur = c.currents()
+        nz = np.nonzero(cur)[0]
+        assert [[int(i), int(cur[i])] for i in nz] == [list(x) for x in case["currents"]]
+        c.close()
+    c = make(31, 2_000_000)
+    hs, _ = c.debug_hash(np.array([int(x) for x in g["siphash13"]], np.uint64))
+    assert hs.tolist() == list(g["siphash13"].values())
+
+
+def test_lif_golden_rows_gpu():
+    """LIF end states (spikes, voltage bits, refractory) per count from the golden file, through
+    both GPU paths (per-count table and direct simulation), and the carried-state rows."""
+    import json
+    from neurokmer_b200.devmem import copy_h2d
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_small.json")))
+    for blk in g["lif"]:
+        counts = np.array([r[0] for r in blk["rows"]], np.uint64)
+        for force_direct in (0, 1):
+            c = make(31, counts.size, threshold=blk["threshold"], leak=blk["leak"], refractory=blk["refractory"])
+            c.set_steps(blk["steps"])
+            c.debug_set_lif_path(force_direct)
+            c.stream_begin()
+            ptr = c.stream_accumulated()       # device currents: inject the golden counts
+            copy_h2d(ptr, counts)
+            c.stream_finish()
+            assert c.timings()["lif_path"] == (1 if force_direct else 2)
+            assert c.spike_counts().tolist() == [r[1] for r in blk["rows"]]
+            assert c.voltages().view(np.uint32).tolist() == [r[2] for r in blk["rows"]]
+            assert c.refractory_ticks().tolist() == [r[3] for r in blk["rows"]]
+            c.close()
+    rows = g["lif_carried"]
+    c = make(31, len(rows))
+    for col in (0, 1):
+        c.stream_begin()
+        copy_h2d(c.stream_accumulated(), np.array([r[col] for r in rows], np.uint64))
+        c.stream_finish()
+        if col == 0:
+            assert c.spike_counts().tolist() == [r[2] for r in rows]
+    assert c.spike_counts().tolist() == [r[2] + r[3] for r in rows]
+    assert c.voltages().view(np.uint32).tolist() == [r[4] for r in rows]
+    assert c.refractory_ticks().tolist() == [r[5] for r in rows]
+    t = g["topn"]
+    c = make(31, len(t["spikes"]))
+
+
+def test_synth_generator_matches_numpy_twin():
+    from neurokmer_b200.devmem import device_to_numpy
+    from oracle.synth import synth_bases
+    c = make(31, 1000)
+    n = 3_000_000
+    db, _ = c.stage_reserve(n, 1)
+    for seed, start, flags in [(2, 0, 3), (5, 10**10 + 7, 3), (1, 123, 0), (4, 1 << 33, 1)]:
+        c.synth_fill(db, seed, start, n, flags)
+        c.synchronize()
+        np.testing.assert_array_equal(device_to_numpy(db, n), synth_bases(seed, start, n, flags))
+
+
+# --- full-size property checks (BASELINE configs at their own sizes, no oracle pass needed) ------
+def test_config1_full_size_properties(coracle):
+    """configs[0]: 10 Mbp random ACGT, k=21, pool 1M, canonical, in-memory: checksum of currents
+    = number of windows; result identical through the host path, the staged path and 3 pushes;
+    the oracle (fast enough at this size) agrees bit for bit."""
+    from neurokmer_b200.devmem import copy_h2d
+    from oracle.synth import synth_bases
+    n, k, pool = 10_000_000, 21, 1_000_000
+    bases = synth_bases(1, 0, n, 0)
+    offsets = np.array([0, n], np.uint64)
+    a = make(k, pool); a.process_batch(bases, offsets)
+    cur = a.currents()
+    assert int(cur.sum()) == n - k + 1 == a.timings()["kmers"]
+    b = make(k, pool)
+    db, do = b.stage_reserve(n, 1)
+    b.synth_fill(db, 1, 0, n, 0); copy_h2d(do, offsets); b.synchronize()
+    b.process_staged(n, 1, 0)
+    np.testing.assert_array_equal(b.currents(), cur)
+    np.testing.assert_array_equal(b.spike_counts(), a.spike_counts())
+    # streaming in 3 pieces that overlap by k-1 bases == one batch
+    s = make(k, pool); s.stream_begin()
+    cuts = [0, 3_333_333, 7_000_001, n]
+    for i in range(3):
+        lo, hi = cuts[i], min(n, cuts[i + 1] + k - 1)
+        s.stream_push(bases[lo:hi], np.array([0, hi - lo], np.uint64))
+    s.stream_end()
+    np.testing.assert_array_equal(s.currents(), cur)
+    exp, tot = coracle.accumulate(bases, offsets, k, pool, True, threads=8)
+    np.testing.assert_array_equal(cur, exp)
+    o = oracle_counter(k, pool); o.process_parallel(bases, offsets)
+    assert_state_equal(a, o); assert_topn_equal(a, o, 20)
+
+
+def test_config4_contention_properties():
+    """configs[3] shape (k=15, pool 65,536 = power of two, heavy collisions) at 200 Mbp on device:
+    Σ currents = windows; every neuron saturates at ceil(1000/3) = 334 spikes; the tie rule makes
+    the top-20 neurons 0..19."""
+    from neurokmer_b200.devmem import copy_h2d
+    n, k, pool = 200_000_000, 15, 65536
+    c = make(k, pool)
+    db, do = c.stage_reserve(n, 1)
+    c.synth_fill(db, 4, 0, n, 0); copy_h2d(do, np.array([0, n], np.uint64)); c.synchronize()
+    c.process_staged(n, 1, 0)
+    cur = c.currents()
+    assert int(cur.sum()) == n - k + 1 and cur.min() >= 1000
+    assert set(c.spike_counts().tolist()) == {334}
+    assert c.energy.total_spikes() == 334 * pool
+    assert [t[0] for t in c.top_abundant_neurons(20)] == list(range(20))
+
+
+def test_config3_reads_properties(coracle):
+    """configs[2] shape: 150 bp reads (here 2 M reads = 300 Mbp), 1 % with an N, 0.1 % shorter than k:
+    Σ currents = Σ max(0, L-k+1); a 100k-read sample agrees with the oracle bit for bit."""
+    rng = np.random.default_rng(3)
+    nreads, k, pool = 2_000_000, 31, 2_000_000
+    lens = np.full(nreads, 150, np.int64)
+    lens[rng.random(nreads) < 0.001] = 20
+    offsets = np.zeros(nreads + 1, np.uint64); offsets[1:] = np.cumsum(lens)
+    from oracle.synth import synth_bases
+    bases = synth_bases(3, 0, int(offsets[-1]), 0)
+    hit = rng.random(nreads) < 0.01
+    bases[(offsets[:-1][hit] + rng.integers(0, 20, size=int(hit.sum())).astype(np.uint64)).astype(np.int64)] = ord("N")
+    c = make(k, pool); c.process_batch(bases, offsets)
+    want = int(np.maximum(lens - k + 1, 0).sum())
+    assert int(c.currents().sum()) == want == c.timings()["kmers"]
+    m = 100_000
+    s = make(k, pool); s.process_batch(bases[: int(offsets[m])], offsets[: m + 1])
+    exp, _ = coracle.accumulate(bases[: int(offsets[m])], offsets[: m + 1], k, pool, True, threads=8)
+    np.testing.assert_array_equal(s.currents(), exp)

@@ -191,7 +191,10 @@ def gpu_arm(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    os.environ["NCCL_DEBUG"] = os.environ.get("NK_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
     torch.cuda.set_device(local)
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)  # NCCL prints a version banner to stdout: keep stdout to the one JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     c = SpikingKmerCounter(K, LIF_REF["threshold"], LIF_REF["leak"], LIF_REF["refractory"], LIF_REF["spike_cost"],
@@ -210,20 +213,33 @@ def gpu_arm(args):
     pinned.array[:] = device_to_numpy(dev_bases, NBASES)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
+    cur_view = {}
+    ar_events = []
+
     def allreduce_currents():
         ptr = c.stream_accumulated()
         if world > 1:
-            t = torch.as_tensor(CurrentsView(ptr, POOL), device=torch.device("cuda", local))
+            if ptr not in cur_view:  # the library's currents buffer never moves: wrap it once
+                cur_view[ptr] = torch.as_tensor(CurrentsView(ptr, POOL), device=torch.device("cuda", local))
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             with torch.cuda.stream(stream):
-                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+                a0.record(stream)
+                dist.all_reduce(cur_view[ptr], op=dist.ReduceOp.SUM)
+                a1.record(stream)
+            ar_events.append((a0, a1))
+
+    trace = []
 
     def job_resident():
-        c.reset()
-        c.stream_begin()
-        c.process_staged(NBASES, nseq, 1)
-        allreduce_currents()
-        c.stream_finish()
-        return c.top_abundant_neurons(TOPN)
+        t = [time.perf_counter()]
+        c.reset(); t.append(time.perf_counter())
+        c.stream_begin(); t.append(time.perf_counter())
+        c.process_staged(NBASES, nseq, 1); t.append(time.perf_counter())
+        allreduce_currents(); t.append(time.perf_counter())
+        c.stream_finish(); t.append(time.perf_counter())
+        top = c.top_abundant_neurons(TOPN); t.append(time.perf_counter())
+        trace.append(np.diff(t) * 1e3)
+        return top
 
     def job_e2e():
         c.reset()
@@ -240,10 +256,10 @@ def gpu_arm(args):
         torch.cuda.synchronize()
 
     def timed(job, nsteps, sampler=None):
-        per_step, phases, ar_ms = [], [], []
-        barrier()
+        per_step, phases = [], []
         if sampler:
-            sampler.start()
+            sampler.start()  # before the barrier: nvidia-smi needs ~0.3 s to emit its first row
+        barrier()
         for _ in range(nsteps):
             with torch.cuda.stream(stream):
                 flush.fill_(1)  # evict the input and the pool from L2 (untimed)
@@ -267,11 +283,17 @@ def gpu_arm(args):
     W = max(args.warmup, 3)
     timed(job_resident, W)
     sampler = ClockSampler(local) if rank == 0 else None
+    ar_events.clear()
     steps_res, phases, top, clocks = timed(job_resident, args.steps, sampler)
+    ar_ms = float(np.mean([a.elapsed_time(b) for a, b in ar_events])) if ar_events else 0.0
     timed(job_e2e, 2)
     steps_e2e, phases_e2e, top_e2e, _ = timed(job_e2e, args.steps)
     assert top == top_e2e or world > 1, "resident and end-to-end legs disagree"
 
+    if os.environ.get("NK_TRACE"):
+        print(f"[rank {rank}] per-step (event ms, wall ms):", [(round(a, 3), round(b, 3)) for a, b in steps_res[:12]], file=sys.stderr)
+        print(f"[rank {rank}] host ms per call (reset, begin, staged, accumulate+allreduce, finish, topn):",
+              np.round(np.mean(trace[-args.steps:], axis=0), 3), file=sys.stderr)
     total_spikes = c.energy.total_spikes()
     dev_ms = float(sum(s[0] for s in steps_res))
     e2e_ms = float(sum(s[1] for s in steps_e2e))
@@ -333,11 +355,13 @@ def gpu_arm(args):
                     "h2d_bytes_per_step": int(phases_e2e[-1]["h2d_bytes"]),
                     "d2h_bytes_per_step": int(phases_e2e[-1]["d2h_bytes"] + 24 + 16 * TOPN)},
             "gpu_launches": launches * args.steps,
-            "phases_ms": ph, "lif_path": int(phases[-1]["lif_path"]),
+            "phases_ms": ph, "allreduce_ms": ar_ms, "lif_path": int(phases[-1]["lif_path"]),
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "result": {"total_spikes": total_spikes, "top1": list(top[0][:2]) if top else None},
         }
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -20,7 +20,8 @@ SYMBOLS = [
     "nk_config_default", "nk_create", "nk_destroy", "nk_reset", "nk_last_error", "nk_version",
     "nk_set_steps", "nk_get_steps", "nk_process_batch", "nk_stream_begin", "nk_stream_push",
     "nk_stream_end", "nk_process_file", "nk_process_sequence", "nk_simulate", "nk_top_n",
-    "nk_total_spikes", "nk_energy_used", "nk_get_count", "nk_debug_kmers", "nk_debug_hash",
+    "nk_total_spikes", "nk_energy_used", "nk_enable_exact_counts", "nk_get_count", "nk_exact_table_size",
+    "nk_copy_exact_table", "nk_copy_uniques", "nk_debug_kmers", "nk_debug_hash",
     "nk_copy_currents", "nk_copy_spike_counts", "nk_copy_voltages", "nk_copy_refractory",
     "nk_last_timings", "nk_debug_set_lif_path", "nk_calibrate", "nk_stage_reserve", "nk_process_staged", "nk_stream_accumulated",
     "nk_stream_finish", "nk_cuda_stream", "nk_synchronize", "nk_synth_fill", "nk_host_alloc",
@@ -85,7 +86,11 @@ def load() -> C.CDLL:
         "nk_top_n": (i32, [vp, u64, P(NkTopEntry), P(u64)]),
         "nk_total_spikes": (i32, [vp, P(u64)]),
         "nk_energy_used": (i32, [vp, P(C.c_double)]),
+        "nk_enable_exact_counts": (i32, [vp, i32]),
         "nk_get_count": (i32, [vp, u64, P(u32), P(C.c_int32)]),
+        "nk_exact_table_size": (i32, [vp, P(u64)]),
+        "nk_copy_exact_table": (i32, [vp, vp, vp]),
+        "nk_copy_uniques": (i32, [vp, vp]),
         "nk_debug_kmers": (i32, [vp, vp, u64, vp, vp, vp, vp, P(u64)]),
         "nk_debug_hash": (i32, [vp, vp, u64, vp, vp]),
         "nk_copy_currents": (i32, [vp, vp]),

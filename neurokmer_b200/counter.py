@@ -156,6 +156,21 @@ class SpikingKmerCounter:
         return [(int(e.idx), int(e.spikes), None if e.uniques == _lib.NK_UNIQUES_NOT_COMPUTED else int(e.uniques))
                 for e in out[: got.value]]
 
+    def enable_exact_counts(self, on: bool = True) -> None:
+        """Build the reference's `counts` / `kmer_per_neuron` side tables (off by default)."""
+        check(self._L.nk_enable_exact_counts(self._h, int(on)))
+
+    def exact_table(self) -> Tuple[np.ndarray, np.ndarray]:
+        """(sorted k-mer words, counts) — the reference's `counts` map."""
+        n = C.c_uint64()
+        check(self._L.nk_exact_table_size(self._h, C.byref(n)))
+        keys, counts = np.zeros(max(n.value, 1), np.uint64), np.zeros(max(n.value, 1), np.uint32)
+        check(self._L.nk_copy_exact_table(self._h, keys.ctypes.data, counts.ctypes.data))
+        return keys[: n.value], counts[: n.value]
+
+    def kmer_per_neuron(self) -> np.ndarray:
+        return self._copy(self._L.nk_copy_uniques, np.uint32)
+
     def get_count(self, kmer: int) -> Optional[int]:
         """src/spiking_hash.rs:675-678"""
         cnt, found = C.c_uint32(), C.c_int32()
@@ -268,6 +283,7 @@ class PySpikingCounter:
 
     def __init__(self, k: int, pool_size: int):
         self._c = SpikingKmerCounter(k, 1.0, 0.95, 2, 1.0, pool_size, False)
+        self._c.enable_exact_counts(True)  # get_counts() walks the exact table
 
     def process_file(self, path: str) -> None:
         # python.rs:21-28 feeds every record to process_sequence, in file order
@@ -276,8 +292,9 @@ class PySpikingCounter:
             self._c.process_sequence(seq)
 
     def get_counts(self) -> dict:
-        # python.rs:31-40 walks the exact side table, which is not built yet
-        raise _lib.NkError(_lib.NK_ERR_UNSUPPORTED, "exact k-mer side table (SURVEY §8 f1) is not built yet")
+        # python.rs:31-40: {key.to_string(): count}
+        keys, counts = self._c.exact_table()
+        return {str(int(k)): int(c) for k, c in zip(keys, counts)}
 
     def energy_used(self) -> float:
         return self._c.energy_used()

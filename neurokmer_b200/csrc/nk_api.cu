@@ -55,6 +55,12 @@ struct DevBuf {
     cudaEvent_t copy_done = nullptr, compute_done = nullptr;
 };
 
+struct PhaseEvents {
+    std::vector<cudaEvent_t> mark0, count0, count1;
+    cudaEvent_t begin = nullptr, copy0 = nullptr, copy1 = nullptr, fold0 = nullptr, fold1 = nullptr,
+                lif1 = nullptr, end = nullptr;
+};
+
 }  // namespace
 
 struct nk_counter {
@@ -104,6 +110,22 @@ struct nk_counter {
     std::vector<cudaEvent_t> evpool;
     size_t ev_used = 0;
     nk_timings last{};
+
+    // a process/stream call returns with its read-back (new spikes, k-mers) and event timings
+    // still in flight on `stream`; resolve() waits for them the first time anything observes them
+    bool pending = false, pending_lif = false, pending_timings = false;
+    PhaseEvents pend_pe;
+    PhaseEvents stream_pe;  // mark/count event pairs of the pushes between stream_begin and stream_finish
+    // host-side upper bound of the largest cumulative spike count (bounds the top-N radix passes
+    // without a device round trip): each LIF call adds at most ceil(steps / (refractory + 1))
+    unsigned long long spike_bound = 0;
+    // exact side tables (opt-in, nk_enable_exact_counts)
+    bool exact = false;
+    nk::ExactTable xt;
+    unsigned int* d_top_uniques = nullptr;
+    bool table_valid = false;
+    nk_config table_cfg{};
+    unsigned long long table_n = 0;
 };
 
 namespace {
@@ -152,12 +174,6 @@ int ensure_offsets(unsigned long long** p, unsigned long long* cap, unsigned lon
     return NK_OK;
 }
 
-struct PhaseEvents {
-    std::vector<cudaEvent_t> mark0, count0, count1;
-    cudaEvent_t begin = nullptr, copy0 = nullptr, copy1 = nullptr, fold0 = nullptr, fold1 = nullptr,
-                lif1 = nullptr, end = nullptr;
-};
-
 // fold acc into currents if a further `incoming` windows could overflow a u32 accumulator
 int fold_now(nk_counter* h) {
     if (!h->acc_dirty) return NK_OK;
@@ -197,8 +213,13 @@ int count_chunk(nk_counter* h, DevBuf& b, const unsigned long long* d_offsets, u
     p.fm = h->fm;
     p.rm = nk::make_rotmul();
     p.k = h->cfg.k;
+    if (h->exact) {
+        NK_CUDA(nk::exact_reserve_words(h->xt, nstarts, h->stream));
+        p.words = h->xt.words;
+        p.words_cursor = h->xt.cursor;
+    }
     const unsigned long long want = p.ntiles < (unsigned long long)h->grid ? p.ntiles : (unsigned long long)h->grid;
-    NK_CUDA(nk::launch_count(p, h->cfg.use_canonical != 0, false, (int)want, h->stream));
+    NK_CUDA(nk::launch_count(p, h->cfg.use_canonical != 0, h->exact ? 2 : 0, (int)want, h->stream));
     ++h->last.launches;
     if (pe) {
         NK_CUDA(cudaEventRecord(e2, h->stream));
@@ -277,12 +298,18 @@ unsigned long long saturation_count(const nk_config& c) {
     return hi;
 }
 
-// LIF over the stored currents; skip_zero: in-memory driver (:187-200) vs SIMD driver (:544-659)
+// LIF over this call's totals; skip_zero: in-memory driver (:187-200) vs SIMD driver (:544-659).
+// If the u32 batch accumulators still hold counts they are folded into `currents` by the LIF
+// kernel itself (fold_mode), otherwise the stored currents are used as they are.
 int simulate(nk_counter* h, bool skip_zero) {
     h->last.lif_path = 0;
-    if (h->cfg.steps == 0 || h->cfg.pool_size == 0) return NK_OK;
+    int fold_mode = 0;
+    if (h->acc_dirty) fold_mode = h->currents_valid_overwrite ? 2 : 1;
+    if (h->cfg.steps == 0 || h->cfg.pool_size == 0) return fold_now(h);
     nk::LifParams p{};
     p.currents = h->currents;
+    p.acc = h->acc;
+    p.fold_mode = fold_mode;
     p.v = h->v;
     p.r = h->r;
     p.spikes = h->spikes;
@@ -302,41 +329,43 @@ int simulate(nk_counter* h, bool skip_zero) {
         if (sat < (1ull << 20)) { use_table = true; table_n = sat + 1; }
     }
     if (use_table) {
-        if (table_n > h->table_cap) {
-            if (h->table.spikes) cudaFree(h->table.spikes);
-            if (h->table.v) cudaFree(h->table.v);
-            if (h->table.r) cudaFree(h->table.r);
-            h->table = nk::LifTable{};
-            h->table_cap = 0;
-            NK_CUDA(cudaMalloc(&h->table.spikes, table_n * sizeof(unsigned int)));
-            NK_CUDA(cudaMalloc(&h->table.v, table_n * sizeof(float)));
-            NK_CUDA(cudaMalloc(&h->table.r, table_n * sizeof(unsigned int)));
-            h->table_cap = table_n;
+        const nk_config& a = h->cfg; const nk_config& b = h->table_cfg;
+        const bool same = h->table_valid && h->table_n == table_n && a.steps == b.steps && a.threshold == b.threshold &&
+                          a.leak == b.leak && a.refractory == b.refractory;
+        if (!same) {  // the table depends on the LIF parameters only: built once, reused by every job
+            if (table_n > h->table_cap) {
+                if (h->table.spikes) cudaFree(h->table.spikes);
+                if (h->table.v) cudaFree(h->table.v);
+                if (h->table.r) cudaFree(h->table.r);
+                h->table = nk::LifTable{};
+                h->table_cap = 0;
+                NK_CUDA(cudaMalloc(&h->table.spikes, table_n * sizeof(unsigned int)));
+                NK_CUDA(cudaMalloc(&h->table.v, table_n * sizeof(float)));
+                NK_CUDA(cudaMalloc(&h->table.r, table_n * sizeof(unsigned int)));
+                h->table_cap = table_n;
+            }
+            NK_CUDA(nk::launch_lif_table_build(p, h->table, table_n, h->stream));
+            ++h->last.launches;
+            h->table_valid = true;
+            h->table_cfg = h->cfg;
+            h->table_n = table_n;
         }
-        NK_CUDA(nk::launch_lif_table(p, h->table, table_n, h->stream));
-        h->last.launches += 2;
+        NK_CUDA(nk::launch_lif_table_apply(p, h->table, table_n, h->stream));
+        ++h->last.launches;
         h->last.lif_path = 2;
     } else {
         NK_CUDA(nk::launch_lif(p, h->stream));
-        h->last.launches += 1;
+        ++h->last.launches;
         h->last.lif_path = 1;
     }
-    h->fresh = false;
-    return NK_OK;
-}
-
-// read back {new spikes, max spikes, kmers}; update EnergyTracker mirrors
-int finish_call(nk_counter* h, bool had_lif) {
-    NK_CUDA(cudaMemcpyAsync(h->h_scalars, h->scalars, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
-    NK_CUDA(cudaStreamSynchronize(h->stream));
-    h->last.d2h_bytes += 3 * sizeof(unsigned long long);
-    if (had_lif) {
-        const unsigned long long fired = h->h_scalars[0];
-        h->total_spikes += fired;
-        // src/models.rs:162-163 / src/spiking_hash.rs:649-655
-        h->energy_fixed += fired * (unsigned long long)(h->cfg.spike_cost * 1000.0);
+    if (fold_mode) {
+        h->acc_dirty = false;
+        h->acc_kmers = 0;
+        h->currents_valid_overwrite = false;
     }
-    h->last.kmers = h->h_scalars[2];
+    h->fresh = false;
+    const unsigned long long per_call = (h->cfg.steps + h->cfg.refractory) / ((unsigned long long)h->cfg.refractory + 1ull);
+    h->spike_bound = (h->spike_bound + per_call < h->spike_bound) ? ~0ull : h->spike_bound + per_call;
     return NK_OK;
 }
 
@@ -352,15 +381,45 @@ void collect_timings(nk_counter* h, const PhaseEvents& pe) {
         mark += ev_ms(pe.mark0[i], pe.count0[i]);
         cnt += ev_ms(pe.count0[i], pe.count1[i]);
     }
-    h->last.h2d_ms = ev_ms(pe.copy0, pe.copy1);
-    h->last.mark_ms = mark;
-    h->last.count_ms = cnt;
-    h->last.fold_ms = ev_ms(pe.fold0, pe.fold1);
-    h->last.lif_ms = ev_ms(pe.fold1, pe.lif1);
-    h->last.total_ms = ev_ms(pe.begin, pe.end);
+    if (pe.copy0) h->last.h2d_ms = ev_ms(pe.copy0, pe.copy1);
+    h->last.mark_ms += mark;
+    h->last.count_ms += cnt;
+    if (pe.fold0) h->last.fold_ms = ev_ms(pe.fold0, pe.fold1);
+    if (pe.fold1) h->last.lif_ms = ev_ms(pe.fold1, pe.lif1);
+    if (pe.begin) h->last.total_ms = ev_ms(pe.begin, pe.end);
+}
+
+// enqueue the read-back of {new spikes, max spikes, kmers}; nothing waits here
+int finish_call(nk_counter* h, bool had_lif, const PhaseEvents* pe) {
+    NK_CUDA(cudaMemcpyAsync(h->h_scalars, h->scalars, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    h->last.d2h_bytes += 3 * sizeof(unsigned long long);
+    h->pending = true;
+    h->pending_lif = had_lif;
+    h->pending_timings = pe != nullptr;
+    if (pe) h->pend_pe = *pe;
+    return NK_OK;
+}
+
+// wait for the in-flight read-back (if any) and fold it into the EnergyTracker mirrors
+int resolve(nk_counter* h) {
+    if (!h->pending) return NK_OK;
+    NK_CUDA(cudaSetDevice(h->cfg.device));
+    NK_CUDA(cudaStreamSynchronize(h->stream));
+    h->pending = false;
+    if (h->pending_lif) {
+        const unsigned long long fired = h->h_scalars[0];
+        h->total_spikes += fired;
+        // src/models.rs:162-163 / src/spiking_hash.rs:649-655
+        h->energy_fixed += fired * (unsigned long long)(h->cfg.spike_cost * 1000.0);
+    }
+    h->last.kmers = h->h_scalars[2];
+    if (h->pending_timings) collect_timings(h, h->pend_pe);
+    h->pend_pe = PhaseEvents{};
+    return NK_OK;
 }
 
 void begin_call(nk_counter* h) {
+    resolve(h);
     h->ev_used = 0;
     const float topn = h->last.topn_ms;
     h->last = nk_timings{};
@@ -384,12 +443,16 @@ int fold_and_simulate(nk_counter* h, bool skip_zero, PhaseEvents& pe) {
         NK_CUDA(cudaMemsetAsync(h->currents, 0, h->cfg.pool_size * sizeof(unsigned long long), h->stream));
         h->currents_valid_overwrite = false;
     }
-    NK_TRY(fold_now(h));
     NK_TRY(get_event(h, &pe.fold1));
     NK_CUDA(cudaEventRecord(pe.fold1, h->stream));
-    NK_TRY(simulate(h, skip_zero));
+    NK_TRY(simulate(h, skip_zero));  // folds acc -> currents inside the LIF kernel
     NK_TRY(get_event(h, &pe.lif1));
     NK_CUDA(cudaEventRecord(pe.lif1, h->stream));
+    if (h->exact) {  // counts.clear() + refill, kmer_per_neuron rebuilt (:157-172, :426-427, :467-473)
+        cudaError_t e = nk::exact_finalize(h->xt, h->fm, h->cfg.pool_size, std::min(64u, 2u * h->cfg.k), false, h->stream);
+        if (e == cudaErrorInvalidValue) return fail(NK_ERR_UNSUPPORTED, "exact counts: more than 2^31 windows in one call");
+        NK_CUDA(e);
+    }
     return NK_OK;
 }
 
@@ -487,8 +550,8 @@ int process_file(nk_counter* h, const char* path, bool streaming, std::string* e
         if ((rc = fold_and_simulate(h, /*skip_zero=*/!streaming, pe)) != NK_OK) { *err = g_err; break; }
         if (get_event(h, &pe.end) != NK_OK) { *err = g_err; rc = NK_ERR_CUDA; break; }
         cudaEventRecord(pe.end, h->stream);
-        if ((rc = finish_call(h, true)) != NK_OK) { *err = g_err; break; }
-        collect_timings(h, pe);
+        if ((rc = finish_call(h, true, &pe)) != NK_OK) { *err = g_err; break; }
+        if ((rc = resolve(h)) != NK_OK) { *err = g_err; break; }
     } while (0);
     cudaStreamSynchronize(h->copy_stream);
     cudaStreamSynchronize(h->stream);
@@ -578,8 +641,11 @@ int nk_reset(nk_counter* h) {
     NK_CUDA(cudaMemsetAsync(h->r, 0, P * sizeof(unsigned int), h->stream));
     NK_CUDA(cudaMemsetAsync(h->spikes, 0, P * sizeof(unsigned long long), h->stream));
     NK_CUDA(cudaMemsetAsync(h->scalars, 0, 8 * sizeof(unsigned long long), h->stream));
+    if (h->pending) { NK_CUDA(cudaStreamSynchronize(h->stream)); h->pending = false; h->pend_pe = PhaseEvents{}; }
+    if (h->exact) NK_CUDA(nk::exact_clear(h->xt, h->cfg.pool_size, true, h->stream));
     h->total_spikes = 0;
     h->energy_fixed = 0;
+    h->spike_bound = 0;
     h->fresh = true;
     h->streaming = false;
     h->acc_dirty = false;
@@ -600,6 +666,8 @@ int nk_destroy(nk_counter* h) {
     cudaFree(h->topn.hist); cudaFree(h->topn.ctrl); cudaFree(h->topn.block_counts);
     cudaFree(h->topn.out_idx); cudaFree(h->topn.out_spikes);
     if (h->h_top) cudaFreeHost(h->h_top);
+    nk::exact_free(h->xt);
+    cudaFree(h->d_top_uniques);
     free_devbuf(h->buf[0]); free_devbuf(h->buf[1]); free_devbuf(h->staged);
     cudaFree(h->d_offsets); cudaFree(h->staged_offsets);
     for (cudaEvent_t e : h->evpool) cudaEventDestroy(e);
@@ -634,8 +702,7 @@ int nk_process_batch(nk_counter* h, const uint8_t* bases, const uint64_t* offset
     NK_TRY(fold_and_simulate(h, /*skip_zero=*/true, pe));
     NK_TRY(get_event(h, &pe.end));
     NK_CUDA(cudaEventRecord(pe.end, h->stream));
-    NK_TRY(finish_call(h, true));
-    collect_timings(h, pe);
+    NK_TRY(finish_call(h, true, &pe));
     return NK_OK;
 }
 
@@ -645,6 +712,7 @@ int nk_stream_begin(nk_counter* h) {
     NK_CUDA(cudaSetDevice(h->cfg.device));
     begin_call(h);
     h->streaming = true;
+    h->stream_pe = PhaseEvents{};
     h->currents_valid_overwrite = true;
     NK_CUDA(cudaMemsetAsync(h->scalars + 2, 0, sizeof(unsigned long long), h->stream));
     return NK_OK;
@@ -654,7 +722,7 @@ int nk_stream_push(nk_counter* h, const uint8_t* bases, const uint64_t* offsets,
     NK_TRY(validate_batch(h, bases, offsets, nseq));
     if (!h->streaming) return fail(NK_ERR_STATE, "nk_stream_push without nk_stream_begin");
     NK_CUDA(cudaSetDevice(h->cfg.device));
-    return count_host_batch(h, bases, offsets, nseq, nullptr);
+    return count_host_batch(h, bases, offsets, nseq, &h->stream_pe);
 }
 
 int nk_stream_accumulated(nk_counter* h, void** dev_currents) {
@@ -666,7 +734,8 @@ int nk_stream_accumulated(nk_counter* h, void** dev_currents) {
         h->currents_valid_overwrite = false;
     }
     NK_TRY(fold_now(h));
-    NK_CUDA(cudaStreamSynchronize(h->stream));
+    // no host synchronisation: the caller's collective must be enqueued on nk_cuda_stream()
+    // (or after nk_synchronize()), which orders it after the fold
     if (dev_currents) *dev_currents = h->currents;
     return NK_OK;
 }
@@ -675,11 +744,9 @@ int nk_stream_finish(nk_counter* h) {
     if (!h) return fail(NK_ERR_BAD_ARG, "null handle");
     if (!h->streaming) return fail(NK_ERR_STATE, "nk_stream_finish without nk_stream_begin");
     NK_CUDA(cudaSetDevice(h->cfg.device));
-    PhaseEvents pe;
+    PhaseEvents pe = h->stream_pe;
     NK_TRY(fold_and_simulate(h, /*skip_zero=*/false, pe));
-    NK_TRY(finish_call(h, true));
-    h->last.fold_ms = ev_ms(pe.fold0, pe.fold1);
-    h->last.lif_ms = ev_ms(pe.fold1, pe.lif1);
+    NK_TRY(finish_call(h, true, &pe));
     h->streaming = false;
     return NK_OK;
 }
@@ -697,9 +764,9 @@ int nk_simulate(nk_counter* h) {
     NK_CUDA(cudaEventRecord(a, h->stream));
     NK_TRY(simulate(h, /*skip_zero=*/false));
     NK_CUDA(cudaEventRecord(b, h->stream));
-    NK_TRY(finish_call(h, true));
-    h->last.lif_ms = ev_ms(a, b);
-    h->last.total_ms = h->last.lif_ms;
+    PhaseEvents pe;
+    pe.fold1 = a; pe.lif1 = b; pe.begin = a; pe.end = b;
+    NK_TRY(finish_call(h, true, &pe));
     return NK_OK;
 }
 
@@ -725,7 +792,9 @@ int nk_process_sequence(nk_counter* h, const uint8_t* seq, uint64_t len) {
     NK_CUDA(nk::launch_lif_single_tick(p, h->currents, h->stream));
     ++h->last.launches;
     h->fresh = false;
-    return finish_call(h, true);
+    if (h->exact) NK_CUDA(nk::exact_finalize(h->xt, h->fm, h->cfg.pool_size, std::min(64u, 2u * h->cfg.k), true, h->stream));
+    h->spike_bound = h->spike_bound + 1 ? h->spike_bound + 1 : h->spike_bound;
+    return finish_call(h, true, nullptr);
 }
 
 int nk_top_n(nk_counter* h, uint64_t top_n, nk_top_entry* out, uint64_t* n_out) {
@@ -747,17 +816,25 @@ int nk_top_n(nk_counter* h, uint64_t top_n, nk_top_entry* out, uint64_t* n_out) 
         NK_CUDA(cudaMallocHost(&h->h_top, 2 * cap * sizeof(unsigned long long)));
         h->topn_cap = cap;
     }
-    // max cumulative spike count bounds the radix passes
-    NK_CUDA(cudaMemcpyAsync(h->h_scalars, h->scalars, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
-    NK_CUDA(cudaStreamSynchronize(h->stream));
-    h->ev_used = 0;
+    // the host-side bound on the largest cumulative spike count picks the radix passes: no round trip
     cudaEvent_t a, b;
+    if (!h->pending) h->ev_used = 0;
     NK_TRY(get_event(h, &a));
     NK_TRY(get_event(h, &b));
     NK_CUDA(cudaEventRecord(a, h->stream));
     uint64_t launches = 0;
-    NK_CUDA(nk::launch_topn(h->spikes, h->cfg.pool_size, n, h->h_scalars[1], h->topn, h->stream, &launches));
+    NK_CUDA(nk::launch_topn(h->spikes, h->cfg.pool_size, n, h->spike_bound, h->topn, h->stream, &launches));
     NK_CUDA(cudaEventRecord(b, h->stream));
+    std::vector<unsigned int> h_uni;
+    const bool have_uniques = h->exact && h->xt.valid && h->xt.uniques;
+    if (have_uniques) {
+        cudaFree(h->d_top_uniques);
+        h->d_top_uniques = nullptr;
+        NK_CUDA(cudaMalloc(&h->d_top_uniques, n * sizeof(unsigned int)));
+        NK_CUDA(nk::exact_gather_uniques(h->xt, h->topn.out_idx, n, h->d_top_uniques, h->stream));
+        h_uni.resize(n);
+        NK_CUDA(cudaMemcpyAsync(h_uni.data(), h->d_top_uniques, n * sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
+    }
     unsigned long long* hi = reinterpret_cast<unsigned long long*>(h->h_top);
     unsigned long long* hs = hi + h->topn_cap;
     NK_CUDA(cudaMemcpyAsync(hi, h->topn.out_idx, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
@@ -766,10 +843,12 @@ int nk_top_n(nk_counter* h, uint64_t top_n, nk_top_entry* out, uint64_t* n_out) 
     for (uint64_t i = 0; i < n; ++i) {
         out[i].idx = hi[i];
         out[i].spikes = hs[i];
-        out[i].uniques = NK_UNIQUES_NOT_COMPUTED;
+        out[i].uniques = have_uniques ? h_uni[i] : NK_UNIQUES_NOT_COMPUTED;
         out[i]._pad = 0;
     }
     *n_out = n;
+    NK_TRY(resolve(h));  // the synchronisation above also completed any in-flight read-back
+    h->last.d2h_bytes += 2 * n * sizeof(unsigned long long);
     h->last.topn_ms = ev_ms(a, b);
     h->last.topn_launches = launches;
     return NK_OK;
@@ -777,17 +856,73 @@ int nk_top_n(nk_counter* h, uint64_t top_n, nk_top_entry* out, uint64_t* n_out) 
 
 int nk_total_spikes(const nk_counter* h, uint64_t* out) {
     if (!h || !out) return fail(NK_ERR_BAD_ARG, "null argument");
+    NK_TRY(resolve(const_cast<nk_counter*>(h)));
     *out = h->total_spikes;
     return NK_OK;
 }
 int nk_energy_used(const nk_counter* h, double* out) {
     if (!h || !out) return fail(NK_ERR_BAD_ARG, "null argument");
+    NK_TRY(resolve(const_cast<nk_counter*>(h)));
     *out = (double)h->energy_fixed / 1000.0;  // src/models.rs:170-172
     return NK_OK;
 }
-int nk_get_count(nk_counter* h, uint64_t, uint32_t*, int32_t*) {
+int nk_enable_exact_counts(nk_counter* h, int on) {
     if (!h) return fail(NK_ERR_BAD_ARG, "null handle");
-    return fail(NK_ERR_UNSUPPORTED, "exact k-mer side table (get_count) is not built yet (SURVEY §8 f1)");
+    if (h->streaming) return fail(NK_ERR_STATE, "nk_enable_exact_counts inside nk_stream_begin/end");
+    NK_CUDA(cudaSetDevice(h->cfg.device));
+    NK_TRY(resolve(h));
+    h->exact = on != 0;
+    if (!h->exact) { NK_CUDA(cudaStreamSynchronize(h->stream)); nk::exact_free(h->xt); }
+    return NK_OK;
+}
+
+int nk_get_count(nk_counter* h, uint64_t kmer, uint32_t* count, int32_t* found) {
+    if (!h || !count || !found) return fail(NK_ERR_BAD_ARG, "null argument");
+    if (!h->exact)
+        return fail(NK_ERR_UNSUPPORTED, "exact k-mer table is off: call nk_enable_exact_counts(h, 1) before processing");
+    NK_CUDA(cudaSetDevice(h->cfg.device));
+    NK_TRY(resolve(h));
+    *count = 0;
+    *found = 0;
+    if (!h->xt.valid || h->xt.n_keys == 0) return NK_OK;
+    NK_CUDA(nk::exact_lookup(h->xt, kmer, h->scalars + 4, h->stream));
+    NK_CUDA(cudaMemcpyAsync(h->h_scalars + 4, h->scalars + 4, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    NK_CUDA(cudaStreamSynchronize(h->stream));
+    *found = (int32_t)h->h_scalars[4];
+    *count = (uint32_t)h->h_scalars[5];
+    return NK_OK;
+}
+
+int nk_exact_table_size(nk_counter* h, uint64_t* n) {
+    if (!h || !n) return fail(NK_ERR_BAD_ARG, "null argument");
+    if (!h->exact) return fail(NK_ERR_UNSUPPORTED, "exact k-mer table is off");
+    NK_TRY(resolve(h));
+    *n = h->xt.valid ? h->xt.n_keys : 0;
+    return NK_OK;
+}
+
+int nk_copy_exact_table(nk_counter* h, uint64_t* keys, uint32_t* counts) {
+    if (!h) return fail(NK_ERR_BAD_ARG, "null handle");
+    if (!h->exact) return fail(NK_ERR_UNSUPPORTED, "exact k-mer table is off");
+    NK_CUDA(cudaSetDevice(h->cfg.device));
+    NK_TRY(resolve(h));
+    const unsigned long long n = h->xt.valid ? h->xt.n_keys : 0;
+    if (n == 0) return NK_OK;
+    if (keys) NK_CUDA(cudaMemcpyAsync(keys, h->xt.keys, n * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (counts) NK_CUDA(cudaMemcpyAsync(counts, h->xt.counts, n * 4, cudaMemcpyDeviceToHost, h->stream));
+    NK_CUDA(cudaStreamSynchronize(h->stream));
+    return NK_OK;
+}
+
+int nk_copy_uniques(nk_counter* h, uint32_t* out) {
+    if (!h || !out) return fail(NK_ERR_BAD_ARG, "null argument");
+    if (!h->exact) return fail(NK_ERR_UNSUPPORTED, "exact k-mer table is off");
+    NK_CUDA(cudaSetDevice(h->cfg.device));
+    NK_TRY(resolve(h));
+    if (!h->xt.uniques) { std::memset(out, 0, h->cfg.pool_size * 4); return NK_OK; }
+    NK_CUDA(cudaMemcpyAsync(out, h->xt.uniques, h->cfg.pool_size * 4, cudaMemcpyDeviceToHost, h->stream));
+    NK_CUDA(cudaStreamSynchronize(h->stream));
+    return NK_OK;
 }
 
 int nk_debug_kmers(nk_counter* h, const uint8_t* seq, uint64_t len, uint64_t* fwd, uint64_t* rc, uint64_t* words,
@@ -797,6 +932,7 @@ int nk_debug_kmers(nk_counter* h, const uint8_t* seq, uint64_t len, uint64_t* fw
     *n_out = 0;
     if (len < h->cfg.k) return NK_OK;
     if (!seq) return fail(NK_ERR_BAD_ARG, "null seq");
+    NK_TRY(resolve(h));
     const uint64_t n = len - h->cfg.k + 1;
     NK_CUDA(cudaStreamSynchronize(h->stream));
     NK_TRY(ensure_devbuf(h->staged, len));
@@ -820,7 +956,7 @@ int nk_debug_kmers(nk_counter* h, const uint8_t* seq, uint64_t len, uint64_t* fw
         p.out_rc = rc ? d_out + n : nullptr;
         p.out_word = words ? d_out + 2 * n : nullptr;
         p.out_idx = idx ? d_out + 3 * n : nullptr;
-        NK_D(nk::launch_count(p, h->cfg.use_canonical != 0, true, (int)std::min<unsigned long long>(p.ntiles, h->grid), h->stream));
+        NK_D(nk::launch_count(p, h->cfg.use_canonical != 0, 1, (int)std::min<unsigned long long>(p.ntiles, h->grid), h->stream));
         if (fwd) NK_D(cudaMemcpyAsync(fwd, d_out, n * 8, cudaMemcpyDeviceToHost, h->stream));
         if (rc) NK_D(cudaMemcpyAsync(rc, d_out + n, n * 8, cudaMemcpyDeviceToHost, h->stream));
         if (words) NK_D(cudaMemcpyAsync(words, d_out + 2 * n, n * 8, cudaMemcpyDeviceToHost, h->stream));
@@ -856,6 +992,7 @@ int nk_debug_hash(nk_counter* h, const uint64_t* words, uint64_t n, uint64_t* ha
 
 static int copy_out(nk_counter* h, void* dst, const void* src, size_t bytes) {
     if (!h || !dst) return fail(NK_ERR_BAD_ARG, "null argument");
+    NK_TRY(resolve(h));
     NK_CUDA(cudaSetDevice(h->cfg.device));
     NK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
     NK_CUDA(cudaStreamSynchronize(h->stream));
@@ -868,6 +1005,7 @@ int nk_copy_refractory(nk_counter* h, uint32_t* out) { return copy_out(h, out, h
 
 int nk_last_timings(const nk_counter* h, nk_timings* out) {
     if (!h || !out) return fail(NK_ERR_BAD_ARG, "null argument");
+    NK_TRY(resolve(const_cast<nk_counter*>(h)));
     *out = h->last;
     return NK_OK;
 }
@@ -883,6 +1021,7 @@ int nk_calibrate(nk_counter* h, int which, double* out) {
     if (!h || !out) return fail(NK_ERR_BAD_ARG, "null argument");
     if (which < 0 || which > 2) return fail(NK_ERR_BAD_ARG, "which must be 0, 1 or 2");
     if (h->streaming || h->acc_dirty) return fail(NK_ERR_STATE, "nk_calibrate needs an idle counter");
+    NK_TRY(resolve(h));
     NK_CUDA(cudaSetDevice(h->cfg.device));
     int sms = 0;
     NK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
@@ -918,6 +1057,7 @@ int nk_calibrate(nk_counter* h, int which, double* out) {
 int nk_stage_reserve(nk_counter* h, uint64_t nbytes, uint64_t nseq, void** dev_bases, void** dev_offsets) {
     if (!h) return fail(NK_ERR_BAD_ARG, "null handle");
     NK_CUDA(cudaSetDevice(h->cfg.device));
+    NK_TRY(resolve(h));
     NK_CUDA(cudaStreamSynchronize(h->stream));
     NK_TRY(ensure_devbuf(h->staged, nbytes));
     NK_TRY(ensure_offsets(&h->staged_offsets, &h->staged_offsets_cap, nseq + 1));
@@ -952,16 +1092,12 @@ int nk_process_staged(nk_counter* h, uint64_t nbytes, uint64_t nseq, int mode) {
         NK_TRY(fold_and_simulate(h, /*skip_zero=*/true, pe));
         NK_TRY(get_event(h, &pe.end));
         NK_CUDA(cudaEventRecord(pe.end, h->stream));
-        NK_TRY(finish_call(h, true));
-        collect_timings(h, pe);
+        NK_TRY(finish_call(h, true, &pe));
     } else {
-        // accumulate the phase times of the pushes of this stream
-        NK_CUDA(cudaStreamSynchronize(h->stream));
-        for (size_t i = 0; i < pe.mark0.size(); ++i) {
-            h->last.mark_ms += ev_ms(pe.mark0[i], pe.count0[i]);
-            h->last.count_ms += ev_ms(pe.count0[i], pe.count1[i]);
-        }
-        h->ev_used = 0;
+        // the mark/count event pairs of this push are collected with the stream's final read-back
+        h->stream_pe.mark0.insert(h->stream_pe.mark0.end(), pe.mark0.begin(), pe.mark0.end());
+        h->stream_pe.count0.insert(h->stream_pe.count0.end(), pe.count0.begin(), pe.count0.end());
+        h->stream_pe.count1.insert(h->stream_pe.count1.end(), pe.count1.begin(), pe.count1.end());
     }
     return NK_OK;
 }
@@ -976,7 +1112,7 @@ int nk_synchronize(nk_counter* h) {
     NK_CUDA(cudaSetDevice(h->cfg.device));
     NK_CUDA(cudaStreamSynchronize(h->copy_stream));
     NK_CUDA(cudaStreamSynchronize(h->stream));
-    return NK_OK;
+    return resolve(h);
 }
 
 int nk_synth_fill(nk_counter* h, void* dev_out, uint64_t seed, uint64_t start, uint64_t n, uint32_t flags) {

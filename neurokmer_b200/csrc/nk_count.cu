@@ -80,7 +80,7 @@ __device__ __noinline__ unsigned long long pack_skip(unsigned F0, unsigned F1, u
     return word;
 }
 
-template <bool CANON, bool EMIT, bool POW2, bool KHI>
+template <bool CANON, int MODE, bool POW2, bool KHI>
 __device__ __forceinline__ void process_chunk(const CountParams& p, const WindowConsts& wc, const Codes16& cur,
                                               const Codes16& nxt, unsigned inv16, unsigned lane,
                                               unsigned long long pos0) {
@@ -110,6 +110,22 @@ __device__ __forceinline__ void process_chunk(const CountParams& p, const Window
         H2 = __funnelshift_r(u2, u1, wc.sh);
     }
 
+    constexpr bool EMIT = MODE == 1;
+    // MODE 2: reserve this warp's slots in the word array with ONE atomic per 512-position chunk
+    unsigned long long* wslot = nullptr;
+    if (MODE == 2) {
+        const unsigned mine = 16u - __popc(inv16 & 0xFFFFu);
+        unsigned incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= (unsigned)o) incl += t;
+        }
+        unsigned long long base = 0;
+        if (lane == 31) base = atomicAdd(p.words_cursor, (unsigned long long)incl);
+        base = __shfl_sync(0xFFFFFFFFu, base, 31);
+        wslot = p.words + base + (incl - mine);
+    }
     constexpr int kUnroll = NK_COUNT_UNROLL;
 #pragma unroll(kUnroll)
     for (unsigned j = 0; j < 16; ++j) {
@@ -143,6 +159,7 @@ __device__ __forceinline__ void process_chunk(const CountParams& p, const Window
                 if (p.out_idx) p.out_idx[pos] = idx;
             }
         } else {
+            if (MODE == 2 && !bad) *wslot++ = word;
 #ifdef NK_EXP_NORED
             // diagnostic build only (tools/variants.sh): no pool update, keep the value alive
             if (idx == 0xFFFFFFFFu) p.acc[0] = bad;
@@ -162,7 +179,7 @@ __device__ __forceinline__ void process_chunk(const CountParams& p, const Window
 #ifndef NK_COUNT_MINBLOCKS
 #define NK_COUNT_MINBLOCKS 2
 #endif
-template <bool CANON, bool EMIT, bool POW2, bool KHI>
+template <bool CANON, int MODE, bool POW2, bool KHI>
 __global__ void __launch_bounds__(COUNT_THREADS, NK_COUNT_MINBLOCKS) count_kernel(const __grid_constant__ CountParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) unsigned long long bars[COUNT_STAGES];
@@ -201,7 +218,7 @@ __global__ void __launch_bounds__(COUNT_THREADS, NK_COUNT_MINBLOCKS) count_kerne
             const Codes16 nxt = convert16<!CANON>(*reinterpret_cast<const uint4*>(lp + (c + 1u) * COUNT_CHUNK));
             const unsigned off = span0 + c * COUNT_CHUNK;
             const unsigned inv16 = bits[(off >> 4) + lane];
-            process_chunk<CANON, EMIT, POW2, KHI>(p, wc, cur, nxt, inv16, lane,
+            process_chunk<CANON, MODE, POW2, KHI>(p, wc, cur, nxt, inv16, lane,
                                        tile * COUNT_TILE + off + 16u * lane);
             cur = nxt;
         }
@@ -261,34 +278,38 @@ __global__ void mark_tail_kernel(unsigned int* invalid, unsigned long long nbyte
 
 size_t count_smem_bytes() { return (size_t)kSmemTotal; }
 
-template <bool CANON, bool EMIT, bool POW2, bool KHI>
+template <bool CANON, int MODE, bool POW2, bool KHI>
 static cudaError_t launch_count_t(const CountParams& p, int grid, cudaStream_t s) {
-    cudaError_t e = cudaFuncSetAttribute(count_kernel<CANON, EMIT, POW2, KHI>,
+    cudaError_t e = cudaFuncSetAttribute(count_kernel<CANON, MODE, POW2, KHI>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
     if (e != cudaSuccess) return e;
-    count_kernel<CANON, EMIT, POW2, KHI><<<grid, COUNT_THREADS, kSmemTotal, s>>>(p);
+    count_kernel<CANON, MODE, POW2, KHI><<<grid, COUNT_THREADS, kSmemTotal, s>>>(p);
     return cudaGetLastError();
 }
 
-template <bool CANON, bool EMIT>
-static cudaError_t launch_count_ce(const CountParams& p, int grid, cudaStream_t s) {
+template <bool CANON, int MODE>
+static cudaError_t launch_count_cm(const CountParams& p, int grid, cudaStream_t s) {
     const bool pow2 = p.fm.is_pow2 != 0, khi = p.k > 16;
-    if (pow2) return khi ? launch_count_t<CANON, EMIT, true, true>(p, grid, s) : launch_count_t<CANON, EMIT, true, false>(p, grid, s);
-    return khi ? launch_count_t<CANON, EMIT, false, true>(p, grid, s) : launch_count_t<CANON, EMIT, false, false>(p, grid, s);
+    if (pow2) return khi ? launch_count_t<CANON, MODE, true, true>(p, grid, s) : launch_count_t<CANON, MODE, true, false>(p, grid, s);
+    return khi ? launch_count_t<CANON, MODE, false, true>(p, grid, s) : launch_count_t<CANON, MODE, false, false>(p, grid, s);
 }
 
-cudaError_t launch_count(const CountParams& p, bool canonical, bool emit, int grid, cudaStream_t s) {
-    if (canonical) return emit ? launch_count_ce<true, true>(p, grid, s) : launch_count_ce<true, false>(p, grid, s);
-    return emit ? launch_count_ce<false, true>(p, grid, s) : launch_count_ce<false, false>(p, grid, s);
+cudaError_t launch_count(const CountParams& p, bool canonical, int mode, int grid, cudaStream_t s) {
+    if (canonical) {
+        if (mode == 0) return launch_count_cm<true, 0>(p, grid, s);
+        return mode == 1 ? launch_count_cm<true, 1>(p, grid, s) : launch_count_cm<true, 2>(p, grid, s);
+    }
+    if (mode == 0) return launch_count_cm<false, 0>(p, grid, s);
+    return mode == 1 ? launch_count_cm<false, 1>(p, grid, s) : launch_count_cm<false, 2>(p, grid, s);
 }
 
 template <bool CANON>
 static cudaError_t max_grid_t(int sms, int* grid) {
     int per_sm = 0;
-    cudaError_t e = cudaFuncSetAttribute(count_kernel<CANON, false, false, true>,
+    cudaError_t e = cudaFuncSetAttribute(count_kernel<CANON, 0, false, true>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
     if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, count_kernel<CANON, false, false, true>, COUNT_THREADS,
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, count_kernel<CANON, 0, false, true>, COUNT_THREADS,
                                                       kSmemTotal);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;

@@ -34,6 +34,9 @@ struct CountParams {
     FastMod fm;
     RotMul rm;                    // make_rotmul(): opaque 2^B multipliers (see nk_device.cuh)
     unsigned int k;
+    // exact side table (MODE 2 instantiation only): every counted word is appended here
+    unsigned long long* words;
+    unsigned long long* words_cursor;
     // debug taps (EMIT instantiation only); any may be null
     unsigned long long* out_fwd;
     unsigned long long* out_rc;
@@ -53,7 +56,8 @@ inline unsigned long long count_bitmap_words(unsigned long long nbytes) {
     return count_ntiles(nbytes) * (COUNT_TILE / 32) + 16;
 }
 
-cudaError_t launch_count(const CountParams& p, bool canonical, bool emit, int grid, cudaStream_t s);
+// mode 0: count; 1: emit the debug taps instead of counting; 2: count and append words (exact side table)
+cudaError_t launch_count(const CountParams& p, bool canonical, int mode, int grid, cudaStream_t s);
 cudaError_t count_max_grid(bool canonical, int device, int* grid);
 
 // invalid-start bitmap: zero, then mark the last k-1 starts of every sequence
@@ -69,7 +73,9 @@ cudaError_t launch_fold(unsigned int* acc, unsigned long long* currents, unsigne
                         bool overwrite, cudaStream_t s);
 
 struct LifParams {
-    const unsigned long long* currents;
+    unsigned long long* currents;
+    unsigned int* acc;               // u32 batch accumulators to fold in first (fold_mode != 0); zeroed
+    int fold_mode;                   // 0: currents as stored; 1: currents += acc; 2: currents = acc (overwrite)
     float* v;
     unsigned int* r;
     unsigned long long* spikes;
@@ -90,7 +96,8 @@ struct LifTable {
     float* v;              // table_n
     unsigned int* r;       // table_n
 };
-cudaError_t launch_lif_table(const LifParams& p, const LifTable& t, unsigned long long table_n, cudaStream_t s);
+cudaError_t launch_lif_table_build(const LifParams& p, const LifTable& t, unsigned long long table_n, cudaStream_t s);
+cudaError_t launch_lif_table_apply(const LifParams& p, const LifTable& t, unsigned long long table_n, cudaStream_t s);
 // one LIF tick per neuron with the raw count as input; currents zeroed (process_sequence)
 cudaError_t launch_lif_single_tick(const LifParams& p, unsigned long long* currents_rw, cudaStream_t s);
 
@@ -110,6 +117,31 @@ cudaError_t launch_topn(const unsigned long long* spikes, unsigned long long poo
 
 cudaError_t launch_hash_words(const unsigned long long* words, unsigned long long n, FastMod fm,
                               unsigned long long* hashes, unsigned long long* idx, cudaStream_t s);
+
+// exact side tables (nk_exact.cu)
+struct ExactTable {
+    unsigned long long* words = nullptr;   // appended by the count kernel
+    unsigned long long words_cap = 0, words_bound = 0;
+    unsigned long long* cursor = nullptr;  // [0] append cursor, [1] scratch (#runs)
+    unsigned long long* alt = nullptr;  unsigned long long alt_cap = 0;
+    void* tmp = nullptr;                unsigned long long tmp_cap = 0;
+    unsigned long long* rk = nullptr;   unsigned long long rk_cap = 0;
+    void* rc = nullptr;                 unsigned long long rc_cap = 0;
+    unsigned long long* keys = nullptr; unsigned long long keys_cap = 0;   // sorted distinct words
+    unsigned int* counts = nullptr;     unsigned long long counts_cap = 0; // occurrences (wrap at 2^32)
+    unsigned long long n_keys = 0;
+    unsigned int* uniques = nullptr;    // per neuron: kmer_per_neuron
+    unsigned int* flags = nullptr;
+    bool valid = false;
+};
+cudaError_t exact_reserve_words(ExactTable& t, unsigned long long extra, cudaStream_t s);
+cudaError_t exact_clear(ExactTable& t, unsigned long long pool, bool tables_too, cudaStream_t s);
+cudaError_t exact_finalize(ExactTable& t, const FastMod& fm, unsigned long long pool, unsigned key_bits, bool merge,
+                           cudaStream_t s);
+cudaError_t exact_lookup(const ExactTable& t, unsigned long long key, unsigned long long* d_out2, cudaStream_t s);
+cudaError_t exact_gather_uniques(const ExactTable& t, const unsigned long long* idx, unsigned long long n,
+                                 unsigned int* out, cudaStream_t s);
+void exact_free(ExactTable& t);
 
 // peak calibration (roofline denominators)
 cudaError_t launch_int_peak(int mode, unsigned int* out, int blocks, unsigned iters, cudaStream_t s);

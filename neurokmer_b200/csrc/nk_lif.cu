@@ -92,6 +92,18 @@ __device__ __forceinline__ float input_current(unsigned long long count, unsigne
     return __double2float_rn(__ull2double_rn(count) / __ull2double_rn(steps));
 }
 
+// this call's total for neuron i: optionally folds the u32 batch accumulator in (the fold
+// kernel fused into the LIF pass: saves a launch and one 24 MB round trip over the pool)
+__device__ __forceinline__ unsigned long long load_count(const LifParams& p, unsigned long long i) {
+    unsigned long long count = p.fold_mode == 2 ? 0ull : p.currents[i];
+    if (p.fold_mode) {
+        count += p.acc[i];
+        p.acc[i] = 0u;
+        p.currents[i] = count;
+    }
+    return count;
+}
+
 __device__ __forceinline__ void block_totals(unsigned long long fired, unsigned long long maxs,
                                              unsigned long long* total_new, unsigned long long* max_spikes) {
     __shared__ unsigned long long s_f[LIF_THREADS / 32], s_m[LIF_THREADS / 32];
@@ -115,7 +127,7 @@ __global__ void __launch_bounds__(LIF_THREADS) lif_kernel(const LifParams p) {
     const unsigned long long i = blockIdx.x * (unsigned long long)LIF_THREADS + threadIdx.x;
     unsigned long long fired = 0, total = 0;
     if (i < p.pool) {
-        const unsigned long long count = p.currents[i];
+        const unsigned long long count = load_count(p, i);
         total = p.spikes[i];
         if (!(p.skip_zero && count == 0)) {
             const NeuronResult o =
@@ -152,7 +164,7 @@ __global__ void __launch_bounds__(LIF_THREADS) lif_table_apply_kernel(const LifP
     const unsigned long long i = blockIdx.x * (unsigned long long)LIF_THREADS + threadIdx.x;
     unsigned long long fired = 0, total = 0;
     if (i < p.pool) {
-        const unsigned long long count = p.currents[i];
+        const unsigned long long count = load_count(p, i);
         total = p.spikes[i];
         if (!(p.skip_zero && count == 0)) {
             const unsigned long long c = count < table_n - 1 ? count : table_n - 1;
@@ -213,11 +225,13 @@ cudaError_t launch_lif(const LifParams& p, cudaStream_t s) {
     return cudaGetLastError();
 }
 
-cudaError_t launch_lif_table(const LifParams& p, const LifTable& t, unsigned long long table_n, cudaStream_t s) {
-    if (p.pool == 0 || p.steps == 0) return cudaSuccess;
+cudaError_t launch_lif_table_build(const LifParams& p, const LifTable& t, unsigned long long table_n, cudaStream_t s) {
     lif_table_build_kernel<<<lif_blocks(table_n), LIF_THREADS, 0, s>>>(p, t, table_n);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_lif_table_apply(const LifParams& p, const LifTable& t, unsigned long long table_n, cudaStream_t s) {
+    if (p.pool == 0 || p.steps == 0) return cudaSuccess;
     lif_table_apply_kernel<<<lif_blocks(p.pool), LIF_THREADS, 0, s>>>(p, t, table_n);
     return cudaGetLastError();
 }

@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(TN_THREADS) topn_hist_kernel(const unsigned lo
 }
 
 // pick the bin that contains the rank-th largest element; one block of 256 threads
-__global__ void topn_pick_kernel(unsigned int* hist, unsigned long long* ctrl) {
+__global__ void topn_pick_kernel(unsigned int* hist, unsigned long long* ctrl, int last) {
     __shared__ unsigned long long above[256];  // elements in bins > b
     const unsigned b = threadIdx.x;
     __shared__ unsigned int h[256];
@@ -73,12 +73,9 @@ __global__ void topn_pick_kernel(unsigned int* hist, unsigned long long* ctrl) {
         ctrl[C_PREFIX] = (ctrl[C_PREFIX] << 8) | b;
         ctrl[C_RANK] = rank - above[b];
         ctrl[C_GT] += above[b];
+        if (last) ctrl[C_NEED] = rank - above[b];
     }
     hist[b] = 0;
-}
-
-__global__ void topn_finish_select_kernel(unsigned long long* ctrl) {
-    ctrl[C_NEED] = ctrl[C_RANK];
 }
 
 __global__ void __launch_bounds__(TN_THREADS) topn_count_eq_kernel(const unsigned long long* __restrict__ spikes,
@@ -252,9 +249,8 @@ cudaError_t launch_topn(const unsigned long long* spikes, unsigned long long poo
     if (hb == 0) hb = 1;
     for (int d = top; d >= 0; --d) {
         topn_hist_kernel<<<(unsigned)hb, TN_THREADS, 0, s>>>(spikes, pool, d, top, sc.hist, sc.ctrl); ++L;
-        topn_pick_kernel<<<1, 256, 0, s>>>(sc.hist, sc.ctrl); ++L;
+        topn_pick_kernel<<<1, 256, 0, s>>>(sc.hist, sc.ctrl, d == 0 ? 1 : 0); ++L;
     }
-    topn_finish_select_kernel<<<1, 1, 0, s>>>(sc.ctrl); ++L;
     const unsigned long long nblocks = (pool + TOPN_BLOCK_ITEMS - 1) / TOPN_BLOCK_ITEMS;
     topn_count_eq_kernel<<<(unsigned)nblocks, TN_THREADS, 0, s>>>(spikes, pool, sc.ctrl, sc.block_counts); ++L;
     topn_scan_kernel<<<1, 1024, 0, s>>>(sc.block_counts, nblocks); ++L;

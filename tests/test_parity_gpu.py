@@ -444,6 +444,7 @@ def test_lif_golden_rows_gpu():
             c.debug_set_lif_path(force_direct)
             c.stream_begin()
             ptr = c.stream_accumulated()       # device currents: inject the golden counts
+            c.synchronize()                    # the hand-off is stream-ordered, cudaMemcpy is not
             copy_h2d(ptr, counts)
             c.stream_finish()
             assert c.timings()["lif_path"] == (1 if force_direct else 2)
@@ -455,7 +456,9 @@ def test_lif_golden_rows_gpu():
     c = make(31, len(rows))
     for col in (0, 1):
         c.stream_begin()
-        copy_h2d(c.stream_accumulated(), np.array([r[col] for r in rows], np.uint64))
+        ptr = c.stream_accumulated()
+        c.synchronize()
+        copy_h2d(ptr, np.array([r[col] for r in rows], np.uint64))
         c.stream_finish()
         if col == 0:
             assert c.spike_counts().tolist() == [r[2] for r in rows]
@@ -547,3 +550,124 @@ def test_config3_reads_properties(coracle):
     s = make(k, pool); s.process_batch(bases[: int(offsets[m])], offsets[: m + 1])
     exp, _ = coracle.accumulate(bases[: int(offsets[m])], offsets[: m + 1], k, pool, True, threads=8)
     np.testing.assert_array_equal(s.currents(), exp)
+
+
+# --- exact side tables and the CLI result block ------------------------------------
+def _oracle_tables(coracle, seqs, k, pool, canonical):
+    words = np.concatenate([coracle.kmer_words(s, k, canonical) for s in seqs] + [np.zeros(0, np.uint64)])
+    keys, counts = np.unique(words, return_counts=True)
+    idx = np.array([coracle.neuron_index(int(w), pool) for w in keys], np.int64)
+    return keys, counts.astype(np.uint32), np.bincount(idx, minlength=pool).astype(np.uint32)
+
+
+@pytest.mark.parametrize("k,pool,canonical", [(11, 5000, True), (31, 100_000, True), (9, 4096, False)])
+def test_exact_side_tables(coracle, k, pool, canonical):
+    """counts / get_count / kmer_per_neuron (spiking_hash.rs:26-27,157-172,675-678) and the
+    `uniques` column of top_abundant_neurons (:667)."""
+    rng = np.random.default_rng(k)
+    seqs = [random_dna(rng, n, 0.01, 0.05) for n in (60_000, 0, 5, 40_000, 1234)]
+    c = make(k, pool, canonical)
+    assert [t[2] for t in c.top_abundant_neurons(3)] == [None] * 3
+    c.enable_exact_counts(True)
+    c.process_parallel(seqs)
+    keys, counts, uni = _oracle_tables(coracle, seqs, k, pool, canonical)
+    gk, gc = c.exact_table()
+    np.testing.assert_array_equal(gk, keys); np.testing.assert_array_equal(gc, counts)
+    np.testing.assert_array_equal(c.kmer_per_neuron(), uni)
+    for i in (0, len(keys) // 2, len(keys) - 1):
+        assert c.get_count(int(keys[i])) == int(counts[i])
+    missing = next(x for x in range(1, 1000) if x not in set(keys[:2000].tolist()))
+    assert c.get_count(missing) is None
+    top = c.top_abundant_neurons(20)
+    assert [t[2] for t in top] == [int(uni[t[0]]) for t in top]
+    # currents/spikes are unaffected by the side-table mode
+    plain = make(k, pool, canonical); plain.process_parallel(seqs)
+    np.testing.assert_array_equal(plain.currents(), c.currents())
+    np.testing.assert_array_equal(plain.spike_counts(), c.spike_counts())
+    # a second batch call REPLACES both tables (counts.clear(), :157)
+    seqs2 = [random_dna(rng, 30_000)]
+    c.process_parallel(seqs2)
+    keys2, counts2, uni2 = _oracle_tables(coracle, seqs2, k, pool, canonical)
+    gk, gc = c.exact_table()
+    np.testing.assert_array_equal(gk, keys2); np.testing.assert_array_equal(gc, counts2)
+    np.testing.assert_array_equal(c.kmer_per_neuron(), uni2)
+    # streaming fills them the same way
+    s = make(k, pool, canonical); s.enable_exact_counts(True)
+    from neurokmer_b200 import flatten
+    s.stream_begin(); s.stream_push(*flatten(seqs[:2])); s.stream_push(*flatten(seqs[2:])); s.stream_end()
+    gk, gc = s.exact_table()
+    np.testing.assert_array_equal(gk, keys); np.testing.assert_array_equal(gc, counts)
+
+
+def test_exact_tables_process_sequence(coracle):
+    """process_sequence ADDS to counts (:218-221) and counts, per neuron, the sequences that touched it (:262-264)."""
+    rng = np.random.default_rng(8)
+    k, pool = 7, 512
+    c = make(k, pool, True); c.enable_exact_counts(True)
+    seqs = [random_dna(rng, n, 0.02) for n in (300, 3, 150, 700)]
+    total = {}
+    touched = np.zeros(pool, np.uint32)
+    for s in seqs:
+        c.process_sequence(s)
+        w = coracle.kmer_words(s, k, True)
+        for x in w.tolist():
+            total[x] = total.get(x, 0) + 1
+        for i in set(coracle.neuron_index(int(x), pool) for x in w):
+            touched[i] += 1
+        gk, gc = c.exact_table()
+        assert dict(zip(gk.tolist(), gc.tolist())) == total
+        np.testing.assert_array_equal(c.kmer_per_neuron(), touched)
+
+
+def test_python_surface(tmp_path, coracle):
+    """src/python.rs:7-53: PySpikingCounter(k, pool_size).process_file / get_counts / energy_used, pack_kmer_py."""
+    from neurokmer_b200 import PySpikingCounter, pack_kmer_py
+    from neurokmer_b200.fastx import write_fasta
+    rng = np.random.default_rng(12)
+    seqs = [random_dna(rng, n, 0.01) for n in (500, 20, 800)]
+    fa = str(tmp_path / "p.fa"); write_fasta(fa, seqs)
+    py = PySpikingCounter(9, 256)
+    py.process_file(fa)
+    want = {}
+    for s in seqs:
+        for x in coracle.kmer_words(s, 9, False).tolist():   # python.rs builds a NON-canonical counter
+            want[str(x)] = want.get(str(x), 0) + 1
+    assert py.get_counts() == want
+    v = np.zeros(256, np.float32); r = np.zeros(256, np.uint32); sp = np.zeros(256, np.uint64); sc = np.zeros(256, np.uint64)
+    fired = sum(coracle.process_sequence(s, 9, 256, False, 1.0, 0.95, 2, sc, v, r, sp) for s in seqs)
+    assert py.energy_used() == float(fired)
+    assert pack_kmer_py(b"ACGTN") == 27
+
+
+def test_cli_result_block(tmp_path, coracle):
+    """The `neurokmer` binary prints the reference's result block (src/main.rs:49-74)."""
+    import subprocess
+    from neurokmer_b200.fastx import write_fasta
+    from neurokmer_b200 import flatten
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "neurokmer_b200", "neurokmer")
+    rng = np.random.default_rng(13)
+    seqs = [random_dna(rng, n, 0.002, 0.01) for n in (400_000, 100, 250_000)]
+    fa = str(tmp_path / "c.fa"); write_fasta(fa, seqs)
+    k, pool = 21, 10_000
+    for streaming in (False, True):
+        args = [exe, "-i", fa, "-k", str(k), "--pool-size", str(pool), "--canonical", "--exact"] + (["--streaming"] if streaming else [])
+        out = subprocess.check_output(args, text=True)
+        o = oracle_counter(k, pool)
+        bases, offsets = flatten(seqs)
+        (o.process_streaming([(bases, offsets)]) if streaming else o.process_parallel(bases, offsets))
+        oi, os_ = o.top_abundant_neurons(20)
+        _, _, uni = _oracle_tables(coracle, seqs, k, pool, True)
+        want = ["", "=== Top 20 Abundant Neuron Groups (Highest Spike Rates) ==="]
+        for rank, (i, s) in enumerate(zip(oi, os_)):
+            want.append(f"{rank + 1:3}: Neuron {int(i):6} → {int(s):8} spikes ({int(uni[int(i)])} unique k-mers colliding)")
+        want += ["", f"Total spikes fired: {o.total_spikes}", f"Simulated energy used: {o.total_spikes}",
+                 f"Neuron pool size used: {pool}", f"Streaming mode: {'true' if streaming else 'false'}"]
+        assert out.splitlines() == want
+    # without --exact the column is "n/a", never a number
+    out = subprocess.check_output([exe, "-i", fa, "-k", "21", "--pool-size", "10000", "--canonical"], text=True)
+    assert "(n/a unique k-mers colliding)" in out
+    # errors: missing file -> exit code 1 and a message on stderr (the reference returns Err from main)
+    p = subprocess.run([exe, "-i", str(tmp_path / "nope.fa")], capture_output=True, text=True)
+    assert p.returncode == 1 and "cannot open" in p.stderr
+    p = subprocess.run([exe], capture_output=True, text=True)
+    assert p.returncode == 2 and "--input" in p.stderr

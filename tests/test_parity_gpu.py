@@ -671,3 +671,41 @@ def test_cli_result_block(tmp_path, coracle):
     assert p.returncode == 1 and "cannot open" in p.stderr
     p = subprocess.run([exe], capture_output=True, text=True)
     assert p.returncode == 2 and "--input" in p.stderr
+
+
+# --- sharded flow (configs[4] shape) emulated on one GPU --------------------------------------------
+def test_sharded_flow_two_ranks_one_gpu(coracle):
+    """configs[4]: k=31, pool 16,000,000, input sharded by sequence chunk with k-1 overlap, full pool
+    replica per rank, currents summed, LIF after the sum.  Two handles on one GPU stand in for two
+    ranks (the all-reduce is an in-place device add through torch); the result must equal the
+    unsharded run and the oracle bit for bit."""
+    import torch
+    from neurokmer_b200 import flatten
+    from neurokmer_b200.shard import shard_batch
+    from bench import CurrentsView
+    rng = np.random.default_rng(5)
+    k, pool = 31, 16_000_000
+    seqs = [random_dna(rng, n, 0.001) for n in (1_500_000, 10, 900_000, 31, 2_000_000)]
+    bases, offsets = flatten(seqs)
+    ranks = [make(k, pool), make(k, pool)]
+    views = []
+    for r, c in enumerate(ranks):
+        b, o = shard_batch(bases, offsets, k, 2, r)
+        c.stream_begin(); c.stream_push(b, o)
+        ptr = c.stream_accumulated(); c.synchronize()
+        views.append(torch.as_tensor(CurrentsView(ptr, pool), device="cuda"))
+    total = views[0] + views[1]
+    for v in views:
+        v.copy_(total)
+    torch.cuda.synchronize()
+    for c in ranks:
+        c.stream_finish()
+    ref = make(k, pool); ref.stream_begin(); ref.stream_push(bases, offsets); ref.stream_end()
+    for c in ranks:
+        np.testing.assert_array_equal(c.currents(), ref.currents())
+        np.testing.assert_array_equal(c.spike_counts(), ref.spike_counts())
+        assert c.energy.total_spikes() == ref.energy.total_spikes()
+        assert c.top_abundant_neurons(20) == ref.top_abundant_neurons(20)
+    exp, tot = coracle.accumulate(bases, offsets, k, pool, True, threads=4)
+    np.testing.assert_array_equal(ref.currents(), exp)
+    assert int(exp.sum()) == tot

@@ -91,6 +91,9 @@ struct nk_counter {
     // host mirrors (EnergyTracker, src/models.rs:145-173)
     unsigned long long total_spikes = 0, energy_fixed = 0;
     bool fresh = true;      // every neuron still has v = 0, r = 0
+    // after nk_reset the pool arrays (currents, v, r, spikes) are LOGICALLY zero but not yet written:
+    // the fused fold+LIF kernel of the next job overwrites all four, anything else materialises first
+    bool lazy_zero = false;
     int force_direct = 0;
     bool streaming = false;
     bool acc_dirty = false;
@@ -119,6 +122,14 @@ struct nk_counter {
     // host-side upper bound of the largest cumulative spike count (bounds the top-N radix passes
     // without a device round trip): each LIF call adds at most ceil(steps / (refractory + 1))
     unsigned long long spike_bound = 0;
+    // fused post kernel (fold + LIF table + top-N): scratch, result pack, cached rows
+    int post_grid = 0;
+    unsigned long long* post_zero = nullptr;   // [8 u64 ctrl][8*256 u32 hist] zeroed before each launch
+    unsigned long long* d_pack = nullptr;      // 4 + 2*2048 u64
+    unsigned long long* h_pack = nullptr;      // pinned mirror
+    unsigned long long topn_hint = 20;         // rows computed speculatively by the fused kernel (CLI: 20)
+    unsigned long long top_cached_n = 0;       // rows of the last fused launch (valid until state changes)
+    bool top_cache_valid = false, pending_pack = false;
     // exact side tables (opt-in, nk_enable_exact_counts)
     bool exact = false;
     nk::ExactTable xt;
@@ -174,9 +185,21 @@ int ensure_offsets(unsigned long long** p, unsigned long long* cap, unsigned lon
     return NK_OK;
 }
 
+int materialize_zero(nk_counter* h) {
+    if (!h->lazy_zero) return NK_OK;
+    const unsigned long long P = h->cfg.pool_size;
+    NK_CUDA(cudaMemsetAsync(h->currents, 0, P * sizeof(unsigned long long), h->stream));
+    NK_CUDA(cudaMemsetAsync(h->v, 0, P * sizeof(float), h->stream));
+    NK_CUDA(cudaMemsetAsync(h->r, 0, P * sizeof(unsigned int), h->stream));
+    NK_CUDA(cudaMemsetAsync(h->spikes, 0, P * sizeof(unsigned long long), h->stream));
+    h->lazy_zero = false;
+    return NK_OK;
+}
+
 // fold acc into currents if a further `incoming` windows could overflow a u32 accumulator
 int fold_now(nk_counter* h) {
     if (!h->acc_dirty) return NK_OK;
+    NK_TRY(materialize_zero(h));
     NK_CUDA(nk::launch_fold(h->acc, h->currents, h->cfg.pool_size, h->currents_valid_overwrite, h->stream));
     ++h->last.launches;
     h->currents_valid_overwrite = false;
@@ -256,8 +279,11 @@ int count_host_batch(nk_counter* h, const uint8_t* bases, const uint64_t* offset
     NK_CUDA(cudaMemcpyAsync(h->d_offsets, offsets, (nseq + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, h->copy_stream));
     h->last.h2d_bytes += (nseq + 1) * sizeof(uint64_t) + nbytes;
 
-    for (unsigned long long c0 = 0; c0 < nbytes; c0 += kChunkBytes) {
-        const unsigned long long c1 = std::min(c0 + kChunkBytes, nbytes);
+    // chunk plan: fixed 32 MiB granules.  Measured alternatives at 113 MB (end to end, B200, PCIe Gen5):
+    // fixed 32 MiB 2.53 ms; geometric tail down to 2 MiB 2.68 ms; 3 x 36 MiB + 4 MiB tail 2.60 ms —
+    // fewer, equal copies win over a shorter exposed tail.
+    for (unsigned long long c0 = 0, c1 = 0; c0 < nbytes; c0 = c1) {
+        c1 = std::min(c0 + kChunkBytes, nbytes);
         const unsigned long long copy_len = std::min(c1 + nk::COUNT_HALO, nbytes) - c0;
         DevBuf& b = h->buf[h->cur_buf];
         h->cur_buf ^= 1;
@@ -301,8 +327,9 @@ unsigned long long saturation_count(const nk_config& c) {
 // LIF over this call's totals; skip_zero: in-memory driver (:187-200) vs SIMD driver (:544-659).
 // If the u32 batch accumulators still hold counts they are folded into `currents` by the LIF
 // kernel itself (fold_mode), otherwise the stored currents are used as they are.
-int simulate(nk_counter* h, bool skip_zero) {
+int simulate(nk_counter* h, bool skip_zero, bool with_topn = false) {
     h->last.lif_path = 0;
+    h->top_cache_valid = false;
     int fold_mode = 0;
     if (h->acc_dirty) fold_mode = h->currents_valid_overwrite ? 2 : 1;
     if (h->cfg.steps == 0 || h->cfg.pool_size == 0) return fold_now(h);
@@ -328,6 +355,14 @@ int simulate(nk_counter* h, bool skip_zero) {
         const unsigned long long sat = saturation_count(h->cfg);
         if (sat < (1ull << 20)) { use_table = true; table_n = sat + 1; }
     }
+    if (h->lazy_zero) {
+        if (use_table && fold_mode != 0) {
+            p.zero_state = 1;   // the kernel writes currents, v, r, spikes of EVERY neuron without reading them
+            p.fold_mode = 2;
+        } else {
+            NK_TRY(materialize_zero(h));
+        }
+    }
     if (use_table) {
         const nk_config& a = h->cfg; const nk_config& b = h->table_cfg;
         const bool same = h->table_valid && h->table_n == table_n && a.steps == b.steps && a.threshold == b.threshold &&
@@ -350,14 +385,44 @@ int simulate(nk_counter* h, bool skip_zero) {
             h->table_cfg = h->cfg;
             h->table_n = table_n;
         }
-        NK_CUDA(nk::launch_lif_table_apply(p, h->table, table_n, h->stream));
-        ++h->last.launches;
-        h->last.lif_path = 2;
+        const unsigned long long per_call_b = (h->cfg.steps + h->cfg.refractory) / ((unsigned long long)h->cfg.refractory + 1ull);
+        const unsigned long long bound = (h->spike_bound + per_call_b < h->spike_bound) ? ~0ull : h->spike_bound + per_call_b;
+        const unsigned long long n_top = std::min<unsigned long long>(h->topn_hint, h->cfg.pool_size);
+        if (with_topn && !h->exact && n_top >= 1 && n_top <= 2048) {
+            // everything after the count kernel in ONE cooperative launch (nk_post.cu)
+            nk::PostParams q{};
+            q.lif = p;
+            q.table = h->table;
+            q.table_n = table_n;
+            q.n = n_top;
+            int bits = 0;
+            while (bits < 64 && (bound >> bits)) ++bits;
+            q.passes = std::max(1, (bits + 7) / 8);
+            q.ctrl = h->post_zero;
+            q.hist = reinterpret_cast<unsigned int*>(h->post_zero + 8);
+            q.seg_counts = h->topn.block_counts;
+            q.out_idx = h->topn.out_idx;
+            q.out_spikes = h->topn.out_spikes;
+            q.pack = h->d_pack;
+            q.kmers = h->scalars + 2;
+            NK_CUDA(cudaMemsetAsync(h->post_zero, 0, 8 * sizeof(unsigned long long) + 8 * 256 * sizeof(unsigned int), h->stream));
+            NK_CUDA(nk::launch_post(q, h->post_grid, h->stream));
+            ++h->last.launches;
+            h->last.lif_path = 3;
+            h->top_cached_n = n_top;
+            h->top_cache_valid = true;
+            h->pending_pack = true;
+        } else {
+            NK_CUDA(nk::launch_lif_table_apply(p, h->table, table_n, h->stream));
+            ++h->last.launches;
+            h->last.lif_path = 2;
+        }
     } else {
         NK_CUDA(nk::launch_lif(p, h->stream));
         ++h->last.launches;
         h->last.lif_path = 1;
     }
+    if (p.zero_state) h->lazy_zero = false;
     if (fold_mode) {
         h->acc_dirty = false;
         h->acc_kmers = 0;
@@ -391,8 +456,14 @@ void collect_timings(nk_counter* h, const PhaseEvents& pe) {
 
 // enqueue the read-back of {new spikes, max spikes, kmers}; nothing waits here
 int finish_call(nk_counter* h, bool had_lif, const PhaseEvents* pe) {
-    NK_CUDA(cudaMemcpyAsync(h->h_scalars, h->scalars, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
-    h->last.d2h_bytes += 3 * sizeof(unsigned long long);
+    if (h->pending_pack) {  // fused post kernel: scalars and the sorted top-N rows come back in one copy
+        const size_t bytes = (4 + 2 * h->top_cached_n) * sizeof(unsigned long long);
+        NK_CUDA(cudaMemcpyAsync(h->h_pack, h->d_pack, bytes, cudaMemcpyDeviceToHost, h->stream));
+        h->last.d2h_bytes += bytes;
+    } else {
+        NK_CUDA(cudaMemcpyAsync(h->h_scalars, h->scalars, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+        h->last.d2h_bytes += 3 * sizeof(unsigned long long);
+    }
     h->pending = true;
     h->pending_lif = had_lif;
     h->pending_timings = pe != nullptr;
@@ -406,6 +477,11 @@ int resolve(nk_counter* h) {
     NK_CUDA(cudaSetDevice(h->cfg.device));
     NK_CUDA(cudaStreamSynchronize(h->stream));
     h->pending = false;
+    if (h->pending_pack) {
+        h->h_scalars[0] = h->h_pack[0];
+        h->h_scalars[2] = h->h_pack[2];
+        h->pending_pack = false;
+    }
     if (h->pending_lif) {
         const unsigned long long fired = h->h_scalars[0];
         h->total_spikes += fired;
@@ -435,17 +511,18 @@ int free_devbuf(DevBuf& b) {
     return NK_OK;
 }
 
-int fold_and_simulate(nk_counter* h, bool skip_zero, PhaseEvents& pe) {
+int fold_and_simulate(nk_counter* h, bool skip_zero, PhaseEvents& pe, bool with_topn = true) {
     NK_TRY(get_event(h, &pe.fold0));
     NK_CUDA(cudaEventRecord(pe.fold0, h->stream));
     if (!h->acc_dirty && h->currents_valid_overwrite) {
         // nothing was counted by this call: totals are all zero (currents are OVERWRITTEN, :174-176)
+        NK_TRY(materialize_zero(h));
         NK_CUDA(cudaMemsetAsync(h->currents, 0, h->cfg.pool_size * sizeof(unsigned long long), h->stream));
         h->currents_valid_overwrite = false;
     }
     NK_TRY(get_event(h, &pe.fold1));
     NK_CUDA(cudaEventRecord(pe.fold1, h->stream));
-    NK_TRY(simulate(h, skip_zero));  // folds acc -> currents inside the LIF kernel
+    NK_TRY(simulate(h, skip_zero, with_topn));  // folds acc -> currents inside the LIF kernel
     NK_TRY(get_event(h, &pe.lif1));
     NK_CUDA(cudaEventRecord(pe.lif1, h->stream));
     if (h->exact) {  // counts.clear() + refill, kmer_per_neuron rebuilt (:157-172, :426-427, :467-473)
@@ -624,7 +701,16 @@ int nk_create(const nk_config* cfg, nk_counter** out) {
     NK_C(cudaMalloc(&h->topn.ctrl, 8 * sizeof(unsigned long long)));
     NK_C(cudaMalloc(&h->topn.block_counts, ((P + nk::TOPN_BLOCK_ITEMS - 1) / nk::TOPN_BLOCK_ITEMS + 1) * sizeof(unsigned int)));
     NK_C(nk::count_max_grid(cfg->use_canonical != 0, cfg->device, &h->grid));
+    NK_C(nk::post_max_grid(cfg->device, &h->post_grid));
+    NK_C(cudaMalloc(&h->post_zero, 8 * sizeof(unsigned long long) + 8 * 256 * sizeof(unsigned int)));
+    NK_C(cudaMalloc(&h->d_pack, (4 + 2 * 2048) * sizeof(unsigned long long)));
+    NK_C(cudaMallocHost(&h->h_pack, (4 + 2 * 2048) * sizeof(unsigned long long)));
+    NK_C(cudaMalloc(&h->topn.out_idx, 2048 * sizeof(unsigned long long)));
+    NK_C(cudaMalloc(&h->topn.out_spikes, 2048 * sizeof(unsigned long long)));
+    NK_C(cudaMallocHost(&h->h_top, 2 * 2048 * sizeof(unsigned long long)));
+    h->topn_cap = 2048;
 #undef NK_C
+    if (cudaMemsetAsync(h->acc, 0, P * sizeof(unsigned int), h->stream) != cudaSuccess) return bail(fail(NK_ERR_CUDA, "memset acc"));
     int rc = nk_reset(h);
     if (rc != NK_OK) return bail(rc);
     *out = h;
@@ -635,11 +721,12 @@ int nk_reset(nk_counter* h) {
     if (!h) return fail(NK_ERR_BAD_ARG, "null handle");
     NK_CUDA(cudaSetDevice(h->cfg.device));
     const unsigned long long P = h->cfg.pool_size;
-    NK_CUDA(cudaMemsetAsync(h->acc, 0, P * sizeof(unsigned int), h->stream));
-    NK_CUDA(cudaMemsetAsync(h->currents, 0, P * sizeof(unsigned long long), h->stream));
-    NK_CUDA(cudaMemsetAsync(h->v, 0, P * sizeof(float), h->stream));
-    NK_CUDA(cudaMemsetAsync(h->r, 0, P * sizeof(unsigned int), h->stream));
-    NK_CUDA(cudaMemsetAsync(h->spikes, 0, P * sizeof(unsigned long long), h->stream));
+    // acc is all-zero whenever no batch is in flight (every fold zeroes it): only a reset in the
+    // middle of a stream has to clear it.  currents / v / r / spikes become lazily zero.
+    if (h->acc_dirty || h->streaming) NK_CUDA(cudaMemsetAsync(h->acc, 0, P * sizeof(unsigned int), h->stream));
+    h->lazy_zero = true;
+    h->top_cache_valid = false;
+    h->pending_pack = false;
     NK_CUDA(cudaMemsetAsync(h->scalars, 0, 8 * sizeof(unsigned long long), h->stream));
     if (h->pending) { NK_CUDA(cudaStreamSynchronize(h->stream)); h->pending = false; h->pend_pe = PhaseEvents{}; }
     if (h->exact) NK_CUDA(nk::exact_clear(h->xt, h->cfg.pool_size, true, h->stream));
@@ -665,6 +752,8 @@ int nk_destroy(nk_counter* h) {
     cudaFree(h->table.spikes); cudaFree(h->table.v); cudaFree(h->table.r);
     cudaFree(h->topn.hist); cudaFree(h->topn.ctrl); cudaFree(h->topn.block_counts);
     cudaFree(h->topn.out_idx); cudaFree(h->topn.out_spikes);
+    cudaFree(h->post_zero); cudaFree(h->d_pack);
+    if (h->h_pack) cudaFreeHost(h->h_pack);
     if (h->h_top) cudaFreeHost(h->h_top);
     nk::exact_free(h->xt);
     cudaFree(h->d_top_uniques);
@@ -729,6 +818,7 @@ int nk_stream_accumulated(nk_counter* h, void** dev_currents) {
     if (!h) return fail(NK_ERR_BAD_ARG, "null handle");
     if (!h->streaming) return fail(NK_ERR_STATE, "nk_stream_accumulated without nk_stream_begin");
     NK_CUDA(cudaSetDevice(h->cfg.device));
+    NK_TRY(materialize_zero(h));
     if (!h->acc_dirty && h->currents_valid_overwrite) {
         NK_CUDA(cudaMemsetAsync(h->currents, 0, h->cfg.pool_size * sizeof(unsigned long long), h->stream));
         h->currents_valid_overwrite = false;
@@ -781,6 +871,7 @@ int nk_process_sequence(nk_counter* h, const uint8_t* seq, uint64_t len) {
     const uint64_t offs[2] = {0, len};
     NK_CUDA(cudaMemsetAsync(h->scalars + 2, 0, sizeof(unsigned long long), h->stream));
     h->currents_valid_overwrite = false;
+    NK_TRY(materialize_zero(h));
     NK_TRY(count_host_batch(h, seq, offs, 1, nullptr));
     NK_TRY(fold_now(h));
     nk::LifParams p{};
@@ -792,6 +883,7 @@ int nk_process_sequence(nk_counter* h, const uint8_t* seq, uint64_t len) {
     NK_CUDA(nk::launch_lif_single_tick(p, h->currents, h->stream));
     ++h->last.launches;
     h->fresh = false;
+    h->top_cache_valid = false;
     if (h->exact) NK_CUDA(nk::exact_finalize(h->xt, h->fm, h->cfg.pool_size, std::min(64u, 2u * h->cfg.k), true, h->stream));
     h->spike_bound = h->spike_bound + 1 ? h->spike_bound + 1 : h->spike_bound;
     return finish_call(h, true, nullptr);
@@ -805,6 +897,22 @@ int nk_top_n(nk_counter* h, uint64_t top_n, nk_top_entry* out, uint64_t* n_out) 
     if (n == 0) return NK_OK;
     if (!out) return fail(NK_ERR_BAD_ARG, "null out");
     if (n > nk::TOPN_MAX_N) return fail(NK_ERR_UNSUPPORTED, "top_n > %llu not supported", nk::TOPN_MAX_N);
+    if (n <= 2048) h->topn_hint = n;  // the next job's fused kernel computes this many rows
+    if (h->top_cache_valid && n <= h->top_cached_n && !h->exact) {
+        // rows already computed by the fused post kernel of the last job (sorted: a prefix is the top-n)
+        NK_TRY(resolve(h));
+        const unsigned long long cn = h->top_cached_n;
+        for (uint64_t i = 0; i < n; ++i) {
+            out[i].idx = h->h_pack[4 + i];
+            out[i].spikes = h->h_pack[4 + cn + i];
+            out[i].uniques = NK_UNIQUES_NOT_COMPUTED;
+            out[i]._pad = 0;
+        }
+        *n_out = n;
+        h->last.topn_ms = 0.f;
+        h->last.topn_launches = 0;
+        return NK_OK;
+    }
     unsigned long long cap = 1;
     while (cap < n) cap <<= 1;
     if (cap > h->topn_cap) {
@@ -816,6 +924,7 @@ int nk_top_n(nk_counter* h, uint64_t top_n, nk_top_entry* out, uint64_t* n_out) 
         NK_CUDA(cudaMallocHost(&h->h_top, 2 * cap * sizeof(unsigned long long)));
         h->topn_cap = cap;
     }
+    NK_TRY(materialize_zero(h));
     // the host-side bound on the largest cumulative spike count picks the radix passes: no round trip
     cudaEvent_t a, b;
     if (!h->pending) h->ev_used = 0;
@@ -993,6 +1102,7 @@ int nk_debug_hash(nk_counter* h, const uint64_t* words, uint64_t n, uint64_t* ha
 static int copy_out(nk_counter* h, void* dst, const void* src, size_t bytes) {
     if (!h || !dst) return fail(NK_ERR_BAD_ARG, "null argument");
     NK_TRY(resolve(h));
+    NK_TRY(materialize_zero(h));
     NK_CUDA(cudaSetDevice(h->cfg.device));
     NK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
     NK_CUDA(cudaStreamSynchronize(h->stream));

@@ -76,6 +76,7 @@ struct LifParams {
     unsigned long long* currents;
     unsigned int* acc;               // u32 batch accumulators to fold in first (fold_mode != 0); zeroed
     int fold_mode;                   // 0: currents as stored; 1: currents += acc; 2: currents = acc (overwrite)
+    int zero_state;                  // 1: v, r, spikes are logically zero and must be WRITTEN for every neuron, never read
     float* v;
     unsigned int* r;
     unsigned long long* spikes;
@@ -117,6 +118,24 @@ cudaError_t launch_topn(const unsigned long long* spikes, unsigned long long poo
 
 cudaError_t launch_hash_words(const unsigned long long* words, unsigned long long n, FastMod fm,
                               unsigned long long* hashes, unsigned long long* idx, cudaStream_t s);
+
+// fused fold + LIF(table) + top-N, one cooperative launch (nk_post.cu)
+struct PostParams {
+    LifParams lif;
+    LifTable table;
+    unsigned long long table_n;
+    unsigned long long n;            // rows wanted, 1..2048 and <= pool
+    int passes;                      // radix digits to visit (from the host-side spike bound)
+    unsigned int* hist;              // passes*256 bins, zeroed
+    unsigned long long* ctrl;        // [0] gather cursor, zeroed
+    unsigned int* seg_counts;        // ceil(pool/4096)
+    unsigned long long* out_idx;     // >= 2048
+    unsigned long long* out_spikes;  // >= 2048
+    unsigned long long* pack;        // 4 + 2n u64: {fired, 0, kmers, n, idx[n], spikes[n]}
+    const unsigned long long* kmers; // device k-mer counter of the call
+};
+cudaError_t post_max_grid(int device, int* grid);
+cudaError_t launch_post(const PostParams& q, int max_grid, cudaStream_t s);
 
 // exact side tables (nk_exact.cu)
 struct ExactTable {

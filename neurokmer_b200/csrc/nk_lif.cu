@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(LIF_THREADS) lif_table_apply_kernel(const LifP
     unsigned long long fired = 0, total = 0;
     if (i < p.pool) {
         const unsigned long long count = load_count(p, i);
-        total = p.spikes[i];
+        total = p.zero_state ? 0ull : p.spikes[i];
         if (!(p.skip_zero && count == 0)) {
             const unsigned long long c = count < table_n - 1 ? count : table_n - 1;
             p.v[i] = t.v[c];
@@ -173,6 +173,10 @@ __global__ void __launch_bounds__(LIF_THREADS) lif_table_apply_kernel(const LifP
             fired = t.spikes[c];
             total += fired;
             p.spikes[i] = total;
+        } else if (p.zero_state) {  // lazily-zero pool: the untouched neuron's state is written here
+            p.v[i] = 0.0f;
+            p.r[i] = 0u;
+            p.spikes[i] = 0ull;
         }
     }
     block_totals(fired, total, p.total_new, p.max_spikes);

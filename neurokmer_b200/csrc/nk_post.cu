@@ -1,0 +1,265 @@
+// nk_post.cu — ONE cooperative launch for everything after the count kernel (sm_100a):
+//   fold (u32 acc -> u64 currents)            src/spiking_hash.rs:174-176, :463-465
+//   LIF via the per-count table               src/spiking_hash.rs:187-200 / :544-659 (see nk_lif.cu)
+//   EnergyTracker total                       src/models.rs:159-172
+//   top-N of the spike counts                 src/spiking_hash.rs:661-673 (see nk_topn.cu)
+// The separate kernels (fold, LIF apply, 8 top-N launches, three small D2H copies) cost ~0.2 ms
+// of launch latency and pool re-reads per job against 0.9 ms of counting; here the phases are
+// separated by grid-wide barriers of a persistent grid (cooperative groups) and the result
+// (scalars + sorted top-N rows) lands in one contiguous pack for a single D2H copy.
+// Used when the LIF table path applies and N <= 2048; otherwise the separate kernels run.
+#include <cooperative_groups.h>
+
+#include "nk_kernels.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace nk {
+
+namespace {
+
+constexpr int PT = 256;                               // threads per block
+constexpr int SEG = TOPN_BLOCK_ITEMS;                 // neurons per segment (4096)
+constexpr int ITEMS = SEG / PT;                       // 16
+
+__device__ __forceinline__ bool before(unsigned long long sa, unsigned long long ia, unsigned long long sb,
+                                       unsigned long long ib) {
+    return sa > sb || (sa == sb && ia < ib);
+}
+
+__device__ __forceinline__ unsigned block_sum(unsigned v, unsigned* s_warp) {
+    v = __reduce_add_sync(0xFFFFFFFFu, v);
+    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = v;
+    __syncthreads();
+    unsigned t = 0;
+#pragma unroll
+    for (int w = 0; w < PT / 32; ++w) t += s_warp[w];
+    __syncthreads();
+    return t;
+}
+
+__global__ void __launch_bounds__(PT) post_kernel(const PostParams q) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ unsigned int s_hist[256];
+    __shared__ unsigned long long s_above[256];
+    __shared__ unsigned int s_warp[PT / 32];
+    __shared__ unsigned long long s_red[PT / 32];
+    __shared__ unsigned int s_pick;
+    __shared__ unsigned long long s_idx[2048], s_spk[2048];
+    const unsigned tid = threadIdx.x;
+    const LifParams& p = q.lif;
+    const unsigned long long nseg = (p.pool + SEG - 1) / SEG;
+    const int top = q.passes - 1;
+
+    // ---- phase 1: fold + LIF table apply + histogram of the top digit of the new spike totals ----
+    s_hist[tid] = 0;
+    __syncthreads();
+    unsigned long long fired_sum = 0;
+    for (unsigned long long seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
+#pragma unroll 4
+        for (int it = 0; it < ITEMS; ++it) {
+            const unsigned long long i = seg * SEG + (unsigned long long)it * PT + tid;
+            if (i >= p.pool) continue;
+            unsigned long long count = p.fold_mode == 2 ? 0ull : p.currents[i];
+            if (p.fold_mode) {
+                count += p.acc[i];
+                p.acc[i] = 0u;
+                p.currents[i] = count;
+            }
+            unsigned long long total = p.zero_state ? 0ull : p.spikes[i];
+            if (!(p.skip_zero && count == 0)) {
+                const unsigned long long c = count < q.table_n - 1 ? count : q.table_n - 1;
+                p.v[i] = q.table.v[c];
+                p.r[i] = q.table.r[c];
+                const unsigned f = q.table.spikes[c];
+                fired_sum += f;
+                total += f;
+                p.spikes[i] = total;
+            } else if (p.zero_state) {
+                p.v[i] = 0.0f;
+                p.r[i] = 0u;
+                p.spikes[i] = 0ull;
+            }
+            atomicAdd(&s_hist[(total >> (8 * top)) & 255u], 1u);
+        }
+    }
+    // spikes fired by this call (EnergyTracker)
+    for (int o = 16; o > 0; o >>= 1) fired_sum += __shfl_down_sync(0xFFFFFFFFu, fired_sum, o);
+    if ((tid & 31) == 0) s_red[tid >> 5] = fired_sum;
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long f = 0;
+        for (int w = 0; w < PT / 32; ++w) f += s_red[w];
+        if (f) atomicAdd(p.total_new, f);
+    }
+    if (s_hist[tid]) atomicAdd(&q.hist[top * 256 + tid], s_hist[tid]);
+    grid.sync();
+
+    // ---- phase 2: MSB-first radix select of the n-th largest total (every block redundantly) ----
+    unsigned long long prefix = 0, rank = q.n, gt = 0;
+    for (int d = top; d >= 0; --d) {
+        if (d != top) {
+            s_hist[tid] = 0;
+            __syncthreads();
+            const int hs = 8 * (d + 1);
+            for (unsigned long long seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
+#pragma unroll 4
+                for (int it = 0; it < ITEMS; ++it) {
+                    const unsigned long long i = seg * SEG + (unsigned long long)it * PT + tid;
+                    if (i >= p.pool) continue;
+                    const unsigned long long v = p.spikes[i];
+                    if ((v >> hs) == prefix) atomicAdd(&s_hist[(v >> (8 * d)) & 255u], 1u);
+                }
+            }
+            __syncthreads();
+            if (s_hist[tid]) atomicAdd(&q.hist[d * 256 + tid], s_hist[tid]);
+            grid.sync();
+        }
+        const unsigned hb = __ldcg(&q.hist[d * 256 + tid]);
+        s_hist[tid] = hb;
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long run = 0;
+            for (int x = 255; x >= 0; --x) { s_above[x] = run; run += s_hist[x]; }
+        }
+        __syncthreads();
+        if (s_above[tid] < rank && rank <= s_above[tid] + hb) s_pick = tid;
+        __syncthreads();
+        const unsigned b = s_pick;
+        prefix = (prefix << 8) | b;
+        gt += s_above[b];
+        rank -= s_above[b];
+        __syncthreads();
+    }
+    const unsigned long long T = prefix, need = rank;
+
+    // ---- phase 3: ties per segment ----
+    for (unsigned long long seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
+        unsigned c = 0;
+#pragma unroll 4
+        for (int it = 0; it < ITEMS; ++it) {
+            const unsigned long long i = seg * SEG + (unsigned long long)it * PT + tid;
+            if (i < p.pool && p.spikes[i] == T) ++c;
+        }
+        c = block_sum(c, s_warp);
+        if (tid == 0) q.seg_counts[seg] = c;
+    }
+    grid.sync();
+
+    // ---- phase 4: ordered gather: every total > T, and the `need` lowest-index totals == T ----
+    for (unsigned long long seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
+        unsigned long long before_me = 0;  // ties in earlier segments
+        for (unsigned long long s = tid; s < seg; s += PT) before_me += __ldcg(&q.seg_counts[s]);
+        for (int o = 16; o > 0; o >>= 1) before_me += __shfl_down_sync(0xFFFFFFFFu, before_me, o);
+        if ((tid & 31) == 0) s_red[tid >> 5] = before_me;
+        __syncthreads();
+        unsigned long long seg_prefix = 0;
+        for (int w = 0; w < PT / 32; ++w) seg_prefix += s_red[w];
+        __syncthreads();
+        // thread t owns ITEMS consecutive neurons (index order)
+        const unsigned long long base = seg * SEG + (unsigned long long)tid * ITEMS;
+        unsigned long long v[ITEMS];
+        unsigned eq = 0;
+#pragma unroll
+        for (int it = 0; it < ITEMS; ++it) {
+            const unsigned long long i = base + it;
+            v[it] = i < p.pool ? p.spikes[i] : 0ull;
+            if (i < p.pool && v[it] == T) ++eq;
+            if (i < p.pool && v[it] > T) {
+                const unsigned long long slot = atomicAdd(&q.ctrl[0], 1ull);
+                q.out_idx[slot] = i;
+                q.out_spikes[slot] = v[it];
+            }
+        }
+        s_hist[tid] = eq;
+        __syncthreads();
+        for (int o = 1; o < PT; o <<= 1) {
+            const unsigned a = tid >= (unsigned)o ? s_hist[tid - o] : 0u;
+            __syncthreads();
+            s_hist[tid] += a;
+            __syncthreads();
+        }
+        unsigned long long r = seg_prefix + (s_hist[tid] - eq);
+        if (eq != 0 && r < need) {
+#pragma unroll
+            for (int it = 0; it < ITEMS; ++it) {
+                const unsigned long long i = base + it;
+                if (i < p.pool && v[it] == T) {
+                    if (r < need) {
+                        q.out_idx[gt + r] = i;
+                        q.out_spikes[gt + r] = T;
+                    }
+                    ++r;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    grid.sync();
+
+    // ---- phase 5: block 0 sorts the n candidates (spikes desc, idx asc) and packs the result ----
+    if (blockIdx.x != 0) return;
+    const unsigned n = (unsigned)q.n;
+    unsigned N = 1;
+    while (N < n) N <<= 1;
+    for (unsigned i = tid; i < N; i += PT) {
+        s_idx[i] = i < n ? __ldcg(&q.out_idx[i]) : ~0ull;
+        s_spk[i] = i < n ? __ldcg(&q.out_spikes[i]) : 0ull;
+    }
+    __syncthreads();
+    for (unsigned k = 2; k <= N; k <<= 1) {
+        for (unsigned j = k >> 1; j > 0; j >>= 1) {
+            for (unsigned i = tid; i < N; i += PT) {
+                const unsigned l = i ^ j;
+                if (l > i) {
+                    const bool up = (i & k) == 0;
+                    const bool swap = up ? before(s_spk[l], s_idx[l], s_spk[i], s_idx[i])
+                                         : before(s_spk[i], s_idx[i], s_spk[l], s_idx[l]);
+                    if (swap) {
+                        const unsigned long long a = s_idx[i], b = s_spk[i];
+                        s_idx[i] = s_idx[l]; s_spk[i] = s_spk[l];
+                        s_idx[l] = a; s_spk[l] = b;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // pack: [0] spikes fired by this call, [1] unused, [2] k-mers of the call, [3] n, then idx[n], spikes[n]
+    for (unsigned i = tid; i < n; i += PT) {
+        q.out_idx[i] = s_idx[i];
+        q.out_spikes[i] = s_spk[i];
+        q.pack[4 + i] = s_idx[i];
+        q.pack[4 + n + i] = s_spk[i];
+    }
+    if (tid == 0) {
+        q.pack[0] = *((volatile unsigned long long*)p.total_new);
+        q.pack[1] = 0;
+        q.pack[2] = *((volatile unsigned long long*)q.kmers);
+        q.pack[3] = n;
+    }
+}
+
+}  // namespace
+
+cudaError_t post_max_grid(int device, int* grid) {
+    int sms = 0, per_sm = 0;
+    cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, post_kernel, PT, 0);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 4) per_sm = 4;
+    *grid = sms * per_sm;
+    return cudaSuccess;
+}
+
+cudaError_t launch_post(const PostParams& q, int max_grid, cudaStream_t s) {
+    const unsigned long long nseg = (q.lif.pool + SEG - 1) / SEG;
+    int grid = (int)(nseg < (unsigned long long)max_grid ? nseg : (unsigned long long)max_grid);
+    if (grid < 1) grid = 1;
+    void* args[] = {(void*)&q};
+    return cudaLaunchCooperativeKernel((const void*)post_kernel, dim3(grid), dim3(PT), args, 0, s);
+}
+
+}  // namespace nk

@@ -142,7 +142,7 @@ def test_process_parallel_full(coracle, k, pool, n):
     o = oracle_counter(k, pool)
     c.process_batch(bases, offsets)
     o.process_parallel(bases, offsets)
-    assert c.timings()["lif_path"] == 2  # fresh state: per-count table
+    assert c.timings()["lif_path"] in (2, 3)  # fresh state: per-count table (3 = fused with top-N)
     assert_state_equal(c, o)
     assert o.total_spikes > 0
     for topn in (1, 20, 500, 3000):
@@ -168,7 +168,7 @@ def test_lif_table_equals_direct(coracle):
     a, b = make(21, pool), make(21, pool)
     b.debug_set_lif_path(1)
     a.process_parallel(seqs); b.process_parallel(seqs)
-    assert a.timings()["lif_path"] == 2 and b.timings()["lif_path"] == 1
+    assert a.timings()["lif_path"] in (2, 3) and b.timings()["lif_path"] == 1
     np.testing.assert_array_equal(a.currents(), b.currents())
     np.testing.assert_array_equal(a.spike_counts(), b.spike_counts())
     np.testing.assert_array_equal(a.refractory_ticks(), b.refractory_ticks())
@@ -447,7 +447,7 @@ def test_lif_golden_rows_gpu():
             c.synchronize()                    # the hand-off is stream-ordered, cudaMemcpy is not
             copy_h2d(ptr, counts)
             c.stream_finish()
-            assert c.timings()["lif_path"] == (1 if force_direct else 2)
+            assert c.timings()["lif_path"] in ((1,) if force_direct else (2, 3))
             assert c.spike_counts().tolist() == [r[1] for r in blk["rows"]]
             assert c.voltages().view(np.uint32).tolist() == [r[2] for r in blk["rows"]]
             assert c.refractory_ticks().tolist() == [r[3] for r in blk["rows"]]

@@ -38,7 +38,7 @@ __device__ __forceinline__ unsigned block_sum(unsigned v, unsigned* s_warp) {
     return t;
 }
 
-__global__ void __launch_bounds__(PT) post_kernel(const PostParams q) {
+__global__ void __launch_bounds__(PT, 3) post_kernel(const PostParams q) {
     cg::grid_group grid = cg::this_grid();
     __shared__ unsigned int s_hist[256];
     __shared__ unsigned long long s_above[256];
@@ -55,32 +55,59 @@ __global__ void __launch_bounds__(PT) post_kernel(const PostParams q) {
     s_hist[tid] = 0;
     __syncthreads();
     unsigned long long fired_sum = 0;
+    // loads are issued in batches of B independent items (memory-level parallelism: a persistent grid
+    // has only ~150 k threads for millions of neurons, so every thread must keep several loads in flight)
+    constexpr int B = 8;
+    unsigned int* __restrict__ acc = p.acc;
+    unsigned long long* __restrict__ currents = p.currents;
+    unsigned long long* __restrict__ spikes = p.spikes;
+    float* __restrict__ vv = p.v;
+    unsigned int* __restrict__ rr = p.r;
+    const unsigned int* __restrict__ tsp = q.table.spikes;
+    const float* __restrict__ tv = q.table.v;
+    const unsigned int* __restrict__ tr = q.table.r;
     for (unsigned long long seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
-#pragma unroll 4
-        for (int it = 0; it < ITEMS; ++it) {
-            const unsigned long long i = seg * SEG + (unsigned long long)it * PT + tid;
-            if (i >= p.pool) continue;
-            unsigned long long count = p.fold_mode == 2 ? 0ull : p.currents[i];
-            if (p.fold_mode) {
-                count += p.acc[i];
-                p.acc[i] = 0u;
-                p.currents[i] = count;
+        for (int b0 = 0; b0 < ITEMS; b0 += B) {
+            unsigned long long count[B], total[B];
+            bool ok[B];
+#pragma unroll
+            for (int u = 0; u < B; ++u) {
+                const unsigned long long i = seg * SEG + (unsigned long long)(b0 + u) * PT + tid;
+                ok[u] = i < p.pool;
+                count[u] = (ok[u] && p.fold_mode != 2) ? currents[i] : 0ull;
+                if (ok[u] && p.fold_mode) count[u] += acc[i];
+                total[u] = (ok[u] && !p.zero_state) ? spikes[i] : 0ull;
             }
-            unsigned long long total = p.zero_state ? 0ull : p.spikes[i];
-            if (!(p.skip_zero && count == 0)) {
-                const unsigned long long c = count < q.table_n - 1 ? count : q.table_n - 1;
-                p.v[i] = q.table.v[c];
-                p.r[i] = q.table.r[c];
-                const unsigned f = q.table.spikes[c];
-                fired_sum += f;
-                total += f;
-                p.spikes[i] = total;
-            } else if (p.zero_state) {
-                p.v[i] = 0.0f;
-                p.r[i] = 0u;
-                p.spikes[i] = 0ull;
+            unsigned c[B], f[B], tr_[B];
+            float tv_[B];
+#pragma unroll
+            for (int u = 0; u < B; ++u) {
+                c[u] = (unsigned)(count[u] < q.table_n - 1 ? count[u] : q.table_n - 1);
+                f[u] = tsp[c[u]];
+                tv_[u] = tv[c[u]];
+                tr_[u] = tr[c[u]];
             }
-            atomicAdd(&s_hist[(total >> (8 * top)) & 255u], 1u);
+#pragma unroll
+            for (int u = 0; u < B; ++u) {
+                const unsigned long long i = seg * SEG + (unsigned long long)(b0 + u) * PT + tid;
+                if (!ok[u]) continue;
+                if (p.fold_mode) {
+                    acc[i] = 0u;
+                    currents[i] = count[u];
+                }
+                if (!(p.skip_zero && count[u] == 0)) {
+                    vv[i] = tv_[u];
+                    rr[i] = tr_[u];
+                    fired_sum += f[u];
+                    total[u] += f[u];
+                    spikes[i] = total[u];
+                } else if (p.zero_state) {
+                    vv[i] = 0.0f;
+                    rr[i] = 0u;
+                    spikes[i] = 0ull;
+                }
+                atomicAdd(&s_hist[(total[u] >> (8 * top)) & 255u], 1u);
+            }
         }
     }
     // spikes fired by this call (EnergyTracker)
@@ -103,12 +130,16 @@ __global__ void __launch_bounds__(PT) post_kernel(const PostParams q) {
             __syncthreads();
             const int hs = 8 * (d + 1);
             for (unsigned long long seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
-#pragma unroll 4
+                unsigned long long v[ITEMS];
+#pragma unroll
                 for (int it = 0; it < ITEMS; ++it) {
                     const unsigned long long i = seg * SEG + (unsigned long long)it * PT + tid;
-                    if (i >= p.pool) continue;
-                    const unsigned long long v = p.spikes[i];
-                    if ((v >> hs) == prefix) atomicAdd(&s_hist[(v >> (8 * d)) & 255u], 1u);
+                    v[it] = i < p.pool ? spikes[i] : ~0ull;
+                }
+#pragma unroll
+                for (int it = 0; it < ITEMS; ++it) {
+                    const unsigned long long i = seg * SEG + (unsigned long long)it * PT + tid;
+                    if (i < p.pool && (v[it] >> hs) == prefix) atomicAdd(&s_hist[(v[it] >> (8 * d)) & 255u], 1u);
                 }
             }
             __syncthreads();
@@ -136,10 +167,10 @@ __global__ void __launch_bounds__(PT) post_kernel(const PostParams q) {
     // ---- phase 3: ties per segment ----
     for (unsigned long long seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
         unsigned c = 0;
-#pragma unroll 4
+#pragma unroll
         for (int it = 0; it < ITEMS; ++it) {
             const unsigned long long i = seg * SEG + (unsigned long long)it * PT + tid;
-            if (i < p.pool && p.spikes[i] == T) ++c;
+            if (i < p.pool && spikes[i] == T) ++c;
         }
         c = block_sum(c, s_warp);
         if (tid == 0) q.seg_counts[seg] = c;
@@ -163,7 +194,7 @@ __global__ void __launch_bounds__(PT) post_kernel(const PostParams q) {
 #pragma unroll
         for (int it = 0; it < ITEMS; ++it) {
             const unsigned long long i = base + it;
-            v[it] = i < p.pool ? p.spikes[i] : 0ull;
+            v[it] = i < p.pool ? spikes[i] : 0ull;
             if (i < p.pool && v[it] == T) ++eq;
             if (i < p.pool && v[it] > T) {
                 const unsigned long long slot = atomicAdd(&q.ctrl[0], 1ull);
@@ -249,7 +280,7 @@ cudaError_t post_max_grid(int device, int* grid) {
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, post_kernel, PT, 0);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
-    if (per_sm > 4) per_sm = 4;
+    if (per_sm > 6) per_sm = 6;
     *grid = sms * per_sm;
     return cudaSuccess;
 }

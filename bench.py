@@ -230,13 +230,50 @@ def gpu_arm(args):
 
     trace = []
 
+    # sharded-pool mode (default for N > 1): the reduce-scatter of the counts is fused into the LIF
+    # kernel over NVLink peer mappings; NCCL only carries a barrier and a few hundred bytes of results
+    fused = world > 1 and args.dist == "fused"
+    if fused:
+        handle, _ = c.dist_export()
+        handles = [None] * world
+        dist.all_gather_object(handles, handle)
+        c.dist_setup(rank, world, handles=b"".join(handles))
+        barrier_t = torch.zeros(1, dtype=torch.int32, device="cuda")
+        pack_views = {}
+
+    def finish_distributed():
+        """everything after counting, for N > 1"""
+        if not fused:
+            allreduce_currents()
+            c.stream_finish()
+            return
+        a0, a1, a2, a3 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
+        with torch.cuda.stream(stream):
+            a0.record(stream)
+            dist.all_reduce(barrier_t)                     # every rank has finished counting
+            a1.record(stream)
+        ptr, n64, each = c.dist_post()                     # slice LIF + top-N, counts summed over peers' memory
+        if ptr not in pack_views:
+            pack_views[ptr] = (torch.as_tensor(CurrentsView(ptr, n64), device=torch.device("cuda", local)),
+                               torch.empty(world * n64, dtype=torch.int64, device="cuda"))
+        mine, gathered = pack_views[ptr]
+        with torch.cuda.stream(stream):
+            a2.record(stream)
+            dist.all_gather_into_tensor(gathered, mine)    # result packs; also: everyone is done reading my counts
+            a3.record(stream)
+        c.dist_complete(gathered.data_ptr(), each)
+        ar_events.append((a0, a1, a2, a3))
+
     def job_resident():
         t = [time.perf_counter()]
         c.reset(); t.append(time.perf_counter())
         c.stream_begin(); t.append(time.perf_counter())
         c.process_staged(NBASES, nseq, 1); t.append(time.perf_counter())
-        allreduce_currents(); t.append(time.perf_counter())
-        c.stream_finish(); t.append(time.perf_counter())
+        if world > 1:
+            finish_distributed(); t.append(time.perf_counter()); t.append(time.perf_counter())
+        else:
+            allreduce_currents(); t.append(time.perf_counter())
+            c.stream_finish(); t.append(time.perf_counter())
         top = c.top_abundant_neurons(TOPN); t.append(time.perf_counter())
         trace.append(np.diff(t) * 1e3)
         return top
@@ -245,8 +282,10 @@ def gpu_arm(args):
         c.reset()
         c.stream_begin()
         c.stream_push(pinned.array, offsets)
-        allreduce_currents()
-        c.stream_finish()
+        if world > 1:
+            finish_distributed()
+        else:
+            c.stream_finish()
         return c.top_abundant_neurons(TOPN)
 
     def barrier():
@@ -285,10 +324,13 @@ def gpu_arm(args):
     sampler = ClockSampler(local) if rank == 0 else None
     ar_events.clear()
     steps_res, phases, top, clocks = timed(job_resident, args.steps, sampler)
-    ar_ms = float(np.mean([a.elapsed_time(b) for a, b in ar_events])) if ar_events else 0.0
+    if ar_events and len(ar_events[0]) == 4:
+        ar_ms = float(np.mean([e[0].elapsed_time(e[1]) + e[2].elapsed_time(e[3]) for e in ar_events]))
+    else:
+        ar_ms = float(np.mean([a.elapsed_time(b) for a, b in ar_events])) if ar_events else 0.0
     timed(job_e2e, 2)
     steps_e2e, phases_e2e, top_e2e, _ = timed(job_e2e, args.steps)
-    assert top == top_e2e or world > 1, "resident and end-to-end legs disagree"
+    assert top == top_e2e, "resident and end-to-end legs disagree"
 
     if os.environ.get("NK_TRACE"):
         print(f"[rank {rank}] per-step (event ms, wall ms):", [(round(a, 3), round(b, 3)) for a, b in steps_res[:12]], file=sys.stderr)
@@ -350,12 +392,16 @@ def gpu_arm(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "k": K, "pool_size": POOL, "lif_steps": STEPS_LIF, "top_n": TOPN,
                        "kmers_per_step_per_gpu": KMERS, "l2": "flushed before every step (256 MiB fill)",
-                       "parallelism": f"dp{world}: sequence-chunk shards, full pool replica, one NCCL all-reduce"},
+                       "parallelism": f"dp{world}: sequence-chunk shards, full accumulator replica per GPU, "
+                                      + ("neuron-sliced LIF/top-N with peer-memory reduce" if fused else "one NCCL all-reduce")},
             "e2e": {"value": e2e_value, "unit": "kmers/s", "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": int(phases_e2e[-1]["h2d_bytes"]),
                     "d2h_bytes_per_step": int(phases_e2e[-1]["d2h_bytes"] + 24 + 16 * TOPN)},
             "gpu_launches": launches * args.steps,
-            "phases_ms": ph, "allreduce_ms": ar_ms, "lif_path": int(phases[-1]["lif_path"]),
+            "phases_ms": ph, "collective_ms": ar_ms,
+            "collective": ("none" if world == 1 else ("barrier + all-gather of result packs (NCCL); count reduce-scatter fused into the LIF "
+                           "kernel over NVLink peer memory" if fused else "all-reduce of the u64 currents (NCCL)")),
+            "lif_path": int(phases[-1]["lif_path"]),
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "result": {"total_spikes": total_spikes, "top1": list(top[0][:2]) if top else None},
         }
@@ -373,6 +419,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--dist", default="fused", choices=["fused", "allreduce"],
+                    help="N > 1: peer-memory reduce fused into the LIF kernel (default) or NCCL all-reduce of the currents")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

@@ -207,6 +207,23 @@ NK_API int nk_process_staged(nk_counter* h, uint64_t nbytes, uint64_t nseq, int 
  * nk_stream_finish.  nk_stream_end == accumulated + finish. */
 NK_API int nk_stream_accumulated(nk_counter* h, void** dev_currents);
 NK_API int nk_stream_finish(nk_counter* h);
+/* Sharded-pool multi-GPU mode: the reduce-scatter of the per-rank counts is fused into the LIF
+ * kernel through NVLink peer mappings of every rank's accumulators (no 16 MB all-reduce).
+ *   setup (once):  nk_dist_export on every rank -> exchange the 64-byte IPC handles ->
+ *                  nk_dist_setup(rank, world, handles, NULL)   [same process: raw pointers instead]
+ *   per job:       nk_reset; nk_stream_begin; push / process_staged(mode 1);
+ *                  <cross-rank barrier on nk_cuda_stream()>;
+ *                  nk_dist_post -> all-gather the returned packs on the stream -> nk_dist_complete
+ * Afterwards nk_total_spikes / nk_energy_used / nk_top_n answer for the WHOLE pool on every rank;
+ * nk_copy_* return data that is only defined inside this rank's slice (nk_dist_slice).
+ * Fresh-state jobs only (one job per nk_reset); otherwise nk_dist_post returns NK_ERR_UNSUPPORTED
+ * and the all-reduce flow above applies. */
+NK_API int nk_dist_export(nk_counter* h, void* ipc_handle_64_bytes, void** raw_acc);
+NK_API int nk_dist_setup(nk_counter* h, int rank, int world, const void* ipc_handles /* world*64 B */,
+                         void* const* raw_ptrs /* world pointers, same process */);
+NK_API int nk_dist_post(nk_counter* h, void** dev_pack, uint64_t* pack_u64s, uint64_t* n_each);
+NK_API int nk_dist_complete(nk_counter* h, const void* dev_gathered_packs, uint64_t n_each);
+NK_API int nk_dist_slice(const nk_counter* h, uint64_t* lo, uint64_t* len);
 /* The CUDA stream (cudaStream_t) the handle's kernels run on. */
 NK_API int nk_cuda_stream(nk_counter* h, void** stream);
 NK_API int nk_synchronize(nk_counter* h);

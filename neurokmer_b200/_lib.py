@@ -24,7 +24,8 @@ SYMBOLS = [
     "nk_copy_exact_table", "nk_copy_uniques", "nk_debug_kmers", "nk_debug_hash",
     "nk_copy_currents", "nk_copy_spike_counts", "nk_copy_voltages", "nk_copy_refractory",
     "nk_last_timings", "nk_debug_set_lif_path", "nk_calibrate", "nk_stage_reserve", "nk_process_staged", "nk_stream_accumulated",
-    "nk_stream_finish", "nk_cuda_stream", "nk_synchronize", "nk_synth_fill", "nk_host_alloc",
+    "nk_stream_finish", "nk_dist_export", "nk_dist_setup", "nk_dist_post", "nk_dist_complete", "nk_dist_slice",
+    "nk_cuda_stream", "nk_synchronize", "nk_synth_fill", "nk_host_alloc",
     "nk_host_free", "nk_pack_kmer",
 ]
 
@@ -104,6 +105,11 @@ def load() -> C.CDLL:
         "nk_process_staged": (i32, [vp, u64, u64, i32]),
         "nk_stream_accumulated": (i32, [vp, P(vp)]),
         "nk_stream_finish": (i32, [vp]),
+        "nk_dist_export": (i32, [vp, vp, P(vp)]),
+        "nk_dist_setup": (i32, [vp, i32, i32, vp, P(vp)]),
+        "nk_dist_post": (i32, [vp, P(vp), P(u64), P(u64)]),
+        "nk_dist_complete": (i32, [vp, vp, u64]),
+        "nk_dist_slice": (i32, [vp, P(u64), P(u64)]),
         "nk_cuda_stream": (i32, [vp, P(vp)]),
         "nk_synchronize": (i32, [vp]),
         "nk_synth_fill": (i32, [vp, vp, u64, u64, u64, u32]),

@@ -257,6 +257,33 @@ class SpikingKmerCounter:
     def stream_finish(self) -> None:
         check(self._L.nk_stream_finish(self._h))
 
+    # sharded-pool multi-GPU mode (reduce-scatter fused into the LIF kernel over NVLink peer memory)
+    def dist_export(self) -> Tuple[bytes, int]:
+        buf = C.create_string_buffer(64)
+        raw = C.c_void_p()
+        check(self._L.nk_dist_export(self._h, buf, C.byref(raw)))
+        return buf.raw, raw.value
+
+    def dist_setup(self, rank: int, world: int, handles: Optional[bytes] = None, raw_ptrs: Optional[Sequence[int]] = None) -> None:
+        if raw_ptrs is not None:
+            arr = (C.c_void_p * world)(*[C.c_void_p(p) for p in raw_ptrs])
+            check(self._L.nk_dist_setup(self._h, rank, world, None, arr))
+        else:
+            check(self._L.nk_dist_setup(self._h, rank, world, C.c_char_p(handles), None))
+
+    def dist_post(self) -> Tuple[int, int, int]:
+        p, n64, each = C.c_void_p(), C.c_uint64(), C.c_uint64()
+        check(self._L.nk_dist_post(self._h, C.byref(p), C.byref(n64), C.byref(each)))
+        return p.value, n64.value, each.value
+
+    def dist_complete(self, dev_gathered: int, n_each: int) -> None:
+        check(self._L.nk_dist_complete(self._h, dev_gathered, n_each))
+
+    def dist_slice(self) -> Tuple[int, int]:
+        lo, ln = C.c_uint64(), C.c_uint64()
+        check(self._L.nk_dist_slice(self._h, C.byref(lo), C.byref(ln)))
+        return lo.value, ln.value
+
     def cuda_stream(self) -> int:
         p = C.c_void_p()
         check(self._L.nk_cuda_stream(self._h, C.byref(p)))

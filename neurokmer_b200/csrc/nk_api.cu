@@ -130,6 +130,12 @@ struct nk_counter {
     unsigned long long topn_hint = 20;         // rows computed speculatively by the fused kernel (CLI: 20)
     unsigned long long top_cached_n = 0;       // rows of the last fused launch (valid until state changes)
     bool top_cache_valid = false, pending_pack = false;
+    // multi-GPU sharded-pool mode (nk_dist_*): peer mappings of every rank's accumulators
+    int dist_rank = 0, dist_world = 0;
+    const unsigned int* dist_peer[16] = {};
+    bool dist_ipc_opened[16] = {};
+    unsigned long long dist_lo = 0, dist_len = 0;
+    unsigned long long* d_merged = nullptr;
     // exact side tables (opt-in, nk_enable_exact_counts)
     bool exact = false;
     nk::ExactTable xt;
@@ -755,6 +761,8 @@ int nk_destroy(nk_counter* h) {
     cudaFree(h->post_zero); cudaFree(h->d_pack);
     if (h->h_pack) cudaFreeHost(h->h_pack);
     if (h->h_top) cudaFreeHost(h->h_top);
+    for (int r = 0; r < 16; ++r) if (h->dist_ipc_opened[r]) cudaIpcCloseMemHandle((void*)h->dist_peer[r]);
+    cudaFree(h->d_merged);
     nk::exact_free(h->xt);
     cudaFree(h->d_top_uniques);
     free_devbuf(h->buf[0]); free_devbuf(h->buf[1]); free_devbuf(h->staged);
@@ -897,7 +905,7 @@ int nk_top_n(nk_counter* h, uint64_t top_n, nk_top_entry* out, uint64_t* n_out) 
     if (n == 0) return NK_OK;
     if (!out) return fail(NK_ERR_BAD_ARG, "null out");
     if (n > nk::TOPN_MAX_N) return fail(NK_ERR_UNSUPPORTED, "top_n > %llu not supported", nk::TOPN_MAX_N);
-    if (n <= 2048) h->topn_hint = n;  // the next job's fused kernel computes this many rows
+    if (n <= 2048 && n > h->topn_hint) h->topn_hint = n;  // later jobs' fused kernel computes at least this many rows
     if (h->top_cache_valid && n <= h->top_cached_n && !h->exact) {
         // rows already computed by the fused post kernel of the last job (sorted: a prefix is the top-n)
         NK_TRY(resolve(h));
@@ -924,6 +932,9 @@ int nk_top_n(nk_counter* h, uint64_t top_n, nk_top_entry* out, uint64_t* n_out) 
         NK_CUDA(cudaMallocHost(&h->h_top, 2 * cap * sizeof(unsigned long long)));
         h->topn_cap = cap;
     }
+    if (h->dist_world && h->last.lif_path == 4)
+        return fail(NK_ERR_STATE, "sharded-pool mode computed %llu rows; ask for more BEFORE the job (the hint is now %llu)",
+                    h->top_cached_n, h->topn_hint);
     NK_TRY(materialize_zero(h));
     // the host-side bound on the largest cumulative spike count picks the radix passes: no round trip
     cudaEvent_t a, b;
@@ -1161,6 +1172,170 @@ int nk_calibrate(nk_counter* h, int which, double* out) {
     if (which == 2) NK_CUDA(cudaMemsetAsync(h->acc, 0, h->cfg.pool_size * sizeof(unsigned int), h->stream));
     NK_CUDA(cudaStreamSynchronize(h->stream));
     *out = best;
+    return NK_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Multi-GPU, sharded pool: "reduce-scatter fused into the LIF kernel" over NVLink peer memory.
+// Every rank counts its shard into its own full u32 accumulator array; rank r then owns the
+// neuron slice [lo_r, hi_r) and its post kernel reads that slice of EVERY rank's accumulators
+// straight through peer mappings (CUDA IPC), sums, runs LIF + a slice-local top-N, and emits a
+// small result pack; the packs are all-gathered (a few hundred bytes) and merged on the device.
+// Against all-reduce(16 MB) + full-pool LIF + full-pool top-N on every rank this moves 1/world of
+// the bytes and does 1/world of the per-neuron work.  Fresh-state (table) path only: otherwise
+// nk_dist_post returns NK_ERR_UNSUPPORTED and the caller uses nk_stream_accumulated + all-reduce.
+// ---------------------------------------------------------------------------
+int nk_dist_export(nk_counter* h, void* handle64, void** raw_acc) {
+    if (!h) return fail(NK_ERR_BAD_ARG, "null handle");
+    NK_CUDA(cudaSetDevice(h->cfg.device));
+    if (handle64) {
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+        cudaIpcMemHandle_t mh;
+        NK_CUDA(cudaIpcGetMemHandle(&mh, h->acc));
+        std::memcpy(handle64, &mh, 64);
+    }
+    if (raw_acc) *raw_acc = h->acc;
+    return NK_OK;
+}
+
+int nk_dist_setup(nk_counter* h, int rank, int world, const void* handles, void* const* raw_ptrs) {
+    if (!h) return fail(NK_ERR_BAD_ARG, "null handle");
+    if (world < 1 || world > 16 || rank < 0 || rank >= world) return fail(NK_ERR_BAD_ARG, "bad rank/world (world <= 16)");
+    if (!handles && !raw_ptrs) return fail(NK_ERR_BAD_ARG, "need IPC handles or raw pointers");
+    NK_CUDA(cudaSetDevice(h->cfg.device));
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) { h->dist_peer[r] = h->acc; continue; }
+        if (raw_ptrs) { h->dist_peer[r] = (const unsigned int*)raw_ptrs[r]; continue; }
+        cudaIpcMemHandle_t mh;
+        std::memcpy(&mh, (const char*)handles + 64 * r, 64);
+        void* p = nullptr;
+        NK_CUDA(cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess));
+        h->dist_peer[r] = (const unsigned int*)p;
+        h->dist_ipc_opened[r] = true;
+    }
+    h->dist_rank = rank;
+    h->dist_world = world;
+    const unsigned long long P = h->cfg.pool_size, per = (P + world - 1) / world;
+    h->dist_lo = std::min(P, per * rank);
+    h->dist_len = std::min(P, h->dist_lo + per) - h->dist_lo;
+    if (!h->d_merged) NK_CUDA(cudaMalloc(&h->d_merged, (4 + 2 * 2048) * sizeof(unsigned long long)));
+    return NK_OK;
+}
+
+// Enqueue this rank's slice post kernel.  PRECONDITION (caller): every rank's counting is complete
+// and ordered before this call on the handle's stream (e.g. a 1-element NCCL all-reduce on it).
+int nk_dist_post(nk_counter* h, void** dev_pack, uint64_t* pack_u64s, uint64_t* n_each) {
+    if (!h || !dev_pack || !pack_u64s || !n_each) return fail(NK_ERR_BAD_ARG, "null argument");
+    if (!h->dist_world) return fail(NK_ERR_STATE, "nk_dist_setup was not called");
+    if (!h->streaming) return fail(NK_ERR_STATE, "nk_dist_post without nk_stream_begin");
+    NK_CUDA(cudaSetDevice(h->cfg.device));
+    const unsigned long long per = (h->cfg.pool_size + h->dist_world - 1) / h->dist_world;
+    const unsigned long long n_top = std::min<unsigned long long>(h->topn_hint, per);
+    const bool table_ok = h->fresh && !h->force_direct && !h->exact && h->cfg.steps > 0 && std::isfinite(h->cfg.threshold) &&
+                          std::isfinite(h->cfg.leak) && saturation_count(h->cfg) < (1ull << 20);
+    if (!table_ok || n_top < 1 || n_top * h->dist_world > 2048 || h->dist_len == 0)
+        return fail(NK_ERR_UNSUPPORTED, "sharded post needs the fresh-state table path, world*top_n <= 2048 and a non-empty slice");
+    // the table (depends on the LIF parameters only)
+    nk::LifParams p{};
+    p.currents = h->currents + h->dist_lo;
+    p.acc = h->acc;
+    p.fold_mode = 2;
+    p.zero_state = 1;  // the slice's v, r, spikes are written, never read (fresh state)
+    p.v = h->v + h->dist_lo;
+    p.r = h->r + h->dist_lo;
+    p.spikes = h->spikes + h->dist_lo;
+    p.total_new = h->scalars + 0;
+    p.max_spikes = h->scalars + 1;
+    p.pool = h->dist_len;
+    p.steps = h->cfg.steps;
+    p.thr = h->cfg.threshold;
+    p.leak = h->cfg.leak;
+    p.period = h->cfg.refractory;
+    p.skip_zero = 0;
+    const unsigned long long table_n = saturation_count(h->cfg) + 1;
+    const nk_config& a = h->cfg; const nk_config& b = h->table_cfg;
+    const bool same = h->table_valid && h->table_n == table_n && a.steps == b.steps && a.threshold == b.threshold &&
+                      a.leak == b.leak && a.refractory == b.refractory;
+    if (!same) {
+        if (table_n > h->table_cap) {
+            cudaFree(h->table.spikes); cudaFree(h->table.v); cudaFree(h->table.r);
+            h->table = nk::LifTable{}; h->table_cap = 0;
+            NK_CUDA(cudaMalloc(&h->table.spikes, table_n * sizeof(unsigned int)));
+            NK_CUDA(cudaMalloc(&h->table.v, table_n * sizeof(float)));
+            NK_CUDA(cudaMalloc(&h->table.r, table_n * sizeof(unsigned int)));
+            h->table_cap = table_n;
+        }
+        NK_CUDA(nk::launch_lif_table_build(p, h->table, table_n, h->stream));
+        ++h->last.launches;
+        h->table_valid = true; h->table_cfg = h->cfg; h->table_n = table_n;
+    }
+    const unsigned long long per_call = (h->cfg.steps + h->cfg.refractory) / ((unsigned long long)h->cfg.refractory + 1ull);
+    nk::PostParams q{};
+    q.lif = p;
+    q.table = h->table;
+    q.table_n = table_n;
+    q.n = std::min<unsigned long long>(n_top, h->dist_len);
+    int bits = 0;
+    while (bits < 64 && (per_call >> bits)) ++bits;
+    q.passes = std::max(1, (bits + 7) / 8);
+    q.ctrl = h->post_zero;
+    q.hist = reinterpret_cast<unsigned int*>(h->post_zero + 8);
+    q.seg_counts = h->topn.block_counts;
+    q.out_idx = h->topn.out_idx;
+    q.out_spikes = h->topn.out_spikes;
+    q.pack = h->d_pack;
+    q.kmers = h->scalars + 2;
+    q.npeers = h->dist_world;
+    for (int r = 0; r < h->dist_world; ++r) q.peer_acc[r] = h->dist_peer[r];
+    q.slice_lo = h->dist_lo;
+    // rows are padded to n_top per rank so that every rank's pack has the same size
+    NK_CUDA(cudaMemsetAsync(h->d_pack, 0, (4 + 2 * n_top) * sizeof(unsigned long long), h->stream));
+    NK_CUDA(cudaMemsetAsync(h->scalars, 0, sizeof(unsigned long long), h->stream));
+    NK_CUDA(cudaMemsetAsync(h->post_zero, 0, 8 * sizeof(unsigned long long) + 8 * 256 * sizeof(unsigned int), h->stream));
+    NK_CUDA(nk::launch_post(q, h->post_grid, h->stream));
+    ++h->last.launches;
+    h->last.lif_path = 4;
+    *dev_pack = h->d_pack;
+    *pack_u64s = 4 + 2 * n_top;
+    *n_each = n_top;
+    return NK_OK;
+}
+
+// `dev_gathered`: the world packs, rank-major, all-gathered by the caller on the handle's stream
+// (which also proves that every rank has finished reading this rank's accumulators).
+int nk_dist_complete(nk_counter* h, const void* dev_gathered, uint64_t n_each) {
+    if (!h || !dev_gathered) return fail(NK_ERR_BAD_ARG, "null argument");
+    if (!h->dist_world || !h->streaming) return fail(NK_ERR_STATE, "nk_dist_complete without nk_dist_post");
+    NK_CUDA(cudaSetDevice(h->cfg.device));
+    const unsigned long long n_out = std::min<unsigned long long>(h->topn_hint, h->cfg.pool_size);
+    NK_CUDA(nk::launch_merge_packs((const unsigned long long*)dev_gathered, h->dist_world, n_each, n_out, h->d_merged, h->stream));
+    ++h->last.launches;
+    // accumulators are all-zero between jobs (every peer has read them by now)
+    NK_CUDA(cudaMemsetAsync(h->acc, 0, h->cfg.pool_size * sizeof(unsigned int), h->stream));
+    const size_t bytes = (4 + 2 * n_out) * sizeof(unsigned long long);
+    NK_CUDA(cudaMemcpyAsync(h->h_pack, h->d_merged, bytes, cudaMemcpyDeviceToHost, h->stream));
+    h->last.d2h_bytes += bytes;
+    h->acc_dirty = false;
+    h->acc_kmers = 0;
+    h->currents_valid_overwrite = false;
+    h->lazy_zero = false;  // NOTE: only this rank's slice of currents/v/r/spikes is defined in this mode
+    h->fresh = false;
+    h->spike_bound += (h->cfg.steps + h->cfg.refractory) / ((unsigned long long)h->cfg.refractory + 1ull);
+    h->top_cached_n = n_out;
+    h->top_cache_valid = true;
+    h->pending_pack = true;
+    h->pending = true;
+    h->pending_lif = true;
+    h->pending_timings = true;
+    h->pend_pe = h->stream_pe;
+    h->streaming = false;
+    return NK_OK;
+}
+
+int nk_dist_slice(const nk_counter* h, uint64_t* lo, uint64_t* len) {
+    if (!h || !lo || !len) return fail(NK_ERR_BAD_ARG, "null argument");
+    *lo = h->dist_lo;
+    *len = h->dist_len;
     return NK_OK;
 }
 

@@ -133,9 +133,18 @@ struct PostParams {
     unsigned long long* out_spikes;  // >= 2048
     unsigned long long* pack;        // 4 + 2n u64: {fired, 0, kmers, n, idx[n], spikes[n]}
     const unsigned long long* kmers; // device k-mer counter of the call
+    // multi-GPU "reduce-scatter fused into LIF": this rank owns neurons [slice_lo, slice_lo + lif.pool);
+    // its counts are the SUM over all ranks' accumulators, read through NVLink peer mappings.
+    // (lif.currents / v / r / spikes are pre-offset by slice_lo; lif.fold_mode must be 2.)
+    int npeers;                      // 0: single GPU; else world size (self included)
+    const unsigned int* peer_acc[16];
+    unsigned long long slice_lo;
 };
 cudaError_t post_max_grid(int device, int* grid);
 cudaError_t launch_post(const PostParams& q, int max_grid, cudaStream_t s);
+// merge `world` result packs (stride 4+2*n_each u64) into one: fired and k-mers summed, rows re-sorted
+cudaError_t launch_merge_packs(const unsigned long long* gathered, int world, unsigned long long n_each,
+                               unsigned long long n_out, unsigned long long* pack_out, cudaStream_t s);
 
 // exact side tables (nk_exact.cu)
 struct ExactTable {

@@ -75,7 +75,16 @@ __global__ void __launch_bounds__(PT, 3) post_kernel(const PostParams q) {
                 const unsigned long long i = seg * SEG + (unsigned long long)(b0 + u) * PT + tid;
                 ok[u] = i < p.pool;
                 count[u] = (ok[u] && p.fold_mode != 2) ? currents[i] : 0ull;
-                if (ok[u] && p.fold_mode) count[u] += acc[i];
+                if (q.npeers) {
+                    // reduce-scatter by peer loads: this neuron's count on every rank (NVLink P2P)
+                    if (ok[u]) {
+                        unsigned long long sum = 0;
+                        for (int r = 0; r < q.npeers; ++r) sum += __ldcg(q.peer_acc[r] + q.slice_lo + i);
+                        count[u] += sum;
+                    }
+                } else if (ok[u] && p.fold_mode) {
+                    count[u] += acc[i];
+                }
                 total[u] = (ok[u] && !p.zero_state) ? spikes[i] : 0ull;
             }
             unsigned c[B], f[B], tr_[B];
@@ -92,7 +101,7 @@ __global__ void __launch_bounds__(PT, 3) post_kernel(const PostParams q) {
                 const unsigned long long i = seg * SEG + (unsigned long long)(b0 + u) * PT + tid;
                 if (!ok[u]) continue;
                 if (p.fold_mode) {
-                    acc[i] = 0u;
+                    if (!q.npeers) acc[i] = 0u;  // sharded: peers may still be reading; the host clears it later
                     currents[i] = count[u];
                 }
                 if (!(p.skip_zero && count[u] == 0)) {
@@ -260,7 +269,7 @@ __global__ void __launch_bounds__(PT, 3) post_kernel(const PostParams q) {
     for (unsigned i = tid; i < n; i += PT) {
         q.out_idx[i] = s_idx[i];
         q.out_spikes[i] = s_spk[i];
-        q.pack[4 + i] = s_idx[i];
+        q.pack[4 + i] = s_idx[i] + q.slice_lo;
         q.pack[4 + n + i] = s_spk[i];
     }
     if (tid == 0) {
@@ -271,6 +280,68 @@ __global__ void __launch_bounds__(PT, 3) post_kernel(const PostParams q) {
     }
 }
 
+// one block: sum the scalars, sort the union of the per-rank rows, keep the best n_out
+__global__ void __launch_bounds__(PT) merge_packs_kernel(const unsigned long long* __restrict__ g, int world,
+                                                         unsigned long long n_each, unsigned long long n_out,
+                                                         unsigned long long* out) {
+    __shared__ unsigned long long s_idx[2048], s_spk[2048];
+    const unsigned tid = threadIdx.x;
+    const unsigned long long stride = 4 + 2 * n_each;
+    unsigned total = 0;
+    for (int r = 0; r < world; ++r) total += (unsigned)g[r * stride + 3];
+    unsigned N = 1;
+    while (N < total) N <<= 1;
+    for (unsigned i = tid; i < N; i += PT) { s_idx[i] = ~0ull; s_spk[i] = 0ull; }
+    __syncthreads();
+    unsigned off = 0;
+    for (int r = 0; r < world; ++r) {
+        const unsigned nr = (unsigned)g[r * stride + 3];
+        for (unsigned i = tid; i < nr; i += PT) {
+            s_idx[off + i] = g[r * stride + 4 + i];
+            s_spk[off + i] = g[r * stride + 4 + nr + i];
+        }
+        off += nr;
+    }
+    __syncthreads();
+    for (unsigned k = 2; k <= N; k <<= 1) {
+        for (unsigned j = k >> 1; j > 0; j >>= 1) {
+            for (unsigned i = tid; i < N; i += PT) {
+                const unsigned l = i ^ j;
+                if (l > i) {
+                    const bool up = (i & k) == 0;
+                    const bool swap = up ? before(s_spk[l], s_idx[l], s_spk[i], s_idx[i])
+                                         : before(s_spk[i], s_idx[i], s_spk[l], s_idx[l]);
+                    if (swap) {
+                        const unsigned long long a = s_idx[i], b = s_spk[i];
+                        s_idx[i] = s_idx[l]; s_spk[i] = s_spk[l];
+                        s_idx[l] = a; s_spk[l] = b;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    const unsigned n = (unsigned)(n_out < total ? n_out : total);
+    for (unsigned i = tid; i < n; i += PT) {
+        out[4 + i] = s_idx[i];
+        out[4 + n + i] = s_spk[i];
+    }
+    if (tid == 0) {
+        unsigned long long fired = 0, kmers = 0;
+        for (int r = 0; r < world; ++r) { fired += g[r * stride + 0]; kmers += g[r * stride + 2]; }
+        out[0] = fired; out[1] = 0; out[2] = kmers; out[3] = n;
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_merge_packs(const unsigned long long* gathered, int world, unsigned long long n_each,
+                               unsigned long long n_out, unsigned long long* pack_out, cudaStream_t s) {
+    merge_packs_kernel<<<1, PT, 0, s>>>(gathered, world, n_each, n_out, pack_out);
+    return cudaGetLastError();
+}
+
+namespace {
 }  // namespace
 
 cudaError_t post_max_grid(int device, int* grid) {

@@ -709,3 +709,50 @@ def test_sharded_flow_two_ranks_one_gpu(coracle):
     exp, tot = coracle.accumulate(bases, offsets, k, pool, True, threads=4)
     np.testing.assert_array_equal(ref.currents(), exp)
     assert int(exp.sum()) == tot
+
+
+def test_sharded_pool_fused_reduce_two_ranks_one_gpu(coracle):
+    """nk_dist_*: the reduce-scatter of the per-rank counts fused into the LIF kernel through peer
+    pointers.  Two handles on one GPU stand in for two ranks (raw pointers instead of CUDA IPC; the
+    all-gather of the result packs is two device copies).  Whole-pool answers (total spikes, top-N)
+    must equal the single-handle run on every rank; per-neuron state must match inside each slice."""
+    import torch
+    from neurokmer_b200 import flatten
+    from neurokmer_b200.devmem import copy_d2d
+    from neurokmer_b200.shard import shard_batch
+    rng = np.random.default_rng(6)
+    for k, pool, world in [(31, 2_000_000, 2), (21, 100_003, 3)]:
+        seqs = [random_dna(rng, n, 0.001) for n in (3_000_000, 10, 1_700_000, 31, 2_000_000)]
+        bases, offsets = flatten(seqs)
+        ranks = [make(k, pool) for _ in range(world)]
+        raws = [c.dist_export()[1] for c in ranks]
+        for r, c in enumerate(ranks):
+            c.dist_setup(r, world, raw_ptrs=raws)
+        ref = make(k, pool); ref.stream_begin(); ref.stream_push(bases, offsets); ref.stream_end()
+        for job in range(2):  # two jobs back to back: accumulators must be clean in between
+            for r, c in enumerate(ranks):
+                c.reset(); c.stream_begin(); c.stream_push(*shard_batch(bases, offsets, k, world, r))
+            for c in ranks:
+                c.synchronize()                      # cross-rank barrier: every rank has counted
+            posts = [c.dist_post() for c in ranks]
+            for c in ranks:
+                c.synchronize()
+            n64, each = posts[0][1], posts[0][2]
+            gathered = torch.zeros(world * n64, dtype=torch.int64, device="cuda")
+            for r, (ptr, _, _) in enumerate(posts):
+                copy_d2d(gathered.data_ptr() + 8 * n64 * r, ptr, 8 * n64)
+            torch.cuda.synchronize()
+            for c in ranks:
+                c.dist_complete(gathered.data_ptr(), each)
+            for c in ranks:
+                assert c.energy.total_spikes() == ref.energy.total_spikes()
+                assert c.energy_used() == ref.energy_used()
+                assert c.top_abundant_neurons(20) == ref.top_abundant_neurons(20)
+                assert c.top_abundant_neurons(7) == ref.top_abundant_neurons(7)
+                assert c.timings()["kmers"] == ref.timings()["kmers"]
+                lo, ln = c.dist_slice()
+                np.testing.assert_array_equal(c.currents()[lo:lo + ln], ref.currents()[lo:lo + ln])
+                np.testing.assert_array_equal(c.spike_counts()[lo:lo + ln], ref.spike_counts()[lo:lo + ln])
+                np.testing.assert_array_equal(c.refractory_ticks()[lo:lo + ln], ref.refractory_ticks()[lo:lo + ln])
+                np.testing.assert_array_equal(c.voltages()[lo:lo + ln].view(np.uint32), ref.voltages()[lo:lo + ln].view(np.uint32))
+        assert sum(c.dist_slice()[1] for c in ranks) == pool

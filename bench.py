@@ -322,14 +322,17 @@ def gpu_arm(args):
     W = max(args.warmup, 3)
     timed(job_resident, W)
     sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()  # sampled through BOTH timed legs (resident + end-to-end)
     ar_events.clear()
-    steps_res, phases, top, clocks = timed(job_resident, args.steps, sampler)
+    steps_res, phases, top, _ = timed(job_resident, args.steps)
     if ar_events and len(ar_events[0]) == 4:
         ar_ms = float(np.mean([e[0].elapsed_time(e[1]) + e[2].elapsed_time(e[3]) for e in ar_events]))
     else:
         ar_ms = float(np.mean([a.elapsed_time(b) for a, b in ar_events])) if ar_events else 0.0
     timed(job_e2e, 2)
     steps_e2e, phases_e2e, top_e2e, _ = timed(job_e2e, args.steps)
+    clocks = sampler.stop() if sampler else None
     assert top == top_e2e, "resident and end-to-end legs disagree"
 
     if os.environ.get("NK_TRACE"):
@@ -366,7 +369,12 @@ def gpu_arm(args):
             "achieved": kps_kernel * SIPHASH_OPS / 1e9 if binding[1] == "int32" else kps_kernel / 1e9,
             "peak": sip_ops / 1e9 if binding[1] == "int32" else binding[0] / 1e9,
             "unit": "Gop/s (32-bit integer, SipHash mix)" if binding[1] == "int32" else "G/s",
-            "frac": kps_kernel / binding[0], "traffic": None,
+            "frac": kps_kernel / binding[0],
+            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this workload, one `ncu --set full`
+            # capture (profiles/r01_count_kernel_ncu.md): 135.16 MB + 5.32 MB per launch vs 127 MB algorithmic
+            "traffic": 140.48e6, "traffic_unit": "bytes per launch (ncu)", "algorithmic_bytes_per_launch": NBASES + NBASES // 8,
+            "bound_note": "north star: binding roofline = slowest of {HBM input bytes, SipHash int ops, L2 pool updates}; "
+                          "the integer ALU pipe binds (ncu: ALU pipe 92 % busy, DRAM 1.9 %); the HBM view is under 'hbm'",
             "kernel_ms": count_ms, "kernel_kmers_per_s": kps_kernel,
             "limits_kmers_per_s": {"hbm": hbm_bound, "int32": int_bound, "l2_atomic": red_bound},
             "hbm": {"achieved": NBASES / (count_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
@@ -415,7 +423,7 @@ def gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -7,7 +7,7 @@ template <int KIND>
 __global__ void __launch_bounds__(256) k(unsigned* out, unsigned iters, unsigned c, unsigned d) {
     unsigned a[CH], b[CH], e[CH], f[CH];
 #pragma unroll
-    for (int i = 0; i < CH; ++i) { a[i] = threadIdx.x * 7 + i + c; b[i] = blockIdx.x * 13 + i * 3 + d; e[i] = a[i] * 5 + 1; f[i] = b[i] * 3 + 7; }
+    for (int i = 0; i < CH; ++i) { a[i] = threadIdx.x * 7 + i + c; b[i] = blockIdx.x * 13 + i * 3 + d; e[i] = a[i] * 5 + 1; f[i] = b[i] * 3 + 7 + threadIdx.x * 11; }
     for (unsigned it = 0; it < iters; ++it) {
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
@@ -32,6 +32,14 @@ __global__ void __launch_bounds__(256) k(unsigned* out, unsigned iters, unsigned
                     asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(b[i]) : "r"(a[i]), "r"(e[i]));
                     asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(e[i]) : "r"(b[i]), "r"(a[i]));
                     asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(f[i]) : "r"(b[(i + 1) % CH]));
+                } else if (KIND == 7 || KIND == 8) {   // N LOP3 : 1 IMAD.WIDE (does the wide multiply block ALU issue?)
+                    constexpr int NL = KIND == 7 ? 4 : 8;
+#pragma unroll
+                    for (int l = 0; l < NL; ++l)
+                        asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b[(i + l) % CH]), "r"(e[(i + l + 1) % CH]));
+                    unsigned long long t;
+                    asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(t) : "r"(f[i]), "r"(c));
+                    f[i] = (unsigned)t ^ (unsigned)(t >> 32);
                 } else if (KIND == 6) {   // 2 ALU : 1 IMAD : distinct (target mix)
                     asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b[i]), "r"(e[i]));
                     asm volatile("shf.l.wrap.b32 %0, %0, %1, 13;" : "+r"(b[i]) : "r"(a[i]));
@@ -51,7 +59,8 @@ int main() {
     unsigned* out; cudaMalloc(&out, 64);
     Case cases[] = {{"LOP3 3 distinct regs", 1, k<0>}, {"LOP3+IMAD distinct 3-reg", 2, k<1>}, {"LOP3 2reg+imm", 1, k<2>},
                     {"LOP3+IMAD 2reg+imm", 2, k<3>}, {"SHF+LOP3+IADD (alu only)", 3, k<4>}, {"3 LOP3 : 1 IMAD.HI", 4, k<5>},
-                    {"LOP3+SHF+IMAD distinct", 3, k<6>}};
+                    {"LOP3+SHF+IMAD distinct", 3, k<6>},
+                    {"4 LOP3 : 1 IMAD.WIDE (+1 LOP3 merge)", 6, k<7>}, {"8 LOP3 : 1 IMAD.WIDE (+1 LOP3 merge)", 10, k<8>}};
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     const unsigned iters = 2048; const int blocks = sms * 8;
     for (auto& cs : cases) {

@@ -66,7 +66,6 @@ struct PhaseEvents {
 struct nk_counter {
     nk_config cfg{};
     nk::FastMod fm{};
-    int grid = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
 
     // pool state (device)
@@ -247,8 +246,10 @@ int count_chunk(nk_counter* h, DevBuf& b, const unsigned long long* d_offsets, u
         p.words = h->xt.words;
         p.words_cursor = h->xt.cursor;
     }
-    const unsigned long long want = p.ntiles < (unsigned long long)h->grid ? p.ntiles : (unsigned long long)h->grid;
-    NK_CUDA(nk::launch_count(p, h->cfg.use_canonical != 0, h->exact ? 2 : 0, (int)want, h->stream));
+    // short-read batches (mean sequence length < 2 KiB): compact the valid window starts first
+    const unsigned long long nseq_here = seq_hi - seq_lo;
+    const bool short_reads = nseq_here > 0 && nstarts / nseq_here < 2048 && h->cfg.k > 1;
+    NK_CUDA(nk::launch_count(p, h->cfg.use_canonical != 0, h->exact ? 2 : (short_reads ? 3 : 0), h->stream));
     ++h->last.launches;
     if (pe) {
         NK_CUDA(cudaEventRecord(e2, h->stream));
@@ -706,7 +707,6 @@ int nk_create(const nk_config* cfg, nk_counter** out) {
     NK_C(cudaMalloc(&h->topn.hist, 256 * sizeof(unsigned int)));
     NK_C(cudaMalloc(&h->topn.ctrl, 8 * sizeof(unsigned long long)));
     NK_C(cudaMalloc(&h->topn.block_counts, ((P + nk::TOPN_BLOCK_ITEMS - 1) / nk::TOPN_BLOCK_ITEMS + 1) * sizeof(unsigned int)));
-    NK_C(nk::count_max_grid(cfg->use_canonical != 0, cfg->device, &h->grid));
     NK_C(nk::post_max_grid(cfg->device, &h->post_grid));
     NK_C(cudaMalloc(&h->post_zero, 8 * sizeof(unsigned long long) + 8 * 256 * sizeof(unsigned int)));
     NK_C(cudaMalloc(&h->d_pack, (4 + 2 * 2048) * sizeof(unsigned long long)));
@@ -1076,7 +1076,7 @@ int nk_debug_kmers(nk_counter* h, const uint8_t* seq, uint64_t len, uint64_t* fw
         p.out_rc = rc ? d_out + n : nullptr;
         p.out_word = words ? d_out + 2 * n : nullptr;
         p.out_idx = idx ? d_out + 3 * n : nullptr;
-        NK_D(nk::launch_count(p, h->cfg.use_canonical != 0, 1, (int)std::min<unsigned long long>(p.ntiles, h->grid), h->stream));
+        NK_D(nk::launch_count(p, h->cfg.use_canonical != 0, 1, h->stream));
         if (fwd) NK_D(cudaMemcpyAsync(fwd, d_out, n * 8, cudaMemcpyDeviceToHost, h->stream));
         if (rc) NK_D(cudaMemcpyAsync(rc, d_out + n, n * 8, cudaMemcpyDeviceToHost, h->stream));
         if (words) NK_D(cudaMemcpyAsync(words, d_out + 2 * n, n * 8, cudaMemcpyDeviceToHost, h->stream));

@@ -30,6 +30,7 @@ constexpr int kBytesPerStage = COUNT_TILE + COUNT_HALO;    // multiple of 16
 constexpr int kBitsPerStage = COUNT_TILE / 8;              // multiple of 16
 constexpr int kStageStride = ((kBytesPerStage + kBitsPerStage + 127) / 128) * 128;
 constexpr int kSmemTotal = COUNT_STAGES * kStageStride;
+constexpr int kCompactBytes = COUNT_WARPS * COUNT_CHUNK * 8;  // MODE 3: one 512-word buffer per warp
 
 static_assert(kBytesPerStage % 16 == 0 && kBitsPerStage % 16 == 0, "TMA bulk copies are 16-byte granular");
 static_assert(COUNT_SPAN * (COUNT_WARPS - 1) + COUNT_SPAN + COUNT_CHUNK <= kStageStride,
@@ -83,7 +84,7 @@ __device__ __noinline__ unsigned long long pack_skip(unsigned F0, unsigned F1, u
 template <bool CANON, int MODE, bool POW2, bool KHI>
 __device__ __forceinline__ void process_chunk(const CountParams& p, const WindowConsts& wc, const Codes16& cur,
                                               const Codes16& nxt, unsigned inv16, unsigned lane,
-                                              unsigned long long pos0) {
+                                              unsigned long long pos0, unsigned long long* wbuf) {
     const unsigned F0 = cur.F;
     const unsigned F1 = neighbour(cur.F, nxt.F, lane, 1);
     const unsigned F2 = neighbour(cur.F, nxt.F, lane, 2);
@@ -127,26 +128,68 @@ __device__ __forceinline__ void process_chunk(const CountParams& p, const Window
         wslot = p.words + base + (incl - mine);
     }
     constexpr int kUnroll = NK_COUNT_UNROLL;
-#pragma unroll(kUnroll)
-    for (unsigned j = 0; j < 16; ++j) {
+    // word of window j of this lane (canonical min, or pack_kmer) — pure function of the code words
+    auto window = [&](unsigned j, unsigned long long& fwd, unsigned long long& rc) -> unsigned long long {
         const unsigned sr = 32u - 2u * j;
         // KHI (k > 16): the low word is all window, only the high word needs the mask;
         // else the window fits the low word and the high word is zero
         const unsigned flo = KHI ? __funnelshift_rc(G2, G1, sr) : (__funnelshift_rc(G2, G1, sr) & wc.mask_lo);
         const unsigned fhi = KHI ? (__funnelshift_rc(G1, G0, sr) & wc.mask_hi) : 0u;
-        const unsigned long long fwd = ((unsigned long long)fhi << 32) | flo;
-        unsigned long long rc = 0, word;
+        fwd = ((unsigned long long)fhi << 32) | flo;
+        rc = 0;
         if (CANON) {
             const unsigned rlo = KHI ? __funnelshift_r(R0, R1, 2u * j) : (__funnelshift_r(R0, R1, 2u * j) & wc.mask_lo);
             const unsigned rhi = KHI ? (__funnelshift_r(R1, R2, 2u * j) & wc.mask_hi) : 0u;
             rc = ((unsigned long long)rhi << 32) | rlo;
-            word = fwd < rc ? fwd : rc;  // src/models.rs:284-286
-        } else {
-            const unsigned vlo = KHI ? __funnelshift_rc(H2, H1, sr) : (__funnelshift_rc(H2, H1, sr) & wc.mask_lo);
-            const unsigned vhi = KHI ? (__funnelshift_rc(H1, H0, sr) & wc.mask_hi) : 0u;
-            word = fwd;  // all k bytes are ACGT: pack_kmer == forward word
-            if (vlo != wc.mask_lo || (KHI && vhi != wc.mask_hi)) word = pack_skip(F0, F1, F2, V0, V1, V2, j, wc.k);
+            return fwd < rc ? fwd : rc;  // src/models.rs:284-286
         }
+        const unsigned vlo = KHI ? __funnelshift_rc(H2, H1, sr) : (__funnelshift_rc(H2, H1, sr) & wc.mask_lo);
+        const unsigned vhi = KHI ? (__funnelshift_rc(H1, H0, sr) & wc.mask_hi) : 0u;
+        // all k bytes ACGT: pack_kmer == forward word; otherwise the skip rule (src/utils.rs:35)
+        if (vlo != wc.mask_lo || (KHI && vhi != wc.mask_hi)) return pack_skip(F0, F1, F2, V0, V1, V2, j, wc.k);
+        return fwd;
+    };
+
+    if constexpr (MODE == 3) {
+        // Short-read batches: ~(k-1)/L of the window starts are read ends (20 % at 150 bp, k=31).
+        // Hashing them and predicating the RED away wastes ALU-pipe slots, so the warp first
+        // compacts the words of its VALID starts into shared memory, then hashes them densely.
+        const unsigned mine = 16u - __popc(inv16 & 0xFFFFu);
+        unsigned incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= (unsigned)o) incl += t;
+        }
+        const unsigned total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        unsigned slot = incl - mine;
+#pragma unroll 4
+        for (unsigned j = 0; j < 16; ++j) {
+            unsigned long long fwd, rc;
+            const unsigned long long word = window(j, fwd, rc);
+            if (!((inv16 >> j) & 1u)) wbuf[slot++] = word;
+        }
+        __syncwarp();
+        const unsigned full = total & ~127u;  // groups of 4 x 32 words in which every lane has work
+        for (unsigned t = lane; t < full; t += 128u) {
+#pragma unroll
+            for (unsigned u = 0; u < 4; ++u) {
+                const unsigned long long word = wbuf[t + 32u * u];
+                const U64 h = siphash13_dev((unsigned)word, (unsigned)(word >> 32), p.rm);
+                atomicAdd(p.acc + fastmod_dev<POW2>(h, p.fm), 1u);
+            }
+        }
+        for (unsigned t = full + lane; t < total; t += 32u) {
+            const unsigned long long word = wbuf[t];
+            const U64 h = siphash13_dev((unsigned)word, (unsigned)(word >> 32), p.rm);
+            atomicAdd(p.acc + fastmod_dev<POW2>(h, p.fm), 1u);
+        }
+        __syncwarp();
+    } else {
+#pragma unroll(kUnroll)
+    for (unsigned j = 0; j < 16; ++j) {
+        unsigned long long fwd, rc;
+        const unsigned long long word = window(j, fwd, rc);
         const unsigned bad = (inv16 >> j) & 1u;
         const U64 h = siphash13_dev((unsigned)word, (unsigned)(word >> 32), p.rm);
         const unsigned idx = fastmod_dev<POW2>(h, p.fm);
@@ -174,6 +217,7 @@ __device__ __forceinline__ void process_chunk(const CountParams& p, const Window
 #endif
         }
     }
+    }  // MODE != 3
 }
 
 #ifndef NK_COUNT_MINBLOCKS
@@ -218,8 +262,8 @@ __global__ void __launch_bounds__(COUNT_THREADS, NK_COUNT_MINBLOCKS) count_kerne
             const Codes16 nxt = convert16<!CANON>(*reinterpret_cast<const uint4*>(lp + (c + 1u) * COUNT_CHUNK));
             const unsigned off = span0 + c * COUNT_CHUNK;
             const unsigned inv16 = bits[(off >> 4) + lane];
-            process_chunk<CANON, MODE, POW2, KHI>(p, wc, cur, nxt, inv16, lane,
-                                       tile * COUNT_TILE + off + 16u * lane);
+            process_chunk<CANON, MODE, POW2, KHI>(p, wc, cur, nxt, inv16, lane, tile * COUNT_TILE + off + 16u * lane,
+                                                  reinterpret_cast<unsigned long long*>(smem + kSmemTotal) + warp * COUNT_CHUNK);
             cur = nxt;
         }
         __syncthreads();
@@ -288,49 +332,46 @@ __global__ void mark_tail_kernel(unsigned int* invalid, unsigned long long nbyte
 size_t count_smem_bytes() { return (size_t)kSmemTotal; }
 
 template <bool CANON, int MODE, bool POW2, bool KHI>
-static cudaError_t launch_count_t(const CountParams& p, int grid, cudaStream_t s) {
-    cudaError_t e = cudaFuncSetAttribute(count_kernel<CANON, MODE, POW2, KHI>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
-    if (e != cudaSuccess) return e;
-    count_kernel<CANON, MODE, POW2, KHI><<<grid, COUNT_THREADS, kSmemTotal, s>>>(p);
+static cudaError_t launch_count_t(const CountParams& p, cudaStream_t s) {
+    constexpr int kSmem = kSmemTotal + (MODE == 3 ? kCompactBytes : 0);
+    static int max_grid = 0;  // persistent grid of this instantiation: SMs x resident CTAs (a multiple of 148 on B200)
+    if (max_grid == 0) {
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(count_kernel<CANON, MODE, POW2, KHI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, count_kernel<CANON, MODE, POW2, KHI>, COUNT_THREADS, kSmem);
+        if (e != cudaSuccess) return e;
+        max_grid = sms * (per_sm < 1 ? 1 : per_sm);
+    }
+    const unsigned long long grid = p.ntiles < (unsigned long long)max_grid ? p.ntiles : (unsigned long long)max_grid;
+    if (grid == 0) return cudaSuccess;
+    count_kernel<CANON, MODE, POW2, KHI><<<(unsigned)grid, COUNT_THREADS, kSmem, s>>>(p);
     return cudaGetLastError();
 }
 
 template <bool CANON, int MODE>
-static cudaError_t launch_count_cm(const CountParams& p, int grid, cudaStream_t s) {
+static cudaError_t launch_count_cm(const CountParams& p, cudaStream_t s) {
     const bool pow2 = p.fm.is_pow2 != 0, khi = p.k > 16;
-    if (pow2) return khi ? launch_count_t<CANON, MODE, true, true>(p, grid, s) : launch_count_t<CANON, MODE, true, false>(p, grid, s);
-    return khi ? launch_count_t<CANON, MODE, false, true>(p, grid, s) : launch_count_t<CANON, MODE, false, false>(p, grid, s);
-}
-
-cudaError_t launch_count(const CountParams& p, bool canonical, int mode, int grid, cudaStream_t s) {
-    if (canonical) {
-        if (mode == 0) return launch_count_cm<true, 0>(p, grid, s);
-        return mode == 1 ? launch_count_cm<true, 1>(p, grid, s) : launch_count_cm<true, 2>(p, grid, s);
-    }
-    if (mode == 0) return launch_count_cm<false, 0>(p, grid, s);
-    return mode == 1 ? launch_count_cm<false, 1>(p, grid, s) : launch_count_cm<false, 2>(p, grid, s);
+    if (pow2) return khi ? launch_count_t<CANON, MODE, true, true>(p, s) : launch_count_t<CANON, MODE, true, false>(p, s);
+    return khi ? launch_count_t<CANON, MODE, false, true>(p, s) : launch_count_t<CANON, MODE, false, false>(p, s);
 }
 
 template <bool CANON>
-static cudaError_t max_grid_t(int sms, int* grid) {
-    int per_sm = 0;
-    cudaError_t e = cudaFuncSetAttribute(count_kernel<CANON, 0, false, true>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
-    if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, count_kernel<CANON, 0, false, true>, COUNT_THREADS,
-                                                      kSmemTotal);
-    if (e != cudaSuccess) return e;
-    if (per_sm < 1) per_sm = 1;
-    *grid = sms * per_sm;  // persistent: one wave, a multiple of the SM count (148 on B200)
-    return cudaSuccess;
+static cudaError_t launch_count_c(const CountParams& p, int mode, cudaStream_t s) {
+    switch (mode) {
+        case 0: return launch_count_cm<CANON, 0>(p, s);
+        case 1: return launch_count_cm<CANON, 1>(p, s);
+        case 2: return launch_count_cm<CANON, 2>(p, s);
+        default: return launch_count_cm<CANON, 3>(p, s);
+    }
 }
 
-cudaError_t count_max_grid(bool canonical, int device, int* grid) {
-    int sms = 0;
-    cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    if (e != cudaSuccess) return e;
-    return canonical ? max_grid_t<true>(sms, grid) : max_grid_t<false>(sms, grid);
+cudaError_t launch_count(const CountParams& p, bool canonical, int mode, cudaStream_t s) {
+    return canonical ? launch_count_c<true>(p, mode, s) : launch_count_c<false>(p, mode, s);
 }
 
 cudaError_t launch_mark_invalid(unsigned int* invalid, const unsigned long long* offsets,

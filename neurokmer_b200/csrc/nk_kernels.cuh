@@ -56,9 +56,10 @@ inline unsigned long long count_bitmap_words(unsigned long long nbytes) {
     return count_ntiles(nbytes) * (COUNT_TILE / 32) + 16;
 }
 
-// mode 0: count; 1: emit the debug taps instead of counting; 2: count and append words (exact side table)
-cudaError_t launch_count(const CountParams& p, bool canonical, int mode, int grid, cudaStream_t s);
-cudaError_t count_max_grid(bool canonical, int device, int* grid);
+// mode 0: count; 1: emit the debug taps instead of counting; 2: count and append words (exact side
+// table); 3: count with warp-level compaction of the valid window starts (short-read batches).
+// The grid is persistent: min(ntiles, SMs x resident CTAs of the instantiation).
+cudaError_t launch_count(const CountParams& p, bool canonical, int mode, cudaStream_t s);
 
 // invalid-start bitmap: zero, then mark the last k-1 starts of every sequence
 // in [seq_lo, seq_hi) (positions relative to `origin`) and everything in

@@ -43,3 +43,9 @@ if __name__ == "__main__":
     run("config3 shape: 10 M reads x 150 bp (1/5 of the 50 M), k=31, pool 2M", 31, 2_000_000, lens, 3, 0)
     run("config4: 1 Gbp, k=15, pool 65536 (contention)", 15, 65536, [1_000_000_000], 4, 0)
     run("config5 shard shape: 1.25 Gbp (1/8 of 10 Gbp), k=31, pool 16M", 31, 16_000_000, [100_000_000] * 12 + [50_000_000], 5, 1)
+    if "--full" in sys.argv:
+        nreads = 50_000_000
+        lens = np.full(nreads, 150, np.int64); lens[::1000] = 20
+        # one launch handles < 2^32 window starts: the 7.5 Gbase batch is staged in two halves
+        half = nreads // 2
+        run("config3 FULL half: 25 M reads x 150 bp, k=31, pool 2M", 31, 2_000_000, lens[:half], 3, 0, reps=2)

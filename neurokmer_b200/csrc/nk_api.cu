@@ -1367,12 +1367,16 @@ int nk_process_staged(nk_counter* h, uint64_t nbytes, uint64_t nseq, int mode) {
         NK_CUDA(cudaMemsetAsync(h->scalars + 2, 0, sizeof(unsigned long long), h->stream));
         h->currents_valid_overwrite = true;
     }
-    // one launch over the whole device-resident batch, in slices of < 2^32 window starts
-    const unsigned long long slice = 0xFFFFFFFFull / nk::COUNT_TILE * nk::COUNT_TILE;
-    if (nbytes > slice)
-        return fail(NK_ERR_UNSUPPORTED, "staged batches of more than %llu bytes must be split by the caller", slice);
-    if (nseq > 0 && nbytes > 0)
-        NK_TRY(count_chunk(h, h->staged, h->staged_offsets, 0, nseq, 0, nbytes, nbytes, mode == 0 ? &pe : &pe));
+    // the device-resident batch is counted in slices of < 2^32 window starts (one launch each; the
+    // u32 accumulators are folded between slices when they could overflow).  Every slice passes the
+    // whole sequence range: the marking kernel clips each sequence to the slice.
+    const unsigned long long slice = (0xFFFFFFFFull / nk::COUNT_TILE - 1) * nk::COUNT_TILE;
+    for (unsigned long long c0 = 0; c0 < nbytes && nseq > 0; c0 += slice) {
+        const unsigned long long n = std::min(slice, nbytes - c0);
+        DevBuf view = h->staged;
+        view.bases = h->staged.bases + c0;
+        NK_TRY(count_chunk(h, view, h->staged_offsets, 0, nseq, c0, n, n, &pe));
+    }
     if (mode == 0) {
         NK_TRY(fold_and_simulate(h, /*skip_zero=*/true, pe));
         NK_TRY(get_event(h, &pe.end));

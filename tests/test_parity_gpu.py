@@ -756,3 +756,24 @@ def test_sharded_pool_fused_reduce_two_ranks_one_gpu(coracle):
                 np.testing.assert_array_equal(c.refractory_ticks()[lo:lo + ln], ref.refractory_ticks()[lo:lo + ln])
                 np.testing.assert_array_equal(c.voltages()[lo:lo + ln].view(np.uint32), ref.voltages()[lo:lo + ln].view(np.uint32))
         assert sum(c.dist_slice()[1] for c in ranks) == pool
+
+
+def test_config3_full_size_two_slices():
+    """configs[2] at FULL size on device: 50 M reads x 150 bp = 7.49 Gbase > 2^32 window starts, so the
+    staged batch is counted in two launches with a fold in between.  Properties: the k-mer total and the
+    checksum of the currents equal Σ max(0, L-k+1); all neurons saturate (334 spikes)."""
+    from neurokmer_b200.devmem import copy_h2d
+    nreads, k, pool = 50_000_000, 31, 2_000_000
+    lens = np.full(nreads, 150, np.int64); lens[::1000] = 20
+    offs = np.zeros(nreads + 1, np.uint64); offs[1:] = np.cumsum(lens)
+    n = int(offs[-1])
+    assert n > 2**32
+    c = make(k, pool)
+    db, do = c.stage_reserve(n, nreads)
+    c.synth_fill(db, 3, 0, n, 0); copy_h2d(do, offs); c.synchronize()
+    c.process_staged(n, nreads, 0)
+    want = int(np.maximum(lens - k + 1, 0).sum())
+    assert c.timings()["kmers"] == want
+    cur = c.currents()
+    assert int(cur.sum()) == want
+    assert set(c.spike_counts().tolist()) == {334} and c.energy.total_spikes() == 334 * pool

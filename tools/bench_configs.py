@@ -46,6 +46,5 @@ if __name__ == "__main__":
     if "--full" in sys.argv:
         nreads = 50_000_000
         lens = np.full(nreads, 150, np.int64); lens[::1000] = 20
-        # one launch handles < 2^32 window starts: the 7.5 Gbase batch is staged in two halves
-        half = nreads // 2
-        run("config3 FULL half: 25 M reads x 150 bp, k=31, pool 2M", 31, 2_000_000, lens[:half], 3, 0, reps=2)
+        run("config3 FULL: 50 M reads x 150 bp (7.5 Gbase, two launches of < 2^32 starts), k=31, pool 2M",
+            31, 2_000_000, lens, 3, 0, reps=2)

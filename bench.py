@@ -40,6 +40,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 K, POOL, STEPS_LIF, TOPN, SEED = 31, 2_000_000, 1000, 20, 2
+SYNTH_FLAGS = 3
 SEQ_LENS = [30_000_000, 25_000_000, 20_000_000, 15_000_000, 10_000_000, 8_000_000, 5_000_000]
 NBASES = sum(SEQ_LENS)
 KMERS = sum(l - K + 1 for l in SEQ_LENS)
@@ -205,12 +206,13 @@ def gpu_arm(args):
 
     # device-resident input: this rank's shard of the stream (weak scaling: NBASES per rank)
     dev_bases, dev_offs = c.stage_reserve(NBASES, nseq)
-    c.synth_fill(dev_bases, SEED, rank * NBASES, NBASES, 3)
+    c.synth_fill(dev_bases, SEED, rank * NBASES, NBASES, SYNTH_FLAGS)
     copy_h2d(dev_offs, offsets)
     c.synchronize()
     # host copy of the same bytes in pinned memory for the end-to-end leg
-    pinned = PinnedBuffer(NBASES)
-    pinned.array[:] = device_to_numpy(dev_bases, NBASES)
+    pinned = PinnedBuffer(NBASES if not args.no_e2e else 16)
+    if not args.no_e2e:
+        pinned.array[:] = device_to_numpy(dev_bases, NBASES)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
     cur_view = {}
@@ -330,8 +332,11 @@ def gpu_arm(args):
         ar_ms = float(np.mean([e[0].elapsed_time(e[1]) + e[2].elapsed_time(e[3]) for e in ar_events]))
     else:
         ar_ms = float(np.mean([a.elapsed_time(b) for a, b in ar_events])) if ar_events else 0.0
-    timed(job_e2e, 2)
-    steps_e2e, phases_e2e, top_e2e, _ = timed(job_e2e, args.steps)
+    if args.no_e2e:
+        steps_e2e, phases_e2e, top_e2e = [(0.0, float("nan"))], [dict(h2d_bytes=0, d2h_bytes=0)], top
+    else:
+        timed(job_e2e, 2)
+        steps_e2e, phases_e2e, top_e2e, _ = timed(job_e2e, args.steps)
     clocks = sampler.stop() if sampler else None
     assert top == top_e2e, "resident and end-to-end legs disagree"
 
@@ -387,7 +392,7 @@ def gpu_arm(args):
         launches = int(phases[-1]["launches"] + phases[-1]["topn_launches"])
         # CPU baseline on a bounded sample (rank 0, N=1 only)
         cpu = None
-        if world == 1 and not args.no_cpu:
+        if world == 1 and not args.no_cpu and not args.no_e2e:
             threads = os.cpu_count() or 1
             sample = min(NBASES, 8_000_000 * threads)
             v, d = cpu_run(sample, threads, pinned.array)
@@ -395,7 +400,7 @@ def gpu_arm(args):
                    "sample": (f"accumulate over the first {sample} bases ({d['sample_kmers']} k-mers, {d['t_acc_sample']:.2f} s) + LIF over "
                               f"the full 2M pool ({d['t_lif']:.2f} s) + top-20; job time extrapolated = {d['t_job_extrapolated']:.2f} s")}
         line = {
-            "metric": "canonical k-mers/sec (k=31, 2M pool)", "value": value, "unit": "kmers/s", "n_gpus": world,
+            "metric": f"canonical k-mers/sec (k={K}, {POOL // 1_000_000}M pool)", "value": value, "unit": "kmers/s", "n_gpus": world,
             "steps": args.steps, "warmup": W, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "k": K, "pool_size": POOL, "lif_steps": STEPS_LIF, "top_n": TOPN,
@@ -420,6 +425,19 @@ def gpu_arm(args):
         dist.destroy_process_group()
 
 
+def select_workload(name: str):
+    """configs[1] is the bench workload; configs[4] (10 Gbp, pool 16 M, sharded over the GPUs) can be
+    timed with --workload config5 (per-GPU shard = 1.25 Gbp, i.e. the full 10 Gbp at --gpus 8)."""
+    global K, POOL, SEQ_LENS, NBASES, KMERS, WORKLOAD, SEED, SYNTH_FLAGS
+    if name == "config5":
+        K, POOL, SEED, SYNTH_FLAGS = 31, 16_000_000, 5, 1
+        SEQ_LENS = [100_000_000] * 12 + [50_000_000]
+        WORKLOAD = ("synthetic multi-FASTA-equivalent, 1.25 Gbase per GPU (10 Gbp at 8 GPUs), sparse N runs, k=31, "
+                    "pool 16M, canonical, streaming")
+    NBASES = sum(SEQ_LENS)
+    KMERS = sum(l - K + 1 for l in SEQ_LENS)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -427,9 +445,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default="config2", choices=["config2", "config5"])
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (large workloads)")
     ap.add_argument("--dist", default="fused", choices=["fused", "allreduce"],
                     help="N > 1: peer-memory reduce fused into the LIF kernel (default) or NCCL all-reduce of the currents")
     args = ap.parse_args()
+    select_workload(args.workload)
     if args.impl == "reference":
         reference_arm(args)
     else:

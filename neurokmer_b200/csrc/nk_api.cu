@@ -102,8 +102,11 @@ struct nk_counter {
     // staging
     DevBuf buf[2];
     int cur_buf = 0;
-    unsigned long long* d_offsets = nullptr;
-    unsigned long long offsets_cap = 0;
+    // offsets of host batches: two buffers alternate so that batch i+1's copy never waits for batch i's kernels
+    unsigned long long* d_offsets2[2] = {nullptr, nullptr};
+    unsigned long long offsets_cap2[2] = {0, 0};
+    cudaEvent_t offsets_done[2] = {nullptr, nullptr};
+    int cur_off = 0;
     // device-resident staged batch (nk_stage_reserve)
     DevBuf staged;
     unsigned long long* staged_offsets = nullptr;
@@ -272,18 +275,26 @@ int validate_batch(const nk_counter* h, const uint8_t* bases, const uint64_t* of
 }
 
 // host batch -> chunked H2D (copy stream) overlapped with mark+count (compute stream)
-int count_host_batch(nk_counter* h, const uint8_t* bases, const uint64_t* offsets, uint64_t nseq, PhaseEvents* pe) {
+int count_host_batch(nk_counter* h, const uint8_t* bases, const uint64_t* offsets, uint64_t nseq, PhaseEvents* pe,
+                     bool wait_copies = true) {
     if (nseq == 0) return NK_OK;
     for (uint64_t s = 0; s < nseq; ++s)
         if (offsets[s + 1] < offsets[s]) return fail(NK_ERR_BAD_ARG, "offsets must be non-decreasing (at %llu)", (unsigned long long)s);
     const unsigned long long nbytes = offsets[nseq];
     if (nbytes == 0) return NK_OK;
-    NK_TRY(ensure_offsets(&h->d_offsets, &h->offsets_cap, nseq + 1));
+    const int ob = h->cur_off;
+    h->cur_off ^= 1;
+    if (h->offsets_done[ob]) {
+        // the kernels of the batch before last read this offsets buffer
+        NK_CUDA(cudaStreamWaitEvent(h->copy_stream, h->offsets_done[ob], 0));
+        if (nseq + 1 > h->offsets_cap2[ob]) NK_CUDA(cudaEventSynchronize(h->offsets_done[ob]));  // about to free it
+    } else {
+        NK_CUDA(cudaEventCreateWithFlags(&h->offsets_done[ob], cudaEventDisableTiming));
+    }
+    NK_TRY(ensure_offsets(&h->d_offsets2[ob], &h->offsets_cap2[ob], nseq + 1));
+    unsigned long long* const d_offsets = h->d_offsets2[ob];
     if (pe && !pe->copy0) { NK_TRY(get_event(h, &pe->copy0)); NK_CUDA(cudaEventRecord(pe->copy0, h->copy_stream)); }
-    // the previous batch's kernels may still read d_offsets
-    if (h->buf[0].compute_done) NK_CUDA(cudaStreamWaitEvent(h->copy_stream, h->buf[0].compute_done, 0));
-    if (h->buf[1].compute_done) NK_CUDA(cudaStreamWaitEvent(h->copy_stream, h->buf[1].compute_done, 0));
-    NK_CUDA(cudaMemcpyAsync(h->d_offsets, offsets, (nseq + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, h->copy_stream));
+    NK_CUDA(cudaMemcpyAsync(d_offsets, offsets, (nseq + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, h->copy_stream));
     h->last.h2d_bytes += (nseq + 1) * sizeof(uint64_t) + nbytes;
 
     // chunk plan: fixed 32 MiB granules.  Measured alternatives at 113 MB (end to end, B200, PCIe Gen5):
@@ -305,15 +316,17 @@ int count_host_batch(nk_counter* h, const uint8_t* bases, const uint64_t* offset
         const unsigned long long seq_lo = (unsigned long long)(first - (offsets + 1));
         const uint64_t* last = std::lower_bound(offsets, offsets + nseq, (uint64_t)c1);
         const unsigned long long seq_hi = (unsigned long long)(last - offsets);
-        NK_TRY(count_chunk(h, b, h->d_offsets, seq_lo, seq_hi, c0, c1 - c0, c1 - c0, pe));
+        NK_TRY(count_chunk(h, b, d_offsets, seq_lo, seq_hi, c0, c1 - c0, c1 - c0, pe));
         NK_CUDA(cudaEventRecord(b.compute_done, h->stream));
     }
+    NK_CUDA(cudaEventRecord(h->offsets_done[ob], h->stream));
     if (pe) {
         if (!pe->copy1) NK_TRY(get_event(h, &pe->copy1));
         NK_CUDA(cudaEventRecord(pe->copy1, h->copy_stream));
     }
-    // the caller's buffers must be reusable on return: wait for the copies (not the kernels)
-    NK_CUDA(cudaStreamSynchronize(h->copy_stream));
+    // the caller's buffers must be reusable on return: wait for the copies (not the kernels).
+    // The file driver owns its pinned batches and double-buffers them instead (wait_copies = false).
+    if (wait_copies) NK_CUDA(cudaStreamSynchronize(h->copy_stream));
     return NK_OK;
 }
 
@@ -560,9 +573,18 @@ int process_file(nk_counter* h, const char* path, bool streaming, std::string* e
     cudaError_t ce = cudaSetDevice(h->cfg.device);
     if (ce != cudaSuccess) return cuda_fail(ce, "cudaSetDevice");
     const size_t cap = (size_t)kChunkBytes;
-    uint8_t* batch = nullptr;
-    ce = cudaMallocHost((void**)&batch, cap);
-    if (ce != cudaSuccess) return cuda_fail(ce, "cudaMallocHost(batch)");
+    // pinned, double-buffered host staging: the parser fills one batch while the other one's
+    // H2D copy (copy stream) and kernels (compute stream) are in flight
+    uint8_t* batches[2] = {nullptr, nullptr};
+    cudaEvent_t copied[2] = {nullptr, nullptr};
+    bool inflight[2] = {false, false};
+    for (int i = 0; i < 2; ++i) {
+        ce = cudaMallocHost((void**)&batches[i], cap);
+        if (ce != cudaSuccess) { if (batches[0]) cudaFreeHost(batches[0]); return cuda_fail(ce, "cudaMallocHost(batch)"); }
+        cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming);
+    }
+    int cur = 0;
+    uint8_t* batch = batches[0];
     std::vector<uint64_t> offsets;
     offsets.reserve(1u << 20);
     offsets.push_back(0);
@@ -574,8 +596,13 @@ int process_file(nk_counter* h, const char* path, bool streaming, std::string* e
     int rc = NK_OK;
     auto flush = [&]() -> int {
         if (offsets.size() > 1 && fill > 0) {
-            int r = count_host_batch(h, batch, offsets.data(), offsets.size() - 1, nullptr);
+            int r = count_host_batch(h, batch, offsets.data(), offsets.size() - 1, nullptr, /*wait_copies=*/false);
             if (r != NK_OK) { *err = g_err; return r; }
+            cudaEventRecord(copied[cur], h->copy_stream);
+            inflight[cur] = true;
+            cur ^= 1;
+            batch = batches[cur];
+            if (inflight[cur]) { cudaEventSynchronize(copied[cur]); inflight[cur] = false; }
         }
         offsets.clear();
         offsets.push_back(0);
@@ -639,7 +666,7 @@ int process_file(nk_counter* h, const char* path, bool streaming, std::string* e
     } while (0);
     cudaStreamSynchronize(h->copy_stream);
     cudaStreamSynchronize(h->stream);
-    cudaFreeHost(batch);
+    for (int i = 0; i < 2; ++i) { cudaFreeHost(batches[i]); cudaEventDestroy(copied[i]); }
     return rc;
 }
 
@@ -766,7 +793,8 @@ int nk_destroy(nk_counter* h) {
     nk::exact_free(h->xt);
     cudaFree(h->d_top_uniques);
     free_devbuf(h->buf[0]); free_devbuf(h->buf[1]); free_devbuf(h->staged);
-    cudaFree(h->d_offsets); cudaFree(h->staged_offsets);
+    for (int i = 0; i < 2; ++i) { cudaFree(h->d_offsets2[i]); if (h->offsets_done[i]) cudaEventDestroy(h->offsets_done[i]); }
+    cudaFree(h->staged_offsets);
     for (cudaEvent_t e : h->evpool) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);

@@ -334,19 +334,24 @@ size_t count_smem_bytes() { return (size_t)kSmemTotal; }
 template <bool CANON, int MODE, bool POW2, bool KHI>
 static cudaError_t launch_count_t(const CountParams& p, cudaStream_t s) {
     constexpr int kSmem = kSmemTotal + (MODE == 3 ? kCompactBytes : 0);
-    static int max_grid = 0;  // persistent grid of this instantiation: SMs x resident CTAs (a multiple of 148 on B200)
-    if (max_grid == 0) {
-        int dev = 0, sms = 0, per_sm = 0;
-        cudaError_t e = cudaGetDevice(&dev);
-        if (e != cudaSuccess) return e;
+    // persistent grid of this instantiation: SMs x resident CTAs (a multiple of 148 on B200); function
+    // attributes are per device, so the cache is too
+    static int max_grid_of[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    if (max_grid_of[dev] == 0) {
+        int sms = 0, per_sm = 0;
         e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(count_kernel<CANON, MODE, POW2, KHI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
         if (e != cudaSuccess) return e;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, count_kernel<CANON, MODE, POW2, KHI>, COUNT_THREADS, kSmem);
         if (e != cudaSuccess) return e;
-        max_grid = sms * (per_sm < 1 ? 1 : per_sm);
+        max_grid_of[dev] = sms * (per_sm < 1 ? 1 : per_sm);
     }
+    const int max_grid = max_grid_of[dev];
     const unsigned long long grid = p.ntiles < (unsigned long long)max_grid ? p.ntiles : (unsigned long long)max_grid;
     if (grid == 0) return cudaSuccess;
     count_kernel<CANON, MODE, POW2, KHI><<<(unsigned)grid, COUNT_THREADS, kSmem, s>>>(p);

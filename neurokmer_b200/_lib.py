@@ -21,7 +21,7 @@ SYMBOLS = [
     "nk_set_steps", "nk_get_steps", "nk_process_batch", "nk_stream_begin", "nk_stream_push",
     "nk_stream_end", "nk_process_file", "nk_process_sequence", "nk_simulate", "nk_top_n",
     "nk_total_spikes", "nk_energy_used", "nk_enable_exact_counts", "nk_get_count", "nk_exact_table_size",
-    "nk_copy_exact_table", "nk_copy_uniques", "nk_debug_kmers", "nk_debug_hash",
+    "nk_copy_exact_table", "nk_copy_uniques", "nk_debug_kmers", "nk_debug_hash", "nk_debug_mod",
     "nk_copy_currents", "nk_copy_spike_counts", "nk_copy_voltages", "nk_copy_refractory",
     "nk_last_timings", "nk_debug_set_lif_path", "nk_calibrate", "nk_stage_reserve", "nk_process_staged", "nk_stream_accumulated",
     "nk_stream_finish", "nk_dist_export", "nk_dist_setup", "nk_dist_post", "nk_dist_complete", "nk_dist_slice",
@@ -94,6 +94,7 @@ def load() -> C.CDLL:
         "nk_copy_uniques": (i32, [vp, vp]),
         "nk_debug_kmers": (i32, [vp, vp, u64, vp, vp, vp, vp, P(u64)]),
         "nk_debug_hash": (i32, [vp, vp, u64, vp, vp]),
+        "nk_debug_mod": (i32, [vp, u64, u64, i32, vp]),
         "nk_copy_currents": (i32, [vp, vp]),
         "nk_copy_spike_counts": (i32, [vp, vp]),
         "nk_copy_voltages": (i32, [vp, vp]),

@@ -293,6 +293,14 @@ class SpikingKmerCounter:
         check(self._L.nk_synchronize(self._h))
 
 
+def debug_mod(values: np.ndarray, pool_size: int, which: int = 0) -> np.ndarray:
+    """values % pool_size computed by the device's exact-modulo routine (parity tap)."""
+    v = np.ascontiguousarray(values, np.uint64)
+    out = np.zeros(max(v.size, 1), np.uint64)
+    check(_lib.lib().nk_debug_mod(_ptr(v), v.size, pool_size, which, out.ctypes.data))
+    return out[: v.size]
+
+
 def pack_kmer(kmer: BytesLike) -> int:
     """reference src/utils.rs:26-39"""
     a = np.frombuffer(kmer, np.uint8) if not isinstance(kmer, np.ndarray) else np.ascontiguousarray(kmer, np.uint8)

@@ -1138,6 +1138,21 @@ int nk_debug_hash(nk_counter* h, const uint64_t* words, uint64_t n, uint64_t* ha
     return rc_;
 }
 
+int nk_debug_mod(const uint64_t* values, uint64_t n, uint64_t pool_size, int which, uint64_t* out) {
+    if (n == 0) return NK_OK;
+    if (!values || !out) return fail(NK_ERR_BAD_ARG, "null argument");
+    if (pool_size == 0 || pool_size >= (1ull << 32)) return fail(NK_ERR_BAD_ARG, "pool_size must be in [1, 2^32)");
+    if (which != 0 && which != 1) return fail(NK_ERR_BAD_ARG, "which must be 0 (FP64-pipe form) or 1 (integer form)");
+    unsigned long long* d = nullptr;
+    NK_CUDA(cudaMalloc(&d, 2 * n * sizeof(unsigned long long)));
+    cudaError_t e = cudaMemcpy(d, values, n * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = nk::launch_mod_words(d, n, nk::make_fastmod(pool_size), d + n, which, nullptr);
+    if (e == cudaSuccess) e = cudaMemcpy(out, d + n, n * 8, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    NK_CUDA(e);
+    return NK_OK;
+}
+
 static int copy_out(nk_counter* h, void* dst, const void* src, size_t bytes) {
     if (!h || !dst) return fail(NK_ERR_BAD_ARG, "null argument");
     NK_TRY(resolve(h));

@@ -119,6 +119,9 @@ __host__ __device__ __forceinline__ unsigned long long siphash13_u64(unsigned lo
 // applied twice to the 96-bit value h << shift.  Powers of two take one AND.
 // ---------------------------------------------------------------------------
 struct FastMod {
+    double dd;        // p as a double, 1/p (round to nearest), 2p
+    double inv;
+    double two_d;
     uint32_t dn;      // p << shift (top bit set)
     uint32_t v;       // floor((2^64-1)/dn) - 2^32
     uint32_t shift;   // clz(p)
@@ -138,6 +141,9 @@ __host__ __device__ __forceinline__ FastMod make_fastmod(unsigned long long p64)
     fm.v = (uint32_t)(0xFFFFFFFFFFFFFFFFULL / fm.dn - 0x100000000ULL);
     fm.is_pow2 = ((p & (p - 1)) == 0) ? 1u : 0u;
     fm.pow2m1 = p - 1;
+    fm.dd = (double)p;
+    fm.inv = 1.0 / (double)p;
+    fm.two_d = 2.0 * (double)p;
     return fm;
 }
 
@@ -163,6 +169,37 @@ __host__ __device__ __forceinline__ uint32_t fastmod_u64(unsigned long long h, c
     const uint32_t r1 = rem_2by1(u2, u1, fm.dn, fm.v);
     const uint32_t r0 = rem_2by1(r1, u0, fm.dn, fm.v);
     return r0 >> s;
+}
+
+// ---------------------------------------------------------------------------
+// The same remainder on the FP64 pipe (device: fastmod_dev; this is its host twin for tests).
+// The count kernel is bound by the integer ALU pipe, and on sm_100a IMAD.HI / IMAD.WIDE block
+// ALU issue (tools/microbench2.cu) while DFMA/DADD/DMUL issue beside it for free — so the
+// exact modulo is done in doubles, 13 FP64 ops and ~5 ALU ops instead of ~15 ALU-slot ops:
+//   stage 1: x1 = h >> 12 (< 2^52, exact);  q1 = floor(x1 * inv);  r1 = x1 - q1*p   (|q1 error| <= 2)
+//            r1 += 2p                                   -> r1 in [0, 5p), r1 == (h >> 12)  (mod p)
+//   stage 2: x2 = r1 * 4096 + (h & 4095) (< 2^48);      q2 = floor(x2 * inv);  r2 = x2 - q2*p
+//            the quotient's fractional part is a multiple of 1/p >= 2^-32 and the rounding error
+//            of x2*inv is < 2^-37, so q2 is exact unless x2 is an exact multiple (then r2 may be p)
+//   result = r2 >= p ? r2 - p : r2.
+// floor() of a non-negative double < 2^52 is (t + 2^52, rounded toward zero) - 2^52; integers <->
+// doubles go through the 0x43300000 exponent trick (no conversion instructions).
+// ---------------------------------------------------------------------------
+inline uint32_t fastmod_fp64_host(unsigned long long h, const FastMod& fm) {
+    if (fm.is_pow2) return (uint32_t)h & fm.pow2m1;
+    const double two52 = 4503599627370496.0;
+    const double x1 = (double)(h >> 12);
+    const double t1 = x1 * fm.inv;
+    const double q1 = (double)(unsigned long long)t1;  // floor, t1 >= 0
+    double r1 = x1 - q1 * fm.dd;                       // exact: an FMA on the device, small integers here
+    r1 += fm.two_d;
+    const double x2 = r1 * 4096.0 + (double)(h & 4095ull);
+    const double t2 = x2 * fm.inv;
+    const double q2 = (double)(unsigned long long)t2;
+    const double r2 = x2 - q2 * fm.dd;
+    (void)two52;
+    const unsigned long long r = (unsigned long long)r2;
+    return (uint32_t)(r >= fm.p ? r - fm.p : r);
 }
 
 #ifdef __CUDACC__
@@ -276,8 +313,9 @@ __device__ __forceinline__ uint32_t rem_2by1_dev(uint32_t u1, uint32_t u0, uint3
     return min(r, r - dn);             // r >= dn ? r - dn : r   (r < 2*dn <= 2^33 never holds both)
 }
 
+// Moeller-Granlund form (integer pipes only); kept for reference and as a cross-check
 template <bool POW2>
-__device__ __forceinline__ uint32_t fastmod_dev(U64 h, const FastMod& fm) {
+__device__ __forceinline__ uint32_t fastmod_mg_dev(U64 h, const FastMod& fm) {
     if (POW2) return h.lo & fm.pow2m1;
     const uint32_t s = fm.shift;
     const uint32_t u2 = __funnelshift_l(h.hi, 0u, s);      // h.hi >> (32-s), 0 for s == 0
@@ -286,6 +324,23 @@ __device__ __forceinline__ uint32_t fastmod_dev(U64 h, const FastMod& fm) {
     const uint32_t r1 = rem_2by1_dev(u2, u1, fm.dn, fm.v);
     const uint32_t r0 = rem_2by1_dev(r1, u0, fm.dn, fm.v);
     return r0 >> s;
+}
+
+// FP64-pipe form (see fastmod_fp64_host for the derivation)
+template <bool POW2>
+__device__ __forceinline__ uint32_t fastmod_dev(U64 h, const FastMod& fm) {
+    if (POW2) return h.lo & fm.pow2m1;
+    const double two52 = 4503599627370496.0;
+    // x1 = h >> 12 as a double: bits (0x43300000 | hi', lo') encode 2^52 + value
+    const uint32_t hi1 = h.hi >> 12, lo1 = __funnelshift_r(h.lo, h.hi, 12);
+    const double x1 = __dadd_rn(__hiloint2double((int)(0x43300000u + hi1), (int)lo1), -two52);
+    const double q1 = __dadd_rn(__dadd_rz(__dmul_rn(x1, fm.inv), two52), -two52);       // floor(x1 / p) +- 2
+    const double r1 = __dadd_rn(__fma_rn(-q1, fm.dd, x1), fm.two_d);                    // in [0, 5p)
+    const double x2 = __dadd_rn(__fma_rn(r1, 4096.0, __hiloint2double(0x43300000, (int)(h.lo & 4095u))), -two52);
+    const double q2 = __dadd_rn(__dadd_rz(__dmul_rn(x2, fm.inv), two52), -two52);
+    const double r2 = __fma_rn(-q2, fm.dd, x2);                                         // in [0, p]
+    const uint32_t r = (uint32_t)__double2loint(__dadd_rn(r2, two52));
+    return min(r, r - fm.p);
 }
 
 // ---------------------------------------------------------------------------

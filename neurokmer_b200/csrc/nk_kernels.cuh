@@ -177,6 +177,9 @@ cudaError_t launch_int_peak(int mode, unsigned int* out, int blocks, unsigned it
 unsigned long long int_peak_ops_per_iter(int mode);
 cudaError_t launch_red_peak(unsigned int* acc, FastMod fm, int blocks, unsigned per_thread, cudaStream_t s);
 
+cudaError_t launch_mod_words(const unsigned long long* h, unsigned long long n, FastMod fm, unsigned long long* out,
+                             int which, cudaStream_t s);
+
 cudaError_t launch_synth(unsigned char* out, unsigned long long seed, unsigned long long start,
                          unsigned long long n, unsigned flags, cudaStream_t s);
 

@@ -18,6 +18,16 @@ __global__ void hash_words_kernel(const unsigned long long* __restrict__ words, 
     if (idx) idx[i] = fastmod_dev<POW2>(h, fm);
 }
 
+// h % pool for an array of raw 64-bit values (parity tap for the exact-modulo routine alone)
+template <bool POW2>
+__global__ void mod_words_kernel(const unsigned long long* __restrict__ h, unsigned long long n, FastMod fm,
+                                 unsigned long long* out, int which) {
+    const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const U64 x{(unsigned)h[i], (unsigned)(h[i] >> 32)};
+    out[i] = which ? fastmod_mg_dev<POW2>(x, fm) : fastmod_dev<POW2>(x, fm);
+}
+
 // Position-addressable synthetic stream: 32 bases per splitmix64 draw.
 //   flags bit0: one run of 100..10000 'N' per 2^20-base block (≈0.5 % of bases)
 //   flags bit1: 1 % of the 4096-base blocks are lower-case (soft-masked)
@@ -134,6 +144,15 @@ cudaError_t launch_hash_words(const unsigned long long* words, unsigned long lon
         hash_words_kernel<true><<<blocks, 256, 0, s>>>(words, n, fm, make_rotmul(), hashes, idx);
     else
         hash_words_kernel<false><<<blocks, 256, 0, s>>>(words, n, fm, make_rotmul(), hashes, idx);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_mod_words(const unsigned long long* h, unsigned long long n, FastMod fm, unsigned long long* out,
+                             int which, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    if (fm.is_pow2) mod_words_kernel<true><<<blocks, 256, 0, s>>>(h, n, fm, out, which);
+    else mod_words_kernel<false><<<blocks, 256, 0, s>>>(h, n, fm, out, which);
     return cudaGetLastError();
 }
 

@@ -777,3 +777,24 @@ def test_config3_full_size_two_slices():
     cur = c.currents()
     assert int(cur.sum()) == want
     assert set(c.spike_counts().tolist()) == {334} and c.energy.total_spikes() == 334 * pool
+
+
+def test_exact_modulo_all_pool_sizes():
+    """`finish() % pool_size` (spiking_hash.rs:81) for pool sizes up to 2^32-1 and adversarial values
+    (exact multiples, multiples ± 1, extremes): the FP64-pipe routine and the integer routine both equal
+    Python's integer remainder."""
+    from neurokmer_b200.counter import debug_mod
+    rng = np.random.default_rng(99)
+    pools = [1, 2, 3, 5, 7, 10, 1000, 4096, 65535, 65536, 65537, 999_983, 1_000_000, 2_000_000, 15_625, 16_000_000,
+             2**24 - 1, 2**31 - 1, 2**31, 2**31 + 1, 4_294_967_291, 2**32 - 2, 2**32 - 1] + \
+            [int(x) for x in rng.integers(1, 2**32, size=40, dtype=np.uint64)]
+    for p in pools:
+        v = rng.integers(0, 2**64, size=20000, dtype=np.uint64)
+        q = rng.integers(0, (2**64 - 1) // p + 1, size=6000, dtype=np.uint64)
+        mult = q * np.uint64(p)
+        v[:6000] = mult                                   # exact multiples
+        v[6000:12000] = mult + np.uint64(p - 1)           # one below the next multiple (may wrap: still valid input)
+        v[12000:12010] = [0, 1, 2**64 - 1, 2**64 - 2, 2**63, 2**32, 2**32 - 1, p, p - 1 if p > 1 else 0, (p * 4096) % 2**64]
+        want = np.array([int(x) % p for x in v], np.uint64)
+        for which in (0, 1):
+            np.testing.assert_array_equal(debug_mod(v, p, which), want, err_msg=f"pool {p} routine {which}")

@@ -40,6 +40,21 @@ __global__ void __launch_bounds__(256) k(unsigned* out, unsigned iters, unsigned
                     unsigned long long t;
                     asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(t) : "r"(f[i]), "r"(c));
                     f[i] = (unsigned)t ^ (unsigned)(t >> 32);
+                } else if (KIND == 9 || KIND == 10) {  // N LOP3 : 1 DFMA (is the FP64 pipe independent of ALU issue?)
+                    constexpr int NL = KIND == 9 ? 4 : 1;
+#pragma unroll
+                    for (int l = 0; l < NL; ++l)
+                        asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b[(i + l) % CH]), "r"(e[(i + l + 1) % CH]));
+                    double dd = __hiloint2double(0x43300000 | (f[i] & 0xFFFF), f[i]);
+                    asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(dd) : "d"(1.0000001), "d"(-4503599627370496.0));
+                    f[i] = __double2loint(dd) ^ __double2hiint(dd);
+                } else if (KIND == 11) {  // DFMA chain alone
+                    double dd = __hiloint2double(0x43300000 | (f[i] & 0xFFFF), f[i]);
+                    asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(dd) : "d"(1.0000001), "d"(-4503599627370496.0));
+                    asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(dd) : "d"(1.0000001), "d"(0.5));
+                    asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(dd) : "d"(0.999), "d"(0.25));
+                    asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(dd) : "d"(1.001), "d"(0.125));
+                    f[i] = __double2loint(dd);
                 } else if (KIND == 6) {   // 2 ALU : 1 IMAD : distinct (target mix)
                     asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b[i]), "r"(e[i]));
                     asm volatile("shf.l.wrap.b32 %0, %0, %1, 13;" : "+r"(b[i]) : "r"(a[i]));
@@ -60,7 +75,8 @@ int main() {
     Case cases[] = {{"LOP3 3 distinct regs", 1, k<0>}, {"LOP3+IMAD distinct 3-reg", 2, k<1>}, {"LOP3 2reg+imm", 1, k<2>},
                     {"LOP3+IMAD 2reg+imm", 2, k<3>}, {"SHF+LOP3+IADD (alu only)", 3, k<4>}, {"3 LOP3 : 1 IMAD.HI", 4, k<5>},
                     {"LOP3+SHF+IMAD distinct", 3, k<6>},
-                    {"4 LOP3 : 1 IMAD.WIDE (+1 LOP3 merge)", 6, k<7>}, {"8 LOP3 : 1 IMAD.WIDE (+1 LOP3 merge)", 10, k<8>}};
+                    {"4 LOP3 : 1 IMAD.WIDE (+1 LOP3 merge)", 6, k<7>}, {"8 LOP3 : 1 IMAD.WIDE (+1 LOP3 merge)", 10, k<8>},
+                    {"4 LOP3 : 1 DFMA (+2 glue ALU)", 7, k<9>}, {"1 LOP3 : 1 DFMA (+2 glue ALU)", 4, k<10>}, {"4 DFMA chain (+1 glue)", 5, k<11>}};
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     const unsigned iters = 2048; const int blocks = sms * 8;
     for (auto& cs : cases) {

@@ -596,7 +596,7 @@ int process_file(nk_counter* h, const char* path, bool streaming, std::string* e
     int rc = NK_OK;
     auto flush = [&]() -> int {
         if (offsets.size() > 1 && fill > 0) {
-            int r = count_host_batch(h, batch, offsets.data(), offsets.size() - 1, nullptr, /*wait_copies=*/false);
+            int r = count_host_batch(h, batch, offsets.data(), offsets.size() - 1, &pe, /*wait_copies=*/false);
             if (r != NK_OK) { *err = g_err; return r; }
             cudaEventRecord(copied[cur], h->copy_stream);
             inflight[cur] = true;

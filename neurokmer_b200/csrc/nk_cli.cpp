@@ -6,6 +6,7 @@
 // --top-n 20 (main.rs:50), --device 0, --exact (build the exact k-mer side table so that the
 // "unique k-mers colliding" column is computed; without it the column prints "n/a" — never a guess).
 // LIF constants are the ones main.rs:37 hard-codes (threshold 1.0, leak 0.95, refractory 2, cost 1.0).
+#include <chrono>
 #include <cinttypes>
 #include <cstdio>
 #include <cstdlib>
@@ -51,7 +52,9 @@ int main(int argc, char** argv) {
     nk_config cfg;
     nk_config_default(&cfg);
     uint64_t top_n = 20;
-    int streaming = 0, exact = 0;
+    int streaming = 0, exact = 0, timing = 0;
+    const auto T0 = std::chrono::steady_clock::now();
+    auto since = [&]() { return std::chrono::duration<double>(std::chrono::steady_clock::now() - T0).count(); };
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
         auto val = [&](const char* name) -> const char* {
@@ -67,6 +70,7 @@ int main(int argc, char** argv) {
         else if (a == "--top-n") top_n = strtoull(val("--top-n"), nullptr, 10);
         else if (a == "--device") cfg.device = atoi(val("--device"));
         else if (a == "--exact") exact = 1;
+        else if (a == "--timing") timing = 1;  // phase wall times on stderr
         else if (a == "-h" || a == "--help") { usage(); return 0; }
         else { fprintf(stderr, "error: unexpected argument '%s'\n\n", a.c_str()); usage(); return 2; }
     }
@@ -74,6 +78,7 @@ int main(int argc, char** argv) {
 
     nk_counter* h = nullptr;
     if (nk_create(&cfg, &h) != NK_OK) { fprintf(stderr, "Error: %s\n", nk_last_error()); return 1; }
+    if (timing) fprintf(stderr, "[timing] nk_create done at %.3f s\n", since());
     if (exact && nk_enable_exact_counts(h, 1) != NK_OK) { fprintf(stderr, "Error: %s\n", nk_last_error()); return 1; }
     if (nk_process_file(h, input.c_str(), streaming) != NK_OK) {
         fprintf(stderr, "Error: %s\n", nk_last_error());  // the reference returns Err from main
@@ -81,6 +86,12 @@ int main(int argc, char** argv) {
         return 1;
     }
 
+    if (timing) {
+        nk_timings t;
+        nk_last_timings(h, &t);
+        fprintf(stderr, "[timing] nk_process_file done at %.3f s (device: h2d %.2f ms, mark %.2f, count %.2f, post %.2f; %llu k-mers)\n",
+                since(), t.h2d_ms, t.mark_ms, t.count_ms, t.lif_ms, (unsigned long long)t.kmers);
+    }
     printf("\n=== Top 20 Abundant Neuron Groups (Highest Spike Rates) ===\n");
     std::vector<nk_top_entry> top(top_n ? top_n : 1);
     uint64_t got = 0;
@@ -107,5 +118,6 @@ int main(int argc, char** argv) {
     printf("Neuron pool size used: %" PRIu64 "\n", (uint64_t)cfg.pool_size);
     printf("Streaming mode: %s\n", streaming ? "true" : "false");
     nk_destroy(h);
+    if (timing) fprintf(stderr, "[timing] exit at %.3f s\n", since());
     return 0;
 }

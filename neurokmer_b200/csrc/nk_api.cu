@@ -44,6 +44,7 @@ int fail(int code, const char* fmt, ...) {
         if (rc_ != NK_OK) return rc_; \
     } while (0)
 
+constexpr size_t kMaxTimedChunks = 1024;
 constexpr unsigned long long kChunkBytes = 32ull << 20;  // host->device pipeline granule (multiple of COUNT_TILE)
 static_assert(kChunkBytes % nk::COUNT_TILE == 0, "chunks must be whole tiles");
 
@@ -225,6 +226,9 @@ int count_chunk(nk_counter* h, DevBuf& b, const unsigned long long* d_offsets, u
     if (nstarts == 0) return NK_OK;
     if (h->acc_kmers + max_windows > 0xFFFFFFFFull) NK_TRY(fold_now(h));
     cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+    // phase timing covers at most kMaxTimedChunks chunks of a job (bounds the event pool of very long
+    // streams; nk_timings.kmers and all results are unaffected)
+    if (pe && pe->mark0.size() >= kMaxTimedChunks) pe = nullptr;
     if (pe) {
         NK_TRY(get_event(h, &e0));
         NK_TRY(get_event(h, &e1));

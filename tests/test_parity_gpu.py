@@ -798,3 +798,24 @@ def test_exact_modulo_all_pool_sizes():
         want = np.array([int(x) % p for x in v], np.uint64)
         for which in (0, 1):
             np.testing.assert_array_equal(debug_mod(v, p, which), want, err_msg=f"pool {p} routine {which}")
+
+
+@pytest.mark.parametrize("k,pool,canonical", [(31, 2_000_000, False), (11, 65536, True), (16, 4099, False), (32, 1_000_003, True), (2, 7, True)])
+def test_short_read_compaction_mode(coracle, k, pool, canonical):
+    """Short-read batches (mean length < 2 KiB) take the warp-compaction instantiation of the count
+    kernel: every template corner of it (non-canonical skip rule, k <= 16, power-of-two pool, k = 32)
+    against the oracle, with N-rich reads, reads shorter than k and empty reads."""
+    rng = np.random.default_rng(1000 + k)
+    lens = rng.choice([0, 1, k - 1, k, k + 1, 36, 75, 100, 150, 151, 250, 511, 512, 513], size=6000)
+    seqs = [random_dna(rng, int(n), 0.03, 0.1, 0.01) for n in lens]
+    from neurokmer_b200 import flatten
+    bases, offsets = flatten(seqs)
+    c = make(k, pool, canonical)
+    c.process_batch(bases, offsets)
+    exp, tot = coracle.accumulate(bases, offsets, k, pool, canonical, threads=4)
+    np.testing.assert_array_equal(c.currents(), exp)
+    assert c.timings()["kmers"] == tot == int(np.maximum(lens - k + 1, 0).sum())
+    # the same reads as ONE long batch with exact tables on (word-append instantiation) agree too
+    e = make(k, pool, canonical); e.enable_exact_counts(True); e.process_batch(bases, offsets)
+    np.testing.assert_array_equal(e.currents(), exp)
+    assert int(e.exact_table()[1].sum()) == tot

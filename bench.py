@@ -274,7 +274,7 @@ def gpu_arm(args):
         if world > 1:
             finish_distributed(); t.append(time.perf_counter()); t.append(time.perf_counter())
         else:
-            allreduce_currents(); t.append(time.perf_counter())
+            t.append(time.perf_counter())
             c.stream_finish(); t.append(time.perf_counter())
         top = c.top_abundant_neurons(TOPN); t.append(time.perf_counter())
         trace.append(np.diff(t) * 1e3)

@@ -762,6 +762,7 @@ int nk_reset(nk_counter* h) {
     // middle of a stream has to clear it.  currents / v / r / spikes become lazily zero.
     if (h->acc_dirty || h->streaming) NK_CUDA(cudaMemsetAsync(h->acc, 0, P * sizeof(unsigned int), h->stream));
     h->lazy_zero = true;
+    h->table_valid = false;  // a reset counter is a fresh counter: its first job rebuilds the LIF table
     h->top_cache_valid = false;
     h->pending_pack = false;
     NK_CUDA(cudaMemsetAsync(h->scalars, 0, 8 * sizeof(unsigned long long), h->stream));

@@ -644,6 +644,8 @@ def test_cli_result_block(tmp_path, coracle):
     import subprocess
     from neurokmer_b200.fastx import write_fasta
     from neurokmer_b200 import flatten
+    from neurokmer_b200 import build as nkbuild
+    nkbuild.build()  # no-op when libneurokmer.so and the CLI binary are up to date
     exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "neurokmer_b200", "neurokmer")
     rng = np.random.default_rng(13)
     seqs = [random_dna(rng, n, 0.002, 0.01) for n in (400_000, 100, 250_000)]

@@ -143,7 +143,8 @@ struct nk_counter {
     bool exact = false;
     nk::ExactTable xt;
     unsigned int* d_top_uniques = nullptr;
-    bool table_valid = false;
+    bool table_valid = false, table_inflight = false;
+    cudaEvent_t table_ready = nullptr;
     nk_config table_cfg{};
     unsigned long long table_n = 0;
 };
@@ -220,6 +221,8 @@ int fold_now(nk_counter* h) {
 // mark + count one device-resident chunk: window starts [origin, origin+nstarts) of the
 // concatenated batch, whose bytes live at `b.bases` (chunk-relative) and whose offsets
 // (batch-absolute) live at d_offsets.
+int prelaunch_table(nk_counter* h);
+
 int count_chunk(nk_counter* h, DevBuf& b, const unsigned long long* d_offsets, unsigned long long seq_lo,
                 unsigned long long seq_hi, unsigned long long origin, unsigned long long nstarts,
                 unsigned long long max_windows, PhaseEvents* pe) {
@@ -266,6 +269,9 @@ int count_chunk(nk_counter* h, DevBuf& b, const unsigned long long* d_offsets, u
     }
     h->acc_dirty = true;
     h->acc_kmers += max_windows;
+    // queued BEHIND the count kernel's persistent grid: the table build (side stream, 4 CTAs) gets
+    // its SM slots when the first count CTAs retire, i.e. it runs in the count kernel's tail
+    NK_TRY(prelaunch_table(h));
     return NK_OK;
 }
 
@@ -348,6 +354,54 @@ unsigned long long saturation_count(const nk_config& c) {
     return hi;
 }
 
+// (Re)build the per-count LIF table if the LIF parameters changed; `on` = stream to build on.
+int ensure_table(nk_counter* h, unsigned long long table_n, cudaStream_t on) {
+    const nk_config& a = h->cfg; const nk_config& b = h->table_cfg;
+    const bool same = h->table_valid && h->table_n == table_n && a.steps == b.steps && a.threshold == b.threshold &&
+                      a.leak == b.leak && a.refractory == b.refractory;
+    if (same) return NK_OK;
+    if (table_n > h->table_cap) {
+        NK_CUDA(cudaStreamSynchronize(h->stream));
+        NK_CUDA(cudaStreamSynchronize(h->copy_stream));
+        cudaFree(h->table.spikes); cudaFree(h->table.v); cudaFree(h->table.r);
+        h->table = nk::LifTable{};
+        h->table_cap = 0;
+        NK_CUDA(cudaMalloc(&h->table.spikes, table_n * sizeof(unsigned int)));
+        NK_CUDA(cudaMalloc(&h->table.v, table_n * sizeof(float)));
+        NK_CUDA(cudaMalloc(&h->table.r, table_n * sizeof(unsigned int)));
+        h->table_cap = table_n;
+    }
+    nk::LifParams p{};
+    p.steps = h->cfg.steps; p.thr = h->cfg.threshold; p.leak = h->cfg.leak; p.period = h->cfg.refractory;
+    NK_CUDA(nk::launch_lif_table_build(p, h->table, table_n, on));
+    ++h->last.launches;
+    h->table_valid = true;
+    h->table_cfg = h->cfg;
+    h->table_n = table_n;
+    if (on != h->stream) {
+        if (!h->table_ready) NK_CUDA(cudaEventCreateWithFlags(&h->table_ready, cudaEventDisableTiming));
+        NK_CUDA(cudaEventRecord(h->table_ready, on));
+        h->table_inflight = true;
+    }
+    return NK_OK;
+}
+
+bool table_path_ok(const nk_counter* h, unsigned long long* table_n) {
+    if (!h->fresh || h->force_direct || h->cfg.steps == 0 || !std::isfinite(h->cfg.threshold) || !std::isfinite(h->cfg.leak)) return false;
+    const unsigned long long sat = saturation_count(h->cfg);
+    if (sat >= (1ull << 20)) return false;
+    *table_n = sat + 1;
+    return true;
+}
+
+// At the start of a job on a fresh counter: the table depends on the LIF parameters only, so it
+// is built on the side stream while the count kernel runs (the post kernel waits for its event).
+int prelaunch_table(nk_counter* h) {
+    unsigned long long table_n = 0;
+    if (!table_path_ok(h, &table_n)) return NK_OK;
+    return ensure_table(h, table_n, h->copy_stream);
+}
+
 // LIF over this call's totals; skip_zero: in-memory driver (:187-200) vs SIMD driver (:544-659).
 // If the u32 batch accumulators still hold counts they are folded into `currents` by the LIF
 // kernel itself (fold_mode), otherwise the stored currents are used as they are.
@@ -373,12 +427,8 @@ int simulate(nk_counter* h, bool skip_zero, bool with_topn = false) {
     p.period = h->cfg.refractory;
     p.skip_zero = skip_zero ? 1 : 0;
     NK_CUDA(cudaMemsetAsync(h->scalars, 0, sizeof(unsigned long long), h->stream));
-    bool use_table = false;
     unsigned long long table_n = 0;
-    if (h->fresh && !h->force_direct && std::isfinite(h->cfg.threshold) && std::isfinite(h->cfg.leak)) {
-        const unsigned long long sat = saturation_count(h->cfg);
-        if (sat < (1ull << 20)) { use_table = true; table_n = sat + 1; }
-    }
+    const bool use_table = table_path_ok(h, &table_n);
     if (h->lazy_zero) {
         if (use_table && fold_mode != 0) {
             p.zero_state = 1;   // the kernel writes currents, v, r, spikes of EVERY neuron without reading them
@@ -388,26 +438,10 @@ int simulate(nk_counter* h, bool skip_zero, bool with_topn = false) {
         }
     }
     if (use_table) {
-        const nk_config& a = h->cfg; const nk_config& b = h->table_cfg;
-        const bool same = h->table_valid && h->table_n == table_n && a.steps == b.steps && a.threshold == b.threshold &&
-                          a.leak == b.leak && a.refractory == b.refractory;
-        if (!same) {  // the table depends on the LIF parameters only: built once, reused by every job
-            if (table_n > h->table_cap) {
-                if (h->table.spikes) cudaFree(h->table.spikes);
-                if (h->table.v) cudaFree(h->table.v);
-                if (h->table.r) cudaFree(h->table.r);
-                h->table = nk::LifTable{};
-                h->table_cap = 0;
-                NK_CUDA(cudaMalloc(&h->table.spikes, table_n * sizeof(unsigned int)));
-                NK_CUDA(cudaMalloc(&h->table.v, table_n * sizeof(float)));
-                NK_CUDA(cudaMalloc(&h->table.r, table_n * sizeof(unsigned int)));
-                h->table_cap = table_n;
-            }
-            NK_CUDA(nk::launch_lif_table_build(p, h->table, table_n, h->stream));
-            ++h->last.launches;
-            h->table_valid = true;
-            h->table_cfg = h->cfg;
-            h->table_n = table_n;
+        NK_TRY(ensure_table(h, table_n, h->stream));  // usually already built by prelaunch_table
+        if (h->table_inflight) {
+            NK_CUDA(cudaStreamWaitEvent(h->stream, h->table_ready, 0));
+            h->table_inflight = false;
         }
         const unsigned long long per_call_b = (h->cfg.steps + h->cfg.refractory) / ((unsigned long long)h->cfg.refractory + 1ull);
         const unsigned long long bound = (h->spike_bound + per_call_b < h->spike_bound) ? ~0ull : h->spike_bound + per_call_b;
@@ -788,6 +822,7 @@ int nk_destroy(nk_counter* h) {
     cudaFree(h->scalars); cudaFree(h->tile_counter);
     if (h->h_scalars) cudaFreeHost(h->h_scalars);
     cudaFree(h->table.spikes); cudaFree(h->table.v); cudaFree(h->table.r);
+    if (h->table_ready) cudaEventDestroy(h->table_ready);
     cudaFree(h->topn.hist); cudaFree(h->topn.ctrl); cudaFree(h->topn.block_counts);
     cudaFree(h->topn.out_idx); cudaFree(h->topn.out_spikes);
     cudaFree(h->post_zero); cudaFree(h->d_pack);
@@ -1301,21 +1336,10 @@ int nk_dist_post(nk_counter* h, void** dev_pack, uint64_t* pack_u64s, uint64_t* 
     p.period = h->cfg.refractory;
     p.skip_zero = 0;
     const unsigned long long table_n = saturation_count(h->cfg) + 1;
-    const nk_config& a = h->cfg; const nk_config& b = h->table_cfg;
-    const bool same = h->table_valid && h->table_n == table_n && a.steps == b.steps && a.threshold == b.threshold &&
-                      a.leak == b.leak && a.refractory == b.refractory;
-    if (!same) {
-        if (table_n > h->table_cap) {
-            cudaFree(h->table.spikes); cudaFree(h->table.v); cudaFree(h->table.r);
-            h->table = nk::LifTable{}; h->table_cap = 0;
-            NK_CUDA(cudaMalloc(&h->table.spikes, table_n * sizeof(unsigned int)));
-            NK_CUDA(cudaMalloc(&h->table.v, table_n * sizeof(float)));
-            NK_CUDA(cudaMalloc(&h->table.r, table_n * sizeof(unsigned int)));
-            h->table_cap = table_n;
-        }
-        NK_CUDA(nk::launch_lif_table_build(p, h->table, table_n, h->stream));
-        ++h->last.launches;
-        h->table_valid = true; h->table_cfg = h->cfg; h->table_n = table_n;
+    NK_TRY(ensure_table(h, table_n, h->stream));  // usually prelaunched by nk_stream_begin on the side stream
+    if (h->table_inflight) {
+        NK_CUDA(cudaStreamWaitEvent(h->stream, h->table_ready, 0));
+        h->table_inflight = false;
     }
     const unsigned long long per_call = (h->cfg.steps + h->cfg.refractory) / ((unsigned long long)h->cfg.refractory + 1ull);
     nk::PostParams q{};

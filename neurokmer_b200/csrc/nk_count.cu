@@ -33,8 +33,7 @@ constexpr int kSmemTotal = COUNT_STAGES * kStageStride;
 constexpr int kCompactBytes = COUNT_WARPS * COUNT_CHUNK * 8;  // MODE 3: one 512-word buffer per warp
 
 static_assert(kBytesPerStage % 16 == 0 && kBitsPerStage % 16 == 0, "TMA bulk copies are 16-byte granular");
-static_assert(COUNT_SPAN * (COUNT_WARPS - 1) + COUNT_SPAN + COUNT_CHUNK <= kStageStride,
-              "the look-ahead load of the last chunk must stay inside the stage");
+static_assert(COUNT_HALO == 32, "the last warp converts exactly two 16-byte halo words");
 
 struct WindowConsts {
     unsigned wide;     // k <= 16: the forward window lives in (F0:F1) only
@@ -228,6 +227,7 @@ __global__ void __launch_bounds__(COUNT_THREADS, NK_COUNT_MINBLOCKS) count_kerne
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) unsigned long long bars[COUNT_STAGES];
     __shared__ unsigned long long tile_of[COUNT_STAGES];
+    __shared__ unsigned int halo[COUNT_WARPS][2][3];
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < COUNT_STAGES; ++s) mbar_init(&bars[s], 1);
@@ -257,9 +257,29 @@ __global__ void __launch_bounds__(COUNT_THREADS, NK_COUNT_MINBLOCKS) count_kerne
         const unsigned span0 = warp * COUNT_SPAN;
         const unsigned char* lp = sb + span0 + 16u * lane;
         Codes16 cur = convert16<!CANON>(*reinterpret_cast<const uint4*>(lp));
+        // The k-1 overlap past the END of a warp's span is the first two code words of the next
+        // warp's span: they are exchanged through shared memory instead of being converted twice
+        // (the last warp converts the tile's 32-byte halo).  This is what makes small tiles cheap,
+        // and small tiles are what keeps the tail of the persistent grid short.
+        if (lane < 2) {
+            halo[warp][lane][0] = cur.F;
+            halo[warp][lane][1] = cur.R;
+            halo[warp][lane][2] = cur.V;
+        }
+        Codes16 tail{0u, 0u, 0u};
+        if (warp == COUNT_WARPS - 1)
+            tail = convert16<!CANON>(*reinterpret_cast<const uint4*>(sb + COUNT_TILE + 16u * (lane & 1u)));
+        __syncthreads();
+        if (warp < COUNT_WARPS - 1 && lane < 2) {
+            tail.F = halo[warp + 1][lane][0];
+            tail.R = halo[warp + 1][lane][1];
+            tail.V = halo[warp + 1][lane][2];
+        }
 #pragma unroll 1
         for (unsigned c = 0; c < COUNT_CHUNKS_PER_SPAN; ++c) {
-            const Codes16 nxt = convert16<!CANON>(*reinterpret_cast<const uint4*>(lp + (c + 1u) * COUNT_CHUNK));
+            Codes16 nxt = tail;
+            if (c + 1u < COUNT_CHUNKS_PER_SPAN)
+                nxt = convert16<!CANON>(*reinterpret_cast<const uint4*>(lp + (c + 1u) * COUNT_CHUNK));
             const unsigned off = span0 + c * COUNT_CHUNK;
             const unsigned inv16 = bits[(off >> 4) + lane];
             process_chunk<CANON, MODE, POW2, KHI>(p, wc, cur, nxt, inv16, lane, tile * COUNT_TILE + off + 16u * lane,

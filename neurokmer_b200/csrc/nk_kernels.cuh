@@ -13,15 +13,18 @@ namespace nk {
 // in chunks of 512 positions: lane L loads the 16 bytes [16L, 16L+16) of the
 // chunk (one LDS.128 from the TMA-staged tile), turns them into 2-bit code words,
 // and receives the words of lanes L+1, L+2 by shuffle (the k-1 <= 31 overlap).
-constexpr int COUNT_THREADS = 256;
+#ifndef NK_COUNT_THREADS
+#define NK_COUNT_THREADS 256
+#endif
+constexpr int COUNT_THREADS = NK_COUNT_THREADS;
 constexpr int COUNT_WARPS = COUNT_THREADS / 32;
 constexpr int COUNT_CHUNK = 512;                         // positions per warp iteration
 #ifndef NK_CHUNKS_PER_SPAN
-#define NK_CHUNKS_PER_SPAN 4
+#define NK_CHUNKS_PER_SPAN 1
 #endif
 constexpr int COUNT_CHUNKS_PER_SPAN = NK_CHUNKS_PER_SPAN;
 constexpr int COUNT_SPAN = COUNT_CHUNK * COUNT_CHUNKS_PER_SPAN;
-constexpr int COUNT_TILE = COUNT_WARPS * COUNT_SPAN;     // 16384 positions
+constexpr int COUNT_TILE = COUNT_WARPS * COUNT_SPAN;     // 4096 positions: small tiles keep the grid's tail short
 constexpr int COUNT_HALO = 32;                           // >= k-1, multiple of 16
 constexpr int COUNT_STAGES = 2;
 

@@ -1,26 +1,26 @@
 #!/bin/bash
-# Build count-kernel variants (different NK_ROT_PLAN = which rotate halves run on the FMA pipe)
-# into gpurun_out/variants/lib_<name>.so; bench each with NEUROKMER_LIB=... python bench.py
+# Build count-kernel variants into neurokmer_b200/build/variants/lib_<name>.so.  Compile-time knobs:
+# NK_ROT_PLAN_ID, NK_COUNT_UNROLL, NK_CHUNKS_PER_SPAN, NK_COUNT_THREADS, NK_COUNT_MINBLOCKS, NK_EXP_NORED.
+# Bench each with tools/bench_variants.sh (NEUROKMER_LIB=... python bench.py) under gpurun.
+# Usage: tools/variants.sh "name1:-DFOO=1 -DBAR=2" "name2:..."   (run `python -m neurokmer_b200.build` first)
 set +e
 cd "$(dirname "$0")/.."
 OUT=neurokmer_b200/build/variants; mkdir -p $OUT
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-fvisibility=hidden"
 build() { # name, defines...
   local name=$1; shift
-  nvcc $FLAGS "$@" -c neurokmer_b200/csrc/nk_count.cu -o $OUT/nk_count_$name.o 2>&1 | grep -E "error" 
-  nvcc $FLAGS "$@" -c neurokmer_b200/csrc/nk_api.cu -o $OUT/nk_api_$name.o 2>&1 | grep -E "error"
-  nvcc -shared -o $OUT/lib_$name.so $OUT/nk_count_$name.o neurokmer_b200/build/nk_lif.o neurokmer_b200/build/nk_topn.o \
-     neurokmer_b200/build/nk_misc.o $OUT/nk_api_$name.o neurokmer_b200/build/nk_fastx.o -cudart static -lpthread -ldl -lrt 2>/dev/null
+  nvcc $FLAGS "$@" -c neurokmer_b200/csrc/nk_count.cu -o $OUT/nk_count_$name.o 2>&1 | grep -E " error"
+  nvcc $FLAGS "$@" -c neurokmer_b200/csrc/nk_api.cu -o $OUT/nk_api_$name.o 2>&1 | grep -E " error"
+  nvcc -shared -o $OUT/lib_$name.so $OUT/nk_count_$name.o $OUT/nk_api_$name.o neurokmer_b200/build/nk_lif.o neurokmer_b200/build/nk_topn.o \
+     neurokmer_b200/build/nk_misc.o neurokmer_b200/build/nk_post.o neurokmer_b200/build/nk_exact.o neurokmer_b200/build/nk_fastx.o \
+     -cudart static -lpthread -ldl -lrt 2>&1 | grep -v deprecated
+  python -c "import ctypes; ctypes.CDLL('$OUT/lib_$name.so')" || echo "lib_$name.so does not load"
 }
 rm -f $OUT/lib_*.so
 build base &
-build u2 -DNK_COUNT_UNROLL=2 &
-build u8 -DNK_COUNT_UNROLL=8 &
-build u16 -DNK_COUNT_UNROLL=16 &
-build span2 -DNK_CHUNKS_PER_SPAN=2 &
-build span2mb8 -DNK_CHUNKS_PER_SPAN=2 -DNK_COUNT_MINBLOCKS=8 &
-build span1mb8 -DNK_CHUNKS_PER_SPAN=1 -DNK_COUNT_MINBLOCKS=8 &
-build p27span2mb8 -DNK_ROT_PLAN_ID=27 -DNK_CHUNKS_PER_SPAN=2 -DNK_COUNT_MINBLOCKS=8 &
-build p27u8 -DNK_ROT_PLAN_ID=27 -DNK_COUNT_UNROLL=8 &
+for spec in "$@"; do
+  name=${spec%%:*}; defs=${spec#*:}
+  build $name $defs &
+done
 wait
 ls $OUT/*.so

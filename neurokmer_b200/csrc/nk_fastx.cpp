@@ -107,10 +107,15 @@ size_t FastxReader::read_seq(uint8_t* dst, size_t cap, bool* done) {
         if (avail > cap - w) avail = cap - w;
         const uint8_t* nl = (const uint8_t*)memchr(s, '\n', avail);
         const size_t n = nl ? (size_t)(nl - s) : avail;
-        // strip '\r' (only ever a line terminator in text FASTA/FASTQ)
-        for (size_t i = 0; i < n; ++i) {
-            const uint8_t b = s[i];
-            if (b != '\r') dst[w++] = b;
+        // strip '\r' (only ever a line terminator in text FASTA/FASTQ); the common line has none: memcpy
+        if (n > 0 && s[n - 1] != '\r' && !memchr(s, '\r', n)) {
+            memcpy(dst + w, s, n);
+            w += n;
+        } else {
+            for (size_t i = 0; i < n; ++i) {
+                const uint8_t b = s[i];
+                if (b != '\r') dst[w++] = b;
+            }
         }
         pos_ += n;
         if (nl) {

@@ -11,6 +11,11 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200, sm_100a); run with -m gpu")
+    # the tests exercise the BUILT shared library; build it (nvcc, sm_100a) if the tree has none yet
+    lib = os.path.join(ROOT, "neurokmer_b200", "libneurokmer.so")
+    if not os.path.exists(lib):
+        from neurokmer_b200 import build as nkbuild
+        nkbuild.build()
 
 
 @pytest.fixture(scope="session")

@@ -821,3 +821,63 @@ def test_short_read_compaction_mode(coracle, k, pool, canonical):
     e = make(k, pool, canonical); e.enable_exact_counts(True); e.process_batch(bases, offsets)
     np.testing.assert_array_equal(e.currents(), exp)
     assert int(e.exact_table()[1].sum()) == tot
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
+def test_api_call_sequence_fuzz(coracle, seed):
+    """Random sequences of the public entry points against the oracle's mirror of the reference's
+    state rules: currents overwritten per batch call, neuron state / energy carried over, streaming vs
+    in-memory LIF drivers, process_sequence's single tick, simulate_spikes_auto on stored currents,
+    set_steps, reset, read-outs in between (they must not perturb anything)."""
+    from neurokmer_b200 import flatten
+    rng = np.random.default_rng(seed)
+    k = int(rng.choice([5, 15, 21, 31]))
+    pool = int(rng.choice([64, 1000, 5003, 65536]))
+    canonical = bool(rng.integers(0, 2))
+    c = make(k, pool, canonical)
+    o = oracle_counter(k, pool, canonical)
+    scratch = np.zeros(pool, np.uint64)
+
+    def batch():
+        n = int(rng.integers(0, 5))
+        seqs = [random_dna(rng, int(rng.choice([0, 3, k, 40, 700, 5000, 60000])), 0.01, 0.05) for _ in range(n)]
+        return flatten(seqs)
+
+    for step in range(24):
+        op = rng.choice(["batch", "stream", "sequence", "simulate", "steps", "reset", "readout"],
+                        p=[0.28, 0.22, 0.14, 0.08, 0.08, 0.08, 0.12])
+        if op == "batch":
+            b, off = batch()
+            c.process_batch(b, off); o.process_parallel(b, off)
+        elif op == "stream":
+            batches = [batch() for _ in range(int(rng.integers(0, 4)))]
+            c.stream_begin()
+            for b, off in batches:
+                c.stream_push(b, off)
+            c.stream_end()
+            o.process_streaming(batches)
+        elif op == "sequence":
+            s = random_dna(rng, int(rng.choice([2, k, 50, 400])), 0.02)
+            c.process_sequence(s)
+            # process_sequence adds to the stored currents, ticks once, zeroes them (spiking_hash.rs:203-273)
+            scratch[:] = o.currents
+            fired = coracle.process_sequence(s, k, pool, canonical, 1.0, 0.95, 2, scratch, o.v, o.r, o.spikes)
+            if len(s) >= k:
+                o.currents = scratch.copy()
+            o.total_spikes += fired
+            o.energy_fixed += fired * 1000
+        elif op == "simulate":
+            c.simulate_spikes_auto(); o._simulate(simd=True)
+        elif op == "steps":
+            st = int(rng.choice([0, 1, 10, 1000]))
+            c.set_steps(st); o.steps = st
+        elif op == "reset":
+            c.reset()
+            o.v[:] = 0; o.r[:] = 0; o.spikes[:] = 0; o.currents[:] = 0; o.total_spikes = 0; o.energy_fixed = 0
+        else:
+            assert_topn_equal(c, o, int(rng.choice([1, 20, 64])))
+            assert c.energy.total_spikes() == o.total_spikes
+        if rng.random() < 0.5:
+            assert_state_equal(c, o)
+    assert_state_equal(c, o)
+    assert_topn_equal(c, o, 20)

@@ -193,6 +193,7 @@ def gpu_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     os.environ["NCCL_DEBUG"] = os.environ.get("NK_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
+    local %= max(torch.cuda.device_count(), 1)  # launchers that expose one device per rank
     torch.cuda.set_device(local)
     saved_stdout = os.dup(1)
     os.dup2(2, 1)  # NCCL prints a version banner to stdout: keep stdout to the one JSON line

@@ -1286,6 +1286,12 @@ int nk_dist_setup(nk_counter* h, int rank, int world, const void* handles, void*
     if (world < 1 || world > 16 || rank < 0 || rank >= world) return fail(NK_ERR_BAD_ARG, "bad rank/world (world <= 16)");
     if (!handles && !raw_ptrs) return fail(NK_ERR_BAD_ARG, "need IPC handles or raw pointers");
     NK_CUDA(cudaSetDevice(h->cfg.device));
+    NK_CUDA(cudaStreamSynchronize(h->stream));
+    for (int r = 0; r < 16; ++r) {  // a repeated setup replaces the previous mappings
+        if (h->dist_ipc_opened[r]) cudaIpcCloseMemHandle((void*)h->dist_peer[r]);
+        h->dist_ipc_opened[r] = false;
+        h->dist_peer[r] = nullptr;
+    }
     for (int r = 0; r < world; ++r) {
         if (r == rank) { h->dist_peer[r] = h->acc; continue; }
         if (raw_ptrs) { h->dist_peer[r] = (const unsigned int*)raw_ptrs[r]; continue; }

@@ -226,7 +226,7 @@ cudaError_t exact_finalize(ExactTable& t, const FastMod& fm, unsigned long long 
     t.valid = true;
     // the words of this call are consumed
     t.words_bound = 0;
-    NKX(cudaMemsetAsync(t.cursor, 0, sizeof(unsigned long long), s));
+    if (t.cursor) NKX(cudaMemsetAsync(t.cursor, 0, sizeof(unsigned long long), s));
     return cudaGetLastError();
 }
 

@@ -599,6 +599,18 @@ def test_exact_side_tables(coracle, k, pool, canonical):
     np.testing.assert_array_equal(gk, keys); np.testing.assert_array_equal(gc, counts)
 
 
+def test_exact_tables_empty_inputs():
+    c = make(31, 1000); c.enable_exact_counts(True)
+    c.process_parallel([])                         # nothing counted at all
+    assert c.exact_table()[0].size == 0 and c.kmer_per_neuron().sum() == 0 and c.get_count(5) is None
+    c.process_parallel([b"ACGT", b""])             # only sequences shorter than k
+    assert c.exact_table()[0].size == 0
+    assert c.top_abundant_neurons(3) == [(0, 0, 0), (1, 0, 0), (2, 0, 0)]
+    c.process_parallel([b"A" * 40])
+    keys, counts = c.exact_table()
+    assert keys.tolist() == [0] and counts.tolist() == [10] and c.get_count(0) == 10
+
+
 def test_exact_tables_process_sequence(coracle):
     """process_sequence ADDS to counts (:218-221) and counts, per neuron, the sequences that touched it (:262-264)."""
     rng = np.random.default_rng(8)

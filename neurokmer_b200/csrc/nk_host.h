@@ -14,6 +14,7 @@ uint64_t host_pack_kmer(const uint8_t* kmer, uint64_t len);
 
 // Incremental FASTA/FASTQ record reader with needletail's record rules as the
 // reference uses them (src/utils.rs:9-24):
+//   * gzip input is decompressed transparently (zlib), like needletail's sniffing reader;
 //   * format by first byte: '>' FASTA, '@' FASTQ; anything else / empty file is an error at open;
 //   * a record's sequence = its sequence line(s) with '\n' and '\r' removed, bytes otherwise untouched;
 //   * FASTQ records are 4 lines; '+' separator and |qual| == |seq| are checked;
@@ -44,6 +45,7 @@ private:
     void skip_line();
 
     int fd_ = -1;
+    void* gz_ = nullptr;  // gzFile when the input is gzip-compressed
     std::vector<uint8_t> buf_;
     size_t pos_ = 0, end_ = 0;
     bool eof_ = false, fastq_ = false, at_line_start_ = true, started_ = false;

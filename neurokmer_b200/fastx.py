@@ -9,8 +9,17 @@ from __future__ import annotations
 from typing import Iterator
 
 
-def read_fastx(path: str) -> Iterator[bytes]:
+def _open(path: str):
     with open(path, "rb") as f:
+        magic = f.read(2)
+    if magic == b"\x1f\x8b":  # gzip, sniffed from the magic bytes like needletail does
+        import gzip
+        return gzip.open(path, "rb")
+    return open(path, "rb")
+
+
+def read_fastx(path: str) -> Iterator[bytes]:
+    with _open(path) as f:
         first = f.read(1)
         if not first:
             raise OSError(f"{path}: empty file")

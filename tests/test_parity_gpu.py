@@ -328,6 +328,14 @@ def test_process_file_fasta_fastq(tmp_path, coracle):
     c = make(k, pool); c.process_file_streaming(crlf)
     exp, _ = coracle.accumulate(bases, offsets, k, pool, True)
     np.testing.assert_array_equal(c.currents(), exp)
+    # gzip input is decompressed transparently (needletail sniffs the magic bytes)
+    import gzip
+    for src in (fa, fq):
+        gzp = src + ".gz"
+        with open(src, "rb") as f, gzip.open(gzp, "wb", compresslevel=1) as g:
+            g.write(f.read())
+        c = make(k, pool); c.process_file_streaming(gzp)
+        np.testing.assert_array_equal(c.currents(), exp)
     # a malformed FASTQ record ends the stream: records before it still count (utils.rs:17-20)
     bad = str(tmp_path / "bad.fastq")
     with open(bad, "wb") as g:

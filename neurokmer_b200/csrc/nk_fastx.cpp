@@ -2,6 +2,7 @@
 // parse_fastx_file as the reference drives it (src/utils.rs:9-24): see nk_host.h.
 #include "nk_host.h"
 
+#include <algorithm>
 #include <cerrno>
 #include <cstring>
 #include <fcntl.h>
@@ -166,6 +167,71 @@ bool FastxReader::finish_record(uint64_t seq_len) {
     (void)saw_nl;
     at_line_start_ = true;
     return q == seq_len;
+}
+
+FastaWindowPlan fasta_plan_window(const uint8_t* file, size_t size, size_t ws, size_t window, int state_in, int* state_next) {
+    FastaWindowPlan w;
+    w.ws = ws;
+    w.start_state = state_in;
+    size_t e = ws + window;
+    if (e >= size) {
+        w.we = size;
+        *state_next = FA_LINE_START;
+        return w;
+    }
+    // prefer to end at a line start: look for the next '\n' at or after the nominal end (bounded, so
+    // that a window never exceeds window + kFastaSlack bytes)
+    const size_t span = std::min(std::min(window, (size_t)kFastaSlack), size - e);
+    const uint8_t* nl = (const uint8_t*)memchr(file + e - 1, '\n', span + 1);
+    if (nl) {
+        w.we = (size_t)(nl - file) + 1;
+        *state_next = FA_LINE_START;
+        return w;
+    }
+    // a line longer than the window: cut mid-line; is that line a header?
+    w.we = e;
+    const uint8_t* prev = (const uint8_t*)memrchr(file + ws, '\n', e - ws);
+    if (prev) {
+        *state_next = (prev + 1 < file + e && prev[1] == '>') ? FA_MID_HEADER : FA_MID_SEQ;
+    } else if (state_in == FA_LINE_START) {
+        *state_next = file[ws] == '>' ? FA_MID_HEADER : FA_MID_SEQ;
+    } else {
+        *state_next = state_in;  // still inside the same overlong line
+    }
+    return w;
+}
+
+void fasta_parse_window(const uint8_t* file, const FastaWindowPlan& w, uint8_t* data, size_t* fill,
+                        std::vector<uint64_t>* rec_starts) {
+    size_t p = w.ws, out = 0;
+    rec_starts->clear();
+    int state = w.start_state;
+    while (p < w.we) {
+        const uint8_t* nl = (const uint8_t*)memchr(file + p, '\n', w.we - p);
+        const size_t line_end = nl ? (size_t)(nl - file) : w.we;
+        bool header;
+        if (state == FA_MID_HEADER) header = true;        // rest of a header that started in an earlier window
+        else if (state == FA_MID_SEQ) header = false;     // rest of a sequence line, whatever its first byte
+        else {
+            header = file[p] == '>';
+            if (header) rec_starts->push_back(out);
+        }
+        if (!header) {
+            const uint8_t* s = file + p;
+            const size_t n = line_end - p;
+            if (n > 0 && s[n - 1] != '\r' && !memchr(s, '\r', n)) {
+                memcpy(data + out, s, n);
+                out += n;
+            } else {
+                for (size_t i = 0; i < n; ++i)
+                    if (s[i] != '\r') data[out++] = s[i];
+            }
+        }
+        // after a '\n' the next line starts fresh; without one the window ended mid-line
+        state = FA_LINE_START;
+        p = line_end + 1;
+    }
+    *fill = out;
 }
 
 }  // namespace nk

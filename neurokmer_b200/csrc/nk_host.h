@@ -29,6 +29,7 @@ public:
     // 0 on success; on failure returns non-zero and fills *err
     int open(const char* path, std::string* err);
     bool is_fastq() const { return fastq_; }
+    bool is_gzip() const { return gz_ != nullptr; }
 
     // Advance to the next record. false: EOF or malformed record (iteration over).
     bool next_record();
@@ -50,6 +51,23 @@ private:
     size_t pos_ = 0, end_ = 0;
     bool eof_ = false, fastq_ = false, at_line_start_ = true, started_ = false;
 };
+
+// ---- parallel FASTA ingest (plain files): the file is cut into windows that several host threads
+// strip (headers, '\n', '\r') concurrently; see process_file in nk_api.cu -------------------------
+constexpr unsigned kFastaSlack = 64u << 10;  // a window ends at most this far past its nominal size
+enum FastaStart { FA_LINE_START = 0, FA_MID_HEADER = 1, FA_MID_SEQ = 2 };
+struct FastaWindowPlan {
+    size_t ws = 0, we = 0;   // file byte range [ws, we)
+    int start_state = FA_LINE_START;
+};
+// Next window after `ws` of nominally `window` bytes: ends at a line start when a '\n' is found within
+// `window` bytes past the nominal end, else mid-line.  `state_in` is the start state of THIS window;
+// the start state of the following window is returned in *state_next.
+FastaWindowPlan fasta_plan_window(const uint8_t* file, size_t size, size_t ws, size_t window, int state_in, int* state_next);
+// Strip one window into `data` (capacity >= we - ws): sequence bytes in file order; rec_starts gets the
+// offset (into data) of every record that STARTS in this window (a header line was seen).
+void fasta_parse_window(const uint8_t* file, const FastaWindowPlan& w, uint8_t* data, size_t* fill,
+                        std::vector<uint64_t>* rec_starts);
 
 // whole-file driver behind nk_process_file (defined in nk_api.cu)
 int process_file(nk_counter* h, const char* path, bool streaming, std::string* err);

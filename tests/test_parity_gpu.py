@@ -901,3 +901,47 @@ def test_api_call_sequence_fuzz(coracle, seed):
             assert_state_equal(c, o)
     assert_state_equal(c, o)
     assert_topn_equal(c, o, 20)
+
+
+@pytest.mark.parametrize("seed,window,threads", [(1, 64, 4), (2, 97, 3), (3, 256, 8), (4, 1000, 2), (5, 4096, 16)])
+def test_parallel_fasta_ingest_fuzz(tmp_path, coracle, seed, window, threads, monkeypatch):
+    """The parallel FASTA ingest (windows stripped by several host threads, stitched with a k-1
+    carry) against the serial Python reader + oracle, with tiny windows so that every boundary case
+    occurs: lines and headers longer than a window, records spanning many windows, empty records,
+    blank lines, CRLF, no trailing newline, '>' inside sequence lines."""
+    from neurokmer_b200 import flatten
+    from neurokmer_b200.fastx import read_fastx
+    rng = np.random.default_rng(seed)
+    parts = []
+    for rec in range(int(rng.integers(3, 40))):
+        hdr = b">r%d " % rec + bytes(rng.choice(np.frombuffer(b"abc >xyz", np.uint8), size=int(rng.choice([0, 5, 300])))).replace(b"\n", b"")
+        parts.append(hdr + (b"\r\n" if seed % 2 else b"\n"))
+        n = int(rng.choice([0, 1, 30, 31, 200, 5000]))
+        seq = random_dna(rng, n, 0.02, 0.05)
+        width = int(rng.choice([1, 7, 60, 61, 10**6]))
+        for j in range(0, n, width):
+            line = seq[j:j + width]
+            if rng.random() < 0.02 and len(line) > 3:
+                line = line[:2] + b">" + line[3:]          # '>' that is NOT at a line start is sequence data
+            parts.append(line + (b"\r\n" if seed % 2 else b"\n"))
+        if rng.random() < 0.2:
+            parts.append(b"\n")                             # blank line
+    blob = b"".join(parts)
+    if seed % 3 == 0:
+        blob = blob.rstrip(b"\r\n")                         # no trailing newline
+    fa = str(tmp_path / "fuzz.fa")
+    with open(fa, "wb") as f:
+        f.write(blob)
+    seqs = list(read_fastx(fa))
+    bases, offsets = flatten(seqs)
+    for k, pool in ((31, 5003), (5, 64), (1, 7)):
+        exp, tot = coracle.accumulate(bases, offsets, k, pool, True)
+        monkeypatch.setenv("NK_FASTA_THREADS", "1")        # serial reader
+        s = make(k, pool); s.process_file_streaming(fa)
+        np.testing.assert_array_equal(s.currents(), exp)
+        monkeypatch.setenv("NK_FASTA_THREADS", str(threads))
+        monkeypatch.setenv("NK_FASTA_WINDOW", str(window))
+        p = make(k, pool); p.process_file_streaming(fa)
+        np.testing.assert_array_equal(p.currents(), exp)
+        assert p.timings()["kmers"] == tot
+        monkeypatch.delenv("NK_FASTA_WINDOW")

@@ -627,6 +627,11 @@ struct FaSlot {
     cudaEvent_t copied = nullptr;
     bool copy_inflight = false;
     int state = 0;                      // 0 free, 1 queued/parsing, 2 parsed
+    // FASTQ windows: [a, b) is a whole number of records; offs = record ends; ok = no malformed record
+    int kind = 0;                       // 0 FASTA window, 1 FASTQ window
+    size_t a = 0, b = 0, cap = 0;
+    std::vector<uint64_t> offs;
+    bool ok = true;
 };
 
 struct FaPool {
@@ -649,7 +654,8 @@ struct FaPool {
                 queue.erase(queue.begin());
             }
             FaSlot& sl = slots[si];
-            fasta_parse_window(file, sl.plan, sl.buf + 32, &sl.fill, &sl.rec_starts);
+            if (sl.kind == 0) fasta_parse_window(file, sl.plan, sl.buf + 32, &sl.fill, &sl.rec_starts);
+            else sl.ok = fastq_parse_window(file, sl.a, sl.b, sl.buf, sl.cap, &sl.fill, &sl.offs);
             {
                 std::lock_guard<std::mutex> lk(mu);
                 sl.state = 2;
@@ -776,6 +782,107 @@ int count_fasta_parallel(nk_counter* h, const char* path, PhaseEvents& pe, std::
     return rc;
 }
 
+// FASTQ twin of count_fasta_parallel (see nk_host.h for how record starts are found)
+int count_fastq_parallel(nk_counter* h, const char* path, PhaseEvents& pe, std::string* err, bool* done) {
+    *done = false;
+    unsigned nthreads = std::thread::hardware_concurrency();
+    if (const char* e = getenv("NK_FASTA_THREADS")) nthreads = (unsigned)atoi(e);
+    if (nthreads > 8) nthreads = 8;
+    size_t window = 4u << 20, min_size = 256u << 20;
+    if (const char* e = getenv("NK_FASTA_WINDOW")) { window = (size_t)atoll(e); min_size = 2 * window; }
+    if (nthreads < 2 || window < 64) return NK_OK;
+    const int fd = ::open(path, O_RDONLY);
+    if (fd < 0) return NK_OK;
+    struct stat st;
+    if (fstat(fd, &st) != 0 || (size_t)st.st_size < min_size) { ::close(fd); return NK_OK; }
+    const size_t size = (size_t)st.st_size;
+    void* map = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+    ::close(fd);
+    if (map == MAP_FAILED) return NK_OK;
+    madvise(map, size, MADV_SEQUENTIAL);
+    const uint8_t* file = (const uint8_t*)map;
+
+    // pass 1: newlines per fixed range (parallel), prefix sum, first record start of every range
+    const size_t nr = (size + window - 1) / window;
+    std::vector<uint64_t> nl(nr + 1, 0);
+    {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nthreads; ++t)
+            th.emplace_back([&, t] {
+                for (size_t i = t; i < nr; i += nthreads)
+                    nl[i + 1] = fastq_count_newlines(file, i * window, std::min(size, (i + 1) * window));
+            });
+        for (auto& x : th) x.join();
+    }
+    for (size_t i = 0; i < nr; ++i) nl[i + 1] += nl[i];
+    std::vector<size_t> starts(nr + 1, size);
+    size_t max_win = 0;
+    for (size_t i = 0; i < nr; ++i) starts[i] = fastq_first_record_start(file, size, i * window, nl[i]);
+    for (size_t i = 0; i < nr; ++i) max_win = std::max(max_win, starts[i + 1] - starts[i]);
+    const size_t slack = std::max<size_t>(kFastaSlack, window / 4);
+    if (max_win > window + slack) {  // reads longer than a window: leave the file to the serial reader
+        munmap(map, size);
+        return NK_OK;
+    }
+
+    FaPool pool;
+    pool.file = file;
+    const int nslots = (int)nthreads + 3;
+    pool.slots.resize(nslots);
+    int rc = NK_OK;
+    const size_t cap = (window + slack) / 2 + 64;  // |seq| == |qual|, so the sequences are under half of a window
+    for (auto& sl : pool.slots) {
+        if (cudaMallocHost((void**)&sl.buf, cap) != cudaSuccess) { rc = NK_ERR_OOM; *err = "cudaMallocHost(FASTQ window)"; break; }
+        cudaEventCreateWithFlags(&sl.copied, cudaEventDisableTiming);
+        sl.kind = 1;
+        sl.cap = cap;
+    }
+    if (rc == NK_OK) {
+        for (unsigned t = 0; t < nthreads; ++t) pool.threads.emplace_back([&pool] { pool.worker(); });
+        size_t dispatched = 0, consumed = 0;
+        bool stop = false;
+        while (rc == NK_OK && (consumed < dispatched || (!stop && dispatched < nr))) {
+            while (!stop && dispatched < nr && dispatched - consumed < (size_t)nslots) {
+                FaSlot& sl = pool.slots[dispatched % nslots];
+                if (sl.copy_inflight) { cudaEventSynchronize(sl.copied); sl.copy_inflight = false; }
+                sl.a = starts[dispatched];
+                sl.b = starts[dispatched + 1];
+                {
+                    std::lock_guard<std::mutex> lk(pool.mu);
+                    sl.state = 1;
+                    pool.queue.push_back((int)(dispatched % nslots));
+                }
+                pool.cv_work.notify_one();
+                ++dispatched;
+            }
+            if (consumed == dispatched) break;
+            FaSlot& sl = pool.slots[consumed % nslots];
+            {
+                std::unique_lock<std::mutex> lk(pool.mu);
+                pool.cv_done.wait(lk, [&] { return sl.state == 2; });
+                sl.state = 0;
+            }
+            if (!stop && sl.fill > 0 && sl.offs.size() > 1) {
+                rc = count_host_batch(h, sl.buf, sl.offs.data(), sl.offs.size() - 1, &pe, /*wait_copies=*/false);
+                if (rc != NK_OK) { *err = g_err; break; }
+                cudaEventRecord(sl.copied, h->copy_stream);
+                sl.copy_inflight = true;
+            }
+            if (!sl.ok) stop = true;  // first malformed record: the iteration ends here (src/utils.rs:17-20)
+            ++consumed;
+        }
+    }
+    pool.stop();
+    cudaStreamSynchronize(h->copy_stream);
+    for (auto& sl : pool.slots) {
+        if (sl.buf) cudaFreeHost(sl.buf);
+        if (sl.copied) cudaEventDestroy(sl.copied);
+    }
+    munmap(map, size);
+    *done = rc == NK_OK;
+    return rc;
+}
+
 }  // namespace
 
 int process_file(nk_counter* h, const char* path, bool streaming, std::string* err) {
@@ -830,9 +937,10 @@ int process_file(nk_counter* h, const char* path, bool streaming, std::string* e
         cudaMemsetAsync(h->scalars + 2, 0, sizeof(unsigned long long), h->stream);
         h->currents_valid_overwrite = true;
         bool stop = false;
-        if (!rd.is_fastq() && !rd.is_gzip()) {
+        if (!rd.is_gzip()) {
             bool handled = false;
-            if ((rc = count_fasta_parallel(h, path, pe, err, &handled)) != NK_OK) break;
+            rc = rd.is_fastq() ? count_fastq_parallel(h, path, pe, err, &handled) : count_fasta_parallel(h, path, pe, err, &handled);
+            if (rc != NK_OK) break;
             stop = handled;  // the whole file was ingested by the parallel path
         }
         while (!stop && rd.next_record()) {

@@ -234,4 +234,78 @@ void fasta_parse_window(const uint8_t* file, const FastaWindowPlan& w, uint8_t* 
     *fill = out;
 }
 
+size_t fastq_count_newlines(const uint8_t* file, size_t a, size_t b) {
+    size_t n = 0;
+    const uint8_t* p = file + a;
+    const uint8_t* end = file + b;
+    while (p < end) {
+        const uint8_t* q = (const uint8_t*)memchr(p, '\n', (size_t)(end - p));
+        if (!q) break;
+        ++n;
+        p = q + 1;
+    }
+    return n;
+}
+
+size_t fastq_first_record_start(const uint8_t* file, size_t size, size_t s, uint64_t newlines_before) {
+    if (s >= size) return size;
+    const bool at_line_start = s == 0 || file[s - 1] == '\n';
+    // index of the line that contains byte s == number of newlines before s
+    uint64_t line = newlines_before;
+    size_t p = s;
+    if (!at_line_start) {  // move to the start of the next line
+        const uint8_t* q = (const uint8_t*)memchr(file + p, '\n', size - p);
+        if (!q) return size;
+        p = (size_t)(q - file) + 1;
+        ++line;
+    }
+    while (line % 4 != 0) {
+        if (p >= size) return size;
+        const uint8_t* q = (const uint8_t*)memchr(file + p, '\n', size - p);
+        if (!q) return size;
+        p = (size_t)(q - file) + 1;
+        ++line;
+    }
+    return p;
+}
+
+bool fastq_parse_window(const uint8_t* file, size_t a, size_t b, uint8_t* data, size_t cap, size_t* fill,
+                        std::vector<uint64_t>* offsets) {
+    size_t p = a, out = 0;
+    offsets->clear();
+    offsets->push_back(0);
+    auto line = [&](size_t from, size_t* end, size_t* next) -> bool {  // [from, *end) without the terminator
+        if (from >= b) return false;
+        const uint8_t* q = (const uint8_t*)memchr(file + from, '\n', b - from);
+        const size_t e = q ? (size_t)(q - file) : b;
+        *next = q ? e + 1 : b;
+        *end = (e > from && file[e - 1] == '\r') ? e - 1 : e;
+        return true;
+    };
+    while (p < b) {
+        size_t e0, e1, e2, e3, n1, n2, n3, n4;
+        if (file[p] != '@' || !line(p, &e0, &n1)) break;                         // header
+        if (!line(n1, &e1, &n2)) break;                                          // sequence
+        if (!line(n2, &e2, &n3) || e2 == n2 || file[n2] != '+') break;           // separator
+        if (!line(n3, &e3, &n4)) break;                                          // quality
+        const size_t len = e1 - n1;
+        if (out + len > cap) break;
+        // like the serial reader: every '\r' of the sequence line is dropped, and the QUALITY length
+        // (trailing '\r' trimmed) must equal the number of bytes kept
+        const size_t before = out;
+        if (len && memchr(file + n1, '\r', len)) {
+            for (size_t i = 0; i < len; ++i)
+                if (file[n1 + i] != '\r') data[out++] = file[n1 + i];
+        } else {
+            memcpy(data + out, file + n1, len);
+            out += len;
+        }
+        if (e3 - n3 != out - before) { out = before; break; }                    // |qual| must equal |seq|
+        offsets->push_back(out);
+        p = n4;
+    }
+    *fill = out;
+    return p >= b;  // false: stopped at a malformed (or truncated) record
+}
+
 }  // namespace nk

@@ -69,6 +69,21 @@ FastaWindowPlan fasta_plan_window(const uint8_t* file, size_t size, size_t ws, s
 void fasta_parse_window(const uint8_t* file, const FastaWindowPlan& w, uint8_t* data, size_t* fill,
                         std::vector<uint64_t>* rec_starts);
 
+// ---- parallel FASTQ ingest (plain files) ------------------------------------------------------------
+// A record is exactly 4 lines, so the line number modulo 4 identifies record starts: newlines are
+// counted per fixed byte range in parallel, prefix-summed, and every range's first record start is
+// the first line start whose global line number is a multiple of 4.  (If an earlier record is
+// malformed the phase of later windows is meaningless — but iteration ends at the first malformed
+// record, so they are discarded anyway.)
+size_t fastq_count_newlines(const uint8_t* file, size_t a, size_t b);
+// first record start at or after byte `s`, given the number of '\n' before `s`
+size_t fastq_first_record_start(const uint8_t* file, size_t size, size_t s, uint64_t newlines_before);
+// Parse the records of [a, b) (a is a record start, b a record start or EOF): sequence bytes are
+// appended to data, offsets gets one entry per record end.  Returns false at the first malformed
+// record (everything before it is kept).
+bool fastq_parse_window(const uint8_t* file, size_t a, size_t b, uint8_t* data, size_t cap, size_t* fill,
+                        std::vector<uint64_t>* offsets);
+
 // whole-file driver behind nk_process_file (defined in nk_api.cu)
 int process_file(nk_counter* h, const char* path, bool streaming, std::string* err);
 

@@ -945,3 +945,54 @@ def test_parallel_fasta_ingest_fuzz(tmp_path, coracle, seed, window, threads, mo
         np.testing.assert_array_equal(p.currents(), exp)
         assert p.timings()["kmers"] == tot
         monkeypatch.delenv("NK_FASTA_WINDOW")
+
+
+@pytest.mark.parametrize("seed,window,threads,defect", [(1, 64, 4, None), (2, 200, 3, "qual"), (3, 333, 8, "plus"),
+                                                        (4, 1000, 2, "trunc"), (5, 97, 5, None), (6, 150, 4, "blank")])
+def test_parallel_fastq_ingest_fuzz(tmp_path, coracle, seed, window, threads, defect, monkeypatch):
+    """Parallel FASTQ ingest (record starts from the line number modulo 4, windows parsed by several
+    host threads) against the serial reader: reads of many lengths, CRLF, no trailing newline, quality
+    lines that start with '@' or '+', and a malformed record somewhere in the middle (the iteration must
+    end exactly there, utils.rs:17-20)."""
+    from neurokmer_b200 import flatten
+    from neurokmer_b200.fastx import read_fastx
+    rng = np.random.default_rng(seed)
+    nrec = int(rng.integers(60, 400))
+    bad_at = int(rng.integers(5, nrec - 5)) if defect else -1
+    eol = b"\r\n" if seed % 2 else b"\n"
+    parts = []
+    for i in range(nrec):
+        n = int(rng.choice([0, 1, 20, 31, 75, 150, 151, 400]))
+        seq = random_dna(rng, n, 0.02, 0.02)
+        qual = bytes(rng.choice(np.frombuffer(b"@+I#5>", np.uint8), size=n))   # '@' and '+' may start a quality line
+        rec = [b"@r%d" % i, seq, b"+", qual]
+        if i == bad_at:
+            if defect == "qual":
+                rec[3] = qual + b"I"
+            elif defect == "plus":
+                rec[2] = b"-"
+            elif defect == "blank":
+                parts.append(eol)
+        parts.append(eol.join(rec) + eol)
+        if i == bad_at and defect == "trunc":
+            parts[-1] = eol.join(rec[:2]) + eol
+    blob = b"".join(parts)
+    if seed % 3 == 0:
+        blob = blob[: len(blob) - len(eol)]
+    fq = str(tmp_path / "fuzz.fq")
+    with open(fq, "wb") as f:
+        f.write(blob)
+    k, pool = 31, 5003
+    monkeypatch.setenv("NK_FASTA_THREADS", "1")
+    s = make(k, pool); s.process_file_streaming(fq)
+    seqs = list(read_fastx(fq))
+    if defect not in ("trunc",):
+        assert len(seqs) == (bad_at if defect else nrec)
+    bases, offsets = flatten(seqs)
+    exp, tot = coracle.accumulate(bases, offsets, k, pool, True)
+    np.testing.assert_array_equal(s.currents(), exp)
+    monkeypatch.setenv("NK_FASTA_THREADS", str(threads))
+    monkeypatch.setenv("NK_FASTA_WINDOW", str(window))
+    p = make(k, pool); p.process_file_streaming(fq)
+    np.testing.assert_array_equal(p.currents(), exp)
+    assert p.timings()["kmers"] == tot

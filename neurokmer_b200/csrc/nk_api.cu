@@ -315,10 +315,29 @@ int count_host_batch(nk_counter* h, const uint8_t* bases, const uint64_t* offset
     NK_CUDA(cudaMemcpyAsync(d_offsets, offsets, (nseq + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, h->copy_stream));
     h->last.h2d_bytes += (nseq + 1) * sizeof(uint64_t) + nbytes;
 
+    // EXPERIMENT (NK_ZEROCOPY=1): count whole tiles straight out of pinned, device-mapped host memory
+    // (the kernel's TMA bulk loads cross PCIe themselves; no staging copy), H2D only for the ragged end.
+    unsigned long long zc_body = 0;
+    if (getenv("NK_ZEROCOPY") && nbytes >= 4 * (unsigned long long)nk::COUNT_TILE && ((uintptr_t)bases & 15) == 0) {
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, bases) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
+            zc_body = (nbytes - nk::COUNT_HALO) / nk::COUNT_TILE * nk::COUNT_TILE;
+            NK_TRY(ensure_devbuf(h->staged, zc_body));
+            NK_CUDA(cudaEventRecord(h->buf[0].copy_done ? h->buf[0].copy_done : h->offsets_done[ob], h->copy_stream));
+            cudaEvent_t off_ready = h->buf[0].copy_done ? h->buf[0].copy_done : h->offsets_done[ob];
+            NK_CUDA(cudaStreamWaitEvent(h->stream, off_ready, 0));  // offsets are on the device
+            DevBuf view = h->staged;
+            view.bases = (unsigned char*)at.devicePointer;
+            NK_TRY(count_chunk(h, view, d_offsets, 0, nseq, 0, zc_body, zc_body, pe));
+        } else {
+            cudaGetLastError();
+        }
+    }
+
     // chunk plan: fixed 32 MiB granules.  Measured alternatives at 113 MB (end to end, B200, PCIe Gen5):
     // fixed 32 MiB 2.53 ms; geometric tail down to 2 MiB 2.68 ms; 3 x 36 MiB + 4 MiB tail 2.60 ms —
     // fewer, equal copies win over a shorter exposed tail.
-    for (unsigned long long c0 = 0, c1 = 0; c0 < nbytes; c0 = c1) {
+    for (unsigned long long c0 = zc_body, c1 = 0; c0 < nbytes; c0 = c1) {
         c1 = std::min(c0 + kChunkBytes, nbytes);
         const unsigned long long copy_len = std::min(c1 + nk::COUNT_HALO, nbytes) - c0;
         DevBuf& b = h->buf[h->cur_buf];
@@ -345,6 +364,7 @@ int count_host_batch(nk_counter* h, const uint8_t* bases, const uint64_t* offset
     // the caller's buffers must be reusable on return: wait for the copies (not the kernels).
     // The file driver owns its pinned batches and double-buffers them instead (wait_copies = false).
     if (wait_copies) NK_CUDA(cudaStreamSynchronize(h->copy_stream));
+    if (zc_body) NK_CUDA(cudaStreamSynchronize(h->stream));  // the kernel itself read the caller's buffer
     return NK_OK;
 }
 

@@ -12,6 +12,8 @@ followed by the top-20 read-out.  One "step" = one whole job on a freshly reset 
   e2e   : the same job through the public host API with HOST buffers: pinned bases ->
           nk_stream_push (chunked async H2D overlapped with the kernels) -> nk_stream_end ->
           nk_top_n (D2H of the result rows), wall clock around the call sequence
+  e2e_prepacked: e2e with the input handed over in the pre-packed form (2 bits per base +
+          `other` bits, nk_stream_push_packed): 3/8 of the bytes on PCIe; packing is untimed
   roofline     : the count kernel (windowing+SipHash+mod+RED) against the three limits the
                  north star names; denominators measured live by nk_calibrate + MEASURED_PEAKS.json
   cpu_baseline : the oracle port (oracle/nk_oracle.c, pthreads, all host cores) on a bounded
@@ -214,6 +216,19 @@ def gpu_arm(args):
     pinned = PinnedBuffer(NBASES if not args.no_e2e else 16)
     if not args.no_e2e:
         pinned.array[:] = device_to_numpy(dev_bases, NBASES)
+    # the same bytes in the pre-packed "nk2" form (2-bit codes + `other` bits) for the e2e_prepacked leg
+    pk_codes = pk_other = None
+    pack_ms = None
+    if not args.no_e2e:
+        from neurokmer_b200 import pack_bases
+        pk_codes = PinnedBuffer(4 * ((NBASES + 15) // 16), np.uint32)
+        pk_other = PinnedBuffer(4 * ((NBASES + 31) // 32), np.uint32)
+        best = 1e9
+        for _ in range(5):
+            t0 = time.perf_counter()
+            _, _, n_other = pack_bases(pinned.array, threads=0, out_codes=pk_codes.array, out_other=pk_other.array)
+            best = min(best, time.perf_counter() - t0)
+        pack_ms = best * 1e3
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
     cur_view = {}
@@ -291,6 +306,16 @@ def gpu_arm(args):
             c.stream_finish()
         return c.top_abundant_neurons(TOPN)
 
+    def job_e2e_packed():
+        c.reset()
+        c.stream_begin()
+        c.stream_push_packed(pk_codes.array, pk_other.array, offsets)
+        if world > 1:
+            finish_distributed()
+        else:
+            c.stream_finish()
+        return c.top_abundant_neurons(TOPN)
+
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
@@ -307,7 +332,7 @@ def gpu_arm(args):
                 flush.fill_(1)  # evict the input and the pool from L2 (untimed)
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(stream)
-            if job is job_e2e:
+            if job is not job_resident:
                 stream.synchronize()  # wall clock must not include the flush
             t0 = time.perf_counter()
             top = job()
@@ -338,6 +363,11 @@ def gpu_arm(args):
     else:
         timed(job_e2e, 2)
         steps_e2e, phases_e2e, top_e2e, _ = timed(job_e2e, args.steps)
+    steps_pk = None
+    if not args.no_e2e:
+        timed(job_e2e_packed, 2)
+        steps_pk, phases_pk, top_pk, _ = timed(job_e2e_packed, args.steps)
+        assert top == top_pk, "pre-packed and ASCII legs disagree"
     clocks = sampler.stop() if sampler else None
     assert top == top_e2e, "resident and end-to-end legs disagree"
 
@@ -348,10 +378,11 @@ def gpu_arm(args):
     total_spikes = c.energy.total_spikes()
     dev_ms = float(sum(s[0] for s in steps_res))
     e2e_ms = float(sum(s[1] for s in steps_e2e))
-    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device="cuda")
+    pk_ms = float(sum(s[1] for s in steps_pk)) if steps_pk else float("nan")
+    t = torch.tensor([dev_ms, e2e_ms, pk_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    dev_ms, e2e_ms, pk_ms = float(t[0]), float(t[1]), float(t[2])
     total_kmers = KMERS * world * args.steps
     value = total_kmers / (dev_ms * 1e-3)
     e2e_value = total_kmers / (e2e_ms * 1e-3)
@@ -411,6 +442,14 @@ def gpu_arm(args):
             "e2e": {"value": e2e_value, "unit": "kmers/s", "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": int(phases_e2e[-1]["h2d_bytes"]),
                     "d2h_bytes_per_step": int(phases_e2e[-1]["d2h_bytes"] + 24 + 16 * TOPN)},
+            # same job, same API, input handed over in the library's pre-packed form (2-bit codes + `other`
+            # bits in pinned host memory: nk_stream_push_packed).  The packing itself (nk_pack_bases, host
+            # SIMD, all cores) is NOT in this timed region — its cost is reported beside it.
+            "e2e_prepacked": None if not steps_pk else {
+                "value": total_kmers / (pk_ms * 1e-3), "unit": "kmers/s", "ms_per_step": pk_ms / args.steps,
+                "h2d_bytes_per_step": int(phases_pk[-1]["h2d_bytes"]),
+                "d2h_bytes_per_step": int(phases_pk[-1]["d2h_bytes"] + 24 + 16 * TOPN),
+                "host_pack_ms_untimed": pack_ms, "host_pack_threads": os.cpu_count()},
             "gpu_launches": launches * args.steps,
             "phases_ms": ph, "collective_ms": ar_ms,
             "collective": ("none" if world == 1 else ("barrier + all-gather of result packs (NCCL); count reduce-scatter fused into the LIF "

@@ -127,6 +127,31 @@ NK_API int nk_stream_begin(nk_counter* h);
 NK_API int nk_stream_push(nk_counter* h, const uint8_t* bases, const uint64_t* offsets, uint64_t nseq);
 NK_API int nk_stream_end(nk_counter* h);
 
+/* ---- pre-packed input (2 bits per base) -------------------------------------
+ * The north star's "ASCII or pre-packed bases": callers that already hold 2-bit data (or pack it
+ * once with nk_pack_bases and count it many times) move 3/8 of the bytes over PCIe and skip the
+ * kernel's byte classifier.  Results are bit-identical to the ASCII entry points on the bytes the
+ * packed form was made from (tests/test_parity_gpu.py::test_packed_*).  Layout ("nk2"), for the
+ * concatenated batch of nbases = offsets[nseq] bases (sequences are NOT word-aligned):
+ *   codes[i], i < nk_packed_code_words(nbases):  bases 16i .. 16i+15, base 16i in bits 31:30;
+ *       A,a=0 C,c=1 G,g=2 T,t=3 (base_to_bits, src/models.rs:231-239), anything else 0;
+ *   other[w], w < nk_packed_other_words(nbases): bit (p & 31) of word p >> 5 set iff byte p was not
+ *       one of ACGTacgt: code 0 on BOTH strands in canonical mode (src/models.rs:237,249), skipped by
+ *       pack_kmer (src/utils.rs:35).  NULL = no such byte in the batch (no array is read or copied).
+ * Unused bits of the last words must be present (readable) but are ignored. */
+NK_API uint64_t nk_packed_code_words(uint64_t nbases);
+NK_API uint64_t nk_packed_other_words(uint64_t nbases);
+/* Host-side packer (SIMD, `threads` host threads; <= 0: all).  *n_other = bytes that were not ACGTacgt
+ * (0 => `other` may be passed as NULL below).  `other` may be NULL if the caller does not want it. */
+NK_API int nk_pack_bases(const uint8_t* bases, uint64_t nbases, uint32_t* codes, uint32_t* other, int threads,
+                         uint64_t* n_other);
+/* process_parallel (src/spiking_hash.rs:84-201) / the push of process_file_streaming (:277-486) on
+ * pre-packed input; same semantics, state rules and asynchrony as nk_process_batch / nk_stream_push. */
+NK_API int nk_process_batch_packed(nk_counter* h, const uint32_t* codes, const uint32_t* other,
+                                   const uint64_t* offsets, uint64_t nseq);
+NK_API int nk_stream_push_packed(nk_counter* h, const uint32_t* codes, const uint32_t* other,
+                                 const uint64_t* offsets, uint64_t nseq);
+
 /* Whole-file drivers: main.rs:170-177.  streaming != 0 → process_file_streaming
  * (:277), else stream_sequences().collect() + process_parallel (main.rs:175-176).
  * FASTA/FASTQ record rules follow src/utils.rs:9-24. */
@@ -172,6 +197,13 @@ NK_API int nk_copy_uniques(nk_counter* h, uint32_t* out /* pool_size */);
  * in canonical mode (RollingKmerHash::forward/reverse_complement). */
 NK_API int nk_debug_kmers(nk_counter* h, const uint8_t* seq, uint64_t len, uint64_t* fwd, uint64_t* rc,
                           uint64_t* words, uint64_t* idx, uint64_t* n_out);
+/* the same taps for one sequence in pre-packed form */
+NK_API int nk_debug_kmers_packed(nk_counter* h, const uint32_t* codes, const uint32_t* other, uint64_t len,
+                                 uint64_t* fwd, uint64_t* rc, uint64_t* words, uint64_t* idx, uint64_t* n_out);
+/* nk_pack_bases with one named body on one thread: 1 portable, 2 AVX2, 3 AVX-512BW
+ * (NK_ERR_UNSUPPORTED if this CPU lacks it) — the CPU tests compare every body with a numpy twin. */
+NK_API int nk_debug_pack_body(const uint8_t* bases, uint64_t nbases, uint32_t* codes, uint32_t* other, int body,
+                              uint64_t* n_other);
 /* SipHash-1-3(keys 0,0) of LE64(word) and word-hash % pool_size for a host array. */
 NK_API int nk_debug_hash(nk_counter* h, const uint64_t* words, uint64_t n, uint64_t* hashes, uint64_t* idx);
 /* values[i] % pool_size on the device for ANY pool_size in [1, 2^32) without allocating a pool:
@@ -203,6 +235,11 @@ NK_API int nk_stage_reserve(nk_counter* h, uint64_t nbytes, uint64_t nseq, void*
 /* Count the staged batch.  mode 0: process_parallel semantics (count, overwrite
  * currents, in-memory LIF); mode 1: accumulate only (inside stream_begin/end). */
 NK_API int nk_process_staged(nk_counter* h, uint64_t nbytes, uint64_t nseq, int mode);
+/* The same for pre-packed input: *dev_codes holds nk_packed_code_words(nbases) u32 (+ padding),
+ * *dev_other nk_packed_other_words(nbases) u32 (+ padding); has_other = 0 ignores the `other` array. */
+NK_API int nk_stage_reserve_packed(nk_counter* h, uint64_t nbases, uint64_t nseq, void** dev_codes, void** dev_other,
+                                   void** dev_offsets);
+NK_API int nk_process_staged_packed(nk_counter* h, uint64_t nbases, uint64_t nseq, int mode, int has_other);
 /* Sharded (one process per GPU) runs: every rank accumulates its shard between
  * nk_stream_begin and nk_stream_accumulated, sum-reduces the u64 array at
  * *dev_currents (pool_size elements) across ranks with its own collective

@@ -27,6 +27,9 @@ SYMBOLS = [
     "nk_stream_finish", "nk_dist_export", "nk_dist_setup", "nk_dist_post", "nk_dist_complete", "nk_dist_slice",
     "nk_cuda_stream", "nk_synchronize", "nk_synth_fill", "nk_host_alloc",
     "nk_host_free", "nk_pack_kmer",
+    "nk_packed_code_words", "nk_packed_other_words", "nk_pack_bases", "nk_process_batch_packed",
+    "nk_stream_push_packed", "nk_debug_kmers_packed", "nk_debug_pack_body", "nk_stage_reserve_packed",
+    "nk_process_staged_packed",
 ]
 
 
@@ -117,6 +120,15 @@ def load() -> C.CDLL:
         "nk_host_alloc": (i32, [P(vp), u64]),
         "nk_host_free": (i32, [vp]),
         "nk_pack_kmer": (u64, [vp, u64]),
+        "nk_packed_code_words": (u64, [u64]),
+        "nk_packed_other_words": (u64, [u64]),
+        "nk_pack_bases": (i32, [vp, u64, vp, vp, i32, P(u64)]),
+        "nk_process_batch_packed": (i32, [vp, vp, vp, vp, u64]),
+        "nk_stream_push_packed": (i32, [vp, vp, vp, vp, u64]),
+        "nk_debug_kmers_packed": (i32, [vp, vp, vp, u64, vp, vp, vp, vp, P(u64)]),
+        "nk_debug_pack_body": (i32, [vp, u64, vp, vp, i32, P(u64)]),
+        "nk_stage_reserve_packed": (i32, [vp, u64, u64, P(vp), P(vp), P(vp)]),
+        "nk_process_staged_packed": (i32, [vp, u64, u64, i32, i32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError if the .so lacks a declared symbol

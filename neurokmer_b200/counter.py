@@ -35,6 +35,24 @@ def _ptr(a: Optional[np.ndarray]) -> Optional[int]:
     return None if a is None or a.size == 0 else a.ctypes.data
 
 
+def pack_bases(bases: BytesLike, threads: int = 0, body: int = 0, out_codes: Optional[np.ndarray] = None,
+               out_other: Optional[np.ndarray] = None) -> Tuple[np.ndarray, np.ndarray, int]:
+    """ASCII bases -> the pre-packed "nk2" form (include/neurokmer.h): (codes u32, other u32, n_other).
+    Done by the library's SIMD host packer (nk_pack_bases); `body` 1..3 names one of its bodies."""
+    a = np.frombuffer(bases, np.uint8) if not isinstance(bases, np.ndarray) else np.ascontiguousarray(bases, np.uint8)
+    L = _lib.lib()
+    nc, no = int(L.nk_packed_code_words(a.size)), int(L.nk_packed_other_words(a.size))
+    codes = out_codes if out_codes is not None else np.zeros(max(nc, 1), np.uint32)
+    other = out_other if out_other is not None else np.zeros(max(no, 1), np.uint32)
+    assert codes.dtype == np.uint32 and other.dtype == np.uint32 and codes.size >= nc and other.size >= no
+    n_other = C.c_uint64()
+    if body:
+        check(L.nk_debug_pack_body(_ptr(a), a.size, codes.ctypes.data, other.ctypes.data, body, C.byref(n_other)))
+    else:
+        check(L.nk_pack_bases(_ptr(a), a.size, codes.ctypes.data, other.ctypes.data, threads, C.byref(n_other)))
+    return codes[:max(nc, 1)], other[:max(no, 1)], int(n_other.value)
+
+
 class PinnedBuffer:
     """Page-locked host memory from the library (nk_host_alloc) viewed as a numpy array."""
 
@@ -140,6 +158,21 @@ class SpikingKmerCounter:
     def stream_end(self) -> None:
         check(self._L.nk_stream_end(self._h))
 
+    # pre-packed input (2 bits per base; include/neurokmer.h "nk2" layout) -------------------
+    def process_batch_packed(self, codes: np.ndarray, other: Optional[np.ndarray], offsets: np.ndarray) -> None:
+        codes = np.ascontiguousarray(codes, np.uint32)
+        other = None if other is None else np.ascontiguousarray(other, np.uint32)
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        check(self._L.nk_process_batch_packed(self._h, codes.ctypes.data, None if other is None else other.ctypes.data,
+                                              offsets.ctypes.data, offsets.size - 1))
+
+    def stream_push_packed(self, codes: np.ndarray, other: Optional[np.ndarray], offsets: np.ndarray) -> None:
+        codes = np.ascontiguousarray(codes, np.uint32)
+        other = None if other is None else np.ascontiguousarray(other, np.uint32)
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        check(self._L.nk_stream_push_packed(self._h, codes.ctypes.data, None if other is None else other.ctypes.data,
+                                            offsets.ctypes.data, offsets.size - 1))
+
     def simulate_spikes_auto(self) -> None:
         """src/spiking_hash.rs:697-714"""
         check(self._L.nk_simulate(self._h))
@@ -201,6 +234,18 @@ class SpikingKmerCounter:
         m = got.value
         return fwd[:m], rc[:m], words[:m], idx[:m]
 
+    def debug_kmers_packed(self, codes: np.ndarray, other: Optional[np.ndarray], length: int):
+        codes = np.ascontiguousarray(codes, np.uint32)
+        other = None if other is None else np.ascontiguousarray(other, np.uint32)
+        n = max(0, length - self.k + 1)
+        fwd, rc, words, idx = (np.zeros(max(n, 1), np.uint64) for _ in range(4))
+        got = C.c_uint64()
+        check(self._L.nk_debug_kmers_packed(self._h, codes.ctypes.data, None if other is None else other.ctypes.data,
+                                            length, fwd.ctypes.data, rc.ctypes.data, words.ctypes.data,
+                                            idx.ctypes.data, C.byref(got)))
+        m = got.value
+        return fwd[:m], rc[:m], words[:m], idx[:m]
+
     def debug_hash(self, words: np.ndarray):
         w = np.ascontiguousarray(words, np.uint64)
         hs, ix = np.zeros(max(w.size, 1), np.uint64), np.zeros(max(w.size, 1), np.uint64)
@@ -245,6 +290,14 @@ class SpikingKmerCounter:
 
     def process_staged(self, nbytes: int, nseq: int, mode: int = 0) -> None:
         check(self._L.nk_process_staged(self._h, nbytes, nseq, mode))
+
+    def stage_reserve_packed(self, nbases: int, nseq: int) -> Tuple[int, int, int]:
+        c, x, o = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        check(self._L.nk_stage_reserve_packed(self._h, nbases, nseq, C.byref(c), C.byref(x), C.byref(o)))
+        return c.value, x.value, o.value
+
+    def process_staged_packed(self, nbases: int, nseq: int, mode: int = 0, has_other: bool = True) -> None:
+        check(self._L.nk_process_staged_packed(self._h, nbases, nseq, mode, int(has_other)))
 
     def synth_fill(self, dev_ptr: int, seed: int, start: int, n: int, flags: int = 0) -> None:
         check(self._L.nk_synth_fill(self._h, dev_ptr, seed, start, n, flags))

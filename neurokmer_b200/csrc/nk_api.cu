@@ -62,6 +62,12 @@ struct DevBuf {
     unsigned int* invalid = nullptr;
     unsigned long long invalid_cap = 0;  // words
     cudaEvent_t copy_done = nullptr, compute_done = nullptr;
+    // pre-packed input (nk_*_packed): 2-bit code words and `other` bits of the chunk
+    unsigned char* codes = nullptr;
+    unsigned long long codes_cap = 0;
+    unsigned char* other = nullptr;
+    unsigned long long other_cap = 0;
+    bool has_other = false;  // this chunk's `other` array was supplied
 };
 
 struct PhaseEvents {
@@ -191,6 +197,37 @@ int ensure_devbuf(DevBuf& b, unsigned long long nbytes) {
     return NK_OK;
 }
 
+// device arrays of a pre-packed chunk of `nbytes` window starts (+ the invalid-start bitmap and events)
+int ensure_devbuf_packed(DevBuf& b, unsigned long long nbytes, bool want_other) {
+    const unsigned long long need_c = nk::count_padded_codes(nbytes);
+    if (need_c > b.codes_cap) {
+        if (b.codes) cudaFree(b.codes);
+        b.codes = nullptr;
+        b.codes_cap = 0;
+        NK_CUDA(cudaMalloc(&b.codes, need_c));
+        b.codes_cap = need_c;
+    }
+    const unsigned long long need_o = nk::count_padded_other(nbytes);
+    if (want_other && need_o > b.other_cap) {
+        if (b.other) cudaFree(b.other);
+        b.other = nullptr;
+        b.other_cap = 0;
+        NK_CUDA(cudaMalloc(&b.other, need_o));
+        b.other_cap = need_o;
+    }
+    const unsigned long long words = nk::count_bitmap_words(nbytes);
+    if (words > b.invalid_cap) {
+        if (b.invalid) cudaFree(b.invalid);
+        b.invalid = nullptr;
+        b.invalid_cap = 0;
+        NK_CUDA(cudaMalloc(&b.invalid, words * sizeof(unsigned int)));
+        b.invalid_cap = words;
+    }
+    if (!b.copy_done) NK_CUDA(cudaEventCreateWithFlags(&b.copy_done, cudaEventDisableTiming));
+    if (!b.compute_done) NK_CUDA(cudaEventCreateWithFlags(&b.compute_done, cudaEventDisableTiming));
+    return NK_OK;
+}
+
 int ensure_offsets(unsigned long long** p, unsigned long long* cap, unsigned long long n) {
     if (n > *cap) {
         if (*p) cudaFree(*p);
@@ -233,7 +270,7 @@ int prelaunch_table(nk_counter* h);
 
 int count_chunk(nk_counter* h, DevBuf& b, const unsigned long long* d_offsets, unsigned long long seq_lo,
                 unsigned long long seq_hi, unsigned long long origin, unsigned long long nstarts,
-                unsigned long long max_windows, PhaseEvents* pe) {
+                unsigned long long max_windows, PhaseEvents* pe, bool packed = false) {
     if (nstarts == 0) return NK_OK;
     if (h->acc_kmers + max_windows > 0xFFFFFFFFull) NK_TRY(fold_now(h));
     cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
@@ -251,7 +288,9 @@ int count_chunk(nk_counter* h, DevBuf& b, const unsigned long long* d_offsets, u
                                     h->scalars + 2, h->stream, &h->last.launches));
     if (pe) NK_CUDA(cudaEventRecord(e1, h->stream));
     nk::CountParams p{};
-    p.bases = b.bases;
+    p.bases = packed ? b.codes : b.bases;
+    p.other = packed && b.has_other ? b.other : nullptr;
+    p.packed = packed ? 1 : 0;
     p.invalid = b.invalid;
     p.acc = h->acc;
     p.tile_counter = h->tile_counter;
@@ -365,6 +404,77 @@ int count_host_batch(nk_counter* h, const uint8_t* bases, const uint64_t* offset
     // The file driver owns its pinned batches and double-buffers them instead (wait_copies = false).
     if (wait_copies) NK_CUDA(cudaStreamSynchronize(h->copy_stream));
     if (zc_body) NK_CUDA(cudaStreamSynchronize(h->stream));  // the kernel itself read the caller's buffer
+    return NK_OK;
+}
+
+// pre-packed host batch -> chunked H2D of the code words (and `other` bits) overlapped with mark+count.
+// Same pipeline as count_host_batch with 1/4 (+1/8) of the bytes on PCIe.
+unsigned long long packed_chunk_bases() {
+    unsigned long long mb = 16;  // measured on B200 / PCIe Gen5: see profiles/r01_bench.md
+    if (const char* e = getenv("NK_PACKED_CHUNK_MBASES")) {
+        const unsigned long long t = strtoull(e, nullptr, 10);
+        if (t >= 1 && t <= 1024) mb = t;
+    }
+    return mb << 20;  // multiple of COUNT_TILE, of 16 (code words) and of 32 (`other` words)
+}
+
+int count_host_batch_packed(nk_counter* h, const uint32_t* codes, const uint32_t* other, const uint64_t* offsets,
+                            uint64_t nseq, PhaseEvents* pe, bool wait_copies = true) {
+    if (nseq == 0) return NK_OK;
+    for (uint64_t s = 0; s < nseq; ++s)
+        if (offsets[s + 1] < offsets[s]) return fail(NK_ERR_BAD_ARG, "offsets must be non-decreasing (at %llu)", (unsigned long long)s);
+    const unsigned long long nbases = offsets[nseq];
+    if (nbases == 0) return NK_OK;
+    if (!codes) return fail(NK_ERR_BAD_ARG, "null codes");
+    const int ob = h->cur_off;
+    h->cur_off ^= 1;
+    if (h->offsets_done[ob]) {
+        NK_CUDA(cudaStreamWaitEvent(h->copy_stream, h->offsets_done[ob], 0));
+        if (nseq + 1 > h->offsets_cap2[ob]) NK_CUDA(cudaEventSynchronize(h->offsets_done[ob]));
+    } else {
+        NK_CUDA(cudaEventCreateWithFlags(&h->offsets_done[ob], cudaEventDisableTiming));
+    }
+    NK_TRY(ensure_offsets(&h->d_offsets2[ob], &h->offsets_cap2[ob], nseq + 1));
+    unsigned long long* const d_offsets = h->d_offsets2[ob];
+    if (pe && !pe->copy0) { NK_TRY(get_event(h, &pe->copy0)); NK_CUDA(cudaEventRecord(pe->copy0, h->copy_stream)); }
+    NK_CUDA(cudaMemcpyAsync(d_offsets, offsets, (nseq + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, h->copy_stream));
+    h->last.h2d_bytes += (nseq + 1) * sizeof(uint64_t);
+
+    const unsigned long long chunk = packed_chunk_bases();
+    const unsigned char* const hc = reinterpret_cast<const unsigned char*>(codes);
+    const unsigned char* const ho = reinterpret_cast<const unsigned char*>(other);
+    for (unsigned long long c0 = 0, c1 = 0; c0 < nbases; c0 = c1) {
+        c1 = std::min(c0 + chunk, nbases);
+        // whole words of the host arrays, including the halo the tiles of this chunk read past c1
+        const unsigned long long code_bytes = (std::min(c1 + 64, nbases) - c0 + 15) / 16 * 4;
+        const unsigned long long other_bytes = (std::min(c1 + 128, nbases) - c0 + 31) / 32 * 4;
+        DevBuf& b = h->buf[h->cur_buf];
+        h->cur_buf ^= 1;
+        const bool had = b.compute_done != nullptr;
+        NK_TRY(ensure_devbuf_packed(b, std::min(chunk, nbases), other != nullptr));
+        if (had) NK_CUDA(cudaStreamWaitEvent(h->copy_stream, b.compute_done, 0));
+        NK_CUDA(cudaMemcpyAsync(b.codes, hc + c0 / 4, code_bytes, cudaMemcpyHostToDevice, h->copy_stream));
+        h->last.h2d_bytes += code_bytes;
+        b.has_other = other != nullptr;
+        if (other) {
+            NK_CUDA(cudaMemcpyAsync(b.other, ho + c0 / 8, other_bytes, cudaMemcpyHostToDevice, h->copy_stream));
+            h->last.h2d_bytes += other_bytes;
+        }
+        NK_CUDA(cudaEventRecord(b.copy_done, h->copy_stream));
+        NK_CUDA(cudaStreamWaitEvent(h->stream, b.copy_done, 0));
+        const uint64_t* first = std::upper_bound(offsets + 1, offsets + nseq + 1, (uint64_t)c0);
+        const unsigned long long seq_lo = (unsigned long long)(first - (offsets + 1));
+        const uint64_t* last = std::lower_bound(offsets, offsets + nseq, (uint64_t)c1);
+        const unsigned long long seq_hi = (unsigned long long)(last - offsets);
+        NK_TRY(count_chunk(h, b, d_offsets, seq_lo, seq_hi, c0, c1 - c0, c1 - c0, pe, true));
+        NK_CUDA(cudaEventRecord(b.compute_done, h->stream));
+    }
+    NK_CUDA(cudaEventRecord(h->offsets_done[ob], h->stream));
+    if (pe) {
+        if (!pe->copy1) NK_TRY(get_event(h, &pe->copy1));
+        NK_CUDA(cudaEventRecord(pe->copy1, h->copy_stream));
+    }
+    if (wait_copies) NK_CUDA(cudaStreamSynchronize(h->copy_stream));
     return NK_OK;
 }
 
@@ -590,6 +700,8 @@ void begin_call(nk_counter* h) {
 
 int free_devbuf(DevBuf& b) {
     if (b.bases) cudaFree(b.bases);
+    if (b.codes) cudaFree(b.codes);
+    if (b.other) cudaFree(b.other);
     if (b.invalid) cudaFree(b.invalid);
     if (b.copy_done) cudaEventDestroy(b.copy_done);
     if (b.compute_done) cudaEventDestroy(b.compute_done);
@@ -1200,6 +1312,62 @@ int nk_stream_push(nk_counter* h, const uint8_t* bases, const uint64_t* offsets,
     return count_host_batch(h, bases, offsets, nseq, &h->stream_pe);
 }
 
+// ---- pre-packed input ("nk2" layout, include/neurokmer.h) ------------------------------------------
+static int validate_packed(const nk_counter* h, const uint32_t* codes, const uint64_t* offsets, uint64_t nseq) {
+    if (!h) return fail(NK_ERR_BAD_ARG, "null handle");
+    if (nseq > 0 && !offsets) return fail(NK_ERR_BAD_ARG, "null offsets");
+    if (nseq == 0) return NK_OK;
+    if (offsets[0] != 0) return fail(NK_ERR_BAD_ARG, "offsets[0] must be 0");
+    if (offsets[nseq] > 0 && !codes) return fail(NK_ERR_BAD_ARG, "null codes");
+    return NK_OK;
+}
+
+uint64_t nk_packed_code_words(uint64_t nbases) { return (nbases + 15) / 16; }
+uint64_t nk_packed_other_words(uint64_t nbases) { return (nbases + 31) / 32; }
+
+int nk_pack_bases(const uint8_t* bases, uint64_t nbases, uint32_t* codes, uint32_t* other, int threads, uint64_t* n_other) {
+    if (nbases > 0 && (!bases || !codes)) return fail(NK_ERR_BAD_ARG, "null argument");
+    const uint64_t n = nk::host_pack_bases(bases, nbases, codes, other, threads, 0);
+    if (n_other) *n_other = n;
+    return NK_OK;
+}
+
+int nk_debug_pack_body(const uint8_t* bases, uint64_t nbases, uint32_t* codes, uint32_t* other, int body, uint64_t* n_other) {
+    if (body < 1 || body > 3) return fail(NK_ERR_BAD_ARG, "body must be 1 (portable), 2 (AVX2) or 3 (AVX-512BW)");
+    if (!nk::host_pack_body_available(body)) return fail(NK_ERR_UNSUPPORTED, "this CPU lacks the instruction set of body %d", body);
+    if (nbases > 0 && (!bases || !codes)) return fail(NK_ERR_BAD_ARG, "null argument");
+    const uint64_t n = nk::host_pack_bases(bases, nbases, codes, other, 1, body);
+    if (n_other) *n_other = n;
+    return NK_OK;
+}
+
+int nk_process_batch_packed(nk_counter* h, const uint32_t* codes, const uint32_t* other, const uint64_t* offsets,
+                            uint64_t nseq) {
+    NK_TRY(validate_packed(h, codes, offsets, nseq));
+    if (h->streaming) return fail(NK_ERR_STATE, "nk_process_batch_packed inside nk_stream_begin/end");
+    NK_CUDA(cudaSetDevice(h->cfg.device));
+    begin_call(h);
+    PhaseEvents pe;
+    NK_TRY(get_event(h, &pe.begin));
+    NK_CUDA(cudaEventRecord(pe.begin, h->stream));
+    NK_CUDA(cudaMemsetAsync(h->scalars + 2, 0, sizeof(unsigned long long), h->stream));
+    h->currents_valid_overwrite = true;
+    NK_TRY(count_host_batch_packed(h, codes, other, offsets, nseq, &pe));
+    NK_TRY(fold_and_simulate(h, /*skip_zero=*/true, pe));
+    NK_TRY(get_event(h, &pe.end));
+    NK_CUDA(cudaEventRecord(pe.end, h->stream));
+    NK_TRY(finish_call(h, true, &pe));
+    return NK_OK;
+}
+
+int nk_stream_push_packed(nk_counter* h, const uint32_t* codes, const uint32_t* other, const uint64_t* offsets,
+                          uint64_t nseq) {
+    NK_TRY(validate_packed(h, codes, offsets, nseq));
+    if (!h->streaming) return fail(NK_ERR_STATE, "nk_stream_push_packed without nk_stream_begin");
+    NK_CUDA(cudaSetDevice(h->cfg.device));
+    return count_host_batch_packed(h, codes, other, offsets, nseq, &h->stream_pe);
+}
+
 int nk_stream_accumulated(nk_counter* h, void** dev_currents) {
     if (!h) return fail(NK_ERR_BAD_ARG, "null handle");
     if (!h->streaming) return fail(NK_ERR_STATE, "nk_stream_accumulated without nk_stream_begin");
@@ -1423,17 +1591,20 @@ int nk_copy_uniques(nk_counter* h, uint32_t* out) {
     return NK_OK;
 }
 
-int nk_debug_kmers(nk_counter* h, const uint8_t* seq, uint64_t len, uint64_t* fwd, uint64_t* rc, uint64_t* words,
-                   uint64_t* idx, uint64_t* n_out) {
+// seq != null: ASCII input; else the pre-packed form (codes, other)
+static int debug_kmers_any(nk_counter* h, const uint8_t* seq, const uint32_t* codes, const uint32_t* other, uint64_t len,
+                           uint64_t* fwd, uint64_t* rc, uint64_t* words, uint64_t* idx, uint64_t* n_out) {
     if (!h || !n_out) return fail(NK_ERR_BAD_ARG, "null argument");
     NK_CUDA(cudaSetDevice(h->cfg.device));
     *n_out = 0;
     if (len < h->cfg.k) return NK_OK;
-    if (!seq) return fail(NK_ERR_BAD_ARG, "null seq");
+    if (!seq && !codes) return fail(NK_ERR_BAD_ARG, "null sequence pointer");
+    const bool packed = seq == nullptr;
     NK_TRY(resolve(h));
     const uint64_t n = len - h->cfg.k + 1;
     NK_CUDA(cudaStreamSynchronize(h->stream));
-    NK_TRY(ensure_devbuf(h->staged, len));
+    if (packed) NK_TRY(ensure_devbuf_packed(h->staged, len, true));
+    else NK_TRY(ensure_devbuf(h->staged, len));
     NK_TRY(ensure_offsets(&h->staged_offsets, &h->staged_offsets_cap, 2));
     const uint64_t offs[2] = {0, len};
     unsigned long long* d_out = nullptr;
@@ -1441,14 +1612,22 @@ int nk_debug_kmers(nk_counter* h, const uint8_t* seq, uint64_t len, uint64_t* fw
     int rc_ = NK_OK;
     do {
 #define NK_D(expr) { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { rc_ = fail(NK_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); break; } }
-        NK_D(cudaMemcpyAsync(h->staged.bases, seq, len, cudaMemcpyHostToDevice, h->stream));
+        if (packed) {
+            NK_D(cudaMemcpyAsync(h->staged.codes, codes, (len + 15) / 16 * 4, cudaMemcpyHostToDevice, h->stream));
+            if (other) NK_D(cudaMemcpyAsync(h->staged.other, other, (len + 31) / 32 * 4, cudaMemcpyHostToDevice, h->stream));
+        } else {
+            NK_D(cudaMemcpyAsync(h->staged.bases, seq, len, cudaMemcpyHostToDevice, h->stream));
+        }
         NK_D(cudaMemcpyAsync(h->staged_offsets, offs, sizeof offs, cudaMemcpyHostToDevice, h->stream));
         NK_D(cudaStreamSynchronize(h->stream));  // offs is on this stack frame
         NK_D(cudaMemsetAsync(h->tile_counter, 0, sizeof(unsigned int), h->stream));
         NK_D(nk::launch_mark_invalid(h->staged.invalid, h->staged_offsets, 0, 1, 0, len, h->cfg.k, h->scalars + 3,
                                      h->stream, nullptr));
         nk::CountParams p{};
-        p.bases = h->staged.bases; p.invalid = h->staged.invalid; p.acc = h->acc; p.tile_counter = h->tile_counter;
+        p.bases = packed ? h->staged.codes : h->staged.bases;
+        p.other = packed && other ? h->staged.other : nullptr;
+        p.packed = packed ? 1 : 0;
+        p.invalid = h->staged.invalid; p.acc = h->acc; p.tile_counter = h->tile_counter;
         p.ntiles = nk::count_ntiles(len); p.fm = h->fm; p.rm = nk::make_rotmul(); p.k = h->cfg.k;
         p.out_fwd = fwd ? d_out : nullptr;
         p.out_rc = rc ? d_out + n : nullptr;
@@ -1465,6 +1644,16 @@ int nk_debug_kmers(nk_counter* h, const uint8_t* seq, uint64_t len, uint64_t* fw
     cudaFree(d_out);
     if (rc_ == NK_OK) *n_out = n;
     return rc_;
+}
+
+int nk_debug_kmers(nk_counter* h, const uint8_t* seq, uint64_t len, uint64_t* fwd, uint64_t* rc, uint64_t* words,
+                   uint64_t* idx, uint64_t* n_out) {
+    return debug_kmers_any(h, seq, nullptr, nullptr, len, fwd, rc, words, idx, n_out);
+}
+
+int nk_debug_kmers_packed(nk_counter* h, const uint32_t* codes, const uint32_t* other, uint64_t len, uint64_t* fwd,
+                          uint64_t* rc, uint64_t* words, uint64_t* idx, uint64_t* n_out) {
+    return debug_kmers_any(h, nullptr, codes, other, len, fwd, rc, words, idx, n_out);
 }
 
 int nk_debug_hash(nk_counter* h, const uint64_t* words, uint64_t n, uint64_t* hashes, uint64_t* idx) {
@@ -1772,6 +1961,59 @@ int nk_process_staged(nk_counter* h, uint64_t nbytes, uint64_t nseq, int mode) {
         NK_TRY(finish_call(h, true, &pe));
     } else {
         // the mark/count event pairs of this push are collected with the stream's final read-back
+        h->stream_pe.mark0.insert(h->stream_pe.mark0.end(), pe.mark0.begin(), pe.mark0.end());
+        h->stream_pe.count0.insert(h->stream_pe.count0.end(), pe.count0.begin(), pe.count0.end());
+        h->stream_pe.count1.insert(h->stream_pe.count1.end(), pe.count1.begin(), pe.count1.end());
+    }
+    return NK_OK;
+}
+
+int nk_stage_reserve_packed(nk_counter* h, uint64_t nbases, uint64_t nseq, void** dev_codes, void** dev_other,
+                            void** dev_offsets) {
+    if (!h) return fail(NK_ERR_BAD_ARG, "null handle");
+    NK_CUDA(cudaSetDevice(h->cfg.device));
+    NK_TRY(resolve(h));
+    NK_CUDA(cudaStreamSynchronize(h->stream));
+    NK_TRY(ensure_devbuf_packed(h->staged, nbases, true));
+    NK_TRY(ensure_offsets(&h->staged_offsets, &h->staged_offsets_cap, nseq + 1));
+    if (dev_codes) *dev_codes = h->staged.codes;
+    if (dev_other) *dev_other = h->staged.other;
+    if (dev_offsets) *dev_offsets = h->staged_offsets;
+    return NK_OK;
+}
+
+int nk_process_staged_packed(nk_counter* h, uint64_t nbases, uint64_t nseq, int mode, int has_other) {
+    if (!h) return fail(NK_ERR_BAD_ARG, "null handle");
+    if (mode != 0 && mode != 1) return fail(NK_ERR_BAD_ARG, "mode must be 0 or 1");
+    if (mode == 1 && !h->streaming) return fail(NK_ERR_STATE, "mode 1 needs nk_stream_begin");
+    if (mode == 0 && h->streaming) return fail(NK_ERR_STATE, "mode 0 inside nk_stream_begin/end");
+    if (nk::count_padded_codes(nbases) > h->staged.codes_cap || nk::count_padded_other(nbases) > h->staged.other_cap ||
+        nseq + 1 > h->staged_offsets_cap)
+        return fail(NK_ERR_STATE, "staged batch larger than the last nk_stage_reserve_packed");
+    NK_CUDA(cudaSetDevice(h->cfg.device));
+    PhaseEvents pe;
+    if (mode == 0) {
+        begin_call(h);
+        NK_TRY(get_event(h, &pe.begin));
+        NK_CUDA(cudaEventRecord(pe.begin, h->stream));
+        NK_CUDA(cudaMemsetAsync(h->scalars + 2, 0, sizeof(unsigned long long), h->stream));
+        h->currents_valid_overwrite = true;
+    }
+    const unsigned long long slice = (0xFFFFFFFFull / nk::COUNT_TILE - 1) * nk::COUNT_TILE;
+    for (unsigned long long c0 = 0; c0 < nbases && nseq > 0; c0 += slice) {
+        const unsigned long long n = std::min(slice, nbases - c0);
+        DevBuf view = h->staged;
+        view.codes = h->staged.codes + c0 / 4;
+        view.other = h->staged.other + c0 / 8;
+        view.has_other = has_other != 0;
+        NK_TRY(count_chunk(h, view, h->staged_offsets, 0, nseq, c0, n, n, &pe, true));
+    }
+    if (mode == 0) {
+        NK_TRY(fold_and_simulate(h, /*skip_zero=*/true, pe));
+        NK_TRY(get_event(h, &pe.end));
+        NK_CUDA(cudaEventRecord(pe.end, h->stream));
+        NK_TRY(finish_call(h, true, &pe));
+    } else {
         h->stream_pe.mark0.insert(h->stream_pe.mark0.end(), pe.mark0.begin(), pe.mark0.end());
         h->stream_pe.count0.insert(h->stream_pe.count0.end(), pe.count0.begin(), pe.count0.end());
         h->stream_pe.count1.insert(h->stream_pe.count1.end(), pe.count1.begin(), pe.count1.end());

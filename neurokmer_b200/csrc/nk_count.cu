@@ -32,6 +32,11 @@ constexpr int kStageStride = ((kBytesPerStage + kBitsPerStage + 127) / 128) * 12
 constexpr int kSmemTotal = COUNT_STAGES * kStageStride;
 constexpr int kCompactBytes = COUNT_WARPS * COUNT_CHUNK * 8;  // MODE 3: one 512-word buffer per warp
 
+// pre-packed input: 2-bit codes (+ 64 bases of halo) and `other` bits (+ 128 bases of halo) per stage
+constexpr int kPkCodes = COUNT_TILE / 4 + 16;
+constexpr int kPkOther = COUNT_TILE / 8 + 16;
+static_assert(kPkCodes + kPkOther + kBitsPerStage <= kStageStride, "a packed stage fits an ASCII stage");
+
 static_assert(kBytesPerStage % 16 == 0 && kBitsPerStage % 16 == 0, "TMA bulk copies are 16-byte granular");
 static_assert(COUNT_HALO == 32, "the last warp converts exactly two 16-byte halo words");
 
@@ -54,12 +59,34 @@ __device__ __forceinline__ WindowConsts make_window_consts(unsigned k) {
     return c;
 }
 
+template <bool PACKED>
 __device__ __forceinline__ void issue_tile(unsigned char* stage, unsigned long long* bar,
                                            const CountParams& p, unsigned long long tile) {
-    mbar_expect_tx(bar, kBytesPerStage + kBitsPerStage);
-    tma_load_1d(stage, p.bases + tile * COUNT_TILE, kBytesPerStage, bar);
-    tma_load_1d(stage + kBytesPerStage, (const unsigned char*)p.invalid + tile * kBitsPerStage,
-                kBitsPerStage, bar);
+    if constexpr (PACKED) {
+        const bool has_other = p.other != nullptr;
+        mbar_expect_tx(bar, kPkCodes + kBitsPerStage + (has_other ? kPkOther : 0));
+        tma_load_1d(stage, p.bases + tile * (COUNT_TILE / 4), kPkCodes, bar);
+        if (has_other) tma_load_1d(stage + kPkCodes, p.other + tile * (COUNT_TILE / 8), kPkOther, bar);
+        tma_load_1d(stage + kPkCodes + kPkOther, (const unsigned char*)p.invalid + tile * kBitsPerStage,
+                    kBitsPerStage, bar);
+    } else {
+        mbar_expect_tx(bar, kBytesPerStage + kBitsPerStage);
+        tma_load_1d(stage, p.bases + tile * COUNT_TILE, kBytesPerStage, bar);
+        tma_load_1d(stage + kBytesPerStage, (const unsigned char*)p.invalid + tile * kBitsPerStage,
+                    kBitsPerStage, bar);
+    }
+}
+
+// code words of the 16 positions [16*i, 16*i + 16) of a staged tile
+template <bool CANON, bool PACKED>
+__device__ __forceinline__ Codes16 load_codes(const unsigned char* sb, unsigned i, bool has_other) {
+    if constexpr (PACKED) {
+        const unsigned f = reinterpret_cast<const unsigned*>(sb)[i];
+        const unsigned x = has_other ? reinterpret_cast<const unsigned short*>(sb + kPkCodes)[i] : 0u;
+        return convert16_packed<!CANON>(f, x);
+    } else {
+        return convert16<!CANON>(reinterpret_cast<const uint4*>(sb)[i]);
+    }
 }
 
 // word of lane (lane + d) of the 64-word sequence {cur[0..31], nxt[0..31]}
@@ -222,7 +249,7 @@ __device__ __forceinline__ void process_chunk(const CountParams& p, const Window
 #ifndef NK_COUNT_MINBLOCKS
 #define NK_COUNT_MINBLOCKS 2
 #endif
-template <bool CANON, int MODE, bool POW2, bool KHI>
+template <bool CANON, int MODE, bool POW2, bool KHI, bool PACKED>
 __global__ void __launch_bounds__(COUNT_THREADS, NK_COUNT_MINBLOCKS) count_kernel(const __grid_constant__ CountParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) unsigned long long bars[COUNT_STAGES];
@@ -234,7 +261,7 @@ __global__ void __launch_bounds__(COUNT_THREADS, NK_COUNT_MINBLOCKS) count_kerne
         mbar_fence_init();
         unsigned long long t0 = atomicAdd(p.tile_counter, 1u);
         tile_of[0] = t0;
-        if (t0 < p.ntiles) issue_tile(smem, &bars[0], p, t0);
+        if (t0 < p.ntiles) issue_tile<PACKED>(smem, &bars[0], p, t0);
     }
     __syncthreads();
 
@@ -248,15 +275,16 @@ __global__ void __launch_bounds__(COUNT_THREADS, NK_COUNT_MINBLOCKS) count_kerne
         if (threadIdx.x == 0) {  // prefetch the next tile into the other stage (consumed at it-1)
             unsigned long long tn = atomicAdd(p.tile_counter, 1u);
             tile_of[s ^ 1u] = tn;
-            if (tn < p.ntiles) issue_tile(smem + (s ^ 1u) * kStageStride, &bars[s ^ 1u], p, tn);
+            if (tn < p.ntiles) issue_tile<PACKED>(smem + (s ^ 1u) * kStageStride, &bars[s ^ 1u], p, tn);
         }
         mbar_wait(&bars[s], (it >> 1) & 1u);
 
         const unsigned char* sb = smem + s * kStageStride;
-        const unsigned short* bits = reinterpret_cast<const unsigned short*>(sb + kBytesPerStage);
+        const unsigned short* bits =
+            reinterpret_cast<const unsigned short*>(sb + (PACKED ? kPkCodes + kPkOther : kBytesPerStage));
+        const bool has_other = PACKED && p.other != nullptr;
         const unsigned span0 = warp * COUNT_SPAN;
-        const unsigned char* lp = sb + span0 + 16u * lane;
-        Codes16 cur = convert16<!CANON>(*reinterpret_cast<const uint4*>(lp));
+        Codes16 cur = load_codes<CANON, PACKED>(sb, (span0 >> 4) + lane, has_other);
         // The k-1 overlap past the END of a warp's span is the first two code words of the next
         // warp's span: they are exchanged through shared memory instead of being converted twice
         // (the last warp converts the tile's 32-byte halo).  This is what makes small tiles cheap,
@@ -268,7 +296,7 @@ __global__ void __launch_bounds__(COUNT_THREADS, NK_COUNT_MINBLOCKS) count_kerne
         }
         Codes16 tail{0u, 0u, 0u};
         if (warp == COUNT_WARPS - 1)
-            tail = convert16<!CANON>(*reinterpret_cast<const uint4*>(sb + COUNT_TILE + 16u * (lane & 1u)));
+            tail = load_codes<CANON, PACKED>(sb, COUNT_TILE / 16 + (lane & 1u), has_other);
         __syncthreads();
         if (warp < COUNT_WARPS - 1 && lane < 2) {
             tail.F = halo[warp + 1][lane][0];
@@ -279,7 +307,7 @@ __global__ void __launch_bounds__(COUNT_THREADS, NK_COUNT_MINBLOCKS) count_kerne
         for (unsigned c = 0; c < COUNT_CHUNKS_PER_SPAN; ++c) {
             Codes16 nxt = tail;
             if (c + 1u < COUNT_CHUNKS_PER_SPAN)
-                nxt = convert16<!CANON>(*reinterpret_cast<const uint4*>(lp + (c + 1u) * COUNT_CHUNK));
+                nxt = load_codes<CANON, PACKED>(sb, ((span0 + (c + 1u) * COUNT_CHUNK) >> 4) + lane, has_other);
             const unsigned off = span0 + c * COUNT_CHUNK;
             const unsigned inv16 = bits[(off >> 4) + lane];
             process_chunk<CANON, MODE, POW2, KHI>(p, wc, cur, nxt, inv16, lane, tile * COUNT_TILE + off + 16u * lane,
@@ -351,7 +379,7 @@ __global__ void mark_tail_kernel(unsigned int* invalid, unsigned long long nbyte
 
 size_t count_smem_bytes() { return (size_t)kSmemTotal; }
 
-template <bool CANON, int MODE, bool POW2, bool KHI>
+template <bool CANON, int MODE, bool POW2, bool KHI, bool PACKED>
 static cudaError_t launch_count_t(const CountParams& p, cudaStream_t s) {
     constexpr int kSmem = kSmemTotal + (MODE == 3 ? kCompactBytes : 0);
     // persistent grid of this instantiation: SMs x resident CTAs (a multiple of 148 on B200); function
@@ -365,38 +393,41 @@ static cudaError_t launch_count_t(const CountParams& p, cudaStream_t s) {
         int sms = 0, per_sm = 0;
         e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(count_kernel<CANON, MODE, POW2, KHI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+        e = cudaFuncSetAttribute(count_kernel<CANON, MODE, POW2, KHI, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
         if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, count_kernel<CANON, MODE, POW2, KHI>, COUNT_THREADS, kSmem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, count_kernel<CANON, MODE, POW2, KHI, PACKED>, COUNT_THREADS, kSmem);
         if (e != cudaSuccess) return e;
         max_grid_of[dev] = sms * (per_sm < 1 ? 1 : per_sm);
     }
     const int max_grid = max_grid_of[dev];
     const unsigned long long grid = p.ntiles < (unsigned long long)max_grid ? p.ntiles : (unsigned long long)max_grid;
     if (grid == 0) return cudaSuccess;
-    count_kernel<CANON, MODE, POW2, KHI><<<(unsigned)grid, COUNT_THREADS, kSmem, s>>>(p);
+    count_kernel<CANON, MODE, POW2, KHI, PACKED><<<(unsigned)grid, COUNT_THREADS, kSmem, s>>>(p);
     return cudaGetLastError();
 }
 
-template <bool CANON, int MODE>
+template <bool CANON, int MODE, bool PACKED>
 static cudaError_t launch_count_cm(const CountParams& p, cudaStream_t s) {
     const bool pow2 = p.fm.is_pow2 != 0, khi = p.k > 16;
-    if (pow2) return khi ? launch_count_t<CANON, MODE, true, true>(p, s) : launch_count_t<CANON, MODE, true, false>(p, s);
-    return khi ? launch_count_t<CANON, MODE, false, true>(p, s) : launch_count_t<CANON, MODE, false, false>(p, s);
+    if (pow2)
+        return khi ? launch_count_t<CANON, MODE, true, true, PACKED>(p, s) : launch_count_t<CANON, MODE, true, false, PACKED>(p, s);
+    return khi ? launch_count_t<CANON, MODE, false, true, PACKED>(p, s) : launch_count_t<CANON, MODE, false, false, PACKED>(p, s);
 }
 
-template <bool CANON>
+template <bool CANON, bool PACKED>
 static cudaError_t launch_count_c(const CountParams& p, int mode, cudaStream_t s) {
     switch (mode) {
-        case 0: return launch_count_cm<CANON, 0>(p, s);
-        case 1: return launch_count_cm<CANON, 1>(p, s);
-        case 2: return launch_count_cm<CANON, 2>(p, s);
-        default: return launch_count_cm<CANON, 3>(p, s);
+        case 0: return launch_count_cm<CANON, 0, PACKED>(p, s);
+        case 1: return launch_count_cm<CANON, 1, PACKED>(p, s);
+        case 2: return launch_count_cm<CANON, 2, PACKED>(p, s);
+        default: return launch_count_cm<CANON, 3, PACKED>(p, s);
     }
 }
 
 cudaError_t launch_count(const CountParams& p, bool canonical, int mode, cudaStream_t s) {
-    return canonical ? launch_count_c<true>(p, mode, s) : launch_count_c<false>(p, mode, s);
+    if (p.packed)
+        return canonical ? launch_count_c<true, true>(p, mode, s) : launch_count_c<false, true>(p, mode, s);
+    return canonical ? launch_count_c<true, false>(p, mode, s) : launch_count_c<false, false>(p, mode, s);
 }
 
 cudaError_t launch_mark_invalid(unsigned int* invalid, const unsigned long long* offsets,

@@ -68,6 +68,34 @@ __device__ __forceinline__ Codes16 convert16(uint4 q) {
         o.V = 0;
     return o;
 }
+
+// Pre-packed input (include/neurokmer.h "nk2" layout): the lane's 16 bases arrive as the forward
+// word itself plus 16 `other` bits (bit j: base j was not ACGTacgt).  The complement word is the
+// 2-bit-group reversal of ~F; an `other` base is code 0 on BOTH strands (models.rs:237,249) and
+// not valid for pack_kmer (utils.rs:35).  ~6 ALU ops per 16 bases instead of ~70 for ASCII.
+__device__ __forceinline__ uint32_t spread16(uint32_t x) {  // bit j -> bit 2j
+    x = (x | (x << 8)) & 0x00FF00FFu;
+    x = (x | (x << 4)) & 0x0F0F0F0Fu;
+    x = (x | (x << 2)) & 0x33333333u;
+    x = (x | (x << 1)) & 0x55555555u;
+    return x;
+}
+template <bool WANT_V>
+__device__ __forceinline__ Codes16 convert16_packed(uint32_t f, uint32_t x16) {
+    Codes16 o;
+    const uint32_t b = __brev(f);  // base j now in bits 2j+1:2j, the two bits of each code swapped
+    o.R = ~(((b >> 1) & 0x55555555u) | ((b & 0x55555555u) << 1));
+    o.F = f;
+    o.V = WANT_V ? 0xFFFFFFFFu : 0u;
+    if (x16) {  // rare: N runs, IUPAC codes
+        const uint32_t xr = spread16(x16) * 3u;  // R layout (base j in bits 2j+1:2j)
+        const uint32_t xf = __brev(xr);          // F layout (base j in bits 31-2j:30-2j)
+        o.R &= ~xr;
+        o.F &= ~xf;  // the packer already wrote 0 there; this makes any input well-defined
+        if (WANT_V) o.V = ~xf;
+    }
+    return o;
+}
 #endif
 
 // ---------------------------------------------------------------------------

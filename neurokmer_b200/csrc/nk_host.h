@@ -84,6 +84,14 @@ size_t fastq_first_record_start(const uint8_t* file, size_t size, size_t s, uint
 bool fastq_parse_window(const uint8_t* file, size_t a, size_t b, uint8_t* data, size_t cap, size_t* fill,
                         std::vector<uint64_t>* offsets);
 
+// ---- 2-bit packer of the pre-packed input path (nk_pack.cpp; layout in include/neurokmer.h) ---------
+// bases [p0, p1) -> codes / other (p0 a multiple of 64; whole words are written).  Returns the number
+// of non-ACGT bytes.  body: 0 best available, 1 portable, 2 AVX2, 3 AVX-512BW.
+uint64_t host_pack_range(const uint8_t* bases, uint64_t p0, uint64_t p1, uint32_t* codes, uint32_t* other, int body);
+// whole array on `threads` host threads (<= 0: all hardware threads)
+uint64_t host_pack_bases(const uint8_t* bases, uint64_t n, uint32_t* codes, uint32_t* other, int threads, int body);
+int host_pack_body_available(int which);
+
 // whole-file driver behind nk_process_file (defined in nk_api.cu)
 int process_file(nk_counter* h, const char* path, bool streaming, std::string* err);
 

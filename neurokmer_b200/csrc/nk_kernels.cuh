@@ -30,6 +30,9 @@ constexpr int COUNT_STAGES = 2;
 
 struct CountParams {
     const unsigned char* bases;   // device, 16-B aligned, readable up to ntiles*TILE + HALO
+                                  // packed != 0: the 2-bit code words, readable up to ntiles*TILE/4 + 16
+    const unsigned char* other;   // packed only: `other` bits, readable up to ntiles*TILE/8 + 16; may be null
+    int packed;                   // 0: ASCII bases, 1: pre-packed input (include/neurokmer.h, "nk2" layout)
     const unsigned int* invalid;  // bit p set => no window starts at p; ntiles*TILE/32 words (+pad)
     unsigned int* acc;            // pool_size u32 batch accumulators
     unsigned int* tile_counter;   // dynamic tile scheduler cursor (zeroed before launch)
@@ -54,6 +57,13 @@ inline unsigned long long count_ntiles(unsigned long long nbytes) {
 }
 inline unsigned long long count_padded_bases(unsigned long long nbytes) {
     return count_ntiles(nbytes) * COUNT_TILE + COUNT_HALO + 64;
+}
+// pre-packed input: device bytes of the code / `other` arrays of a chunk of nbytes window starts
+inline unsigned long long count_padded_codes(unsigned long long nbytes) {
+    return count_ntiles(nbytes) * (COUNT_TILE / 4) + 16 + 64;
+}
+inline unsigned long long count_padded_other(unsigned long long nbytes) {
+    return count_ntiles(nbytes) * (COUNT_TILE / 8) + 16 + 64;
 }
 inline unsigned long long count_bitmap_words(unsigned long long nbytes) {
     return count_ntiles(nbytes) * (COUNT_TILE / 32) + 16;

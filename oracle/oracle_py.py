@@ -52,6 +52,27 @@ def pack_kmer(window: bytes) -> int:
     return w
 
 
+def pack_nk2(bases) -> Tuple[np.ndarray, np.ndarray, int]:
+    """numpy restatement of the product's pre-packed input layout (include/neurokmer.h, "nk2"):
+    codes u32 (16 bases per word, first base in bits 31:30, F codes of src/models.rs:231-239),
+    other u32 (bit p%32 of word p//32: byte p is not ACGTacgt), number of such bytes.
+    Test infrastructure: the checker of nk_pack_bases, never called by the product."""
+    a = np.frombuffer(bytes(bases), np.uint8) if not isinstance(bases, np.ndarray) else bases.astype(np.uint8)
+    n = a.size
+    lut_c = np.zeros(256, np.uint32)
+    lut_o = np.ones(256, np.uint32)
+    for b, c in _F.items():
+        lut_c[b] = c
+        lut_o[b] = 0
+    c = np.zeros((n + 15) // 16 * 16, np.uint32)
+    c[:n] = lut_c[a]
+    codes = (c.reshape(-1, 16) << (30 - 2 * np.arange(16, dtype=np.uint32))).sum(axis=1, dtype=np.uint64).astype(np.uint32)
+    o = np.zeros((n + 31) // 32 * 32, np.uint32)
+    o[:n] = lut_o[a]
+    other = (o.reshape(-1, 32) << np.arange(32, dtype=np.uint32)).sum(axis=1, dtype=np.uint64).astype(np.uint32)
+    return codes, other, int(lut_o[a].sum())
+
+
 def kmer_words(seq: bytes, k: int, canonical: bool = True) -> List[int]:
     out = []
     for i in range(0, len(seq) - k + 1):

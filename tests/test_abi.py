@@ -76,6 +76,43 @@ def test_host_only_entry_points(built):
     assert lib.nk_destroy(None) == 0 and lib.nk_reset(None) == built.NK_ERR_BAD_ARG
 
 
+def test_host_packer_matches_numpy_twin(built):
+    """nk_pack_bases (every SIMD body this CPU has, and the threaded driver) against the numpy
+    restatement of the "nk2" layout, over all 256 byte values and ragged lengths."""
+    from neurokmer_b200 import pack_bases
+    from oracle import oracle_py as op
+    lib = built.lib()
+    assert lib.nk_packed_code_words(0) == 0 and lib.nk_packed_code_words(17) == 2 and lib.nk_packed_other_words(33) == 2
+    rng = np.random.default_rng(7)
+    cases = [np.zeros(0, np.uint8), np.frombuffer(b"ACGTNacgtn", np.uint8), np.arange(256, dtype=np.uint8)]
+    for n in (1, 15, 16, 17, 31, 32, 33, 63, 64, 65, 127, 1000, 4097, 200_003):
+        a = rng.choice(np.frombuffer(b"ACGTacgtNnRY-*\x00\xff", np.uint8), size=n,
+                       p=[.2, .2, .2, .2, .03, .03, .03, .03, .02, .01, .01, .01, .01, .01, .005, .005])
+        cases.append(a)
+    cases.append(rng.integers(0, 256, size=70_001, dtype=np.uint8))
+    bodies = [0, 1]
+    for b in (2, 3):
+        rc = lib.nk_debug_pack_body(None, 0, None, None, b, None)
+        assert rc in (0, built.NK_ERR_UNSUPPORTED)
+        if rc == 0:
+            bodies.append(b)
+    for a in cases:
+        want_c, want_o, want_n = op.pack_nk2(a)
+        for body in bodies:
+            codes, other, n_other = pack_bases(a, body=body)
+            assert n_other == want_n, (a.size, body)
+            assert (codes[: want_c.size] == want_c).all(), (a.size, body)
+            assert (other[: want_o.size] == want_o).all(), (a.size, body)
+        codes, other, n_other = pack_bases(a, threads=3)
+        assert n_other == want_n and (codes[: want_c.size] == want_c).all() and (other[: want_o.size] == want_o).all()
+    # multi-range split (grain 65536) on a larger array, 4 threads
+    a = rng.choice(np.frombuffer(b"ACGTN", np.uint8), size=1_000_003, p=[.24, .25, .25, .25, .01])
+    want_c, want_o, want_n = op.pack_nk2(a)
+    codes, other, n_other = pack_bases(a, threads=4)
+    assert n_other == want_n and (codes == want_c).all() and (other == want_o).all()
+    assert lib.nk_pack_bases(None, 5, None, None, 1, None) == built.NK_ERR_BAD_ARG
+
+
 def test_no_cpu_fallback_without_device(built):
     """Without a usable sm_100 device the product path must fail loudly, not compute on the CPU."""
     try:

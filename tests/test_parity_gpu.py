@@ -996,3 +996,171 @@ def test_parallel_fastq_ingest_fuzz(tmp_path, coracle, seed, window, threads, de
     p = make(k, pool); p.process_file_streaming(fq)
     np.testing.assert_array_equal(p.currents(), exp)
     assert p.timings()["kmers"] == tot
+
+
+# --- pre-packed input ("nk2" layout): same results as the ASCII entry points ---------------------
+@pytest.mark.parametrize("k", [1, 2, 5, 15, 16, 17, 21, 31, 32])
+@pytest.mark.parametrize("canonical", [True, False])
+def test_packed_kmer_words_and_indices(coracle, k, canonical):
+    """The pre-packed windowing stage (convert16_packed) yields the words of models.rs:206-286 /
+    utils.rs:26-39 for the bytes the packed form was made from — `other` bases are code 0 on both
+    strands (canonical) and skipped (pack_kmer)."""
+    from neurokmer_b200 import pack_bases
+    rng = np.random.default_rng(300 + k)
+    pool = 1_000_003 if k % 2 else 65536
+    c = make(k, pool, canonical)
+    for n, pn, pl, pi in [(k, 0, 0, 0), (k + 1, 0.2, 0, 0), (700, 0.05, 0.2, 0.02), (20000, 0.01, 0.01, 0.01),
+                          (16384 + 40, 0.0, 0.0, 0.0), (33000, 0.3, 0.3, 0.1), (4096, 0.0, 0.0, 0.0), (4097, 0.5, 0, 0)]:
+        s = random_dna(rng, n, pn, pl, pi)
+        codes, other, n_other = pack_bases(s)
+        ow = coracle.kmer_words(s, k, canonical)
+        for oth in ([other] if n_other else [other, None]):
+            fwd, rc, words, idx = c.debug_kmers_packed(codes, oth, n)
+            assert words.size == ow.size == n - k + 1
+            np.testing.assert_array_equal(words, ow)
+            if canonical:
+                of, orc = coracle.kmer_fwd_rc(s, k)
+                np.testing.assert_array_equal(fwd, of)
+                np.testing.assert_array_equal(rc, orc)
+            step = max(1, ow.size // 3000)
+            np.testing.assert_array_equal(idx[::step], coracle.indices(ow[::step], pool))
+    assert c.debug_kmers_packed(np.zeros(1, np.uint32), None, k - 1)[2].size == 0
+
+
+def test_packed_ignores_codes_under_other_bits(coracle):
+    """A set `other` bit wins over whatever code the producer left there (well-defined for any input)."""
+    from neurokmer_b200 import pack_bases
+    rng = np.random.default_rng(5)
+    s = bytearray(random_dna(rng, 5000, 0.0, 0.0))
+    codes, other, _ = pack_bases(bytes(s))
+    for p in (0, 17, 31, 32, 4095, 4096, 4999):
+        other[p >> 5] |= np.uint32(1 << (p & 31))  # codes keep the letter's code
+        s[p] = ord("N")
+    for canonical in (True, False):
+        c = make(21, 1000, canonical)
+        words = c.debug_kmers_packed(codes, other, len(s))[2]
+        np.testing.assert_array_equal(words, coracle.kmer_words(bytes(s), 21, canonical))
+
+
+@pytest.mark.parametrize("k,pool,canonical", [(21, 1_000_000, True), (31, 2_000_000, True), (15, 65536, True),
+                                              (32, 999_983, True), (31, 1_000_000, False), (7, 1000, False), (1, 3, True)])
+def test_packed_currents_ragged(coracle, k, pool, canonical):
+    """nk_process_batch_packed on a ragged batch (sequences are not word-aligned in the packed form)."""
+    from neurokmer_b200 import flatten, pack_bases
+    rng = np.random.default_rng(k * 1000 + pool % 997 + 1)
+    seqs = ragged_batch(rng, k)
+    bases, offsets = flatten(seqs)
+    codes, other, _ = pack_bases(bases)
+    c = make(k, pool, canonical)
+    c.process_batch_packed(codes, other, offsets)
+    exp, tot = coracle.accumulate(bases, offsets, k, pool, canonical, threads=4)
+    got = c.currents()
+    np.testing.assert_array_equal(got, exp)
+    assert int(got.sum()) == tot and c.timings()["kmers"] == tot
+    # the ASCII entry point on the same counter: identical state rules (currents overwritten)
+    c2 = make(k, pool, canonical)
+    c2.process_batch(bases, offsets)
+    np.testing.assert_array_equal(c2.currents(), got)
+    np.testing.assert_array_equal(c2.spike_counts(), c.spike_counts())
+
+
+def test_packed_short_reads_and_no_other(coracle):
+    """150 bp reads (compaction mode of the count kernel) in packed form; all-ACGT batch with other=NULL."""
+    from neurokmer_b200 import flatten, pack_bases
+    rng = np.random.default_rng(77)
+    seqs = [random_dna(rng, int(n), 0.0, 0.02) for n in rng.choice([150, 150, 150, 20, 151, 31, 30], size=6000)]
+    bases, offsets = flatten(seqs)
+    codes, other, n_other = pack_bases(bases)
+    assert n_other == 0
+    k, pool = 31, 2_000_000
+    exp, tot = coracle.accumulate(bases, offsets, k, pool, True, threads=4)
+    for oth in (other, None):
+        c = make(k, pool)
+        c.process_batch_packed(codes, oth, offsets)
+        np.testing.assert_array_equal(c.currents(), exp)
+    seqs = [random_dna(rng, 150, 0.01, 0.02, 0.01) for _ in range(3000)]
+    bases, offsets = flatten(seqs)
+    codes, other, n_other = pack_bases(bases)
+    assert n_other > 0
+    exp, tot = coracle.accumulate(bases, offsets, k, pool, True, threads=4)
+    c = make(k, pool)
+    c.process_batch_packed(codes, other, offsets)
+    np.testing.assert_array_equal(c.currents(), exp)
+
+
+def test_packed_streaming_full_pipeline_and_chunk_straddle(coracle, monkeypatch):
+    """nk_stream_push_packed across several pushes and several H2D chunks (1 Mbase granules here),
+    then LIF + totals + top-N: identical to the oracle and to the ASCII stream."""
+    from neurokmer_b200 import flatten, pack_bases
+    monkeypatch.setenv("NK_PACKED_CHUNK_MBASES", "1")
+    rng = np.random.default_rng(99)
+    k, pool = 31, 20_000
+    batches = []
+    for lens in ([1_500_000, 700_000, 40], [(1 << 20) - 15, 31, 1 << 20, 100], [2_200_000]):
+        seqs = [random_dna(rng, n, 0.002, 0.01, 0.001) for n in lens]
+        batches.append(flatten(seqs))
+    c = make(k, pool)
+    c.stream_begin()
+    for bases, offsets in batches:
+        codes, other, _ = pack_bases(bases, threads=2)
+        c.stream_push_packed(codes, other, offsets)
+    c.stream_end()
+    o = oracle_counter(k, pool)
+    o.process_streaming(batches)
+    assert_state_equal(c, o)
+    assert_topn_equal(c, o, 20)
+    c2 = make(k, pool)
+    c2.stream_begin()
+    for bases, offsets in batches:
+        c2.stream_push(bases, offsets)
+    c2.stream_end()
+    np.testing.assert_array_equal(c2.spike_counts(), c.spike_counts())
+    assert c2.top_abundant_neurons(20) == c.top_abundant_neurons(20)
+
+
+def test_packed_exact_tables_and_state_errors(coracle):
+    """Exact side tables fed from packed input; call-sequence errors mirror the ASCII entry points."""
+    from neurokmer_b200 import NkError, flatten, pack_bases
+    rng = np.random.default_rng(3)
+    seqs = [random_dna(rng, 30_000, 0.01, 0.02), random_dna(rng, 500, 0.0, 0.0)]
+    bases, offsets = flatten(seqs)
+    codes, other, _ = pack_bases(bases)
+    k, pool = 15, 4096
+    c = make(k, pool)
+    c.enable_exact_counts(True)
+    c.process_batch_packed(codes, other, offsets)
+    words = np.concatenate([coracle.kmer_words(s, k, True) for s in seqs])
+    keys, counts = np.unique(words, return_counts=True)
+    gk, gc = c.exact_table()
+    np.testing.assert_array_equal(gk, keys)
+    np.testing.assert_array_equal(gc, counts.astype(np.uint32))
+    with pytest.raises(NkError) as ei:
+        c.stream_push_packed(codes, other, offsets)
+    assert ei.value.code == 6  # NK_ERR_STATE
+    c.stream_begin()
+    with pytest.raises(NkError):
+        c.process_batch_packed(codes, other, offsets)
+    c.stream_end()
+    bad = offsets.copy(); bad[0] = 1
+    with pytest.raises(NkError) as ei:
+        c.process_batch_packed(codes, other, bad)
+    assert ei.value.code == 1
+
+
+def test_packed_staged_device_resident(coracle):
+    """nk_stage_reserve_packed / nk_process_staged_packed: device-resident packed batch."""
+    import torch
+    from neurokmer_b200 import flatten, pack_bases
+    from neurokmer_b200.devmem import copy_h2d
+    rng = np.random.default_rng(11)
+    seqs = [random_dna(rng, n, 0.003, 0.01) for n in (300_000, 77, 150_000)]
+    bases, offsets = flatten(seqs)
+    codes, other, _ = pack_bases(bases)
+    k, pool = 31, 50_000
+    c = make(k, pool)
+    dc, dx, do = c.stage_reserve_packed(bases.size, len(seqs))
+    copy_h2d(dc, codes); copy_h2d(dx, other); copy_h2d(do, offsets)
+    c.process_staged_packed(bases.size, len(seqs), 0, True)
+    o = oracle_counter(k, pool)
+    o.process_parallel(bases, offsets)
+    assert_state_equal(c, o)

@@ -410,7 +410,7 @@ int count_host_batch(nk_counter* h, const uint8_t* bases, const uint64_t* offset
 // pre-packed host batch -> chunked H2D of the code words (and `other` bits) overlapped with mark+count.
 // Same pipeline as count_host_batch with 1/4 (+1/8) of the bytes on PCIe.
 unsigned long long packed_chunk_bases() {
-    unsigned long long mb = 16;  // measured on B200 / PCIe Gen5: see profiles/r01_bench.md
+    unsigned long long mb = 32;  // B200 / PCIe Gen5, 113 Mbase: 16 -> 1.55 ms, 32 -> 1.44 ms, 64 -> 1.53 ms (profiles/r01_bench.md)
     if (const char* e = getenv("NK_PACKED_CHUNK_MBASES")) {
         const unsigned long long t = strtoull(e, nullptr, 10);
         if (t >= 1 && t <= 1024) mb = t;
@@ -443,7 +443,41 @@ int count_host_batch_packed(nk_counter* h, const uint32_t* codes, const uint32_t
     const unsigned long long chunk = packed_chunk_bases();
     const unsigned char* const hc = reinterpret_cast<const unsigned char*>(codes);
     const unsigned char* const ho = reinterpret_cast<const unsigned char*>(other);
-    for (unsigned long long c0 = 0, c1 = 0; c0 < nbases; c0 = c1) {
+
+    // Zero-copy body: when the packed arrays live in pinned, device-mapped host memory (nk_host_alloc,
+    // cudaHostAlloc/Register) the count kernel's TMA bulk loads read the tiles straight across PCIe —
+    // one launch, no staging copy, no per-chunk pipeline bubbles (3/8 B per base keeps PCIe at the
+    // kernel's own pace: 113 Mbase end to end 1.44 ms staged -> 1.11 ms, profiles/r01_bench.md).  Only whole tiles whose halo stays inside
+    // the host arrays are read this way; the ragged end takes the staged path below.  NK_ZEROCOPY=0
+    // forces the staged path.
+    unsigned long long zc_body = 0;
+    const char* zc_env = getenv("NK_ZEROCOPY");
+    const bool zc_on = !zc_env || atoi(zc_env) != 0;
+    if (zc_on && nbases >= 4ull * nk::COUNT_TILE + 128 && ((uintptr_t)codes & 15) == 0 && ((uintptr_t)other & 15) == 0) {
+        cudaPointerAttributes ac{}, ao{};
+        bool ok = cudaPointerGetAttributes(&ac, codes) == cudaSuccess && ac.type == cudaMemoryTypeHost && ac.devicePointer;
+        if (ok && other) ok = cudaPointerGetAttributes(&ao, other) == cudaSuccess && ao.type == cudaMemoryTypeHost && ao.devicePointer;
+        if (ok) {
+            zc_body = (nbases - 128) / nk::COUNT_TILE * nk::COUNT_TILE;
+            const unsigned long long slice = (0xFFFFFFFFull / nk::COUNT_TILE - 1) * nk::COUNT_TILE;
+            NK_TRY(ensure_devbuf_packed(h->staged, std::min(zc_body, slice), false));
+            NK_CUDA(cudaEventRecord(h->staged.copy_done, h->copy_stream));  // the offsets are on the device
+            NK_CUDA(cudaStreamWaitEvent(h->stream, h->staged.copy_done, 0));
+            for (unsigned long long c0 = 0; c0 < zc_body; c0 += slice) {
+                const unsigned long long n = std::min(slice, zc_body - c0);
+                DevBuf view = h->staged;
+                view.codes = static_cast<unsigned char*>(ac.devicePointer) + c0 / 4;
+                view.other = other ? static_cast<unsigned char*>(ao.devicePointer) + c0 / 8 : nullptr;
+                view.has_other = other != nullptr;
+                NK_TRY(count_chunk(h, view, d_offsets, 0, nseq, c0, n, n, pe, true));
+            }
+            h->last.h2d_bytes += zc_body / 4 + (other ? zc_body / 8 : 0);
+        } else {
+            cudaGetLastError();  // pageable memory: not an error, take the staged path
+        }
+    }
+
+    for (unsigned long long c0 = zc_body, c1 = 0; c0 < nbases; c0 = c1) {
         c1 = std::min(c0 + chunk, nbases);
         // whole words of the host arrays, including the halo the tiles of this chunk read past c1
         const unsigned long long code_bytes = (std::min(c1 + 64, nbases) - c0 + 15) / 16 * 4;
@@ -475,6 +509,7 @@ int count_host_batch_packed(nk_counter* h, const uint32_t* codes, const uint32_t
         NK_CUDA(cudaEventRecord(pe->copy1, h->copy_stream));
     }
     if (wait_copies) NK_CUDA(cudaStreamSynchronize(h->copy_stream));
+    if (zc_body) NK_CUDA(cudaStreamSynchronize(h->stream));  // the kernel itself read the caller's arrays
     return NK_OK;
 }
 

@@ -1164,3 +1164,38 @@ def test_packed_staged_device_resident(coracle):
     o = oracle_counter(k, pool)
     o.process_parallel(bases, offsets)
     assert_state_equal(c, o)
+
+
+def test_packed_zero_copy_from_pinned_memory(coracle, monkeypatch):
+    """Packed arrays in pinned (device-mapped) host memory: the count kernel reads whole tiles
+    straight from host memory, the ragged end is staged; same result as pageable input and oracle."""
+    from neurokmer_b200 import PinnedBuffer, flatten, pack_bases
+    rng = np.random.default_rng(21)
+    k, pool = 31, 100_000
+    seqs = [random_dna(rng, n, 0.004, 0.01, 0.001) for n in (700_001, 33, 90_000, 1_234_567)]
+    bases, offsets = flatten(seqs)
+    pc = PinnedBuffer(4 * ((bases.size + 15) // 16), np.uint32)
+    po = PinnedBuffer(4 * ((bases.size + 31) // 32), np.uint32)
+    pack_bases(bases, out_codes=pc.array, out_other=po.array)
+    exp, tot = coracle.accumulate(bases, offsets, k, pool, True, threads=4)
+    for zc in ("1", "0"):
+        monkeypatch.setenv("NK_ZEROCOPY", zc)
+        c = make(k, pool)
+        c.process_batch_packed(pc.array, po.array, offsets)
+        np.testing.assert_array_equal(c.currents(), exp)
+        assert c.timings()["kmers"] == tot
+        # staged H2D moves whole chunks; the zero-copy body is one launch + the staged ragged end
+        assert c.timings()["h2d_bytes"] > 0
+    o = oracle_counter(k, pool)
+    o.process_parallel(bases, offsets)
+    assert_state_equal(c, o)
+    # a batch too small for a zero-copy body, and one that ends exactly on a tile boundary
+    for n in (5000, 4 * 4096 + 128, 8 * 4096):
+        s = random_dna(rng, n, 0.01, 0.0)
+        b2, o2 = flatten([s])
+        pack_bases(b2, out_codes=pc.array, out_other=po.array)
+        monkeypatch.setenv("NK_ZEROCOPY", "1")
+        c = make(k, pool)
+        c.process_batch_packed(pc.array[: (n + 15) // 16], po.array[: (n + 31) // 32], o2)
+        e2, _ = coracle.accumulate(b2, o2, k, pool, True, threads=2)
+        np.testing.assert_array_equal(c.currents(), e2)

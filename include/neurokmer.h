@@ -204,6 +204,10 @@ NK_API int nk_debug_kmers_packed(nk_counter* h, const uint32_t* codes, const uin
  * (NK_ERR_UNSUPPORTED if this CPU lacks it) — the CPU tests compare every body with a numpy twin. */
 NK_API int nk_debug_pack_body(const uint8_t* bases, uint64_t nbases, uint32_t* codes, uint32_t* other, int body,
                               uint64_t* n_other);
+/* Host-only check of the record reader behind nk_process_file (src/utils.rs:9-24 rules; plain, gzip,
+ * bzip2, xz, zstd input): number of records, total sequence bytes and FNV-1a-64 over every record's
+ * sequence bytes followed by one 0xFF byte.  Needs no device. */
+NK_API int nk_debug_fastx_digest(const char* path, uint64_t* nrecords, uint64_t* nbases, uint64_t* fnv1a);
 /* SipHash-1-3(keys 0,0) of LE64(word) and word-hash % pool_size for a host array. */
 NK_API int nk_debug_hash(nk_counter* h, const uint64_t* words, uint64_t n, uint64_t* hashes, uint64_t* idx);
 /* values[i] % pool_size on the device for ANY pool_size in [1, 2^32) without allocating a pool:

@@ -29,7 +29,7 @@ SYMBOLS = [
     "nk_host_free", "nk_pack_kmer",
     "nk_packed_code_words", "nk_packed_other_words", "nk_pack_bases", "nk_process_batch_packed",
     "nk_stream_push_packed", "nk_debug_kmers_packed", "nk_debug_pack_body", "nk_stage_reserve_packed",
-    "nk_process_staged_packed",
+    "nk_process_staged_packed", "nk_debug_fastx_digest",
 ]
 
 
@@ -129,6 +129,7 @@ def load() -> C.CDLL:
         "nk_debug_pack_body": (i32, [vp, u64, vp, vp, i32, P(u64)]),
         "nk_stage_reserve_packed": (i32, [vp, u64, u64, P(vp), P(vp), P(vp)]),
         "nk_process_staged_packed": (i32, [vp, u64, u64, i32, i32]),
+        "nk_debug_fastx_digest": (i32, [C.c_char_p, P(u64), P(u64), P(u64)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError if the .so lacks a declared symbol

@@ -1104,7 +1104,7 @@ int process_file(nk_counter* h, const char* path, bool streaming, std::string* e
         cudaMemsetAsync(h->scalars + 2, 0, sizeof(unsigned long long), h->stream);
         h->currents_valid_overwrite = true;
         bool stop = false;
-        if (!rd.is_gzip()) {
+        if (!rd.is_compressed()) {
             bool handled = false;
             rc = rd.is_fastq() ? count_fastq_parallel(h, path, pe, err, &handled) : count_fasta_parallel(h, path, pe, err, &handled);
             if (rc != NK_OK) break;
@@ -2089,6 +2089,34 @@ int nk_host_free(void* ptr) {
 }
 
 uint64_t nk_pack_kmer(const uint8_t* kmer, uint64_t len) { return nk::host_pack_kmer(kmer, len); }
+
+// Host-only: run the C++ record reader over a file and digest what it yields, so that the reader
+// (formats, compression sniffing, stop-at-first-malformed-record) can be checked without a device.
+int nk_debug_fastx_digest(const char* path, uint64_t* nrecords, uint64_t* nbases, uint64_t* fnv1a) {
+    if (!path) return fail(NK_ERR_BAD_ARG, "null path");
+    nk::FastxReader rd;
+    std::string err;
+    if (rd.open(path, &err) != 0) return fail(NK_ERR_IO, "%s", err.c_str());
+    uint64_t nrec = 0, nb = 0, hsh = 0xcbf29ce484222325ull;
+    std::vector<uint8_t> buf(1u << 20), rec;
+    while (rd.next_record()) {
+        rec.clear();
+        bool done = false;
+        while (!done) {
+            const size_t n = rd.read_seq(buf.data(), buf.size(), &done);
+            rec.insert(rec.end(), buf.begin(), buf.begin() + n);
+        }
+        if (!rd.finish_record(rec.size())) break;  // malformed FASTQ record: iteration ends, record dropped
+        for (uint8_t b : rec) { hsh ^= b; hsh *= 0x100000001b3ull; }
+        hsh ^= 0xFFu; hsh *= 0x100000001b3ull;  // record separator
+        ++nrec;
+        nb += rec.size();
+    }
+    if (nrecords) *nrecords = nrec;
+    if (nbases) *nbases = nb;
+    if (fnv1a) *fnv1a = hsh;
+    return NK_OK;
+}
 
 int nk_process_file(nk_counter* h, const char* path, int streaming) {
     if (!h || !path) return fail(NK_ERR_BAD_ARG, "null argument");

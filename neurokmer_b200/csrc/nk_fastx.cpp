@@ -28,6 +28,7 @@ uint64_t host_pack_kmer(const uint8_t* kmer, uint64_t len) {
 }
 
 FastxReader::~FastxReader() {
+    delete dec_;
     if (gz_) gzclose((gzFile)gz_);  // also closes the descriptor
     else if (fd_ >= 0) ::close(fd_);
 }
@@ -37,9 +38,10 @@ bool FastxReader::fill() {
     pos_ = 0;
     end_ = 0;
     for (;;) {
-        ssize_t n = gz_ ? (ssize_t)gzread((gzFile)gz_, buf_.data(), (unsigned)buf_.size())
-                        : ::read(fd_, buf_.data(), buf_.size());
-        if (n < 0 && !gz_ && errno == EINTR) continue;
+        ssize_t n = dec_ ? (ssize_t)dec_->read(buf_.data(), buf_.size())
+                  : gz_  ? (ssize_t)gzread((gzFile)gz_, buf_.data(), (unsigned)buf_.size())
+                         : ::read(fd_, buf_.data(), buf_.size());
+        if (n < 0 && !gz_ && !dec_ && errno == EINTR) continue;
         if (n <= 0) { eof_ = true; return false; }  // a truncated / corrupt gzip stream ends the iteration
         end_ = (size_t)n;
         return true;
@@ -67,19 +69,21 @@ int FastxReader::open(const char* path, std::string* err) {
         return 1;
     }
     buf_.resize(4u << 20);
-    // needletail sniffs the compression format from the magic bytes; gzip is handled here through
-    // zlib (present in this image), bzip2 / xz / zstd are not (no headers to build against)
+    // needletail sniffs the compression format from the magic bytes: gzip through zlib here,
+    // bzip2 / xz / zstd through nk_decomp.cpp
     unsigned char magic[4] = {0, 0, 0, 0};
     const ssize_t got = ::pread(fd_, magic, 4, 0);
     if (got >= 2 && magic[0] == 0x1f && magic[1] == 0x8b) {
         gz_ = gzdopen(fd_, "rb");
         if (!gz_) { if (err) *err = std::string(path) + ": cannot start gzip decompression"; return 1; }
         gzbuffer((gzFile)gz_, 1u << 20);
-    } else if ((got >= 3 && magic[0] == 'B' && magic[1] == 'Z' && magic[2] == 'h') ||
-               (got >= 4 && magic[0] == 0xfd && magic[1] == '7' && magic[2] == 'z' && magic[3] == 'X') ||
-               (got >= 4 && magic[0] == 0x28 && magic[1] == 0xb5 && magic[2] == 0x2f && magic[3] == 0xfd)) {
-        if (err) *err = std::string(path) + ": bzip2 / xz / zstd input is not supported (plain or gzip FASTA/FASTQ only)";
-        return 1;
+    } else if (const int kind = StreamDecoder::sniff(magic, got > 0 ? (size_t)got : 0)) {
+        dec_ = new StreamDecoder;
+        std::string why;
+        if (!dec_->start(kind, fd_, &why)) {
+            if (err) *err = std::string(path) + ": " + why;
+            return 1;
+        }
     }
     const int c = peek();
     if (c < 0) { if (err) *err = std::string(path) + ": empty file"; return 1; }

@@ -14,11 +14,29 @@ uint64_t host_pack_kmer(const uint8_t* kmer, uint64_t len);
 
 // Incremental FASTA/FASTQ record reader with needletail's record rules as the
 // reference uses them (src/utils.rs:9-24):
-//   * gzip input is decompressed transparently (zlib), like needletail's sniffing reader;
+//   * gzip (zlib), bzip2, xz and zstd input is decompressed transparently, sniffed from the magic
+//     bytes like needletail's reader;
 //   * format by first byte: '>' FASTA, '@' FASTQ; anything else / empty file is an error at open;
 //   * a record's sequence = its sequence line(s) with '\n' and '\r' removed, bytes otherwise untouched;
 //   * FASTQ records are 4 lines; '+' separator and |qual| == |seq| are checked;
 //   * iteration ends at EOF or at the first malformed record (not an error to the caller).
+// bzip2 / xz / zstd stream decoder over a file descriptor (nk_decomp.cpp: the libraries are resolved
+// with dlopen at first use).  sniff() -> 0 none, 1 bzip2, 2 xz, 3 zstd.
+class StreamDecoder {
+public:
+    StreamDecoder();
+    ~StreamDecoder();
+    StreamDecoder(const StreamDecoder&) = delete;
+    StreamDecoder& operator=(const StreamDecoder&) = delete;
+    static int sniff(const unsigned char* magic, size_t n);
+    bool start(int kind, int fd, std::string* err);
+    size_t read(uint8_t* dst, size_t cap);
+
+private:
+    struct Impl;
+    Impl* p_ = nullptr;
+};
+
 class FastxReader {
 public:
     FastxReader() = default;
@@ -30,6 +48,7 @@ public:
     int open(const char* path, std::string* err);
     bool is_fastq() const { return fastq_; }
     bool is_gzip() const { return gz_ != nullptr; }
+    bool is_compressed() const { return gz_ != nullptr || dec_ != nullptr; }
 
     // Advance to the next record. false: EOF or malformed record (iteration over).
     bool next_record();
@@ -47,6 +66,7 @@ private:
 
     int fd_ = -1;
     void* gz_ = nullptr;  // gzFile when the input is gzip-compressed
+    StreamDecoder* dec_ = nullptr;  // bzip2 / xz / zstd
     std::vector<uint8_t> buf_;
     size_t pos_ = 0, end_ = 0;
     bool eof_ = false, fastq_ = false, at_line_start_ = true, started_ = false;

@@ -11,10 +11,21 @@ from typing import Iterator
 
 def _open(path: str):
     with open(path, "rb") as f:
-        magic = f.read(2)
-    if magic == b"\x1f\x8b":  # gzip, sniffed from the magic bytes like needletail does
+        magic = f.read(4)
+    if magic[:2] == b"\x1f\x8b":  # compression sniffed from the magic bytes like needletail does
         import gzip
         return gzip.open(path, "rb")
+    if magic[:3] == b"BZh":
+        import bz2
+        return bz2.open(path, "rb")
+    if magic == b"\xfd7zX":
+        import lzma
+        return lzma.open(path, "rb")
+    if magic == b"\x28\xb5\x2f\xfd":
+        import io
+        import pyarrow as pa
+        with open(path, "rb") as f:
+            return io.BytesIO(pa.input_stream(f, compression="zstd").read())
     return open(path, "rb")
 
 

@@ -151,3 +151,73 @@ def test_fastx_python_reader_matches_rules(tmp_path):
     with open(fq, "ab") as f:
         f.write(b"@bad\nACGT\n+\nII\n@after\nAC\n+\nII\n")
     assert list(read_fastx(fq)) == seqs  # stops at the malformed record (utils.rs:17-20)
+
+
+def _digest(seqs):
+    h, nb = 0xcbf29ce484222325, 0
+    for s in seqs:
+        for b in bytes(s) + b"\xff":
+            h = ((h ^ b) * 0x100000001b3) & 0xFFFFFFFFFFFFFFFF
+        nb += len(s)
+    return len(seqs), nb, h
+
+
+def _cxx_digest(lib, path):
+    n, nb, h = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    rc = lib.nk_debug_fastx_digest(str(path).encode(), C.byref(n), C.byref(nb), C.byref(h))
+    return rc, (n.value, nb.value, h.value)
+
+
+def test_cxx_reader_formats_and_compression(built, tmp_path):
+    """The C++ record reader behind nk_process_file (host only): FASTA / FASTQ, CRLF, multi-line records,
+    gzip / bzip2 / xz / zstd sniffed from the magic bytes (needletail's reader), multi-member gzip and
+    multi-frame zstd, truncated streams, stop at the first malformed record (src/utils.rs:17-20)."""
+    import bz2
+    import gzip
+    import lzma
+    import pyarrow as pa
+    from neurokmer_b200.fastx import read_fastx, write_fasta, write_fastq
+    lib = built.lib()
+    rng = np.random.default_rng(12)
+    seqs = [rng.choice(np.frombuffer(b"ACGTNacgt", np.uint8), size=n).tobytes() for n in (3_000_000, 0, 61, 60, 59, 1, 250_000)]
+    fa, fq = tmp_path / "a.fa", tmp_path / "a.fq"
+    write_fasta(str(fa), seqs); write_fastq(str(fq), seqs)
+    want = _digest(seqs)
+    zstd = pa.Codec("zstd")
+    for src in (fa, fq):
+        raw = src.read_bytes()
+        assert _cxx_digest(lib, src) == (0, want)
+        variants = {
+            ".gz": gzip.compress(raw, 1), ".bz2": bz2.compress(raw, 1), ".xz": lzma.compress(raw, preset=0),
+            ".zst": zstd.compress(raw, asbytes=True),
+            ".crlf": raw.replace(b"\n", b"\r\n"),
+        }
+        half = len(raw) // 2
+        cut = raw.rfind(b"\n", 0, half) + 1 if src is fa else 0
+        if cut:
+            # concatenated members / frames: gzip (MultiGzDecoder) and zstd read all of them
+            variants[".multi.gz"] = gzip.compress(raw[:cut], 1) + gzip.compress(raw[cut:], 1)
+            variants[".multi.zst"] = zstd.compress(raw[:cut], asbytes=True) + zstd.compress(raw[cut:], asbytes=True)
+        for ext, blob in variants.items():
+            p = tmp_path / (src.name + ext)
+            p.write_bytes(blob)
+            rc, got = _cxx_digest(lib, p)
+            assert rc == 0 and got == want, (src.name, ext)
+            assert _digest(list(read_fastx(str(p)))) == want, (src.name, ext, "python reader")
+    # a truncated compressed stream ends the iteration early instead of failing
+    for ext, blob in ((".bz2", bz2.compress(fa.read_bytes(), 1)), (".xz", lzma.compress(fa.read_bytes(), preset=0)),
+                      (".zst", zstd.compress(fa.read_bytes(), asbytes=True))):
+        p = tmp_path / ("trunc.fa" + ext)
+        p.write_bytes(blob[: len(blob) // 2])
+        rc, got = _cxx_digest(lib, p)
+        assert rc == 0 and 0 < got[1] < want[1], ext
+    # malformed FASTQ record: everything before it is kept
+    with open(fq, "ab") as f:
+        f.write(b"@bad\nACGT\n+\nII\n@after\nAC\n+\nII\n")
+    assert _cxx_digest(lib, fq) == (0, want)
+    # open errors
+    assert _cxx_digest(lib, tmp_path / "missing.fa")[0] == built.NK_ERR_IO
+    (tmp_path / "empty.fa").write_bytes(b"")
+    assert _cxx_digest(lib, tmp_path / "empty.fa")[0] == built.NK_ERR_IO
+    (tmp_path / "junk.txt").write_bytes(b"hello\n")
+    assert _cxx_digest(lib, tmp_path / "junk.txt")[0] == built.NK_ERR_IO

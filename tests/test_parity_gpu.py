@@ -336,6 +336,17 @@ def test_process_file_fasta_fastq(tmp_path, coracle):
             g.write(f.read())
         c = make(k, pool); c.process_file_streaming(gzp)
         np.testing.assert_array_equal(c.currents(), exp)
+    # ... and so are bzip2, xz and zstd (needletail's "compression" feature)
+    import bz2
+    import lzma
+    import pyarrow as pa
+    raw = open(fa, "rb").read()
+    for ext, blob in ((".bz2", bz2.compress(raw, 1)), (".xz", lzma.compress(raw, preset=0)),
+                      (".zst", pa.Codec("zstd").compress(raw, asbytes=True))):
+        with open(fa + ext, "wb") as g:
+            g.write(blob)
+        c = make(k, pool); c.process_file_streaming(fa + ext)
+        np.testing.assert_array_equal(c.currents(), exp)
     # a malformed FASTQ record ends the stream: records before it still count (utils.rs:17-20)
     bad = str(tmp_path / "bad.fastq")
     with open(bad, "wb") as g:

@@ -250,12 +250,14 @@ def gpu_arm(args):
 
     # sharded-pool mode (default for N > 1): the reduce-scatter of the counts is fused into the LIF
     # kernel over NVLink peer mappings; NCCL only carries a barrier and a few hundred bytes of results
-    fused = world > 1 and args.dist == "fused"
+    fused = world > 1 and args.dist in ("fused", "peer")
+    peer = world > 1 and args.dist == "peer"
     if fused:
         handle, _ = c.dist_export()
         handles = [None] * world
         dist.all_gather_object(handles, handle)
         c.dist_setup(rank, world, handles=b"".join(handles))
+        dist.barrier()  # every rank's mailbox is set up before anyone signals into it
         barrier_t = torch.zeros(1, dtype=torch.int32, device="cuda")
         pack_views = {}
 
@@ -264,6 +266,10 @@ def gpu_arm(args):
         if not fused:
             allreduce_currents()
             c.stream_finish()
+            return
+        if peer:
+            # signal + wait + slice LIF/top-N + pack delivery + merge: kernels only, no NCCL, no host barrier
+            c.dist_run()
             return
         a0, a1, a2, a3 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
         with torch.cuda.stream(stream):
@@ -438,7 +444,8 @@ def gpu_arm(args):
             "config": {"workload": WORKLOAD, "k": K, "pool_size": POOL, "lif_steps": STEPS_LIF, "top_n": TOPN,
                        "kmers_per_step_per_gpu": KMERS, "l2": "flushed before every step (256 MiB fill)",
                        "parallelism": f"dp{world}: sequence-chunk shards, full accumulator replica per GPU, "
-                                      + ("neuron-sliced LIF/top-N with peer-memory reduce" if fused else "one NCCL all-reduce")},
+                                      + ("neuron-sliced LIF/top-N with peer-memory reduce" if fused else "one NCCL all-reduce")
+                                      + (", peer-memory signalling (no NCCL per job)" if peer else "")},
             "e2e": {"value": e2e_value, "unit": "kmers/s", "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": int(phases_e2e[-1]["h2d_bytes"]),
                     "d2h_bytes_per_step": int(phases_e2e[-1]["d2h_bytes"] + 24 + 16 * TOPN)},
@@ -452,8 +459,11 @@ def gpu_arm(args):
                 "host_pack_ms_untimed": pack_ms, "host_pack_threads": os.cpu_count()},
             "gpu_launches": launches * args.steps,
             "phases_ms": ph, "collective_ms": ar_ms,
-            "collective": ("none" if world == 1 else ("barrier + all-gather of result packs (NCCL); count reduce-scatter fused into the LIF "
-                           "kernel over NVLink peer memory" if fused else "all-reduce of the u64 currents (NCCL)")),
+            "collective": ("none" if world == 1 else (
+                "none per job: counting-finished flags, count reduce-scatter and result-pack exchange are NVLink peer-memory "
+                "loads/stores inside the kernels" if peer else (
+                    "barrier + all-gather of result packs (NCCL); count reduce-scatter fused into the LIF "
+                    "kernel over NVLink peer memory" if fused else "all-reduce of the u64 currents (NCCL)"))),
             "lif_path": int(phases[-1]["lif_path"]),
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "result": {"total_spikes": total_spikes, "top1": list(top[0][:2]) if top else None},
@@ -487,8 +497,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--workload", default="config2", choices=["config2", "config5"])
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (large workloads)")
-    ap.add_argument("--dist", default="fused", choices=["fused", "allreduce"],
-                    help="N > 1: peer-memory reduce fused into the LIF kernel (default) or NCCL all-reduce of the currents")
+    ap.add_argument("--dist", default="peer", choices=["peer", "fused", "allreduce"],
+                    help="N > 1: peer = sharded pool, every exchange through NVLink peer memory inside the kernels (default); "
+                         "fused = same kernels with an NCCL barrier + all-gather around them; allreduce = NCCL all-reduce of the currents")
     args = ap.parse_args()
     select_workload(args.workload)
     if args.impl == "reference":

@@ -268,6 +268,15 @@ NK_API int nk_dist_setup(nk_counter* h, int rank, int world, const void* ipc_han
 NK_API int nk_dist_post(nk_counter* h, void** dev_pack, uint64_t* pack_u64s, uint64_t* n_each);
 NK_API int nk_dist_complete(nk_counter* h, const void* dev_gathered_packs, uint64_t n_each);
 NK_API int nk_dist_slice(const nk_counter* h, uint64_t* lo, uint64_t* len);
+/* The same exchange with NO host or NCCL synchronisation per job (one handle per GPU):
+ *   per job:  nk_reset; nk_stream_begin; push / process_staged(mode 1); nk_dist_run
+ * nk_dist_run signals "this rank finished counting" into every peer's memory (NVLink stores), its slice
+ * kernel waits for all ranks' signals before reading their counts, delivers its result pack into every
+ * rank's mailbox, and a one-block kernel waits for all packs and merges them — nothing but kernels on
+ * the handle's stream.  nk_dist_setup is a collective call: a cross-rank barrier must separate it from the
+ * first nk_dist_run.  A rank that never arrives surfaces as NK_ERR_STATE from the first call that observes
+ * the result, after NK_DIST_TIMEOUT_MS (environment, default 30000). */
+NK_API int nk_dist_run(nk_counter* h);
 /* The CUDA stream (cudaStream_t) the handle's kernels run on. */
 NK_API int nk_cuda_stream(nk_counter* h, void** stream);
 NK_API int nk_synchronize(nk_counter* h);

@@ -29,7 +29,7 @@ SYMBOLS = [
     "nk_host_free", "nk_pack_kmer",
     "nk_packed_code_words", "nk_packed_other_words", "nk_pack_bases", "nk_process_batch_packed",
     "nk_stream_push_packed", "nk_debug_kmers_packed", "nk_debug_pack_body", "nk_stage_reserve_packed",
-    "nk_process_staged_packed", "nk_debug_fastx_digest",
+    "nk_process_staged_packed", "nk_debug_fastx_digest", "nk_dist_run",
 ]
 
 
@@ -114,6 +114,7 @@ def load() -> C.CDLL:
         "nk_dist_post": (i32, [vp, P(vp), P(u64), P(u64)]),
         "nk_dist_complete": (i32, [vp, vp, u64]),
         "nk_dist_slice": (i32, [vp, P(u64), P(u64)]),
+        "nk_dist_run": (i32, [vp]),
         "nk_cuda_stream": (i32, [vp, P(vp)]),
         "nk_synchronize": (i32, [vp]),
         "nk_synth_fill": (i32, [vp, vp, u64, u64, u64, u32]),

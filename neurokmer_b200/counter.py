@@ -332,6 +332,10 @@ class SpikingKmerCounter:
     def dist_complete(self, dev_gathered: int, n_each: int) -> None:
         check(self._L.nk_dist_complete(self._h, dev_gathered, n_each))
 
+    def dist_run(self) -> None:
+        """sharded-pool exchange with peer-memory signalling only (no NCCL / host barrier per job)"""
+        check(self._L.nk_dist_run(self._h))
+
     def dist_slice(self) -> Tuple[int, int]:
         lo, ln = C.c_uint64(), C.c_uint64()
         check(self._L.nk_dist_slice(self._h, C.byref(lo), C.byref(ln)))

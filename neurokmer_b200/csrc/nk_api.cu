@@ -153,6 +153,10 @@ struct nk_counter {
     bool dist_ipc_opened[16] = {};
     unsigned long long dist_lo = 0, dist_len = 0;
     unsigned long long* d_merged = nullptr;
+    // peer-signalled mode (nk_dist_run): every rank's mailbox (tail of its accumulator allocation)
+    unsigned char* dist_mail[16] = {};
+    unsigned long long dist_epoch = 0;
+    bool dist_failed = false;
     // exact side tables (opt-in, nk_enable_exact_counts)
     bool exact = false;
     nk::ExactTable xt;
@@ -712,6 +716,14 @@ int resolve(nk_counter* h) {
         h->h_scalars[0] = h->h_pack[0];
         h->h_scalars[2] = h->h_pack[2];
         h->pending_pack = false;
+        if (h->h_pack[1] != 0) {  // peer-signalled multi-GPU job: a rank's signal never arrived
+            h->pending_lif = false;
+            h->top_cache_valid = false;
+            h->dist_failed = true;
+            h->pend_pe = PhaseEvents{};
+            return fail(NK_ERR_STATE, "multi-GPU job failed: timed out waiting for a peer rank (code %llu: 1 = counting-finished "
+                        "signal, 2 = result pack)", h->h_pack[1]);
+        }
     }
     if (h->pending_lif) {
         const unsigned long long fired = h->h_scalars[0];
@@ -1218,7 +1230,9 @@ int nk_create(const nk_config* cfg, nk_counter** out) {
     NK_C(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     NK_C(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     const unsigned long long P = cfg->pool_size;
-    NK_C(cudaMalloc(&h->acc, P * sizeof(unsigned int)));
+    // the accumulators carry the multi-GPU mailbox at their tail: one IPC handle maps both into the peers
+    NK_C(cudaMalloc(&h->acc, nk::dist_mail_offset(P) + nk::DIST_MAIL_BYTES));
+    NK_C(cudaMemset(reinterpret_cast<unsigned char*>(h->acc) + nk::dist_mail_offset(P), 0, nk::DIST_MAIL_BYTES));
     NK_C(cudaMalloc(&h->currents, P * sizeof(unsigned long long)));
     NK_C(cudaMalloc(&h->v, P * sizeof(float)));
     NK_C(cudaMalloc(&h->r, P * sizeof(unsigned int)));
@@ -1838,6 +1852,14 @@ int nk_dist_setup(nk_counter* h, int rank, int world, const void* handles, void*
     }
     h->dist_rank = rank;
     h->dist_world = world;
+    const unsigned long long mail_off = nk::dist_mail_offset(h->cfg.pool_size);
+    for (int r = 0; r < 16; ++r)
+        h->dist_mail[r] = r < world ? reinterpret_cast<unsigned char*>(const_cast<unsigned int*>(h->dist_peer[r])) + mail_off : nullptr;
+    // epochs restart with every setup: the setup is a collective call, and a cross-rank barrier must
+    // separate it from the first nk_dist_run (peers write into this mailbox from then on)
+    NK_CUDA(cudaMemset(h->dist_mail[rank], 0, nk::DIST_MAIL_BYTES));
+    h->dist_epoch = 0;
+    h->dist_failed = false;
     const unsigned long long P = h->cfg.pool_size, per = (P + world - 1) / world;
     h->dist_lo = std::min(P, per * rank);
     h->dist_len = std::min(P, h->dist_lo + per) - h->dist_lo;
@@ -1845,20 +1867,14 @@ int nk_dist_setup(nk_counter* h, int rank, int world, const void* handles, void*
     return NK_OK;
 }
 
-// Enqueue this rank's slice post kernel.  PRECONDITION (caller): every rank's counting is complete
-// and ordered before this call on the handle's stream (e.g. a 1-element NCCL all-reduce on it).
-int nk_dist_post(nk_counter* h, void** dev_pack, uint64_t* pack_u64s, uint64_t* n_each) {
-    if (!h || !dev_pack || !pack_u64s || !n_each) return fail(NK_ERR_BAD_ARG, "null argument");
-    if (!h->dist_world) return fail(NK_ERR_STATE, "nk_dist_setup was not called");
-    if (!h->streaming) return fail(NK_ERR_STATE, "nk_dist_post without nk_stream_begin");
-    NK_CUDA(cudaSetDevice(h->cfg.device));
+// parameters of this rank's slice post kernel (shared by nk_dist_post and nk_dist_run)
+static int dist_build_post(nk_counter* h, nk::PostParams& q, unsigned long long* n_top_out) {
     const unsigned long long per = (h->cfg.pool_size + h->dist_world - 1) / h->dist_world;
     const unsigned long long n_top = std::min<unsigned long long>(h->topn_hint, per);
     const bool table_ok = h->fresh && !h->force_direct && !h->exact && h->cfg.steps > 0 && std::isfinite(h->cfg.threshold) &&
                           std::isfinite(h->cfg.leak) && saturation_count(h->cfg) < (1ull << 20);
     if (!table_ok || n_top < 1 || n_top * h->dist_world > 2048 || h->dist_len == 0)
         return fail(NK_ERR_UNSUPPORTED, "sharded post needs the fresh-state table path, world*top_n <= 2048 and a non-empty slice");
-    // the table (depends on the LIF parameters only)
     nk::LifParams p{};
     p.currents = h->currents + h->dist_lo;
     p.acc = h->acc;
@@ -1875,6 +1891,7 @@ int nk_dist_post(nk_counter* h, void** dev_pack, uint64_t* pack_u64s, uint64_t* 
     p.leak = h->cfg.leak;
     p.period = h->cfg.refractory;
     p.skip_zero = 0;
+    // the table (depends on the LIF parameters only)
     const unsigned long long table_n = saturation_count(h->cfg) + 1;
     NK_TRY(ensure_table(h, table_n, h->stream));  // usually prelaunched by nk_stream_begin on the side stream
     if (h->table_inflight) {
@@ -1882,7 +1899,7 @@ int nk_dist_post(nk_counter* h, void** dev_pack, uint64_t* pack_u64s, uint64_t* 
         h->table_inflight = false;
     }
     const unsigned long long per_call = (h->cfg.steps + h->cfg.refractory) / ((unsigned long long)h->cfg.refractory + 1ull);
-    nk::PostParams q{};
+    q = nk::PostParams{};
     q.lif = p;
     q.table = h->table;
     q.table_n = table_n;
@@ -1900,28 +1917,17 @@ int nk_dist_post(nk_counter* h, void** dev_pack, uint64_t* pack_u64s, uint64_t* 
     q.npeers = h->dist_world;
     for (int r = 0; r < h->dist_world; ++r) q.peer_acc[r] = h->dist_peer[r];
     q.slice_lo = h->dist_lo;
+    q.rank = h->dist_rank;
     // rows are padded to n_top per rank so that every rank's pack has the same size
     NK_CUDA(cudaMemsetAsync(h->d_pack, 0, (4 + 2 * n_top) * sizeof(unsigned long long), h->stream));
     NK_CUDA(cudaMemsetAsync(h->scalars, 0, sizeof(unsigned long long), h->stream));
     NK_CUDA(cudaMemsetAsync(h->post_zero, 0, 8 * sizeof(unsigned long long) + 8 * 256 * sizeof(unsigned int), h->stream));
-    NK_CUDA(nk::launch_post(q, h->post_grid, h->stream));
-    ++h->last.launches;
-    h->last.lif_path = 4;
-    *dev_pack = h->d_pack;
-    *pack_u64s = 4 + 2 * n_top;
-    *n_each = n_top;
+    *n_top_out = n_top;
     return NK_OK;
 }
 
-// `dev_gathered`: the world packs, rank-major, all-gathered by the caller on the handle's stream
-// (which also proves that every rank has finished reading this rank's accumulators).
-int nk_dist_complete(nk_counter* h, const void* dev_gathered, uint64_t n_each) {
-    if (!h || !dev_gathered) return fail(NK_ERR_BAD_ARG, "null argument");
-    if (!h->dist_world || !h->streaming) return fail(NK_ERR_STATE, "nk_dist_complete without nk_dist_post");
-    NK_CUDA(cudaSetDevice(h->cfg.device));
-    const unsigned long long n_out = std::min<unsigned long long>(h->topn_hint, h->cfg.pool_size);
-    NK_CUDA(nk::launch_merge_packs((const unsigned long long*)dev_gathered, h->dist_world, n_each, n_out, h->d_merged, h->stream));
-    ++h->last.launches;
+// host-side state after a sharded job's merged pack has been queued for read-back
+static int dist_finish(nk_counter* h, unsigned long long n_out) {
     // accumulators are all-zero between jobs (every peer has read them by now)
     NK_CUDA(cudaMemsetAsync(h->acc, 0, h->cfg.pool_size * sizeof(unsigned int), h->stream));
     const size_t bytes = (4 + 2 * n_out) * sizeof(unsigned long long);
@@ -1942,6 +1948,74 @@ int nk_dist_complete(nk_counter* h, const void* dev_gathered, uint64_t n_each) {
     h->pend_pe = h->stream_pe;
     h->streaming = false;
     return NK_OK;
+}
+
+// Enqueue this rank's slice post kernel.  PRECONDITION (caller): every rank's counting is complete
+// and ordered before this call on the handle's stream (e.g. a 1-element NCCL all-reduce on it).
+int nk_dist_post(nk_counter* h, void** dev_pack, uint64_t* pack_u64s, uint64_t* n_each) {
+    if (!h || !dev_pack || !pack_u64s || !n_each) return fail(NK_ERR_BAD_ARG, "null argument");
+    if (!h->dist_world) return fail(NK_ERR_STATE, "nk_dist_setup was not called");
+    if (!h->streaming) return fail(NK_ERR_STATE, "nk_dist_post without nk_stream_begin");
+    NK_CUDA(cudaSetDevice(h->cfg.device));
+    nk::PostParams q{};
+    unsigned long long n_top = 0;
+    NK_TRY(dist_build_post(h, q, &n_top));
+    NK_CUDA(nk::launch_post(q, h->post_grid, h->stream));
+    ++h->last.launches;
+    h->last.lif_path = 4;
+    *dev_pack = h->d_pack;
+    *pack_u64s = 4 + 2 * n_top;
+    *n_each = n_top;
+    return NK_OK;
+}
+
+// The whole exchange with NO host or NCCL synchronisation per job: the ranks signal each other through
+// flags in peer memory (NVLink stores), the post kernel waits for "everyone finished counting" before it
+// reads the peers' counts and delivers its result pack into every rank's mailbox, and a one-block kernel
+// waits for all packs and merges them.  One handle per GPU (the waiting kernels of two handles on one GPU
+// could starve each other); a lost peer surfaces as NK_ERR_STATE after NK_DIST_TIMEOUT_MS (default 30 s).
+int nk_dist_run(nk_counter* h) {
+    if (!h) return fail(NK_ERR_BAD_ARG, "null handle");
+    if (!h->dist_world) return fail(NK_ERR_STATE, "nk_dist_setup was not called");
+    if (!h->streaming) return fail(NK_ERR_STATE, "nk_dist_run without nk_stream_begin");
+    if (h->dist_failed) return fail(NK_ERR_STATE, "an earlier multi-GPU job timed out: call nk_dist_setup again on every rank");
+    NK_CUDA(cudaSetDevice(h->cfg.device));
+    unsigned long long timeout_ms = 30000;
+    if (const char* e = getenv("NK_DIST_TIMEOUT_MS")) {
+        const unsigned long long t = strtoull(e, nullptr, 10);
+        if (t >= 1) timeout_ms = t;
+    }
+    nk::PostParams q{};
+    unsigned long long n_top = 0;
+    NK_TRY(dist_build_post(h, q, &n_top));  // validates before any signal is sent
+    const unsigned long long epoch = ++h->dist_epoch;
+    // "this rank finished counting": ordered after its count kernels on the stream
+    NK_CUDA(nk::launch_dist_signal(h->dist_mail, h->dist_world, h->dist_rank, 0, epoch, h->stream));
+    ++h->last.launches;
+    q.wait_flags = nk::dist_mail_flags(h->dist_mail[h->dist_rank], 0);
+    q.epoch = epoch;
+    q.timeout_ns = timeout_ms * 1000000ull;
+    for (int r = 0; r < h->dist_world; ++r) q.peer_mail[r] = h->dist_mail[r];
+    NK_CUDA(nk::launch_post(q, h->post_grid, h->stream));
+    ++h->last.launches;
+    h->last.lif_path = 4;
+    const unsigned long long n_out = std::min<unsigned long long>(h->topn_hint, h->cfg.pool_size);
+    NK_CUDA(nk::launch_merge_mailbox(h->dist_mail[h->dist_rank], h->dist_world, n_top, n_out, epoch, q.timeout_ns,
+                                     h->d_merged, h->stream));
+    ++h->last.launches;
+    return dist_finish(h, n_out);
+}
+
+// `dev_gathered`: the world packs, rank-major, all-gathered by the caller on the handle's stream
+// (which also proves that every rank has finished reading this rank's accumulators).
+int nk_dist_complete(nk_counter* h, const void* dev_gathered, uint64_t n_each) {
+    if (!h || !dev_gathered) return fail(NK_ERR_BAD_ARG, "null argument");
+    if (!h->dist_world || !h->streaming) return fail(NK_ERR_STATE, "nk_dist_complete without nk_dist_post");
+    NK_CUDA(cudaSetDevice(h->cfg.device));
+    const unsigned long long n_out = std::min<unsigned long long>(h->topn_hint, h->cfg.pool_size);
+    NK_CUDA(nk::launch_merge_packs((const unsigned long long*)dev_gathered, h->dist_world, n_each, n_out, h->d_merged, h->stream));
+    ++h->last.launches;
+    return dist_finish(h, n_out);
 }
 
 int nk_dist_slice(const nk_counter* h, uint64_t* lo, uint64_t* len) {

@@ -153,7 +153,38 @@ struct PostParams {
     int npeers;                      // 0: single GPU; else world size (self included)
     const unsigned int* peer_acc[16];
     unsigned long long slice_lo;
+    // peer-signalled mode (nk_dist_run): no host / NCCL barrier around this kernel.
+    //   wait_flags != null: before touching any peer's counts every block waits until wait_flags[r] >= epoch
+    //   for all r < npeers (rank r's "counting finished" signal, written into THIS rank's mailbox).
+    //   peer_mail[r] != null: block 0 delivers the result pack into rank r's mailbox slot `rank` and then
+    //   raises rank r's "pack delivered" flag — which also tells r that this rank is done reading r's counts.
+    const unsigned long long* wait_flags;
+    unsigned long long epoch;
+    unsigned long long timeout_ns;
+    int rank;
+    unsigned char* peer_mail[16];
 };
+
+// Mailbox appended to every rank's accumulator allocation (so that the ONE IPC handle of nk_dist_export
+// maps it into the peers): flags[0][r] "rank r finished counting", flags[1][r] "rank r's pack delivered"
+// (epoch numbers, written by rank r), then 16 pack slots.
+constexpr int DIST_MAX_WORLD = 16;
+constexpr unsigned long long DIST_PACK_SLOT_U64 = 4 + 2 * 2048;
+constexpr unsigned long long DIST_MAIL_BYTES = (2 * DIST_MAX_WORLD + DIST_MAX_WORLD * DIST_PACK_SLOT_U64) * 8;
+inline unsigned long long dist_mail_offset(unsigned long long pool) { return (pool * 4 + 255) / 256 * 256; }
+inline unsigned long long* dist_mail_flags(unsigned char* mail, int which) {
+    return reinterpret_cast<unsigned long long*>(mail) + which * DIST_MAX_WORLD;
+}
+inline unsigned long long* dist_mail_slot(unsigned char* mail, int r) {
+    return reinterpret_cast<unsigned long long*>(mail) + 2 * DIST_MAX_WORLD + r * DIST_PACK_SLOT_U64;
+}
+// raise flags[which][rank] = epoch in every peer's mailbox (one tiny kernel after the count kernels)
+cudaError_t launch_dist_signal(unsigned char* const* peer_mail, int world, int rank, int which, unsigned long long epoch,
+                               cudaStream_t s);
+// wait for every rank's "pack delivered" flag in the local mailbox, then merge the packs found there
+cudaError_t launch_merge_mailbox(unsigned char* mail, int world, unsigned long long n_each, unsigned long long n_out,
+                                 unsigned long long epoch, unsigned long long timeout_ns, unsigned long long* pack_out,
+                                 cudaStream_t s);
 cudaError_t post_max_grid(int device, int* grid);
 cudaError_t launch_post(const PostParams& q, int max_grid, cudaStream_t s);
 // merge `world` result packs (stride 4+2*n_each u64) into one: fired and k-mers summed, rows re-sorted

@@ -18,6 +18,10 @@ namespace nk {
 
 namespace {
 
+struct PeerMail {
+    unsigned char* mail[DIST_MAX_WORLD];
+};
+
 constexpr int PT = 256;                               // threads per block
 constexpr int SEG = TOPN_BLOCK_ITEMS;                 // neurons per segment (4096)
 constexpr int ITEMS = SEG / PT;                       // 16
@@ -38,6 +42,38 @@ __device__ __forceinline__ unsigned block_sum(unsigned v, unsigned* s_warp) {
     return t;
 }
 
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// one thread: wait until flags[r] >= epoch for all r < world; false on timeout
+__device__ bool wait_flags(const unsigned long long* flags, int world, unsigned long long epoch, unsigned long long timeout_ns) {
+    const unsigned long long t0 = global_ns();
+    for (int r = 0; r < world; ++r) {
+        while (ld_acquire_sys(flags + r) < epoch) {
+            if (global_ns() - t0 > timeout_ns) return false;
+            __nanosleep(100);
+        }
+    }
+    return true;
+}
+
+__global__ void dist_signal_kernel(PeerMail pm, int world, int rank, int which, unsigned long long epoch) {
+    const int r = threadIdx.x;
+    if (r >= world) return;
+    __threadfence_system();  // this rank's counts (earlier kernels of the stream) before the flag
+    st_release_sys(reinterpret_cast<unsigned long long*>(pm.mail[r]) + which * DIST_MAX_WORLD + rank, epoch);
+}
+
 __global__ void __launch_bounds__(PT, 3) post_kernel(const PostParams q) {
     cg::grid_group grid = cg::this_grid();
     __shared__ unsigned int s_hist[256];
@@ -50,6 +86,15 @@ __global__ void __launch_bounds__(PT, 3) post_kernel(const PostParams q) {
     const LifParams& p = q.lif;
     const unsigned long long nseg = (p.pool + SEG - 1) / SEG;
     const int top = q.passes - 1;
+
+    // ---- peer-signalled mode: every rank must have finished counting before its counts are read ----
+    __shared__ int s_timeout;
+    if (q.wait_flags) {
+        if (tid == 0) s_timeout = wait_flags(q.wait_flags, q.npeers, q.epoch, q.timeout_ns) ? 0 : 1;
+        __syncthreads();
+        // a timed-out block keeps going (leaving would deadlock grid.sync); the pack carries the error
+        if (tid == 0 && s_timeout) atomicExch(&q.ctrl[1], 1ull);
+    }
 
     // ---- phase 1: fold + LIF table apply + histogram of the top digit of the new spike totals ----
     s_hist[tid] = 0;
@@ -274,31 +319,59 @@ __global__ void __launch_bounds__(PT, 3) post_kernel(const PostParams q) {
     }
     if (tid == 0) {
         q.pack[0] = *((volatile unsigned long long*)p.total_new);
-        q.pack[1] = 0;
+        q.pack[1] = *((volatile unsigned long long*)&q.ctrl[1]);  // 1: a peer's "counting finished" signal timed out
         q.pack[2] = *((volatile unsigned long long*)q.kmers);
         q.pack[3] = n;
+    }
+    if (q.wait_flags) {
+        // deliver the pack into every rank's mailbox (slot = this rank), then raise "pack delivered"
+        __syncthreads();
+        const unsigned words = 4u + 2u * n;
+        for (int r = 0; r < q.npeers; ++r) {
+            unsigned long long* slot = reinterpret_cast<unsigned long long*>(q.peer_mail[r]) + 2 * DIST_MAX_WORLD +
+                                       (unsigned long long)q.rank * DIST_PACK_SLOT_U64;
+            for (unsigned i = tid; i < words; i += PT) slot[i] = q.pack[i];
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (tid < (unsigned)q.npeers)
+            st_release_sys(reinterpret_cast<unsigned long long*>(q.peer_mail[tid]) + DIST_MAX_WORLD + q.rank, q.epoch);
     }
 }
 
 // one block: sum the scalars, sort the union of the per-rank rows, keep the best n_out
-__global__ void __launch_bounds__(PT) merge_packs_kernel(const unsigned long long* __restrict__ g, int world,
-                                                         unsigned long long n_each, unsigned long long n_out,
-                                                         unsigned long long* out) {
+// `flags` != null (peer-signalled mode): first wait until every rank's pack has been delivered.
+// No __restrict__ / non-coherent loads on g: in that mode it is written by the peers while this kernel waits.
+__global__ void __launch_bounds__(PT) merge_packs_kernel(const unsigned long long* g, int world,
+                                                         unsigned long long n_each, unsigned long long stride,
+                                                         unsigned long long n_out, unsigned long long* out,
+                                                         const unsigned long long* flags, unsigned long long epoch,
+                                                         unsigned long long timeout_ns) {
     __shared__ unsigned long long s_idx[2048], s_spk[2048];
+    __shared__ int s_err;
     const unsigned tid = threadIdx.x;
-    const unsigned long long stride = 4 + 2 * n_each;
+    if (tid == 0) s_err = 0;
+    if (flags) {
+        if (tid == 0) s_err = wait_flags(flags, world, epoch, timeout_ns) ? 0 : 2;
+        __syncthreads();
+        __threadfence_system();
+        if (s_err) {  // a rank never delivered its pack: report, do not touch the slots
+            if (tid == 0) { out[0] = 0; out[1] = (unsigned long long)s_err; out[2] = 0; out[3] = 0; }
+            return;
+        }
+    }
     unsigned total = 0;
-    for (int r = 0; r < world; ++r) total += (unsigned)g[r * stride + 3];
+    for (int r = 0; r < world; ++r) total += (unsigned)__ldcg(&g[r * stride + 3]);
     unsigned N = 1;
     while (N < total) N <<= 1;
     for (unsigned i = tid; i < N; i += PT) { s_idx[i] = ~0ull; s_spk[i] = 0ull; }
     __syncthreads();
     unsigned off = 0;
     for (int r = 0; r < world; ++r) {
-        const unsigned nr = (unsigned)g[r * stride + 3];
+        const unsigned nr = (unsigned)__ldcg(&g[r * stride + 3]);
         for (unsigned i = tid; i < nr; i += PT) {
-            s_idx[off + i] = g[r * stride + 4 + i];
-            s_spk[off + i] = g[r * stride + 4 + nr + i];
+            s_idx[off + i] = __ldcg(&g[r * stride + 4 + i]);
+            s_spk[off + i] = __ldcg(&g[r * stride + 4 + nr + i]);
         }
         off += nr;
     }
@@ -327,9 +400,9 @@ __global__ void __launch_bounds__(PT) merge_packs_kernel(const unsigned long lon
         out[4 + n + i] = s_spk[i];
     }
     if (tid == 0) {
-        unsigned long long fired = 0, kmers = 0;
-        for (int r = 0; r < world; ++r) { fired += g[r * stride + 0]; kmers += g[r * stride + 2]; }
-        out[0] = fired; out[1] = 0; out[2] = kmers; out[3] = n;
+        unsigned long long fired = 0, kmers = 0, err = (unsigned long long)s_err;
+        for (int r = 0; r < world; ++r) { fired += __ldcg(&g[r * stride + 0]); err |= __ldcg(&g[r * stride + 1]); kmers += __ldcg(&g[r * stride + 2]); }
+        out[0] = fired; out[1] = err; out[2] = kmers; out[3] = n;
     }
 }
 
@@ -337,7 +410,23 @@ __global__ void __launch_bounds__(PT) merge_packs_kernel(const unsigned long lon
 
 cudaError_t launch_merge_packs(const unsigned long long* gathered, int world, unsigned long long n_each,
                                unsigned long long n_out, unsigned long long* pack_out, cudaStream_t s) {
-    merge_packs_kernel<<<1, PT, 0, s>>>(gathered, world, n_each, n_out, pack_out);
+    merge_packs_kernel<<<1, PT, 0, s>>>(gathered, world, n_each, 4 + 2 * n_each, n_out, pack_out, nullptr, 0, 0);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_merge_mailbox(unsigned char* mail, int world, unsigned long long n_each, unsigned long long n_out,
+                                 unsigned long long epoch, unsigned long long timeout_ns, unsigned long long* pack_out,
+                                 cudaStream_t s) {
+    merge_packs_kernel<<<1, PT, 0, s>>>(dist_mail_slot(mail, 0), world, n_each, DIST_PACK_SLOT_U64, n_out, pack_out,
+                                        dist_mail_flags(mail, 1), epoch, timeout_ns);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_dist_signal(unsigned char* const* peer_mail, int world, int rank, int which, unsigned long long epoch,
+                               cudaStream_t s) {
+    PeerMail pm{};
+    for (int r = 0; r < world; ++r) pm.mail[r] = peer_mail[r];
+    dist_signal_kernel<<<1, 32, 0, s>>>(pm, world, rank, which, epoch);
     return cudaGetLastError();
 }
 

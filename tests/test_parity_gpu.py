@@ -1210,3 +1210,55 @@ def test_packed_zero_copy_from_pinned_memory(coracle, monkeypatch):
         c.process_batch_packed(pc.array[: (n + 15) // 16], po.array[: (n + 31) // 32], o2)
         e2, _ = coracle.accumulate(b2, o2, k, pool, True, threads=2)
         np.testing.assert_array_equal(c.currents(), e2)
+
+
+def test_sharded_pool_peer_signalled_run_one_gpu(coracle):
+    """nk_dist_run: counting-finished flags, count reduce-scatter and result-pack exchange all through peer
+    memory, no host barrier between the ranks.  Two / three handles on one GPU stand in for ranks (small pools:
+    the waiting kernels of all handles must be co-resident on the one device)."""
+    from neurokmer_b200 import flatten
+    from neurokmer_b200.shard import shard_batch
+    rng = np.random.default_rng(16)
+    for k, pool, world in [(31, 40_000, 2), (21, 30_011, 3)]:
+        seqs = [random_dna(rng, n, 0.001) for n in (1_500_000, 10, 700_000, 31, 900_000)]
+        bases, offsets = flatten(seqs)
+        ranks = [make(k, pool) for _ in range(world)]
+        raws = [c.dist_export()[1] for c in ranks]
+        for r, c in enumerate(ranks):
+            c.dist_setup(r, world, raw_ptrs=raws)
+        ref = make(k, pool); ref.stream_begin(); ref.stream_push(bases, offsets); ref.stream_end()
+        for job in range(3):  # back to back: epochs advance, accumulators are clean in between
+            for r, c in enumerate(ranks):
+                c.reset(); c.stream_begin(); c.stream_push(*shard_batch(bases, offsets, k, world, r))
+            for c in ranks:      # no barrier of any kind between the ranks
+                c.dist_run()
+            for c in ranks:
+                assert c.energy.total_spikes() == ref.energy.total_spikes()
+                assert c.top_abundant_neurons(20) == ref.top_abundant_neurons(20)
+                assert c.timings()["kmers"] == ref.timings()["kmers"]
+                lo, ln = c.dist_slice()
+                np.testing.assert_array_equal(c.currents()[lo:lo + ln], ref.currents()[lo:lo + ln])
+                np.testing.assert_array_equal(c.spike_counts()[lo:lo + ln], ref.spike_counts()[lo:lo + ln])
+        for c in ranks:
+            c.close()
+
+
+def test_peer_signalled_run_times_out_on_a_missing_rank(monkeypatch):
+    """A rank that never calls nk_dist_run must not hang the others: NK_ERR_STATE after the timeout."""
+    from neurokmer_b200 import NkError, flatten
+    monkeypatch.setenv("NK_DIST_TIMEOUT_MS", "300")
+    rng = np.random.default_rng(17)
+    bases, offsets = flatten([random_dna(rng, 200_000)])
+    ranks = [make(31, 20_000) for _ in range(2)]
+    raws = [c.dist_export()[1] for c in ranks]
+    for r, c in enumerate(ranks):
+        c.dist_setup(r, 2, raw_ptrs=raws)
+    c = ranks[0]
+    c.reset(); c.stream_begin(); c.stream_push(bases, offsets)
+    c.dist_run()
+    with pytest.raises(NkError) as ei:
+        c.energy.total_spikes()
+    assert ei.value.code == 6 and "timed out" in str(ei.value)
+    c.reset(); c.stream_begin()
+    with pytest.raises(NkError):
+        c.dist_run()       # sticky until the ranks set up again

@@ -20,8 +20,11 @@ followed by the top-20 read-out.  One "step" = one whole job on a freshly reset 
                  sample of the same workload — a reported baseline, not the target
 
 N > 1 (torchrun, one process per GPU): weak scaling — every rank counts its own 113 Mbase
-shard of the same synthetic stream into a full pool replica; the u64 currents are summed with
-ONE NCCL all-reduce over NVLink before LIF + top-N run (redundantly) on every rank.
+shard of the same synthetic stream into a full accumulator replica.  Default (--dist peer): each
+rank owns a neuron slice; its LIF/top-N kernel sums that slice of every rank's counts through
+NVLink peer memory, and the "finished counting" flags and result packs travel the same way — no
+NCCL call per job.  --dist fused: the same kernels with an NCCL barrier + all-gather around them;
+--dist allreduce: ONE NCCL all-reduce of the u64 currents, then LIF + top-N on every rank.
 
 `--impl reference` times the reference's CPU algorithm (the oracle port: the Rust crate
 cannot be built here, no cargo/rustc) on the host cores, same config/metric.

@@ -1242,7 +1242,7 @@ int nk_create(const nk_config* cfg, nk_counter** out) {
     NK_C(cudaMallocHost(&h->h_scalars, 8 * sizeof(unsigned long long)));
     NK_C(cudaMalloc(&h->topn.hist, 256 * sizeof(unsigned int)));
     NK_C(cudaMalloc(&h->topn.ctrl, 8 * sizeof(unsigned long long)));
-    NK_C(cudaMalloc(&h->topn.block_counts, ((P + nk::TOPN_BLOCK_ITEMS - 1) / nk::TOPN_BLOCK_ITEMS + 1) * sizeof(unsigned int)));
+    NK_C(cudaMalloc(&h->topn.block_counts, ((P + nk::POST_SEG_ITEMS - 1) / nk::POST_SEG_ITEMS + 1) * sizeof(unsigned int)));
     NK_C(nk::post_max_grid(cfg->device, &h->post_grid));
     NK_C(cudaMalloc(&h->post_zero, 8 * sizeof(unsigned long long) + 8 * 256 * sizeof(unsigned int)));
     NK_C(cudaMalloc(&h->d_pack, (4 + 2 * 2048) * sizeof(unsigned long long)));

@@ -125,6 +125,7 @@ struct TopNScratch {
     unsigned long long* out_spikes;  // capacity >= n_cap
 };
 constexpr int TOPN_BLOCK_ITEMS = 4096;
+constexpr int POST_SEG_ITEMS = 1024;  // segment of the fused post kernel's ordered phases (block_counts is sized for it)
 constexpr unsigned long long TOPN_MAX_N = 1ull << 20;
 cudaError_t launch_topn(const unsigned long long* spikes, unsigned long long pool, unsigned long long n,
                         unsigned long long max_spikes, const TopNScratch& sc, cudaStream_t s,

@@ -23,8 +23,14 @@ struct PeerMail {
 };
 
 constexpr int PT = 256;                               // threads per block
-constexpr int SEG = TOPN_BLOCK_ITEMS;                 // neurons per segment (4096)
-constexpr int ITEMS = SEG / PT;                       // 16
+// Work partition (ncu, profiles/r01_post_kernel_ncu.md): with 4096-neuron segments dealt round-robin,
+// 2 M neurons are 489 segments for 444 resident blocks — 45 blocks do two rounds while 399 wait at the
+// grid barrier, i.e. ~45 % of the kernel was barrier wait.  The elementwise phases (1, 2) therefore run
+// flat grid-stride loops (every thread gets the same number of neurons +-1), and the ordered phases
+// (3, 4) use 1024-neuron segments in CONTIGUOUS per-block ranges (balanced to one small segment, and
+// the running tie prefix is carried instead of being re-summed per segment).
+constexpr int SEG = POST_SEG_ITEMS;                   // neurons per segment of the ordered phases (1024)
+constexpr int ITEMS = SEG / PT;                       // 4
 
 __device__ __forceinline__ bool before(unsigned long long sa, unsigned long long ia, unsigned long long sb,
                                        unsigned long long ib) {
@@ -111,13 +117,14 @@ __global__ void __launch_bounds__(PT, 3) post_kernel(const PostParams q) {
     const unsigned int* __restrict__ tsp = q.table.spikes;
     const float* __restrict__ tv = q.table.v;
     const unsigned int* __restrict__ tr = q.table.r;
-    for (unsigned long long seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
-        for (int b0 = 0; b0 < ITEMS; b0 += B) {
+    const unsigned long long gthreads = (unsigned long long)gridDim.x * PT;
+    {
+        for (unsigned long long i0 = (unsigned long long)blockIdx.x * PT + tid; i0 < p.pool; i0 += gthreads * B) {
             unsigned long long count[B], total[B];
             bool ok[B];
 #pragma unroll
             for (int u = 0; u < B; ++u) {
-                const unsigned long long i = seg * SEG + (unsigned long long)(b0 + u) * PT + tid;
+                const unsigned long long i = i0 + (unsigned long long)u * gthreads;
                 ok[u] = i < p.pool;
                 count[u] = (ok[u] && p.fold_mode != 2) ? currents[i] : 0ull;
                 if (q.npeers) {
@@ -143,7 +150,7 @@ __global__ void __launch_bounds__(PT, 3) post_kernel(const PostParams q) {
             }
 #pragma unroll
             for (int u = 0; u < B; ++u) {
-                const unsigned long long i = seg * SEG + (unsigned long long)(b0 + u) * PT + tid;
+                const unsigned long long i = i0 + (unsigned long long)u * gthreads;
                 if (!ok[u]) continue;
                 if (p.fold_mode) {
                     if (!q.npeers) acc[i] = 0u;  // sharded: peers may still be reading; the host clears it later
@@ -183,16 +190,16 @@ __global__ void __launch_bounds__(PT, 3) post_kernel(const PostParams q) {
             s_hist[tid] = 0;
             __syncthreads();
             const int hs = 8 * (d + 1);
-            for (unsigned long long seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
-                unsigned long long v[ITEMS];
+            for (unsigned long long i0 = (unsigned long long)blockIdx.x * PT + tid; i0 < p.pool; i0 += gthreads * B) {
+                unsigned long long v[B];
 #pragma unroll
-                for (int it = 0; it < ITEMS; ++it) {
-                    const unsigned long long i = seg * SEG + (unsigned long long)it * PT + tid;
+                for (int it = 0; it < B; ++it) {
+                    const unsigned long long i = i0 + (unsigned long long)it * gthreads;
                     v[it] = i < p.pool ? spikes[i] : ~0ull;
                 }
 #pragma unroll
-                for (int it = 0; it < ITEMS; ++it) {
-                    const unsigned long long i = seg * SEG + (unsigned long long)it * PT + tid;
+                for (int it = 0; it < B; ++it) {
+                    const unsigned long long i = i0 + (unsigned long long)it * gthreads;
                     if (i < p.pool && (v[it] >> hs) == prefix) atomicAdd(&s_hist[(v[it] >> (8 * d)) & 255u], 1u);
                 }
             }
@@ -218,8 +225,11 @@ __global__ void __launch_bounds__(PT, 3) post_kernel(const PostParams q) {
     }
     const unsigned long long T = prefix, need = rank;
 
-    // ---- phase 3: ties per segment ----
-    for (unsigned long long seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
+    // ---- phase 3: ties per segment (each block owns a contiguous range of segments) ----
+    const unsigned long long seg_per = (nseg + gridDim.x - 1) / gridDim.x;
+    const unsigned long long seg_lo = (unsigned long long)blockIdx.x * seg_per;
+    const unsigned long long seg_hi = seg_lo + seg_per < nseg ? seg_lo + seg_per : nseg;
+    for (unsigned long long seg = seg_lo; seg < seg_hi; ++seg) {
         unsigned c = 0;
 #pragma unroll
         for (int it = 0; it < ITEMS; ++it) {
@@ -232,53 +242,59 @@ __global__ void __launch_bounds__(PT, 3) post_kernel(const PostParams q) {
     grid.sync();
 
     // ---- phase 4: ordered gather: every total > T, and the `need` lowest-index totals == T ----
-    for (unsigned long long seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
-        unsigned long long before_me = 0;  // ties in earlier segments
-        for (unsigned long long s = tid; s < seg; s += PT) before_me += __ldcg(&q.seg_counts[s]);
+    if (seg_lo < seg_hi) {
+        unsigned long long before_me = 0;  // ties in the segments before this block's range
+        for (unsigned long long s = tid; s < seg_lo; s += PT) before_me += __ldcg(&q.seg_counts[s]);
         for (int o = 16; o > 0; o >>= 1) before_me += __shfl_down_sync(0xFFFFFFFFu, before_me, o);
         if ((tid & 31) == 0) s_red[tid >> 5] = before_me;
         __syncthreads();
         unsigned long long seg_prefix = 0;
         for (int w = 0; w < PT / 32; ++w) seg_prefix += s_red[w];
         __syncthreads();
-        // thread t owns ITEMS consecutive neurons (index order)
-        const unsigned long long base = seg * SEG + (unsigned long long)tid * ITEMS;
-        unsigned long long v[ITEMS];
-        unsigned eq = 0;
-#pragma unroll
-        for (int it = 0; it < ITEMS; ++it) {
-            const unsigned long long i = base + it;
-            v[it] = i < p.pool ? spikes[i] : 0ull;
-            if (i < p.pool && v[it] == T) ++eq;
-            if (i < p.pool && v[it] > T) {
-                const unsigned long long slot = atomicAdd(&q.ctrl[0], 1ull);
-                q.out_idx[slot] = i;
-                q.out_spikes[slot] = v[it];
-            }
-        }
-        s_hist[tid] = eq;
-        __syncthreads();
-        for (int o = 1; o < PT; o <<= 1) {
-            const unsigned a = tid >= (unsigned)o ? s_hist[tid - o] : 0u;
-            __syncthreads();
-            s_hist[tid] += a;
-            __syncthreads();
-        }
-        unsigned long long r = seg_prefix + (s_hist[tid] - eq);
-        if (eq != 0 && r < need) {
+        for (unsigned long long seg = seg_lo; seg < seg_hi; ++seg) {
+            // thread t owns ITEMS consecutive neurons (index order)
+            const unsigned long long base = seg * SEG + (unsigned long long)tid * ITEMS;
+            unsigned long long v[ITEMS];
+            unsigned eq = 0;
 #pragma unroll
             for (int it = 0; it < ITEMS; ++it) {
                 const unsigned long long i = base + it;
-                if (i < p.pool && v[it] == T) {
-                    if (r < need) {
-                        q.out_idx[gt + r] = i;
-                        q.out_spikes[gt + r] = T;
-                    }
-                    ++r;
+                v[it] = i < p.pool ? spikes[i] : 0ull;
+                if (i < p.pool && v[it] == T) ++eq;
+                if (i < p.pool && v[it] > T) {
+                    const unsigned long long slot = atomicAdd(&q.ctrl[0], 1ull);
+                    q.out_idx[slot] = i;
+                    q.out_spikes[slot] = v[it];
                 }
             }
+            const unsigned seg_ties = __ldcg(&q.seg_counts[seg]);
+            if (seg_prefix < need && seg_ties != 0) {  // block-uniform: only segments that still contribute ties scan
+                s_hist[tid] = eq;
+                __syncthreads();
+                for (int o = 1; o < PT; o <<= 1) {
+                    const unsigned a = tid >= (unsigned)o ? s_hist[tid - o] : 0u;
+                    __syncthreads();
+                    s_hist[tid] += a;
+                    __syncthreads();
+                }
+                unsigned long long r = seg_prefix + (s_hist[tid] - eq);
+                if (eq != 0 && r < need) {
+#pragma unroll
+                    for (int it = 0; it < ITEMS; ++it) {
+                        const unsigned long long i = base + it;
+                        if (i < p.pool && v[it] == T) {
+                            if (r < need) {
+                                q.out_idx[gt + r] = i;
+                                q.out_spikes[gt + r] = T;
+                            }
+                            ++r;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+            seg_prefix += seg_ties;
         }
-        __syncthreads();
     }
     grid.sync();
 

@@ -361,7 +361,8 @@ int count_host_batch(nk_counter* h, const uint8_t* bases, const uint64_t* offset
     // EXPERIMENT (NK_ZEROCOPY=1): count whole tiles straight out of pinned, device-mapped host memory
     // (the kernel's TMA bulk loads cross PCIe themselves; no staging copy), H2D only for the ragged end.
     unsigned long long zc_body = 0;
-    if (getenv("NK_ZEROCOPY") && nbytes >= 4 * (unsigned long long)nk::COUNT_TILE && ((uintptr_t)bases & 15) == 0) {
+    const char* zc_env = getenv("NK_ZEROCOPY");
+    if (zc_env && atoi(zc_env) != 0 && nbytes >= 4 * (unsigned long long)nk::COUNT_TILE && ((uintptr_t)bases & 15) == 0) {
         cudaPointerAttributes at{};
         if (cudaPointerGetAttributes(&at, bases) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
             zc_body = (nbytes - nk::COUNT_HALO) / nk::COUNT_TILE * nk::COUNT_TILE;

@@ -189,6 +189,22 @@ NK_API int nk_copy_exact_table(nk_counter* h, uint64_t* keys /* n */, uint32_t* 
 /* kmer_per_neuron for every neuron (0 where the reference's map has no entry) */
 NK_API int nk_copy_uniques(nk_counter* h, uint32_t* out /* pool_size */);
 
+/* The `uniques` column for the TOP ROWS ONLY, without the exact table: a second pass over the same input
+ * that keeps just the windows mapped to those rows' neurons (memory O(matches), not O(windows); this is
+ * all the reference's CLI prints, src/main.rs:54-61).
+ *   nk_uniques_begin(h, top_n)   fixes the top_n (<= 2048) rows of the current state and arms the filter;
+ *   nk_uniques_push[_packed]     re-supply the batches that were counted, in any batching (synchronous);
+ *   nk_uniques_end(h)            afterwards nk_top_n(h, n <= top_n, ...) reports `uniques` for its rows,
+ *                                until the next job changes the state.
+ * nk_set_file_uniques(h, top_n): nk_process_file does this itself by reading the file a second time
+ * (top_n = 0 turns it off again; ignored while the exact table is enabled). */
+NK_API int nk_uniques_begin(nk_counter* h, uint64_t top_n);
+NK_API int nk_uniques_push(nk_counter* h, const uint8_t* bases, const uint64_t* offsets, uint64_t nseq);
+NK_API int nk_uniques_push_packed(nk_counter* h, const uint32_t* codes, const uint32_t* other, const uint64_t* offsets,
+                                  uint64_t nseq);
+NK_API int nk_uniques_end(nk_counter* h);
+NK_API int nk_set_file_uniques(nk_counter* h, uint64_t top_n);
+
 /* ---- parity taps (debug; not on the timed path) ---------------------------- */
 /* Words and neuron indices of every window of one sequence, in order: the
  * values `packed`/`idx` take at src/spiking_hash.rs:108-111,121-125 (canonical)

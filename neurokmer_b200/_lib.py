@@ -30,6 +30,7 @@ SYMBOLS = [
     "nk_packed_code_words", "nk_packed_other_words", "nk_pack_bases", "nk_process_batch_packed",
     "nk_stream_push_packed", "nk_debug_kmers_packed", "nk_debug_pack_body", "nk_stage_reserve_packed",
     "nk_process_staged_packed", "nk_debug_fastx_digest", "nk_dist_run",
+    "nk_uniques_begin", "nk_uniques_push", "nk_uniques_push_packed", "nk_uniques_end", "nk_set_file_uniques",
 ]
 
 
@@ -115,6 +116,11 @@ def load() -> C.CDLL:
         "nk_dist_complete": (i32, [vp, vp, u64]),
         "nk_dist_slice": (i32, [vp, P(u64), P(u64)]),
         "nk_dist_run": (i32, [vp]),
+        "nk_uniques_begin": (i32, [vp, u64]),
+        "nk_uniques_push": (i32, [vp, vp, vp, u64]),
+        "nk_uniques_push_packed": (i32, [vp, vp, vp, vp, u64]),
+        "nk_uniques_end": (i32, [vp]),
+        "nk_set_file_uniques": (i32, [vp, u64]),
         "nk_cuda_stream": (i32, [vp, P(vp)]),
         "nk_synchronize": (i32, [vp]),
         "nk_synth_fill": (i32, [vp, vp, u64, u64, u64, u32]),

@@ -189,6 +189,38 @@ class SpikingKmerCounter:
         return [(int(e.idx), int(e.spikes), None if e.uniques == _lib.NK_UNIQUES_NOT_COMPUTED else int(e.uniques))
                 for e in out[: got.value]]
 
+    # `uniques` of the top rows by a second pass over the input (no O(windows) table) ----------------
+    def uniques_begin(self, top_n: int) -> None:
+        check(self._L.nk_uniques_begin(self._h, top_n))
+
+    def uniques_push(self, bases: np.ndarray, offsets: np.ndarray) -> None:
+        bases = np.ascontiguousarray(bases, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        check(self._L.nk_uniques_push(self._h, _ptr(bases), offsets.ctypes.data, offsets.size - 1))
+
+    def uniques_push_packed(self, codes: np.ndarray, other: Optional[np.ndarray], offsets: np.ndarray) -> None:
+        codes = np.ascontiguousarray(codes, np.uint32)
+        other = None if other is None else np.ascontiguousarray(other, np.uint32)
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        check(self._L.nk_uniques_push_packed(self._h, codes.ctypes.data, None if other is None else other.ctypes.data,
+                                             offsets.ctypes.data, offsets.size - 1))
+
+    def uniques_end(self) -> None:
+        check(self._L.nk_uniques_end(self._h))
+
+    def top_uniques(self, top_n: int, batches) -> List[Tuple[int, int, Optional[int]]]:
+        """top_abundant_neurons(top_n) with the `uniques` column filled by re-supplying the (bases, offsets)
+        batches that were counted."""
+        self.uniques_begin(top_n)
+        for bases, offsets in batches:
+            self.uniques_push(bases, offsets)
+        self.uniques_end()
+        return self.top_abundant_neurons(top_n)
+
+    def set_file_uniques(self, top_n: int) -> None:
+        """process_file_* then fills `uniques` of the top_n rows by reading the file a second time"""
+        check(self._L.nk_set_file_uniques(self._h, top_n))
+
     def enable_exact_counts(self, on: bool = True) -> None:
         """Build the reference's `counts` / `kmer_per_neuron` side tables (off by default)."""
         check(self._L.nk_enable_exact_counts(self._h, int(on)))

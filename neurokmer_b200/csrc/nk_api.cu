@@ -161,6 +161,17 @@ struct nk_counter {
     bool exact = false;
     nk::ExactTable xt;
     unsigned int* d_top_uniques = nullptr;
+    // uniques pass (nk_uniques_*): `uniques` of the top rows by a second pass over the input, without the
+    // O(windows) exact table — the words that map to the rows' neurons are collected, sorted and counted
+    nk::ExactTable ut;
+    unsigned int* d_filter = nullptr;        // pool_size bits: neurons of the fixed rows
+    unsigned long long* d_rows = nullptr;    // their indices (device), row order
+    unsigned long long d_rows_cap = 0;
+    std::vector<unsigned long long> row_idx; // rows fixed by nk_uniques_begin
+    std::vector<unsigned int> row_uniques;   // filled by nk_uniques_end
+    bool rows_valid = false, uniques_open = false;
+    unsigned long long ut_count = 0;         // host mirror of the append cursor
+    unsigned long long file_uniques = 0;     // nk_set_file_uniques: rows nk_process_file resolves by re-reading the file
     bool table_valid = false, table_inflight = false;
     cudaEvent_t table_ready = nullptr;
     nk_config table_cfg{};
@@ -335,10 +346,14 @@ int validate_batch(const nk_counter* h, const uint8_t* bases, const uint64_t* of
     return NK_OK;
 }
 
+int uniques_host_batch(nk_counter* h, const uint8_t* bases, const uint32_t* codes, const uint32_t* other,
+                       const uint64_t* offsets, uint64_t nseq);
+
 // host batch -> chunked H2D (copy stream) overlapped with mark+count (compute stream)
 int count_host_batch(nk_counter* h, const uint8_t* bases, const uint64_t* offsets, uint64_t nseq, PhaseEvents* pe,
                      bool wait_copies = true) {
     if (nseq == 0) return NK_OK;
+    if (h->uniques_open) return uniques_host_batch(h, bases, nullptr, nullptr, offsets, nseq);  // second read of a file
     for (uint64_t s = 0; s < nseq; ++s)
         if (offsets[s + 1] < offsets[s]) return fail(NK_ERR_BAD_ARG, "offsets must be non-decreasing (at %llu)", (unsigned long long)s);
     const unsigned long long nbytes = offsets[nseq];
@@ -515,6 +530,92 @@ int count_host_batch_packed(nk_counter* h, const uint32_t* codes, const uint32_t
     }
     if (wait_copies) NK_CUDA(cudaStreamSynchronize(h->copy_stream));
     if (zc_body) NK_CUDA(cudaStreamSynchronize(h->stream));  // the kernel itself read the caller's arrays
+    return NK_OK;
+}
+
+// ---- uniques pass (second pass over the input) -------------------------------------------------------
+// One device-resident chunk: mark the invalid starts, then run the count kernel in mode 4 (no pool update;
+// words whose neuron is in the filter are appended).  If the word array was too small the cursor says by
+// how much: grow and run the chunk again (the appended prefix of the failed run is simply overwritten).
+int uniques_chunk(nk_counter* h, DevBuf& b, const unsigned long long* d_offsets, unsigned long long seq_lo,
+                  unsigned long long seq_hi, unsigned long long origin, unsigned long long nstarts, bool packed) {
+    if (nstarts == 0) return NK_OK;
+    NK_CUDA(nk::launch_mark_invalid(b.invalid, d_offsets, seq_lo, seq_hi, origin, nstarts, h->cfg.k, h->scalars + 3,
+                                    h->stream, nullptr));
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        nk::CountParams p{};
+        p.bases = packed ? b.codes : b.bases;
+        p.other = packed && b.has_other ? b.other : nullptr;
+        p.packed = packed ? 1 : 0;
+        p.invalid = b.invalid;
+        p.acc = h->acc;
+        p.tile_counter = h->tile_counter;
+        p.ntiles = nk::count_ntiles(nstarts);
+        p.fm = h->fm;
+        p.rm = nk::make_rotmul();
+        p.k = h->cfg.k;
+        p.filter = h->d_filter;
+        p.words = h->ut.words;
+        p.words_cursor = h->ut.cursor;
+        p.words_cap = h->ut.words_cap;
+        NK_CUDA(cudaMemsetAsync(h->tile_counter, 0, sizeof(unsigned int), h->stream));
+        NK_CUDA(nk::launch_count(p, h->cfg.use_canonical != 0, 4, h->stream));
+        unsigned long long cursor = 0;
+        NK_CUDA(cudaMemcpyAsync(&cursor, h->ut.cursor, sizeof cursor, cudaMemcpyDeviceToHost, h->stream));
+        NK_CUDA(cudaStreamSynchronize(h->stream));
+        if (cursor <= h->ut.words_cap) {
+            h->ut_count = cursor;
+            return NK_OK;
+        }
+        if (cursor > 0x7FFFFFF0ull)
+            return fail(NK_ERR_UNSUPPORTED, "uniques pass: more than 2^31 windows map to the requested rows "
+                        "(tiny pool?); use nk_enable_exact_counts on smaller batches");
+        // too small: keep what earlier chunks appended, rewind the cursor, grow, run the chunk again
+        NK_CUDA(nk::exact_grow_words(h->ut, cursor + cursor / 4 + 4096, h->ut_count, h->stream));
+        NK_CUDA(cudaMemcpyAsync(h->ut.cursor, &h->ut_count, sizeof(unsigned long long), cudaMemcpyHostToDevice, h->stream));
+        NK_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    return fail(NK_ERR_CUDA, "uniques pass: the word array kept overflowing");
+}
+
+// a host batch (ASCII when bases != null, else packed) through the uniques pass, synchronously
+int uniques_host_batch(nk_counter* h, const uint8_t* bases, const uint32_t* codes, const uint32_t* other,
+                       const uint64_t* offsets, uint64_t nseq) {
+    if (nseq == 0) return NK_OK;
+    for (uint64_t s = 0; s < nseq; ++s)
+        if (offsets[s + 1] < offsets[s]) return fail(NK_ERR_BAD_ARG, "offsets must be non-decreasing (at %llu)", (unsigned long long)s);
+    const unsigned long long n = offsets[nseq];
+    if (n == 0) return NK_OK;
+    const bool packed = bases == nullptr;
+    NK_CUDA(cudaStreamSynchronize(h->stream));
+    NK_CUDA(cudaStreamSynchronize(h->copy_stream));
+    NK_TRY(ensure_offsets(&h->d_offsets2[0], &h->offsets_cap2[0], nseq + 1));
+    NK_CUDA(cudaMemcpyAsync(h->d_offsets2[0], offsets, (nseq + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
+    const unsigned long long chunk = packed ? packed_chunk_bases() : kChunkBytes;
+    DevBuf& b = h->buf[0];
+    for (unsigned long long c0 = 0, c1 = 0; c0 < n; c0 = c1) {
+        c1 = std::min(c0 + chunk, n);
+        if (packed) {
+            NK_TRY(ensure_devbuf_packed(b, std::min(chunk, n), other != nullptr));
+            const unsigned long long code_bytes = (std::min(c1 + 64, n) - c0 + 15) / 16 * 4;
+            const unsigned long long other_bytes = (std::min(c1 + 128, n) - c0 + 31) / 32 * 4;
+            NK_CUDA(cudaMemcpyAsync(b.codes, reinterpret_cast<const unsigned char*>(codes) + c0 / 4, code_bytes,
+                                    cudaMemcpyHostToDevice, h->stream));
+            b.has_other = other != nullptr;
+            if (other)
+                NK_CUDA(cudaMemcpyAsync(b.other, reinterpret_cast<const unsigned char*>(other) + c0 / 8, other_bytes,
+                                        cudaMemcpyHostToDevice, h->stream));
+        } else {
+            NK_TRY(ensure_devbuf(b, std::min((unsigned long long)kChunkBytes, n)));
+            const unsigned long long copy_len = std::min(c1 + nk::COUNT_HALO, n) - c0;
+            NK_CUDA(cudaMemcpyAsync(b.bases, bases + c0, copy_len, cudaMemcpyHostToDevice, h->stream));
+        }
+        const uint64_t* first = std::upper_bound(offsets + 1, offsets + nseq + 1, (uint64_t)c0);
+        const unsigned long long seq_lo = (unsigned long long)(first - (offsets + 1));
+        const uint64_t* last = std::lower_bound(offsets, offsets + nseq, (uint64_t)c1);
+        const unsigned long long seq_hi = (unsigned long long)(last - offsets);
+        NK_TRY(uniques_chunk(h, b, h->d_offsets2[0], seq_lo, seq_hi, c0, c1 - c0, packed));  // synchronises
+    }
     return NK_OK;
 }
 
@@ -740,6 +841,7 @@ int resolve(nk_counter* h) {
 
 void begin_call(nk_counter* h) {
     resolve(h);
+    h->rows_valid = false;  // a new job: the rows fixed by nk_uniques_begin no longer describe the state
     h->ev_used = 0;
     const float topn = h->last.topn_ms;
     h->last = nk_timings{};
@@ -1065,7 +1167,9 @@ int count_fastq_parallel(nk_counter* h, const char* path, PhaseEvents& pe, std::
 
 }  // namespace
 
-int process_file(nk_counter* h, const char* path, bool streaming, std::string* err) {
+// ingest_only: the second read of a file by the uniques pass — the batches are routed to
+// uniques_host_batch (count_host_batch checks h->uniques_open), nothing is simulated or read back
+int process_file(nk_counter* h, const char* path, bool streaming, std::string* err, bool ingest_only) {
     FastxReader rd;
     if (rd.open(path, err) != 0) return NK_ERR_IO;
     auto cuda_fail = [&](cudaError_t e, const char* what) {
@@ -1093,7 +1197,7 @@ int process_file(nk_counter* h, const char* path, bool streaming, std::string* e
     size_t fill = 0;
     const unsigned k = h->cfg.k;
 
-    begin_call(h);
+    if (!ingest_only) begin_call(h);
     PhaseEvents pe;
     int rc = NK_OK;
     auto flush = [&]() -> int {
@@ -1112,10 +1216,12 @@ int process_file(nk_counter* h, const char* path, bool streaming, std::string* e
         return NK_OK;
     };
     do {
-        if (get_event(h, &pe.begin) != NK_OK) { *err = g_err; rc = NK_ERR_CUDA; break; }
-        cudaEventRecord(pe.begin, h->stream);
-        cudaMemsetAsync(h->scalars + 2, 0, sizeof(unsigned long long), h->stream);
-        h->currents_valid_overwrite = true;
+        if (!ingest_only) {
+            if (get_event(h, &pe.begin) != NK_OK) { *err = g_err; rc = NK_ERR_CUDA; break; }
+            cudaEventRecord(pe.begin, h->stream);
+            cudaMemsetAsync(h->scalars + 2, 0, sizeof(unsigned long long), h->stream);
+            h->currents_valid_overwrite = true;
+        }
         bool stop = false;
         if (!rd.is_compressed()) {
             bool handled = false;
@@ -1166,6 +1272,7 @@ int process_file(nk_counter* h, const char* path, bool streaming, std::string* e
         }
         if (rc != NK_OK) break;
         if ((rc = flush()) != NK_OK) break;
+        if (ingest_only) break;
         if ((rc = fold_and_simulate(h, /*skip_zero=*/!streaming, pe)) != NK_OK) { *err = g_err; break; }
         if (get_event(h, &pe.end) != NK_OK) { *err = g_err; rc = NK_ERR_CUDA; break; }
         cudaEventRecord(pe.end, h->stream);
@@ -1300,6 +1407,9 @@ int nk_destroy(nk_counter* h) {
     cudaFree(h->post_zero); cudaFree(h->d_pack);
     if (h->h_pack) cudaFreeHost(h->h_pack);
     if (h->h_top) cudaFreeHost(h->h_top);
+    nk::exact_free(h->ut);
+    cudaFree(h->d_filter);
+    cudaFree(h->d_rows);
     for (int r = 0; r < 16; ++r) if (h->dist_ipc_opened[r]) cudaIpcCloseMemHandle((void*)h->dist_peer[r]);
     cudaFree(h->d_merged);
     nk::exact_free(h->xt);
@@ -1509,7 +1619,8 @@ int nk_top_n(nk_counter* h, uint64_t top_n, nk_top_entry* out, uint64_t* n_out) 
         for (uint64_t i = 0; i < n; ++i) {
             out[i].idx = h->h_pack[4 + i];
             out[i].spikes = h->h_pack[4 + cn + i];
-            out[i].uniques = NK_UNIQUES_NOT_COMPUTED;
+            out[i].uniques = (h->rows_valid && i < h->row_idx.size() && h->row_idx[i] == out[i].idx) ? h->row_uniques[i]
+                                                                                                     : NK_UNIQUES_NOT_COMPUTED;
             out[i]._pad = 0;
         }
         *n_out = n;
@@ -1559,7 +1670,9 @@ int nk_top_n(nk_counter* h, uint64_t top_n, nk_top_entry* out, uint64_t* n_out) 
     for (uint64_t i = 0; i < n; ++i) {
         out[i].idx = hi[i];
         out[i].spikes = hs[i];
-        out[i].uniques = have_uniques ? h_uni[i] : NK_UNIQUES_NOT_COMPUTED;
+        out[i].uniques = have_uniques ? h_uni[i]
+                         : (h->rows_valid && i < h->row_idx.size() && h->row_idx[i] == hi[i]) ? h->row_uniques[i]
+                                                                                             : NK_UNIQUES_NOT_COMPUTED;
         out[i]._pad = 0;
     }
     *n_out = n;
@@ -2165,6 +2278,95 @@ int nk_host_free(void* ptr) {
 
 uint64_t nk_pack_kmer(const uint8_t* kmer, uint64_t len) { return nk::host_pack_kmer(kmer, len); }
 
+// ---- uniques of the top rows by a second pass over the input (no O(windows) table) -------------------
+static int uniques_begin(nk_counter* h, uint64_t top_n) {
+    if (h->streaming) return fail(NK_ERR_STATE, "nk_uniques_begin inside nk_stream_begin/end");
+    if (h->uniques_open) return fail(NK_ERR_STATE, "nk_uniques_begin called twice");
+    const uint64_t n = std::min<uint64_t>(top_n, h->cfg.pool_size);
+    if (n == 0 || n > 2048) return fail(NK_ERR_BAD_ARG, "nk_uniques_begin: top_n must be in 1..2048");
+    std::vector<nk_top_entry> rows(n);
+    uint64_t got = 0;
+    NK_TRY(nk_top_n(h, n, rows.data(), &got));
+    NK_CUDA(cudaStreamSynchronize(h->stream));
+    h->rows_valid = false;
+    h->row_idx.resize(got);
+    for (uint64_t i = 0; i < got; ++i) h->row_idx[i] = rows[i].idx;
+    h->row_uniques.assign(got, 0u);
+    const unsigned long long fwords = (h->cfg.pool_size + 31) / 32;
+    if (!h->d_filter) NK_CUDA(cudaMalloc(&h->d_filter, fwords * sizeof(unsigned int)));
+    if (got > h->d_rows_cap) {
+        cudaFree(h->d_rows);
+        h->d_rows = nullptr;
+        h->d_rows_cap = 0;
+        NK_CUDA(cudaMalloc(&h->d_rows, got * sizeof(unsigned long long)));
+        h->d_rows_cap = got;
+    }
+    NK_CUDA(cudaMemsetAsync(h->d_filter, 0, fwords * sizeof(unsigned int), h->stream));
+    NK_CUDA(cudaMemcpyAsync(h->d_rows, h->row_idx.data(), got * sizeof(unsigned long long), cudaMemcpyHostToDevice, h->stream));
+    NK_CUDA(nk::launch_filter_set(h->d_filter, h->d_rows, got, h->stream));
+    NK_CUDA(nk::exact_grow_words(h->ut, 1ull << 20, 0, h->stream));
+    NK_CUDA(nk::exact_clear(h->ut, h->cfg.pool_size, true, h->stream));
+    NK_CUDA(cudaStreamSynchronize(h->stream));
+    h->ut_count = 0;
+    h->uniques_open = true;
+    return NK_OK;
+}
+
+static int uniques_end(nk_counter* h) {
+    h->uniques_open = false;
+    cudaError_t e = nk::exact_finalize(h->ut, h->fm, h->cfg.pool_size, std::min(64u, 2u * h->cfg.k), false, h->stream);
+    if (e == cudaErrorInvalidValue) return fail(NK_ERR_UNSUPPORTED, "uniques pass: more than 2^31 collected windows");
+    NK_CUDA(e);
+    const uint64_t n = h->row_idx.size();
+    if (n) {
+        cudaFree(h->d_top_uniques);
+        h->d_top_uniques = nullptr;
+        NK_CUDA(cudaMalloc(&h->d_top_uniques, n * sizeof(unsigned int)));
+        NK_CUDA(nk::exact_gather_uniques(h->ut, h->d_rows, n, h->d_top_uniques, h->stream));
+        NK_CUDA(cudaMemcpyAsync(h->row_uniques.data(), h->d_top_uniques, n * sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
+        NK_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    h->ut.valid = false;  // not an exact table: nk_get_count must not answer from it
+    h->rows_valid = true;
+    return NK_OK;
+}
+
+int nk_uniques_begin(nk_counter* h, uint64_t top_n) {
+    if (!h) return fail(NK_ERR_BAD_ARG, "null handle");
+    NK_CUDA(cudaSetDevice(h->cfg.device));
+    return uniques_begin(h, top_n);
+}
+
+int nk_uniques_push(nk_counter* h, const uint8_t* bases, const uint64_t* offsets, uint64_t nseq) {
+    NK_TRY(validate_batch(h, bases, offsets, nseq));
+    if (!h->uniques_open) return fail(NK_ERR_STATE, "nk_uniques_push without nk_uniques_begin");
+    NK_CUDA(cudaSetDevice(h->cfg.device));
+    if (nseq > 0 && offsets[nseq] > 0 && !bases) return fail(NK_ERR_BAD_ARG, "null bases");
+    return uniques_host_batch(h, bases, nullptr, nullptr, offsets, nseq);
+}
+
+int nk_uniques_push_packed(nk_counter* h, const uint32_t* codes, const uint32_t* other, const uint64_t* offsets,
+                           uint64_t nseq) {
+    NK_TRY(validate_packed(h, codes, offsets, nseq));
+    if (!h->uniques_open) return fail(NK_ERR_STATE, "nk_uniques_push_packed without nk_uniques_begin");
+    NK_CUDA(cudaSetDevice(h->cfg.device));
+    return uniques_host_batch(h, nullptr, codes, other, offsets, nseq);
+}
+
+int nk_uniques_end(nk_counter* h) {
+    if (!h) return fail(NK_ERR_BAD_ARG, "null handle");
+    if (!h->uniques_open) return fail(NK_ERR_STATE, "nk_uniques_end without nk_uniques_begin");
+    NK_CUDA(cudaSetDevice(h->cfg.device));
+    return uniques_end(h);
+}
+
+int nk_set_file_uniques(nk_counter* h, uint64_t top_n) {
+    if (!h) return fail(NK_ERR_BAD_ARG, "null handle");
+    if (top_n > 2048) return fail(NK_ERR_BAD_ARG, "nk_set_file_uniques: top_n must be at most 2048");
+    h->file_uniques = top_n;
+    return NK_OK;
+}
+
 // Host-only: run the C++ record reader over a file and digest what it yields, so that the reader
 // (formats, compression sniffing, stop-at-first-malformed-record) can be checked without a device.
 int nk_debug_fastx_digest(const char* path, uint64_t* nrecords, uint64_t* nbases, uint64_t* fnv1a) {
@@ -2197,8 +2399,18 @@ int nk_process_file(nk_counter* h, const char* path, int streaming) {
     if (!h || !path) return fail(NK_ERR_BAD_ARG, "null argument");
     if (h->streaming) return fail(NK_ERR_STATE, "nk_process_file inside nk_stream_begin/end");
     std::string err;
-    int rc = nk::process_file(h, path, streaming != 0, &err);
+    int rc = nk::process_file(h, path, streaming != 0, &err, false);
     if (rc != NK_OK) return fail(rc, "%s", err.c_str());
+    if (h->file_uniques > 0 && !h->exact) {
+        // `uniques` of the top rows: read the file a second time, keeping only the windows of those neurons
+        NK_TRY(uniques_begin(h, h->file_uniques));
+        rc = nk::process_file(h, path, streaming != 0, &err, true);
+        if (rc != NK_OK) {
+            h->uniques_open = false;
+            return fail(rc, "%s", err.c_str());
+        }
+        NK_TRY(uniques_end(h));
+    }
     return NK_OK;
 }
 

@@ -3,8 +3,9 @@
 // Flag surface and result block of the reference binary (src/main.rs:10-25, :49-74):
 //   neurokmer --input/-i FILE [--k/-k 31] [--pool-size 1000000] [--canonical] [--streaming]
 // Additive flags with the reference's constants as defaults: --steps 1000 (spiking_hash.rs:70),
-// --top-n 20 (main.rs:50), --device 0, --exact (build the exact k-mer side table so that the
-// "unique k-mers colliding" column is computed; without it the column prints "n/a" — never a guess).
+// --top-n 20 (main.rs:50), --device 0.  The "unique k-mers colliding" column (kmer_per_neuron, main.rs:54-61)
+// is computed for the printed rows by a second read of the file (nk_set_file_uniques); --exact builds the
+// whole exact k-mer side table instead (O(windows) memory), --no-uniques skips the column ("n/a", never a guess).
 // LIF constants are the ones main.rs:37 hard-codes (threshold 1.0, leak 0.95, refractory 2, cost 1.0).
 #include <chrono>
 #include <cinttypes>
@@ -28,7 +29,8 @@ static void usage() {
             "      --steps <N>              LIF ticks [default: 1000]\n"
             "      --top-n <N>              rows of the result block [default: 20]\n"
             "      --device <ID>            CUDA device ordinal [default: 0]\n"
-            "      --exact                  build the exact k-mer table (uniques column, get_count)\n");
+            "      --exact                  build the exact k-mer table (uniques column by sort, get_count)\n"
+            "      --no-uniques             skip the second read of the file that fills the uniques column\n");
 }
 
 // Rust's `{}` for f64 prints the shortest representation that round-trips, without a
@@ -52,7 +54,7 @@ int main(int argc, char** argv) {
     nk_config cfg;
     nk_config_default(&cfg);
     uint64_t top_n = 20;
-    int streaming = 0, exact = 0, timing = 0;
+    int streaming = 0, exact = 0, timing = 0, no_uniques = 0;
     const auto T0 = std::chrono::steady_clock::now();
     auto since = [&]() { return std::chrono::duration<double>(std::chrono::steady_clock::now() - T0).count(); };
     for (int i = 1; i < argc; ++i) {
@@ -70,6 +72,7 @@ int main(int argc, char** argv) {
         else if (a == "--top-n") top_n = strtoull(val("--top-n"), nullptr, 10);
         else if (a == "--device") cfg.device = atoi(val("--device"));
         else if (a == "--exact") exact = 1;
+        else if (a == "--no-uniques") no_uniques = 1;
         else if (a == "--timing") timing = 1;  // phase wall times on stderr
         else if (a == "-h" || a == "--help") { usage(); return 0; }
         else { fprintf(stderr, "error: unexpected argument '%s'\n\n", a.c_str()); usage(); return 2; }
@@ -80,6 +83,10 @@ int main(int argc, char** argv) {
     if (nk_create(&cfg, &h) != NK_OK) { fprintf(stderr, "Error: %s\n", nk_last_error()); return 1; }
     if (timing) fprintf(stderr, "[timing] nk_create done at %.3f s\n", since());
     if (exact && nk_enable_exact_counts(h, 1) != NK_OK) { fprintf(stderr, "Error: %s\n", nk_last_error()); return 1; }
+    if (!exact && !no_uniques && top_n >= 1 && top_n <= 2048 && nk_set_file_uniques(h, top_n) != NK_OK) {
+        fprintf(stderr, "Error: %s\n", nk_last_error());
+        return 1;
+    }
     if (nk_process_file(h, input.c_str(), streaming) != NK_OK) {
         fprintf(stderr, "Error: %s\n", nk_last_error());  // the reference returns Err from main
         nk_destroy(h);

@@ -227,6 +227,12 @@ __device__ __forceinline__ void process_chunk(const CountParams& p, const Window
                 if (p.out_word) p.out_word[pos] = word;
                 if (p.out_idx) p.out_idx[pos] = idx;
             }
+        } else if (MODE == 4) {
+            // uniques pass: keep the words that map to a neuron of the filter (rare: a few rows of millions)
+            if (!bad && ((__ldg(p.filter + (idx >> 5)) >> (idx & 31u)) & 1u)) {
+                const unsigned long long slot = atomicAdd(p.words_cursor, 1ull);
+                if (slot < p.words_cap) p.words[slot] = word;
+            }
         } else {
             if (MODE == 2 && !bad) *wslot++ = word;
 #ifdef NK_EXP_NORED
@@ -420,6 +426,7 @@ static cudaError_t launch_count_c(const CountParams& p, int mode, cudaStream_t s
         case 0: return launch_count_cm<CANON, 0, PACKED>(p, s);
         case 1: return launch_count_cm<CANON, 1, PACKED>(p, s);
         case 2: return launch_count_cm<CANON, 2, PACKED>(p, s);
+        case 4: return launch_count_cm<CANON, 4, PACKED>(p, s);
         default: return launch_count_cm<CANON, 3, PACKED>(p, s);
     }
 }

@@ -112,6 +112,37 @@ cudaError_t exact_reserve_words(ExactTable& t, unsigned long long extra, cudaStr
     return cudaSuccess;
 }
 
+cudaError_t exact_grow_words(ExactTable& t, unsigned long long cap, unsigned long long keep, cudaStream_t s) {
+    if (!t.cursor) {
+        NKX(cudaMalloc(&t.cursor, 4 * sizeof(unsigned long long)));
+        NKX(cudaMemsetAsync(t.cursor, 0, 4 * sizeof(unsigned long long), s));
+    }
+    if (cap <= t.words_cap) return cudaSuccess;
+    unsigned long long* nw = nullptr;
+    NKX(cudaMalloc(&nw, cap * sizeof(unsigned long long)));
+    if (t.words) {
+        if (keep) NKX(cudaMemcpyAsync(nw, t.words, keep * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s));
+        NKX(cudaStreamSynchronize(s));
+        cudaFree(t.words);
+    }
+    t.words = nw;
+    t.words_cap = cap;
+    return cudaSuccess;
+}
+
+namespace {
+__global__ void filter_set_kernel(unsigned int* filter, const unsigned long long* __restrict__ idx, unsigned long long n) {
+    const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (i < n) atomicOr(filter + (idx[i] >> 5), 1u << (idx[i] & 31u));
+}
+}  // namespace
+
+cudaError_t launch_filter_set(unsigned int* filter, const unsigned long long* idx, unsigned long long n, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    filter_set_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(filter, idx, n);
+    return cudaGetLastError();
+}
+
 cudaError_t exact_clear(ExactTable& t, unsigned long long pool, bool tables_too, cudaStream_t s) {
     t.words_bound = 0;
     if (t.cursor) NKX(cudaMemsetAsync(t.cursor, 0, sizeof(unsigned long long), s));

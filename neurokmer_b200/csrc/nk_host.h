@@ -113,6 +113,6 @@ uint64_t host_pack_bases(const uint8_t* bases, uint64_t n, uint32_t* codes, uint
 int host_pack_body_available(int which);
 
 // whole-file driver behind nk_process_file (defined in nk_api.cu)
-int process_file(nk_counter* h, const char* path, bool streaming, std::string* err);
+int process_file(nk_counter* h, const char* path, bool streaming, std::string* err, bool ingest_only);
 
 }  // namespace nk

@@ -43,6 +43,11 @@ struct CountParams {
     // exact side table (MODE 2 instantiation only): every counted word is appended here
     unsigned long long* words;
     unsigned long long* words_cursor;
+    // uniques pass (MODE 4 instantiation only): nothing is counted; the words of the windows whose neuron
+    // has its bit set in `filter` (pool_size bits) are appended while the cursor stays below words_cap
+    // (the cursor keeps counting past it, so the host learns how much room a re-run needs)
+    const unsigned int* filter;
+    unsigned long long words_cap;
     // debug taps (EMIT instantiation only); any may be null
     unsigned long long* out_fwd;
     unsigned long long* out_rc;
@@ -70,7 +75,8 @@ inline unsigned long long count_bitmap_words(unsigned long long nbytes) {
 }
 
 // mode 0: count; 1: emit the debug taps instead of counting; 2: count and append words (exact side
-// table); 3: count with warp-level compaction of the valid window starts (short-read batches).
+// table); 3: count with warp-level compaction of the valid window starts (short-read batches);
+// 4: uniques pass (no counting: append the words that map to the neurons of `filter`).
 // The grid is persistent: min(ntiles, SMs x resident CTAs of the instantiation).
 cudaError_t launch_count(const CountParams& p, bool canonical, int mode, cudaStream_t s);
 
@@ -216,6 +222,9 @@ cudaError_t exact_lookup(const ExactTable& t, unsigned long long key, unsigned l
 cudaError_t exact_gather_uniques(const ExactTable& t, const unsigned long long* idx, unsigned long long n,
                                  unsigned int* out, cudaStream_t s);
 void exact_free(ExactTable& t);
+// uniques pass helpers: grow the word array to `cap` entries keeping the first `keep`; set filter bits
+cudaError_t exact_grow_words(ExactTable& t, unsigned long long cap, unsigned long long keep, cudaStream_t s);
+cudaError_t launch_filter_set(unsigned int* filter, const unsigned long long* idx, unsigned long long n, cudaStream_t s);
 
 // peak calibration (roofline denominators)
 cudaError_t launch_int_peak(int mode, unsigned int* out, int blocks, unsigned iters, cudaStream_t s);

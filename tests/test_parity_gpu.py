@@ -682,8 +682,9 @@ def test_cli_result_block(tmp_path, coracle):
     seqs = [random_dna(rng, n, 0.002, 0.01) for n in (400_000, 100, 250_000)]
     fa = str(tmp_path / "c.fa"); write_fasta(fa, seqs)
     k, pool = 21, 10_000
-    for streaming in (False, True):
-        args = [exe, "-i", fa, "-k", str(k), "--pool-size", str(pool), "--canonical", "--exact"] + (["--streaming"] if streaming else [])
+    # default: uniques of the printed rows by a second read of the file; --exact: the full exact table
+    for streaming, extra in ((False, ["--exact"]), (True, ["--exact"]), (False, []), (True, [])):
+        args = [exe, "-i", fa, "-k", str(k), "--pool-size", str(pool), "--canonical"] + extra + (["--streaming"] if streaming else [])
         out = subprocess.check_output(args, text=True)
         o = oracle_counter(k, pool)
         bases, offsets = flatten(seqs)
@@ -696,8 +697,8 @@ def test_cli_result_block(tmp_path, coracle):
         want += ["", f"Total spikes fired: {o.total_spikes}", f"Simulated energy used: {o.total_spikes}",
                  f"Neuron pool size used: {pool}", f"Streaming mode: {'true' if streaming else 'false'}"]
         assert out.splitlines() == want
-    # without --exact the column is "n/a", never a number
-    out = subprocess.check_output([exe, "-i", fa, "-k", "21", "--pool-size", "10000", "--canonical"], text=True)
+    # with --no-uniques the column is "n/a", never a number
+    out = subprocess.check_output([exe, "-i", fa, "-k", "21", "--pool-size", "10000", "--canonical", "--no-uniques"], text=True)
     assert "(n/a unique k-mers colliding)" in out
     # errors: missing file -> exit code 1 and a message on stderr (the reference returns Err from main)
     p = subprocess.run([exe, "-i", str(tmp_path / "nope.fa")], capture_output=True, text=True)
@@ -1262,3 +1263,69 @@ def test_peer_signalled_run_times_out_on_a_missing_rank(monkeypatch):
     c.reset(); c.stream_begin()
     with pytest.raises(NkError):
         c.dist_run()       # sticky until the ranks set up again
+
+
+# --- uniques of the top rows by a second pass (no exact table) ---------------------------------------
+@pytest.mark.parametrize("k,pool,canonical", [(21, 10_000, True), (31, 2_000_000, True), (15, 4096, False), (5, 7, True)])
+def test_uniques_pass_matches_exact_tables(coracle, k, pool, canonical):
+    """nk_uniques_begin/push/end: kmer_per_neuron (spiking_hash.rs:167-172) of the top rows from a second pass over the
+    same batches equals the oracle's table and the exact-table mode; ASCII and packed re-supply, several pushes.
+    pool 7: every window maps to a requested row, so the word array has to grow (> 2^20 matches)."""
+    from neurokmer_b200 import NkError, flatten, pack_bases
+    rng = np.random.default_rng(k * 7 + pool % 13)
+    seqs = [random_dna(rng, n, 0.003, 0.01) for n in (900_000, 100, 450_000, 20)]
+    b1, o1 = flatten(seqs[:2]); b2, o2 = flatten(seqs[2:])
+    _, _, uni = _oracle_tables(coracle, seqs, k, pool, canonical)
+    c = make(k, pool, canonical)
+    c.stream_begin(); c.stream_push(b1, o1); c.stream_push(b2, o2); c.stream_end()
+    n = min(20, pool)
+    plain = c.top_abundant_neurons(n)
+    assert all(r[2] is None for r in plain)
+    rows = c.top_uniques(n, [(b1, o1), (b2, o2)])
+    assert [r[:2] for r in rows] == [r[:2] for r in plain]
+    assert [r[2] for r in rows] == [int(uni[r[0]]) for r in rows]
+    assert [r[2] for r in c.top_abundant_neurons(min(5, n))] == [int(uni[r[0]]) for r in rows[:min(5, n)]]
+    # packed re-supply, one push
+    bases, offsets = flatten(seqs)
+    codes, other, _ = pack_bases(bases)
+    c.uniques_begin(n); c.uniques_push_packed(codes, other, offsets); c.uniques_end()
+    assert c.top_abundant_neurons(n) == rows
+    # the exact-table mode agrees
+    cx = make(k, pool, canonical); cx.enable_exact_counts(True)
+    cx.stream_begin(); cx.stream_push(bases, offsets); cx.stream_end()
+    assert cx.top_abundant_neurons(n) == rows
+    # a new job invalidates the rows; call-sequence errors
+    c.process_batch(b1, o1)
+    assert all(r[2] is None for r in c.top_abundant_neurons(n))
+    with pytest.raises(NkError):
+        c.uniques_push(b1, o1)
+    with pytest.raises(NkError):
+        c.uniques_end()
+    c.uniques_begin(n)
+    with pytest.raises(NkError):
+        c.uniques_begin(n)
+    c.uniques_end()
+    with pytest.raises(NkError):
+        c.get_count(0)  # the exact table is off: the second pass does not make get_count answerable
+
+
+def test_process_file_fills_uniques_by_second_read(tmp_path, coracle):
+    """nk_set_file_uniques: nk_process_file reads the file twice and the top rows carry `uniques`
+    (FASTA and gzip FASTQ; the serial reader and the small-window parallel reader)."""
+    import gzip
+    from neurokmer_b200.fastx import write_fasta, write_fastq
+    rng = np.random.default_rng(31)
+    seqs = [random_dna(rng, n, 0.002, 0.02) for n in (300_000, 61, 0, 200_000)]
+    fa, fq = str(tmp_path / "u.fa"), str(tmp_path / "u.fq")
+    write_fasta(fa, seqs); write_fastq(fq, seqs)
+    with open(fq, "rb") as f, gzip.open(fq + ".gz", "wb", compresslevel=1) as g:
+        g.write(f.read())
+    k, pool = 31, 50_000
+    _, _, uni = _oracle_tables(coracle, seqs, k, pool, True)
+    for path in (fa, fq + ".gz"):
+        c = make(k, pool); c.set_file_uniques(20)
+        c.process_file_streaming(path)
+        rows = c.top_abundant_neurons(20)
+        assert [r[2] for r in rows] == [int(uni[r[0]]) for r in rows]
+        c2 = make(k, pool); c2.process_file_streaming(path)
+        assert [r[:2] for r in c2.top_abundant_neurons(20)] == [r[:2] for r in rows]

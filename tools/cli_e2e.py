@@ -24,7 +24,7 @@ with open(path, "wb") as f:
             f.write(s[n // 60 * 60:].tobytes() + b"\n")
 print(f"wrote {os.path.getsize(path) / 1e6:.1f} MB in {time.time() - t0:.1f} s", flush=True)
 exe = os.path.join(ROOT, "neurokmer_b200", "neurokmer")
-for extra in ([], ["--exact"]):
+for extra in (["--no-uniques"], [], ["--exact"]):
     for rep in range(2):
         t0 = time.time()
         p = subprocess.run([exe, "-i", path, "-k", "31", "--pool-size", "2000000", "--canonical", "--streaming", "--timing"] + extra,

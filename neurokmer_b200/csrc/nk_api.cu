@@ -124,6 +124,7 @@ struct nk_counter {
     int cur_off = 0;
     // device-resident staged batch (nk_stage_reserve)
     DevBuf staged;
+    DevBuf zc;  // zero-copy pushes: just the invalid-start bitmap of the body (the bases stay in host memory)
     unsigned long long* staged_offsets = nullptr;
     unsigned long long staged_offsets_cap = 0;
 
@@ -199,6 +200,21 @@ int ensure_devbuf(DevBuf& b, unsigned long long nbytes) {
         NK_CUDA(cudaMalloc(&b.bases, need));
         b.bases_cap = need;
     }
+    const unsigned long long words = nk::count_bitmap_words(nbytes);
+    if (words > b.invalid_cap) {
+        if (b.invalid) cudaFree(b.invalid);
+        b.invalid = nullptr;
+        b.invalid_cap = 0;
+        NK_CUDA(cudaMalloc(&b.invalid, words * sizeof(unsigned int)));
+        b.invalid_cap = words;
+    }
+    if (!b.copy_done) NK_CUDA(cudaEventCreateWithFlags(&b.copy_done, cudaEventDisableTiming));
+    if (!b.compute_done) NK_CUDA(cudaEventCreateWithFlags(&b.compute_done, cudaEventDisableTiming));
+    return NK_OK;
+}
+
+// only the invalid-start bitmap (+ events) of a chunk: the zero-copy paths read the bases from host memory
+int ensure_bitmap_only(DevBuf& b, unsigned long long nbytes) {
     const unsigned long long words = nk::count_bitmap_words(nbytes);
     if (words > b.invalid_cap) {
         if (b.invalid) cudaFree(b.invalid);
@@ -373,21 +389,29 @@ int count_host_batch(nk_counter* h, const uint8_t* bases, const uint64_t* offset
     NK_CUDA(cudaMemcpyAsync(d_offsets, offsets, (nseq + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, h->copy_stream));
     h->last.h2d_bytes += (nseq + 1) * sizeof(uint64_t) + nbytes;
 
-    // EXPERIMENT (NK_ZEROCOPY=1): count whole tiles straight out of pinned, device-mapped host memory
-    // (the kernel's TMA bulk loads cross PCIe themselves; no staging copy), H2D only for the ragged end.
+    // Zero-copy body: when the batch lives in pinned, device-mapped host memory (nk_host_alloc, cudaHostAlloc /
+    // cudaHostRegister) the count kernel's TMA bulk loads read whole tiles straight across PCIe — one launch
+    // per < 2^32 starts, no staging copy, no per-chunk pipeline; H2D only for the ragged end.  PCIe binds either
+    // way for ASCII (113 MB: 2.42 ms in place vs 2.46 ms staged, and a tighter spread); NK_ZEROCOPY=0 forces the
+    // staged pipeline, which pageable memory always takes.
     unsigned long long zc_body = 0;
     const char* zc_env = getenv("NK_ZEROCOPY");
-    if (zc_env && atoi(zc_env) != 0 && nbytes >= 4 * (unsigned long long)nk::COUNT_TILE && ((uintptr_t)bases & 15) == 0) {
+    // (the file driver double-buffers its own pinned batches and must not block on the kernels: wait_copies == false)
+    if (wait_copies && (!zc_env || atoi(zc_env) != 0) && nbytes >= 4 * (unsigned long long)nk::COUNT_TILE &&
+        ((uintptr_t)bases & 15) == 0) {
         cudaPointerAttributes at{};
         if (cudaPointerGetAttributes(&at, bases) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
             zc_body = (nbytes - nk::COUNT_HALO) / nk::COUNT_TILE * nk::COUNT_TILE;
-            NK_TRY(ensure_devbuf(h->staged, zc_body));
-            NK_CUDA(cudaEventRecord(h->buf[0].copy_done ? h->buf[0].copy_done : h->offsets_done[ob], h->copy_stream));
-            cudaEvent_t off_ready = h->buf[0].copy_done ? h->buf[0].copy_done : h->offsets_done[ob];
-            NK_CUDA(cudaStreamWaitEvent(h->stream, off_ready, 0));  // offsets are on the device
-            DevBuf view = h->staged;
-            view.bases = (unsigned char*)at.devicePointer;
-            NK_TRY(count_chunk(h, view, d_offsets, 0, nseq, 0, zc_body, zc_body, pe));
+            const unsigned long long slice = (0xFFFFFFFFull / nk::COUNT_TILE - 1) * nk::COUNT_TILE;
+            NK_TRY(ensure_bitmap_only(h->zc, std::min(zc_body, slice)));
+            NK_CUDA(cudaEventRecord(h->zc.copy_done, h->copy_stream));  // the offsets are on the device
+            NK_CUDA(cudaStreamWaitEvent(h->stream, h->zc.copy_done, 0));
+            for (unsigned long long c0 = 0; c0 < zc_body; c0 += slice) {  // < 2^32 window starts per launch
+                const unsigned long long n = std::min(slice, zc_body - c0);
+                DevBuf view = h->zc;
+                view.bases = static_cast<unsigned char*>(at.devicePointer) + c0;
+                NK_TRY(count_chunk(h, view, d_offsets, 0, nseq, c0, n, n, pe));
+            }
         } else {
             cudaGetLastError();
         }
@@ -480,12 +504,12 @@ int count_host_batch_packed(nk_counter* h, const uint32_t* codes, const uint32_t
         if (ok) {
             zc_body = (nbases - 128) / nk::COUNT_TILE * nk::COUNT_TILE;
             const unsigned long long slice = (0xFFFFFFFFull / nk::COUNT_TILE - 1) * nk::COUNT_TILE;
-            NK_TRY(ensure_devbuf_packed(h->staged, std::min(zc_body, slice), false));
-            NK_CUDA(cudaEventRecord(h->staged.copy_done, h->copy_stream));  // the offsets are on the device
-            NK_CUDA(cudaStreamWaitEvent(h->stream, h->staged.copy_done, 0));
+            NK_TRY(ensure_bitmap_only(h->zc, std::min(zc_body, slice)));
+            NK_CUDA(cudaEventRecord(h->zc.copy_done, h->copy_stream));  // the offsets are on the device
+            NK_CUDA(cudaStreamWaitEvent(h->stream, h->zc.copy_done, 0));
             for (unsigned long long c0 = 0; c0 < zc_body; c0 += slice) {
                 const unsigned long long n = std::min(slice, zc_body - c0);
-                DevBuf view = h->staged;
+                DevBuf view = h->zc;
                 view.codes = static_cast<unsigned char*>(ac.devicePointer) + c0 / 4;
                 view.other = other ? static_cast<unsigned char*>(ao.devicePointer) + c0 / 8 : nullptr;
                 view.has_other = other != nullptr;
@@ -1414,7 +1438,7 @@ int nk_destroy(nk_counter* h) {
     cudaFree(h->d_merged);
     nk::exact_free(h->xt);
     cudaFree(h->d_top_uniques);
-    free_devbuf(h->buf[0]); free_devbuf(h->buf[1]); free_devbuf(h->staged);
+    free_devbuf(h->buf[0]); free_devbuf(h->buf[1]); free_devbuf(h->staged); free_devbuf(h->zc);
     for (int i = 0; i < 2; ++i) { cudaFree(h->d_offsets2[i]); if (h->offsets_done[i]) cudaEventDestroy(h->offsets_done[i]); }
     cudaFree(h->staged_offsets);
     for (cudaEvent_t e : h->evpool) cudaEventDestroy(e);

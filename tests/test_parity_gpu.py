@@ -1329,3 +1329,38 @@ def test_process_file_fills_uniques_by_second_read(tmp_path, coracle):
         assert [r[2] for r in rows] == [int(uni[r[0]]) for r in rows]
         c2 = make(k, pool); c2.process_file_streaming(path)
         assert [r[:2] for r in c2.top_abundant_neurons(20)] == [r[:2] for r in rows]
+
+
+def test_ascii_zero_copy_from_pinned_memory(coracle, monkeypatch):
+    """ASCII batches in pinned (device-mapped) host memory are read in place by the count kernel (whole tiles;
+    the ragged end is staged); pageable memory and NK_ZEROCOPY=0 take the staged pipeline.  Same results."""
+    from neurokmer_b200 import PinnedBuffer, flatten
+    rng = np.random.default_rng(23)
+    k, pool = 31, 100_000
+    seqs = [random_dna(rng, n, 0.004, 0.01, 0.001) for n in (700_001, 33, 90_000, 1_234_567, 150, 150, 20)]
+    bases, offsets = flatten(seqs)
+    pb = PinnedBuffer(bases.size)
+    pb.array[:] = bases
+    o = oracle_counter(k, pool)
+    o.process_streaming([(bases, offsets)])
+    for zc in ("1", "0"):
+        monkeypatch.setenv("NK_ZEROCOPY", zc)
+        for src in (pb.array, bases):
+            c = make(k, pool)
+            c.stream_begin(); c.stream_push(src, offsets); c.stream_end()
+            assert_state_equal(c, o)
+            assert c.timings()["kmers"] == sum(max(0, len(s) - k + 1) for s in seqs)
+    # unaligned view of pinned memory (not 16-byte aligned): staged path, same answer
+    monkeypatch.setenv("NK_ZEROCOPY", "1")
+    pb2 = PinnedBuffer(bases.size + 16)
+    pb2.array[3:3 + bases.size] = bases
+    c = make(k, pool)
+    c.stream_begin(); c.stream_push(pb2.array[3:3 + bases.size], offsets); c.stream_end()
+    assert_state_equal(c, o)
+    # short-read batch in pinned memory (compaction mode of the kernel over the zero-copy body)
+    reads = [random_dna(rng, 150, 0.01, 0.0) for _ in range(4000)]
+    rb, ro = flatten(reads)
+    pr = PinnedBuffer(rb.size); pr.array[:] = rb
+    c = make(k, pool); c.process_batch(pr.array, ro)
+    exp, _ = coracle.accumulate(rb, ro, k, pool, True, threads=4)
+    np.testing.assert_array_equal(c.currents(), exp)

@@ -155,7 +155,12 @@ def reference_arm(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    sample = int(os.environ.get("NK_REF_SAMPLE_BASES", str(min(NBASES, 8_000_000 * threads))))
+    # bounded sample: the whole --steps K --warmup W run should end within a few minutes.  The LIF + top-N part
+    # (~0.2 s on 16 cores) is always run in full; the accumulate part is sized from a conservative rate of
+    # 15 Mbase/s per thread so that (K + W) steps take about 150 s, and never more than the whole workload.
+    budget_s = max(0.05, 150.0 / max(1, args.steps + args.warmup) - 0.2)
+    sample = int(os.environ.get("NK_REF_SAMPLE_BASES", str(min(NBASES, 8_000_000 * threads, int(15e6 * threads * budget_s)))))
+    sample = max(sample, 1_000_000)
     from oracle.synth import synth_bases
     bases = synth_bases(SEED, 0, min(sample, NBASES), 3)
     vals = []

@@ -2306,6 +2306,9 @@ uint64_t nk_pack_kmer(const uint8_t* kmer, uint64_t len) { return nk::host_pack_
 static int uniques_begin(nk_counter* h, uint64_t top_n) {
     if (h->streaming) return fail(NK_ERR_STATE, "nk_uniques_begin inside nk_stream_begin/end");
     if (h->uniques_open) return fail(NK_ERR_STATE, "nk_uniques_begin called twice");
+    if (h->dist_world && h->last.lif_path == 4)
+        return fail(NK_ERR_UNSUPPORTED, "uniques pass after a sharded-pool job: every rank holds only its shard of the input "
+                    "(the per-rank word sets are not merged)");
     const uint64_t n = std::min<uint64_t>(top_n, h->cfg.pool_size);
     if (n == 0 || n > 2048) return fail(NK_ERR_BAD_ARG, "nk_uniques_begin: top_n must be in 1..2048");
     std::vector<nk_top_entry> rows(n);

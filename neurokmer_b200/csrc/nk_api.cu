@@ -68,6 +68,8 @@ struct DevBuf {
     unsigned char* other = nullptr;
     unsigned long long other_cap = 0;
     bool has_other = false;  // this chunk's `other` array was supplied
+    // zero-copy views: readable bytes (multiples of 16) of bases/codes and other from the view's start; 0 = padded
+    unsigned long long bases_bytes = 0, other_bytes = 0;
 };
 
 struct PhaseEvents {
@@ -322,6 +324,8 @@ int count_chunk(nk_counter* h, DevBuf& b, const unsigned long long* d_offsets, u
     p.bases = packed ? b.codes : b.bases;
     p.other = packed && b.has_other ? b.other : nullptr;
     p.packed = packed ? 1 : 0;
+    p.bases_bytes = b.bases_bytes;
+    p.other_bytes = b.other_bytes;
     p.invalid = b.invalid;
     p.acc = h->acc;
     p.tile_counter = h->tile_counter;
@@ -391,7 +395,8 @@ int count_host_batch(nk_counter* h, const uint8_t* bases, const uint64_t* offset
 
     // Zero-copy body: when the batch lives in pinned, device-mapped host memory (nk_host_alloc, cudaHostAlloc /
     // cudaHostRegister) the count kernel's TMA bulk loads read whole tiles straight across PCIe — one launch
-    // per < 2^32 starts, no staging copy, no per-chunk pipeline; H2D only for the ragged end.  PCIe binds either
+    // per < 2^32 starts, no staging copy, no per-chunk pipeline (the last tile's copy is clamped to the end of the
+    // array, so nothing at all is staged).  PCIe binds either
     // way for ASCII (113 MB: 2.42 ms in place vs 2.46 ms staged, and a tighter spread); NK_ZEROCOPY=0 forces the
     // staged pipeline, which pageable memory always takes.
     unsigned long long zc_body = 0;
@@ -401,7 +406,7 @@ int count_host_batch(nk_counter* h, const uint8_t* bases, const uint64_t* offset
         ((uintptr_t)bases & 15) == 0) {
         cudaPointerAttributes at{};
         if (cudaPointerGetAttributes(&at, bases) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
-            zc_body = (nbytes - nk::COUNT_HALO) / nk::COUNT_TILE * nk::COUNT_TILE;
+            zc_body = nbytes;  // the whole batch: the last tile's copy is clamped to the end of the array
             const unsigned long long slice = (0xFFFFFFFFull / nk::COUNT_TILE - 1) * nk::COUNT_TILE;
             NK_TRY(ensure_bitmap_only(h->zc, std::min(zc_body, slice)));
             NK_CUDA(cudaEventRecord(h->zc.copy_done, h->copy_stream));  // the offsets are on the device
@@ -410,6 +415,7 @@ int count_host_batch(nk_counter* h, const uint8_t* bases, const uint64_t* offset
                 const unsigned long long n = std::min(slice, zc_body - c0);
                 DevBuf view = h->zc;
                 view.bases = static_cast<unsigned char*>(at.devicePointer) + c0;
+                view.bases_bytes = (nbytes - c0 + 15) / 16 * 16;
                 NK_TRY(count_chunk(h, view, d_offsets, 0, nseq, c0, n, n, pe));
             }
         } else {
@@ -491,8 +497,8 @@ int count_host_batch_packed(nk_counter* h, const uint32_t* codes, const uint32_t
     // Zero-copy body: when the packed arrays live in pinned, device-mapped host memory (nk_host_alloc,
     // cudaHostAlloc/Register) the count kernel's TMA bulk loads read the tiles straight across PCIe —
     // one launch, no staging copy, no per-chunk pipeline bubbles (3/8 B per base keeps PCIe at the
-    // kernel's own pace: 113 Mbase end to end 1.44 ms staged -> 1.11 ms, profiles/r01_bench.md).  Only whole tiles whose halo stays inside
-    // the host arrays are read this way; the ragged end takes the staged path below.  NK_ZEROCOPY=0
+    // kernel's own pace: 113 Mbase end to end 1.44 ms staged -> 1.11 ms, profiles/r01_bench.md).  The last tile's copies
+    // are clamped to the ends of the host arrays, so the whole batch is read this way.  NK_ZEROCOPY=0
     // forces the staged path.
     unsigned long long zc_body = 0;
     const char* zc_env = getenv("NK_ZEROCOPY");
@@ -502,7 +508,7 @@ int count_host_batch_packed(nk_counter* h, const uint32_t* codes, const uint32_t
         bool ok = cudaPointerGetAttributes(&ac, codes) == cudaSuccess && ac.type == cudaMemoryTypeHost && ac.devicePointer;
         if (ok && other) ok = cudaPointerGetAttributes(&ao, other) == cudaSuccess && ao.type == cudaMemoryTypeHost && ao.devicePointer;
         if (ok) {
-            zc_body = (nbases - 128) / nk::COUNT_TILE * nk::COUNT_TILE;
+            zc_body = nbases;  // the whole batch: the last tile's copies are clamped to the ends of the arrays
             const unsigned long long slice = (0xFFFFFFFFull / nk::COUNT_TILE - 1) * nk::COUNT_TILE;
             NK_TRY(ensure_bitmap_only(h->zc, std::min(zc_body, slice)));
             NK_CUDA(cudaEventRecord(h->zc.copy_done, h->copy_stream));  // the offsets are on the device
@@ -513,9 +519,11 @@ int count_host_batch_packed(nk_counter* h, const uint32_t* codes, const uint32_t
                 view.codes = static_cast<unsigned char*>(ac.devicePointer) + c0 / 4;
                 view.other = other ? static_cast<unsigned char*>(ao.devicePointer) + c0 / 8 : nullptr;
                 view.has_other = other != nullptr;
+                view.bases_bytes = ((nbases + 15) / 16 * 4 - c0 / 4 + 15) / 16 * 16;
+                view.other_bytes = ((nbases + 31) / 32 * 4 - c0 / 8 + 15) / 16 * 16;
                 NK_TRY(count_chunk(h, view, d_offsets, 0, nseq, c0, n, n, pe, true));
             }
-            h->last.h2d_bytes += zc_body / 4 + (other ? zc_body / 8 : 0);
+            h->last.h2d_bytes += (nbases + 15) / 16 * 4 + (other ? (nbases + 31) / 32 * 4 : 0);
         } else {
             cudaGetLastError();  // pageable memory: not an error, take the staged path
         }

@@ -62,16 +62,25 @@ __device__ __forceinline__ WindowConsts make_window_consts(unsigned k) {
 template <bool PACKED>
 __device__ __forceinline__ void issue_tile(unsigned char* stage, unsigned long long* bar,
                                            const CountParams& p, unsigned long long tile) {
+    // bytes of a tile copy that starts at `off`, clamped to the caller's array when it has a known end
+    auto clamp = [](unsigned full, unsigned long long off, unsigned long long total) -> unsigned {
+        return (total != 0 && off + full > total) ? (unsigned)(total - off) : full;
+    };
     if constexpr (PACKED) {
         const bool has_other = p.other != nullptr;
-        mbar_expect_tx(bar, kPkCodes + kBitsPerStage + (has_other ? kPkOther : 0));
-        tma_load_1d(stage, p.bases + tile * (COUNT_TILE / 4), kPkCodes, bar);
-        if (has_other) tma_load_1d(stage + kPkCodes, p.other + tile * (COUNT_TILE / 8), kPkOther, bar);
+        const unsigned long long coff = tile * (COUNT_TILE / 4), ooff = tile * (COUNT_TILE / 8);
+        const unsigned cb = clamp(kPkCodes, coff, p.bases_bytes);
+        const unsigned ob = has_other ? clamp(kPkOther, ooff, p.other_bytes) : 0u;
+        mbar_expect_tx(bar, cb + kBitsPerStage + ob);
+        tma_load_1d(stage, p.bases + coff, cb, bar);
+        if (has_other) tma_load_1d(stage + kPkCodes, p.other + ooff, ob, bar);
         tma_load_1d(stage + kPkCodes + kPkOther, (const unsigned char*)p.invalid + tile * kBitsPerStage,
                     kBitsPerStage, bar);
     } else {
-        mbar_expect_tx(bar, kBytesPerStage + kBitsPerStage);
-        tma_load_1d(stage, p.bases + tile * COUNT_TILE, kBytesPerStage, bar);
+        const unsigned long long boff = tile * COUNT_TILE;
+        const unsigned bb = clamp(kBytesPerStage, boff, p.bases_bytes);
+        mbar_expect_tx(bar, bb + kBitsPerStage);
+        tma_load_1d(stage, p.bases + boff, bb, bar);
         tma_load_1d(stage + kBytesPerStage, (const unsigned char*)p.invalid + tile * kBitsPerStage,
                     kBitsPerStage, bar);
     }

@@ -33,6 +33,12 @@ struct CountParams {
                                   // packed != 0: the 2-bit code words, readable up to ntiles*TILE/4 + 16
     const unsigned char* other;   // packed only: `other` bits, readable up to ntiles*TILE/8 + 16; may be null
     int packed;                   // 0: ASCII bases, 1: pre-packed input (include/neurokmer.h, "nk2" layout)
+    // Readable bytes of `bases` / `other`, multiples of 16; 0 = padded device buffers, every tile copy is in
+    // bounds.  Set for zero-copy input (the caller's host arrays end where they end): the last tile's bulk
+    // copies are clamped to them.  A 16-byte aligned chunk never straddles a page, so rounding the array size
+    // up to 16 stays inside the page that holds its last byte.
+    unsigned long long bases_bytes;
+    unsigned long long other_bytes;
     const unsigned int* invalid;  // bit p set => no window starts at p; ntiles*TILE/32 words (+pad)
     unsigned int* acc;            // pool_size u32 batch accumulators
     unsigned int* tile_counter;   // dynamic tile scheduler cursor (zeroed before launch)

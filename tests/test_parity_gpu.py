@@ -1364,3 +1364,27 @@ def test_ascii_zero_copy_from_pinned_memory(coracle, monkeypatch):
     c = make(k, pool); c.process_batch(pr.array, ro)
     exp, _ = coracle.accumulate(rb, ro, k, pool, True, threads=4)
     np.testing.assert_array_equal(c.currents(), exp)
+
+
+def test_zero_copy_ragged_ends(coracle):
+    """Zero-copy input whose end falls anywhere relative to a tile / a 16-byte line: the last tile's bulk copies
+    are clamped to the end of the caller's pinned array (exact-size allocations), ASCII and packed."""
+    from neurokmer_b200 import PinnedBuffer, flatten, pack_bases
+    rng = np.random.default_rng(29)
+    k, pool = 31, 65536
+    T = 4096
+    for n in (4 * T, 4 * T + 1, 4 * T + 15, 4 * T + 16, 4 * T + 17, 5 * T - 1, 5 * T + 31, 5 * T + 33, 6 * T + 64, 7 * T + 127, 7 * T + 129,
+              16 * T + 4095):
+        s = random_dna(rng, n, 0.01, 0.0)
+        b, o = flatten([s[: n // 3], s[n // 3:]])
+        exp, _ = coracle.accumulate(b, o, k, pool, True, threads=2)
+        pa = PinnedBuffer(n); pa.array[:] = b
+        c = make(k, pool); c.process_batch(pa.array, o)
+        np.testing.assert_array_equal(c.currents(), exp, err_msg=f"ASCII n={n}")
+        pc = PinnedBuffer(4 * ((n + 15) // 16), np.uint32); po = PinnedBuffer(4 * ((n + 31) // 32), np.uint32)
+        pack_bases(b, out_codes=pc.array, out_other=po.array)
+        c = make(k, pool); c.process_batch_packed(pc.array, po.array, o)
+        np.testing.assert_array_equal(c.currents(), exp, err_msg=f"packed n={n}")
+        c = make(k, pool, False); c.process_batch_packed(pc.array, po.array, o)
+        exp_nc, _ = coracle.accumulate(b, o, k, pool, False, threads=2)
+        np.testing.assert_array_equal(c.currents(), exp_nc, err_msg=f"packed non-canonical n={n}")

@@ -87,7 +87,8 @@ typedef struct nk_timings {
     uint64_t launches;   /* kernels launched by the call */
     uint64_t h2d_bytes;  /* bytes copied host→device by the call */
     uint64_t d2h_bytes;  /* bytes copied device→host by the call */
-    int32_t  lif_path;   /* 0 none, 1 direct simulation, 2 per-count table (uniform fresh state) */
+    int32_t  lif_path;   /* 0 none, 1 direct simulation, 2 per-count table (uniform fresh state), 3 table fused with
+                          * top-N, 4 sharded-pool slice kernel, 5 memoised (one simulation per distinct state+count) */
     int32_t  _pad;
     uint64_t topn_launches; /* kernels launched by the last nk_top_n */
 } nk_timings;
@@ -234,8 +235,10 @@ NK_API int nk_copy_spike_counts(nk_counter* h, uint64_t* out /* pool_size */);
 NK_API int nk_copy_voltages(nk_counter* h, float* out /* pool_size */);
 NK_API int nk_copy_refractory(nk_counter* h, uint32_t* out /* pool_size */);
 NK_API int nk_last_timings(const nk_counter* h, nk_timings* out);
-/* LIF path selection for tests: 0 = automatic (per-count table while every neuron is
- * still in its initial state, direct simulation otherwise), 1 = always direct. */
+/* LIF path selection for tests: 0 = automatic (per-count table while every neuron is still in its
+ * initial state; afterwards one simulation per distinct (state, count) key — "memoised" — where the
+ * parameters allow it, else one per neuron), 1 = always one simulation per neuron (direct),
+ * 2 = never the per-count table (memoised even from the initial state). */
 NK_API int nk_debug_set_lif_path(nk_counter* h, int mode);
 
 /* Roofline denominators measured on this device (micro-kernels, CUDA events, best of 3):

@@ -95,6 +95,8 @@ struct nk_counter {
     unsigned int* tile_counter = nullptr;
     unsigned long long* h_scalars = nullptr;  // pinned mirror
 
+    // carried-state LIF by memoisation (allocated at first use)
+    nk::LifMemo memo{};
     // LIF per-count table
     nk::LifTable table{};
     unsigned long long table_cap = 0;
@@ -698,7 +700,7 @@ int ensure_table(nk_counter* h, unsigned long long table_n, cudaStream_t on) {
 }
 
 bool table_path_ok(const nk_counter* h, unsigned long long* table_n) {
-    if (!h->fresh || h->force_direct || h->cfg.steps == 0 || !std::isfinite(h->cfg.threshold) || !std::isfinite(h->cfg.leak)) return false;
+    if (!h->fresh || h->force_direct != 0 || h->cfg.steps == 0 || !std::isfinite(h->cfg.threshold) || !std::isfinite(h->cfg.leak)) return false;
     const unsigned long long sat = saturation_count(h->cfg);
     if (sat >= (1ull << 20)) return false;
     *table_n = sat + 1;
@@ -787,9 +789,29 @@ int simulate(nk_counter* h, bool skip_zero, bool with_topn = false) {
             h->last.lif_path = 2;
         }
     } else {
-        NK_CUDA(nk::launch_lif(p, h->stream));
-        ++h->last.launches;
-        h->last.lif_path = 1;
+        // carried (or forced non-table) state: one simulation per distinct (state, count) key when the parameters
+        // allow the saturation clamp (leak >= 0), else one per neuron
+        const unsigned long long sat = saturation_count(h->cfg);
+        const bool memo_ok = h->force_direct != 1 && std::isfinite(h->cfg.threshold) && std::isfinite(h->cfg.leak) &&
+                             h->cfg.leak >= 0.0f && !std::signbit(h->cfg.leak) && sat < (1ull << 21) - 1 &&
+                             (h->force_direct == 2 || h->cfg.pool_size >= (1ull << 18));  // small pools: direct is as fast
+        if (memo_ok) {
+            if (!h->memo.keys) {
+                NK_CUDA(cudaMalloc(&h->memo.keys, nk::LIF_MEMO_SLOTS * sizeof(unsigned long long)));
+                NK_CUDA(cudaMalloc(&h->memo.dense, nk::LIF_MEMO_SLOTS / 2 * sizeof(unsigned int)));
+                NK_CUDA(cudaMalloc(&h->memo.res_v, nk::LIF_MEMO_SLOTS * sizeof(float)));
+                NK_CUDA(cudaMalloc(&h->memo.res_r, nk::LIF_MEMO_SLOTS * sizeof(unsigned int)));
+                NK_CUDA(cudaMalloc(&h->memo.res_f, nk::LIF_MEMO_SLOTS * sizeof(unsigned int)));
+                NK_CUDA(cudaMalloc(&h->memo.slot_of, h->cfg.pool_size * sizeof(unsigned int)));
+                NK_CUDA(cudaMalloc(&h->memo.ctrl, 4 * sizeof(unsigned long long)));
+            }
+            NK_CUDA(nk::launch_lif_memo(p, h->memo, sat, h->stream, &h->last.launches));
+            h->last.lif_path = 5;
+        } else {
+            NK_CUDA(nk::launch_lif(p, h->stream));
+            ++h->last.launches;
+            h->last.lif_path = 1;
+        }
     }
     if (p.zero_state) h->lazy_zero = false;
     if (fold_mode) {
@@ -1439,6 +1461,8 @@ int nk_destroy(nk_counter* h) {
     cudaFree(h->post_zero); cudaFree(h->d_pack);
     if (h->h_pack) cudaFreeHost(h->h_pack);
     if (h->h_top) cudaFreeHost(h->h_top);
+    cudaFree(h->memo.keys); cudaFree(h->memo.dense); cudaFree(h->memo.res_v); cudaFree(h->memo.res_r);
+    cudaFree(h->memo.res_f); cudaFree(h->memo.slot_of); cudaFree(h->memo.ctrl);
     nk::exact_free(h->ut);
     cudaFree(h->d_filter);
     cudaFree(h->d_rows);
@@ -1910,7 +1934,7 @@ int nk_last_timings(const nk_counter* h, nk_timings* out) {
 
 int nk_debug_set_lif_path(nk_counter* h, int mode) {
     if (!h) return fail(NK_ERR_BAD_ARG, "null handle");
-    if (mode != 0 && mode != 1) return fail(NK_ERR_BAD_ARG, "mode must be 0 or 1");
+    if (mode < 0 || mode > 2) return fail(NK_ERR_BAD_ARG, "mode must be 0, 1 or 2");
     h->force_direct = mode;
     return NK_OK;
 }

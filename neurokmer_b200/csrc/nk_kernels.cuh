@@ -125,6 +125,26 @@ struct LifTable {
 };
 cudaError_t launch_lif_table_build(const LifParams& p, const LifTable& t, unsigned long long table_n, cudaStream_t s);
 cudaError_t launch_lif_table_apply(const LifParams& p, const LifTable& t, unsigned long long table_n, cudaStream_t s);
+// Carried-state fast path: memoised simulation.  A neuron's evolution over a call depends only on
+// (voltage, refractory ticks, count): after a fresh job the state is itself a function of the first
+// count, so a pool of millions of neurons holds only a few thousand distinct (state, count) keys.  The keys
+// are deduplicated in a device hash set, each distinct key is simulated ONCE, and every neuron looks its
+// result up.  If the pool turns out to be diverse (more than LIF_MEMO_SLOTS/2 distinct keys) nothing is
+// applied and the direct kernel — launched behind it with `only_if` set — does the work instead.
+constexpr unsigned long long LIF_MEMO_SLOTS = 1ull << 20;
+struct LifMemo {
+    unsigned long long* keys;      // LIF_MEMO_SLOTS, all-ones = empty
+    unsigned int* dense;           // LIF_MEMO_SLOTS / 2: occupied slots, compacted
+    float* res_v;                  // per slot
+    unsigned int* res_r;
+    unsigned int* res_f;
+    unsigned int* slot_of;         // pool entries: the neuron's slot (all-ones: neuron skipped)
+    unsigned long long* ctrl;      // [0] distinct keys, [1] overflow flag, [2] dense cursor
+};
+// counts >= sat share one trajectory (needs leak >= 0: see nk_lif.cu); requires p.period < 2^31, sat < 2^21
+cudaError_t launch_lif_memo(const LifParams& p, const LifMemo& m, unsigned long long sat, cudaStream_t s, uint64_t* launches);
+// the direct kernel, running only if *only_if != 0 (device-side fallback of the memo path; p.fold_mode must be 0)
+cudaError_t launch_lif_if(const LifParams& p, const unsigned long long* only_if, cudaStream_t s);
 // one LIF tick per neuron with the raw count as input; currents zeroed (process_sequence)
 cudaError_t launch_lif_single_tick(const LifParams& p, unsigned long long* currents_rw, cudaStream_t s);
 

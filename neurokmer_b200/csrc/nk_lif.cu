@@ -123,7 +123,8 @@ __device__ __forceinline__ void block_totals(unsigned long long fired, unsigned 
     }
 }
 
-__global__ void __launch_bounds__(LIF_THREADS) lif_kernel(const LifParams p) {
+__global__ void __launch_bounds__(LIF_THREADS) lif_kernel(const LifParams p, const unsigned long long* only_if) {
+    if (only_if && *only_if == 0ull) return;  // device-side fallback of the memo path: nothing to do
     const unsigned long long i = blockIdx.x * (unsigned long long)LIF_THREADS + threadIdx.x;
     unsigned long long fired = 0, total = 0;
     if (i < p.pool) {
@@ -182,6 +183,86 @@ __global__ void __launch_bounds__(LIF_THREADS) lif_table_apply_kernel(const LifP
     block_totals(fired, total, p.total_new, p.max_spikes);
 }
 
+// ---- carried-state fast path: memoised simulation --------------------------------------------------
+// Key = (state, clamped count) in 54 bits.  State: the invariant above (r > 0 implies v == 0) makes it either a
+// voltage (r == 0) or a refractory count (v == 0): 33 bits.  Count: clamped to `sat`, the first count whose input
+// current reaches the threshold — with leak >= 0 the voltage is never negative, so for such a count
+// fl(fl(v*leak) + I) >= I >= thr on EVERY active tick whatever v is: all saturating counts follow one
+// trajectory from any reachable state (the argument of the fresh-state table, extended to carried state).
+constexpr unsigned long long MEMO_EMPTY = ~0ull;
+constexpr unsigned int MEMO_NONE = 0xFFFFFFFFu;
+
+__device__ __forceinline__ unsigned long long memo_key(float v, unsigned r, unsigned long long c) {
+    const unsigned long long state = r ? ((1ull << 32) | r) : (unsigned long long)__float_as_uint(v);
+    return (state << 21) | c;
+}
+
+__global__ void __launch_bounds__(LIF_THREADS) lif_memo_insert_kernel(const LifParams p, const LifMemo m, unsigned long long sat) {
+    const unsigned long long i = blockIdx.x * (unsigned long long)LIF_THREADS + threadIdx.x;
+    if (i >= p.pool) return;
+    const unsigned long long count = load_count(p, i);  // folds the batch accumulators in (once: the fallback must not)
+    if (p.skip_zero && count == 0) {
+        m.slot_of[i] = MEMO_NONE;
+        return;
+    }
+    const unsigned long long key = memo_key(p.v[i], p.r[i], count < sat ? count : sat);
+    unsigned long long slot = splitmix64(key) & (LIF_MEMO_SLOTS - 1);
+    for (unsigned long long probe = 0; probe < LIF_MEMO_SLOTS; ++probe) {
+        if (*reinterpret_cast<volatile unsigned long long*>(m.ctrl + 1)) break;  // already given up: do not fill the table
+        // most neurons find their key already present: a plain load first keeps them off the atomic unit
+        unsigned long long seen = *reinterpret_cast<volatile unsigned long long*>(m.keys + slot);
+        if (seen == key) break;
+        if (seen == MEMO_EMPTY) seen = atomicCAS(m.keys + slot, MEMO_EMPTY, key);
+        if (seen == MEMO_EMPTY) {  // this thread inserted the key
+            if (atomicAdd(m.ctrl + 0, 1ull) >= LIF_MEMO_SLOTS / 2) m.ctrl[1] = 1ull;  // too diverse: direct kernel
+            break;
+        }
+        if (seen == key) break;
+        slot = (slot + 1) & (LIF_MEMO_SLOTS - 1);
+        if (probe + 1 == LIF_MEMO_SLOTS) m.ctrl[1] = 1ull;
+    }
+    m.slot_of[i] = (unsigned)slot;
+}
+
+__global__ void __launch_bounds__(LIF_THREADS) lif_memo_compact_kernel(const LifMemo m) {
+    if (m.ctrl[1]) return;
+    const unsigned long long slot = blockIdx.x * (unsigned long long)LIF_THREADS + threadIdx.x;
+    if (slot < LIF_MEMO_SLOTS && m.keys[slot] != MEMO_EMPTY) m.dense[atomicAdd(m.ctrl + 2, 1ull)] = (unsigned)slot;
+}
+
+__global__ void __launch_bounds__(LIF_THREADS) lif_memo_run_kernel(const LifParams p, const LifMemo m) {
+    if (m.ctrl[1]) return;
+    const unsigned long long id = blockIdx.x * (unsigned long long)LIF_THREADS + threadIdx.x;
+    if (id >= m.ctrl[0]) return;
+    const unsigned slot = m.dense[id];
+    const unsigned long long key = m.keys[slot];
+    const unsigned long long c = key & ((1ull << 21) - 1), state = key >> 21;
+    const bool refr = (state >> 32) != 0;
+    const NeuronResult o = lif_run(refr ? 0.0f : __uint_as_float((unsigned)state), refr ? (unsigned)state : 0u,
+                                   input_current(c, p.steps), p.steps, p.thr, p.leak, p.period);
+    m.res_v[slot] = o.v;
+    m.res_r[slot] = o.r;
+    m.res_f[slot] = o.fired;
+}
+
+__global__ void __launch_bounds__(LIF_THREADS) lif_memo_apply_kernel(const LifParams p, const LifMemo m) {
+    if (m.ctrl[1]) return;  // block-uniform: the direct kernel behind this one does the work
+    const unsigned long long i = blockIdx.x * (unsigned long long)LIF_THREADS + threadIdx.x;
+    unsigned long long fired = 0, total = 0;
+    if (i < p.pool) {
+        total = p.spikes[i];
+        const unsigned slot = m.slot_of[i];
+        if (slot != MEMO_NONE) {
+            p.v[i] = m.res_v[slot];
+            p.r[i] = m.res_r[slot];
+            fired = m.res_f[slot];
+            total += fired;
+            p.spikes[i] = total;
+        }
+    }
+    block_totals(fired, total, p.total_new, p.max_spikes);
+}
+
 // process_sequence tail (src/spiking_hash.rs:266-272): one update(count as f32) per
 // neuron with count > 0, then currents[i] = 0.
 __global__ void __launch_bounds__(LIF_THREADS) lif_single_tick_kernel(const LifParams p,
@@ -225,8 +306,33 @@ static unsigned lif_blocks(unsigned long long n) { return (unsigned)((n + LIF_TH
 
 cudaError_t launch_lif(const LifParams& p, cudaStream_t s) {
     if (p.pool == 0 || p.steps == 0) return cudaSuccess;  // steps == 0: :548-551 / empty loop :195
-    lif_kernel<<<lif_blocks(p.pool), LIF_THREADS, 0, s>>>(p);
+    lif_kernel<<<lif_blocks(p.pool), LIF_THREADS, 0, s>>>(p, nullptr);
     return cudaGetLastError();
+}
+
+cudaError_t launch_lif_if(const LifParams& p, const unsigned long long* only_if, cudaStream_t s) {
+    if (p.pool == 0 || p.steps == 0) return cudaSuccess;
+    lif_kernel<<<lif_blocks(p.pool), LIF_THREADS, 0, s>>>(p, only_if);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_lif_memo(const LifParams& p, const LifMemo& m, unsigned long long sat, cudaStream_t s, uint64_t* launches) {
+    if (p.pool == 0 || p.steps == 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(m.keys, 0xFF, LIF_MEMO_SLOTS * sizeof(unsigned long long), s);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(m.ctrl, 0, 4 * sizeof(unsigned long long), s);
+    if (e != cudaSuccess) return e;
+    lif_memo_insert_kernel<<<lif_blocks(p.pool), LIF_THREADS, 0, s>>>(p, m, sat);
+    lif_memo_compact_kernel<<<lif_blocks(LIF_MEMO_SLOTS), LIF_THREADS, 0, s>>>(m);
+    lif_memo_run_kernel<<<lif_blocks(LIF_MEMO_SLOTS / 2), LIF_THREADS, 0, s>>>(p, m);
+    lif_memo_apply_kernel<<<lif_blocks(p.pool), LIF_THREADS, 0, s>>>(p, m);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    // too diverse a pool: the direct kernel runs instead (the counts are already folded into `currents`)
+    LifParams d = p;
+    d.fold_mode = 0;
+    e = launch_lif_if(d, m.ctrl + 1, s);
+    if (launches) *launches += 5;
+    return e;
 }
 
 cudaError_t launch_lif_table_build(const LifParams& p, const LifTable& t, unsigned long long table_n, cudaStream_t s) {

@@ -457,7 +457,7 @@ def test_lif_golden_rows_gpu():
     g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_small.json")))
     for blk in g["lif"]:
         counts = np.array([r[0] for r in blk["rows"]], np.uint64)
-        for force_direct in (0, 1):
+        for force_direct in (0, 1, 2):
             c = make(31, counts.size, threshold=blk["threshold"], leak=blk["leak"], refractory=blk["refractory"])
             c.set_steps(blk["steps"])
             c.debug_set_lif_path(force_direct)
@@ -466,7 +466,8 @@ def test_lif_golden_rows_gpu():
             c.synchronize()                    # the hand-off is stream-ordered, cudaMemcpy is not
             copy_h2d(ptr, counts)
             c.stream_finish()
-            assert c.timings()["lif_path"] in ((1,) if force_direct else (2, 3))
+            memo_able = blk["leak"] >= 0
+            assert c.timings()["lif_path"] in {0: (2, 3), 1: (1,), 2: ((5,) if memo_able else (1,))}[force_direct]
             assert c.spike_counts().tolist() == [r[1] for r in blk["rows"]]
             assert c.voltages().view(np.uint32).tolist() == [r[2] for r in blk["rows"]]
             assert c.refractory_ticks().tolist() == [r[3] for r in blk["rows"]]
@@ -1388,3 +1389,66 @@ def test_zero_copy_ragged_ends(coracle):
         c = make(k, pool, False); c.process_batch_packed(pc.array, po.array, o)
         exp_nc, _ = coracle.accumulate(b, o, k, pool, False, threads=2)
         np.testing.assert_array_equal(c.currents(), exp_nc, err_msg=f"packed non-canonical n={n}")
+
+
+def _inject(c, counts, streaming=True):
+    """one job whose per-neuron totals are `counts` (written straight into the device currents)"""
+    from neurokmer_b200.devmem import copy_h2d
+    c.stream_begin()
+    ptr = c.stream_accumulated()
+    c.synchronize()
+    copy_h2d(ptr, np.ascontiguousarray(counts, np.uint64))
+    c.stream_finish()
+
+
+def test_lif_memoised_carried_state_equals_direct(coracle):
+    """Carried state (second and later jobs on one counter): one simulation per distinct (state, count) key gives the
+    state the per-neuron simulation gives, bit for bit, and both equal the oracle (models.rs:34-51 over
+    spiking_hash.rs:544-659); a pool too diverse for the key table falls back to the direct kernel on the device."""
+    rng = np.random.default_rng(41)
+    pool = 600_000
+    a, b = make(31, pool), make(31, pool)
+    b.debug_set_lif_path(1)
+    o = oracle_counter(31, pool)
+    for job in range(4):
+        counts = rng.poisson(56 if job % 2 == 0 else 900, size=pool).astype(np.uint64)
+        counts[rng.integers(0, pool, 1000)] = 0
+        counts[rng.integers(0, pool, 1000)] = rng.integers(1000, 5000, 1000)   # saturating counts
+        _inject(a, counts); _inject(b, counts)
+        o.currents = counts.copy(); o._simulate(True)
+        assert a.timings()["lif_path"] == (3 if job == 0 else 5), job
+        assert b.timings()["lif_path"] == 1
+        for c in (a, b):
+            np.testing.assert_array_equal(c.spike_counts(), o.spikes)
+            np.testing.assert_array_equal(c.refractory_ticks(), o.r)
+            np.testing.assert_array_equal(c.voltages().view(np.uint32), o.v.view(np.uint32))
+            assert c.energy.total_spikes() == o.total_spikes
+        assert a.top_abundant_neurons(50) == b.top_abundant_neurons(50)
+    # nk_simulate on the stored currents goes the same way
+    a.simulate_spikes_auto(); b.simulate_spikes_auto(); o._simulate(True)
+    np.testing.assert_array_equal(a.spike_counts(), o.spikes)
+    np.testing.assert_array_equal(a.voltages().view(np.uint32), b.voltages().view(np.uint32))
+    # too diverse: > 2^19 distinct (state, count) keys -> nothing is applied by the memo kernels, the direct kernel runs
+    pool = 1_200_000
+    a, b = make(31, pool), make(31, pool)
+    b.debug_set_lif_path(1)
+    i = np.arange(pool, dtype=np.uint64)
+    for counts in (i % 1000, (i // 1000) % 1000, (i * 7) % 1000):
+        _inject(a, counts); _inject(b, counts)
+    assert a.timings()["lif_path"] == 5
+    np.testing.assert_array_equal(a.spike_counts(), b.spike_counts())
+    np.testing.assert_array_equal(a.refractory_ticks(), b.refractory_ticks())
+    np.testing.assert_array_equal(a.voltages().view(np.uint32), b.voltages().view(np.uint32))
+    assert a.energy.total_spikes() == b.energy.total_spikes()
+    # the in-memory driver's skip rule (zero-current neurons are not stepped) under memoisation
+    pool = 300_000
+    a, b = make(31, pool), make(31, pool)
+    b.debug_set_lif_path(1)
+    from neurokmer_b200 import flatten
+    for n in (2_000_000, 300_000, 900_000):
+        bases, offsets = flatten([random_dna(rng, n, 0.001)])
+        a.process_batch(bases, offsets); b.process_batch(bases, offsets)
+        np.testing.assert_array_equal(a.voltages().view(np.uint32), b.voltages().view(np.uint32))
+        np.testing.assert_array_equal(a.spike_counts(), b.spike_counts())
+        np.testing.assert_array_equal(a.refractory_ticks(), b.refractory_ticks())
+    assert a.timings()["lif_path"] == 5 and b.timings()["lif_path"] == 1

@@ -13,6 +13,7 @@ build() { # name, defines...
   nvcc $FLAGS "$@" -c neurokmer_b200/csrc/nk_api.cu -o $OUT/nk_api_$name.o 2>&1 | grep -E " error"
   nvcc -shared -o $OUT/lib_$name.so $OUT/nk_count_$name.o $OUT/nk_api_$name.o neurokmer_b200/build/nk_lif.o neurokmer_b200/build/nk_topn.o \
      neurokmer_b200/build/nk_misc.o neurokmer_b200/build/nk_post.o neurokmer_b200/build/nk_exact.o neurokmer_b200/build/nk_fastx.o \
+     neurokmer_b200/build/nk_pack.o neurokmer_b200/build/nk_decomp.o \
      -cudart static -lpthread -ldl -lrt -lz 2>&1 | grep -v deprecated
   python -c "import ctypes; ctypes.CDLL('$OUT/lib_$name.so')" || echo "lib_$name.so does not load"
 }

@@ -247,6 +247,23 @@ __device__ __forceinline__ void process_chunk(const CountParams& p, const Window
 #ifdef NK_EXP_NORED
             // diagnostic build only (tools/variants.sh): no pool update, keep the value alive
             if (idx == 0xFFFFFFFFu) p.acc[0] = bad;
+#elif defined(NK_EXP_ADDR32)
+            // experiment: 64-bit address by an explicit 32-bit carry chain instead of IMAD.WIDE
+            {
+                const unsigned long long base = reinterpret_cast<unsigned long long>(p.acc);
+                unsigned alo, ahi;
+                asm("add.cc.u32 %0, %2, %4;\n\taddc.u32 %1, %3, 0;" : "=r"(alo), "=r"(ahi)
+                    : "r"((unsigned)base), "r"((unsigned)(base >> 32)), "r"(idx << 2));
+                const unsigned long long addr = ((unsigned long long)ahi << 32) | alo;
+                asm volatile(
+                    "{\n\t.reg .pred q;\n\t"
+                    "setp.eq.u32 q, %2, 0;\n\t"
+                    "@q red.global.add.u32 [%0], %1;\n\t}" ::"l"(addr), "r"(1u), "r"(bad)
+                    : "memory");
+            }
+#elif defined(NK_EXP_REDVAL)
+            // experiment: unconditional RED of (1 - bad): no predicate, no branch region
+            asm volatile("red.global.add.u32 [%0], %1;" ::"l"(p.acc + idx), "r"(1u - bad) : "memory");
 #else
             // predicated RED.E.ADD (no divergence region around a single instruction)
             asm volatile(

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Build count-kernel variants into neurokmer_b200/build/variants/lib_<name>.so.  Compile-time knobs:
-# NK_ROT_PLAN_ID, NK_COUNT_UNROLL, NK_CHUNKS_PER_SPAN, NK_COUNT_THREADS, NK_COUNT_MINBLOCKS, NK_EXP_NORED.
+# NK_ROT_PLAN_ID, NK_COUNT_UNROLL, NK_CHUNKS_PER_SPAN, NK_COUNT_THREADS, NK_COUNT_MINBLOCKS, NK_EXP_NORED, NK_EXP_ADDR32, NK_EXP_REDVAL.
 # Bench each with tools/bench_variants.sh (NEUROKMER_LIB=... python bench.py) under gpurun.
 # Usage: tools/variants.sh "name1:-DFOO=1 -DBAR=2" "name2:..."   (run `python -m neurokmer_b200.build` first)
 set +e

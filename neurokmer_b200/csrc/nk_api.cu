@@ -769,6 +769,7 @@ int simulate(nk_counter* h, bool skip_zero, bool with_topn = false) {
             int bits = 0;
             while (bits < 64 && (bound >> bits)) ++bits;
             q.passes = std::max(1, (bits + 7) / 8);
+            q.single_pass = bound < (unsigned long long)nk::POST_EXACT_BINS ? 1 : 0;
             q.ctrl = h->post_zero;
             q.hist = reinterpret_cast<unsigned int*>(h->post_zero + 8);
             q.seg_counts = h->topn.block_counts;
@@ -2077,6 +2078,7 @@ static int dist_build_post(nk_counter* h, nk::PostParams& q, unsigned long long*
     int bits = 0;
     while (bits < 64 && (per_call >> bits)) ++bits;
     q.passes = std::max(1, (bits + 7) / 8);
+    q.single_pass = per_call < (unsigned long long)nk::POST_EXACT_BINS ? 1 : 0;
     q.ctrl = h->post_zero;
     q.hist = reinterpret_cast<unsigned int*>(h->post_zero + 8);
     q.seg_counts = h->topn.block_counts;

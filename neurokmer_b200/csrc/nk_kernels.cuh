@@ -157,6 +157,7 @@ struct TopNScratch {
     unsigned long long* out_spikes;  // capacity >= n_cap
 };
 constexpr int TOPN_BLOCK_ITEMS = 4096;
+constexpr int POST_EXACT_BINS = 2048;  // = the 8 x 256 radix bins of PostParams::hist
 constexpr int POST_SEG_ITEMS = 1024;  // segment of the fused post kernel's ordered phases (block_counts is sized for it)
 constexpr unsigned long long TOPN_MAX_N = 1ull << 20;
 cudaError_t launch_topn(const unsigned long long* spikes, unsigned long long pool, unsigned long long n,
@@ -173,6 +174,7 @@ struct PostParams {
     unsigned long long table_n;
     unsigned long long n;            // rows wanted, 1..2048 and <= pool
     int passes;                      // radix digits to visit (from the host-side spike bound)
+    int single_pass;                 // 1: every total is < POST_EXACT_BINS: one exact histogram instead of radix passes
     unsigned int* hist;              // passes*256 bins, zeroed
     unsigned long long* ctrl;        // [0] gather cursor, zeroed
     unsigned int* seg_counts;        // ceil(pool/4096)

@@ -82,7 +82,7 @@ __global__ void dist_signal_kernel(PeerMail pm, int world, int rank, int which, 
 
 __global__ void __launch_bounds__(PT, 3) post_kernel(const PostParams q) {
     cg::grid_group grid = cg::this_grid();
-    __shared__ unsigned int s_hist[256];
+    __shared__ unsigned int s_hist[POST_EXACT_BINS];  // 256 radix bins, or one bin per spike total (single pass)
     __shared__ unsigned long long s_above[256];
     __shared__ unsigned int s_warp[PT / 32];
     __shared__ unsigned long long s_red[PT / 32];
@@ -103,7 +103,11 @@ __global__ void __launch_bounds__(PT, 3) post_kernel(const PostParams q) {
     }
 
     // ---- phase 1: fold + LIF table apply + histogram of the top digit of the new spike totals ----
-    s_hist[tid] = 0;
+    // q.single_pass: the host-side bound says every total is < POST_EXACT_BINS (the reference's parameters cap a
+    // call at 334 spikes), so phase 1 histograms the totals THEMSELVES and the n-th largest value falls out of
+    // that one histogram: no second pass over the pool, one grid barrier less.
+    const bool single = q.single_pass != 0;
+    for (unsigned b = tid; b < POST_EXACT_BINS; b += PT) s_hist[b] = 0;
     __syncthreads();
     unsigned long long fired_sum = 0;
     // loads are issued in batches of B independent items (memory-level parallelism: a persistent grid
@@ -167,7 +171,8 @@ __global__ void __launch_bounds__(PT, 3) post_kernel(const PostParams q) {
                     rr[i] = 0u;
                     spikes[i] = 0ull;
                 }
-                atomicAdd(&s_hist[(total[u] >> (8 * top)) & 255u], 1u);
+                atomicAdd(&s_hist[single ? (unsigned)(total[u] < POST_EXACT_BINS - 1 ? total[u] : POST_EXACT_BINS - 1)
+                                         : (unsigned)(total[u] >> (8 * top)) & 255u], 1u);
             }
         }
     }
@@ -180,12 +185,47 @@ __global__ void __launch_bounds__(PT, 3) post_kernel(const PostParams q) {
         for (int w = 0; w < PT / 32; ++w) f += s_red[w];
         if (f) atomicAdd(p.total_new, f);
     }
-    if (s_hist[tid]) atomicAdd(&q.hist[top * 256 + tid], s_hist[tid]);
+    if (single) {
+        for (unsigned b = tid; b < POST_EXACT_BINS; b += PT)
+            if (s_hist[b]) atomicAdd(&q.hist[b], s_hist[b]);
+    } else if (s_hist[tid]) {
+        atomicAdd(&q.hist[top * 256 + tid], s_hist[tid]);
+    }
     grid.sync();
 
     // ---- phase 2: MSB-first radix select of the n-th largest total (every block redundantly) ----
     unsigned long long prefix = 0, rank = q.n, gt = 0;
-    for (int d = top; d >= 0; --d) {
+    if (single) {
+        // thread t owns the bins [8t, 8t+8); walk down from the largest total
+        constexpr unsigned PER = POST_EXACT_BINS / PT;
+        unsigned part = 0;
+        for (unsigned b = 0; b < PER; ++b) {
+            const unsigned hb = __ldcg(&q.hist[tid * PER + b]);
+            s_hist[tid * PER + b] = hb;
+            part += hb;
+        }
+        __shared__ unsigned int s_part[PT];
+        s_part[tid] = part;
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long run = 0;
+            for (int x = PT - 1; x >= 0; --x) { s_above[x] = run; run += s_part[x]; }
+        }
+        __syncthreads();
+        if (s_above[tid] < rank && rank <= s_above[tid] + part) s_pick = tid;
+        __syncthreads();
+        const unsigned c = s_pick;
+        unsigned long long run = s_above[c];
+        for (int b = (int)PER - 1; b >= 0; --b) {
+            const unsigned hb = s_hist[c * PER + b];
+            if (run < rank && rank <= run + hb) { prefix = c * PER + b; break; }
+            run += hb;
+        }
+        gt = run;
+        rank -= run;
+        __syncthreads();
+    }
+    for (int d = single ? -1 : top; d >= 0; --d) {
         if (d != top) {
             s_hist[tid] = 0;
             __syncthreads();

@@ -10,7 +10,8 @@ followed by the top-20 read-out.  One "step" = one whole job on a freshly reset 
   value : whole-job throughput with the bases already resident in HBM (CUDA events on the
           library's stream, L2 flushed before every step, max over ranks)
   e2e   : the same job through the public host API with HOST buffers: pinned bases ->
-          nk_stream_push (chunked async H2D overlapped with the kernels) -> nk_stream_end ->
+          nk_stream_push (the count kernel reads the pinned batch in place across PCIe; pageable
+          memory would take the chunked, double-buffered H2D pipeline) -> nk_stream_end ->
           nk_top_n (D2H of the result rows), wall clock around the call sequence
   e2e_prepacked: e2e with the input handed over in the pre-packed form (2 bits per base +
           `other` bits, nk_stream_push_packed): 3/8 of the bytes on PCIe; packing is untimed

@@ -225,6 +225,10 @@ NK_API int nk_debug_pack_body(const uint8_t* bases, uint64_t nbases, uint32_t* c
  * bzip2, xz, zstd input): number of records, total sequence bytes and FNV-1a-64 over every record's
  * sequence bytes followed by one 0xFF byte.  Needs no device. */
 NK_API int nk_debug_fastx_digest(const char* path, uint64_t* nrecords, uint64_t* nbases, uint64_t* fnv1a);
+/* the same digest (plain FASTA only) through the parallel ingest's window planner + window parser, with windows
+ * of `window` bytes (>= 64), run serially: checks the code the multi-threaded file path is made of */
+NK_API int nk_debug_fasta_windows_digest(const char* path, uint64_t window, uint64_t* nrecords, uint64_t* nbases,
+                                         uint64_t* fnv1a);
 /* SipHash-1-3(keys 0,0) of LE64(word) and word-hash % pool_size for a host array. */
 NK_API int nk_debug_hash(nk_counter* h, const uint64_t* words, uint64_t n, uint64_t* hashes, uint64_t* idx);
 /* values[i] % pool_size on the device for ANY pool_size in [1, 2^32) without allocating a pool:

@@ -128,6 +128,7 @@ struct nk_counter {
     int cur_off = 0;
     // device-resident staged batch (nk_stage_reserve)
     DevBuf staged;
+    uint8_t* file_batch[2] = {nullptr, nullptr};  // pinned, 32 MiB each: the file driver's double buffer
     DevBuf zc;  // zero-copy pushes: just the invalid-start bitmap of the body (the bases stay in host memory)
     unsigned long long* staged_offsets = nullptr;
     unsigned long long staged_offsets_cap = 0;
@@ -1236,12 +1237,16 @@ int process_file(nk_counter* h, const char* path, bool streaming, std::string* e
     const size_t cap = (size_t)kChunkBytes;
     // pinned, double-buffered host staging: the parser fills one batch while the other one's
     // H2D copy (copy stream) and kernels (compute stream) are in flight
+    // (the two batches live in the handle: pinning 64 MB costs ~25 ms, and the uniques pass reads the file again)
     uint8_t* batches[2] = {nullptr, nullptr};
     cudaEvent_t copied[2] = {nullptr, nullptr};
     bool inflight[2] = {false, false};
     for (int i = 0; i < 2; ++i) {
-        ce = cudaMallocHost((void**)&batches[i], cap);
-        if (ce != cudaSuccess) { if (batches[0]) cudaFreeHost(batches[0]); return cuda_fail(ce, "cudaMallocHost(batch)"); }
+        if (!h->file_batch[i]) {
+            ce = cudaMallocHost((void**)&h->file_batch[i], cap);
+            if (ce != cudaSuccess) { h->file_batch[i] = nullptr; return cuda_fail(ce, "cudaMallocHost(batch)"); }
+        }
+        batches[i] = h->file_batch[i];
         cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming);
     }
     int cur = 0;
@@ -1336,7 +1341,7 @@ int process_file(nk_counter* h, const char* path, bool streaming, std::string* e
     } while (0);
     cudaStreamSynchronize(h->copy_stream);
     cudaStreamSynchronize(h->stream);
-    for (int i = 0; i < 2; ++i) { cudaFreeHost(batches[i]); cudaEventDestroy(copied[i]); }
+    for (int i = 0; i < 2; ++i) cudaEventDestroy(copied[i]);
     return rc;
 }
 
@@ -1464,6 +1469,7 @@ int nk_destroy(nk_counter* h) {
     if (h->h_top) cudaFreeHost(h->h_top);
     cudaFree(h->memo.keys); cudaFree(h->memo.dense); cudaFree(h->memo.res_v); cudaFree(h->memo.res_r);
     cudaFree(h->memo.res_f); cudaFree(h->memo.slot_of); cudaFree(h->memo.ctrl);
+    for (int i = 0; i < 2; ++i) if (h->file_batch[i]) cudaFreeHost(h->file_batch[i]);
     nk::exact_free(h->ut);
     cudaFree(h->d_filter);
     cudaFree(h->d_rows);
@@ -2445,11 +2451,61 @@ int nk_debug_fastx_digest(const char* path, uint64_t* nrecords, uint64_t* nbases
             rec.insert(rec.end(), buf.begin(), buf.begin() + n);
         }
         if (!rd.finish_record(rec.size())) break;  // malformed FASTQ record: iteration ends, record dropped
-        for (uint8_t b : rec) { hsh ^= b; hsh *= 0x100000001b3ull; }
-        hsh ^= 0xFFu; hsh *= 0x100000001b3ull;  // record separator
+        if (fnv1a) {  // NULL: parse only (reader throughput measurements)
+            for (uint8_t b : rec) { hsh ^= b; hsh *= 0x100000001b3ull; }
+            hsh ^= 0xFFu; hsh *= 0x100000001b3ull;  // record separator
+        }
         ++nrec;
         nb += rec.size();
     }
+    if (nrecords) *nrecords = nrec;
+    if (nbases) *nbases = nb;
+    if (fnv1a) *fnv1a = hsh;
+    return NK_OK;
+}
+
+// Host-only: the same digest through the PARALLEL ingest's window planner + parser (run serially here):
+// the file is cut into windows of `window` bytes exactly as count_fasta_parallel does, every window is
+// stripped by fasta_parse_window, and the records are re-assembled from the per-window record starts.
+int nk_debug_fasta_windows_digest(const char* path, uint64_t window, uint64_t* nrecords, uint64_t* nbases, uint64_t* fnv1a) {
+    if (!path || window < 64) return fail(NK_ERR_BAD_ARG, "null path or window < 64");
+    const int fd = ::open(path, O_RDONLY);
+    if (fd < 0) return fail(NK_ERR_IO, "cannot open %s", path);
+    struct stat st;
+    if (fstat(fd, &st) != 0 || st.st_size == 0) { ::close(fd); return fail(NK_ERR_IO, "%s: empty file", path); }
+    const size_t size = (size_t)st.st_size;
+    void* map = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+    ::close(fd);
+    if (map == MAP_FAILED) return fail(NK_ERR_IO, "mmap failed");
+    const uint8_t* file = (const uint8_t*)map;
+    uint64_t nrec = 0, nb = 0, hsh = 0xcbf29ce484222325ull;
+    bool open_rec = false;
+    std::vector<uint8_t> data((size_t)window + nk::kFastaSlack + 64);
+    std::vector<uint64_t> starts;
+    size_t ws = 0;
+    int state = nk::FA_LINE_START;
+    while (ws < size) {
+        int next_state = nk::FA_LINE_START;
+        const nk::FastaWindowPlan w = nk::fasta_plan_window(file, size, ws, (size_t)window, state, &next_state);
+        size_t fill = 0;
+        nk::fasta_parse_window(file, w, data.data(), &fill, &starts);
+        size_t at = 0;
+        for (size_t r = 0; r <= starts.size(); ++r) {
+            const size_t end = r < starts.size() ? (size_t)starts[r] : fill;
+            if (fnv1a)
+                for (size_t i = at; i < end; ++i) { hsh ^= data[i]; hsh *= 0x100000001b3ull; }
+            nb += end - at;
+            at = end;
+            if (r < starts.size()) {  // a header: the open record (if any) ends, a new one begins
+                if (open_rec) { hsh ^= 0xFFu; hsh *= 0x100000001b3ull; ++nrec; }
+                open_rec = true;
+            }
+        }
+        ws = w.we;
+        state = next_state;
+    }
+    if (open_rec) { hsh ^= 0xFFu; hsh *= 0x100000001b3ull; ++nrec; }
+    munmap(map, size);
     if (nrecords) *nrecords = nrec;
     if (nbases) *nbases = nb;
     if (fnv1a) *fnv1a = hsh;

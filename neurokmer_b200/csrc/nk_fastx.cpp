@@ -7,7 +7,12 @@
 #include <cstring>
 #include <fcntl.h>
 #include <unistd.h>
+#include <immintrin.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
 #include <zlib.h>
+
+#include <cstdlib>
 
 namespace nk {
 
@@ -27,14 +32,93 @@ uint64_t host_pack_kmer(const uint8_t* kmer, uint64_t len) {
     return packed;
 }
 
+// ---- FASTA sequence data: dst <- src without '\n' / '\r', up to the next header -------------------------
+// Stripping the terminators of 60-column lines is what bounds FASTA ingest: one memchr + one memcpy per line
+// ran at ~1.5 GB/s, a separate search for the next header was a second pass over the data.  One fused pass:
+// copy src[0, n) without '\n' and '\r' ('\r' never occurs inside FASTA text) and stop at the first '>' that
+// starts a line (previous byte '\n'; src[0] itself is data by contract).  With AVX-512 VBMI2 a 64-byte block
+// is compared against the three bytes, compressed in a register and stored with a length mask; otherwise a
+// per-line loop runs.  *consumed = input bytes taken (n, or the index of the header); returns bytes written.
+namespace {
+
+size_t strip_generic(uint8_t* dst, const uint8_t* src, size_t n, size_t* consumed) {
+    size_t w = 0, p = 0;
+    while (p < n) {
+        if (p > 0 && src[p] == '>') break;  // p > 0 here means a line start: the previous byte was '\n'
+        const uint8_t* nl = (const uint8_t*)memchr(src + p, '\n', n - p);
+        const size_t len = nl ? (size_t)(nl - (src + p)) : n - p;
+        const uint8_t* s = src + p;
+        if (len > 0 && s[len - 1] != '\r' && !memchr(s, '\r', len)) {
+            memcpy(dst + w, s, len);
+            w += len;
+        } else {
+            for (size_t i = 0; i < len; ++i)
+                if (s[i] != '\r') dst[w++] = s[i];
+        }
+        p += len + (nl ? 1 : 0);
+    }
+    *consumed = p;
+    return w;
+}
+
+__attribute__((target("avx512f,avx512bw,avx512vbmi2"))) size_t strip_avx512(uint8_t* dst, const uint8_t* src, size_t n,
+                                                                             size_t* consumed) {
+    const __m512i lf = _mm512_set1_epi8('\n'), cr = _mm512_set1_epi8('\r'), gt = _mm512_set1_epi8('>');
+    size_t w = 0, p = 0;
+    unsigned long long prev_lf = 0;  // bit 0: the byte before this block is '\n' (src[0] is data: starts clear)
+    for (; p + 64 <= n; p += 64) {
+        const __m512i v = _mm512_loadu_si512(src + p);
+        const __mmask64 m_lf = _mm512_cmpeq_epi8_mask(v, lf);
+        __mmask64 keep = ~(m_lf | _mm512_cmpeq_epi8_mask(v, cr));
+        const __mmask64 hdr = _mm512_cmpeq_epi8_mask(v, gt) & ((m_lf << 1) | prev_lf);
+        if (hdr) {  // a header starts inside this block: take the bytes before it and stop
+            const unsigned first = (unsigned)__builtin_ctzll(hdr);
+            keep &= (1ull << first) - 1;  // first < 64
+            const unsigned cnt = (unsigned)__builtin_popcountll(keep);
+            _mm512_mask_storeu_epi8(dst + w, (1ull << cnt) - 1, _mm512_maskz_compress_epi8(keep, v));  // cnt < 64
+            *consumed = p + first;
+            return w + cnt;
+        }
+        const unsigned cnt = (unsigned)__builtin_popcountll(keep);
+        _mm512_mask_storeu_epi8(dst + w, cnt == 64 ? ~0ull : ((1ull << cnt) - 1), _mm512_maskz_compress_epi8(keep, v));
+        w += cnt;
+        prev_lf = m_lf >> 63;
+    }
+    for (; p < n; ++p) {
+        const uint8_t b = src[p];
+        if (b == '>' && p > 0 && src[p - 1] == '\n') break;
+        if (b != '\n' && b != '\r') dst[w++] = b;
+    }
+    *consumed = p;
+    return w;
+}
+
+using StripFn = size_t (*)(uint8_t*, const uint8_t*, size_t, size_t*);
+StripFn pick_strip() {
+    __builtin_cpu_init();
+    if (__builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512vbmi2") &&
+        !getenv("NK_NO_SIMD_STRIP"))
+        return strip_avx512;
+    return strip_generic;
+}
+
+}  // namespace
+
+size_t strip_until_header(uint8_t* dst, const uint8_t* src, size_t n, size_t* consumed) {
+    static const StripFn fn = pick_strip();
+    return fn(dst, src, n, consumed);
+}
+
 FastxReader::~FastxReader() {
     delete dec_;
+    if (map_) munmap(map_, map_size_);
     if (gz_) gzclose((gzFile)gz_);  // also closes the descriptor
     else if (fd_ >= 0) ::close(fd_);
 }
 
 bool FastxReader::fill() {
     if (eof_) return false;
+    if (map_) { eof_ = true; return false; }  // a mapped file is one buffer: [0, size) was handed out at open()
     pos_ = 0;
     end_ = 0;
     for (;;) {
@@ -50,14 +134,14 @@ bool FastxReader::fill() {
 
 int FastxReader::peek() {
     if (pos_ == end_ && !fill()) return -1;
-    return buf_[pos_];
+    return base_[pos_];
 }
 
 void FastxReader::skip_line() {
     for (;;) {
         if (pos_ == end_ && !fill()) return;
-        const uint8_t* p = (const uint8_t*)memchr(buf_.data() + pos_, '\n', end_ - pos_);
-        if (p) { pos_ = (size_t)(p - buf_.data()) + 1; at_line_start_ = true; return; }
+        const uint8_t* p = (const uint8_t*)memchr(base_ + pos_, '\n', end_ - pos_);
+        if (p) { pos_ = (size_t)(p - base_) + 1; at_line_start_ = true; return; }
         pos_ = end_;
     }
 }
@@ -68,7 +152,8 @@ int FastxReader::open(const char* path, std::string* err) {
         if (err) *err = std::string("cannot open ") + path + ": " + strerror(errno);
         return 1;
     }
-    buf_.resize(4u << 20);
+    struct stat st;
+    const bool regular = fstat(fd_, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0;
     // needletail sniffs the compression format from the magic bytes: gzip through zlib here,
     // bzip2 / xz / zstd through nk_decomp.cpp
     unsigned char magic[4] = {0, 0, 0, 0};
@@ -84,6 +169,24 @@ int FastxReader::open(const char* path, std::string* err) {
             if (err) *err = std::string(path) + ": " + why;
             return 1;
         }
+    }
+    if (!gz_ && !dec_ && regular) {
+        // plain file: map it (no read() copy); the whole file is the reader's one buffer
+        // small files are pre-faulted in one go (demand faults cost as much as the read() copy they replace)
+        const int populate = st.st_size <= (1ll << 30) ? MAP_POPULATE : 0;
+        void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE | populate, fd_, 0);
+        if (m != MAP_FAILED) {
+            map_ = m;
+            map_size_ = (size_t)st.st_size;
+            madvise(m, map_size_, MADV_SEQUENTIAL);
+            base_ = static_cast<const uint8_t*>(m);
+            pos_ = 0;
+            end_ = map_size_;
+        }
+    }
+    if (!map_) {
+        buf_.resize(4u << 20);
+        base_ = buf_.data();
     }
     const int c = peek();
     if (c < 0) { if (err) *err = std::string(path) + ": empty file"; return 1; }
@@ -113,14 +216,25 @@ bool FastxReader::next_record() {
 size_t FastxReader::read_seq(uint8_t* dst, size_t cap, bool* done) {
     size_t w = 0;
     *done = false;
-    while (w < cap) {
+    // FASTA: whole regions between headers are stripped at once (a line-start '>' ends the record)
+    while (!fastq_ && w < cap) {
+        if (pos_ == end_ && !fill()) { *done = true; return w; }
+        if (at_line_start_ && base_[pos_] == '>') { *done = true; return w; }
+        const uint8_t* s = base_ + pos_;
+        const size_t n = std::min(end_ - pos_, cap - w);
+        size_t q = 0;  // s[0] is data: not '>' or not at a line start
+        w += strip_until_header(dst + w, s, n, &q);
+        at_line_start_ = s[q - 1] == '\n';
+        pos_ += q;
+        if (q < n) { *done = true; return w; }
+    }
+    while (fastq_ && w < cap) {
         if (pos_ == end_ && !fill()) { *done = true; return w; }
         if (at_line_start_) {
-            if (!fastq_ && buf_[pos_] == '>') { *done = true; return w; }
             at_line_start_ = false;
         }
         // copy up to end of line
-        const uint8_t* s = buf_.data() + pos_;
+        const uint8_t* s = base_ + pos_;
         size_t avail = end_ - pos_;
         if (avail > cap - w) avail = cap - w;
         const uint8_t* nl = (const uint8_t*)memchr(s, '\n', avail);
@@ -145,7 +259,7 @@ size_t FastxReader::read_seq(uint8_t* dst, size_t cap, bool* done) {
     // cap reached: the record may or may not be finished
     if (!fastq_) {
         if (pos_ == end_ && !fill()) { *done = true; return w; }
-        if (at_line_start_ && buf_[pos_] == '>') *done = true;
+        if (at_line_start_ && base_[pos_] == '>') *done = true;
     }
     return w;
 }
@@ -159,7 +273,7 @@ bool FastxReader::finish_record(uint64_t seq_len) {
     bool saw_nl = false;
     for (;;) {
         if (pos_ == end_ && !fill()) break;
-        const uint8_t* s = buf_.data() + pos_;
+        const uint8_t* s = base_ + pos_;
         const size_t avail = end_ - pos_;
         const uint8_t* nl = (const uint8_t*)memchr(s, '\n', avail);
         const size_t n = nl ? (size_t)(nl - s) : avail;
@@ -211,29 +325,19 @@ void fasta_parse_window(const uint8_t* file, const FastaWindowPlan& w, uint8_t* 
     rec_starts->clear();
     int state = w.start_state;
     while (p < w.we) {
-        const uint8_t* nl = (const uint8_t*)memchr(file + p, '\n', w.we - p);
-        const size_t line_end = nl ? (size_t)(nl - file) : w.we;
-        bool header;
-        if (state == FA_MID_HEADER) header = true;        // rest of a header that started in an earlier window
-        else if (state == FA_MID_SEQ) header = false;     // rest of a sequence line, whatever its first byte
-        else {
-            header = file[p] == '>';
-            if (header) rec_starts->push_back(out);
+        if (state == FA_MID_HEADER || (state == FA_LINE_START && file[p] == '>')) {
+            // a header line (or the rest of one that started in an earlier window): skip it
+            if (state == FA_LINE_START) rec_starts->push_back(out);
+            const uint8_t* nl = (const uint8_t*)memchr(file + p, '\n', w.we - p);
+            p = nl ? (size_t)(nl - file) + 1 : w.we;
+            state = FA_LINE_START;
+            continue;
         }
-        if (!header) {
-            const uint8_t* s = file + p;
-            const size_t n = line_end - p;
-            if (n > 0 && s[n - 1] != '\r' && !memchr(s, '\r', n)) {
-                memcpy(data + out, s, n);
-                out += n;
-            } else {
-                for (size_t i = 0; i < n; ++i)
-                    if (s[i] != '\r') data[out++] = s[i];
-            }
-        }
-        // after a '\n' the next line starts fresh; without one the window ended mid-line
-        state = FA_LINE_START;
-        p = line_end + 1;
+        // sequence data up to the next line-start '>' (file[p] itself is data: mid-line, or not '>')
+        size_t took = 0;
+        out += strip_until_header(data + out, file + p, w.we - p, &took);
+        p += took;
+        state = FA_LINE_START;  // either at a header or at the end of the window
     }
     *fill = out;
 }

@@ -67,10 +67,18 @@ private:
     int fd_ = -1;
     void* gz_ = nullptr;  // gzFile when the input is gzip-compressed
     StreamDecoder* dec_ = nullptr;  // bzip2 / xz / zstd
-    std::vector<uint8_t> buf_;
+    std::vector<uint8_t> buf_;            // read buffer of compressed / non-regular input
+    const uint8_t* base_ = nullptr;       // the current buffer: buf_.data(), or the mapping of a plain file
+    void* map_ = nullptr;
+    size_t map_size_ = 0;
     size_t pos_ = 0, end_ = 0;
     bool eof_ = false, fastq_ = false, at_line_start_ = true, started_ = false;
 };
+
+// FASTA sequence data: dst <- src[0, n) without '\n' / '\r', stopping at the first '>' that starts a line
+// (src[0] itself is data).  *consumed = input bytes taken; returns bytes written.  One fused pass
+// (AVX-512 VBMI2 compress where the CPU has it).
+size_t strip_until_header(uint8_t* dst, const uint8_t* src, size_t n, size_t* consumed);
 
 // ---- parallel FASTA ingest (plain files): the file is cut into windows that several host threads
 // strip (headers, '\n', '\r') concurrently; see process_file in nk_api.cu -------------------------

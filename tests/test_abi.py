@@ -221,3 +221,60 @@ def test_cxx_reader_formats_and_compression(built, tmp_path):
     assert _cxx_digest(lib, tmp_path / "empty.fa")[0] == built.NK_ERR_IO
     (tmp_path / "junk.txt").write_bytes(b"hello\n")
     assert _cxx_digest(lib, tmp_path / "junk.txt")[0] == built.NK_ERR_IO
+
+
+def test_fasta_readers_fuzz_against_python_twin(built, tmp_path):
+    """Serial C++ reader and the parallel ingest's window planner/parser against the Python reader on randomised
+    FASTA: ragged line widths, CRLF, empty lines, empty records, '>' inside sequence lines, no final newline,
+    headers longer than a window.  Both newline-stripping bodies (AVX-512 VBMI2 / portable) are exercised: the
+    portable one in a child process with NK_NO_SIMD_STRIP=1."""
+    import subprocess
+    import sys
+    from neurokmer_b200.fastx import read_fastx
+    lib = built.lib()
+    rng = np.random.default_rng(2024)
+    alphabet = np.frombuffer(b"ACGTNacgtn>", np.uint8)
+    paths = []
+    for case in range(12):
+        out = bytearray()
+        nrec = int(rng.integers(1, 9))
+        for r in range(nrec):
+            out += b">" + bytes(rng.choice(np.frombuffer(b"abc >|xyz", np.uint8), size=int(rng.integers(0, 300 if case % 3 else 5000)))) + (b"\r\n" if case % 4 == 1 else b"\n")
+            total = int(rng.choice([0, 1, 59, 60, 61, 1000, 70_000]))
+            width = int(rng.choice([1, 7, 60, 61, 64, 80, 100_000]))
+            seq = rng.choice(alphabet, size=total, p=[.22, .22, .22, .22, .03, .02, .02, .02, .02, .005, .005]).tobytes()
+            pos = 0
+            while pos < len(seq):
+                line = seq[pos:pos + width]
+                if line.startswith(b">"):
+                    line = b"A" + line[1:]          # a line may CONTAIN '>' but must not start with it
+                out += line + (b"\r\n" if case % 4 == 1 else b"\n")
+                pos += width
+                if case % 5 == 2 and rng.random() < 0.05:
+                    out += b"\n"                     # empty line inside a record
+        if case % 6 == 3 and out.endswith(b"\n"):
+            out = out[:-1]                           # no final newline
+        p = tmp_path / f"fuzz{case}.fa"
+        p.write_bytes(bytes(out))
+        paths.append(str(p))
+    for path in paths:
+        want = _digest(list(read_fastx(path)))
+        assert _cxx_digest(lib, path) == (0, want), path
+        for window in (64, 100, 1000, 4096, 1 << 20):
+            n, nb, h = C.c_uint64(), C.c_uint64(), C.c_uint64()
+            assert lib.nk_debug_fasta_windows_digest(path.encode(), window, C.byref(n), C.byref(nb), C.byref(h)) == 0
+            assert (n.value, nb.value, h.value) == want, (path, window)
+    # the portable stripping body, in a child process
+    code = ("import sys, ctypes as C; sys.path.insert(0, %r); from neurokmer_b200 import _lib; lib = _lib.lib()\n"
+            "for p in sys.argv[1:]:\n"
+            "    n, nb, h = C.c_uint64(), C.c_uint64(), C.c_uint64()\n"
+            "    assert lib.nk_debug_fastx_digest(p.encode(), C.byref(n), C.byref(nb), C.byref(h)) == 0\n"
+            "    a = (n.value, nb.value, h.value)\n"
+            "    assert lib.nk_debug_fasta_windows_digest(p.encode(), 1000, C.byref(n), C.byref(nb), C.byref(h)) == 0\n"
+            "    print(*a, n.value, nb.value, h.value)\n") % ROOT
+    env = dict(os.environ, NK_NO_SIMD_STRIP="1")
+    outp = subprocess.check_output([sys.executable, "-c", code] + paths, text=True, env=env)
+    for path, line in zip(paths, outp.splitlines()):
+        want = _digest(list(read_fastx(path)))
+        vals = tuple(int(x) for x in line.split())
+        assert vals[:3] == want and vals[3:] == want, path

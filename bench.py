@@ -262,11 +262,19 @@ def gpu_arm(args):
     fused = world > 1 and args.dist in ("fused", "peer")
     peer = world > 1 and args.dist == "peer"
     if fused:
-        handle, _ = c.dist_export()
-        handles = [None] * world
-        dist.all_gather_object(handles, handle)
-        c.dist_setup(rank, world, handles=b"".join(handles))
-        dist.barrier()  # every rank's mailbox is set up before anyone signals into it
+        ok = torch.ones(1, dtype=torch.int32, device="cuda")
+        try:
+            handle, _ = c.dist_export()
+            handles = [None] * world
+            dist.all_gather_object(handles, handle)
+            c.dist_setup(rank, world, handles=b"".join(handles))
+        except Exception as e:  # no peer access between these devices (CUDA IPC refused): every rank must fall back
+            print(f"[rank {rank}] sharded-pool setup failed ({e}); falling back to the NCCL all-reduce of the currents", file=sys.stderr)
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)  # also the barrier between setup and the first signal
+        if int(ok.item()) == 0:
+            fused = peer = False
+            args.dist = "allreduce"
         barrier_t = torch.zeros(1, dtype=torch.int32, device="cuda")
         pack_views = {}
 

@@ -197,6 +197,45 @@ NKO_EXPORT uint64_t nko_kmer_fwd_rc(const uint8_t *seq, uint64_t len, unsigned k
     return len - k + 1;
 }
 
+/* Exact-count map of the reference: `local_counts: HashMap<u64, u32>` per rayon task
+ * (src/spiking_hash.rs:96,110,124,134) merged into `counts: DashMap<u64, AtomicU32>` (:157-165).
+ * Open addressing, linear probing, grown at 60 % load; a slot is empty while its count is 0. */
+typedef struct {
+    uint64_t *keys;
+    uint32_t *vals;
+    uint64_t cap, n; /* cap is a power of two */
+} kmap_t;
+
+static void kmap_init(kmap_t *m, uint64_t cap) {
+    m->cap = cap;
+    m->n = 0;
+    m->keys = (uint64_t *)malloc(cap * sizeof(uint64_t));
+    m->vals = (uint32_t *)calloc(cap, sizeof(uint32_t));
+}
+static void kmap_free(kmap_t *m) { free(m->keys); free(m->vals); m->keys = NULL; m->vals = NULL; }
+static inline uint64_t kmap_hash(uint64_t x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+    return x;
+}
+static void kmap_add(kmap_t *m, uint64_t key, uint32_t by);
+static void kmap_grow(kmap_t *m) {
+    kmap_t big;
+    kmap_init(&big, m->cap * 2);
+    for (uint64_t i = 0; i < m->cap; i++)
+        if (m->vals[i]) kmap_add(&big, m->keys[i], m->vals[i]);
+    kmap_free(m);
+    *m = big;
+}
+static void kmap_add(kmap_t *m, uint64_t key, uint32_t by) {
+    if ((m->n + 1) * 5 > m->cap * 3) kmap_grow(m);
+    uint64_t i = kmap_hash(key) & (m->cap - 1);
+    for (;;) {
+        if (!m->vals[i]) { m->keys[i] = key; m->vals[i] = by; m->n++; return; }
+        if (m->keys[i] == key) { m->vals[i] += by; return; } /* wraps like AtomicU32::fetch_add */
+        i = (i + 1) & (m->cap - 1);
+    }
+}
+
 /* currents[idx] += 1 for every window of every sequence in [s_lo, s_hi) —
  * the body of the rayon fold (src/spiking_hash.rs:98-143) and of the
  * streaming worker (:319-352), minus the exact-count HashMap. */
@@ -222,6 +261,41 @@ static uint64_t accumulate_range(const uint8_t *bases, const uint64_t *offsets, 
         } else {
             for (uint64_t i = 0; i + k <= len; i++)
                 currents[nko_neuron_index(nko_pack_kmer(seq + i, k), pool_size)] += 1;
+        }
+        total += len - k + 1;
+    }
+    return total;
+}
+
+/* The same WITH the exact-count HashMap — a separate copy, so that the hot-path-only baseline above
+ * is compiled exactly as it was before this variant existed. */
+static uint64_t accumulate_range_exact(const uint8_t *bases, const uint64_t *offsets, uint64_t s_lo,
+                                       uint64_t s_hi, unsigned k, uint64_t pool_size, int canonical,
+                                       uint64_t *currents, kmap_t *map) {
+    uint64_t total = 0;
+    for (uint64_t s = s_lo; s < s_hi; s++) {
+        const uint8_t *seq = bases + offsets[s];
+        uint64_t len = offsets[s + 1] - offsets[s];
+        if (len < k) continue;
+        if (canonical) {
+            rolling_t r;
+            rolling_new(&r, k);
+            rolling_init(&r, seq);
+            uint64_t w = r.forward < r.reverse ? r.forward : r.reverse;
+            currents[nko_neuron_index(w, pool_size)] += 1;
+            kmap_add(map, w, 1);
+            for (uint64_t i = 1; i <= len - k; i++) {
+                rolling_slide(&r, seq[i + k - 1], seq[i - 1]);
+                w = r.forward < r.reverse ? r.forward : r.reverse;
+                currents[nko_neuron_index(w, pool_size)] += 1;
+                kmap_add(map, w, 1);
+            }
+        } else {
+            for (uint64_t i = 0; i + k <= len; i++) {
+                const uint64_t w = nko_pack_kmer(seq + i, k);
+                currents[nko_neuron_index(w, pool_size)] += 1;
+                kmap_add(map, w, 1);
+            }
         }
         total += len - k + 1;
     }
@@ -258,6 +332,11 @@ typedef struct {
     int canonical;
     uint64_t *currents; /* private */
     uint64_t total;
+    kmap_t *map;        /* private exact-count map, or NULL (hot path only) */
+    /* merge phase of the exact variant: thread t owns the keys with kmap_hash(key) >> 40 % nthreads == t */
+    kmap_t *all_maps;
+    unsigned nthreads, tid;
+    kmap_t merged;
 } mt_arg_t;
 
 static void *mt_worker(void *p) {
@@ -271,8 +350,10 @@ static void *mt_worker(void *p) {
         uint64_t end = pc->hi + a->k - 1;
         if (end > pc->seq_end) end = pc->seq_end;
         uint64_t off[2] = {pc->lo, end};
-        a->total += accumulate_range(a->bases, off, 0, 1, a->k, a->pool_size, a->canonical,
-                                     a->currents);
+        if (a->map)
+            a->total += accumulate_range_exact(a->bases, off, 0, 1, a->k, a->pool_size, a->canonical, a->currents, a->map);
+        else
+            a->total += accumulate_range(a->bases, off, 0, 1, a->k, a->pool_size, a->canonical, a->currents);
     }
     return NULL;
 }
@@ -322,6 +403,91 @@ NKO_EXPORT uint64_t nko_accumulate_mt(const uint8_t *bases, const uint64_t *offs
         }
     }
     free(args); free(th); free(pieces);
+    return total;
+}
+
+/* The same with the reference's exact side tables (the work its CPU path ALWAYS does):
+ * per-task HashMap<u64,u32> (:96), merged into the global `counts` map (:157-165), then
+ * kmer_per_neuron = distinct k-mers per neuron (:167-172).  The merge is key-partitioned
+ * over the threads (the reference's DashMap shards play that role).  *n_distinct = |counts|;
+ * uniques (pool_size u32, may be NULL) receives kmer_per_neuron. */
+static void *merge_worker(void *p) {
+    mt_arg_t *a = (mt_arg_t *)p;
+    kmap_init(&a->merged, 1u << 16);
+    for (unsigned t = 0; t < a->nthreads; t++) {
+        const kmap_t *m = &a->all_maps[t];
+        for (uint64_t i = 0; i < m->cap; i++)
+            if (m->vals[i] && (kmap_hash(m->keys[i]) >> 40) % a->nthreads == a->tid)
+                kmap_add(&a->merged, m->keys[i], m->vals[i]);
+    }
+    return NULL;
+}
+
+NKO_EXPORT uint64_t nko_accumulate_exact_mt(const uint8_t *bases, const uint64_t *offsets,
+                                            uint64_t nseq, unsigned k, uint64_t pool_size,
+                                            int canonical, uint64_t *currents, unsigned nthreads,
+                                            uint64_t *n_distinct, uint32_t *uniques) {
+    const uint64_t CHUNK = 1u << 20;
+    if (nthreads == 0) nthreads = 1;
+    uint64_t npieces = 0;
+    for (uint64_t s = 0; s < nseq; s++) {
+        uint64_t len = offsets[s + 1] - offsets[s];
+        if (len < k) continue;
+        npieces += (len - k + 1 + CHUNK - 1) / CHUNK;
+    }
+    piece_t *pieces = (piece_t *)malloc((npieces ? npieces : 1) * sizeof(piece_t));
+    uint64_t ip = 0;
+    for (uint64_t s = 0; s < nseq; s++) {
+        uint64_t len = offsets[s + 1] - offsets[s];
+        if (len < k) continue;
+        uint64_t nwin = len - k + 1;
+        for (uint64_t w = 0; w < nwin; w += CHUNK) {
+            pieces[ip].bases = bases;
+            pieces[ip].lo = offsets[s] + w;
+            pieces[ip].hi = offsets[s] + (w + CHUNK < nwin ? w + CHUNK : nwin);
+            pieces[ip].seq_end = offsets[s + 1];
+            ip++;
+        }
+    }
+    uint64_t next = 0, total = 0;
+    pthread_t *th = (pthread_t *)malloc(nthreads * sizeof(pthread_t));
+    mt_arg_t *args = (mt_arg_t *)calloc(nthreads, sizeof(mt_arg_t));
+    kmap_t *maps = (kmap_t *)calloc(nthreads, sizeof(kmap_t));
+    for (unsigned t = 0; t < nthreads; t++) {
+        kmap_init(&maps[t], 1u << 16);
+        args[t].bases = bases; args[t].pieces = pieces; args[t].npieces = npieces;
+        args[t].next = &next; args[t].k = k; args[t].pool_size = pool_size;
+        args[t].canonical = canonical;
+        args[t].currents = (t == 0) ? currents : (uint64_t *)calloc(pool_size, sizeof(uint64_t));
+        args[t].map = &maps[t];
+        pthread_create(&th[t], NULL, mt_worker, &args[t]);
+    }
+    for (unsigned t = 0; t < nthreads; t++) {
+        pthread_join(th[t], NULL);
+        total += args[t].total;
+        if (t > 0) {
+            for (uint64_t i = 0; i < pool_size; i++) currents[i] += args[t].currents[i];
+            free(args[t].currents);
+        }
+    }
+    /* merge the per-task maps (counts), then the per-neuron distinct counts (kmer_per_neuron) */
+    for (unsigned t = 0; t < nthreads; t++) {
+        args[t].all_maps = maps; args[t].nthreads = nthreads; args[t].tid = t;
+        pthread_create(&th[t], NULL, merge_worker, &args[t]);
+    }
+    uint64_t distinct = 0;
+    for (unsigned t = 0; t < nthreads; t++) {
+        pthread_join(th[t], NULL);
+        const kmap_t *m = &args[t].merged;
+        distinct += m->n;
+        if (uniques)
+            for (uint64_t i = 0; i < m->cap; i++)
+                if (m->vals[i]) uniques[nko_neuron_index(m->keys[i], pool_size)] += 1;
+        kmap_free(&args[t].merged);
+    }
+    for (unsigned t = 0; t < nthreads; t++) kmap_free(&maps[t]);
+    if (n_distinct) *n_distinct = distinct;
+    free(maps); free(args); free(th); free(pieces);
     return total;
 }
 

@@ -275,6 +275,24 @@ class COracle:
                                              self._p(currents, ctypes.c_uint64), threads)
         return currents, tot
 
+    def accumulate_exact(self, bases: np.ndarray, offsets: np.ndarray, k: int, pool: int, canonical: bool = True,
+                         threads: int = 1, want_uniques: bool = True):
+        """accumulate + the reference's exact side tables (per-task HashMap, merged counts, kmer_per_neuron):
+        returns (currents, windows, n_distinct, uniques or None)."""
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        currents = np.zeros(pool, dtype=np.uint64)
+        uniques = np.zeros(pool, dtype=np.uint32) if want_uniques else None
+        b = bases if bases.size else np.zeros(1, np.uint8)
+        nd = ctypes.c_uint64()
+        fn = self.lib.nko_accumulate_exact_mt
+        fn.restype = ctypes.c_uint64
+        fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint, ctypes.c_uint64, ctypes.c_int,
+                       ctypes.c_void_p, ctypes.c_uint, ctypes.POINTER(ctypes.c_uint64), ctypes.c_void_p]
+        tot = fn(b.ctypes.data, offsets.ctypes.data, offsets.size - 1, k, pool, int(canonical), currents.ctypes.data,
+                 max(1, threads), ctypes.byref(nd), None if uniques is None else uniques.ctypes.data)
+        return currents, int(tot), int(nd.value), uniques
+
     def lif(self, currents: np.ndarray, steps: int, thr: float, leak: float, period: int,
             v: np.ndarray | None = None, r: np.ndarray | None = None, spikes: np.ndarray | None = None,
             simd_semantics: bool = False, threads: int = 1):

@@ -221,3 +221,23 @@ def test_synth_twin_properties():
     assert 0.0005 < n < 0.02
     plain = synth_bases(1, 0, 100000, 0)
     assert set(np.unique(plain).tolist()) == set(b"ACGT")
+
+
+def test_exact_map_variant_of_the_cpu_baseline(coracle):
+    """nko_accumulate_exact_mt (hot path + the reference's per-task HashMap, merged `counts`, kmer_per_neuron —
+    spiking_hash.rs:96,157-172): same currents as the plain accumulate, |counts| and the per-neuron distinct
+    counts equal numpy's, for any thread count."""
+    rng = np.random.default_rng(8)
+    seqs = [rng.choice(np.frombuffer(b"ACGTNacgt", np.uint8), size=n).tobytes() for n in (200_000, 20, 0, 90_000, 31)]
+    bases = np.frombuffer(b"".join(seqs), np.uint8)
+    offsets = np.concatenate([[0], np.cumsum([len(s) for s in seqs])]).astype(np.uint64)
+    for k, pool, canon in ((21, 5000, True), (31, 100_003, True), (9, 4096, False)):
+        cur, tot = coracle.accumulate(bases, offsets, k, pool, canon, threads=2)
+        words = np.concatenate([coracle.kmer_words(s, k, canon) for s in seqs] + [np.zeros(0, np.uint64)])
+        keys = np.unique(words)
+        idx = np.array([coracle.neuron_index(int(w), pool) for w in keys], np.int64)
+        for threads in (1, 3, 8):
+            cur2, tot2, nd, uni = coracle.accumulate_exact(bases, offsets, k, pool, canon, threads=threads)
+            assert tot2 == tot and nd == keys.size
+            np.testing.assert_array_equal(cur2, cur)
+            np.testing.assert_array_equal(uni, np.bincount(idx, minlength=pool).astype(np.uint32))

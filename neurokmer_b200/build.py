@@ -43,15 +43,24 @@ def build(force: bool = False, verbose: bool = False) -> str:
     hdrs = [os.path.join(CSRC, h) for h in HEADERS]
     objs = []
     flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
+    jobs = []
     for src in SOURCES:
         sp = os.path.join(CSRC, src)
         obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
         objs.append(obj)
         if force or _stale(obj, [sp] + hdrs):
-            cmd = [nvcc] + flags + ["-c", sp, "-o", obj]
+            jobs.append([nvcc] + flags + ["-c", sp, "-o", obj])
+    if jobs:
+        # the translation units are independent: compile them side by side (nk_count.cu alone takes about a minute)
+        from concurrent.futures import ThreadPoolExecutor
+
+        def run(cmd):
             if verbose:
                 print(" ".join(cmd), file=sys.stderr)
             subprocess.check_call(cmd)
+
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as ex:
+            list(ex.map(run, jobs))
     if force or _stale(LIB, objs):
         cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-cudart", "static", "-Xlinker", "--no-undefined", "-lpthread", "-ldl", "-lrt", "-lz"]
         if verbose:

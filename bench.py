@@ -170,8 +170,9 @@ def reference_arm(args):
     threads = os.cpu_count() or 1
     # bounded sample: the whole --steps K --warmup W run should end within a few minutes.  The LIF + top-N part
     # (~0.2 s on 16 cores) is always run in full; the accumulate part is sized from a conservative rate of
-    # 15 Mbase/s per thread so that (K + W) steps take about 150 s, and never more than the whole workload.
-    budget_s = max(0.05, 150.0 / max(1, args.steps + args.warmup) - 0.2)
+    # 15 Mbase/s per thread so that (K + W) steps take about two minutes (measured on the 16-core GPU box: the
+    # fixed part of a step — LIF, top-N, array copies — is ~0.4 s), and never more than the whole workload.
+    budget_s = max(0.05, 100.0 / max(1, args.steps + args.warmup) - 0.3)
     sample = int(os.environ.get("NK_REF_SAMPLE_BASES", str(min(NBASES, 8_000_000 * threads, int(15e6 * threads * budget_s)))))
     sample = max(sample, 1_000_000)
     from oracle.synth import synth_bases

@@ -113,6 +113,21 @@ def test_host_packer_matches_numpy_twin(built):
     assert lib.nk_pack_bases(None, 5, None, None, 1, None) == built.NK_ERR_BAD_ARG
 
 
+def test_host_packer_against_golden_layout_vectors(built):
+    """tests/golden/golden_nk2.json pins the "nk2" layout (first base in bits 31:30, `other` bit p%32 of word p//32)."""
+    import json
+    from neurokmer_b200 import pack_bases
+    from oracle import oracle_py as op
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "golden_nk2.json")))
+    for row in g["rows"]:
+        b = row["bases"].encode("latin1")
+        codes, other, n_other = pack_bases(b)
+        nc, no = (len(b) + 15) // 16, (len(b) + 31) // 32
+        assert codes[:nc].tolist() == row["codes"] and other[:no].tolist() == row["other"] and n_other == row["n_other"]
+        tc, to, tn = op.pack_nk2(b)
+        assert tc.tolist() == row["codes"] and to.tolist() == row["other"] and tn == row["n_other"]
+
+
 def test_no_cpu_fallback_without_device(built):
     """Without a usable sm_100 device the product path must fail loudly, not compute on the CPU."""
     try:

@@ -36,6 +36,22 @@ def test_library_exports_every_declared_symbol(built):
     assert lib.nk_version().startswith(b"neurokmer-b200")
 
 
+def test_rust_shim_binds_only_declared_symbols():
+    """integration/rust/src/ffi.rs (source only — no rustc here) must not drift from the header: every
+    `pub fn nk_*` it declares is an entry point of include/neurokmer.h, and the #[repr(C)] structs list the
+    header's fields in the header's order."""
+    ffi = open(os.path.join(ROOT, "integration", "rust", "src", "ffi.rs")).read()
+    bound = set(re.findall(r"pub fn (nk_\w+)\s*\(", ffi))
+    assert len(bound) >= 30 and bound <= set(header_symbols()), bound - set(header_symbols())
+    hdr = open(HDR).read()
+    for c_name, rs_name in (("nk_config", "NkConfig"), ("nk_top_entry", "NkTopEntry")):
+        c_body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (c_name, c_name), hdr, re.S).group(1)
+        c_fields = re.findall(r"\b(\w+);", re.sub(r"/\*.*?\*/", "", c_body, flags=re.S))
+        rs_body = re.search(r"pub struct %s \{(.*?)\}" % rs_name, ffi, re.S).group(1)
+        rs_fields = re.findall(r"pub (\w+):", rs_body)
+        assert rs_fields == c_fields, (c_name, c_fields, rs_fields)
+
+
 def test_struct_layouts_match_c(built, tmp_path):
     src = tmp_path / "layout.c"
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "neurokmer.h"\nint main(){'

@@ -16,6 +16,7 @@
 #include <cerrno>
 #include <cstdint>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -75,6 +76,7 @@ struct Libs {
     size_t (*zs_free)(void*) = nullptr;
 };
 Libs g_libs;
+std::mutex g_libs_mu;  // distinct handles may open compressed files from different threads
 
 template <typename F>
 bool sym(void* lib, const char* name, F* out) {
@@ -83,6 +85,7 @@ bool sym(void* lib, const char* name, F* out) {
 }
 
 bool load_bz(std::string* err) {
+    std::lock_guard<std::mutex> lock(g_libs_mu);
     Libs& L = g_libs;
     if (L.bz_run) return true;
     L.bz = dlopen("libbz2.so.1.0", RTLD_NOW | RTLD_LOCAL);
@@ -96,6 +99,7 @@ bool load_bz(std::string* err) {
     return true;
 }
 bool load_xz(std::string* err) {
+    std::lock_guard<std::mutex> lock(g_libs_mu);
     Libs& L = g_libs;
     if (L.xz_code) return true;
     L.xz = dlopen("liblzma.so.5", RTLD_NOW | RTLD_LOCAL);
@@ -108,6 +112,7 @@ bool load_xz(std::string* err) {
     return true;
 }
 bool load_zs(std::string* err) {
+    std::lock_guard<std::mutex> lock(g_libs_mu);
     Libs& L = g_libs;
     if (L.zs_run) return true;
     L.zs = dlopen("libzstd.so.1", RTLD_NOW | RTLD_LOCAL);

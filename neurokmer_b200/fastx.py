@@ -23,7 +23,10 @@ def _open(path: str):
         return lzma.open(path, "rb")
     if magic == b"\x28\xb5\x2f\xfd":
         import io
-        import pyarrow as pa
+        try:
+            import pyarrow as pa  # the only zstd decoder in this image's Python (3.12 has no zstd module)
+        except ImportError as e:
+            raise OSError(f"{path}: zstd input needs pyarrow in this Python reader (the C++ reader decodes it itself)") from e
         with open(path, "rb") as f:
             return io.BytesIO(pa.input_stream(f, compression="zstd").read())
     return open(path, "rb")

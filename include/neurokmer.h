@@ -91,6 +91,16 @@ typedef struct nk_timings {
                           * top-N, 4 sharded-pool slice kernel, 5 memoised (one simulation per distinct state+count) */
     int32_t  _pad;
     uint64_t topn_launches; /* kernels launched by the last nk_top_n */
+    /* The fused fold + LIF + top-N kernel and, for sharded-pool multi-GPU jobs, the EXCHANGE reported on its
+     * own (north star: "the allreduce cost reported separately").  Measured by the kernels themselves with
+     * %globaltimer on this GPU; all 0 when the fused kernel did not run. */
+    float post_ms;          /* fused kernel: start -> result pack written */
+    float exch_wait_ms;     /* waiting for the peers: their "finished counting" flags (slice kernel) + their result
+                             * packs (merge kernel) — rank skew, not bytes */
+    float exch_reduce_ms;   /* the phase that reads this rank's neuron slice of EVERY rank's counts over NVLink peer
+                             * memory (reduce-scatter) fused with the LIF look-up and the top-N histogram */
+    float merge_ms;         /* merging the ranks' result packs */
+    uint64_t exch_bytes;    /* bytes this rank read from peer memory for the job */
 } nk_timings;
 
 /* ---- lifecycle ---------------------------------------------------------- */
@@ -107,6 +117,28 @@ NK_API int nk_reset(nk_counter* h);
 NK_API const char* nk_last_error(void);
 NK_API const char* nk_version(void);
 
+/* ---- one input sharded over several GPUs of THIS process --------------------------------------------
+ * The reference spreads one input over the cores of one process (rayon fold/reduce over per-thread current
+ * vectors, src/spiking_hash.rs:94-154; worker threads, :292-403).  nk_create_multi is the same thing with
+ * GPUs: the returned handle is used exactly like one from nk_create — nk_process_batch, nk_stream_*,
+ * nk_process_file, the packed variants, nk_top_n, totals, nk_copy_*, nk_uniques_* — and every batch is cut
+ * by window start into one contiguous range per device (sequences are cut wherever a range ends; the owner of
+ * starts [a, b) reads bases [a, min(b + k-1, end of sequence)), so every window is counted exactly once).
+ * Each device counts into its own accumulators; the exchange is a reduce-scatter fused into the LIF/top-N
+ * kernel over NVLink peer memory (device r owns neurons [r*P/N, (r+1)*P/N)), ordered by CUDA events.
+ * Results are bit-identical to a single-GPU counter.  `devices` = NULL means ordinals 0..n_devices-1;
+ * cfg->device is ignored.  Needs peer access between the devices (NK_ERR_UNSUPPORTED otherwise).
+ * Not available on a group handle (NK_ERR_UNSUPPORTED): nk_process_sequence (sequential by definition:
+ * replicas only), the exact side tables, device-resident staging, the nk_dist_* plumbing. */
+NK_API int nk_device_count(int32_t* n);
+NK_API int nk_create_multi(const nk_config* cfg, const int32_t* devices, int32_t n_devices, nk_counter** out);
+/* number of devices behind the handle (1 for nk_create) */
+NK_API int nk_group_size(const nk_counter* h, int32_t* n);
+/* Host-only view of the shard plan (needs no device): member `rank` of `world` reads the batch from base
+ * *start on and counts the pieces piece_offsets[0 .. *n_pieces] (relative to *start; capacity nseq+1). */
+NK_API int nk_debug_shard(const uint64_t* offsets, uint64_t nseq, uint32_t k, int32_t world, int32_t rank,
+                          uint64_t* start, uint64_t* piece_offsets, uint64_t* n_pieces);
+
 /* set_steps / get_steps — src/spiking_hash.rs:688-695 */
 NK_API int nk_set_steps(nk_counter* h, uint64_t steps);
 NK_API int nk_get_steps(const nk_counter* h, uint64_t* steps);
@@ -120,10 +152,17 @@ NK_API int nk_get_steps(const nk_counter* h, uint64_t* steps);
 NK_API int nk_process_batch(nk_counter* h, const uint8_t* bases, const uint64_t* offsets, uint64_t nseq);
 
 /* process_file_streaming minus parsing — src/spiking_hash.rs:277-486.
- * begin: zero the accumulators; push: count a batch (asynchronous: returns as
- * soon as the batch is staged, overlapping the next push's copy with this
- * push's kernels); end: totals OVERWRITE currents, then the streaming LIF
- * driver runs (every neuron stepped, :544-659). */
+ * begin: zero the accumulators; push: count a batch; end: totals OVERWRITE currents, then the
+ * streaming LIF driver runs (every neuron stepped, :544-659).
+ * When does push return?  Always once the caller's buffers may be reused, and no later:
+ *  - pageable memory: the batch is staged through the library's pinned ring in 32 MiB chunks; push returns
+ *    when the last chunk has been copied, with that chunk's kernels still running (the next push's copies
+ *    overlap them);
+ *  - pinned, device-mapped memory (nk_host_alloc, cudaHostAlloc, cudaHostRegister) at a 16-byte aligned
+ *    address: the count kernel reads the batch IN PLACE across PCIe (no staging copy), so push returns when
+ *    that kernel has finished — synchronous, but the copy it replaces would have taken as long.  The kernel's
+ *    16-byte bulk reads may touch up to 15 bytes past offsets[nseq] (never past the end of the page that
+ *    holds the last base).  NK_ZEROCOPY=0 in the environment forces the staged path. */
 NK_API int nk_stream_begin(nk_counter* h);
 NK_API int nk_stream_push(nk_counter* h, const uint8_t* bases, const uint64_t* offsets, uint64_t nseq);
 NK_API int nk_stream_end(nk_counter* h);
@@ -244,6 +283,10 @@ NK_API int nk_last_timings(const nk_counter* h, nk_timings* out);
  * parameters allow it, else one per neuron), 1 = always one simulation per neuron (direct),
  * 2 = never the per-count table (memoised even from the initial state). */
 NK_API int nk_debug_set_lif_path(nk_counter* h, int mode);
+/* The u32 batch accumulators are folded away (into the u64 currents; on a sharded-pool handle into the u64 spill
+ * array its peers read) before more than `limit` window starts could have been added to them.  Default and
+ * maximum 2^32-1; tests lower it to exercise the guard without 4.3 Gbase of input. */
+NK_API int nk_debug_set_fold_limit(nk_counter* h, uint64_t limit);
 
 /* Roofline denominators measured on this device (micro-kernels, CUDA events, best of 3):
  *   which 0: 32-bit ALU-pipe ops/s of independent LOP3+SHF chains (xor/rotate: what SipHash

@@ -4,8 +4,8 @@ The product is `libneurokmer.so` (C ABI, include/neurokmer.h).  This package is 
 host-side mirror of the reference's public counter API over that ABI.  Importing the
 counter classes requires the built shared library; there is no CPU fallback.
 """
-from .counter import (PinnedBuffer, PySpikingCounter, SpikingKmerCounter, flatten, pack_bases,  # noqa: F401
-                      pack_kmer, pack_kmer_py)
+from .counter import (PinnedBuffer, PySpikingCounter, SpikingKmerCounter, device_count, flatten,  # noqa: F401
+                      pack_bases, pack_kmer, pack_kmer_py)
 from ._lib import NkError  # noqa: F401
 
-__all__ = ["SpikingKmerCounter", "PySpikingCounter", "PinnedBuffer", "flatten", "pack_bases", "pack_kmer", "pack_kmer_py", "NkError"]
+__all__ = ["SpikingKmerCounter", "PySpikingCounter", "PinnedBuffer", "device_count", "flatten", "pack_bases", "pack_kmer", "pack_kmer_py", "NkError"]

@@ -31,6 +31,7 @@ SYMBOLS = [
     "nk_stream_push_packed", "nk_debug_kmers_packed", "nk_debug_pack_body", "nk_stage_reserve_packed",
     "nk_process_staged_packed", "nk_debug_fastx_digest", "nk_dist_run",
     "nk_debug_fasta_windows_digest", "nk_uniques_begin", "nk_uniques_push", "nk_uniques_push_packed", "nk_uniques_end", "nk_set_file_uniques",
+    "nk_debug_set_fold_limit", "nk_device_count", "nk_create_multi", "nk_group_size", "nk_debug_shard",
 ]
 
 
@@ -52,6 +53,8 @@ class NkTimings(C.Structure):
         ("lif_ms", C.c_float), ("topn_ms", C.c_float), ("total_ms", C.c_float),
         ("kmers", C.c_uint64), ("launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
         ("lif_path", C.c_int32), ("_pad", C.c_int32), ("topn_launches", C.c_uint64),
+        ("post_ms", C.c_float), ("exch_wait_ms", C.c_float), ("exch_reduce_ms", C.c_float), ("merge_ms", C.c_float),
+        ("exch_bytes", C.c_uint64),
     ]
 
     def as_dict(self):
@@ -76,6 +79,10 @@ def load() -> C.CDLL:
         "nk_config_default": (i32, [P(NkConfig)]),
         "nk_create": (i32, [P(NkConfig), P(vp)]),
         "nk_destroy": (i32, [vp]),
+        "nk_device_count": (i32, [P(C.c_int32)]),
+        "nk_create_multi": (i32, [P(NkConfig), P(C.c_int32), C.c_int32, P(vp)]),
+        "nk_group_size": (i32, [vp, P(C.c_int32)]),
+        "nk_debug_shard": (i32, [vp, u64, u32, C.c_int32, C.c_int32, P(u64), vp, P(u64)]),
         "nk_reset": (i32, [vp]),
         "nk_last_error": (C.c_char_p, []),
         "nk_version": (C.c_char_p, []),
@@ -105,6 +112,7 @@ def load() -> C.CDLL:
         "nk_copy_refractory": (i32, [vp, vp]),
         "nk_last_timings": (i32, [vp, P(NkTimings)]),
         "nk_debug_set_lif_path": (i32, [vp, i32]),
+        "nk_debug_set_fold_limit": (i32, [vp, u64]),
         "nk_calibrate": (i32, [vp, i32, P(C.c_double)]),
         "nk_stage_reserve": (i32, [vp, u64, u64, P(vp), P(vp)]),
         "nk_process_staged": (i32, [vp, u64, u64, i32]),

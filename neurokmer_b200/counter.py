@@ -95,7 +95,9 @@ class SpikingKmerCounter:
     """reference src/spiking_hash.rs:16-37 (`new` at :40-77)."""
 
     def __init__(self, k: int, threshold: float, leak: float, refractory: int, spike_cost: float,
-                 pool_size: int, use_canonical: bool, device: int = 0):
+                 pool_size: int, use_canonical: bool, device: int = 0, devices: Optional[Sequence[int]] = None):
+        """`devices`: shard every input over these GPUs inside this process (nk_create_multi); the object is
+        used exactly like a single-GPU counter."""
         self._L = _lib.lib()
         cfg = NkConfig()
         check(self._L.nk_config_default(C.byref(cfg)))
@@ -103,9 +105,18 @@ class SpikingKmerCounter:
         cfg.refractory, cfg.spike_cost, cfg.pool_size = refractory, spike_cost, pool_size
         cfg.use_canonical, cfg.device = int(bool(use_canonical)), device
         self._h = C.c_void_p()
-        check(self._L.nk_create(C.byref(cfg), C.byref(self._h)))
+        if devices is not None:
+            arr = (C.c_int32 * len(devices))(*[int(d) for d in devices])
+            check(self._L.nk_create_multi(C.byref(cfg), arr, len(devices), C.byref(self._h)))
+        else:
+            check(self._L.nk_create(C.byref(cfg), C.byref(self._h)))
         self.k, self.pool_size, self.use_canonical = k, pool_size, bool(use_canonical)
         self.energy = _Energy(self)
+
+    def group_size(self) -> int:
+        n = C.c_int32()
+        check(self._L.nk_group_size(self._h, C.byref(n)))
+        return n.value
 
     # lifecycle ------------------------------------------------------------
     def close(self) -> None:
@@ -304,6 +315,9 @@ class SpikingKmerCounter:
     def debug_set_lif_path(self, mode: int) -> None:
         check(self._L.nk_debug_set_lif_path(self._h, mode))
 
+    def debug_set_fold_limit(self, limit: int) -> None:
+        check(self._L.nk_debug_set_fold_limit(self._h, limit))
+
     def calibrate(self, which: int) -> float:
         out = C.c_double()
         check(self._L.nk_calibrate(self._h, which, C.byref(out)))
@@ -380,6 +394,22 @@ class SpikingKmerCounter:
 
     def synchronize(self) -> None:
         check(self._L.nk_synchronize(self._h))
+
+
+def debug_shard(offsets: np.ndarray, k: int, world: int, rank: int) -> Tuple[int, np.ndarray]:
+    """(start, piece offsets relative to start) of member `rank` in the shard plan of a batch (host only)."""
+    offsets = np.ascontiguousarray(offsets, np.uint64)
+    out = np.zeros(offsets.size, np.uint64)
+    start, n = C.c_uint64(), C.c_uint64()
+    check(_lib.lib().nk_debug_shard(offsets.ctypes.data, offsets.size - 1, k, world, rank, C.byref(start),
+                                    out.ctypes.data, C.byref(n)))
+    return int(start.value), out[: n.value + 1].copy()
+
+
+def device_count() -> int:
+    n = C.c_int32()
+    check(_lib.lib().nk_device_count(C.byref(n)))
+    return n.value
 
 
 def debug_mod(values: np.ndarray, pool_size: int, which: int = 0) -> np.ndarray:

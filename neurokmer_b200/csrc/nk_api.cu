@@ -20,11 +20,9 @@
 #include <string>
 #include <vector>
 
-#include "../../include/neurokmer.h"
-#include "nk_host.h"
-#include "nk_kernels.cuh"
+#include "nk_internal.h"
 
-namespace {
+namespace nkd {
 
 thread_local std::string g_err;
 
@@ -38,153 +36,6 @@ int fail(int code, const char* fmt, ...) {
     return code;
 }
 
-#define NK_CUDA(expr)                                                                          \
-    do {                                                                                       \
-        cudaError_t e_ = (expr);                                                               \
-        if (e_ != cudaSuccess)                                                                 \
-            return fail(e_ == cudaErrorMemoryAllocation ? NK_ERR_OOM : NK_ERR_CUDA, "%s: %s", #expr, \
-                        cudaGetErrorString(e_));                                               \
-    } while (0)
-
-#define NK_TRY(expr)              \
-    do {                          \
-        int rc_ = (expr);         \
-        if (rc_ != NK_OK) return rc_; \
-    } while (0)
-
-constexpr size_t kMaxTimedChunks = 1024;
-constexpr unsigned long long kChunkBytes = 32ull << 20;  // host->device pipeline granule (multiple of COUNT_TILE)
-static_assert(kChunkBytes % nk::COUNT_TILE == 0, "chunks must be whole tiles");
-
-struct DevBuf {
-    unsigned char* bases = nullptr;
-    unsigned long long bases_cap = 0;
-    unsigned int* invalid = nullptr;
-    unsigned long long invalid_cap = 0;  // words
-    cudaEvent_t copy_done = nullptr, compute_done = nullptr;
-    // pre-packed input (nk_*_packed): 2-bit code words and `other` bits of the chunk
-    unsigned char* codes = nullptr;
-    unsigned long long codes_cap = 0;
-    unsigned char* other = nullptr;
-    unsigned long long other_cap = 0;
-    bool has_other = false;  // this chunk's `other` array was supplied
-    // zero-copy views: readable bytes (multiples of 16) of bases/codes and other from the view's start; 0 = padded
-    unsigned long long bases_bytes = 0, other_bytes = 0;
-};
-
-struct PhaseEvents {
-    std::vector<cudaEvent_t> mark0, count0, count1;
-    cudaEvent_t begin = nullptr, copy0 = nullptr, copy1 = nullptr, fold0 = nullptr, fold1 = nullptr,
-                lif1 = nullptr, end = nullptr;
-};
-
-}  // namespace
-
-struct nk_counter {
-    nk_config cfg{};
-    nk::FastMod fm{};
-    cudaStream_t stream = nullptr, copy_stream = nullptr;
-
-    // pool state (device)
-    unsigned int* acc = nullptr;           // u32 batch accumulators (RED target)
-    unsigned long long* currents = nullptr;
-    float* v = nullptr;
-    unsigned int* r = nullptr;
-    unsigned long long* spikes = nullptr;
-    unsigned long long* scalars = nullptr;  // [0] spikes fired by last LIF, [1] max cumulative spikes, [2] kmers
-    unsigned int* tile_counter = nullptr;
-    unsigned long long* h_scalars = nullptr;  // pinned mirror
-
-    // carried-state LIF by memoisation (allocated at first use)
-    nk::LifMemo memo{};
-    // LIF per-count table
-    nk::LifTable table{};
-    unsigned long long table_cap = 0;
-
-    // top-N scratch
-    nk::TopNScratch topn{};
-    unsigned long long topn_cap = 0;
-    nk_top_entry* h_top = nullptr;  // pinned, topn_cap rows (built from two arrays)
-
-    // host mirrors (EnergyTracker, src/models.rs:145-173)
-    unsigned long long total_spikes = 0, energy_fixed = 0;
-    bool fresh = true;      // every neuron still has v = 0, r = 0
-    // after nk_reset the pool arrays (currents, v, r, spikes) are LOGICALLY zero but not yet written:
-    // the fused fold+LIF kernel of the next job overwrites all four, anything else materialises first
-    bool lazy_zero = false;
-    int force_direct = 0;
-    bool streaming = false;
-    bool acc_dirty = false;
-    unsigned long long acc_kmers = 0;  // windows added to acc since the last fold (u32 overflow guard)
-    bool currents_valid_overwrite = true;  // next fold overwrites currents (first fold of a call)
-
-    // staging
-    DevBuf buf[2];
-    int cur_buf = 0;
-    // offsets of host batches: two buffers alternate so that batch i+1's copy never waits for batch i's kernels
-    unsigned long long* d_offsets2[2] = {nullptr, nullptr};
-    unsigned long long offsets_cap2[2] = {0, 0};
-    cudaEvent_t offsets_done[2] = {nullptr, nullptr};
-    int cur_off = 0;
-    // device-resident staged batch (nk_stage_reserve)
-    DevBuf staged;
-    uint8_t* file_batch[2] = {nullptr, nullptr};  // pinned, 32 MiB each: the file driver's double buffer
-    DevBuf zc;  // zero-copy pushes: just the invalid-start bitmap of the body (the bases stay in host memory)
-    unsigned long long* staged_offsets = nullptr;
-    unsigned long long staged_offsets_cap = 0;
-
-    std::vector<cudaEvent_t> evpool;
-    size_t ev_used = 0;
-    nk_timings last{};
-
-    // a process/stream call returns with its read-back (new spikes, k-mers) and event timings
-    // still in flight on `stream`; resolve() waits for them the first time anything observes them
-    bool pending = false, pending_lif = false, pending_timings = false;
-    PhaseEvents pend_pe;
-    PhaseEvents stream_pe;  // mark/count event pairs of the pushes between stream_begin and stream_finish
-    // host-side upper bound of the largest cumulative spike count (bounds the top-N radix passes
-    // without a device round trip): each LIF call adds at most ceil(steps / (refractory + 1))
-    unsigned long long spike_bound = 0;
-    // fused post kernel (fold + LIF table + top-N): scratch, result pack, cached rows
-    int post_grid = 0;
-    unsigned long long* post_zero = nullptr;   // [8 u64 ctrl][8*256 u32 hist] zeroed before each launch
-    unsigned long long* d_pack = nullptr;      // 4 + 2*2048 u64
-    unsigned long long* h_pack = nullptr;      // pinned mirror
-    unsigned long long topn_hint = 20;         // rows computed speculatively by the fused kernel (CLI: 20)
-    unsigned long long top_cached_n = 0;       // rows of the last fused launch (valid until state changes)
-    bool top_cache_valid = false, pending_pack = false;
-    // multi-GPU sharded-pool mode (nk_dist_*): peer mappings of every rank's accumulators
-    int dist_rank = 0, dist_world = 0;
-    const unsigned int* dist_peer[16] = {};
-    bool dist_ipc_opened[16] = {};
-    unsigned long long dist_lo = 0, dist_len = 0;
-    unsigned long long* d_merged = nullptr;
-    // peer-signalled mode (nk_dist_run): every rank's mailbox (tail of its accumulator allocation)
-    unsigned char* dist_mail[16] = {};
-    unsigned long long dist_epoch = 0;
-    bool dist_failed = false;
-    // exact side tables (opt-in, nk_enable_exact_counts)
-    bool exact = false;
-    nk::ExactTable xt;
-    unsigned int* d_top_uniques = nullptr;
-    // uniques pass (nk_uniques_*): `uniques` of the top rows by a second pass over the input, without the
-    // O(windows) exact table — the words that map to the rows' neurons are collected, sorted and counted
-    nk::ExactTable ut;
-    unsigned int* d_filter = nullptr;        // pool_size bits: neurons of the fixed rows
-    unsigned long long* d_rows = nullptr;    // their indices (device), row order
-    unsigned long long d_rows_cap = 0;
-    std::vector<unsigned long long> row_idx; // rows fixed by nk_uniques_begin
-    std::vector<unsigned int> row_uniques;   // filled by nk_uniques_end
-    bool rows_valid = false, uniques_open = false;
-    unsigned long long ut_count = 0;         // host mirror of the append cursor
-    unsigned long long file_uniques = 0;     // nk_set_file_uniques: rows nk_process_file resolves by re-reading the file
-    bool table_valid = false, table_inflight = false;
-    cudaEvent_t table_ready = nullptr;
-    nk_config table_cfg{};
-    unsigned long long table_n = 0;
-};
-
-namespace {
 
 int get_event(nk_counter* h, cudaEvent_t* out) {
     if (h->ev_used == h->evpool.size()) {
@@ -299,6 +150,35 @@ int fold_now(nk_counter* h) {
     return NK_OK;
 }
 
+unsigned char* own_mail(nk_counter* h) {
+    return reinterpret_cast<unsigned char*>(h->acc) + nk::dist_mail_offset(h->cfg.pool_size);
+}
+
+// sharded-pool handles: acc -> spill (u64, visible to the peers), and raise this rank's "spilled" flag
+int spill_now(nk_counter* h) {
+    if (!h->acc_dirty) return NK_OK;
+    NK_CUDA(nk::launch_fold(h->acc, h->spill, h->cfg.pool_size, /*overwrite=*/!h->spill_dirty, h->stream));
+    ++h->last.launches;
+    if (!h->spill_dirty) NK_CUDA(cudaMemsetAsync(nk::dist_mail_flags(own_mail(h), 2), 1, 1, h->stream));  // u64 flag = 1
+    h->spill_dirty = true;
+    h->acc_dirty = false;
+    h->acc_kmers = 0;
+    return NK_OK;
+}
+
+// a stream that spilled ends on the NON-sharded path after all (all-reduce flow, plain stream_end): the
+// spilled counts join `currents` like a fold would have put them there
+int unspill(nk_counter* h) {
+    if (!h->spill_dirty) return NK_OK;
+    NK_TRY(materialize_zero(h));
+    NK_CUDA(nk::launch_fold64(h->spill, h->currents, h->cfg.pool_size, h->currents_valid_overwrite, h->stream));
+    ++h->last.launches;
+    NK_CUDA(cudaMemsetAsync(nk::dist_mail_flags(own_mail(h), 2), 0, 8, h->stream));
+    h->currents_valid_overwrite = false;
+    h->spill_dirty = false;
+    return NK_OK;
+}
+
 // mark + count one device-resident chunk: window starts [origin, origin+nstarts) of the
 // concatenated batch, whose bytes live at `b.bases` (chunk-relative) and whose offsets
 // (batch-absolute) live at d_offsets.
@@ -308,7 +188,7 @@ int count_chunk(nk_counter* h, DevBuf& b, const unsigned long long* d_offsets, u
                 unsigned long long seq_hi, unsigned long long origin, unsigned long long nstarts,
                 unsigned long long max_windows, PhaseEvents* pe, bool packed = false) {
     if (nstarts == 0) return NK_OK;
-    if (h->acc_kmers + max_windows > 0xFFFFFFFFull) NK_TRY(fold_now(h));
+    if (h->acc_kmers + max_windows > h->fold_limit) NK_TRY(h->dist_world > 0 && h->streaming ? spill_now(h) : fold_now(h));
     cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
     // phase timing covers at most kMaxTimedChunks chunks of a job (bounds the event pool of very long
     // streams; nk_timings.kmers and all results are unaffected)
@@ -374,7 +254,9 @@ int uniques_host_batch(nk_counter* h, const uint8_t* bases, const uint32_t* code
 
 // host batch -> chunked H2D (copy stream) overlapped with mark+count (compute stream)
 int count_host_batch(nk_counter* h, const uint8_t* bases, const uint64_t* offsets, uint64_t nseq, PhaseEvents* pe,
-                     bool wait_copies = true) {
+                     int sync) {
+    const bool wait_copies = sync != kPushFileDriver;
+    h->last_push_zc = false;
     if (nseq == 0) return NK_OK;
     if (h->uniques_open) return uniques_host_batch(h, bases, nullptr, nullptr, offsets, nseq);  // second read of a file
     for (uint64_t s = 0; s < nseq; ++s)
@@ -455,8 +337,11 @@ int count_host_batch(nk_counter* h, const uint8_t* bases, const uint64_t* offset
     }
     // the caller's buffers must be reusable on return: wait for the copies (not the kernels).
     // The file driver owns its pinned batches and double-buffers them instead (wait_copies = false).
-    if (wait_copies) NK_CUDA(cudaStreamSynchronize(h->copy_stream));
-    if (zc_body) NK_CUDA(cudaStreamSynchronize(h->stream));  // the kernel itself read the caller's buffer
+    h->last_push_zc = zc_body != 0;
+    if (sync == kPushSync) {
+        NK_CUDA(cudaStreamSynchronize(h->copy_stream));
+        if (zc_body) NK_CUDA(cudaStreamSynchronize(h->stream));  // the kernel itself read the caller's buffer
+    }
     return NK_OK;
 }
 
@@ -472,7 +357,8 @@ unsigned long long packed_chunk_bases() {
 }
 
 int count_host_batch_packed(nk_counter* h, const uint32_t* codes, const uint32_t* other, const uint64_t* offsets,
-                            uint64_t nseq, PhaseEvents* pe, bool wait_copies = true) {
+                            uint64_t nseq, PhaseEvents* pe, int sync) {
+    h->last_push_zc = false;
     if (nseq == 0) return NK_OK;
     for (uint64_t s = 0; s < nseq; ++s)
         if (offsets[s + 1] < offsets[s]) return fail(NK_ERR_BAD_ARG, "offsets must be non-decreasing (at %llu)", (unsigned long long)s);
@@ -563,8 +449,11 @@ int count_host_batch_packed(nk_counter* h, const uint32_t* codes, const uint32_t
         if (!pe->copy1) NK_TRY(get_event(h, &pe->copy1));
         NK_CUDA(cudaEventRecord(pe->copy1, h->copy_stream));
     }
-    if (wait_copies) NK_CUDA(cudaStreamSynchronize(h->copy_stream));
-    if (zc_body) NK_CUDA(cudaStreamSynchronize(h->stream));  // the kernel itself read the caller's arrays
+    h->last_push_zc = zc_body != 0;
+    if (sync == kPushSync) {
+        NK_CUDA(cudaStreamSynchronize(h->copy_stream));
+        if (zc_body) NK_CUDA(cudaStreamSynchronize(h->stream));  // the kernel itself read the caller's arrays
+    }
     return NK_OK;
 }
 
@@ -719,7 +608,7 @@ int prelaunch_table(nk_counter* h) {
 // LIF over this call's totals; skip_zero: in-memory driver (:187-200) vs SIMD driver (:544-659).
 // If the u32 batch accumulators still hold counts they are folded into `currents` by the LIF
 // kernel itself (fold_mode), otherwise the stored currents are used as they are.
-int simulate(nk_counter* h, bool skip_zero, bool with_topn = false) {
+int simulate(nk_counter* h, bool skip_zero, bool with_topn) {
     h->last.lif_path = 0;
     h->top_cache_valid = false;
     int fold_mode = 0;
@@ -827,6 +716,16 @@ int simulate(nk_counter* h, bool skip_zero, bool with_topn = false) {
     return NK_OK;
 }
 
+// `(cost * 1000.0) as u64` — src/models.rs:162, src/spiking_hash.rs:649.  Rust's float -> integer `as` cast
+// truncates toward zero and saturates (NaN -> 0, negative -> 0, >= 2^64 -> u64::MAX); the same cast is
+// undefined behaviour in C++ outside [0, 2^64), so the clamp is explicit.
+unsigned long long cost_fixed(double spike_cost) {
+    const double x = spike_cost * 1000.0;
+    if (!(x > 0.0)) return 0ull;
+    if (x >= 18446744073709551616.0) return ~0ull;
+    return (unsigned long long)x;
+}
+
 float ev_ms(cudaEvent_t a, cudaEvent_t b) {
     float ms = 0.f;
     if (a && b) cudaEventElapsedTime(&ms, a, b);
@@ -850,7 +749,7 @@ void collect_timings(nk_counter* h, const PhaseEvents& pe) {
 // enqueue the read-back of {new spikes, max spikes, kmers}; nothing waits here
 int finish_call(nk_counter* h, bool had_lif, const PhaseEvents* pe) {
     if (h->pending_pack) {  // fused post kernel: scalars and the sorted top-N rows come back in one copy
-        const size_t bytes = (4 + 2 * h->top_cached_n) * sizeof(unsigned long long);
+        const size_t bytes = (nk::PACK_HDR + 2 * h->top_cached_n) * sizeof(unsigned long long);
         NK_CUDA(cudaMemcpyAsync(h->h_pack, h->d_pack, bytes, cudaMemcpyDeviceToHost, h->stream));
         h->last.d2h_bytes += bytes;
     } else {
@@ -870,6 +769,7 @@ int resolve(nk_counter* h) {
     NK_CUDA(cudaSetDevice(h->cfg.device));
     NK_CUDA(cudaStreamSynchronize(h->stream));
     h->pending = false;
+    const bool had_pack = h->pending_pack;
     if (h->pending_pack) {
         h->h_scalars[0] = h->h_pack[0];
         h->h_scalars[2] = h->h_pack[2];
@@ -887,9 +787,24 @@ int resolve(nk_counter* h) {
         const unsigned long long fired = h->h_scalars[0];
         h->total_spikes += fired;
         // src/models.rs:162-163 / src/spiking_hash.rs:649-655
-        h->energy_fixed += fired * (unsigned long long)(h->cfg.spike_cost * 1000.0);
+        h->energy_fixed += fired * cost_fixed(h->cfg.spike_cost);
     }
     h->last.kmers = h->h_scalars[2];
+    if (had_pack) {
+        // %globaltimer stamps of the fused kernel(s), nanoseconds on this GPU's clock (see nk_post.cu)
+        const unsigned long long* t = h->h_pack + 4;
+        auto ms = [](unsigned long long a, unsigned long long b) { return b > a ? (float)((double)(b - a) * 1e-6) : 0.f; };
+        h->last.post_ms = ms(t[0], t[3]);
+        if (h->dist_job) {
+            h->last.exch_wait_ms = ms(t[0], t[1]) + ms(t[4], t[5]);
+            h->last.exch_reduce_ms = ms(t[1], t[2]);
+            h->last.merge_ms = ms(t[5], t[6]);
+            // peer memory read by this rank's slice kernel (u32 counts of its slice on every OTHER rank) + the packs
+            h->last.exch_bytes = (unsigned long long)(h->dist_world - 1) *
+                                 (h->dist_len * 4ull + (nk::PACK_HDR + 2 * h->dist_n_each) * 8ull);
+        }
+        h->dist_job = false;
+    }
     if (h->pending_timings) collect_timings(h, h->pend_pe);
     h->pend_pe = PhaseEvents{};
     return NK_OK;
@@ -918,6 +833,7 @@ int free_devbuf(DevBuf& b) {
 int fold_and_simulate(nk_counter* h, bool skip_zero, PhaseEvents& pe, bool with_topn = true) {
     NK_TRY(get_event(h, &pe.fold0));
     NK_CUDA(cudaEventRecord(pe.fold0, h->stream));
+    NK_TRY(unspill(h));
     if (!h->acc_dirty && h->currents_valid_overwrite) {
         // nothing was counted by this call: totals are all zero (currents are OVERWRITTEN, :174-176)
         NK_TRY(materialize_zero(h));
@@ -937,7 +853,9 @@ int fold_and_simulate(nk_counter* h, bool skip_zero, PhaseEvents& pe, bool with_
     return NK_OK;
 }
 
-}  // namespace
+}  // namespace nkd
+
+using namespace nkd;
 
 // ---------------------------------------------------------------------------
 // Whole-file driver (nk_process_file): FastxReader -> pinned batch -> count_host_batch.
@@ -1101,7 +1019,7 @@ int count_fasta_parallel(nk_counter* h, const char* path, PhaseEvents& pe, std::
                 memcpy(carry, data + sl.fill - carry_len, carry_len);
             }
             if (ov + sl.fill > 0) {
-                rc = count_host_batch(h, data - ov, offsets.data(), offsets.size() - 1, &pe, /*wait_copies=*/false);
+                rc = count_host_batch(h, data - ov, offsets.data(), offsets.size() - 1, &pe, kPushFileDriver);
                 if (rc != NK_OK) { *err = g_err; break; }
                 cudaEventRecord(sl.copied, h->copy_stream);
                 sl.copy_inflight = true;
@@ -1201,7 +1119,7 @@ int count_fastq_parallel(nk_counter* h, const char* path, PhaseEvents& pe, std::
                 sl.state = 0;
             }
             if (!stop && sl.fill > 0 && sl.offs.size() > 1) {
-                rc = count_host_batch(h, sl.buf, sl.offs.data(), sl.offs.size() - 1, &pe, /*wait_copies=*/false);
+                rc = count_host_batch(h, sl.buf, sl.offs.data(), sl.offs.size() - 1, &pe, kPushFileDriver);
                 if (rc != NK_OK) { *err = g_err; break; }
                 cudaEventRecord(sl.copied, h->copy_stream);
                 sl.copy_inflight = true;
@@ -1257,12 +1175,27 @@ int process_file(nk_counter* h, const char* path, bool streaming, std::string* e
     size_t fill = 0;
     const unsigned k = h->cfg.k;
 
-    if (!ingest_only) begin_call(h);
+    // a multi-GPU group handle: every batch is sharded over the members (group_push waits for the members'
+    // copies, and for the kernels that read the pinned batch in place, before the parser refills it)
+    const bool grp = is_group(h);
+    if (!ingest_only && !grp) begin_call(h);
     PhaseEvents pe;
     int rc = NK_OK;
+    if (grp && !ingest_only && (rc = group_begin(h)) != NK_OK) { *err = g_err; for (int i = 0; i < 2; ++i) cudaEventDestroy(copied[i]); return rc; }
     auto flush = [&]() -> int {
+        if (grp) {
+            if (offsets.size() > 1 && fill > 0) {
+                int r = ingest_only ? nk_uniques_push(h->group[0], batch, offsets.data(), offsets.size() - 1)
+                                    : group_push(h, batch, nullptr, nullptr, offsets.data(), offsets.size() - 1);
+                if (r != NK_OK) { *err = g_err; return r; }
+            }
+            offsets.clear();
+            offsets.push_back(0);
+            fill = 0;
+            return NK_OK;
+        }
         if (offsets.size() > 1 && fill > 0) {
-            int r = count_host_batch(h, batch, offsets.data(), offsets.size() - 1, &pe, /*wait_copies=*/false);
+            int r = count_host_batch(h, batch, offsets.data(), offsets.size() - 1, &pe, kPushFileDriver);
             if (r != NK_OK) { *err = g_err; return r; }
             cudaEventRecord(copied[cur], h->copy_stream);
             inflight[cur] = true;
@@ -1276,14 +1209,14 @@ int process_file(nk_counter* h, const char* path, bool streaming, std::string* e
         return NK_OK;
     };
     do {
-        if (!ingest_only) {
+        if (!ingest_only && !grp) {
             if (get_event(h, &pe.begin) != NK_OK) { *err = g_err; rc = NK_ERR_CUDA; break; }
             cudaEventRecord(pe.begin, h->stream);
             cudaMemsetAsync(h->scalars + 2, 0, sizeof(unsigned long long), h->stream);
             h->currents_valid_overwrite = true;
         }
         bool stop = false;
-        if (!rd.is_compressed()) {
+        if (!rd.is_compressed() && !grp) {
             bool handled = false;
             rc = rd.is_fastq() ? count_fastq_parallel(h, path, pe, err, &handled) : count_fasta_parallel(h, path, pe, err, &handled);
             if (rc != NK_OK) break;
@@ -1333,14 +1266,24 @@ int process_file(nk_counter* h, const char* path, bool streaming, std::string* e
         if (rc != NK_OK) break;
         if ((rc = flush()) != NK_OK) break;
         if (ingest_only) break;
+        if (grp) {
+            if ((rc = group_end(h, /*skip_zero=*/!streaming)) != NK_OK) { *err = g_err; break; }
+            uint64_t spikes = 0;
+            if ((rc = nk_total_spikes(h, &spikes)) != NK_OK) *err = g_err;  // observes the result: surfaces device errors here
+            break;
+        }
         if ((rc = fold_and_simulate(h, /*skip_zero=*/!streaming, pe)) != NK_OK) { *err = g_err; break; }
         if (get_event(h, &pe.end) != NK_OK) { *err = g_err; rc = NK_ERR_CUDA; break; }
         cudaEventRecord(pe.end, h->stream);
         if ((rc = finish_call(h, true, &pe)) != NK_OK) { *err = g_err; break; }
         if ((rc = resolve(h)) != NK_OK) { *err = g_err; break; }
     } while (0);
-    cudaStreamSynchronize(h->copy_stream);
-    cudaStreamSynchronize(h->stream);
+    if (grp) {
+        if (rc != NK_OK && !ingest_only) group_reset(h);
+    } else {
+        cudaStreamSynchronize(h->copy_stream);
+        cudaStreamSynchronize(h->stream);
+    }
     for (int i = 0; i < 2; ++i) cudaEventDestroy(copied[i]);
     return rc;
 }
@@ -1399,8 +1342,9 @@ int nk_create(const nk_config* cfg, nk_counter** out) {
     NK_C(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     const unsigned long long P = cfg->pool_size;
     // the accumulators carry the multi-GPU mailbox at their tail: one IPC handle maps both into the peers
-    NK_C(cudaMalloc(&h->acc, nk::dist_mail_offset(P) + nk::DIST_MAIL_BYTES));
+    NK_C(cudaMalloc(&h->acc, nk::dist_alloc_bytes(P)));
     NK_C(cudaMemset(reinterpret_cast<unsigned char*>(h->acc) + nk::dist_mail_offset(P), 0, nk::DIST_MAIL_BYTES));
+    h->spill = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(h->acc) + nk::dist_spill_offset(P));
     NK_C(cudaMalloc(&h->currents, P * sizeof(unsigned long long)));
     NK_C(cudaMalloc(&h->v, P * sizeof(float)));
     NK_C(cudaMalloc(&h->r, P * sizeof(unsigned int)));
@@ -1413,8 +1357,8 @@ int nk_create(const nk_config* cfg, nk_counter** out) {
     NK_C(cudaMalloc(&h->topn.block_counts, ((P + nk::POST_SEG_ITEMS - 1) / nk::POST_SEG_ITEMS + 1) * sizeof(unsigned int)));
     NK_C(nk::post_max_grid(cfg->device, &h->post_grid));
     NK_C(cudaMalloc(&h->post_zero, 8 * sizeof(unsigned long long) + 8 * 256 * sizeof(unsigned int)));
-    NK_C(cudaMalloc(&h->d_pack, (4 + 2 * 2048) * sizeof(unsigned long long)));
-    NK_C(cudaMallocHost(&h->h_pack, (4 + 2 * 2048) * sizeof(unsigned long long)));
+    NK_C(cudaMalloc(&h->d_pack, nk::PACK_MAX_U64 * sizeof(unsigned long long)));
+    NK_C(cudaMallocHost(&h->h_pack, nk::PACK_MAX_U64 * sizeof(unsigned long long)));
     NK_C(cudaMalloc(&h->topn.out_idx, 2048 * sizeof(unsigned long long)));
     NK_C(cudaMalloc(&h->topn.out_spikes, 2048 * sizeof(unsigned long long)));
     NK_C(cudaMallocHost(&h->h_top, 2 * 2048 * sizeof(unsigned long long)));
@@ -1428,12 +1372,17 @@ int nk_create(const nk_config* cfg, nk_counter** out) {
 }
 
 int nk_reset(nk_counter* h) {
+    if (is_group(h)) return group_reset(h);
     if (!h) return fail(NK_ERR_BAD_ARG, "null handle");
     NK_CUDA(cudaSetDevice(h->cfg.device));
     const unsigned long long P = h->cfg.pool_size;
     // acc is all-zero whenever no batch is in flight (every fold zeroes it): only a reset in the
     // middle of a stream has to clear it.  currents / v / r / spikes become lazily zero.
     if (h->acc_dirty || h->streaming) NK_CUDA(cudaMemsetAsync(h->acc, 0, P * sizeof(unsigned int), h->stream));
+    if (h->spill_dirty) {
+        NK_CUDA(cudaMemsetAsync(nk::dist_mail_flags(own_mail(h), 2), 0, 8, h->stream));
+        h->spill_dirty = false;
+    }
     h->lazy_zero = true;
     h->table_valid = false;  // a reset counter is a fresh counter: its first job rebuilds the LIF table
     h->top_cache_valid = false;
@@ -1444,6 +1393,7 @@ int nk_reset(nk_counter* h) {
     h->total_spikes = 0;
     h->energy_fixed = 0;
     h->spike_bound = 0;
+    h->slice_only = false;
     h->fresh = true;
     h->streaming = false;
     h->acc_dirty = false;
@@ -1453,6 +1403,7 @@ int nk_reset(nk_counter* h) {
 }
 
 int nk_destroy(nk_counter* h) {
+    if (is_group(h)) return group_destroy(h);
     if (!h) return NK_OK;
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
@@ -1488,6 +1439,7 @@ int nk_destroy(nk_counter* h) {
 }
 
 int nk_set_steps(nk_counter* h, uint64_t steps) {
+    if (is_group(h)) return group_set_steps(h, steps);
     if (!h) return fail(NK_ERR_BAD_ARG, "null handle");
     h->cfg.steps = steps;
     return NK_OK;
@@ -1499,6 +1451,7 @@ int nk_get_steps(const nk_counter* h, uint64_t* steps) {
 }
 
 int nk_process_batch(nk_counter* h, const uint8_t* bases, const uint64_t* offsets, uint64_t nseq) {
+    if (is_group(h)) { NK_TRY(validate_batch(h, bases, offsets, nseq)); return group_process_batch(h, bases, nullptr, nullptr, offsets, nseq); }
     NK_TRY(validate_batch(h, bases, offsets, nseq));
     if (h->streaming) return fail(NK_ERR_STATE, "nk_process_batch inside nk_stream_begin/end");
     NK_CUDA(cudaSetDevice(h->cfg.device));
@@ -1508,7 +1461,7 @@ int nk_process_batch(nk_counter* h, const uint8_t* bases, const uint64_t* offset
     NK_CUDA(cudaEventRecord(pe.begin, h->stream));
     NK_CUDA(cudaMemsetAsync(h->scalars + 2, 0, sizeof(unsigned long long), h->stream));
     h->currents_valid_overwrite = true;  // totals of THIS call overwrite the stored currents (:174-176)
-    NK_TRY(count_host_batch(h, bases, offsets, nseq, &pe));
+    NK_TRY(count_host_batch(h, bases, offsets, nseq, &pe, kPushSync));
     NK_TRY(fold_and_simulate(h, /*skip_zero=*/true, pe));
     NK_TRY(get_event(h, &pe.end));
     NK_CUDA(cudaEventRecord(pe.end, h->stream));
@@ -1517,6 +1470,7 @@ int nk_process_batch(nk_counter* h, const uint8_t* bases, const uint64_t* offset
 }
 
 int nk_stream_begin(nk_counter* h) {
+    if (is_group(h)) return group_begin(h);
     if (!h) return fail(NK_ERR_BAD_ARG, "null handle");
     if (h->streaming) return fail(NK_ERR_STATE, "nk_stream_begin called twice");
     NK_CUDA(cudaSetDevice(h->cfg.device));
@@ -1529,10 +1483,11 @@ int nk_stream_begin(nk_counter* h) {
 }
 
 int nk_stream_push(nk_counter* h, const uint8_t* bases, const uint64_t* offsets, uint64_t nseq) {
+    if (is_group(h)) { NK_TRY(validate_batch(h, bases, offsets, nseq)); return group_push(h, bases, nullptr, nullptr, offsets, nseq); }
     NK_TRY(validate_batch(h, bases, offsets, nseq));
     if (!h->streaming) return fail(NK_ERR_STATE, "nk_stream_push without nk_stream_begin");
     NK_CUDA(cudaSetDevice(h->cfg.device));
-    return count_host_batch(h, bases, offsets, nseq, &h->stream_pe);
+    return count_host_batch(h, bases, offsets, nseq, &h->stream_pe, kPushSync);
 }
 
 // ---- pre-packed input ("nk2" layout, include/neurokmer.h) ------------------------------------------
@@ -1566,6 +1521,7 @@ int nk_debug_pack_body(const uint8_t* bases, uint64_t nbases, uint32_t* codes, u
 
 int nk_process_batch_packed(nk_counter* h, const uint32_t* codes, const uint32_t* other, const uint64_t* offsets,
                             uint64_t nseq) {
+    if (is_group(h)) { NK_TRY(validate_packed(h, codes, offsets, nseq)); return group_process_batch(h, nullptr, codes, other, offsets, nseq); }
     NK_TRY(validate_packed(h, codes, offsets, nseq));
     if (h->streaming) return fail(NK_ERR_STATE, "nk_process_batch_packed inside nk_stream_begin/end");
     NK_CUDA(cudaSetDevice(h->cfg.device));
@@ -1575,7 +1531,7 @@ int nk_process_batch_packed(nk_counter* h, const uint32_t* codes, const uint32_t
     NK_CUDA(cudaEventRecord(pe.begin, h->stream));
     NK_CUDA(cudaMemsetAsync(h->scalars + 2, 0, sizeof(unsigned long long), h->stream));
     h->currents_valid_overwrite = true;
-    NK_TRY(count_host_batch_packed(h, codes, other, offsets, nseq, &pe));
+    NK_TRY(count_host_batch_packed(h, codes, other, offsets, nseq, &pe, kPushSync));
     NK_TRY(fold_and_simulate(h, /*skip_zero=*/true, pe));
     NK_TRY(get_event(h, &pe.end));
     NK_CUDA(cudaEventRecord(pe.end, h->stream));
@@ -1585,17 +1541,20 @@ int nk_process_batch_packed(nk_counter* h, const uint32_t* codes, const uint32_t
 
 int nk_stream_push_packed(nk_counter* h, const uint32_t* codes, const uint32_t* other, const uint64_t* offsets,
                           uint64_t nseq) {
+    if (is_group(h)) { NK_TRY(validate_packed(h, codes, offsets, nseq)); return group_push(h, nullptr, codes, other, offsets, nseq); }
     NK_TRY(validate_packed(h, codes, offsets, nseq));
     if (!h->streaming) return fail(NK_ERR_STATE, "nk_stream_push_packed without nk_stream_begin");
     NK_CUDA(cudaSetDevice(h->cfg.device));
-    return count_host_batch_packed(h, codes, other, offsets, nseq, &h->stream_pe);
+    return count_host_batch_packed(h, codes, other, offsets, nseq, &h->stream_pe, kPushSync);
 }
 
 int nk_stream_accumulated(nk_counter* h, void** dev_currents) {
+    if (is_group(h)) return group_unsupported("nk_stream_accumulated");
     if (!h) return fail(NK_ERR_BAD_ARG, "null handle");
     if (!h->streaming) return fail(NK_ERR_STATE, "nk_stream_accumulated without nk_stream_begin");
     NK_CUDA(cudaSetDevice(h->cfg.device));
     NK_TRY(materialize_zero(h));
+    NK_TRY(unspill(h));
     if (!h->acc_dirty && h->currents_valid_overwrite) {
         NK_CUDA(cudaMemsetAsync(h->currents, 0, h->cfg.pool_size * sizeof(unsigned long long), h->stream));
         h->currents_valid_overwrite = false;
@@ -1608,6 +1567,7 @@ int nk_stream_accumulated(nk_counter* h, void** dev_currents) {
 }
 
 int nk_stream_finish(nk_counter* h) {
+    if (is_group(h)) return group_end(h, /*skip_zero=*/false);
     if (!h) return fail(NK_ERR_BAD_ARG, "null handle");
     if (!h->streaming) return fail(NK_ERR_STATE, "nk_stream_finish without nk_stream_begin");
     NK_CUDA(cudaSetDevice(h->cfg.device));
@@ -1621,6 +1581,7 @@ int nk_stream_finish(nk_counter* h) {
 int nk_stream_end(nk_counter* h) { return nk_stream_finish(h); }
 
 int nk_simulate(nk_counter* h) {
+    if (is_group(h)) return group_simulate(h);
     if (!h) return fail(NK_ERR_BAD_ARG, "null handle");
     if (h->streaming) return fail(NK_ERR_STATE, "nk_simulate inside nk_stream_begin/end");
     NK_CUDA(cudaSetDevice(h->cfg.device));
@@ -1629,7 +1590,7 @@ int nk_simulate(nk_counter* h) {
     NK_TRY(get_event(h, &a));
     NK_TRY(get_event(h, &b));
     NK_CUDA(cudaEventRecord(a, h->stream));
-    NK_TRY(simulate(h, /*skip_zero=*/false));
+    NK_TRY(simulate(h, /*skip_zero=*/false, false));
     NK_CUDA(cudaEventRecord(b, h->stream));
     PhaseEvents pe;
     pe.fold1 = a; pe.lif1 = b; pe.begin = a; pe.end = b;
@@ -1638,6 +1599,7 @@ int nk_simulate(nk_counter* h) {
 }
 
 int nk_process_sequence(nk_counter* h, const uint8_t* seq, uint64_t len) {
+    if (is_group(h)) return group_unsupported("nk_process_sequence (sequential per-sequence API: replicas only)");
     if (!h) return fail(NK_ERR_BAD_ARG, "null handle");
     if (len > 0 && !seq) return fail(NK_ERR_BAD_ARG, "null seq");
     if (h->streaming) return fail(NK_ERR_STATE, "nk_process_sequence inside nk_stream_begin/end");
@@ -1649,7 +1611,7 @@ int nk_process_sequence(nk_counter* h, const uint8_t* seq, uint64_t len) {
     NK_CUDA(cudaMemsetAsync(h->scalars + 2, 0, sizeof(unsigned long long), h->stream));
     h->currents_valid_overwrite = false;
     NK_TRY(materialize_zero(h));
-    NK_TRY(count_host_batch(h, seq, offs, 1, nullptr));
+    NK_TRY(count_host_batch(h, seq, offs, 1, nullptr, kPushSync));
     NK_TRY(fold_now(h));
     nk::LifParams p{};
     p.currents = h->currents; p.v = h->v; p.r = h->r; p.spikes = h->spikes;
@@ -1667,6 +1629,7 @@ int nk_process_sequence(nk_counter* h, const uint8_t* seq, uint64_t len) {
 }
 
 int nk_top_n(nk_counter* h, uint64_t top_n, nk_top_entry* out, uint64_t* n_out) {
+    if (is_group(h)) return group_top_n(h, top_n, out, n_out);
     if (!h || !n_out) return fail(NK_ERR_BAD_ARG, "null argument");
     NK_CUDA(cudaSetDevice(h->cfg.device));
     uint64_t n = std::min<uint64_t>(top_n, h->cfg.pool_size);
@@ -1680,8 +1643,8 @@ int nk_top_n(nk_counter* h, uint64_t top_n, nk_top_entry* out, uint64_t* n_out) 
         NK_TRY(resolve(h));
         const unsigned long long cn = h->top_cached_n;
         for (uint64_t i = 0; i < n; ++i) {
-            out[i].idx = h->h_pack[4 + i];
-            out[i].spikes = h->h_pack[4 + cn + i];
+            out[i].idx = h->h_pack[nk::PACK_HDR + i];
+            out[i].spikes = h->h_pack[nk::PACK_HDR + cn + i];
             out[i].uniques = (h->rows_valid && i < h->row_idx.size() && h->row_idx[i] == out[i].idx) ? h->row_uniques[i]
                                                                                                      : NK_UNIQUES_NOT_COMPUTED;
             out[i]._pad = 0;
@@ -1702,7 +1665,7 @@ int nk_top_n(nk_counter* h, uint64_t top_n, nk_top_entry* out, uint64_t* n_out) 
         NK_CUDA(cudaMallocHost(&h->h_top, 2 * cap * sizeof(unsigned long long)));
         h->topn_cap = cap;
     }
-    if (h->dist_world && h->last.lif_path == 4)
+    if (h->slice_only)
         return fail(NK_ERR_STATE, "sharded-pool mode computed %llu rows; ask for more BEFORE the job (the hint is now %llu)",
                     h->top_cached_n, h->topn_hint);
     NK_TRY(materialize_zero(h));
@@ -1747,18 +1710,21 @@ int nk_top_n(nk_counter* h, uint64_t top_n, nk_top_entry* out, uint64_t* n_out) 
 }
 
 int nk_total_spikes(const nk_counter* h, uint64_t* out) {
+    if (is_group(h)) return nk_total_spikes(h->group[0], out);
     if (!h || !out) return fail(NK_ERR_BAD_ARG, "null argument");
     NK_TRY(resolve(const_cast<nk_counter*>(h)));
     *out = h->total_spikes;
     return NK_OK;
 }
 int nk_energy_used(const nk_counter* h, double* out) {
+    if (is_group(h)) return nk_energy_used(h->group[0], out);
     if (!h || !out) return fail(NK_ERR_BAD_ARG, "null argument");
     NK_TRY(resolve(const_cast<nk_counter*>(h)));
     *out = (double)h->energy_fixed / 1000.0;  // src/models.rs:170-172
     return NK_OK;
 }
 int nk_enable_exact_counts(nk_counter* h, int on) {
+    if (is_group(h)) return group_unsupported("nk_enable_exact_counts");
     if (!h) return fail(NK_ERR_BAD_ARG, "null handle");
     if (h->streaming) return fail(NK_ERR_STATE, "nk_enable_exact_counts inside nk_stream_begin/end");
     NK_CUDA(cudaSetDevice(h->cfg.device));
@@ -1769,6 +1735,7 @@ int nk_enable_exact_counts(nk_counter* h, int on) {
 }
 
 int nk_get_count(nk_counter* h, uint64_t kmer, uint32_t* count, int32_t* found) {
+    if (is_group(h)) return group_unsupported("nk_get_count");
     if (!h || !count || !found) return fail(NK_ERR_BAD_ARG, "null argument");
     if (!h->exact)
         return fail(NK_ERR_UNSUPPORTED, "exact k-mer table is off: call nk_enable_exact_counts(h, 1) before processing");
@@ -1786,6 +1753,7 @@ int nk_get_count(nk_counter* h, uint64_t kmer, uint32_t* count, int32_t* found) 
 }
 
 int nk_exact_table_size(nk_counter* h, uint64_t* n) {
+    if (is_group(h)) return group_unsupported("nk_exact_table_size");
     if (!h || !n) return fail(NK_ERR_BAD_ARG, "null argument");
     if (!h->exact) return fail(NK_ERR_UNSUPPORTED, "exact k-mer table is off");
     NK_TRY(resolve(h));
@@ -1794,6 +1762,7 @@ int nk_exact_table_size(nk_counter* h, uint64_t* n) {
 }
 
 int nk_copy_exact_table(nk_counter* h, uint64_t* keys, uint32_t* counts) {
+    if (is_group(h)) return group_unsupported("nk_copy_exact_table");
     if (!h) return fail(NK_ERR_BAD_ARG, "null handle");
     if (!h->exact) return fail(NK_ERR_UNSUPPORTED, "exact k-mer table is off");
     NK_CUDA(cudaSetDevice(h->cfg.device));
@@ -1807,6 +1776,7 @@ int nk_copy_exact_table(nk_counter* h, uint64_t* keys, uint32_t* counts) {
 }
 
 int nk_copy_uniques(nk_counter* h, uint32_t* out) {
+    if (is_group(h)) return group_unsupported("nk_copy_uniques");
     if (!h || !out) return fail(NK_ERR_BAD_ARG, "null argument");
     if (!h->exact) return fail(NK_ERR_UNSUPPORTED, "exact k-mer table is off");
     NK_CUDA(cudaSetDevice(h->cfg.device));
@@ -1874,15 +1844,18 @@ static int debug_kmers_any(nk_counter* h, const uint8_t* seq, const uint32_t* co
 
 int nk_debug_kmers(nk_counter* h, const uint8_t* seq, uint64_t len, uint64_t* fwd, uint64_t* rc, uint64_t* words,
                    uint64_t* idx, uint64_t* n_out) {
+    if (is_group(h)) return nk_debug_kmers(h->group[0], seq, len, fwd, rc, words, idx, n_out);
     return debug_kmers_any(h, seq, nullptr, nullptr, len, fwd, rc, words, idx, n_out);
 }
 
 int nk_debug_kmers_packed(nk_counter* h, const uint32_t* codes, const uint32_t* other, uint64_t len, uint64_t* fwd,
                           uint64_t* rc, uint64_t* words, uint64_t* idx, uint64_t* n_out) {
+    if (is_group(h)) return nk_debug_kmers_packed(h->group[0], codes, other, len, fwd, rc, words, idx, n_out);
     return debug_kmers_any(h, nullptr, codes, other, len, fwd, rc, words, idx, n_out);
 }
 
 int nk_debug_hash(nk_counter* h, const uint64_t* words, uint64_t n, uint64_t* hashes, uint64_t* idx) {
+    if (is_group(h)) return nk_debug_hash(h->group[0], words, n, hashes, idx);
     if (!h) return fail(NK_ERR_BAD_ARG, "null handle");
     if (n == 0) return NK_OK;
     if (!words) return fail(NK_ERR_BAD_ARG, "null words");
@@ -1918,7 +1891,9 @@ int nk_debug_mod(const uint64_t* values, uint64_t n, uint64_t pool_size, int whi
     return NK_OK;
 }
 
-static int copy_out(nk_counter* h, void* dst, const void* src, size_t bytes) {
+}  // extern "C"
+namespace nkd {
+int copy_out(nk_counter* h, void* dst, const void* src, size_t bytes) {
     if (!h || !dst) return fail(NK_ERR_BAD_ARG, "null argument");
     NK_TRY(resolve(h));
     NK_TRY(materialize_zero(h));
@@ -1927,12 +1902,15 @@ static int copy_out(nk_counter* h, void* dst, const void* src, size_t bytes) {
     NK_CUDA(cudaStreamSynchronize(h->stream));
     return NK_OK;
 }
-int nk_copy_currents(nk_counter* h, uint64_t* out) { return copy_out(h, out, h ? h->currents : nullptr, h ? h->cfg.pool_size * 8 : 0); }
-int nk_copy_spike_counts(nk_counter* h, uint64_t* out) { return copy_out(h, out, h ? h->spikes : nullptr, h ? h->cfg.pool_size * 8 : 0); }
-int nk_copy_voltages(nk_counter* h, float* out) { return copy_out(h, out, h ? h->v : nullptr, h ? h->cfg.pool_size * 4 : 0); }
-int nk_copy_refractory(nk_counter* h, uint32_t* out) { return copy_out(h, out, h ? h->r : nullptr, h ? h->cfg.pool_size * 4 : 0); }
+}  // namespace nkd
+extern "C" {
+int nk_copy_currents(nk_counter* h, uint64_t* out) { if (is_group(h)) return group_copy(h, 0, out); return copy_out(h, out, h ? h->currents : nullptr, h ? h->cfg.pool_size * 8 : 0); }
+int nk_copy_spike_counts(nk_counter* h, uint64_t* out) { if (is_group(h)) return group_copy(h, 1, out); return copy_out(h, out, h ? h->spikes : nullptr, h ? h->cfg.pool_size * 8 : 0); }
+int nk_copy_voltages(nk_counter* h, float* out) { if (is_group(h)) return group_copy(h, 2, out); return copy_out(h, out, h ? h->v : nullptr, h ? h->cfg.pool_size * 4 : 0); }
+int nk_copy_refractory(nk_counter* h, uint32_t* out) { if (is_group(h)) return group_copy(h, 3, out); return copy_out(h, out, h ? h->r : nullptr, h ? h->cfg.pool_size * 4 : 0); }
 
 int nk_last_timings(const nk_counter* h, nk_timings* out) {
+    if (is_group(h)) return out ? group_timings(const_cast<nk_counter*>(h), out) : fail(NK_ERR_BAD_ARG, "null argument");
     if (!h || !out) return fail(NK_ERR_BAD_ARG, "null argument");
     NK_TRY(resolve(const_cast<nk_counter*>(h)));
     *out = h->last;
@@ -1940,13 +1918,23 @@ int nk_last_timings(const nk_counter* h, nk_timings* out) {
 }
 
 int nk_debug_set_lif_path(nk_counter* h, int mode) {
+    if (is_group(h)) { for (nk_counter* c : h->group) NK_TRY(nk_debug_set_lif_path(c, mode)); return NK_OK; }
     if (!h) return fail(NK_ERR_BAD_ARG, "null handle");
     if (mode < 0 || mode > 2) return fail(NK_ERR_BAD_ARG, "mode must be 0, 1 or 2");
     h->force_direct = mode;
     return NK_OK;
 }
 
+int nk_debug_set_fold_limit(nk_counter* h, uint64_t limit) {
+    if (is_group(h)) { for (nk_counter* c : h->group) NK_TRY(nk_debug_set_fold_limit(c, limit)); return NK_OK; }
+    if (!h) return fail(NK_ERR_BAD_ARG, "null handle");
+    if (limit == 0 || limit > 0xFFFFFFFFull) return fail(NK_ERR_BAD_ARG, "limit must be in 1..2^32-1");
+    h->fold_limit = limit;
+    return NK_OK;
+}
+
 int nk_calibrate(nk_counter* h, int which, double* out) {
+    if (is_group(h)) return nk_calibrate(h->group[0], which, out);
     if (!h || !out) return fail(NK_ERR_BAD_ARG, "null argument");
     if (which < 0 || which > 2) return fail(NK_ERR_BAD_ARG, "which must be 0, 1 or 2");
     if (h->streaming || h->acc_dirty) return fail(NK_ERR_STATE, "nk_calibrate needs an idle counter");
@@ -1994,6 +1982,7 @@ int nk_calibrate(nk_counter* h, int which, double* out) {
 // nk_dist_post returns NK_ERR_UNSUPPORTED and the caller uses nk_stream_accumulated + all-reduce.
 // ---------------------------------------------------------------------------
 int nk_dist_export(nk_counter* h, void* handle64, void** raw_acc) {
+    if (is_group(h)) return group_unsupported("nk_dist_export");
     if (!h) return fail(NK_ERR_BAD_ARG, "null handle");
     NK_CUDA(cudaSetDevice(h->cfg.device));
     if (handle64) {
@@ -2007,6 +1996,7 @@ int nk_dist_export(nk_counter* h, void* handle64, void** raw_acc) {
 }
 
 int nk_dist_setup(nk_counter* h, int rank, int world, const void* handles, void* const* raw_ptrs) {
+    if (is_group(h)) return group_unsupported("nk_dist_setup");
     if (!h) return fail(NK_ERR_BAD_ARG, "null handle");
     if (world < 1 || world > 16 || rank < 0 || rank >= world) return fail(NK_ERR_BAD_ARG, "bad rank/world (world <= 16)");
     if (!handles && !raw_ptrs) return fail(NK_ERR_BAD_ARG, "need IPC handles or raw pointers");
@@ -2040,12 +2030,16 @@ int nk_dist_setup(nk_counter* h, int rank, int world, const void* handles, void*
     const unsigned long long P = h->cfg.pool_size, per = (P + world - 1) / world;
     h->dist_lo = std::min(P, per * rank);
     h->dist_len = std::min(P, h->dist_lo + per) - h->dist_lo;
-    if (!h->d_merged) NK_CUDA(cudaMalloc(&h->d_merged, (4 + 2 * 2048) * sizeof(unsigned long long)));
+    if (!h->d_merged) NK_CUDA(cudaMalloc(&h->d_merged, nk::PACK_MAX_U64 * sizeof(unsigned long long)));
     return NK_OK;
 }
 
+}  // extern "C"
+
+namespace nkd {
+
 // parameters of this rank's slice post kernel (shared by nk_dist_post and nk_dist_run)
-static int dist_build_post(nk_counter* h, nk::PostParams& q, unsigned long long* n_top_out) {
+int dist_build_post(nk_counter* h, nk::PostParams& q, unsigned long long* n_top_out) {
     const unsigned long long per = (h->cfg.pool_size + h->dist_world - 1) / h->dist_world;
     const unsigned long long n_top = std::min<unsigned long long>(h->topn_hint, per);
     const bool table_ok = h->fresh && !h->force_direct && !h->exact && h->cfg.steps > 0 && std::isfinite(h->cfg.threshold) &&
@@ -2093,22 +2087,34 @@ static int dist_build_post(nk_counter* h, nk::PostParams& q, unsigned long long*
     q.pack = h->d_pack;
     q.kmers = h->scalars + 2;
     q.npeers = h->dist_world;
-    for (int r = 0; r < h->dist_world; ++r) q.peer_acc[r] = h->dist_peer[r];
+    const unsigned long long spill_off = nk::dist_spill_offset(h->cfg.pool_size);
+    for (int r = 0; r < h->dist_world; ++r) {
+        q.peer_acc[r] = h->dist_peer[r];
+        q.peer_spill[r] = reinterpret_cast<const unsigned long long*>(reinterpret_cast<const unsigned char*>(h->dist_peer[r]) + spill_off);
+        q.peer_mail[r] = h->dist_mail[r];
+    }
     q.slice_lo = h->dist_lo;
     q.rank = h->dist_rank;
     // rows are padded to n_top per rank so that every rank's pack has the same size
-    NK_CUDA(cudaMemsetAsync(h->d_pack, 0, (4 + 2 * n_top) * sizeof(unsigned long long), h->stream));
+    NK_CUDA(cudaMemsetAsync(h->d_pack, 0, (nk::PACK_HDR + 2 * n_top) * sizeof(unsigned long long), h->stream));
     NK_CUDA(cudaMemsetAsync(h->scalars, 0, sizeof(unsigned long long), h->stream));
     NK_CUDA(cudaMemsetAsync(h->post_zero, 0, 8 * sizeof(unsigned long long) + 8 * 256 * sizeof(unsigned int), h->stream));
     *n_top_out = n_top;
+    h->dist_n_each = n_top;
     return NK_OK;
 }
 
 // host-side state after a sharded job's merged pack has been queued for read-back
-static int dist_finish(nk_counter* h, unsigned long long n_out) {
+int dist_finish(nk_counter* h, unsigned long long n_out) {
     // accumulators are all-zero between jobs (every peer has read them by now)
     NK_CUDA(cudaMemsetAsync(h->acc, 0, h->cfg.pool_size * sizeof(unsigned int), h->stream));
-    const size_t bytes = (4 + 2 * n_out) * sizeof(unsigned long long);
+    if (h->spill_dirty) {  // the spill array itself is overwritten by its next use
+        NK_CUDA(cudaMemsetAsync(nk::dist_mail_flags(own_mail(h), 2), 0, 8, h->stream));
+        h->spill_dirty = false;
+    }
+    h->dist_job = true;
+    h->slice_only = true;
+    const size_t bytes = (nk::PACK_HDR + 2 * n_out) * sizeof(unsigned long long);
     NK_CUDA(cudaMemcpyAsync(h->h_pack, h->d_merged, bytes, cudaMemcpyDeviceToHost, h->stream));
     h->last.d2h_bytes += bytes;
     h->acc_dirty = false;
@@ -2128,9 +2134,14 @@ static int dist_finish(nk_counter* h, unsigned long long n_out) {
     return NK_OK;
 }
 
+}  // namespace nkd
+
+extern "C" {
+
 // Enqueue this rank's slice post kernel.  PRECONDITION (caller): every rank's counting is complete
 // and ordered before this call on the handle's stream (e.g. a 1-element NCCL all-reduce on it).
 int nk_dist_post(nk_counter* h, void** dev_pack, uint64_t* pack_u64s, uint64_t* n_each) {
+    if (is_group(h)) return group_unsupported("nk_dist_post");
     if (!h || !dev_pack || !pack_u64s || !n_each) return fail(NK_ERR_BAD_ARG, "null argument");
     if (!h->dist_world) return fail(NK_ERR_STATE, "nk_dist_setup was not called");
     if (!h->streaming) return fail(NK_ERR_STATE, "nk_dist_post without nk_stream_begin");
@@ -2142,7 +2153,7 @@ int nk_dist_post(nk_counter* h, void** dev_pack, uint64_t* pack_u64s, uint64_t* 
     ++h->last.launches;
     h->last.lif_path = 4;
     *dev_pack = h->d_pack;
-    *pack_u64s = 4 + 2 * n_top;
+    *pack_u64s = nk::PACK_HDR + 2 * n_top;
     *n_each = n_top;
     return NK_OK;
 }
@@ -2153,6 +2164,7 @@ int nk_dist_post(nk_counter* h, void** dev_pack, uint64_t* pack_u64s, uint64_t* 
 // waits for all packs and merges them.  One handle per GPU (the waiting kernels of two handles on one GPU
 // could starve each other); a lost peer surfaces as NK_ERR_STATE after NK_DIST_TIMEOUT_MS (default 30 s).
 int nk_dist_run(nk_counter* h) {
+    if (is_group(h)) return group_unsupported("nk_dist_run");
     if (!h) return fail(NK_ERR_BAD_ARG, "null handle");
     if (!h->dist_world) return fail(NK_ERR_STATE, "nk_dist_setup was not called");
     if (!h->streaming) return fail(NK_ERR_STATE, "nk_dist_run without nk_stream_begin");
@@ -2173,12 +2185,11 @@ int nk_dist_run(nk_counter* h) {
     q.wait_flags = nk::dist_mail_flags(h->dist_mail[h->dist_rank], 0);
     q.epoch = epoch;
     q.timeout_ns = timeout_ms * 1000000ull;
-    for (int r = 0; r < h->dist_world; ++r) q.peer_mail[r] = h->dist_mail[r];
     NK_CUDA(nk::launch_post(q, h->post_grid, h->stream));
     ++h->last.launches;
     h->last.lif_path = 4;
     const unsigned long long n_out = std::min<unsigned long long>(h->topn_hint, h->cfg.pool_size);
-    NK_CUDA(nk::launch_merge_mailbox(h->dist_mail[h->dist_rank], h->dist_world, n_top, n_out, epoch, q.timeout_ns,
+    NK_CUDA(nk::launch_merge_mailbox(h->dist_mail[h->dist_rank], h->dist_world, h->dist_rank, n_top, n_out, epoch, q.timeout_ns,
                                      h->d_merged, h->stream));
     ++h->last.launches;
     return dist_finish(h, n_out);
@@ -2187,16 +2198,18 @@ int nk_dist_run(nk_counter* h) {
 // `dev_gathered`: the world packs, rank-major, all-gathered by the caller on the handle's stream
 // (which also proves that every rank has finished reading this rank's accumulators).
 int nk_dist_complete(nk_counter* h, const void* dev_gathered, uint64_t n_each) {
+    if (is_group(h)) return group_unsupported("nk_dist_complete");
     if (!h || !dev_gathered) return fail(NK_ERR_BAD_ARG, "null argument");
     if (!h->dist_world || !h->streaming) return fail(NK_ERR_STATE, "nk_dist_complete without nk_dist_post");
     NK_CUDA(cudaSetDevice(h->cfg.device));
     const unsigned long long n_out = std::min<unsigned long long>(h->topn_hint, h->cfg.pool_size);
-    NK_CUDA(nk::launch_merge_packs((const unsigned long long*)dev_gathered, h->dist_world, n_each, n_out, h->d_merged, h->stream));
+    NK_CUDA(nk::launch_merge_packs((const unsigned long long*)dev_gathered, h->dist_world, h->dist_rank, n_each, n_out, h->d_merged, h->stream));
     ++h->last.launches;
     return dist_finish(h, n_out);
 }
 
 int nk_dist_slice(const nk_counter* h, uint64_t* lo, uint64_t* len) {
+    if (is_group(h)) return group_unsupported("nk_dist_slice");
     if (!h || !lo || !len) return fail(NK_ERR_BAD_ARG, "null argument");
     *lo = h->dist_lo;
     *len = h->dist_len;
@@ -2204,6 +2217,7 @@ int nk_dist_slice(const nk_counter* h, uint64_t* lo, uint64_t* len) {
 }
 
 int nk_stage_reserve(nk_counter* h, uint64_t nbytes, uint64_t nseq, void** dev_bases, void** dev_offsets) {
+    if (is_group(h)) return group_unsupported("nk_stage_reserve");
     if (!h) return fail(NK_ERR_BAD_ARG, "null handle");
     NK_CUDA(cudaSetDevice(h->cfg.device));
     NK_TRY(resolve(h));
@@ -2216,6 +2230,7 @@ int nk_stage_reserve(nk_counter* h, uint64_t nbytes, uint64_t nseq, void** dev_b
 }
 
 int nk_process_staged(nk_counter* h, uint64_t nbytes, uint64_t nseq, int mode) {
+    if (is_group(h)) return group_unsupported("nk_process_staged");
     if (!h) return fail(NK_ERR_BAD_ARG, "null handle");
     if (mode != 0 && mode != 1) return fail(NK_ERR_BAD_ARG, "mode must be 0 or 1");
     if (mode == 1 && !h->streaming) return fail(NK_ERR_STATE, "mode 1 needs nk_stream_begin");
@@ -2257,6 +2272,7 @@ int nk_process_staged(nk_counter* h, uint64_t nbytes, uint64_t nseq, int mode) {
 
 int nk_stage_reserve_packed(nk_counter* h, uint64_t nbases, uint64_t nseq, void** dev_codes, void** dev_other,
                             void** dev_offsets) {
+    if (is_group(h)) return group_unsupported("nk_stage_reserve_packed");
     if (!h) return fail(NK_ERR_BAD_ARG, "null handle");
     NK_CUDA(cudaSetDevice(h->cfg.device));
     NK_TRY(resolve(h));
@@ -2270,6 +2286,7 @@ int nk_stage_reserve_packed(nk_counter* h, uint64_t nbases, uint64_t nseq, void*
 }
 
 int nk_process_staged_packed(nk_counter* h, uint64_t nbases, uint64_t nseq, int mode, int has_other) {
+    if (is_group(h)) return group_unsupported("nk_process_staged_packed");
     if (!h) return fail(NK_ERR_BAD_ARG, "null handle");
     if (mode != 0 && mode != 1) return fail(NK_ERR_BAD_ARG, "mode must be 0 or 1");
     if (mode == 1 && !h->streaming) return fail(NK_ERR_STATE, "mode 1 needs nk_stream_begin");
@@ -2309,11 +2326,13 @@ int nk_process_staged_packed(nk_counter* h, uint64_t nbases, uint64_t nseq, int 
 }
 
 int nk_cuda_stream(nk_counter* h, void** stream) {
+    if (is_group(h)) return nk_cuda_stream(h->group[0], stream);
     if (!h || !stream) return fail(NK_ERR_BAD_ARG, "null argument");
     *stream = (void*)h->stream;
     return NK_OK;
 }
 int nk_synchronize(nk_counter* h) {
+    if (is_group(h)) return group_synchronize(h);
     if (!h) return fail(NK_ERR_BAD_ARG, "null handle");
     NK_CUDA(cudaSetDevice(h->cfg.device));
     NK_CUDA(cudaStreamSynchronize(h->copy_stream));
@@ -2322,6 +2341,7 @@ int nk_synchronize(nk_counter* h) {
 }
 
 int nk_synth_fill(nk_counter* h, void* dev_out, uint64_t seed, uint64_t start, uint64_t n, uint32_t flags) {
+    if (is_group(h)) return group_unsupported("nk_synth_fill");
     if (!h || (!dev_out && n)) return fail(NK_ERR_BAD_ARG, "null argument");
     NK_CUDA(cudaSetDevice(h->cfg.device));
     NK_CUDA(nk::launch_synth((unsigned char*)dev_out, seed, start, n, flags, h->stream));
@@ -2346,7 +2366,7 @@ uint64_t nk_pack_kmer(const uint8_t* kmer, uint64_t len) { return nk::host_pack_
 static int uniques_begin(nk_counter* h, uint64_t top_n) {
     if (h->streaming) return fail(NK_ERR_STATE, "nk_uniques_begin inside nk_stream_begin/end");
     if (h->uniques_open) return fail(NK_ERR_STATE, "nk_uniques_begin called twice");
-    if (h->dist_world && h->last.lif_path == 4)
+    if (h->slice_only && !h->uniques_whole_input)
         return fail(NK_ERR_UNSUPPORTED, "uniques pass after a sharded-pool job: every rank holds only its shard of the input "
                     "(the per-rank word sets are not merged)");
     const uint64_t n = std::min<uint64_t>(top_n, h->cfg.pool_size);
@@ -2399,12 +2419,24 @@ static int uniques_end(nk_counter* h) {
 }
 
 int nk_uniques_begin(nk_counter* h, uint64_t top_n) {
+    if (is_group(h)) {
+        // the second pass runs on group[0], which is handed the WHOLE input again (the rows are the merged ones)
+        if (top_n == 0 || top_n > 2048) return fail(NK_ERR_BAD_ARG, "nk_uniques_begin: top_n must be in 1..2048");
+        std::vector<nk_top_entry> rows(top_n);
+        uint64_t got = 0;
+        NK_TRY(group_top_n(h, top_n, rows.data(), &got));  // brings the state to group[0] if the slices computed fewer rows
+        nk_counter* c0 = h->group[0];
+        NK_CUDA(cudaSetDevice(c0->cfg.device));
+        c0->uniques_whole_input = true;
+        return uniques_begin(c0, top_n);
+    }
     if (!h) return fail(NK_ERR_BAD_ARG, "null handle");
     NK_CUDA(cudaSetDevice(h->cfg.device));
     return uniques_begin(h, top_n);
 }
 
 int nk_uniques_push(nk_counter* h, const uint8_t* bases, const uint64_t* offsets, uint64_t nseq) {
+    if (is_group(h)) return nk_uniques_push(h->group[0], bases, offsets, nseq);
     NK_TRY(validate_batch(h, bases, offsets, nseq));
     if (!h->uniques_open) return fail(NK_ERR_STATE, "nk_uniques_push without nk_uniques_begin");
     NK_CUDA(cudaSetDevice(h->cfg.device));
@@ -2414,6 +2446,7 @@ int nk_uniques_push(nk_counter* h, const uint8_t* bases, const uint64_t* offsets
 
 int nk_uniques_push_packed(nk_counter* h, const uint32_t* codes, const uint32_t* other, const uint64_t* offsets,
                            uint64_t nseq) {
+    if (is_group(h)) return nk_uniques_push_packed(h->group[0], codes, other, offsets, nseq);
     NK_TRY(validate_packed(h, codes, offsets, nseq));
     if (!h->uniques_open) return fail(NK_ERR_STATE, "nk_uniques_push_packed without nk_uniques_begin");
     NK_CUDA(cudaSetDevice(h->cfg.device));
@@ -2421,6 +2454,7 @@ int nk_uniques_push_packed(nk_counter* h, const uint32_t* codes, const uint32_t*
 }
 
 int nk_uniques_end(nk_counter* h) {
+    if (is_group(h)) return nk_uniques_end(h->group[0]);
     if (!h) return fail(NK_ERR_BAD_ARG, "null handle");
     if (!h->uniques_open) return fail(NK_ERR_STATE, "nk_uniques_end without nk_uniques_begin");
     NK_CUDA(cudaSetDevice(h->cfg.device));
@@ -2514,19 +2548,19 @@ int nk_debug_fasta_windows_digest(const char* path, uint64_t window, uint64_t* n
 
 int nk_process_file(nk_counter* h, const char* path, int streaming) {
     if (!h || !path) return fail(NK_ERR_BAD_ARG, "null argument");
-    if (h->streaming) return fail(NK_ERR_STATE, "nk_process_file inside nk_stream_begin/end");
+    if (h->streaming || h->group_streaming) return fail(NK_ERR_STATE, "nk_process_file inside nk_stream_begin/end");
     std::string err;
     int rc = nk::process_file(h, path, streaming != 0, &err, false);
     if (rc != NK_OK) return fail(rc, "%s", err.c_str());
     if (h->file_uniques > 0 && !h->exact) {
         // `uniques` of the top rows: read the file a second time, keeping only the windows of those neurons
-        NK_TRY(uniques_begin(h, h->file_uniques));
+        NK_TRY(nk_uniques_begin(h, h->file_uniques));
         rc = nk::process_file(h, path, streaming != 0, &err, true);
         if (rc != NK_OK) {
-            h->uniques_open = false;
+            (is_group(h) ? h->group[0] : h)->uniques_open = false;
             return fail(rc, "%s", err.c_str());
         }
-        NK_TRY(uniques_end(h));
+        NK_TRY(nk_uniques_end(h));
     }
     return NK_OK;
 }

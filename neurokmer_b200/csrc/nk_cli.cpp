@@ -3,7 +3,7 @@
 // Flag surface and result block of the reference binary (src/main.rs:10-25, :49-74):
 //   neurokmer --input/-i FILE [--k/-k 31] [--pool-size 1000000] [--canonical] [--streaming]
 // Additive flags with the reference's constants as defaults: --steps 1000 (spiking_hash.rs:70),
-// --top-n 20 (main.rs:50), --device 0.  The "unique k-mers colliding" column (kmer_per_neuron, main.rs:54-61)
+// --top-n 20 (main.rs:50), --device 0, --gpus N (shard the input over N GPUs of this process: nk_create_multi).  The "unique k-mers colliding" column (kmer_per_neuron, main.rs:54-61)
 // is computed for the printed rows by a second read of the file (nk_set_file_uniques); --exact builds the
 // whole exact k-mer side table instead (O(windows) memory), --no-uniques skips the column ("n/a", never a guess).
 // LIF constants are the ones main.rs:37 hard-codes (threshold 1.0, leak 0.95, refractory 2, cost 1.0).
@@ -29,6 +29,8 @@ static void usage() {
             "      --steps <N>              LIF ticks [default: 1000]\n"
             "      --top-n <N>              rows of the result block [default: 20]\n"
             "      --device <ID>            CUDA device ordinal [default: 0]\n"
+            "      --gpus <N>               shard the input over GPUs 0..N-1 (0 = all) [default: 1]\n"
+            "      --devices <a,b,..>       shard the input over exactly these CUDA devices\n"
             "      --exact                  build the exact k-mer table (uniques column by sort, get_count)\n"
             "      --no-uniques             skip the second read of the file that fills the uniques column\n");
 }
@@ -54,7 +56,8 @@ int main(int argc, char** argv) {
     nk_config cfg;
     nk_config_default(&cfg);
     uint64_t top_n = 20;
-    int streaming = 0, exact = 0, timing = 0, no_uniques = 0;
+    int streaming = 0, exact = 0, timing = 0, no_uniques = 0, gpus = 1;
+    std::vector<int32_t> devices;
     const auto T0 = std::chrono::steady_clock::now();
     auto since = [&]() { return std::chrono::duration<double>(std::chrono::steady_clock::now() - T0).count(); };
     for (int i = 1; i < argc; ++i) {
@@ -71,6 +74,13 @@ int main(int argc, char** argv) {
         else if (a == "--steps") cfg.steps = strtoull(val("--steps"), nullptr, 10);
         else if (a == "--top-n") top_n = strtoull(val("--top-n"), nullptr, 10);
         else if (a == "--device") cfg.device = atoi(val("--device"));
+        else if (a == "--gpus") gpus = atoi(val("--gpus"));
+        else if (a == "--devices") {
+            for (const char* p = val("--devices"); *p;) {
+                devices.push_back((int32_t)strtol(p, const_cast<char**>(&p), 10));
+                if (*p == ',') ++p; else if (*p) { fprintf(stderr, "error: --devices takes a comma-separated list of ordinals\n"); return 2; }
+            }
+        }
         else if (a == "--exact") exact = 1;
         else if (a == "--no-uniques") no_uniques = 1;
         else if (a == "--timing") timing = 1;  // phase wall times on stderr
@@ -80,7 +90,18 @@ int main(int argc, char** argv) {
     if (input.empty()) { fprintf(stderr, "error: the following required arguments were not provided:\n  --input <INPUT>\n\n"); usage(); return 2; }
 
     nk_counter* h = nullptr;
-    if (nk_create(&cfg, &h) != NK_OK) { fprintf(stderr, "Error: %s\n", nk_last_error()); return 1; }
+    if (gpus == 0) {
+        int32_t nd = 0;
+        nk_device_count(&nd);
+        gpus = nd > 0 ? nd : 1;
+    }
+    if (gpus < 0) { fprintf(stderr, "error: --gpus must be >= 0\n"); return 2; }
+    if (!devices.empty()) gpus = (int)devices.size();
+    if ((gpus > 1 || !devices.empty()) && exact) { fprintf(stderr, "error: --exact needs --gpus 1 (the exact k-mer table is single-GPU)\n"); return 2; }
+    const int crc = !devices.empty() ? nk_create_multi(&cfg, devices.data(), (int32_t)devices.size(), &h)
+                    : gpus > 1       ? nk_create_multi(&cfg, nullptr, gpus, &h)
+                                     : nk_create(&cfg, &h);
+    if (crc != NK_OK) { fprintf(stderr, "Error: %s\n", nk_last_error()); return 1; }
     if (timing) fprintf(stderr, "[timing] nk_create done at %.3f s\n", since());
     if (exact && nk_enable_exact_counts(h, 1) != NK_OK) { fprintf(stderr, "Error: %s\n", nk_last_error()); return 1; }
     if (!exact && !no_uniques && top_n >= 1 && top_n <= 2048 && nk_set_file_uniques(h, top_n) != NK_OK) {

@@ -16,6 +16,9 @@
 //   A k-mer is a pure function of its own k bytes (the reference has no N-break
 //   state: non-ACGT -> code 0 on BOTH strands), so there is no serial dependency.
 //   min(fwd, rc) -> SipHash-1-3 -> exact mod -> RED.ADD.U32 into the L2-resident pool.
+#include <atomic>
+#include <mutex>
+
 #include "nk_kernels.cuh"
 
 #ifndef NK_COUNT_UNROLL
@@ -416,12 +419,15 @@ static cudaError_t launch_count_t(const CountParams& p, cudaStream_t s) {
     constexpr int kSmem = kSmemTotal + (MODE == 3 ? kCompactBytes : 0);
     // persistent grid of this instantiation: SMs x resident CTAs (a multiple of 148 on B200); function
     // attributes are per device, so the cache is too
-    static int max_grid_of[64] = {};
+    // (distinct handles may launch from different threads: the cache is atomic, its fill serialised)
+    static std::atomic<int> max_grid_of[64];
+    static std::mutex fill_mu;
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
-    if (max_grid_of[dev] == 0) {
+    if (max_grid_of[dev].load(std::memory_order_acquire) == 0) {
+        std::lock_guard<std::mutex> lk(fill_mu);
         int sms = 0, per_sm = 0;
         e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return e;
@@ -429,9 +435,9 @@ static cudaError_t launch_count_t(const CountParams& p, cudaStream_t s) {
         if (e != cudaSuccess) return e;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, count_kernel<CANON, MODE, POW2, KHI, PACKED>, COUNT_THREADS, kSmem);
         if (e != cudaSuccess) return e;
-        max_grid_of[dev] = sms * (per_sm < 1 ? 1 : per_sm);
+        max_grid_of[dev].store(sms * (per_sm < 1 ? 1 : per_sm), std::memory_order_release);
     }
-    const int max_grid = max_grid_of[dev];
+    const int max_grid = max_grid_of[dev].load(std::memory_order_acquire);
     const unsigned long long grid = p.ntiles < (unsigned long long)max_grid ? p.ntiles : (unsigned long long)max_grid;
     if (grid == 0) return cudaSuccess;
     count_kernel<CANON, MODE, POW2, KHI, PACKED><<<(unsigned)grid, COUNT_THREADS, kSmem, s>>>(p);

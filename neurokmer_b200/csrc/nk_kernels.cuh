@@ -98,6 +98,22 @@ cudaError_t launch_mark_invalid(unsigned int* invalid, const unsigned long long*
 cudaError_t launch_fold(unsigned int* acc, unsigned long long* currents, unsigned long long pool,
                         bool overwrite, cudaStream_t s);
 
+// spill (u64) -> currents (u64): currents[i] = (overwrite ? 0 : currents[i]) + spill[i]
+cudaError_t launch_fold64(const unsigned long long* spill, unsigned long long* currents, unsigned long long pool,
+                          bool overwrite, cudaStream_t s);
+
+// multi-GPU group, carried-state path: currents[i] = (overwrite ? 0 : currents[i]) + sum over members of their u32
+// counts (+ u64 spill where spill_mask has the member's bit); *kmers_out = sum of the members' k-mer counters
+struct PeerSumParams {
+    const unsigned int* acc[16];
+    const unsigned long long* spill[16];
+    const unsigned long long* kmers[16];
+    unsigned spill_mask;
+    int n;
+};
+cudaError_t launch_peer_sum(const PeerSumParams& ps, unsigned long long* currents, unsigned long long pool, bool overwrite,
+                            unsigned long long* kmers_out, cudaStream_t s);
+
 struct LifParams {
     unsigned long long* currents;
     unsigned int* acc;               // u32 batch accumulators to fold in first (fold_mode != 0); zeroed
@@ -180,19 +196,21 @@ struct PostParams {
     unsigned int* seg_counts;        // ceil(pool/4096)
     unsigned long long* out_idx;     // >= 2048
     unsigned long long* out_spikes;  // >= 2048
-    unsigned long long* pack;        // 4 + 2n u64: {fired, 0, kmers, n, idx[n], spikes[n]}
+    unsigned long long* pack;        // PACK_HDR + 2n u64: {fired, error, kmers, n, 8 time stamps, idx[n], spikes[n]}
     const unsigned long long* kmers; // device k-mer counter of the call
     // multi-GPU "reduce-scatter fused into LIF": this rank owns neurons [slice_lo, slice_lo + lif.pool);
     // its counts are the SUM over all ranks' accumulators, read through NVLink peer mappings.
     // (lif.currents / v / r / spikes are pre-offset by slice_lo; lif.fold_mode must be 2.)
     int npeers;                      // 0: single GPU; else world size (self included)
     const unsigned int* peer_acc[16];
+    const unsigned long long* peer_spill[16];  // every rank's u64 spill array (read only for ranks whose spill flag is set)
     unsigned long long slice_lo;
     // peer-signalled mode (nk_dist_run): no host / NCCL barrier around this kernel.
     //   wait_flags != null: before touching any peer's counts every block waits until wait_flags[r] >= epoch
     //   for all r < npeers (rank r's "counting finished" signal, written into THIS rank's mailbox).
-    //   peer_mail[r] != null: block 0 delivers the result pack into rank r's mailbox slot `rank` and then
-    //   raises rank r's "pack delivered" flag — which also tells r that this rank is done reading r's counts.
+    //   peer_mail[r] (set whenever npeers != 0: the spill flags live there); with wait_flags != null block 0 also
+    //   delivers the result pack into rank r's mailbox slot `rank` and then raises rank r's "pack delivered"
+    //   flag — which also tells r that this rank is done reading r's counts.
     const unsigned long long* wait_flags;
     unsigned long long epoch;
     unsigned long long timeout_ns;
@@ -202,28 +220,38 @@ struct PostParams {
 
 // Mailbox appended to every rank's accumulator allocation (so that the ONE IPC handle of nk_dist_export
 // maps it into the peers): flags[0][r] "rank r finished counting", flags[1][r] "rank r's pack delivered"
-// (epoch numbers, written by rank r), then 16 pack slots.
+// (epoch numbers, written by rank r), flags[2][0] "the owner spilled counts into its u64 spill array during
+// this job" (written by the owner, read by the peers' slice kernels), then 16 pack slots.  Behind the mailbox
+// the allocation carries the owner's SPILL array (pool_size u64): when a stream could overflow the u32
+// accumulators (> 2^32-1 window starts on one rank) they are folded into it instead of into `currents`, so
+// that the peers — which only ever see this allocation — still read every count.
 constexpr int DIST_MAX_WORLD = 16;
-constexpr unsigned long long DIST_PACK_SLOT_U64 = 4 + 2 * 2048;
-constexpr unsigned long long DIST_MAIL_BYTES = (2 * DIST_MAX_WORLD + DIST_MAX_WORLD * DIST_PACK_SLOT_U64) * 8;
+constexpr int DIST_FLAG_ROWS = 3;
+constexpr unsigned long long PACK_HDR = 12;             // 4 scalars + 8 time stamps before the rows of a result pack
+constexpr unsigned long long PACK_MAX_U64 = PACK_HDR + 2 * 2048;
+constexpr unsigned long long DIST_PACK_SLOT_U64 = PACK_MAX_U64;
+constexpr unsigned long long DIST_MAIL_BYTES =
+    ((DIST_FLAG_ROWS * DIST_MAX_WORLD + DIST_MAX_WORLD * DIST_PACK_SLOT_U64) * 8 + 255) / 256 * 256;
 inline unsigned long long dist_mail_offset(unsigned long long pool) { return (pool * 4 + 255) / 256 * 256; }
+inline unsigned long long dist_spill_offset(unsigned long long pool) { return dist_mail_offset(pool) + DIST_MAIL_BYTES; }
+inline unsigned long long dist_alloc_bytes(unsigned long long pool) { return dist_spill_offset(pool) + pool * 8; }
 inline unsigned long long* dist_mail_flags(unsigned char* mail, int which) {
     return reinterpret_cast<unsigned long long*>(mail) + which * DIST_MAX_WORLD;
 }
 inline unsigned long long* dist_mail_slot(unsigned char* mail, int r) {
-    return reinterpret_cast<unsigned long long*>(mail) + 2 * DIST_MAX_WORLD + r * DIST_PACK_SLOT_U64;
+    return reinterpret_cast<unsigned long long*>(mail) + DIST_FLAG_ROWS * DIST_MAX_WORLD + r * DIST_PACK_SLOT_U64;
 }
 // raise flags[which][rank] = epoch in every peer's mailbox (one tiny kernel after the count kernels)
 cudaError_t launch_dist_signal(unsigned char* const* peer_mail, int world, int rank, int which, unsigned long long epoch,
                                cudaStream_t s);
 // wait for every rank's "pack delivered" flag in the local mailbox, then merge the packs found there
-cudaError_t launch_merge_mailbox(unsigned char* mail, int world, unsigned long long n_each, unsigned long long n_out,
+cudaError_t launch_merge_mailbox(unsigned char* mail, int world, int rank, unsigned long long n_each, unsigned long long n_out,
                                  unsigned long long epoch, unsigned long long timeout_ns, unsigned long long* pack_out,
                                  cudaStream_t s);
 cudaError_t post_max_grid(int device, int* grid);
 cudaError_t launch_post(const PostParams& q, int max_grid, cudaStream_t s);
 // merge `world` result packs (stride 4+2*n_each u64) into one: fired and k-mers summed, rows re-sorted
-cudaError_t launch_merge_packs(const unsigned long long* gathered, int world, unsigned long long n_each,
+cudaError_t launch_merge_packs(const unsigned long long* gathered, int world, int rank, unsigned long long n_each,
                                unsigned long long n_out, unsigned long long* pack_out, cudaStream_t s);
 
 // exact side tables (nk_exact.cu)

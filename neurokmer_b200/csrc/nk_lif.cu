@@ -33,6 +33,35 @@ __global__ void fold_kernel(unsigned int* __restrict__ acc, unsigned long long* 
     }
 }
 
+// u64 spill array (sharded-pool handles) -> currents; the spill array is left as it is (overwritten by its next use)
+__global__ void fold64_kernel(const unsigned long long* __restrict__ spill, unsigned long long* __restrict__ currents,
+                              unsigned long long pool, int overwrite) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < pool; i += stride)
+        currents[i] = (overwrite ? 0ull : currents[i]) + spill[i];
+}
+
+// Single-process multi-GPU groups, carried-state path: the leader GPU sums every member's u32 counts (and the
+// u64 spill arrays of the members that spilled) straight out of peer memory into its u64 currents
+// (= the reference's reduce over per-thread vectors, src/spiking_hash.rs:145-154, then :174-176).
+__global__ void peer_sum_kernel(const PeerSumParams ps, unsigned long long* __restrict__ currents,
+                                unsigned long long pool, int overwrite, unsigned long long* kmers_out) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < pool; i += stride) {
+        unsigned long long sum = overwrite ? 0ull : currents[i];
+        for (int r = 0; r < ps.n; ++r) sum += __ldcg(ps.acc[r] + i);
+        if (ps.spill_mask)
+            for (int r = 0; r < ps.n; ++r)
+                if ((ps.spill_mask >> r) & 1u) sum += __ldcg(ps.spill[r] + i);
+        currents[i] = sum;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long k = 0;
+        for (int r = 0; r < ps.n; ++r) k += __ldcg(ps.kmers[r]);
+        *kmers_out = k;
+    }
+}
+
 struct NeuronResult {
     float v;
     unsigned r;
@@ -299,6 +328,24 @@ cudaError_t launch_fold(unsigned int* acc, unsigned long long* currents, unsigne
     if (blocks > 148ull * 16) blocks = 148ull * 16;
     if (blocks == 0) blocks = 1;
     fold_kernel<<<(unsigned)blocks, 256, 0, s>>>(acc, currents, pool, overwrite ? 1 : 0);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fold64(const unsigned long long* spill, unsigned long long* currents, unsigned long long pool,
+                          bool overwrite, cudaStream_t s) {
+    unsigned long long blocks = (pool + 255) / 256;
+    if (blocks > 148ull * 16) blocks = 148ull * 16;
+    if (blocks == 0) blocks = 1;
+    fold64_kernel<<<(unsigned)blocks, 256, 0, s>>>(spill, currents, pool, overwrite ? 1 : 0);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_peer_sum(const PeerSumParams& ps, unsigned long long* currents, unsigned long long pool, bool overwrite,
+                            unsigned long long* kmers_out, cudaStream_t s) {
+    unsigned long long blocks = (pool + 255) / 256;
+    if (blocks > 148ull * 16) blocks = 148ull * 16;
+    if (blocks == 0) blocks = 1;
+    peer_sum_kernel<<<(unsigned)blocks, 256, 0, s>>>(ps, currents, pool, overwrite ? 1 : 0, kmers_out);
     return cudaGetLastError();
 }
 

@@ -95,12 +95,26 @@ __global__ void __launch_bounds__(PT, 3) post_kernel(const PostParams q) {
 
     // ---- peer-signalled mode: every rank must have finished counting before its counts are read ----
     __shared__ int s_timeout;
+    __shared__ unsigned s_spill_mask;
+    unsigned long long t_start = 0, t_ready = 0, t_phase1 = 0;
+    if (blockIdx.x == 0 && tid == 0) t_start = global_ns();
     if (q.wait_flags) {
         if (tid == 0) s_timeout = wait_flags(q.wait_flags, q.npeers, q.epoch, q.timeout_ns) ? 0 : 1;
         __syncthreads();
         // a timed-out block keeps going (leaving would deadlock grid.sync); the pack carries the error
         if (tid == 0 && s_timeout) atomicExch(&q.ctrl[1], 1ull);
     }
+    // which ranks spilled part of this job's counts into their u64 spill array (u32 overflow guard)
+    if (q.npeers) {
+        if (tid == 0) s_spill_mask = 0u;
+        __syncthreads();
+        if (tid < (unsigned)q.npeers && q.peer_mail[tid] != nullptr &&
+            ld_acquire_sys(reinterpret_cast<const unsigned long long*>(q.peer_mail[tid]) + 2 * DIST_MAX_WORLD) != 0ull)
+            atomicOr(&s_spill_mask, 1u << tid);
+        __syncthreads();
+    }
+    const unsigned spill_mask = q.npeers ? s_spill_mask : 0u;
+    if (blockIdx.x == 0 && tid == 0) t_ready = global_ns();
 
     // ---- phase 1: fold + LIF table apply + histogram of the top digit of the new spike totals ----
     // q.single_pass: the host-side bound says every total is < POST_EXACT_BINS (the reference's parameters cap a
@@ -136,6 +150,9 @@ __global__ void __launch_bounds__(PT, 3) post_kernel(const PostParams q) {
                     if (ok[u]) {
                         unsigned long long sum = 0;
                         for (int r = 0; r < q.npeers; ++r) sum += __ldcg(q.peer_acc[r] + q.slice_lo + i);
+                        if (spill_mask)  // rare: a rank counted more than 2^32-1 window starts in this job
+                            for (int r = 0; r < q.npeers; ++r)
+                                if ((spill_mask >> r) & 1u) sum += __ldcg(q.peer_spill[r] + q.slice_lo + i);
                         count[u] += sum;
                     }
                 } else if (ok[u] && p.fold_mode) {
@@ -192,6 +209,7 @@ __global__ void __launch_bounds__(PT, 3) post_kernel(const PostParams q) {
         atomicAdd(&q.hist[top * 256 + tid], s_hist[tid]);
     }
     grid.sync();
+    if (blockIdx.x == 0 && tid == 0) t_phase1 = global_ns();
 
     // ---- phase 2: MSB-first radix select of the n-th largest total (every block redundantly) ----
     unsigned long long prefix = 0, rank = q.n, gt = 0;
@@ -366,25 +384,31 @@ __global__ void __launch_bounds__(PT, 3) post_kernel(const PostParams q) {
             __syncthreads();
         }
     }
-    // pack: [0] spikes fired by this call, [1] unused, [2] k-mers of the call, [3] n, then idx[n], spikes[n]
+    // pack: [0] spikes fired by this call, [1] error, [2] k-mers of the call, [3] n, [4..11] time stamps
+    // (%globaltimer ns of THIS GPU: kernel start, peers' counts readable, end of the fused reduce + LIF
+    // phase, pack written; [8..10] belong to the merge kernel), then idx[n], spikes[n]
     for (unsigned i = tid; i < n; i += PT) {
         q.out_idx[i] = s_idx[i];
         q.out_spikes[i] = s_spk[i];
-        q.pack[4 + i] = s_idx[i] + q.slice_lo;
-        q.pack[4 + n + i] = s_spk[i];
+        q.pack[PACK_HDR + i] = s_idx[i] + q.slice_lo;
+        q.pack[PACK_HDR + n + i] = s_spk[i];
     }
     if (tid == 0) {
         q.pack[0] = *((volatile unsigned long long*)p.total_new);
         q.pack[1] = *((volatile unsigned long long*)&q.ctrl[1]);  // 1: a peer's "counting finished" signal timed out
         q.pack[2] = *((volatile unsigned long long*)q.kmers);
         q.pack[3] = n;
+        q.pack[4] = t_start;
+        q.pack[5] = t_ready;
+        q.pack[6] = t_phase1;
+        q.pack[7] = global_ns();
     }
     if (q.wait_flags) {
         // deliver the pack into every rank's mailbox (slot = this rank), then raise "pack delivered"
         __syncthreads();
-        const unsigned words = 4u + 2u * n;
+        const unsigned words = (unsigned)PACK_HDR + 2u * n;
         for (int r = 0; r < q.npeers; ++r) {
-            unsigned long long* slot = reinterpret_cast<unsigned long long*>(q.peer_mail[r]) + 2 * DIST_MAX_WORLD +
+            unsigned long long* slot = reinterpret_cast<unsigned long long*>(q.peer_mail[r]) + DIST_FLAG_ROWS * DIST_MAX_WORLD +
                                        (unsigned long long)q.rank * DIST_PACK_SLOT_U64;
             for (unsigned i = tid; i < words; i += PT) slot[i] = q.pack[i];
         }
@@ -402,11 +426,12 @@ __global__ void __launch_bounds__(PT) merge_packs_kernel(const unsigned long lon
                                                          unsigned long long n_each, unsigned long long stride,
                                                          unsigned long long n_out, unsigned long long* out,
                                                          const unsigned long long* flags, unsigned long long epoch,
-                                                         unsigned long long timeout_ns) {
+                                                         unsigned long long timeout_ns, int rank) {
     __shared__ unsigned long long s_idx[2048], s_spk[2048];
     __shared__ int s_err;
     const unsigned tid = threadIdx.x;
-    if (tid == 0) s_err = 0;
+    unsigned long long t_start = 0, t_ready = 0;
+    if (tid == 0) { s_err = 0; t_start = global_ns(); }
     if (flags) {
         if (tid == 0) s_err = wait_flags(flags, world, epoch, timeout_ns) ? 0 : 2;
         __syncthreads();
@@ -416,6 +441,7 @@ __global__ void __launch_bounds__(PT) merge_packs_kernel(const unsigned long lon
             return;
         }
     }
+    if (tid == 0) t_ready = global_ns();
     unsigned total = 0;
     for (int r = 0; r < world; ++r) total += (unsigned)__ldcg(&g[r * stride + 3]);
     unsigned N = 1;
@@ -426,8 +452,8 @@ __global__ void __launch_bounds__(PT) merge_packs_kernel(const unsigned long lon
     for (int r = 0; r < world; ++r) {
         const unsigned nr = (unsigned)__ldcg(&g[r * stride + 3]);
         for (unsigned i = tid; i < nr; i += PT) {
-            s_idx[off + i] = __ldcg(&g[r * stride + 4 + i]);
-            s_spk[off + i] = __ldcg(&g[r * stride + 4 + nr + i]);
+            s_idx[off + i] = __ldcg(&g[r * stride + PACK_HDR + i]);
+            s_spk[off + i] = __ldcg(&g[r * stride + PACK_HDR + nr + i]);
         }
         off += nr;
     }
@@ -452,29 +478,32 @@ __global__ void __launch_bounds__(PT) merge_packs_kernel(const unsigned long lon
     }
     const unsigned n = (unsigned)(n_out < total ? n_out : total);
     for (unsigned i = tid; i < n; i += PT) {
-        out[4 + i] = s_idx[i];
-        out[4 + n + i] = s_spk[i];
+        out[PACK_HDR + i] = s_idx[i];
+        out[PACK_HDR + n + i] = s_spk[i];
     }
     if (tid == 0) {
         unsigned long long fired = 0, kmers = 0, err = (unsigned long long)s_err;
         for (int r = 0; r < world; ++r) { fired += __ldcg(&g[r * stride + 0]); err |= __ldcg(&g[r * stride + 1]); kmers += __ldcg(&g[r * stride + 2]); }
         out[0] = fired; out[1] = err; out[2] = kmers; out[3] = n;
+        // this rank's own slice-kernel stamps travel with the merged pack; then the merge kernel's
+        for (int x = 4; x < 8; ++x) out[x] = __ldcg(&g[rank * stride + x]);
+        out[8] = t_start; out[9] = t_ready; out[10] = global_ns(); out[11] = 0;
     }
 }
 
 }  // namespace
 
-cudaError_t launch_merge_packs(const unsigned long long* gathered, int world, unsigned long long n_each,
+cudaError_t launch_merge_packs(const unsigned long long* gathered, int world, int rank, unsigned long long n_each,
                                unsigned long long n_out, unsigned long long* pack_out, cudaStream_t s) {
-    merge_packs_kernel<<<1, PT, 0, s>>>(gathered, world, n_each, 4 + 2 * n_each, n_out, pack_out, nullptr, 0, 0);
+    merge_packs_kernel<<<1, PT, 0, s>>>(gathered, world, n_each, PACK_HDR + 2 * n_each, n_out, pack_out, nullptr, 0, 0, rank);
     return cudaGetLastError();
 }
 
-cudaError_t launch_merge_mailbox(unsigned char* mail, int world, unsigned long long n_each, unsigned long long n_out,
+cudaError_t launch_merge_mailbox(unsigned char* mail, int world, int rank, unsigned long long n_each, unsigned long long n_out,
                                  unsigned long long epoch, unsigned long long timeout_ns, unsigned long long* pack_out,
                                  cudaStream_t s) {
     merge_packs_kernel<<<1, PT, 0, s>>>(dist_mail_slot(mail, 0), world, n_each, DIST_PACK_SLOT_U64, n_out, pack_out,
-                                        dist_mail_flags(mail, 1), epoch, timeout_ns);
+                                        dist_mail_flags(mail, 1), epoch, timeout_ns, rank);
     return cudaGetLastError();
 }
 

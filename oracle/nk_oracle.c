@@ -599,8 +599,16 @@ NKO_EXPORT uint64_t nko_lif_mt(const uint64_t *currents, uint64_t pool_size, uin
 }
 
 /* EnergyTracker — src/models.rs:159-172, src/spiking_hash.rs:649-655 */
+/* `(cost * 1000.0) as u64`: Rust's cast saturates (NaN -> 0, negative -> 0, >= 2^64 -> u64::MAX); the product
+ * wraps (release-mode u64 multiply / repeated fetch_add). */
+static uint64_t cost_fixed(double spike_cost) {
+    const double x = spike_cost * 1000.0;
+    if (!(x > 0.0)) return 0;
+    if (x >= 18446744073709551616.0) return UINT64_MAX;
+    return (uint64_t)x;
+}
 NKO_EXPORT uint64_t nko_energy_fixed(uint64_t new_spikes, double spike_cost) {
-    return new_spikes * (uint64_t)(spike_cost * 1000.0);
+    return new_spikes * cost_fixed(spike_cost);
 }
 NKO_EXPORT double nko_energy_total(uint64_t fixed) { return (double)fixed / 1000.0; }
 

@@ -170,9 +170,20 @@ def top_n(spikes: Sequence[int], n: int) -> List[Tuple[int, int]]:
     return [(i, int(spikes[i])) for i in order[:n]]
 
 
+def cost_fixed(spike_cost: float) -> int:
+    """`(cost * 1000.0) as u64` (reference src/models.rs:162, src/spiking_hash.rs:649): Rust's float -> int
+    `as` cast truncates toward zero and SATURATES (NaN -> 0, negative -> 0, >= 2^64 -> u64::MAX)."""
+    x = float(spike_cost) * 1000.0
+    if x != x or x <= 0.0:
+        return 0
+    if x >= 18446744073709551616.0:
+        return M64
+    return int(x)
+
+
 def energy(total_spikes: int, spike_cost: float) -> float:
-    """reference src/models.rs:159-172 + src/spiking_hash.rs:649-655."""
-    return float((total_spikes * int(spike_cost * 1000.0)) & M64) / 1000.0
+    """reference src/models.rs:159-172 + src/spiking_hash.rs:649-655 (wrapping u64 arithmetic)."""
+    return float((total_spikes * cost_fixed(spike_cost)) & M64) / 1000.0
 
 
 # --- ctypes wrapper around libnk_oracle.so -----------------------------------
@@ -346,7 +357,7 @@ class OracleCounter:
         fired, *_ = self.c.lif(self.currents, self.steps, float(self.threshold), float(self.leak),
                                self.refractory, self.v, self.r, self.spikes, simd, self.threads)
         self.total_spikes += fired
-        self.energy_fixed = (self.energy_fixed + fired * int(self.spike_cost * 1000.0)) & M64
+        self.energy_fixed = (self.energy_fixed + fired * cost_fixed(self.spike_cost)) & M64
 
     def process_parallel(self, bases: np.ndarray, offsets: np.ndarray) -> None:
         self.currents, _ = self.c.accumulate(bases, offsets, self.k, self.pool_size, self.use_canonical,

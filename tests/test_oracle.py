@@ -241,3 +241,31 @@ def test_exact_map_variant_of_the_cpu_baseline(coracle):
             assert tot2 == tot and nd == keys.size
             np.testing.assert_array_equal(cur2, cur)
             np.testing.assert_array_equal(uni, np.bincount(idx, minlength=pool).astype(np.uint32))
+
+
+def test_shard_plan_partitions_the_windows():
+    """nk_create_multi's shard plan (host logic, nk_debug_shard): the pieces of all members partition the windows
+    of the batch — sequences cut by a shard boundary are read with a k-1 overlap and every window start has
+    exactly one owner (the reference's fold over whole sequences, src/spiking_hash.rs:94-154, cut finer)."""
+    from neurokmer_b200.counter import debug_shard, flatten
+    from oracle.oracle_py import COracle
+    c = COracle()
+    rng = np.random.default_rng(12)
+    for k, world in [(31, 2), (21, 3), (5, 8), (32, 4), (1, 5)]:
+        lens = [0, 1, k - 1, k, 9000, 150, 20, 0, 30000, 4096, 4097, 12288 - k + 1, 7]
+        seqs = [rng.choice(np.frombuffer(b"ACGTN", np.uint8), size=n).tobytes() for n in lens]
+        bases, offsets = flatten(seqs)
+        pool = 10007
+        want, tot = c.accumulate(bases, offsets, k, pool, True)
+        got = np.zeros(pool, np.uint64)
+        windows = 0
+        for r in range(world):
+            start, po = debug_shard(offsets, k, world, r)
+            assert start % 4096 == 0 or start == bases.size
+            assert np.all(np.diff(po.astype(np.int64)) > 0) or po.size == 1
+            piece = bases[start:start + int(po[-1])]
+            cur, t = c.accumulate(piece, po, k, pool, True)
+            got += cur
+            windows += t
+        assert windows == tot
+        np.testing.assert_array_equal(got, want)

@@ -1452,3 +1452,66 @@ def test_lif_memoised_carried_state_equals_direct(coracle):
         np.testing.assert_array_equal(a.spike_counts(), b.spike_counts())
         np.testing.assert_array_equal(a.refractory_ticks(), b.refractory_ticks())
     assert a.timings()["lif_path"] == 5 and b.timings()["lif_path"] == 1
+
+
+@pytest.mark.parametrize("cost", [0.0015, 2.5, 0.0009, 0.0, -3.0, float("nan"), 1e30, 123456.789])
+def test_energy_tracker_cost_truncation(cost):
+    """EnergyTracker (models.rs:159-172, spiking_hash.rs:649-655): `(cost * 1000.0) as u64` truncates toward zero and
+    saturates (NaN and negatives -> 0, >= 2^64 -> u64::MAX), the product with the spike count wraps mod 2^64,
+    total_energy() = fixed / 1000.0.  Fresh job (fused kernel) and carried state (separate kernels)."""
+    from neurokmer_b200 import flatten
+    rng = np.random.default_rng(31)
+    k, pool = 15, 4096
+    bases, offsets = flatten([random_dna(rng, 600_000, 0.001), random_dna(rng, 150)])
+    c = make(k, pool, spike_cost=cost)
+    o = oracle_counter(k, pool, spike_cost=cost)
+    for _ in range(2):
+        c.process_batch(bases, offsets); o.process_parallel(bases, offsets)
+        assert c.energy.total_spikes() == o.total_spikes > 0
+        assert c.energy_used() == o.energy_used()
+    from oracle.oracle_py import cost_fixed
+    assert o.energy_used() == ((o.total_spikes * cost_fixed(cost)) & (2**64 - 1)) / 1000.0
+    c.close()
+
+
+def test_config2_full_size_against_oracle():
+    """BASELINE configs[1] — the configuration the metric is quoted on — at FULL size (113 Mbase, 7 sequences,
+    sparse N runs, 1 % lower case, k=31, pool 2 M, canonical, streaming), bit-exact against the oracle: currents,
+    spike counts, voltages, refractory ticks, totals, top-20.  Three ways in: the device-resident batch bench.py's
+    `value` times, the host batch its `e2e` times (pageable here, pinned below), and the pre-packed form."""
+    import bench
+    from neurokmer_b200 import PinnedBuffer, pack_bases
+    from neurokmer_b200.devmem import copy_h2d
+    from oracle.oracle_py import OracleCounter
+    from oracle.synth import synth_bases
+    k, pool = bench.K, bench.POOL
+    n, nseq = bench.NBASES, len(bench.SEQ_LENS)
+    offsets = np.concatenate([[0], np.cumsum(bench.SEQ_LENS)]).astype(np.uint64)
+    c = make(k, pool)
+    db, do = c.stage_reserve(n, nseq)
+    c.synth_fill(db, bench.SEED, 0, n, bench.SYNTH_FLAGS); copy_h2d(do, offsets); c.synchronize()
+    # the oracle's input: the generator's bytes read back from the device (the numpy twin takes ~25 s for 113 Mbase);
+    # three windows of it are checked against the twin here, the generator itself in test_synth_generator_matches_numpy_twin
+    from neurokmer_b200.devmem import device_to_numpy
+    bases = device_to_numpy(db, n)
+    for at in (0, 56_123_457, n - 1_000_000):
+        np.testing.assert_array_equal(bases[at:at + 1_000_000], synth_bases(bench.SEED, at, 1_000_000, bench.SYNTH_FLAGS))
+    o = OracleCounter(k, 1.0, 0.95, 2, 1.0, pool, True, 1000, threads=os.cpu_count() or 4)
+    o.process_streaming([(bases, offsets)])
+    assert int(o.currents.sum()) == bench.KMERS
+    c.stream_begin(); c.process_staged(n, nseq, 1); c.stream_finish()
+    assert c.timings()["kmers"] == bench.KMERS
+    assert_topn_equal(c, o, 20); assert_state_equal(c, o)
+    c.reset(); c.stream_begin(); c.stream_push(bases, offsets); c.stream_end()
+    assert_topn_equal(c, o, 20); assert_state_equal(c, o)
+    pin = PinnedBuffer(n); pin.array[:] = bases
+    c.reset(); c.stream_begin(); c.stream_push(pin.array, offsets); c.stream_end()
+    assert_topn_equal(c, o, 20); assert_state_equal(c, o)
+    codes, other, _ = pack_bases(bases)
+    c.reset(); c.stream_begin(); c.stream_push_packed(codes, other, offsets); c.stream_end()
+    assert_topn_equal(c, o, 20); assert_state_equal(c, o)
+    # one input over several members (all on this GPU): sequences cut at 113 M / 3
+    from neurokmer_b200 import SpikingKmerCounter
+    g = SpikingKmerCounter(k, 1.0, 0.95, 2, 1.0, pool, True, devices=[0, 0, 0])
+    g.stream_begin(); g.stream_push(pin.array, offsets); g.stream_end()
+    assert_topn_equal(g, o, 20); assert_state_equal(g, o)

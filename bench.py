@@ -20,8 +20,14 @@ followed by the top-20 read-out.  One "step" = one whole job on a freshly reset 
   cpu_baseline : the oracle port (oracle/nk_oracle.c, pthreads, all host cores) on a bounded
                  sample of the same workload — a reported baseline, not the target
 
-N > 1 (torchrun, one process per GPU): weak scaling — every rank counts its own 113 Mbase
-shard of the same synthetic stream into a full accumulator replica.  Default (--dist peer): each
+  e2e_pageable : e2e with the bases in plain pageable memory (what the reference's `&[Vec<u8>]` is)
+  result.parity: after the timed legs rank 0 runs the CPU oracle over the WHOLE job (all ranks' shards) and
+                 compares currents (sha256 of the u64 array), spike counts, total spikes and the top-20
+
+N > 1 (torchrun, one process per GPU): weak scaling — ONE synthetic stream of N x 113 Mbase (7 sequences of
+N x {30,25,20,15,10,8,5} Mbase) cut by window start into N equal ranges: rank r owns starts
+[r*113M, (r+1)*113M) and reads k-1 bases past its range, so sequences are cut between GPUs.  Each rank
+counts into a full accumulator replica.  `strong_scaling` (N > 1): the 113 Mbase job itself split N ways.  Default (--dist peer): each
 rank owns a neuron slice; its LIF/top-N kernel sums that slice of every rank's counts through
 NVLink peer memory, and the "finished counting" flags and result packs travel the same way — no
 NCCL call per job.  --dist fused: the same kernels with an NCCL barrier + all-gather around them;
@@ -53,6 +59,39 @@ KMERS = sum(l - K + 1 for l in SEQ_LENS)
 WORKLOAD = "synthetic 113 Mbase FASTA-equivalent (7 seqs, sparse N runs, 1% lowercase), k=31, pool 2M, canonical, streaming"
 LIF_REF = dict(threshold=1.0, leak=0.95, refractory=2, spike_cost=1.0)
 SIPHASH_OPS = 131  # 32-bit integer ops per k-mer of SipHash-1-3 on one 8-byte block
+
+
+def make_config(world: int, dist: str):
+    """the `config` object of BOTH arms (the driver compares them)"""
+    fused = world > 1 and dist in ("fused", "peer")
+    return {"workload": WORKLOAD, "k": K, "pool_size": POOL, "lif_steps": STEPS_LIF, "top_n": TOPN,
+            "kmers_per_step_per_gpu": KMERS, "l2": "flushed before every step (256 MiB fill)",
+            "parallelism": f"dp{world}: ONE stream cut by window start (k-1 overlap), full accumulator replica per GPU, "
+                           + ("neuron-sliced LIF/top-N with peer-memory reduce" if fused or world == 1 else "one NCCL all-reduce")
+                           + (", peer-memory signalling (no NCCL per job)" if world > 1 and dist == "peer" else "")}
+
+
+def stream_layout(world: int):
+    """the whole job at `world` ranks: 7 sequences of world x SEQ_LENS bases"""
+    lens = [l * world for l in SEQ_LENS]
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    return lens, offs
+
+
+def shard_of(offs: np.ndarray, lo: int, hi: int):
+    """pieces (offsets relative to lo) the owner of window starts [lo, hi) counts: every sequence clipped to
+    [lo, hi + K - 1) — the rule of neurokmer_b200/csrc/nk_multi.cu (shard_pieces)"""
+    total = int(offs[-1])
+    lim = min(hi + K - 1, total)
+    out = [0]
+    for s in range(len(offs) - 1):
+        a, e = int(offs[s]), int(offs[s + 1])
+        if a >= hi:
+            break
+        p0, p1 = max(a, lo), min(e, lim)
+        if p1 > p0:
+            out.append(p1 - lo)
+    return np.array(out, np.uint64)
 
 
 def peaks():
@@ -190,7 +229,7 @@ def reference_arm(args):
         "impl": "reference", "metric": "canonical k-mers/sec (k=31, 2M pool)", "value": v, "unit": "kmers/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "k": K, "pool_size": POOL, "lif_steps": STEPS_LIF, "top_n": TOPN},
+        "config": make_config(args.gpus, args.dist),
         "cpu_baseline": {"value": v, "unit": "kmers/s", "cores": threads, "kind": "port", "sample": samp},
         "e2e": {"value": v, "unit": "kmers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference is a Rust crate (no cargo/rustc in this image): timed the C restatement oracle/nk_oracle.c",
@@ -208,6 +247,7 @@ class CurrentsView:
 
 
 def gpu_arm(args):
+    import hashlib
     import torch
     import torch.distributed as dist
     from neurokmer_b200 import PinnedBuffer, SpikingKmerCounter
@@ -216,35 +256,42 @@ def gpu_arm(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    os.environ["NCCL_DEBUG"] = os.environ.get("NK_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
+    # NCCL_DEBUG is the environment's (the driver reads the communicator lines); NCCL's output and everything else
+    # this process prints go to stderr — stdout carries the one JSON line
     local %= max(torch.cuda.device_count(), 1)  # launchers that expose one device per rank
     torch.cuda.set_device(local)
     saved_stdout = os.dup(1)
-    os.dup2(2, 1)  # NCCL prints a version banner to stdout: keep stdout to the one JSON line
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     c = SpikingKmerCounter(K, LIF_REF["threshold"], LIF_REF["leak"], LIF_REF["refractory"], LIF_REF["spike_cost"],
                            POOL, True, device=local)
     stream = torch.cuda.ExternalStream(c.cuda_stream(), device=torch.device("cuda", local))
-    offsets = np.concatenate([[0], np.cumsum(SEQ_LENS)]).astype(np.uint64)
-    nseq = len(SEQ_LENS)
 
-    # device-resident input: this rank's shard of the stream (weak scaling: NBASES per rank)
-    dev_bases, dev_offs = c.stage_reserve(NBASES, nseq)
-    c.synth_fill(dev_bases, SEED, rank * NBASES, NBASES, SYNTH_FLAGS)
+    # ---- the job: ONE stream of world x NBASES bases; this rank owns window starts [lo, hi) -----------------
+    lens_all, offs_all = stream_layout(world)
+    total_bases = int(offs_all[-1])
+    total_kmers = int(sum(l - K + 1 for l in lens_all))
+    lo, hi = rank * NBASES, (rank + 1) * NBASES
+    offsets = shard_of(offs_all, lo, hi)                  # pieces of this rank (sequences cut at lo / hi)
+    nseq, nb = len(offsets) - 1, int(offsets[-1])        # nb = NBASES + k-1 halo (except on the last rank)
+    my_kmers = int(sum(max(0, int(offsets[i + 1] - offsets[i]) - K + 1) for i in range(nseq)))
+
+    dev_bases, dev_offs = c.stage_reserve(nb, nseq)
+    c.synth_fill(dev_bases, SEED, lo, nb, SYNTH_FLAGS)
     copy_h2d(dev_offs, offsets)
     c.synchronize()
-    # host copy of the same bytes in pinned memory for the end-to-end leg
-    pinned = PinnedBuffer(NBASES if not args.no_e2e else 16)
-    if not args.no_e2e:
-        pinned.array[:] = device_to_numpy(dev_bases, NBASES)
-    # the same bytes in the pre-packed "nk2" form (2-bit codes + `other` bits) for the e2e_prepacked leg
+    # host copies of the same bytes for the end-to-end legs: pinned, pageable, pre-packed
+    pinned = PinnedBuffer(nb if not args.no_e2e else 16)
+    pageable = None
     pk_codes = pk_other = None
     pack_ms = None
     if not args.no_e2e:
+        pinned.array[:] = device_to_numpy(dev_bases, nb)
+        pageable = np.array(pinned.array, copy=True)      # plain malloc memory: what the reference's &[Vec<u8>] is
         from neurokmer_b200 import pack_bases
-        pk_codes = PinnedBuffer(4 * ((NBASES + 15) // 16), np.uint32)
-        pk_other = PinnedBuffer(4 * ((NBASES + 31) // 32), np.uint32)
+        pk_codes = PinnedBuffer(4 * ((nb + 15) // 16), np.uint32)
+        pk_other = PinnedBuffer(4 * ((nb + 31) // 32), np.uint32)
         best = 1e9
         for _ in range(5):
             t0 = time.perf_counter()
@@ -318,11 +365,13 @@ def gpu_arm(args):
         c.dist_complete(gathered.data_ptr(), each)
         ar_events.append((a0, a1, a2, a3))
 
+    staged_now = {"nb": nb, "nseq": nseq}
+
     def job_resident():
         t = [time.perf_counter()]
         c.reset(); t.append(time.perf_counter())
         c.stream_begin(); t.append(time.perf_counter())
-        c.process_staged(NBASES, nseq, 1); t.append(time.perf_counter())
+        c.process_staged(staged_now["nb"], staged_now["nseq"], 1); t.append(time.perf_counter())
         if world > 1:
             finish_distributed(); t.append(time.perf_counter()); t.append(time.perf_counter())
         else:
@@ -332,25 +381,21 @@ def gpu_arm(args):
         trace.append(np.diff(t) * 1e3)
         return top
 
-    def job_e2e():
-        c.reset()
-        c.stream_begin()
-        c.stream_push(pinned.array, offsets)
-        if world > 1:
-            finish_distributed()
-        else:
-            c.stream_finish()
-        return c.top_abundant_neurons(TOPN)
+    def host_job(push):
+        def job():
+            c.reset()
+            c.stream_begin()
+            push()
+            if world > 1:
+                finish_distributed()
+            else:
+                c.stream_finish()
+            return c.top_abundant_neurons(TOPN)
+        return job
 
-    def job_e2e_packed():
-        c.reset()
-        c.stream_begin()
-        c.stream_push_packed(pk_codes.array, pk_other.array, offsets)
-        if world > 1:
-            finish_distributed()
-        else:
-            c.stream_finish()
-        return c.top_abundant_neurons(TOPN)
+    job_e2e = host_job(lambda: c.stream_push(pinned.array, offsets))
+    job_e2e_pageable = host_job(lambda: c.stream_push(pageable, offsets))
+    job_e2e_packed = host_job(lambda: c.stream_push_packed(pk_codes.array, pk_other.array, offsets))
 
     def barrier():
         torch.cuda.synchronize()
@@ -387,76 +432,149 @@ def gpu_arm(args):
     timed(job_resident, W)
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
-        sampler.start()  # sampled through BOTH timed legs (resident + end-to-end)
+        sampler.start()  # sampled through ALL timed legs (resident + end-to-end)
     ar_events.clear()
     steps_res, phases, top, _ = timed(job_resident, args.steps)
     if ar_events and len(ar_events[0]) == 4:
         ar_ms = float(np.mean([e[0].elapsed_time(e[1]) + e[2].elapsed_time(e[3]) for e in ar_events]))
     else:
         ar_ms = float(np.mean([a.elapsed_time(b) for a, b in ar_events])) if ar_events else 0.0
-    if args.no_e2e:
-        steps_e2e, phases_e2e, top_e2e = [(0.0, float("nan"))], [dict(h2d_bytes=0, d2h_bytes=0)], top
-    else:
-        timed(job_e2e, 2)
-        steps_e2e, phases_e2e, top_e2e, _ = timed(job_e2e, args.steps)
-    steps_pk = None
+    # the job's result + the state the oracle is compared with (taken NOW: later legs reuse the counter)
+    total_spikes = c.energy.total_spikes()
+    slice_lo, slice_len = c.dist_slice() if fused else (0, POOL)
+    my_currents = c.currents()[slice_lo:slice_lo + slice_len].copy()
+    my_spikes = c.spike_counts()[slice_lo:slice_lo + slice_len].copy()
+
+    legs = {}
     if not args.no_e2e:
-        timed(job_e2e_packed, 2)
-        steps_pk, phases_pk, top_pk, _ = timed(job_e2e_packed, args.steps)
-        assert top == top_pk, "pre-packed and ASCII legs disagree"
+        for name, job in (("e2e", job_e2e), ("e2e_pageable", job_e2e_pageable), ("e2e_prepacked", job_e2e_packed)):
+            timed(job, 2)
+            st, ph, tp, _ = timed(job, args.steps)
+            assert tp == top, f"{name} and resident legs disagree"
+            legs[name] = (st, ph)
+
+    # ---- strong scaling (N > 1): the 113 Mbase job itself, cut N ways ------------------------------------------
+    strong = None
+    if world > 1:
+        _, offs1 = stream_layout(1)
+        per = -(-NBASES // world)
+        slo, shi = min(NBASES, rank * per), min(NBASES, (rank + 1) * per)
+        s_offsets = shard_of(offs1, slo, shi)
+        s_nseq, s_nb = len(s_offsets) - 1, int(s_offsets[-1])
+        db, do = c.stage_reserve(s_nb, s_nseq)           # the staged buffer only grows: same device memory
+        c.synth_fill(db, SEED, slo, s_nb, SYNTH_FLAGS)
+        copy_h2d(do, s_offsets)
+        c.synchronize()
+        staged_now.update(nb=s_nb, nseq=s_nseq)
+        timed(job_resident, 2)
+        st, ph, s_top, _ = timed(job_resident, args.steps)
+        strong = (st, ph, s_top, c.energy.total_spikes())
+        staged_now.update(nb=nb, nseq=nseq)
     clocks = sampler.stop() if sampler else None
-    assert top == top_e2e, "resident and end-to-end legs disagree"
 
     if os.environ.get("NK_TRACE"):
         print(f"[rank {rank}] per-step (event ms, wall ms):", [(round(a, 3), round(b, 3)) for a, b in steps_res[:12]], file=sys.stderr)
         print(f"[rank {rank}] host ms per call (reset, begin, staged, accumulate+allreduce, finish, topn):",
               np.round(np.mean(trace[-args.steps:], axis=0), 3), file=sys.stderr)
-    total_spikes = c.energy.total_spikes()
-    dev_ms = float(sum(s[0] for s in steps_res))
-    e2e_ms = float(sum(s[1] for s in steps_e2e))
-    pk_ms = float(sum(s[1] for s in steps_pk)) if steps_pk else float("nan")
-    t = torch.tensor([dev_ms, e2e_ms, pk_ms], dtype=torch.float64, device="cuda")
+
+    def leg_ms(name):
+        return float(sum(x[1] for x in legs[name][0])) if name in legs else float("nan")
+
+    ph_mean = lambda key, src=None: float(np.mean([p[key] for p in (src or phases)]))
+    vals = [float(sum(x[0] for x in steps_res)), leg_ms("e2e"), leg_ms("e2e_pageable"), leg_ms("e2e_prepacked"),
+            float(sum(x[0] for x in strong[0])) if strong else float("nan"),
+            ph_mean("count_ms"), ph_mean("exch_wait_ms"), ph_mean("exch_reduce_ms"), ph_mean("merge_ms"), ph_mean("post_ms")]
+    t = torch.tensor(vals, dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, pk_ms = float(t[0]), float(t[1]), float(t[2])
-    total_kmers = KMERS * world * args.steps
-    value = total_kmers / (dev_ms * 1e-3)
-    e2e_value = total_kmers / (e2e_ms * 1e-3)
+    dev_ms, e2e_ms, pg_ms, pk_ms, strong_ms, count_ms_max, wait_ms, reduce_ms, merge_ms, post_ms = (float(x) for x in t)
+    job_kmers = total_kmers * args.steps
+    value = job_kmers / (dev_ms * 1e-3)
+
+    # ---- parity: the CPU oracle over the WHOLE job (all ranks' shards), outside every timed region ---------
+    parity = {"checked": False}
+    if not args.no_parity:
+        if world > 1:
+            gathered = [None] * world if rank == 0 else None
+            dist.gather_object((slice_lo, my_currents, my_spikes), gathered, dst=0)
+        else:
+            gathered = [(slice_lo, my_currents, my_spikes)]
+        if rank == 0:
+            from oracle.oracle_py import COracle
+            t0 = time.perf_counter()
+            whole = torch.empty(total_bases, dtype=torch.uint8, device="cuda")
+            c.synth_fill(whole.data_ptr(), SEED, 0, total_bases, SYNTH_FLAGS)   # the generator is position-addressable
+            c.synchronize()
+            host = whole.cpu().numpy()
+            del whole
+            orc = COracle()
+            threads = os.cpu_count() or 1
+            o_cur, o_tot = orc.accumulate(host, offs_all, K, POOL, True, threads=threads)
+            o_fired, _, _, o_spk = orc.lif(o_cur, STEPS_LIF, LIF_REF["threshold"], LIF_REF["leak"], LIF_REF["refractory"],
+                                           simd_semantics=True, threads=threads)
+            o_idx, o_sp = orc.top_n(o_spk, TOPN)
+            g_cur = np.zeros(POOL, np.uint64)
+            g_spk = np.zeros(POOL, np.uint64)
+            for lo_r, cur_r, spk_r in gathered:
+                g_cur[lo_r:lo_r + cur_r.size] = cur_r
+                g_spk[lo_r:lo_r + spk_r.size] = spk_r
+            parity = {
+                "checked": True,
+                "oracle": "oracle/nk_oracle.c over the whole job (all ranks' shards as ONE stream), LIF, top-%d" % TOPN,
+                "currents_equal": bool(np.array_equal(g_cur, o_cur)),
+                "currents_sha256": hashlib.sha256(g_cur.tobytes()).hexdigest(),
+                "oracle_currents_sha256": hashlib.sha256(o_cur.tobytes()).hexdigest(),
+                "spike_counts_equal": bool(np.array_equal(g_spk, o_spk)),
+                "total_spikes_equal": bool(int(o_fired) == int(total_spikes)),
+                "kmers_equal": bool(int(o_tot) == total_kmers == int(g_cur.sum())),
+                "topn_equal": bool([(int(a), int(b)) for a, b in zip(o_idx, o_sp)] == [(r[0], r[1]) for r in top]),
+                "oracle_seconds": round(time.perf_counter() - t0, 2), "oracle_threads": threads,
+            }
+            if strong:  # the strong-scaling leg runs the N=1 job: its result is checked against the same oracle at N=1 size
+                _, offs1 = stream_layout(1)
+                s_cur, _ = orc.accumulate(host[:NBASES], offs1, K, POOL, True, threads=threads)  # same generator, same positions
+                s_fired, _, _, s_spk = orc.lif(s_cur, STEPS_LIF, LIF_REF["threshold"], LIF_REF["leak"], LIF_REF["refractory"],
+                                               simd_semantics=True, threads=threads)
+                s_idx, s_sp = orc.top_n(s_spk, TOPN)
+                parity["strong_total_spikes_equal"] = bool(int(s_fired) == int(strong[3]))
+                parity["strong_topn_equal"] = bool([(int(a), int(b)) for a, b in zip(s_idx, s_sp)] == [(r[0], r[1]) for r in strong[2]])
 
     if rank == 0:
         pk, pk_kind = peaks()
-        count_ms = float(np.mean([p["count_ms"] for p in phases]))
-        kps_kernel = KMERS / (count_ms * 1e-3)
+        count_ms = ph_mean("count_ms")
+        kps_kernel = my_kmers / (count_ms * 1e-3)
         # the three limits of the north star, denominators measured on this device
         c.reset()
         alu_ops = c.calibrate(0)
         sip_ops = c.calibrate(1)
         red_ps = c.calibrate(2)
         c.reset()
-        hbm_bound = pk["hbm_gbs"] * 1e9 / (NBASES / KMERS)       # 1 B of ASCII per k-mer
+        hbm_bound = pk["hbm_gbs"] * 1e9 / (nb / my_kmers)       # 1 B of ASCII per k-mer
         int_bound = sip_ops / SIPHASH_OPS
         red_bound = red_ps
         binding = min((hbm_bound, "hbm"), (int_bound, "int32"), (red_bound, "l2_atomic"))
+        traffic, traffic_src = ncu_traffic()
         roofline = {
             "bound": binding[1], "kernel": "count_kernel (windowing+SipHash-1-3+mod+RED.ADD)",
             "achieved": kps_kernel * SIPHASH_OPS / 1e9 if binding[1] == "int32" else kps_kernel / 1e9,
             "peak": sip_ops / 1e9 if binding[1] == "int32" else binding[0] / 1e9,
             "unit": "Gop/s (32-bit integer, SipHash mix)" if binding[1] == "int32" else "G/s",
             "frac": kps_kernel / binding[0],
-            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this workload, one `ncu --set full`
-            # capture (profiles/r01_count_kernel_ncu.md): 135.16 MB + 5.32 MB per launch vs 127 MB algorithmic
-            "traffic": 140.48e6, "traffic_unit": "bytes per launch (ncu)", "algorithmic_bytes_per_launch": NBASES + NBASES // 8,
+            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this workload from the committed
+            # `ncu --set full` capture (profiles/, see tools/ncu_summary.py); null when no capture matches this kernel
+            "traffic": traffic, "traffic_unit": "bytes per launch (ncu)", "traffic_source": traffic_src,
+            "algorithmic_bytes_per_launch": nb,
             "bound_note": "north star: binding roofline = slowest of {HBM input bytes, SipHash int ops, L2 pool updates}; "
-                          "the integer ALU pipe binds (ncu: ALU pipe 92 % busy, DRAM 1.9 %); the HBM view is under 'hbm'",
+                          "the integer ALU pipe binds; the HBM view is under 'hbm'",
             "kernel_ms": count_ms, "kernel_kmers_per_s": kps_kernel,
             "limits_kmers_per_s": {"hbm": hbm_bound, "int32": int_bound, "l2_atomic": red_bound},
-            "hbm": {"achieved": NBASES / (count_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                    "frac": NBASES / (count_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "peak_source": pk_kind + " (MEASURED_PEAKS.json)"},
+            "hbm": {"achieved": nb / (count_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                    "frac": nb / (count_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "peak_source": pk_kind + " (MEASURED_PEAKS.json)"},
             "peaks_measured_live": {"alu_lop3_shf_gops": alu_ops / 1e9, "sipround_mix_gops": sip_ops / 1e9,
-                                    "red_add_u32_random_2M_gps": red_ps / 1e9},
-            "algorithmic_per_kmer": {"hbm_bytes": NBASES / KMERS, "int32_ops": SIPHASH_OPS, "l2_reductions": 1},
+                                    "red_add_u32_hashed_addresses_gps": red_ps / 1e9},
+            "algorithmic_per_kmer": {"hbm_bytes": nb / my_kmers, "int32_ops": SIPHASH_OPS, "l2_reductions": 1},
         }
-        ph = {k: float(np.mean([p[k] for p in phases])) for k in ("mark_ms", "count_ms", "fold_ms", "lif_ms", "topn_ms")}
+        ph = {k: ph_mean(k) for k in ("mark_ms", "count_ms", "fold_ms", "lif_ms", "topn_ms", "post_ms")}
         launches = int(phases[-1]["launches"] + phases[-1]["topn_launches"])
         # CPU baseline on a bounded sample (rank 0, N=1 only)
         cpu = None
@@ -473,42 +591,81 @@ def gpu_arm(args):
                                                  f"{d['exact_sample_bases']} bases ({d['exact_distinct']} distinct k-mers, "
                                                  f"{d['exact_sample_s']:.2f} s), same LIF + top-20; job time extrapolated = "
                                                  f"{d['exact_job_extrapolated']:.2f} s")}}
+
+        def leg_record(name, ms, extra=None):
+            if name not in legs:
+                return None
+            ph_l = legs[name][1]
+            rec = {"value": job_kmers / (ms * 1e-3), "unit": "kmers/s", "ms_per_step": ms / args.steps,
+                   "h2d_bytes_per_step": int(ph_l[-1]["h2d_bytes"]),
+                   "d2h_bytes_per_step": int(ph_l[-1]["d2h_bytes"] + 24 + 16 * TOPN)}
+            if rec["h2d_bytes_per_step"]:
+                rec["pcie_gbs_per_rank"] = rec["h2d_bytes_per_step"] / (ms / args.steps * 1e-3) / 1e9
+            rec.update(extra or {})
+            return rec
+
+        if peer:
+            collective_ms = wait_ms + reduce_ms + merge_ms
+        else:
+            collective_ms = ar_ms
         line = {
             "metric": f"canonical k-mers/sec (k={K}, {POOL // 1_000_000}M pool)", "value": value, "unit": "kmers/s", "n_gpus": world,
             "steps": args.steps, "warmup": W, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "k": K, "pool_size": POOL, "lif_steps": STEPS_LIF, "top_n": TOPN,
-                       "kmers_per_step_per_gpu": KMERS, "l2": "flushed before every step (256 MiB fill)",
-                       "parallelism": f"dp{world}: sequence-chunk shards, full accumulator replica per GPU, "
-                                      + ("neuron-sliced LIF/top-N with peer-memory reduce" if fused else "one NCCL all-reduce")
-                                      + (", peer-memory signalling (no NCCL per job)" if peer else "")},
-            "e2e": {"value": e2e_value, "unit": "kmers/s", "ms_per_step": e2e_ms / args.steps,
-                    "h2d_bytes_per_step": int(phases_e2e[-1]["h2d_bytes"]),
-                    "d2h_bytes_per_step": int(phases_e2e[-1]["d2h_bytes"] + 24 + 16 * TOPN)},
+            "config": make_config(world, args.dist),
+            "e2e": leg_record("e2e", e2e_ms),
+            # the same job from PAGEABLE host memory (plain malloc: the reference's &[Vec<u8>]): staged through the
+            # library's pinned ring in 32 MiB chunks instead of being read in place
+            "e2e_pageable": leg_record("e2e_pageable", pg_ms),
             # same job, same API, input handed over in the library's pre-packed form (2-bit codes + `other`
             # bits in pinned host memory: nk_stream_push_packed).  The packing itself (nk_pack_bases, host
             # SIMD, all cores) is NOT in this timed region — its cost is reported beside it.
-            "e2e_prepacked": None if not steps_pk else {
-                "value": total_kmers / (pk_ms * 1e-3), "unit": "kmers/s", "ms_per_step": pk_ms / args.steps,
-                "h2d_bytes_per_step": int(phases_pk[-1]["h2d_bytes"]),
-                "d2h_bytes_per_step": int(phases_pk[-1]["d2h_bytes"] + 24 + 16 * TOPN),
-                "host_pack_ms_untimed": pack_ms, "host_pack_threads": os.cpu_count()},
+            "e2e_prepacked": leg_record("e2e_prepacked", pk_ms, {"host_pack_ms_untimed": pack_ms, "host_pack_threads": os.cpu_count()}),
             "gpu_launches": launches * args.steps,
-            "phases_ms": ph, "collective_ms": ar_ms,
+            "phases_ms": ph, "collective_ms": collective_ms,
+            # the exchange on its own (north star): measured by the kernels with %globaltimer, max over ranks.
+            #   wait_ms    waiting for the peers' "finished counting" flags and result packs (rank skew)
+            #   reduce_ms  the fused phase that reads this rank's neuron slice of every rank's counts over NVLink
+            #              (reduce-scatter) + LIF look-up + top-N histogram; at N=1 the same phase on local memory
+            #   merge_ms   merging the ranks' result packs
+            "exchange": {"wait_ms": wait_ms, "reduce_ms": reduce_ms, "merge_ms": merge_ms, "post_kernel_ms": post_ms,
+                         "count_ms_slowest_rank": count_ms_max,
+                         "bytes_read_from_peers_per_rank": int(phases[-1]["exch_bytes"])},
             "collective": ("none" if world == 1 else (
                 "none per job: counting-finished flags, count reduce-scatter and result-pack exchange are NVLink peer-memory "
-                "loads/stores inside the kernels" if peer else (
+                "loads/stores inside the kernels; collective_ms = flag/pack waits + the fused reduce phase + pack merge" if peer else (
                     "barrier + all-gather of result packs (NCCL); count reduce-scatter fused into the LIF "
                     "kernel over NVLink peer memory" if fused else "all-reduce of the u64 currents (NCCL)"))),
             "lif_path": int(phases[-1]["lif_path"]),
+            "strong_scaling": None if not strong else {
+                "value": KMERS * args.steps / (strong_ms * 1e-3), "unit": "kmers/s", "ms_per_step": strong_ms / args.steps,
+                "kmers_per_step": KMERS, "note": "the N=1 job (113 Mbase, 7 sequences) cut by window start into N ranges"},
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-            "result": {"total_spikes": total_spikes, "top1": list(top[0][:2]) if top else None},
+            "result": {"total_spikes": total_spikes, "top1": list(top[0][:2]) if top else None, "parity": parity},
         }
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def ncu_traffic():
+    """dram bytes (read + write) per launch of the count kernel from the committed ncu capture — only if the
+    capture was taken from THIS kernel source (sha256 of nk_count.cu + nk_device.cuh recorded beside it)"""
+    import hashlib
+    try:
+        with open(os.path.join(ROOT, "profiles", "count_kernel_traffic.json")) as f:
+            rec = json.load(f)
+        h = hashlib.sha256()
+        for name in ("nk_count.cu", "nk_device.cuh"):
+            with open(os.path.join(ROOT, "neurokmer_b200", "csrc", name), "rb") as f:
+                h.update(f.read())
+        if rec.get("source_sha256") != h.hexdigest():
+            return None, "profiles/count_kernel_traffic.json is from another build of the kernel"
+        return float(rec["dram_bytes_per_launch"]), rec.get("capture", "profiles/count_kernel_traffic.json")
+    except Exception:
+        return None, "no ncu capture committed for this kernel build"
 
 
 def select_workload(name: str):
@@ -533,6 +690,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--workload", default="config2", choices=["config2", "config5"])
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (large workloads)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the job's result (large workloads)")
     ap.add_argument("--dist", default="peer", choices=["peer", "fused", "allreduce"],
                     help="N > 1: peer = sharded pool, every exchange through NVLink peer memory inside the kernels (default); "
                          "fused = same kernels with an NCCL barrier + all-gather around them; allreduce = NCCL all-reduce of the currents")

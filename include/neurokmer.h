@@ -293,7 +293,8 @@ NK_API int nk_debug_set_fold_limit(nk_counter* h, uint64_t limit);
  *            cannot move off the ALU pipe);
  *   which 1: 32-bit integer ops/s of register-only SipRound chains (SipHash's own
  *            add:xor:rotate mix, 24 ops per round) — the integer-pipe ceiling of step 2;
- *   which 2: RED.ADD.U32 per second to uniformly random slots of THIS handle's pool
+ *   which 2: RED.ADD.U32 per second at the addresses real k-mer traffic produces (SipHash-1-3 of
+ *            consecutive words % pool_size, precomputed) into THIS handle's pool
  *            (the pool-update ceiling of step 3).  Needs an idle counter; leaves it unchanged. */
 NK_API int nk_calibrate(nk_counter* h, int which, double* out);
 

@@ -1948,6 +1948,14 @@ int nk_calibrate(nk_counter* h, int which, double* out) {
     NK_TRY(get_event(h, &a));
     NK_TRY(get_event(h, &b));
     double best = 0.0;
+    // which == 2: the addresses of real k-mer traffic (SipHash-1-3 of consecutive words % pool), precomputed
+    const unsigned long long n_idx = 64ull << 20;
+    unsigned int* d_idx = nullptr;
+    if (which == 2) {
+        NK_CUDA(cudaMalloc(&d_idx, n_idx * sizeof(unsigned int)));
+        cudaError_t e = nk::launch_hashed_idx(d_idx, n_idx, 0x5EEDull, h->fm, h->stream);
+        if (e != cudaSuccess) { cudaFree(d_idx); NK_CUDA(e); }
+    }
     for (int rep = 0; rep < 4; ++rep) {
         double work = 0.0;
         NK_CUDA(cudaEventRecord(a, h->stream));
@@ -1956,9 +1964,9 @@ int nk_calibrate(nk_counter* h, int which, double* out) {
             NK_CUDA(nk::launch_int_peak(which, h->tile_counter + 4, blocks, iters, h->stream));
             work = (double)blocks * 256.0 * iters * (double)nk::int_peak_ops_per_iter(which);
         } else {
-            const unsigned per_thread = 512;
-            NK_CUDA(nk::launch_red_peak(h->acc, h->fm, blocks, per_thread, h->stream));
-            work = (double)blocks * 256.0 * per_thread;
+            cudaError_t e = nk::launch_red_peak(h->acc, d_idx, n_idx, blocks, h->stream);
+            if (e != cudaSuccess) { cudaFree(d_idx); NK_CUDA(e); }
+            work = (double)n_idx;
         }
         NK_CUDA(cudaEventRecord(b, h->stream));
         NK_CUDA(cudaStreamSynchronize(h->stream));
@@ -1967,6 +1975,7 @@ int nk_calibrate(nk_counter* h, int which, double* out) {
     }
     if (which == 2) NK_CUDA(cudaMemsetAsync(h->acc, 0, h->cfg.pool_size * sizeof(unsigned int), h->stream));
     NK_CUDA(cudaStreamSynchronize(h->stream));
+    if (d_idx) cudaFree(d_idx);
     *out = best;
     return NK_OK;
 }

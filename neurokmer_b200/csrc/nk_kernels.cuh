@@ -285,7 +285,9 @@ cudaError_t launch_filter_set(unsigned int* filter, const unsigned long long* id
 // peak calibration (roofline denominators)
 cudaError_t launch_int_peak(int mode, unsigned int* out, int blocks, unsigned iters, cudaStream_t s);
 unsigned long long int_peak_ops_per_iter(int mode);
-cudaError_t launch_red_peak(unsigned int* acc, FastMod fm, int blocks, unsigned per_thread, cudaStream_t s);
+// idx[i] = SipHash-1-3(seed + i) % pool: the address stream of real k-mer traffic, for the RED ceiling
+cudaError_t launch_hashed_idx(unsigned int* idx, unsigned long long n, unsigned long long seed, FastMod fm, cudaStream_t s);
+cudaError_t launch_red_peak(unsigned int* acc, const unsigned int* idx, unsigned long long n, int blocks, cudaStream_t s);
 
 cudaError_t launch_mod_words(const unsigned long long* h, unsigned long long n, FastMod fm, unsigned long long* out,
                              int which, cudaStream_t s);

@@ -110,15 +110,32 @@ __global__ void __launch_bounds__(256) int_peak_kernel(unsigned int* out, unsign
     }
 }
 
-// RED.ADD.U32 to pseudo-random slots of `pool` (the pool-update limit): `per_thread` reductions per thread
-__global__ void __launch_bounds__(256) red_peak_kernel(unsigned int* acc, FastMod fm, unsigned per_thread) {
-    unsigned x = (blockIdx.x * 256u + threadIdx.x) * 2654435761u + 12345u;
-    const unsigned p = fm.p;
-    for (unsigned i = 0; i < per_thread; ++i) {
-        x = x * 1664525u + 1013904223u;
-        const unsigned idx = __umulhi(x, p);  // uniform in [0, p)
-        atomicAdd(acc + idx, 1u);
+// The pool-update limit: RED.ADD.U32 at the addresses real k-mer traffic produces — SipHash-1-3 of consecutive
+// words modulo the pool, precomputed into `idx` so that the timed kernel does nothing but stream 4-byte indices
+// (evict-first loads) and fire reductions.  (Round 1 generated addresses with an LCG inside the kernel; at
+// 64 K neurons the count kernel itself beat that "ceiling", i.e. the address stream, not the L2, was the limit.)
+template <bool POW2>
+__global__ void hashed_idx_kernel(unsigned int* __restrict__ idx, unsigned long long n, unsigned long long seed, FastMod fm, RotMul rm) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n; i += stride) {
+        const unsigned long long w = seed + i;
+        const U64 h = siphash13_dev((unsigned)w, (unsigned)(w >> 32), rm);
+        idx[i] = fastmod_dev<POW2>(h, fm);
     }
+}
+
+__global__ void __launch_bounds__(256) red_peak_kernel(unsigned int* acc, const unsigned int* __restrict__ idx, unsigned long long n) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n; i += 4 * stride) {
+        const unsigned a = __ldcs(idx + i), b = __ldcs(idx + i + stride), c = __ldcs(idx + i + 2 * stride),
+                       d = __ldcs(idx + i + 3 * stride);
+        atomicAdd(acc + a, 1u);
+        atomicAdd(acc + b, 1u);
+        atomicAdd(acc + c, 1u);
+        atomicAdd(acc + d, 1u);
+    }
+    for (; i < n; i += stride) atomicAdd(acc + __ldcs(idx + i), 1u);
 }
 
 }  // namespace
@@ -131,8 +148,14 @@ cudaError_t launch_int_peak(int mode, unsigned int* out, int blocks, unsigned it
 // 32-bit integer ops one thread executes per `iters` unit in launch_int_peak
 unsigned long long int_peak_ops_per_iter(int mode) { return mode == 0 ? 8ull * 8 * 2 : 2ull * 4 * 24; }
 
-cudaError_t launch_red_peak(unsigned int* acc, FastMod fm, int blocks, unsigned per_thread, cudaStream_t s) {
-    red_peak_kernel<<<blocks, 256, 0, s>>>(acc, fm, per_thread);
+cudaError_t launch_hashed_idx(unsigned int* idx, unsigned long long n, unsigned long long seed, FastMod fm, cudaStream_t s) {
+    if (fm.is_pow2) hashed_idx_kernel<true><<<148 * 8, 256, 0, s>>>(idx, n, seed, fm, make_rotmul());
+    else hashed_idx_kernel<false><<<148 * 8, 256, 0, s>>>(idx, n, seed, fm, make_rotmul());
+    return cudaGetLastError();
+}
+
+cudaError_t launch_red_peak(unsigned int* acc, const unsigned int* idx, unsigned long long n, int blocks, cudaStream_t s) {
+    red_peak_kernel<<<blocks, 256, 0, s>>>(acc, idx, n);
     return cudaGetLastError();
 }
 

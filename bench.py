@@ -21,6 +21,9 @@ followed by the top-20 read-out.  One "step" = one whole job on a freshly reset 
                  sample of the same workload — a reported baseline, not the target
 
   e2e_pageable : e2e with the bases in plain pageable memory (what the reference's `&[Vec<u8>]` is)
+  e2e_file     : (N=1) the reference's real entry point — a FASTA file (115 MB, 60-column lines, in the page cache)
+                 -> nk_process_file (raw bytes staged by a pool of host threads, records parsed on the device)
+                 -> top-20, wall clock
   result.parity: after the timed legs rank 0 runs the CPU oracle over the WHOLE job (all ranks' shards) and
                  compares currents (sha256 of the u64 array), spike counts, total spikes and the top-20
 
@@ -92,6 +95,22 @@ def shard_of(offs: np.ndarray, lo: int, hi: int):
         if p1 > p0:
             out.append(p1 - lo)
     return np.array(out, np.uint64)
+
+
+def write_fasta(path: str, bases: np.ndarray, offsets: np.ndarray, width: int = 60) -> int:
+    """the workload as the file the reference would be given: one record per sequence, 60-column lines"""
+    with open(path, "wb") as f:
+        for i in range(len(offsets) - 1):
+            s = bases[int(offsets[i]):int(offsets[i + 1])]
+            f.write(b">seq%d synthetic workload of bench.py\n" % i)
+            n = s.size // width * width
+            body = np.empty((n // width, width + 1), np.uint8)
+            body[:, :width] = s[:n].reshape(-1, width)
+            body[:, width] = 10
+            f.write(body.tobytes())
+            if s.size > n:
+                f.write(s[n:].tobytes() + b"\n")
+    return os.path.getsize(path)
 
 
 def peaks():
@@ -446,12 +465,33 @@ def gpu_arm(args):
     my_spikes = c.spike_counts()[slice_lo:slice_lo + slice_len].copy()
 
     legs = {}
+    file_path, file_bytes = None, 0
+    if not args.no_e2e and world == 1:
+        import tempfile
+        tmpdir = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else tempfile.gettempdir()
+        file_path = os.path.join(tmpdir, f"nk_bench_{os.getpid()}.fa")
+        file_bytes = write_fasta(file_path, pinned.array, offsets)
+
+    def job_e2e_file():
+        c.reset()
+        c.process_file_streaming(file_path)
+        return c.top_abundant_neurons(TOPN)
+
     if not args.no_e2e:
-        for name, job in (("e2e", job_e2e), ("e2e_pageable", job_e2e_pageable), ("e2e_prepacked", job_e2e_packed)):
+        for name, job in (("e2e", job_e2e), ("e2e_pageable", job_e2e_pageable), ("e2e_prepacked", job_e2e_packed),
+                          ("e2e_file", job_e2e_file)):
+            if name == "e2e_file" and file_path is None:
+                continue
             timed(job, 2)
             st, ph, tp, _ = timed(job, args.steps)
             assert tp == top, f"{name} and resident legs disagree"
             legs[name] = (st, ph)
+
+    if file_path:
+        try:
+            os.unlink(file_path)
+        except OSError:
+            pass
 
     # ---- strong scaling (N > 1): the 113 Mbase job itself, cut N ways ------------------------------------------
     strong = None
@@ -481,6 +521,7 @@ def gpu_arm(args):
         return float(sum(x[1] for x in legs[name][0])) if name in legs else float("nan")
 
     ph_mean = lambda key, src=None: float(np.mean([p[key] for p in (src or phases)]))
+    file_ms = leg_ms("e2e_file")
     vals = [float(sum(x[0] for x in steps_res)), leg_ms("e2e"), leg_ms("e2e_pageable"), leg_ms("e2e_prepacked"),
             float(sum(x[0] for x in strong[0])) if strong else float("nan"),
             ph_mean("count_ms"), ph_mean("exch_wait_ms"), ph_mean("exch_reduce_ms"), ph_mean("merge_ms"), ph_mean("post_ms")]
@@ -621,6 +662,9 @@ def gpu_arm(args):
             # bits in pinned host memory: nk_stream_push_packed).  The packing itself (nk_pack_bases, host
             # SIMD, all cores) is NOT in this timed region — its cost is reported beside it.
             "e2e_prepacked": leg_record("e2e_prepacked", pk_ms, {"host_pack_ms_untimed": pack_ms, "host_pack_threads": os.cpu_count()}),
+            # the reference's own entry point: a FASTA file (page cache / tmpfs) -> nk_process_file -> top-20, wall clock
+            "e2e_file": leg_record("e2e_file", file_ms, {"file_bytes": file_bytes, "file": "FASTA, 7 records, 60-column lines",
+                                                         "ratio_to_e2e": (file_ms / e2e_ms) if e2e_ms == e2e_ms and e2e_ms > 0 else None}),
             "gpu_launches": launches * args.steps,
             "phases_ms": ph, "collective_ms": collective_ms,
             # the exchange on its own (north star): measured by the kernels with %globaltimer, max over ranks.

@@ -194,7 +194,10 @@ NK_API int nk_stream_push_packed(nk_counter* h, const uint32_t* codes, const uin
 
 /* Whole-file drivers: main.rs:170-177.  streaming != 0 → process_file_streaming
  * (:277), else stream_sequences().collect() + process_parallel (main.rs:175-176).
- * FASTA/FASTQ record rules follow src/utils.rs:9-24. */
+ * FASTA/FASTQ record rules follow src/utils.rs:9-24.
+ * Plain regular files that fit the device are copied there raw by a pool of host threads (pread -> pinned
+ * slots -> async H2D) and split into records ON THE DEVICE (no host pass over the bytes); compressed input,
+ * pipes and larger files go through the host reader (NK_GPU_PARSE=0 forces it).  Same results either way. */
 NK_API int nk_process_file(nk_counter* h, const char* path, int streaming);
 
 /* process_sequence — src/spiking_hash.rs:203-273 (per-sequence API: one LIF tick
@@ -264,6 +267,9 @@ NK_API int nk_debug_pack_body(const uint8_t* bases, uint64_t nbases, uint32_t* c
  * bzip2, xz, zstd input): number of records, total sequence bytes and FNV-1a-64 over every record's
  * sequence bytes followed by one 0xFF byte.  Needs no device. */
 NK_API int nk_debug_fastx_digest(const char* path, uint64_t* nrecords, uint64_t* nbases, uint64_t* fnv1a);
+/* The same digest of what the DEVICE-side record parser (nk_parse.cu: the path nk_process_file takes for plain
+ * regular FASTA / FASTQ files) yields; NK_ERR_UNSUPPORTED where that path does not apply (compressed input, ...). */
+NK_API int nk_debug_parse_file(nk_counter* h, const char* path, uint64_t* nrecords, uint64_t* nbases, uint64_t* fnv1a);
 /* the same digest (plain FASTA only) through the parallel ingest's window planner + window parser, with windows
  * of `window` bytes (>= 64), run serially: checks the code the multi-threaded file path is made of */
 NK_API int nk_debug_fasta_windows_digest(const char* path, uint64_t window, uint64_t* nrecords, uint64_t* nbases,

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libneurokmer.so")
 CLI = os.path.join(HERE, "neurokmer")
-SOURCES = ["nk_count.cu", "nk_lif.cu", "nk_topn.cu", "nk_misc.cu", "nk_post.cu", "nk_exact.cu", "nk_api.cu", "nk_multi.cu", "nk_fastx.cpp", "nk_pack.cpp", "nk_decomp.cpp"]
+SOURCES = ["nk_count.cu", "nk_lif.cu", "nk_topn.cu", "nk_misc.cu", "nk_post.cu", "nk_exact.cu", "nk_api.cu", "nk_multi.cu", "nk_parse.cu", "nk_ingest.cu", "nk_fastx.cpp", "nk_pack.cpp", "nk_decomp.cpp"]
 HEADERS = ["nk_device.cuh", "nk_kernels.cuh", "nk_host.h", "nk_internal.h", os.path.join("..", "..", "include", "neurokmer.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

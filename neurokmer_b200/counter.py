@@ -315,6 +315,12 @@ class SpikingKmerCounter:
     def debug_set_lif_path(self, mode: int) -> None:
         check(self._L.nk_debug_set_lif_path(self._h, mode))
 
+    def debug_parse_file(self, path: str) -> Tuple[int, int, int]:
+        """(records, bases, FNV-1a digest) of the device-side record parser on a plain FASTA / FASTQ file"""
+        nr, nb, hs = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        check(self._L.nk_debug_parse_file(self._h, str(path).encode(), C.byref(nr), C.byref(nb), C.byref(hs)))
+        return nr.value, nb.value, hs.value
+
     def debug_set_fold_limit(self, limit: int) -> None:
         check(self._L.nk_debug_set_fold_limit(self._h, limit))
 

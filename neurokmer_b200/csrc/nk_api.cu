@@ -186,7 +186,7 @@ int prelaunch_table(nk_counter* h);
 
 int count_chunk(nk_counter* h, DevBuf& b, const unsigned long long* d_offsets, unsigned long long seq_lo,
                 unsigned long long seq_hi, unsigned long long origin, unsigned long long nstarts,
-                unsigned long long max_windows, PhaseEvents* pe, bool packed = false) {
+                unsigned long long max_windows, PhaseEvents* pe, bool packed) {
     if (nstarts == 0) return NK_OK;
     if (h->acc_kmers + max_windows > h->fold_limit) NK_TRY(h->dist_world > 0 && h->streaming ? spill_now(h) : fold_now(h));
     cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
@@ -286,11 +286,17 @@ int count_host_batch(nk_counter* h, const uint8_t* bases, const uint64_t* offset
     // staged pipeline, which pageable memory always takes.
     unsigned long long zc_body = 0;
     const char* zc_env = getenv("NK_ZEROCOPY");
+    cudaPointerAttributes at{};
+    const bool at_ok = cudaPointerGetAttributes(&at, bases) == cudaSuccess;
+    if (!at_ok) cudaGetLastError();
+    // plain malloc / mmap memory (what the reference's &[Vec<u8>] is), and enough of it to be worth a thread pool
+    const char* sp_env = getenv("NK_STAGE_POOL");
+    const bool pageable_pool = wait_copies && at_ok && at.type == cudaMemoryTypeUnregistered && nbytes >= (8ull << 20) &&
+                               (!sp_env || atoi(sp_env) != 0);
     // (the file driver double-buffers its own pinned batches and must not block on the kernels: wait_copies == false)
     if (wait_copies && (!zc_env || atoi(zc_env) != 0) && nbytes >= 4 * (unsigned long long)nk::COUNT_TILE &&
         ((uintptr_t)bases & 15) == 0) {
-        cudaPointerAttributes at{};
-        if (cudaPointerGetAttributes(&at, bases) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
+        if (at_ok && at.type == cudaMemoryTypeHost && at.devicePointer) {
             zc_body = nbytes;  // the whole batch: the last tile's copy is clamped to the end of the array
             const unsigned long long slice = (0xFFFFFFFFull / nk::COUNT_TILE - 1) * nk::COUNT_TILE;
             NK_TRY(ensure_bitmap_only(h->zc, std::min(zc_body, slice)));
@@ -301,7 +307,7 @@ int count_host_batch(nk_counter* h, const uint8_t* bases, const uint64_t* offset
                 DevBuf view = h->zc;
                 view.bases = static_cast<unsigned char*>(at.devicePointer) + c0;
                 view.bases_bytes = (nbytes - c0 + 15) / 16 * 16;
-                NK_TRY(count_chunk(h, view, d_offsets, 0, nseq, c0, n, n, pe));
+                NK_TRY(count_chunk(h, view, d_offsets, 0, nseq, c0, n, n, pe, false));
             }
         } else {
             cudaGetLastError();
@@ -318,8 +324,15 @@ int count_host_batch(nk_counter* h, const uint8_t* bases, const uint64_t* offset
         h->cur_buf ^= 1;
         const bool had = b.compute_done != nullptr;
         NK_TRY(ensure_devbuf(b, std::min(kChunkBytes, nbytes)));
-        if (had) NK_CUDA(cudaStreamWaitEvent(h->copy_stream, b.compute_done, 0));
-        NK_CUDA(cudaMemcpyAsync(b.bases, bases + c0, copy_len, cudaMemcpyHostToDevice, h->copy_stream));
+        if (pageable_pool) {
+            // pageable memory: the pool of host threads copies 2 MiB pieces into its pinned slots and issues their H2D
+            // copies on its own streams (one cudaMemcpy from pageable memory runs at ~11 GB/s); returns once the source
+            // bytes of this chunk have been consumed, with the copies in flight behind the previous user of `b`
+            NK_TRY(stage_to_device(h, bases + c0, -1, 0, copy_len, b.bases, had ? b.compute_done : nullptr, h->copy_stream));
+        } else {
+            if (had) NK_CUDA(cudaStreamWaitEvent(h->copy_stream, b.compute_done, 0));
+            NK_CUDA(cudaMemcpyAsync(b.bases, bases + c0, copy_len, cudaMemcpyHostToDevice, h->copy_stream));
+        }
         NK_CUDA(cudaEventRecord(b.copy_done, h->copy_stream));
         NK_CUDA(cudaStreamWaitEvent(h->stream, b.copy_done, 0));
         // sequences that overlap [c0, c1): first with end > c0 ... first with start >= c1
@@ -327,7 +340,7 @@ int count_host_batch(nk_counter* h, const uint8_t* bases, const uint64_t* offset
         const unsigned long long seq_lo = (unsigned long long)(first - (offsets + 1));
         const uint64_t* last = std::lower_bound(offsets, offsets + nseq, (uint64_t)c1);
         const unsigned long long seq_hi = (unsigned long long)(last - offsets);
-        NK_TRY(count_chunk(h, b, d_offsets, seq_lo, seq_hi, c0, c1 - c0, c1 - c0, pe));
+        NK_TRY(count_chunk(h, b, d_offsets, seq_lo, seq_hi, c0, c1 - c0, c1 - c0, pe, false));
         NK_CUDA(cudaEventRecord(b.compute_done, h->stream));
     }
     NK_CUDA(cudaEventRecord(h->offsets_done[ob], h->stream));
@@ -830,7 +843,7 @@ int free_devbuf(DevBuf& b) {
     return NK_OK;
 }
 
-int fold_and_simulate(nk_counter* h, bool skip_zero, PhaseEvents& pe, bool with_topn = true) {
+int fold_and_simulate(nk_counter* h, bool skip_zero, PhaseEvents& pe, bool with_topn) {
     NK_TRY(get_event(h, &pe.fold0));
     NK_CUDA(cudaEventRecord(pe.fold0, h->stream));
     NK_TRY(unspill(h));
@@ -1143,7 +1156,66 @@ int count_fastq_parallel(nk_counter* h, const char* path, PhaseEvents& pe, std::
 
 // ingest_only: the second read of a file by the uniques pass — the batches are routed to
 // uniques_host_batch (count_host_batch checks h->uniques_open), nothing is simulated or read back
+// Plain FASTA / FASTQ files: raw bytes -> device (pool of host threads, pread + pinned slots + async H2D), records
+// parsed THERE (nk_parse.cu), then the ordinary count kernels over the device-resident result.  *handled = false:
+// the host reader below takes the file (compressed input, pipes, files larger than the device can hold).
+static int process_file_device(nk_counter* h, const char* path, bool streaming, std::string* err, bool ingest_only, bool* handled) {
+    *handled = false;
+    cudaError_t ce = cudaSetDevice(h->cfg.device);
+    if (ce != cudaSuccess) { *err = std::string("cudaSetDevice: ") + cudaGetErrorString(ce); return NK_ERR_CUDA; }
+    const unsigned long long slice = (0xFFFFFFFFull / nk::COUNT_TILE - 1) * nk::COUNT_TILE;
+    auto failed = [&](int rc) { *err = g_err; return rc; };
+    if (ingest_only) {
+        // the uniques pass: the parsed file of the counting pass is normally still resident
+        struct stat st;
+        bool same = h->fp_valid && h->fp_path == path && ::stat(path, &st) == 0 && (unsigned long long)st.st_size == h->fp_size &&
+                    (unsigned long long)st.st_mtim.tv_sec * 1000000000ull + (unsigned long long)st.st_mtim.tv_nsec == h->fp_mtime_ns;
+        unsigned long long nb = h->fp_nbases, nr = h->fp_nrec;
+        if (!same) {
+            bool fq = false;
+            int rc = parse_file_on_device(h, path, handled, &fq, &nb, &nr, err);
+            if (rc != NK_OK || !*handled) return rc;
+        }
+        *handled = true;
+        for (unsigned long long c0 = 0; c0 < nb && nr > 0; c0 += slice) {
+            DevBuf view = h->staged;
+            view.bases = h->staged.bases + c0;
+            int rc = uniques_chunk(h, view, h->staged_offsets, 0, nr, c0, std::min(slice, nb - c0), false);
+            if (rc != NK_OK) return failed(rc);
+        }
+        return NK_OK;
+    }
+    begin_call(h);
+    PhaseEvents pe;
+    int rc;
+    if ((rc = get_event(h, &pe.begin)) != NK_OK) return failed(rc);
+    cudaEventRecord(pe.begin, h->stream);
+    bool fq = false;
+    unsigned long long nb = 0, nr = 0;
+    rc = parse_file_on_device(h, path, handled, &fq, &nb, &nr, err);
+    if (rc != NK_OK || !*handled) return rc;
+    cudaMemsetAsync(h->scalars + 2, 0, sizeof(unsigned long long), h->stream);
+    h->currents_valid_overwrite = true;
+    for (unsigned long long c0 = 0; c0 < nb && nr > 0; c0 += slice) {
+        const unsigned long long n = std::min(slice, nb - c0);
+        DevBuf view = h->staged;
+        view.bases = h->staged.bases + c0;
+        if ((rc = count_chunk(h, view, h->staged_offsets, 0, nr, c0, n, n, &pe, false)) != NK_OK) return failed(rc);
+    }
+    if ((rc = fold_and_simulate(h, /*skip_zero=*/!streaming, pe, true)) != NK_OK) return failed(rc);
+    if ((rc = get_event(h, &pe.end)) != NK_OK) return failed(rc);
+    cudaEventRecord(pe.end, h->stream);
+    if ((rc = finish_call(h, true, &pe)) != NK_OK) return failed(rc);
+    if ((rc = resolve(h)) != NK_OK) return failed(rc);
+    return NK_OK;
+}
+
 int process_file(nk_counter* h, const char* path, bool streaming, std::string* err, bool ingest_only) {
+    if (!is_group(h)) {
+        bool handled = false;
+        const int rc = process_file_device(h, path, streaming, err, ingest_only, &handled);
+        if (rc != NK_OK || handled) return rc;
+    }
     FastxReader rd;
     if (rd.open(path, err) != 0) return NK_ERR_IO;
     auto cuda_fail = [&](cudaError_t e, const char* what) {
@@ -1272,7 +1344,7 @@ int process_file(nk_counter* h, const char* path, bool streaming, std::string* e
             if ((rc = nk_total_spikes(h, &spikes)) != NK_OK) *err = g_err;  // observes the result: surfaces device errors here
             break;
         }
-        if ((rc = fold_and_simulate(h, /*skip_zero=*/!streaming, pe)) != NK_OK) { *err = g_err; break; }
+        if ((rc = fold_and_simulate(h, /*skip_zero=*/!streaming, pe, true)) != NK_OK) { *err = g_err; break; }
         if (get_event(h, &pe.end) != NK_OK) { *err = g_err; rc = NK_ERR_CUDA; break; }
         cudaEventRecord(pe.end, h->stream);
         if ((rc = finish_call(h, true, &pe)) != NK_OK) { *err = g_err; break; }
@@ -1428,6 +1500,7 @@ int nk_destroy(nk_counter* h) {
     cudaFree(h->d_merged);
     nk::exact_free(h->xt);
     cudaFree(h->d_top_uniques);
+    ingest_free(h);
     free_devbuf(h->buf[0]); free_devbuf(h->buf[1]); free_devbuf(h->staged); free_devbuf(h->zc);
     for (int i = 0; i < 2; ++i) { cudaFree(h->d_offsets2[i]); if (h->offsets_done[i]) cudaEventDestroy(h->offsets_done[i]); }
     cudaFree(h->staged_offsets);
@@ -1462,7 +1535,7 @@ int nk_process_batch(nk_counter* h, const uint8_t* bases, const uint64_t* offset
     NK_CUDA(cudaMemsetAsync(h->scalars + 2, 0, sizeof(unsigned long long), h->stream));
     h->currents_valid_overwrite = true;  // totals of THIS call overwrite the stored currents (:174-176)
     NK_TRY(count_host_batch(h, bases, offsets, nseq, &pe, kPushSync));
-    NK_TRY(fold_and_simulate(h, /*skip_zero=*/true, pe));
+    NK_TRY(fold_and_simulate(h, /*skip_zero=*/true, pe, true));
     NK_TRY(get_event(h, &pe.end));
     NK_CUDA(cudaEventRecord(pe.end, h->stream));
     NK_TRY(finish_call(h, true, &pe));
@@ -1532,7 +1605,7 @@ int nk_process_batch_packed(nk_counter* h, const uint32_t* codes, const uint32_t
     NK_CUDA(cudaMemsetAsync(h->scalars + 2, 0, sizeof(unsigned long long), h->stream));
     h->currents_valid_overwrite = true;
     NK_TRY(count_host_batch_packed(h, codes, other, offsets, nseq, &pe, kPushSync));
-    NK_TRY(fold_and_simulate(h, /*skip_zero=*/true, pe));
+    NK_TRY(fold_and_simulate(h, /*skip_zero=*/true, pe, true));
     NK_TRY(get_event(h, &pe.end));
     NK_CUDA(cudaEventRecord(pe.end, h->stream));
     NK_TRY(finish_call(h, true, &pe));
@@ -1572,7 +1645,7 @@ int nk_stream_finish(nk_counter* h) {
     if (!h->streaming) return fail(NK_ERR_STATE, "nk_stream_finish without nk_stream_begin");
     NK_CUDA(cudaSetDevice(h->cfg.device));
     PhaseEvents pe = h->stream_pe;
-    NK_TRY(fold_and_simulate(h, /*skip_zero=*/false, pe));
+    NK_TRY(fold_and_simulate(h, /*skip_zero=*/false, pe, true));
     NK_TRY(finish_call(h, true, &pe));
     h->streaming = false;
     return NK_OK;
@@ -1799,6 +1872,7 @@ static int debug_kmers_any(nk_counter* h, const uint8_t* seq, const uint32_t* co
     NK_TRY(resolve(h));
     const uint64_t n = len - h->cfg.k + 1;
     NK_CUDA(cudaStreamSynchronize(h->stream));
+    h->fp_valid = false;  // the staged buffers are about to be reused
     if (packed) NK_TRY(ensure_devbuf_packed(h->staged, len, true));
     else NK_TRY(ensure_devbuf(h->staged, len));
     NK_TRY(ensure_offsets(&h->staged_offsets, &h->staged_offsets_cap, 2));
@@ -2231,6 +2305,7 @@ int nk_stage_reserve(nk_counter* h, uint64_t nbytes, uint64_t nseq, void** dev_b
     NK_CUDA(cudaSetDevice(h->cfg.device));
     NK_TRY(resolve(h));
     NK_CUDA(cudaStreamSynchronize(h->stream));
+    h->fp_valid = false;
     NK_TRY(ensure_devbuf(h->staged, nbytes));
     NK_TRY(ensure_offsets(&h->staged_offsets, &h->staged_offsets_cap, nseq + 1));
     if (dev_bases) *dev_bases = h->staged.bases;
@@ -2263,10 +2338,10 @@ int nk_process_staged(nk_counter* h, uint64_t nbytes, uint64_t nseq, int mode) {
         const unsigned long long n = std::min(slice, nbytes - c0);
         DevBuf view = h->staged;
         view.bases = h->staged.bases + c0;
-        NK_TRY(count_chunk(h, view, h->staged_offsets, 0, nseq, c0, n, n, &pe));
+        NK_TRY(count_chunk(h, view, h->staged_offsets, 0, nseq, c0, n, n, &pe, false));
     }
     if (mode == 0) {
-        NK_TRY(fold_and_simulate(h, /*skip_zero=*/true, pe));
+        NK_TRY(fold_and_simulate(h, /*skip_zero=*/true, pe, true));
         NK_TRY(get_event(h, &pe.end));
         NK_CUDA(cudaEventRecord(pe.end, h->stream));
         NK_TRY(finish_call(h, true, &pe));
@@ -2286,6 +2361,7 @@ int nk_stage_reserve_packed(nk_counter* h, uint64_t nbases, uint64_t nseq, void*
     NK_CUDA(cudaSetDevice(h->cfg.device));
     NK_TRY(resolve(h));
     NK_CUDA(cudaStreamSynchronize(h->stream));
+    h->fp_valid = false;
     NK_TRY(ensure_devbuf_packed(h->staged, nbases, true));
     NK_TRY(ensure_offsets(&h->staged_offsets, &h->staged_offsets_cap, nseq + 1));
     if (dev_codes) *dev_codes = h->staged.codes;
@@ -2322,7 +2398,7 @@ int nk_process_staged_packed(nk_counter* h, uint64_t nbases, uint64_t nseq, int 
         NK_TRY(count_chunk(h, view, h->staged_offsets, 0, nseq, c0, n, n, &pe, true));
     }
     if (mode == 0) {
-        NK_TRY(fold_and_simulate(h, /*skip_zero=*/true, pe));
+        NK_TRY(fold_and_simulate(h, /*skip_zero=*/true, pe, true));
         NK_TRY(get_event(h, &pe.end));
         NK_CUDA(cudaEventRecord(pe.end, h->stream));
         NK_TRY(finish_call(h, true, &pe));

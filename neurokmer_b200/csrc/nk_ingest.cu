@@ -1,0 +1,396 @@
+// nk_ingest.cu — getting bytes that sit in PAGEABLE host memory (a plain malloc'ed batch, the page cache
+// behind a file) onto the device at link speed, and parsing FASTA / FASTQ there.
+//
+// Replaces the reference's producer thread + unbounded channels (src/spiking_hash.rs:285-303, 405-422) and
+// needletail's host parser (src/utils.rs:9-24).  A single cudaMemcpy from pageable memory runs at ~11 GB/s
+// (the driver stages it on one thread); here a pool of host threads copies 2 MiB pieces into its own pinned
+// slots (memcpy, or pread straight from the file) and each thread issues the H2D copy of its piece on its own
+// stream — page-cache reads, the staging copies and PCIe overlap.  The pool's threads are bound to the CPUs
+// that are local to the GPU (sysfs local_cpulist) and allocate their pinned slots themselves, so the staging
+// memory sits on the GPU's NUMA node.
+#include <fcntl.h>
+#include <sched.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <cstring>
+#include <mutex>
+#include <thread>
+
+#include "nk_internal.h"
+
+using namespace nkd;
+
+namespace nkd {
+
+namespace {
+
+constexpr size_t kPiece = 2u << 20;
+
+// CPUs local to the device's PCIe root ("0-15,32-47" style list from sysfs); empty if unknown
+std::vector<int> local_cpus(int device) {
+    std::vector<int> cpus;
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) { cudaGetLastError(); return cpus; }
+    for (char* p = bus; *p; ++p) *p = (char)tolower(*p);
+    const std::string path = std::string("/sys/bus/pci/devices/") + bus + "/local_cpulist";
+    FILE* f = fopen(path.c_str(), "r");
+    if (!f) return cpus;
+    char line[4096];
+    if (fgets(line, sizeof line, f)) {
+        for (char* p = line; *p && *p != '\n';) {
+            char* e = nullptr;
+            const long a = strtol(p, &e, 10);
+            if (e == p) break;
+            long b = a;
+            p = e;
+            if (*p == '-') { b = strtol(p + 1, &e, 10); p = e; }
+            for (long c = a; c <= b && cpus.size() < 4096; ++c) cpus.push_back((int)c);
+            if (*p == ',') ++p;
+        }
+    }
+    fclose(f);
+    return cpus;
+}
+
+}  // namespace
+
+class StagePool {
+public:
+    StagePool(int device, unsigned nthreads) : device_(device) {
+        const std::vector<int> cpus = getenv("NK_STAGE_NO_AFFINITY") ? std::vector<int>() : local_cpus(device);
+        workers_.resize(nthreads);
+        for (unsigned t = 0; t < nthreads; ++t) {
+            workers_[t].th = std::thread([this, t, cpus] { run(t, cpus); });
+        }
+        // wait until every worker has its stream and slots (or failed)
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_done_.wait(lk, [&] { return ready_ == workers_.size(); });
+    }
+    ~StagePool() {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            quit_ = true;
+            ++gen_;
+        }
+        cv_job_.notify_all();
+        for (auto& w : workers_) w.th.join();
+    }
+    bool ok() const { return !init_failed_; }
+
+    int copy(const uint8_t* src, int fd, uint64_t off, uint64_t n, unsigned char* dst, cudaEvent_t after, cudaStream_t then) {
+        if (n == 0) return NK_OK;
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            job_ = Job{src, fd, off, n, dst, after};
+            next_.store(0);
+            npieces_ = (n + kPiece - 1) / kPiece;
+            finished_ = 0;
+            failed_ = false;
+            ++gen_;
+        }
+        cv_job_.notify_all();
+        {
+            std::unique_lock<std::mutex> lk(mu_);
+            cv_done_.wait(lk, [&] { return finished_ == workers_.size(); });
+        }
+        if (failed_) return fail(NK_ERR_IO, "staging copy failed: %s", err_.c_str());
+        for (auto& w : workers_) {
+            if (!w.used) continue;
+            cudaError_t e = cudaStreamWaitEvent(then, w.done, 0);
+            if (e != cudaSuccess) return fail(NK_ERR_CUDA, "cudaStreamWaitEvent: %s", cudaGetErrorString(e));
+        }
+        return NK_OK;
+    }
+
+private:
+    struct Job {
+        const uint8_t* src; int fd; uint64_t off, n; unsigned char* dst; cudaEvent_t after;
+    };
+    struct Worker {
+        std::thread th;
+        cudaStream_t stream = nullptr;
+        uint8_t* slot[2] = {nullptr, nullptr};
+        cudaEvent_t ev[2] = {nullptr, nullptr};
+        bool inflight[2] = {false, false};
+        cudaEvent_t done = nullptr;
+        bool used = false;
+    };
+
+    void run(unsigned t, const std::vector<int>& cpus) {
+        Worker& w = workers_[t];
+        if (!cpus.empty()) {
+            cpu_set_t set;
+            CPU_ZERO(&set);
+            for (int c : cpus) if (c < CPU_SETSIZE) CPU_SET(c, &set);
+            sched_setaffinity(0, sizeof set, &set);  // best effort
+        }
+        bool good = cudaSetDevice(device_) == cudaSuccess &&
+                    cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking) == cudaSuccess &&
+                    cudaEventCreateWithFlags(&w.done, cudaEventDisableTiming) == cudaSuccess;
+        for (int i = 0; i < 2 && good; ++i) {
+            good = cudaMallocHost((void**)&w.slot[i], kPiece) == cudaSuccess &&
+                   cudaEventCreateWithFlags(&w.ev[i], cudaEventDisableTiming) == cudaSuccess;
+            if (good) memset(w.slot[i], 0, kPiece);  // first touch on this (GPU-local) CPU
+        }
+        unsigned long long seen = 0;
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            if (!good) init_failed_ = true;
+            ++ready_;
+        }
+        cv_done_.notify_all();
+        for (;;) {
+            Job job;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_job_.wait(lk, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (quit_) break;
+                job = job_;
+            }
+            w.used = false;
+            bool bad = !good;
+            std::string why = "worker initialisation failed";
+            if (!bad && job.after && cudaStreamWaitEvent(w.stream, job.after, 0) != cudaSuccess) { bad = true; why = "cudaStreamWaitEvent"; }
+            int k = 0;
+            while (!bad) {
+                const uint64_t i = next_.fetch_add(1);
+                if (i >= npieces_) break;
+                const uint64_t o = i * kPiece, len = std::min<uint64_t>(kPiece, job.n - o);
+                const int s = k & 1;
+                ++k;
+                if (w.inflight[s]) { cudaEventSynchronize(w.ev[s]); w.inflight[s] = false; }
+                if (job.fd >= 0) {
+                    uint64_t got = 0;
+                    while (got < len) {
+                        const ssize_t r = pread(job.fd, w.slot[s] + got, len - got, (off_t)(job.off + o + got));
+                        if (r < 0 && errno == EINTR) continue;
+                        if (r <= 0) { bad = true; why = r == 0 ? "unexpected end of file" : strerror(errno); break; }
+                        got += (uint64_t)r;
+                    }
+                    if (bad) break;
+                } else {
+                    memcpy(w.slot[s], job.src + o, len);
+                }
+                if (cudaMemcpyAsync(job.dst + o, w.slot[s], len, cudaMemcpyHostToDevice, w.stream) != cudaSuccess ||
+                    cudaEventRecord(w.ev[s], w.stream) != cudaSuccess) { bad = true; why = "cudaMemcpyAsync"; break; }
+                w.inflight[s] = true;
+                w.used = true;
+            }
+            if (w.used) cudaEventRecord(w.done, w.stream);
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                if (bad) { failed_ = true; err_ = why; }
+                ++finished_;
+            }
+            cv_done_.notify_all();
+        }
+        if (w.stream) cudaStreamSynchronize(w.stream);
+        for (int i = 0; i < 2; ++i) {
+            if (w.slot[i]) cudaFreeHost(w.slot[i]);
+            if (w.ev[i]) cudaEventDestroy(w.ev[i]);
+        }
+        if (w.done) cudaEventDestroy(w.done);
+        if (w.stream) cudaStreamDestroy(w.stream);
+    }
+
+    int device_;
+    std::vector<Worker> workers_;
+    std::mutex mu_;
+    std::condition_variable cv_job_, cv_done_;
+    unsigned long long gen_ = 0;
+    bool quit_ = false, failed_ = false, init_failed_ = false;
+    size_t ready_ = 0, finished_ = 0;
+    Job job_{};
+    std::atomic<uint64_t> next_{0};
+    uint64_t npieces_ = 0;
+    std::string err_;
+};
+
+static StagePool* pool_of(nk_counter* h) {
+    if (!h->stage_pool) {
+        unsigned n = std::thread::hardware_concurrency();
+        if (const char* e = getenv("NK_STAGE_THREADS")) n = (unsigned)atoi(e);
+        if (n > 12) n = 12;
+        if (n < 1) n = 1;
+        StagePool* p = new StagePool(h->cfg.device, n);
+        if (!p->ok()) { delete p; return nullptr; }
+        h->stage_pool = p;
+    }
+    return static_cast<StagePool*>(h->stage_pool);
+}
+
+int stage_to_device(nk_counter* h, const uint8_t* src, int fd, uint64_t off, uint64_t n, unsigned char* dst,
+                    cudaEvent_t after, cudaStream_t then) {
+    StagePool* p = pool_of(h);
+    if (!p) return fail(NK_ERR_OOM, "cannot create the host staging pool (pinned memory / streams)");
+    return p->copy(src, fd, off, n, dst, after, then);
+}
+
+void stage_pool_destroy(nk_counter* h) {
+    delete static_cast<StagePool*>(h->stage_pool);
+    h->stage_pool = nullptr;
+}
+
+void ingest_free(nk_counter* h) {
+    stage_pool_destroy(h);
+    cudaFree(h->d_raw);
+    cudaFree(h->d_parse_scratch);
+    cudaFree(h->d_line_end);
+    cudaFree(h->d_parse_totals);
+    if (h->h_parse_totals) cudaFreeHost(h->h_parse_totals);
+    h->d_raw = nullptr; h->d_parse_scratch = nullptr; h->d_line_end = nullptr; h->d_parse_totals = nullptr; h->h_parse_totals = nullptr;
+    h->raw_cap = h->parse_scratch_cap = h->line_end_cap = 0;
+    h->fp_valid = false;
+}
+
+namespace {
+
+int grow(void** p, unsigned long long* cap, unsigned long long need) {
+    if (need <= *cap) return NK_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    const unsigned long long want = need + need / 8 + 256;
+    NK_CUDA(cudaMalloc(p, want));
+    *cap = want;
+    return NK_OK;
+}
+
+}  // namespace
+
+int parse_file_on_device(nk_counter* h, const char* path, bool* handled, bool* is_fastq, unsigned long long* nbases,
+                         unsigned long long* nrec, std::string* err) {
+    *handled = false;
+    if (const char* e = getenv("NK_GPU_PARSE")) if (atoi(e) == 0) return NK_OK;
+    if (getenv("NK_FASTA_WINDOW")) return NK_OK;  // the tests of the host reader's parallel ingest pin that path
+    const int fd = ::open(path, O_RDONLY);
+    if (fd < 0) return NK_OK;  // the host reader reports the error
+    struct stat st;
+    unsigned char magic[4] = {0, 0, 0, 0};
+    if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode) || st.st_size < 1 || ::pread(fd, magic, 4, 0) < 1 ||
+        (magic[0] != '>' && magic[0] != '@')) {  // compressed, empty, not FASTA/FASTQ, a pipe: the host reader decides
+        ::close(fd);
+        return NK_OK;
+    }
+    const unsigned long long size_real = (unsigned long long)st.st_size;
+    const bool fastq = magic[0] == '@';
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    // raw bytes + stripped bases (+ bitmap) + FASTQ line table must fit beside the pool: else the host reader streams
+    const unsigned long long have = (unsigned long long)free_b + h->raw_cap + h->staged.bases_cap + h->line_end_cap * 8;
+    if (size_real * (fastq ? 3ull : 2ull) + (size_real >> 2) + (256ull << 20) > have) { ::close(fd); return NK_OK; }
+
+    int rc = NK_OK;
+    do {
+        unsigned char last = '\n';
+        if (::pread(fd, &last, 1, (off_t)(size_real - 1)) != 1) { rc = fail(NK_ERR_IO, "%s: read failed", path); break; }
+        const bool add_nl = fastq && last != '\n';  // FASTQ: the end of the file ends the last line
+        const unsigned long long size = size_real + (add_nl ? 1 : 0);
+        if ((rc = grow((void**)&h->d_raw, &h->raw_cap, size + 64)) != NK_OK) break;
+        if ((rc = grow(&h->d_parse_scratch, &h->parse_scratch_cap, nk::parse_scratch_bytes(size))) != NK_OK) break;
+        if (!h->d_parse_totals) {
+            if (cudaMalloc(&h->d_parse_totals, 8 * sizeof(unsigned long long)) != cudaSuccess ||
+                cudaMallocHost(&h->h_parse_totals, 8 * sizeof(unsigned long long)) != cudaSuccess) {
+                rc = fail(NK_ERR_OOM, "parse totals");
+                break;
+            }
+        }
+        h->fp_valid = false;
+        // raw bytes -> device (the kernels of an earlier job may still read d_raw / staged: order behind them)
+        cudaEvent_t prev = nullptr;
+        if ((rc = get_event(h, &prev)) != NK_OK) break;
+        if (cudaEventRecord(prev, h->stream) != cudaSuccess) { rc = fail(NK_ERR_CUDA, "cudaEventRecord"); break; }
+        if ((rc = stage_to_device(h, nullptr, fd, 0, size_real, h->d_raw, prev, h->stream)) != NK_OK) break;
+        h->last.h2d_bytes += size_real;
+        if (add_nl && cudaMemsetAsync(h->d_raw + size_real, '\n', 1, h->stream) != cudaSuccess) { rc = fail(NK_ERR_CUDA, "cudaMemsetAsync"); break; }
+        unsigned long long nb = 0, nr = 0;
+#define NK_B(expr) { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { rc = fail(e_ == cudaErrorMemoryAllocation ? NK_ERR_OOM : NK_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); break; } }
+        if (!fastq) {
+            NK_B(nk::launch_fasta_plan(h->d_raw, size, h->d_parse_scratch, h->d_parse_totals, h->stream));
+            NK_B(cudaMemcpyAsync(h->h_parse_totals, h->d_parse_totals, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+            NK_B(cudaStreamSynchronize(h->stream));
+            nb = h->h_parse_totals[0];
+            nr = h->h_parse_totals[1];
+            if ((rc = ensure_devbuf(h->staged, nb)) != NK_OK) break;
+            if ((rc = ensure_offsets(&h->staged_offsets, &h->staged_offsets_cap, nr + 1)) != NK_OK) break;
+            NK_B(nk::launch_fasta_write(h->d_raw, size, h->d_parse_scratch, h->staged.bases, h->staged_offsets, h->stream));
+            // offsets[nrec] = number of bases (h_parse_totals[0] stays put until the next parse, which synchronises first)
+            NK_B(cudaMemcpyAsync(h->staged_offsets + nr, h->h_parse_totals, sizeof(unsigned long long), cudaMemcpyHostToDevice, h->stream));
+        } else {
+            NK_B(nk::launch_fastq_lines(h->d_raw, size, h->d_parse_scratch, h->d_parse_totals, h->stream));
+            NK_B(cudaMemcpyAsync(h->h_parse_totals + 2, h->d_parse_totals + 2, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+            NK_B(cudaStreamSynchronize(h->stream));
+            const unsigned long long nlines = h->h_parse_totals[2];
+            unsigned long long le_bytes = h->line_end_cap * 8;
+            if ((rc = grow((void**)&h->d_line_end, &le_bytes, (nlines + 1) * 8)) != NK_OK) break;
+            h->line_end_cap = le_bytes / 8;
+            // sequence lines are at most half of a well-formed file; a malformed one may keep more (dropped later)
+            if ((rc = ensure_devbuf(h->staged, size)) != NK_OK) break;
+            if ((rc = ensure_offsets(&h->staged_offsets, &h->staged_offsets_cap, nlines / 4 + 2)) != NK_OK) break;
+            NK_B(nk::launch_fastq_write(h->d_raw, size, size_real, h->d_parse_scratch, h->staged.bases, h->staged_offsets, h->d_line_end,
+                                        nlines, h->d_parse_totals, h->stream));
+            NK_B(cudaMemcpyAsync(h->h_parse_totals, h->d_parse_totals, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+            NK_B(cudaStreamSynchronize(h->stream));
+            nb = h->h_parse_totals[0];
+            nr = h->h_parse_totals[1];
+        }
+#undef NK_B
+        *nbases = nb;
+        *nrec = nr;
+        *is_fastq = fastq;
+        *handled = true;
+        h->fp_valid = true;
+        h->fp_path = path;
+        h->fp_size = size_real;
+        h->fp_mtime_ns = (unsigned long long)st.st_mtim.tv_sec * 1000000000ull + (unsigned long long)st.st_mtim.tv_nsec;
+        h->fp_nbases = nb;
+        h->fp_nrec = nr;
+    } while (0);
+    ::close(fd);
+    if (rc != NK_OK && err) *err = g_err;
+    return rc;
+}
+
+}  // namespace nkd
+
+extern "C" {
+
+// Parity tap: parse a plain FASTA / FASTQ file ON THE DEVICE and digest what comes out exactly like
+// nk_debug_fastx_digest digests the host reader's records (FNV-1a-64 over every record's bases + one 0xFF).
+int nk_debug_parse_file(nk_counter* h, const char* path, uint64_t* nrecords, uint64_t* nbases, uint64_t* fnv1a) {
+    if (!h || !path) return fail(NK_ERR_BAD_ARG, "null argument");
+    if (is_group(h)) return nk_debug_parse_file(h->group[0], path, nrecords, nbases, fnv1a);
+    NK_CUDA(cudaSetDevice(h->cfg.device));
+    NK_TRY(resolve(h));
+    NK_CUDA(cudaStreamSynchronize(h->stream));
+    bool handled = false, fq = false;
+    unsigned long long nb = 0, nr = 0;
+    std::string err;
+    NK_TRY(parse_file_on_device(h, path, &handled, &fq, &nb, &nr, &err));
+    if (!handled) return fail(NK_ERR_UNSUPPORTED, "%s: not a plain regular FASTA/FASTQ file the device parser takes", path);
+    std::vector<uint8_t> bases(nb ? nb : 1);
+    std::vector<uint64_t> offs(nr + 1);
+    NK_CUDA(cudaMemcpyAsync(bases.data(), h->staged.bases, nb, cudaMemcpyDeviceToHost, h->stream));
+    NK_CUDA(cudaMemcpyAsync(offs.data(), h->staged_offsets, (nr + 1) * 8, cudaMemcpyDeviceToHost, h->stream));
+    NK_CUDA(cudaStreamSynchronize(h->stream));
+    uint64_t hsh = 0xcbf29ce484222325ull;
+    if (offs[0] != 0 || offs[nr] != nb) return fail(NK_ERR_CUDA, "device parser: inconsistent offsets (%llu .. %llu of %llu)",
+                                                    (unsigned long long)offs[0], (unsigned long long)offs[nr], nb);
+    for (uint64_t r = 0; r < nr; ++r) {
+        if (offs[r + 1] < offs[r]) return fail(NK_ERR_CUDA, "device parser: offsets decrease at record %llu", (unsigned long long)r);
+        if (fnv1a) {
+            for (uint64_t i = offs[r]; i < offs[r + 1]; ++i) { hsh ^= bases[i]; hsh *= 0x100000001b3ull; }
+            hsh ^= 0xFFu; hsh *= 0x100000001b3ull;
+        }
+    }
+    if (nrecords) *nrecords = nr;
+    if (nbases) *nbases = nb;
+    if (fnv1a) *fnv1a = hsh;
+    return NK_OK;
+}
+
+}  // extern "C"

@@ -156,6 +156,20 @@ struct nk_counter {
     unsigned char* dist_mail[16] = {};
     unsigned long long dist_epoch = 0;
     bool dist_failed = false;
+    // ---- host -> device staging by a pool of host threads, and record parsing on the device (nk_ingest.cu) ----
+    void* stage_pool = nullptr;             // nkd::StagePool*, created at first use
+    unsigned char* d_raw = nullptr;         // raw file bytes
+    unsigned long long raw_cap = 0;
+    void* d_parse_scratch = nullptr;
+    unsigned long long parse_scratch_cap = 0;
+    unsigned long long* d_line_end = nullptr;  // FASTQ: position of every newline
+    unsigned long long line_end_cap = 0;
+    unsigned long long* d_parse_totals = nullptr;  // 8 u64
+    unsigned long long* h_parse_totals = nullptr;  // pinned mirror
+    // the parsed file that still sits in `staged` / `staged_offsets` (the uniques pass re-uses it instead of a second read)
+    bool fp_valid = false;
+    std::string fp_path;
+    unsigned long long fp_size = 0, fp_mtime_ns = 0, fp_nbases = 0, fp_nrec = 0;
     bool uniques_whole_input = false;  // group[0] of a multi-GPU group: its uniques pass is handed the whole input again
     bool slice_only = false;  // after a sharded-pool job: currents / v / r / spikes are only defined inside this rank's slice
     bool last_push_zc = false;  // the last host batch was read in place (zero-copy): its kernels hold the caller's buffer
@@ -210,9 +224,31 @@ int resolve(nk_counter* h);
 void begin_call(nk_counter* h);
 void collect_timings(nk_counter* h, const PhaseEvents& pe);
 float ev_ms(cudaEvent_t a, cudaEvent_t b);
+int fold_and_simulate(nk_counter* h, bool skip_zero, PhaseEvents& pe, bool with_topn);
 int dist_build_post(nk_counter* h, nk::PostParams& q, unsigned long long* n_top_out);
 int dist_finish(nk_counter* h, unsigned long long n_out);
 int copy_out(nk_counter* h, void* dst, const void* src, size_t bytes);
+
+// ---- parallel staging + device-side record parsing (nk_ingest.cu) ---------------------------------------
+// host memory [src, src+n) (fd < 0) or file bytes [off, off+n) of fd -> device dst, by the handle's pool of
+// host threads (memcpy / pread into pinned slots, async H2D on per-thread streams).  Returns when every
+// copy has been ENQUEUED and the source bytes have been consumed; `after` (may be null): the copies wait
+// for this event on the device; `then`: this stream waits for all of them.
+int stage_to_device(nk_counter* h, const uint8_t* src, int fd, uint64_t off, uint64_t n, unsigned char* dst,
+                    cudaEvent_t after, cudaStream_t then);
+void stage_pool_destroy(nk_counter* h);
+// Whole plain FASTA / FASTQ file -> h->staged (bases) + h->staged_offsets, parsed on the device.
+// *handled = false (and NK_OK): this path does not apply (compressed, not a regular file, too large, disabled)
+int parse_file_on_device(nk_counter* h, const char* path, bool* handled, bool* is_fastq, unsigned long long* nbases,
+                         unsigned long long* nrec, std::string* err);
+void ingest_free(nk_counter* h);
+int uniques_chunk(nk_counter* h, DevBuf& b, const unsigned long long* d_offsets, unsigned long long seq_lo,
+                  unsigned long long seq_hi, unsigned long long origin, unsigned long long nstarts, bool packed);
+int count_chunk(nk_counter* h, DevBuf& b, const unsigned long long* d_offsets, unsigned long long seq_lo,
+                unsigned long long seq_hi, unsigned long long origin, unsigned long long nstarts,
+                unsigned long long max_windows, PhaseEvents* pe, bool packed);
+int ensure_devbuf(DevBuf& b, unsigned long long nbytes);
+int ensure_offsets(unsigned long long** p, unsigned long long* cap, unsigned long long n);
 
 // ---- single-process multi-GPU groups (nk_multi.cu) ---------------------------------------------------
 inline bool is_group(const nk_counter* h) { return h && !h->group.empty(); }

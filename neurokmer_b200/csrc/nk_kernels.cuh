@@ -282,6 +282,19 @@ void exact_free(ExactTable& t);
 cudaError_t exact_grow_words(ExactTable& t, unsigned long long cap, unsigned long long keep, cudaStream_t s);
 cudaError_t launch_filter_set(unsigned int* filter, const unsigned long long* idx, unsigned long long n, cudaStream_t s);
 
+// record parsing on the device (nk_parse.cu).  `file`: raw bytes, 16-byte aligned, readable up to size + 16.
+// totals (device, 8 u64): [0] bases, [1] records, [2] newlines, [3] kept bytes incl. dropped records, [4] first bad record
+size_t parse_scratch_bytes(unsigned long long size);
+cudaError_t launch_fasta_plan(const unsigned char* file, unsigned long long size, void* scratch,
+                              unsigned long long* totals, cudaStream_t s);
+cudaError_t launch_fasta_write(const unsigned char* file, unsigned long long size, void* scratch, unsigned char* bases,
+                               unsigned long long* offsets, cudaStream_t s);
+cudaError_t launch_fastq_lines(const unsigned char* file, unsigned long long size, void* scratch,
+                               unsigned long long* totals, cudaStream_t s);
+cudaError_t launch_fastq_write(const unsigned char* file, unsigned long long size, unsigned long long size_real, void* scratch,
+                               unsigned char* bases, unsigned long long* offsets, unsigned long long* line_end,
+                               unsigned long long nlines, unsigned long long* totals, cudaStream_t s);
+
 // peak calibration (roofline denominators)
 cudaError_t launch_int_peak(int mode, unsigned int* out, int blocks, unsigned iters, cudaStream_t s);
 unsigned long long int_peak_ops_per_iter(int mode);

@@ -270,6 +270,9 @@ NK_API int nk_debug_fastx_digest(const char* path, uint64_t* nrecords, uint64_t*
 /* The same digest of what the DEVICE-side record parser (nk_parse.cu: the path nk_process_file takes for plain
  * regular FASTA / FASTQ files) yields; NK_ERR_UNSUPPORTED where that path does not apply (compressed input, ...). */
 NK_API int nk_debug_parse_file(nk_counter* h, const char* path, uint64_t* nrecords, uint64_t* nbases, uint64_t* fnv1a);
+/* Measurement tap for the file path: milliseconds the staging pool needs to pread the whole file into its pinned
+ * slots with no device work (host_only_ms), and with the H2D copies into device memory, completed (with_h2d_ms). */
+NK_API int nk_debug_stage_file(nk_counter* h, const char* path, double* host_only_ms, double* with_h2d_ms);
 /* the same digest (plain FASTA only) through the parallel ingest's window planner + window parser, with windows
  * of `window` bytes (>= 64), run serially: checks the code the multi-threaded file path is made of */
 NK_API int nk_debug_fasta_windows_digest(const char* path, uint64_t window, uint64_t* nrecords, uint64_t* nbases,

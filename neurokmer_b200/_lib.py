@@ -31,7 +31,7 @@ SYMBOLS = [
     "nk_stream_push_packed", "nk_debug_kmers_packed", "nk_debug_pack_body", "nk_stage_reserve_packed",
     "nk_process_staged_packed", "nk_debug_fastx_digest", "nk_dist_run",
     "nk_debug_fasta_windows_digest", "nk_uniques_begin", "nk_uniques_push", "nk_uniques_push_packed", "nk_uniques_end", "nk_set_file_uniques",
-    "nk_debug_set_fold_limit", "nk_device_count", "nk_create_multi", "nk_group_size", "nk_debug_shard", "nk_debug_parse_file",
+    "nk_debug_set_fold_limit", "nk_device_count", "nk_create_multi", "nk_group_size", "nk_debug_shard", "nk_debug_parse_file", "nk_debug_stage_file",
 ]
 
 
@@ -146,6 +146,7 @@ def load() -> C.CDLL:
         "nk_process_staged_packed": (i32, [vp, u64, u64, i32, i32]),
         "nk_debug_fastx_digest": (i32, [C.c_char_p, P(u64), P(u64), P(u64)]),
         "nk_debug_parse_file": (i32, [vp, C.c_char_p, P(u64), P(u64), P(u64)]),
+        "nk_debug_stage_file": (i32, [vp, C.c_char_p, P(C.c_double), P(C.c_double)]),
         "nk_debug_fasta_windows_digest": (i32, [C.c_char_p, u64, P(u64), P(u64), P(u64)]),
     }
     for name, (res, args) in sig.items():

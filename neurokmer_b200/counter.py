@@ -321,6 +321,12 @@ class SpikingKmerCounter:
         check(self._L.nk_debug_parse_file(self._h, str(path).encode(), C.byref(nr), C.byref(nb), C.byref(hs)))
         return nr.value, nb.value, hs.value
 
+    def debug_stage_file(self, path: str) -> Tuple[float, float]:
+        """(host-only ms, ms with the H2D copies) of the staging pool on a file: the ceiling of the file path"""
+        a, b = C.c_double(), C.c_double()
+        check(self._L.nk_debug_stage_file(self._h, str(path).encode(), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def debug_set_fold_limit(self, limit: int) -> None:
         check(self._L.nk_debug_set_fold_limit(self._h, limit))
 

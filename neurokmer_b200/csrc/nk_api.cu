@@ -150,6 +150,13 @@ int fold_now(nk_counter* h) {
     return NK_OK;
 }
 
+// the device k-mer counter of the call (scalars[2]) starts at zero; the fused post kernel leaves it zeroed
+int zero_kmers(nk_counter* h) {
+    if (!h->kmers_clean) NK_CUDA(cudaMemsetAsync(h->scalars + 2, 0, sizeof(unsigned long long), h->stream));
+    h->kmers_clean = true;
+    return NK_OK;
+}
+
 unsigned char* own_mail(nk_counter* h) {
     return reinterpret_cast<unsigned char*>(h->acc) + nk::dist_mail_offset(h->cfg.pool_size);
 }
@@ -188,6 +195,7 @@ int count_chunk(nk_counter* h, DevBuf& b, const unsigned long long* d_offsets, u
                 unsigned long long seq_hi, unsigned long long origin, unsigned long long nstarts,
                 unsigned long long max_windows, PhaseEvents* pe, bool packed) {
     if (nstarts == 0) return NK_OK;
+    NvtxRange nvtx("nk:count (mark + windowing/SipHash/mod/RED)");
     if (h->acc_kmers + max_windows > h->fold_limit) NK_TRY(h->dist_world > 0 && h->streaming ? spill_now(h) : fold_now(h));
     cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
     // phase timing covers at most kMaxTimedChunks chunks of a job (bounds the event pool of very long
@@ -199,9 +207,17 @@ int count_chunk(nk_counter* h, DevBuf& b, const unsigned long long* d_offsets, u
         NK_TRY(get_event(h, &e2));
         NK_CUDA(cudaEventRecord(e0, h->stream));
     }
-    NK_CUDA(cudaMemsetAsync(h->tile_counter, 0, sizeof(unsigned int), h->stream));
-    NK_CUDA(nk::launch_mark_invalid(b.invalid, d_offsets, seq_lo, seq_hi, origin, nstarts, h->cfg.k,
-                                    h->scalars + 2, h->stream, &h->last.launches));
+    // short-read batches (mean sequence length < 2 KiB): compact the valid window starts first (mode 3).
+    // Long sequences: no invalid-start bitmap at all — every tile looks the few sequence ends that reach into
+    // it up in the offsets (mode 5): no memset, no marking kernels, 1/8 B per base less HBM traffic.
+    const unsigned long long nseq_here = seq_hi - seq_lo;
+    const bool short_reads = nseq_here > 0 && nstarts / nseq_here < 2048 && h->cfg.k > 1;
+    const char* bm_env = getenv("NK_BITMAP");  // NK_BITMAP=1: the bitmap path for long sequences too (A/B runs, tests)
+    const bool force_bitmap = bm_env && atoi(bm_env) != 0;
+    const int mode = h->exact ? 2 : (short_reads ? 3 : (force_bitmap || nseq_here == 0 ? 0 : 5));
+    if (mode != 5)
+        NK_CUDA(nk::launch_mark_invalid(b.invalid, d_offsets, seq_lo, seq_hi, origin, nstarts, h->cfg.k,
+                                        h->scalars + 2, h->stream, &h->last.launches));
     if (pe) NK_CUDA(cudaEventRecord(e1, h->stream));
     nk::CountParams p{};
     p.bases = packed ? b.codes : b.bases;
@@ -221,10 +237,12 @@ int count_chunk(nk_counter* h, DevBuf& b, const unsigned long long* d_offsets, u
         p.words = h->xt.words;
         p.words_cursor = h->xt.cursor;
     }
-    // short-read batches (mean sequence length < 2 KiB): compact the valid window starts first
-    const unsigned long long nseq_here = seq_hi - seq_lo;
-    const bool short_reads = nseq_here > 0 && nstarts / nseq_here < 2048 && h->cfg.k > 1;
-    NK_CUDA(nk::launch_count(p, h->cfg.use_canonical != 0, h->exact ? 2 : (short_reads ? 3 : 0), h->stream));
+    p.offsets = d_offsets + seq_lo;
+    p.nseq = nseq_here;
+    p.origin = origin;
+    p.nstarts = nstarts;
+    p.kmers_out = h->scalars + 2;
+    NK_CUDA(nk::launch_count(p, h->cfg.use_canonical != 0, mode, h->stream));
     ++h->last.launches;
     if (pe) {
         NK_CUDA(cudaEventRecord(e2, h->stream));
@@ -233,6 +251,7 @@ int count_chunk(nk_counter* h, DevBuf& b, const unsigned long long* d_offsets, u
         pe->count1.push_back(e2);
     }
     h->acc_dirty = true;
+    h->kmers_clean = false;
     h->acc_kmers += max_windows;
     // queued BEHIND the count kernel's persistent grid: the table build (side stream, 4 CTAs) gets
     // its SM slots when the first count CTAs retire, i.e. it runs in the count kernel's tail
@@ -495,7 +514,6 @@ int uniques_chunk(nk_counter* h, DevBuf& b, const unsigned long long* d_offsets,
         p.words = h->ut.words;
         p.words_cursor = h->ut.cursor;
         p.words_cap = h->ut.words_cap;
-        NK_CUDA(cudaMemsetAsync(h->tile_counter, 0, sizeof(unsigned int), h->stream));
         NK_CUDA(nk::launch_count(p, h->cfg.use_canonical != 0, 4, h->stream));
         unsigned long long cursor = 0;
         NK_CUDA(cudaMemcpyAsync(&cursor, h->ut.cursor, sizeof cursor, cudaMemcpyDeviceToHost, h->stream));
@@ -622,6 +640,7 @@ int prelaunch_table(nk_counter* h) {
 // If the u32 batch accumulators still hold counts they are folded into `currents` by the LIF
 // kernel itself (fold_mode), otherwise the stored currents are used as they are.
 int simulate(nk_counter* h, bool skip_zero, bool with_topn) {
+    NvtxRange nvtx("nk:post (fold + LIF + top-N)");
     h->last.lif_path = 0;
     h->top_cache_valid = false;
     int fold_mode = 0;
@@ -642,7 +661,8 @@ int simulate(nk_counter* h, bool skip_zero, bool with_topn) {
     p.leak = h->cfg.leak;
     p.period = h->cfg.refractory;
     p.skip_zero = skip_zero ? 1 : 0;
-    NK_CUDA(cudaMemsetAsync(h->scalars, 0, sizeof(unsigned long long), h->stream));
+    if (!h->fired_clean) NK_CUDA(cudaMemsetAsync(h->scalars, 0, sizeof(unsigned long long), h->stream));
+    h->fired_clean = false;
     unsigned long long table_n = 0;
     const bool use_table = table_path_ok(h, &table_n);
     if (h->lazy_zero) {
@@ -675,13 +695,15 @@ int simulate(nk_counter* h, bool skip_zero, bool with_topn) {
             q.single_pass = bound < (unsigned long long)nk::POST_EXACT_BINS ? 1 : 0;
             q.ctrl = h->post_zero;
             q.hist = reinterpret_cast<unsigned int*>(h->post_zero + 8);
+            q.block_ties = q.hist + 8 * 256;
             q.seg_counts = h->topn.block_counts;
             q.out_idx = h->topn.out_idx;
             q.out_spikes = h->topn.out_spikes;
             q.pack = h->d_pack;
             q.kmers = h->scalars + 2;
-            NK_CUDA(cudaMemsetAsync(h->post_zero, 0, 8 * sizeof(unsigned long long) + 8 * 256 * sizeof(unsigned int), h->stream));
+            // (no memsets: the kernel leaves its scratch, the spike counter and the k-mer counter zeroed)
             NK_CUDA(nk::launch_post(q, h->post_grid, h->stream));
+            h->fired_clean = h->kmers_clean = true;
             ++h->last.launches;
             h->last.lif_path = 3;
             h->top_cached_n = n_top;
@@ -1194,7 +1216,7 @@ static int process_file_device(nk_counter* h, const char* path, bool streaming, 
     unsigned long long nb = 0, nr = 0;
     rc = parse_file_on_device(h, path, handled, &fq, &nb, &nr, err);
     if (rc != NK_OK || !*handled) return rc;
-    cudaMemsetAsync(h->scalars + 2, 0, sizeof(unsigned long long), h->stream);
+    zero_kmers(h);
     h->currents_valid_overwrite = true;
     for (unsigned long long c0 = 0; c0 < nb && nr > 0; c0 += slice) {
         const unsigned long long n = std::min(slice, nb - c0);
@@ -1284,7 +1306,7 @@ int process_file(nk_counter* h, const char* path, bool streaming, std::string* e
         if (!ingest_only && !grp) {
             if (get_event(h, &pe.begin) != NK_OK) { *err = g_err; rc = NK_ERR_CUDA; break; }
             cudaEventRecord(pe.begin, h->stream);
-            cudaMemsetAsync(h->scalars + 2, 0, sizeof(unsigned long long), h->stream);
+            zero_kmers(h);
             h->currents_valid_overwrite = true;
         }
         bool stop = false;
@@ -1423,12 +1445,14 @@ int nk_create(const nk_config* cfg, nk_counter** out) {
     NK_C(cudaMalloc(&h->spikes, P * sizeof(unsigned long long)));
     NK_C(cudaMalloc(&h->scalars, 8 * sizeof(unsigned long long)));
     NK_C(cudaMalloc(&h->tile_counter, 64));
+    NK_C(cudaMemset(h->tile_counter, 0, 64));  // [0] tile cursor, [1] finished CTAs: the count kernel re-arms both itself
     NK_C(cudaMallocHost(&h->h_scalars, 8 * sizeof(unsigned long long)));
     NK_C(cudaMalloc(&h->topn.hist, 256 * sizeof(unsigned int)));
     NK_C(cudaMalloc(&h->topn.ctrl, 8 * sizeof(unsigned long long)));
     NK_C(cudaMalloc(&h->topn.block_counts, ((P + nk::POST_SEG_ITEMS - 1) / nk::POST_SEG_ITEMS + 1) * sizeof(unsigned int)));
     NK_C(nk::post_max_grid(cfg->device, &h->post_grid));
-    NK_C(cudaMalloc(&h->post_zero, 8 * sizeof(unsigned long long) + 8 * 256 * sizeof(unsigned int)));
+    NK_C(cudaMalloc(&h->post_zero, nk::POST_SCRATCH_BYTES));
+    NK_C(cudaMemset(h->post_zero, 0, nk::POST_SCRATCH_BYTES));  // the fused kernel leaves it zeroed
     NK_C(cudaMalloc(&h->d_pack, nk::PACK_MAX_U64 * sizeof(unsigned long long)));
     NK_C(cudaMallocHost(&h->h_pack, nk::PACK_MAX_U64 * sizeof(unsigned long long)));
     NK_C(cudaMalloc(&h->topn.out_idx, 2048 * sizeof(unsigned long long)));
@@ -1459,7 +1483,8 @@ int nk_reset(nk_counter* h) {
     h->table_valid = false;  // a reset counter is a fresh counter: its first job rebuilds the LIF table
     h->top_cache_valid = false;
     h->pending_pack = false;
-    NK_CUDA(cudaMemsetAsync(h->scalars, 0, 8 * sizeof(unsigned long long), h->stream));
+    if (!(h->fired_clean && h->kmers_clean)) NK_CUDA(cudaMemsetAsync(h->scalars, 0, 8 * sizeof(unsigned long long), h->stream));
+    h->fired_clean = h->kmers_clean = true;
     if (h->pending) { NK_CUDA(cudaStreamSynchronize(h->stream)); h->pending = false; h->pend_pe = PhaseEvents{}; }
     if (h->exact) NK_CUDA(nk::exact_clear(h->xt, h->cfg.pool_size, true, h->stream));
     h->total_spikes = 0;
@@ -1532,7 +1557,7 @@ int nk_process_batch(nk_counter* h, const uint8_t* bases, const uint64_t* offset
     PhaseEvents pe;
     NK_TRY(get_event(h, &pe.begin));
     NK_CUDA(cudaEventRecord(pe.begin, h->stream));
-    NK_CUDA(cudaMemsetAsync(h->scalars + 2, 0, sizeof(unsigned long long), h->stream));
+    NK_TRY(zero_kmers(h));
     h->currents_valid_overwrite = true;  // totals of THIS call overwrite the stored currents (:174-176)
     NK_TRY(count_host_batch(h, bases, offsets, nseq, &pe, kPushSync));
     NK_TRY(fold_and_simulate(h, /*skip_zero=*/true, pe, true));
@@ -1551,7 +1576,7 @@ int nk_stream_begin(nk_counter* h) {
     h->streaming = true;
     h->stream_pe = PhaseEvents{};
     h->currents_valid_overwrite = true;
-    NK_CUDA(cudaMemsetAsync(h->scalars + 2, 0, sizeof(unsigned long long), h->stream));
+    NK_TRY(zero_kmers(h));
     return NK_OK;
 }
 
@@ -1602,7 +1627,7 @@ int nk_process_batch_packed(nk_counter* h, const uint32_t* codes, const uint32_t
     PhaseEvents pe;
     NK_TRY(get_event(h, &pe.begin));
     NK_CUDA(cudaEventRecord(pe.begin, h->stream));
-    NK_CUDA(cudaMemsetAsync(h->scalars + 2, 0, sizeof(unsigned long long), h->stream));
+    NK_TRY(zero_kmers(h));
     h->currents_valid_overwrite = true;
     NK_TRY(count_host_batch_packed(h, codes, other, offsets, nseq, &pe, kPushSync));
     NK_TRY(fold_and_simulate(h, /*skip_zero=*/true, pe, true));
@@ -1681,7 +1706,7 @@ int nk_process_sequence(nk_counter* h, const uint8_t* seq, uint64_t len) {
     if (len < h->cfg.k) return NK_OK;  // src/spiking_hash.rs:206-208
     // process_sequence ADDS to neuron_currents (fetch_add, :225,241,258) and zeroes them afterwards
     const uint64_t offs[2] = {0, len};
-    NK_CUDA(cudaMemsetAsync(h->scalars + 2, 0, sizeof(unsigned long long), h->stream));
+    NK_TRY(zero_kmers(h));
     h->currents_valid_overwrite = false;
     NK_TRY(materialize_zero(h));
     NK_TRY(count_host_batch(h, seq, offs, 1, nullptr, kPushSync));
@@ -1692,6 +1717,7 @@ int nk_process_sequence(nk_counter* h, const uint8_t* seq, uint64_t len) {
     p.pool = h->cfg.pool_size; p.steps = 1; p.thr = h->cfg.threshold; p.leak = h->cfg.leak;
     p.period = h->cfg.refractory; p.skip_zero = 1;
     NK_CUDA(cudaMemsetAsync(h->scalars, 0, sizeof(unsigned long long), h->stream));
+    h->fired_clean = false;
     NK_CUDA(nk::launch_lif_single_tick(p, h->currents, h->stream));
     ++h->last.launches;
     h->fresh = false;
@@ -1890,7 +1916,6 @@ static int debug_kmers_any(nk_counter* h, const uint8_t* seq, const uint32_t* co
         }
         NK_D(cudaMemcpyAsync(h->staged_offsets, offs, sizeof offs, cudaMemcpyHostToDevice, h->stream));
         NK_D(cudaStreamSynchronize(h->stream));  // offs is on this stack frame
-        NK_D(cudaMemsetAsync(h->tile_counter, 0, sizeof(unsigned int), h->stream));
         NK_D(nk::launch_mark_invalid(h->staged.invalid, h->staged_offsets, 0, 1, 0, len, h->cfg.k, h->scalars + 3,
                                      h->stream, nullptr));
         nk::CountParams p{};
@@ -2164,6 +2189,7 @@ int dist_build_post(nk_counter* h, nk::PostParams& q, unsigned long long* n_top_
     q.single_pass = per_call < (unsigned long long)nk::POST_EXACT_BINS ? 1 : 0;
     q.ctrl = h->post_zero;
     q.hist = reinterpret_cast<unsigned int*>(h->post_zero + 8);
+    q.block_ties = q.hist + 8 * 256;
     q.seg_counts = h->topn.block_counts;
     q.out_idx = h->topn.out_idx;
     q.out_spikes = h->topn.out_spikes;
@@ -2180,8 +2206,8 @@ int dist_build_post(nk_counter* h, nk::PostParams& q, unsigned long long* n_top_
     q.rank = h->dist_rank;
     // rows are padded to n_top per rank so that every rank's pack has the same size
     NK_CUDA(cudaMemsetAsync(h->d_pack, 0, (nk::PACK_HDR + 2 * n_top) * sizeof(unsigned long long), h->stream));
-    NK_CUDA(cudaMemsetAsync(h->scalars, 0, sizeof(unsigned long long), h->stream));
-    NK_CUDA(cudaMemsetAsync(h->post_zero, 0, 8 * sizeof(unsigned long long) + 8 * 256 * sizeof(unsigned int), h->stream));
+    if (!h->fired_clean) NK_CUDA(cudaMemsetAsync(h->scalars, 0, sizeof(unsigned long long), h->stream));
+    h->fired_clean = h->kmers_clean = true;  // the slice kernel every caller launches next leaves them zeroed
     *n_top_out = n_top;
     h->dist_n_each = n_top;
     return NK_OK;
@@ -2248,6 +2274,7 @@ int nk_dist_post(nk_counter* h, void** dev_pack, uint64_t* pack_u64s, uint64_t* 
 // could starve each other); a lost peer surfaces as NK_ERR_STATE after NK_DIST_TIMEOUT_MS (default 30 s).
 int nk_dist_run(nk_counter* h) {
     if (is_group(h)) return group_unsupported("nk_dist_run");
+    NvtxRange nvtx("nk:exchange (signal + slice reduce/LIF/top-N + pack merge)");
     if (!h) return fail(NK_ERR_BAD_ARG, "null handle");
     if (!h->dist_world) return fail(NK_ERR_STATE, "nk_dist_setup was not called");
     if (!h->streaming) return fail(NK_ERR_STATE, "nk_dist_run without nk_stream_begin");
@@ -2327,7 +2354,7 @@ int nk_process_staged(nk_counter* h, uint64_t nbytes, uint64_t nseq, int mode) {
         begin_call(h);
         NK_TRY(get_event(h, &pe.begin));
         NK_CUDA(cudaEventRecord(pe.begin, h->stream));
-        NK_CUDA(cudaMemsetAsync(h->scalars + 2, 0, sizeof(unsigned long long), h->stream));
+        NK_TRY(zero_kmers(h));
         h->currents_valid_overwrite = true;
     }
     // the device-resident batch is counted in slices of < 2^32 window starts (one launch each; the
@@ -2385,7 +2412,7 @@ int nk_process_staged_packed(nk_counter* h, uint64_t nbases, uint64_t nseq, int 
         begin_call(h);
         NK_TRY(get_event(h, &pe.begin));
         NK_CUDA(cudaEventRecord(pe.begin, h->stream));
-        NK_CUDA(cudaMemsetAsync(h->scalars + 2, 0, sizeof(unsigned long long), h->stream));
+        NK_TRY(zero_kmers(h));
         h->currents_valid_overwrite = true;
     }
     const unsigned long long slice = (0xFFFFFFFFull / nk::COUNT_TILE - 1) * nk::COUNT_TILE;

@@ -62,7 +62,7 @@ __device__ __forceinline__ WindowConsts make_window_consts(unsigned k) {
     return c;
 }
 
-template <bool PACKED>
+template <bool PACKED, bool BITMAP>
 __device__ __forceinline__ void issue_tile(unsigned char* stage, unsigned long long* bar,
                                            const CountParams& p, unsigned long long tile) {
     // bytes of a tile copy that starts at `off`, clamped to the caller's array when it has a known end
@@ -74,18 +74,20 @@ __device__ __forceinline__ void issue_tile(unsigned char* stage, unsigned long l
         const unsigned long long coff = tile * (COUNT_TILE / 4), ooff = tile * (COUNT_TILE / 8);
         const unsigned cb = clamp(kPkCodes, coff, p.bases_bytes);
         const unsigned ob = has_other ? clamp(kPkOther, ooff, p.other_bytes) : 0u;
-        mbar_expect_tx(bar, cb + kBitsPerStage + ob);
+        mbar_expect_tx(bar, cb + (BITMAP ? kBitsPerStage : 0) + ob);
         tma_load_1d(stage, p.bases + coff, cb, bar);
         if (has_other) tma_load_1d(stage + kPkCodes, p.other + ooff, ob, bar);
-        tma_load_1d(stage + kPkCodes + kPkOther, (const unsigned char*)p.invalid + tile * kBitsPerStage,
-                    kBitsPerStage, bar);
+        if (BITMAP)
+            tma_load_1d(stage + kPkCodes + kPkOther, (const unsigned char*)p.invalid + tile * kBitsPerStage,
+                        kBitsPerStage, bar);
     } else {
         const unsigned long long boff = tile * COUNT_TILE;
         const unsigned bb = clamp(kBytesPerStage, boff, p.bases_bytes);
-        mbar_expect_tx(bar, bb + kBitsPerStage);
+        mbar_expect_tx(bar, bb + (BITMAP ? kBitsPerStage : 0));
         tma_load_1d(stage, p.bases + boff, bb, bar);
-        tma_load_1d(stage + kBytesPerStage, (const unsigned char*)p.invalid + tile * kBitsPerStage,
-                    kBitsPerStage, bar);
+        if (BITMAP)
+            tma_load_1d(stage + kBytesPerStage, (const unsigned char*)p.invalid + tile * kBitsPerStage,
+                        kBitsPerStage, bar);
     }
 }
 
@@ -99,6 +101,63 @@ __device__ __forceinline__ Codes16 load_codes(const unsigned char* sb, unsigned 
     } else {
         return convert16<!CANON>(reinterpret_cast<const uint4*>(sb)[i]);
     }
+}
+
+// ---- MODE 5: invalid window starts without a bitmap ---------------------------------------------------
+// Start x is invalid iff the first sequence end e > x satisfies x > e - k (the window would cross e), or x lies
+// beyond the chunk.  Per tile, one thread looks up the (at most kTileEnds) sequence ends that can reach into the
+// tile; lanes turn them into their 16 bits.  A tile with more ends than that (a run of tiny sequences inside a
+// long-sequence batch) makes every lane walk the offsets itself.
+constexpr int kTileEnds = 4;
+struct TileEnds {
+    int n;                          // ends stored; kTileEnds + 1: dense tile, lanes walk `offsets` from `first`
+    int limit;                      // tile-relative end of the chunk's window starts (COUNT_TILE, less in the last tile)
+    int rel[kTileEnds];             // tile-relative positions of the ends (> 0, < COUNT_TILE + 32)
+    unsigned long long first;       // index (into offsets[1..]) of the first end > tile start
+};
+
+__device__ __forceinline__ void find_tile_ends(const CountParams& p, unsigned long long tile, TileEnds* te) {
+    const unsigned long long t0 = p.origin + tile * COUNT_TILE;
+    // first end > t0 among offsets[1 .. nseq]
+    unsigned long long lo = 0, hi = p.nseq;  // answer in [lo, hi]: index i means offsets[i + 1]
+    while (lo < hi) {
+        const unsigned long long mid = (lo + hi) >> 1;
+        if (__ldg(p.offsets + mid + 1) > t0) hi = mid; else lo = mid + 1;
+    }
+    te->first = lo;
+    const unsigned long long reach = t0 + COUNT_TILE + (p.k - 1);  // an end e invalidates starts e-k+1 .. e-1
+    int n = 0;
+    for (unsigned long long i = lo; i < p.nseq; ++i) {
+        const unsigned long long e = __ldg(p.offsets + i + 1);
+        if (e >= reach) break;
+        if (n == kTileEnds) { n = kTileEnds + 1; break; }
+        te->rel[n++] = (int)(e - t0);
+    }
+    te->n = n;
+    const unsigned long long left = p.nstarts - tile * COUNT_TILE;
+    te->limit = left < (unsigned long long)COUNT_TILE ? (int)left : COUNT_TILE;
+}
+
+// bits j (0..15): start q + j (tile-relative) is invalid
+__device__ __forceinline__ unsigned range_bits(int lo, int hi) {  // positions [lo, hi) clipped to [0, 16)
+    lo = lo < 0 ? 0 : lo;
+    hi = hi > 16 ? 16 : hi;
+    return hi > lo ? ((1u << hi) - 1u) & ~((1u << lo) - 1u) : 0u;
+}
+__device__ __forceinline__ unsigned invalid_bits(const CountParams& p, const TileEnds& te, unsigned long long tile, int q) {
+    unsigned inv = range_bits(te.limit - q, 16);
+    const int km1 = (int)p.k - 1;
+    if (te.n <= kTileEnds) {
+        for (int i = 0; i < te.n; ++i) inv |= range_bits(te.rel[i] - km1 - q, te.rel[i] - q);
+    } else {
+        const unsigned long long t0 = p.origin + tile * COUNT_TILE;
+        for (unsigned long long i = te.first; i < p.nseq; ++i) {
+            const long long e = (long long)(__ldg(p.offsets + i + 1) - t0);  // tile-relative, > 0
+            if (e - km1 >= (long long)q + 16) break;
+            inv |= range_bits((int)(e - km1) - q, e - q > 16 ? 16 : (int)e - q);
+        }
+    }
+    return inv;
 }
 
 // word of lane (lane + d) of the 64-word sequence {cur[0..31], nxt[0..31]}
@@ -290,13 +349,19 @@ __global__ void __launch_bounds__(COUNT_THREADS, NK_COUNT_MINBLOCKS) count_kerne
     __shared__ __align__(8) unsigned long long bars[COUNT_STAGES];
     __shared__ unsigned long long tile_of[COUNT_STAGES];
     __shared__ unsigned int halo[COUNT_WARPS][2][3];
+    __shared__ TileEnds tends[COUNT_STAGES];
+    constexpr bool BITMAP = MODE != 5;
+    unsigned valid_starts = 0;  // MODE 5: window starts this thread counted
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < COUNT_STAGES; ++s) mbar_init(&bars[s], 1);
         mbar_fence_init();
         unsigned long long t0 = atomicAdd(p.tile_counter, 1u);
         tile_of[0] = t0;
-        if (t0 < p.ntiles) issue_tile<PACKED>(smem, &bars[0], p, t0);
+        if (t0 < p.ntiles) {
+            issue_tile<PACKED, BITMAP>(smem, &bars[0], p, t0);
+            if (!BITMAP) find_tile_ends(p, t0, &tends[0]);
+        }
     }
     __syncthreads();
 
@@ -310,7 +375,10 @@ __global__ void __launch_bounds__(COUNT_THREADS, NK_COUNT_MINBLOCKS) count_kerne
         if (threadIdx.x == 0) {  // prefetch the next tile into the other stage (consumed at it-1)
             unsigned long long tn = atomicAdd(p.tile_counter, 1u);
             tile_of[s ^ 1u] = tn;
-            if (tn < p.ntiles) issue_tile<PACKED>(smem + (s ^ 1u) * kStageStride, &bars[s ^ 1u], p, tn);
+            if (tn < p.ntiles) {
+                issue_tile<PACKED, BITMAP>(smem + (s ^ 1u) * kStageStride, &bars[s ^ 1u], p, tn);
+                if (!BITMAP) find_tile_ends(p, tn, &tends[s ^ 1u]);
+            }
         }
         mbar_wait(&bars[s], (it >> 1) & 1u);
 
@@ -344,12 +412,30 @@ __global__ void __launch_bounds__(COUNT_THREADS, NK_COUNT_MINBLOCKS) count_kerne
             if (c + 1u < COUNT_CHUNKS_PER_SPAN)
                 nxt = load_codes<CANON, PACKED>(sb, ((span0 + (c + 1u) * COUNT_CHUNK) >> 4) + lane, has_other);
             const unsigned off = span0 + c * COUNT_CHUNK;
-            const unsigned inv16 = bits[(off >> 4) + lane];
-            process_chunk<CANON, MODE, POW2, KHI>(p, wc, cur, nxt, inv16, lane, tile * COUNT_TILE + off + 16u * lane,
+            unsigned inv16;
+            if (BITMAP) {
+                inv16 = bits[(off >> 4) + lane];
+            } else {
+                inv16 = invalid_bits(p, tends[s], tile, (int)(off + 16u * lane));
+                valid_starts += 16u - __popc(inv16);
+            }
+            process_chunk<CANON, (MODE == 5 ? 0 : MODE), POW2, KHI>(p, wc, cur, nxt, inv16, lane, tile * COUNT_TILE + off + 16u * lane,
                                                   reinterpret_cast<unsigned long long*>(smem + kSmemTotal) + warp * COUNT_CHUNK);
             cur = nxt;
         }
         __syncthreads();
+    }
+    if (!BITMAP) {  // the metric's unit: windows counted (the bitmap path's marking kernel does this otherwise)
+        valid_starts = __reduce_add_sync(0xFFFFFFFFu, valid_starts);
+        if (lane == 0 && valid_starts) atomicAdd(p.kmers_out, (unsigned long long)valid_starts);
+    }
+    // the last CTA to leave re-arms the tile scheduler for the next launch
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(p.tile_counter + 1, 1u) == gridDim.x - 1u) {
+            p.tile_counter[0] = 0u;
+            p.tile_counter[1] = 0u;
+        }
     }
 }
 
@@ -459,6 +545,7 @@ static cudaError_t launch_count_c(const CountParams& p, int mode, cudaStream_t s
         case 1: return launch_count_cm<CANON, 1, PACKED>(p, s);
         case 2: return launch_count_cm<CANON, 2, PACKED>(p, s);
         case 4: return launch_count_cm<CANON, 4, PACKED>(p, s);
+        case 5: return launch_count_cm<CANON, 5, PACKED>(p, s);
         default: return launch_count_cm<CANON, 3, PACKED>(p, s);
     }
 }

@@ -27,7 +27,14 @@ namespace nkd {
 
 namespace {
 
-constexpr size_t kPiece = 2u << 20;
+size_t piece_bytes() {
+    static const size_t v = [] {
+        size_t kb = 2048;
+        if (const char* e = getenv("NK_STAGE_PIECE_KB")) { const long t = atol(e); if (t >= 64 && t <= 65536) kb = (size_t)t; }
+        return kb << 10;
+    }();
+    return v;
+}
 
 // CPUs local to the device's PCIe root ("0-15,32-47" style list from sysfs); empty if unknown
 std::vector<int> local_cpus(int device) {
@@ -86,7 +93,7 @@ public:
             std::lock_guard<std::mutex> lk(mu_);
             job_ = Job{src, fd, off, n, dst, after};
             next_.store(0);
-            npieces_ = (n + kPiece - 1) / kPiece;
+            npieces_ = (n + piece_bytes() - 1) / piece_bytes();
             finished_ = 0;
             failed_ = false;
             ++gen_;
@@ -131,9 +138,9 @@ private:
                     cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking) == cudaSuccess &&
                     cudaEventCreateWithFlags(&w.done, cudaEventDisableTiming) == cudaSuccess;
         for (int i = 0; i < 2 && good; ++i) {
-            good = cudaMallocHost((void**)&w.slot[i], kPiece) == cudaSuccess &&
+            good = cudaMallocHost((void**)&w.slot[i], piece_bytes()) == cudaSuccess &&
                    cudaEventCreateWithFlags(&w.ev[i], cudaEventDisableTiming) == cudaSuccess;
-            if (good) memset(w.slot[i], 0, kPiece);  // first touch on this (GPU-local) CPU
+            if (good) memset(w.slot[i], 0, piece_bytes());  // first touch on this (GPU-local) CPU
         }
         unsigned long long seen = 0;
         {
@@ -159,7 +166,7 @@ private:
             while (!bad) {
                 const uint64_t i = next_.fetch_add(1);
                 if (i >= npieces_) break;
-                const uint64_t o = i * kPiece, len = std::min<uint64_t>(kPiece, job.n - o);
+                const uint64_t o = i * piece_bytes(), len = std::min<uint64_t>(piece_bytes(), job.n - o);
                 const int s = k & 1;
                 ++k;
                 if (w.inflight[s]) { cudaEventSynchronize(w.ev[s]); w.inflight[s] = false; }
@@ -175,6 +182,7 @@ private:
                 } else {
                     memcpy(w.slot[s], job.src + o, len);
                 }
+                if (!job.dst) continue;  // host-only measurement of the read ceiling (nk_debug_stage_file)
                 if (cudaMemcpyAsync(job.dst + o, w.slot[s], len, cudaMemcpyHostToDevice, w.stream) != cudaSuccess ||
                     cudaEventRecord(w.ev[s], w.stream) != cudaSuccess) { bad = true; why = "cudaMemcpyAsync"; break; }
                 w.inflight[s] = true;
@@ -213,8 +221,12 @@ private:
 static StagePool* pool_of(nk_counter* h) {
     if (!h->stage_pool) {
         unsigned n = std::thread::hardware_concurrency();
+        // measured on the 16-vCPU B200 boxes (tools/stage_sweep.py, profiles/r02_bench.md): 113 MB of pageable memory
+        // in 8.7 / 4.6 / 2.9 / 4.0 / 4.9 ms with 1 / 2 / 4 / 8 / 12 threads and 2 MiB pieces — beyond four the threads
+        // fight the DMA engine for host memory bandwidth (the slots stop fitting the last-level cache)
+        if (n > 4) n = 4;
         if (const char* e = getenv("NK_STAGE_THREADS")) n = (unsigned)atoi(e);
-        if (n > 12) n = 12;
+        if (n > 32) n = 32;
         if (n < 1) n = 1;
         StagePool* p = new StagePool(h->cfg.device, n);
         if (!p->ok()) { delete p; return nullptr; }
@@ -225,6 +237,7 @@ static StagePool* pool_of(nk_counter* h) {
 
 int stage_to_device(nk_counter* h, const uint8_t* src, int fd, uint64_t off, uint64_t n, unsigned char* dst,
                     cudaEvent_t after, cudaStream_t then) {
+    NvtxRange nvtx("nk:stage (host threads -> pinned slots -> H2D)");
     StagePool* p = pool_of(h);
     if (!p) return fail(NK_ERR_OOM, "cannot create the host staging pool (pinned memory / streams)");
     return p->copy(src, fd, off, n, dst, after, then);
@@ -307,6 +320,7 @@ int parse_file_on_device(nk_counter* h, const char* path, bool* handled, bool* i
         if ((rc = stage_to_device(h, nullptr, fd, 0, size_real, h->d_raw, prev, h->stream)) != NK_OK) break;
         h->last.h2d_bytes += size_real;
         if (add_nl && cudaMemsetAsync(h->d_raw + size_real, '\n', 1, h->stream) != cudaSuccess) { rc = fail(NK_ERR_CUDA, "cudaMemsetAsync"); break; }
+        NvtxRange nvtx("nk:parse (FASTA/FASTQ records on the device)");
         unsigned long long nb = 0, nr = 0;
 #define NK_B(expr) { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { rc = fail(e_ == cudaErrorMemoryAllocation ? NK_ERR_OOM : NK_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); break; } }
         if (!fastq) {
@@ -358,6 +372,40 @@ int parse_file_on_device(nk_counter* h, const char* path, bool* handled, bool* i
 }  // namespace nkd
 
 extern "C" {
+
+// Measurement tap: how fast can this host hand the file's bytes over at all?  host_only_ms: the staging pool
+// preads the whole file into its pinned slots and drops the bytes (no device work); with_h2d_ms: the same with
+// the H2D copies into the raw buffer, waited for.  The file path of nk_process_file cannot beat the second.
+int nk_debug_stage_file(nk_counter* h, const char* path, double* host_only_ms, double* with_h2d_ms) {
+    if (!h || !path || !host_only_ms || !with_h2d_ms) return fail(NK_ERR_BAD_ARG, "null argument");
+    if (is_group(h)) return nk_debug_stage_file(h->group[0], path, host_only_ms, with_h2d_ms);
+    NK_CUDA(cudaSetDevice(h->cfg.device));
+    NK_TRY(resolve(h));
+    const int fd = ::open(path, O_RDONLY);
+    if (fd < 0) return fail(NK_ERR_IO, "cannot open %s", path);
+    struct stat st;
+    if (fstat(fd, &st) != 0 || st.st_size < 1) { ::close(fd); return fail(NK_ERR_IO, "%s: empty or unreadable", path); }
+    const unsigned long long size = (unsigned long long)st.st_size;
+    int rc = grow((void**)&h->d_raw, &h->raw_cap, size + 64);
+    h->fp_valid = false;
+    auto now = [] { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec * 1e3 + t.tv_nsec * 1e-6; };
+    double best0 = 1e30, best1 = 1e30;
+    for (int rep = 0; rep < 4 && rc == NK_OK; ++rep) {
+        cudaStreamSynchronize(h->stream);
+        double t0 = now();
+        rc = stage_to_device(h, nullptr, fd, 0, size, nullptr, nullptr, h->stream);
+        double t1 = now();
+        if (rc != NK_OK) break;
+        rc = stage_to_device(h, nullptr, fd, 0, size, h->d_raw, nullptr, h->stream);
+        cudaStreamSynchronize(h->stream);
+        double t2 = now();
+        if (rep) { best0 = std::min(best0, t1 - t0); best1 = std::min(best1, t2 - t1); }
+    }
+    ::close(fd);
+    *host_only_ms = best0;
+    *with_h2d_ms = best1;
+    return rc;
+}
 
 // Parity tap: parse a plain FASTA / FASTQ file ON THE DEVICE and digest what comes out exactly like
 // nk_debug_fastx_digest digests the host reader's records (FNV-1a-64 over every record's bases + one 0xFF).

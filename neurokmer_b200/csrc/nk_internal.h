@@ -7,11 +7,22 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/neurokmer.h"
 #include "nk_host.h"
 #include "nk_kernels.cuh"
 
 namespace nkd {
+
+// NVTX range over a host-side phase (header-only NVTX v3: a no-op unless a profiler is attached).  The ranges
+// bracket the ENQUEUE of a phase's work; nsys / ncu correlate the kernels launched inside them.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 extern thread_local std::string g_err;
 int fail(int code, const char* fmt, ...);
@@ -170,6 +181,9 @@ struct nk_counter {
     bool fp_valid = false;
     std::string fp_path;
     unsigned long long fp_size = 0, fp_mtime_ns = 0, fp_nbases = 0, fp_nrec = 0;
+    // scalars[0] (spikes fired) / scalars[2] (k-mers) are known to be zero on the device: the fused post kernel
+    // zeroes what it consumed, so a job of resident kernels needs no memset at all
+    bool fired_clean = false, kmers_clean = false;
     bool uniques_whole_input = false;  // group[0] of a multi-GPU group: its uniques pass is handed the whole input again
     bool slice_only = false;  // after a sharded-pool job: currents / v / r / spikes are only defined inside this rank's slice
     bool last_push_zc = false;  // the last host batch was read in place (zero-copy): its kernels hold the caller's buffer
@@ -214,6 +228,7 @@ int get_event(nk_counter* h, cudaEvent_t* out);
 int materialize_zero(nk_counter* h);
 int fold_now(nk_counter* h);
 unsigned char* own_mail(nk_counter* h);
+int zero_kmers(nk_counter* h);
 int count_host_batch(nk_counter* h, const uint8_t* bases, const uint64_t* offsets, uint64_t nseq, PhaseEvents* pe, int sync);
 int count_host_batch_packed(nk_counter* h, const uint32_t* codes, const uint32_t* other, const uint64_t* offsets,
                             uint64_t nseq, PhaseEvents* pe, int sync);

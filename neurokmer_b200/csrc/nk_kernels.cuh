@@ -41,7 +41,15 @@ struct CountParams {
     unsigned long long other_bytes;
     const unsigned int* invalid;  // bit p set => no window starts at p; ntiles*TILE/32 words (+pad)
     unsigned int* acc;            // pool_size u32 batch accumulators
-    unsigned int* tile_counter;   // dynamic tile scheduler cursor (zeroed before launch)
+    unsigned int* tile_counter;   // [0] dynamic tile scheduler cursor, [1] CTAs that finished: both zero before a
+                                  // launch; the last CTA to leave zeroes them again (no memset between launches)
+    // MODE 5 (long sequences, no invalid-start bitmap): the kernel finds the sequence ends itself.
+    //   offsets[0..nseq]: batch-absolute sequence bounds of the sequences that overlap this chunk;
+    //   window starts [origin, origin + nstarts) belong to the chunk (tile 0 starts at `origin`);
+    //   *kmers_out += number of valid window starts counted.
+    const unsigned long long* offsets;
+    unsigned long long nseq, origin, nstarts;
+    unsigned long long* kmers_out;
     unsigned long long ntiles;
     FastMod fm;
     RotMul rm;                    // make_rotmul(): opaque 2^B multipliers (see nk_device.cuh)
@@ -82,7 +90,8 @@ inline unsigned long long count_bitmap_words(unsigned long long nbytes) {
 
 // mode 0: count; 1: emit the debug taps instead of counting; 2: count and append words (exact side
 // table); 3: count with warp-level compaction of the valid window starts (short-read batches);
-// 4: uniques pass (no counting: append the words that map to the neurons of `filter`).
+// 4: uniques pass (no counting: append the words that map to the neurons of `filter`);
+// 5: count WITHOUT the invalid-start bitmap (long sequences: each tile looks its sequence ends up in `offsets`).
 // The grid is persistent: min(ntiles, SMs x resident CTAs of the instantiation).
 cudaError_t launch_count(const CountParams& p, bool canonical, int mode, cudaStream_t s);
 
@@ -174,6 +183,8 @@ struct TopNScratch {
 };
 constexpr int TOPN_BLOCK_ITEMS = 4096;
 constexpr int POST_EXACT_BINS = 2048;  // = the 8 x 256 radix bins of PostParams::hist
+constexpr int POST_MAX_GRID = 1024;   // >= 148 SMs x 6 resident CTAs
+constexpr size_t POST_SCRATCH_BYTES = 8 * sizeof(unsigned long long) + 8 * 256 * sizeof(unsigned int) + POST_MAX_GRID * sizeof(unsigned int);
 constexpr int POST_SEG_ITEMS = 1024;  // segment of the fused post kernel's ordered phases (block_counts is sized for it)
 constexpr unsigned long long TOPN_MAX_N = 1ull << 20;
 cudaError_t launch_topn(const unsigned long long* spikes, unsigned long long pool, unsigned long long n,
@@ -191,8 +202,10 @@ struct PostParams {
     unsigned long long n;            // rows wanted, 1..2048 and <= pool
     int passes;                      // radix digits to visit (from the host-side spike bound)
     int single_pass;                 // 1: every total is < POST_EXACT_BINS: one exact histogram instead of radix passes
-    unsigned int* hist;              // passes*256 bins, zeroed
-    unsigned long long* ctrl;        // [0] gather cursor, zeroed
+    // scratch, all-zero at launch and left all-zero by the kernel (POST_SCRATCH_BYTES, see post_scratch_*):
+    unsigned int* hist;              // 8 * 256 bins
+    unsigned long long* ctrl;        // 8 u64: [0] gather cursor, [1] error, [2] finished blocks, [4..6] block 0's time stamps
+    unsigned int* block_ties;        // POST_MAX_GRID: per block, (its number of ties) + 1 once published
     unsigned int* seg_counts;        // ceil(pool/4096)
     unsigned long long* out_idx;     // >= 2048
     unsigned long long* out_spikes;  // >= 2048

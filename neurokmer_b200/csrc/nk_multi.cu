@@ -120,6 +120,7 @@ int gather_to_leader(nk_counter* g) {
 }
 
 int end_sliced(nk_counter* g, bool skip_zero) {
+    NvtxRange nvtx("nk:exchange (multi-GPU group: slice reduce/LIF/top-N over peer memory + pack merge)");
     const int n = (int)g->group.size();
     nk_counter* c0 = g->group[0];
     for (int r = 0; r < n; ++r) {

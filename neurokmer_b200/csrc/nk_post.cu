@@ -80,6 +80,52 @@ __global__ void dist_signal_kernel(PeerMail pm, int world, int rank, int which, 
     st_release_sys(reinterpret_cast<unsigned long long*>(pm.mail[r]) + which * DIST_MAX_WORLD + rank, epoch);
 }
 
+// block-wide: s_pick <- the bin (walking DOWN from the largest total) that holds the `rank`-th largest value
+// of the POST_EXACT_BINS-bin histogram `hist` (shared memory copy); returns through refs the value, how many
+// totals are strictly greater, and how many of the ties are still needed
+__device__ __forceinline__ void select_from_exact_hist(const unsigned* hist, unsigned long long n, unsigned long long* s_above,
+                                                       unsigned* s_part, unsigned* s_pick, unsigned long long& T,
+                                                       unsigned long long& gt, unsigned long long& need) {
+    const unsigned tid = threadIdx.x;
+    constexpr unsigned PER = POST_EXACT_BINS / PT;  // thread t owns the bins [8t, 8t+8)
+    unsigned part = 0;
+    for (unsigned b = 0; b < PER; ++b) part += hist[tid * PER + b];
+    s_part[tid] = part;
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long run = 0;
+        for (int x = PT - 1; x >= 0; --x) { s_above[x] = run; run += s_part[x]; }
+    }
+    __syncthreads();
+    if (s_above[tid] < n && n <= s_above[tid] + part) *s_pick = tid;
+    __syncthreads();
+    const unsigned c = *s_pick;
+    unsigned long long run = s_above[c];
+    unsigned long long prefix = 0;
+    for (int b = (int)PER - 1; b >= 0; --b) {
+        const unsigned hb = hist[c * PER + b];
+        if (run < n && n <= run + hb) { prefix = c * PER + b; break; }
+        run += hb;
+    }
+    T = prefix;
+    gt = run;
+    need = n - run;
+    __syncthreads();
+}
+
+// Phase structure (single-histogram case: every spike total < POST_EXACT_BINS, which the reference's parameters
+// guarantee — a call adds at most 334):
+//   1  every block owns a CONTIGUOUS neuron range: fold + LIF table look-up + write-back, and a shared-memory
+//      histogram of the new totals that is (a) added to the global histogram and (b) kept;
+//      -- the ONE grid barrier --
+//   2  every block selects the n-th largest total T from the global histogram, takes its OWN number of ties from
+//      the histogram it kept, publishes it, and sums the published counts of the blocks before it (they are all
+//      resident: a short spin, no barrier);
+//   3  only blocks that hold a total > T or one of the `need` lowest-index ties re-read their range and emit rows;
+//   4  the last block to finish (atomic ticket) sorts the n rows, packs the result, delivers it (multi-GPU), and
+//      zeroes the scratch so that the next launch needs no memset.
+// Round 1 ran four grid barriers and two more passes over the pool here (profiles/r01_post_kernel_ncu.md: 8.1 barrier
+// stall cycles per issued instruction).  Totals beyond the single histogram take the radix passes below (rare).
 __global__ void __launch_bounds__(PT, 3) post_kernel(const PostParams q) {
     cg::grid_group grid = cg::this_grid();
     __shared__ unsigned int s_hist[POST_EXACT_BINS];  // 256 radix bins, or one bin per spike total (single pass)
@@ -87,7 +133,9 @@ __global__ void __launch_bounds__(PT, 3) post_kernel(const PostParams q) {
     __shared__ unsigned int s_warp[PT / 32];
     __shared__ unsigned long long s_red[PT / 32];
     __shared__ unsigned int s_pick;
+    __shared__ unsigned int s_part[PT];
     __shared__ unsigned long long s_idx[2048], s_spk[2048];
+    __shared__ int s_last;
     const unsigned tid = threadIdx.x;
     const LifParams& p = q.lif;
     const unsigned long long nseg = (p.pool + SEG - 1) / SEG;
@@ -116,10 +164,7 @@ __global__ void __launch_bounds__(PT, 3) post_kernel(const PostParams q) {
     const unsigned spill_mask = q.npeers ? s_spill_mask : 0u;
     if (blockIdx.x == 0 && tid == 0) t_ready = global_ns();
 
-    // ---- phase 1: fold + LIF table apply + histogram of the top digit of the new spike totals ----
-    // q.single_pass: the host-side bound says every total is < POST_EXACT_BINS (the reference's parameters cap a
-    // call at 334 spikes), so phase 1 histograms the totals THEMSELVES and the n-th largest value falls out of
-    // that one histogram: no second pass over the pool, one grid barrier less.
+    // ---- phase 1: fold + LIF table apply + histogram of the new spike totals --------------------------------
     const bool single = q.single_pass != 0;
     for (unsigned b = tid; b < POST_EXACT_BINS; b += PT) s_hist[b] = 0;
     __syncthreads();
@@ -136,14 +181,20 @@ __global__ void __launch_bounds__(PT, 3) post_kernel(const PostParams q) {
     const float* __restrict__ tv = q.table.v;
     const unsigned int* __restrict__ tr = q.table.r;
     const unsigned long long gthreads = (unsigned long long)gridDim.x * PT;
+    // this block's contiguous neuron range (a multiple of ITEMS neurons, so a thread's ITEMS consecutive neurons
+    // of phase 3 never straddle two blocks)
+    unsigned long long per_block = (p.pool + gridDim.x - 1) / gridDim.x;
+    per_block = (per_block + ITEMS - 1) / ITEMS * ITEMS;
+    const unsigned long long my_lo = (unsigned long long)blockIdx.x * per_block < p.pool ? (unsigned long long)blockIdx.x * per_block : p.pool;
+    const unsigned long long my_hi = my_lo + per_block < p.pool ? my_lo + per_block : p.pool;
     {
-        for (unsigned long long i0 = (unsigned long long)blockIdx.x * PT + tid; i0 < p.pool; i0 += gthreads * B) {
+        for (unsigned long long i0 = my_lo + tid; i0 < my_hi; i0 += (unsigned long long)PT * B) {
             unsigned long long count[B], total[B];
             bool ok[B];
 #pragma unroll
             for (int u = 0; u < B; ++u) {
-                const unsigned long long i = i0 + (unsigned long long)u * gthreads;
-                ok[u] = i < p.pool;
+                const unsigned long long i = i0 + (unsigned long long)u * PT;
+                ok[u] = i < my_hi;
                 count[u] = (ok[u] && p.fold_mode != 2) ? currents[i] : 0ull;
                 if (q.npeers) {
                     // reduce-scatter by peer loads: this neuron's count on every rank (NVLink P2P)
@@ -171,7 +222,7 @@ __global__ void __launch_bounds__(PT, 3) post_kernel(const PostParams q) {
             }
 #pragma unroll
             for (int u = 0; u < B; ++u) {
-                const unsigned long long i = i0 + (unsigned long long)u * gthreads;
+                const unsigned long long i = i0 + (unsigned long long)u * PT;
                 if (!ok[u]) continue;
                 if (p.fold_mode) {
                     if (!q.npeers) acc[i] = 0u;  // sharded: peers may still be reading; the host clears it later
@@ -209,41 +260,104 @@ __global__ void __launch_bounds__(PT, 3) post_kernel(const PostParams q) {
         atomicAdd(&q.hist[top * 256 + tid], s_hist[tid]);
     }
     grid.sync();
-    if (blockIdx.x == 0 && tid == 0) t_phase1 = global_ns();
-
-    // ---- phase 2: MSB-first radix select of the n-th largest total (every block redundantly) ----
-    unsigned long long prefix = 0, rank = q.n, gt = 0;
-    if (single) {
-        // thread t owns the bins [8t, 8t+8); walk down from the largest total
-        constexpr unsigned PER = POST_EXACT_BINS / PT;
-        unsigned part = 0;
-        for (unsigned b = 0; b < PER; ++b) {
-            const unsigned hb = __ldcg(&q.hist[tid * PER + b]);
-            s_hist[tid * PER + b] = hb;
-            part += hb;
-        }
-        __shared__ unsigned int s_part[PT];
-        s_part[tid] = part;
-        __syncthreads();
-        if (tid == 0) {
-            unsigned long long run = 0;
-            for (int x = PT - 1; x >= 0; --x) { s_above[x] = run; run += s_part[x]; }
-        }
-        __syncthreads();
-        if (s_above[tid] < rank && rank <= s_above[tid] + part) s_pick = tid;
-        __syncthreads();
-        const unsigned c = s_pick;
-        unsigned long long run = s_above[c];
-        for (int b = (int)PER - 1; b >= 0; --b) {
-            const unsigned hb = s_hist[c * PER + b];
-            if (run < rank && rank <= run + hb) { prefix = c * PER + b; break; }
-            run += hb;
-        }
-        gt = run;
-        rank -= run;
-        __syncthreads();
+    if (blockIdx.x == 0 && tid == 0) {
+        t_phase1 = global_ns();
+        q.ctrl[4] = t_start; q.ctrl[5] = t_ready; q.ctrl[6] = t_phase1;  // for whichever block packs the result
     }
-    for (int d = single ? -1 : top; d >= 0; --d) {
+
+    if (single) {
+        // ---- phase 2: select T from the global histogram; ties of the blocks before this one -----------------
+        unsigned* s_ghist = reinterpret_cast<unsigned*>(s_idx);  // s_idx is not needed before the final sort
+        for (unsigned b = tid; b < POST_EXACT_BINS; b += PT) s_ghist[b] = __ldcg(&q.hist[b]);
+        __syncthreads();
+        unsigned long long T, gt, need;
+        select_from_exact_hist(s_ghist, q.n, s_above, s_part, &s_pick, T, gt, need);
+        const unsigned my_ties = s_hist[T];                       // this block's own range (kept from phase 1)
+        unsigned my_gt = 0;
+        for (unsigned b = (unsigned)T + 1 + tid; b < POST_EXACT_BINS; b += PT) my_gt += s_hist[b];
+        my_gt = block_sum(my_gt, s_warp);
+        if (tid == 0) {
+            // published as count + 1 (0 = not yet); release so that a reader that sees it sees a finished value
+            unsigned* slot = q.block_ties + blockIdx.x;
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(slot), "r"(my_ties + 1u) : "memory");
+        }
+        unsigned long long ties_before = 0;
+        if (my_ties != 0) {  // (a block without ties has no use for the prefix)
+            for (unsigned bb = tid; bb < blockIdx.x; bb += PT) {
+                unsigned v;
+                do {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(q.block_ties + bb) : "memory");
+                } while (v == 0u);
+                ties_before += v - 1u;
+            }
+            for (int o = 16; o > 0; o >>= 1) ties_before += __shfl_down_sync(0xFFFFFFFFu, ties_before, o);
+            if ((tid & 31) == 0) s_red[tid >> 5] = ties_before;
+            __syncthreads();
+            ties_before = 0;
+            for (int w = 0; w < PT / 32; ++w) ties_before += s_red[w];
+            __syncthreads();
+        }
+        // ---- phase 3: ordered gather, only where this block contributes rows ---------------------------------
+        if (my_gt != 0 || (my_ties != 0 && ties_before < need)) {
+            unsigned long long seg_prefix = ties_before;
+            for (unsigned long long base0 = my_lo; base0 < my_hi; base0 += SEG) {
+                // thread t owns ITEMS consecutive neurons (index order)
+                const unsigned long long base = base0 + (unsigned long long)tid * ITEMS;
+                unsigned long long v[ITEMS];
+                unsigned eq = 0;
+#pragma unroll
+                for (int it = 0; it < ITEMS; ++it) {
+                    const unsigned long long i = base + it;
+                    v[it] = i < my_hi ? spikes[i] : 0ull;
+                    if (i < my_hi && v[it] == T) ++eq;
+                    if (i < my_hi && v[it] > T) {
+                        const unsigned long long slot = atomicAdd(&q.ctrl[0], 1ull);
+                        q.out_idx[slot] = i;
+                        q.out_spikes[slot] = v[it];
+                    }
+                }
+                if (seg_prefix < need) {  // block-uniform: only while ties are still wanted
+                    s_part[tid] = eq;
+                    __syncthreads();
+                    for (int o = 1; o < PT; o <<= 1) {
+                        const unsigned a = tid >= (unsigned)o ? s_part[tid - o] : 0u;
+                        __syncthreads();
+                        s_part[tid] += a;
+                        __syncthreads();
+                    }
+                    const unsigned seg_ties = s_part[PT - 1];
+                    unsigned long long r = seg_prefix + (s_part[tid] - eq);
+                    if (eq != 0 && r < need) {
+#pragma unroll
+                        for (int it = 0; it < ITEMS; ++it) {
+                            const unsigned long long i = base + it;
+                            if (i < my_hi && v[it] == T) {
+                                if (r < need) {
+                                    q.out_idx[gt + r] = i;
+                                    q.out_spikes[gt + r] = T;
+                                }
+                                ++r;
+                            }
+                        }
+                    }
+                    __syncthreads();
+                    seg_prefix += seg_ties;
+                } else if (my_gt == 0) {
+                    break;  // nothing above T in this range and all wanted ties are placed
+                }
+            }
+        }
+        // ---- the last block to get here does the rest --------------------------------------------------------
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_last = atomicAdd(&q.ctrl[2], 1ull) == (unsigned long long)gridDim.x - 1ull ? 1 : 0;
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+    } else {
+    // ---- radix passes (totals beyond the single histogram): MSB-first select, every block redundantly ----
+    unsigned long long prefix = 0, rank = q.n, gt = 0;
+    for (int d = top; d >= 0; --d) {
         if (d != top) {
             s_hist[tid] = 0;
             __syncthreads();
@@ -283,7 +397,7 @@ __global__ void __launch_bounds__(PT, 3) post_kernel(const PostParams q) {
     }
     const unsigned long long T = prefix, need = rank;
 
-    // ---- phase 3: ties per segment (each block owns a contiguous range of segments) ----
+    // ties per segment (each block owns a contiguous range of segments)
     const unsigned long long seg_per = (nseg + gridDim.x - 1) / gridDim.x;
     const unsigned long long seg_lo = (unsigned long long)blockIdx.x * seg_per;
     const unsigned long long seg_hi = seg_lo + seg_per < nseg ? seg_lo + seg_per : nseg;
@@ -299,7 +413,7 @@ __global__ void __launch_bounds__(PT, 3) post_kernel(const PostParams q) {
     }
     grid.sync();
 
-    // ---- phase 4: ordered gather: every total > T, and the `need` lowest-index totals == T ----
+    // ordered gather: every total > T, and the `need` lowest-index totals == T
     if (seg_lo < seg_hi) {
         unsigned long long before_me = 0;  // ties in the segments before this block's range
         for (unsigned long long s = tid; s < seg_lo; s += PT) before_me += __ldcg(&q.seg_counts[s]);
@@ -355,12 +469,14 @@ __global__ void __launch_bounds__(PT, 3) post_kernel(const PostParams q) {
         }
     }
     grid.sync();
-
-    // ---- phase 5: block 0 sorts the n candidates (spikes desc, idx asc) and packs the result ----
     if (blockIdx.x != 0) return;
+    }  // radix passes
+
+    // ---- final phase (one block): sort the n candidates (spikes desc, idx asc) and pack the result ----
     const unsigned n = (unsigned)q.n;
     unsigned N = 1;
     while (N < n) N <<= 1;
+    __syncthreads();
     for (unsigned i = tid; i < N; i += PT) {
         s_idx[i] = i < n ? __ldcg(&q.out_idx[i]) : ~0ull;
         s_spk[i] = i < n ? __ldcg(&q.out_spikes[i]) : 0ull;
@@ -394,13 +510,13 @@ __global__ void __launch_bounds__(PT, 3) post_kernel(const PostParams q) {
         q.pack[PACK_HDR + n + i] = s_spk[i];
     }
     if (tid == 0) {
-        q.pack[0] = *((volatile unsigned long long*)p.total_new);
-        q.pack[1] = *((volatile unsigned long long*)&q.ctrl[1]);  // 1: a peer's "counting finished" signal timed out
-        q.pack[2] = *((volatile unsigned long long*)q.kmers);
+        q.pack[0] = __ldcg(p.total_new);
+        q.pack[1] = __ldcg(&q.ctrl[1]);  // 1: a peer's "counting finished" signal timed out
+        q.pack[2] = __ldcg(q.kmers);
         q.pack[3] = n;
-        q.pack[4] = t_start;
-        q.pack[5] = t_ready;
-        q.pack[6] = t_phase1;
+        // the stamps of block 0; when another block finishes last they travel through the scratch
+        if (blockIdx.x == 0) { q.pack[4] = t_start; q.pack[5] = t_ready; q.pack[6] = t_phase1; }
+        else { q.pack[4] = __ldcg(&q.ctrl[4]); q.pack[5] = __ldcg(&q.ctrl[5]); q.pack[6] = __ldcg(&q.ctrl[6]); }
         q.pack[7] = global_ns();
     }
     if (q.wait_flags) {
@@ -417,6 +533,12 @@ __global__ void __launch_bounds__(PT, 3) post_kernel(const PostParams q) {
         if (tid < (unsigned)q.npeers)
             st_release_sys(reinterpret_cast<unsigned long long*>(q.peer_mail[tid]) + DIST_MAX_WORLD + q.rank, q.epoch);
     }
+    // leave the scratch as the next launch wants it: no memsets between jobs
+    __syncthreads();
+    for (unsigned b = tid; b < POST_EXACT_BINS; b += PT) q.hist[b] = 0u;
+    for (unsigned b = tid; b < POST_MAX_GRID; b += PT) q.block_ties[b] = 0u;
+    if (tid < 8) q.ctrl[tid] = 0ull;
+    if (tid == 0) { *p.total_new = 0ull; *const_cast<unsigned long long*>(q.kmers) = 0ull; }
 }
 
 // one block: sum the scalars, sort the union of the per-rank rows, keep the best n_out
@@ -534,6 +656,7 @@ cudaError_t launch_post(const PostParams& q, int max_grid, cudaStream_t s) {
     const unsigned long long nseg = (q.lif.pool + SEG - 1) / SEG;
     int grid = (int)(nseg < (unsigned long long)max_grid ? nseg : (unsigned long long)max_grid);
     if (grid < 1) grid = 1;
+    if (grid > POST_MAX_GRID) grid = POST_MAX_GRID;
     void* args[] = {(void*)&q};
     return cudaLaunchCooperativeKernel((const void*)post_kernel, dim3(grid), dim3(PT), args, 0, s);
 }

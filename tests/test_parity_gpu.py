@@ -1515,3 +1515,30 @@ def test_config2_full_size_against_oracle():
     g = SpikingKmerCounter(k, 1.0, 0.95, 2, 1.0, pool, True, devices=[0, 0, 0])
     g.stream_begin(); g.stream_push(pin.array, offsets); g.stream_end()
     assert_topn_equal(g, o, 20); assert_state_equal(g, o)
+
+
+@pytest.mark.parametrize("k,pool,canonical", [(31, 2_000_000, True), (21, 99_991, False), (5, 4096, True), (32, 65_537, True)])
+def test_long_sequence_mode_without_bitmap_equals_bitmap_mode(coracle, k, pool, canonical, monkeypatch):
+    """Long-sequence batches are counted without the invalid-start bitmap (every tile looks its sequence ends up
+    in the offsets); NK_BITMAP=1 forces the bitmap kernels.  Both must equal the oracle, including tiles that
+    hold more sequence ends than the per-tile list (a run of tiny sequences inside a long-sequence batch),
+    sequences shorter than k, ends exactly on tile boundaries, and a batch that ends mid-tile."""
+    from neurokmer_b200 import PinnedBuffer, flatten
+    rng = np.random.default_rng(k + pool)
+    lens = [300_000, 4096 * 3, k - 1, 1, 0, 4096 - 7, 7, 20_000] + [int(x) for x in rng.integers(0, 40, size=60)] + \
+           [250_000, k, k + 1, 4096 * 5 + 1, 150_000]
+    seqs = [random_dna(rng, n, 0.002, 0.01) for n in lens]
+    bases, offsets = flatten(seqs)
+    assert bases.size / len(seqs) >= 2048          # mean length: the long-sequence path
+    exp, tot = coracle.accumulate(bases, offsets, k, pool, canonical, threads=4)
+    pin = PinnedBuffer(bases.size); pin.array[:] = bases
+    for env in (None, "1"):
+        if env:
+            monkeypatch.setenv("NK_BITMAP", env)
+        c = make(k, pool, canonical)
+        for src in (bases, pin.array):
+            c.process_batch(src, offsets)
+            np.testing.assert_array_equal(c.currents(), exp)
+            assert c.timings()["kmers"] == tot
+        c.close()
+    monkeypatch.delenv("NK_BITMAP", raising=False)

@@ -387,6 +387,8 @@ def gpu_arm(args):
     staged_now = {"nb": nb, "nseq": nseq}
 
     def job_resident():
+        """everything of the job is ENQUEUED here, the result pack's D2H copy included; the caller stops the device
+        clock behind it and only then reads the rows on the host (read_result)"""
         t = [time.perf_counter()]
         c.reset(); t.append(time.perf_counter())
         c.stream_begin(); t.append(time.perf_counter())
@@ -396,9 +398,8 @@ def gpu_arm(args):
         else:
             t.append(time.perf_counter())
             c.stream_finish(); t.append(time.perf_counter())
-        top = c.top_abundant_neurons(TOPN); t.append(time.perf_counter())
         trace.append(np.diff(t) * 1e3)
-        return top
+        return None
 
     def host_job(push):
         def job():
@@ -438,6 +439,8 @@ def gpu_arm(args):
             top = job()
             with torch.cuda.stream(stream):
                 e1.record(stream)
+            if top is None:                       # resident leg: the rows are read after the device clock stopped
+                top = c.top_abundant_neurons(TOPN)
             e1.synchronize()
             wall = (time.perf_counter() - t0) * 1e3
             per_step.append((e0.elapsed_time(e1), wall))
@@ -495,6 +498,28 @@ def gpu_arm(args):
             os.unlink(file_path)
         except OSError:
             pass
+
+    # ---- what the box's host links can do at all: every rank copies its pinned shard to its GPU at the same time ----
+    h2d_ceiling = None
+    if not args.no_e2e:
+        src = torch.from_numpy(pinned.array)      # the library's pinned allocation (cudaMallocHost)
+        dst = torch.empty(nb, dtype=torch.uint8, device="cuda")
+        best = 1e9
+        for rep in range(6):
+            barrier()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            dst.copy_(src, non_blocking=True)
+            a1.record()
+            a1.synchronize()
+            tt = torch.tensor([a0.elapsed_time(a1)], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            if rep:
+                best = min(best, float(tt[0]))
+        h2d_ceiling = {"ms_slowest_rank": best, "gbs_per_rank": nb / (best * 1e-3) / 1e9, "gbs_aggregate": world * nb / (best * 1e-3) / 1e9,
+                       "what": "all ranks cudaMemcpyAsync their pinned 113 MB shard to their GPU simultaneously (max over ranks)"}
+        del dst
 
     # ---- strong scaling (N > 1): the 113 Mbase job itself, cut N ways ------------------------------------------
     strong = None
@@ -680,6 +705,7 @@ def gpu_arm(args):
             #              (reduce-scatter) + LIF look-up + top-N histogram; at N=1 the same phase on local memory
             #   merge_ms   merging the ranks' result packs
             "exchange": {"wait_ms": wait_ms, "reduce_ms": reduce_ms, "merge_ms": merge_ms, "post_kernel_ms": post_ms,
+                         "h2d_ceiling": h2d_ceiling,
                          "count_ms_slowest_rank": count_ms_max,
                          "bytes_read_from_peers_per_rank": int(phases[-1]["exch_bytes"])},
             "collective": ("none" if world == 1 else (

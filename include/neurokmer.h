@@ -98,7 +98,8 @@ typedef struct nk_timings {
     float exch_wait_ms;     /* waiting for the peers: their "finished counting" flags (slice kernel) + their result
                              * packs (merge kernel) — rank skew, not bytes */
     float exch_reduce_ms;   /* the phase that reads this rank's neuron slice of EVERY rank's counts over NVLink peer
-                             * memory (reduce-scatter) fused with the LIF look-up and the top-N histogram */
+                             * memory (reduce-scatter) fused with the LIF look-up and the top-N histogram; on a single
+                             * GPU the same phase over local memory (the baseline the exchange is compared with) */
     float merge_ms;         /* merging the ranks' result packs */
     uint64_t exch_bytes;    /* bytes this rank read from peer memory for the job */
 } nk_timings;

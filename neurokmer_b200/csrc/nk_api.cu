@@ -830,9 +830,9 @@ int resolve(nk_counter* h) {
         const unsigned long long* t = h->h_pack + 4;
         auto ms = [](unsigned long long a, unsigned long long b) { return b > a ? (float)((double)(b - a) * 1e-6) : 0.f; };
         h->last.post_ms = ms(t[0], t[3]);
+        h->last.exch_reduce_ms = ms(t[1], t[2]);  // single GPU: the same phase on local memory
         if (h->dist_job) {
             h->last.exch_wait_ms = ms(t[0], t[1]) + ms(t[4], t[5]);
-            h->last.exch_reduce_ms = ms(t[1], t[2]);
             h->last.merge_ms = ms(t[5], t[6]);
             // peer memory read by this rank's slice kernel (u32 counts of its slice on every OTHER rank) + the packs
             h->last.exch_bytes = (unsigned long long)(h->dist_world - 1) *

@@ -237,12 +237,15 @@ class SpikingKmerCounter:
         check(self._L.nk_enable_exact_counts(self._h, int(on)))
 
     def exact_table(self) -> Tuple[np.ndarray, np.ndarray]:
-        """(sorted k-mer words, counts) — the reference's `counts` map."""
+        """(k-mer words, counts) — the reference's `counts` map.  The library hands the table out grouped by neuron
+        range (a hash map has no order); it is put in ascending word order here for the caller's convenience."""
         n = C.c_uint64()
         check(self._L.nk_exact_table_size(self._h, C.byref(n)))
         keys, counts = np.zeros(max(n.value, 1), np.uint64), np.zeros(max(n.value, 1), np.uint32)
         check(self._L.nk_copy_exact_table(self._h, keys.ctypes.data, counts.ctypes.data))
-        return keys[: n.value], counts[: n.value]
+        keys, counts = keys[: n.value], counts[: n.value]
+        order = np.argsort(keys, kind="stable")
+        return keys[order], counts[order]
 
     def kmer_per_neuron(self) -> np.ndarray:
         return self._copy(self._L.nk_copy_uniques, np.uint32)

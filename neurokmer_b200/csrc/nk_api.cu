@@ -235,6 +235,7 @@ int count_chunk(nk_counter* h, DevBuf& b, const unsigned long long* d_offsets, u
     if (h->exact) {
         NK_CUDA(nk::exact_reserve_words(h->xt, nstarts, h->stream));
         p.words = h->xt.words;
+        p.widx = h->xt.widx;
         p.words_cursor = h->xt.cursor;
     }
     p.offsets = d_offsets + seq_lo;
@@ -512,6 +513,7 @@ int uniques_chunk(nk_counter* h, DevBuf& b, const unsigned long long* d_offsets,
         p.k = h->cfg.k;
         p.filter = h->d_filter;
         p.words = h->ut.words;
+        p.widx = h->ut.widx;
         p.words_cursor = h->ut.cursor;
         p.words_cap = h->ut.words_cap;
         NK_CUDA(nk::launch_count(p, h->cfg.use_canonical != 0, 4, h->stream));
@@ -882,7 +884,7 @@ int fold_and_simulate(nk_counter* h, bool skip_zero, PhaseEvents& pe, bool with_
     NK_CUDA(cudaEventRecord(pe.lif1, h->stream));
     if (h->exact) {  // counts.clear() + refill, kmer_per_neuron rebuilt (:157-172, :426-427, :467-473)
         cudaError_t e = nk::exact_finalize(h->xt, h->fm, h->cfg.pool_size, std::min(64u, 2u * h->cfg.k), false, h->stream);
-        if (e == cudaErrorInvalidValue) return fail(NK_ERR_UNSUPPORTED, "exact counts: more than 2^31 windows in one call");
+        if (e == cudaErrorInvalidValue) return fail(NK_ERR_UNSUPPORTED, "exact counts: the words could not be partitioned into buckets that fit the on-chip tables");
         NK_CUDA(e);
     }
     return NK_OK;
@@ -1843,7 +1845,7 @@ int nk_get_count(nk_counter* h, uint64_t kmer, uint32_t* count, int32_t* found) 
     *count = 0;
     *found = 0;
     if (!h->xt.valid || h->xt.n_keys == 0) return NK_OK;
-    NK_CUDA(nk::exact_lookup(h->xt, kmer, h->scalars + 4, h->stream));
+    NK_CUDA(nk::exact_lookup(h->xt, h->fm, kmer, h->scalars + 4, h->stream));
     NK_CUDA(cudaMemcpyAsync(h->h_scalars + 4, h->scalars + 4, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
     NK_CUDA(cudaStreamSynchronize(h->stream));
     *found = (int32_t)h->h_scalars[4];
@@ -1868,9 +1870,18 @@ int nk_copy_exact_table(nk_counter* h, uint64_t* keys, uint32_t* counts) {
     NK_TRY(resolve(h));
     const unsigned long long n = h->xt.valid ? h->xt.n_keys : 0;
     if (n == 0) return NK_OK;
-    if (keys) NK_CUDA(cudaMemcpyAsync(keys, h->xt.keys, n * 8, cudaMemcpyDeviceToHost, h->stream));
-    if (counts) NK_CUDA(cudaMemcpyAsync(counts, h->xt.counts, n * 4, cudaMemcpyDeviceToHost, h->stream));
-    NK_CUDA(cudaStreamSynchronize(h->stream));
+    // the table lives bucket by bucket: compact it into dense device arrays, then copy those out
+    unsigned long long* dk = nullptr;
+    unsigned int* dc = nullptr;
+    if (keys) NK_CUDA(cudaMalloc(&dk, n * 8));
+    if (counts && cudaMalloc(&dc, n * 4) != cudaSuccess) { cudaFree(dk); return fail(NK_ERR_OOM, "cudaMalloc(exact table copy)"); }
+    cudaError_t e = nk::exact_dense_copy(h->xt, dk, dc, nullptr, h->stream);
+    if (e == cudaSuccess && keys) e = cudaMemcpyAsync(keys, dk, n * 8, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess && counts) e = cudaMemcpyAsync(counts, dc, n * 4, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(dk);
+    cudaFree(dc);
+    NK_CUDA(e);
     return NK_OK;
 }
 
@@ -2514,7 +2525,7 @@ static int uniques_begin(nk_counter* h, uint64_t top_n) {
 static int uniques_end(nk_counter* h) {
     h->uniques_open = false;
     cudaError_t e = nk::exact_finalize(h->ut, h->fm, h->cfg.pool_size, std::min(64u, 2u * h->cfg.k), false, h->stream);
-    if (e == cudaErrorInvalidValue) return fail(NK_ERR_UNSUPPORTED, "uniques pass: more than 2^31 collected windows");
+    if (e == cudaErrorInvalidValue) return fail(NK_ERR_UNSUPPORTED, "uniques pass: the collected words could not be partitioned");
     NK_CUDA(e);
     const uint64_t n = h->row_idx.size();
     if (n) {

@@ -211,6 +211,7 @@ __device__ __forceinline__ void process_chunk(const CountParams& p, const Window
     constexpr bool EMIT = MODE == 1;
     // MODE 2: reserve this warp's slots in the word array with ONE atomic per 512-position chunk
     unsigned long long* wslot = nullptr;
+    unsigned int* islot = nullptr;
     if (MODE == 2) {
         const unsigned mine = 16u - __popc(inv16 & 0xFFFFu);
         unsigned incl = mine;
@@ -223,6 +224,7 @@ __device__ __forceinline__ void process_chunk(const CountParams& p, const Window
         if (lane == 31) base = atomicAdd(p.words_cursor, (unsigned long long)incl);
         base = __shfl_sync(0xFFFFFFFFu, base, 31);
         wslot = p.words + base + (incl - mine);
+        islot = p.widx + base + (incl - mine);
     }
     constexpr int kUnroll = NK_COUNT_UNROLL;
     // word of window j of this lane (canonical min, or pack_kmer) — pure function of the code words
@@ -302,10 +304,10 @@ __device__ __forceinline__ void process_chunk(const CountParams& p, const Window
             // uniques pass: keep the words that map to a neuron of the filter (rare: a few rows of millions)
             if (!bad && ((__ldg(p.filter + (idx >> 5)) >> (idx & 31u)) & 1u)) {
                 const unsigned long long slot = atomicAdd(p.words_cursor, 1ull);
-                if (slot < p.words_cap) p.words[slot] = word;
+                if (slot < p.words_cap) { p.words[slot] = word; p.widx[slot] = idx; }
             }
         } else {
-            if (MODE == 2 && !bad) *wslot++ = word;
+            if (MODE == 2 && !bad) { *wslot++ = word; *islot++ = idx; }
 #ifdef NK_EXP_NORED
             // diagnostic build only (tools/variants.sh): no pool update, keep the value alive
             if (idx == 0xFFFFFFFFu) p.acc[0] = bad;

@@ -56,6 +56,7 @@ struct CountParams {
     unsigned int k;
     // exact side table (MODE 2 instantiation only): every counted word is appended here
     unsigned long long* words;
+    unsigned int* widx;           // the neuron index of every appended word, parallel to `words`
     unsigned long long* words_cursor;
     // uniques pass (MODE 4 instantiation only): nothing is counted; the words of the windows whose neuron
     // has its bit set in `filter` (pool_size bits) are appended while the cursor stays below words_cap
@@ -268,17 +269,28 @@ cudaError_t launch_merge_packs(const unsigned long long* gathered, int world, in
                                unsigned long long n_out, unsigned long long* pack_out, cudaStream_t s);
 
 // exact side tables (nk_exact.cu)
+struct BucketPlan {
+    unsigned int neurons_per_bucket = 1;   // consecutive neurons that share a bucket ...
+    unsigned int splits = 1;               // ... or sub-buckets per neuron (pools with few neurons), by a mix of the word
+    unsigned long long nbuckets = 0;
+};
 struct ExactTable {
-    unsigned long long* words = nullptr;   // appended by the count kernel
+    // appended by the count kernel (mode 2 / 4): the word and the neuron index of every window
+    unsigned long long* words = nullptr;
+    unsigned int* widx = nullptr;
     unsigned long long words_cap = 0, words_bound = 0;
-    unsigned long long* cursor = nullptr;  // [0] append cursor, [1] scratch (#runs)
-    unsigned long long* alt = nullptr;  unsigned long long alt_cap = 0;
-    void* tmp = nullptr;                unsigned long long tmp_cap = 0;
-    unsigned long long* rk = nullptr;   unsigned long long rk_cap = 0;
-    void* rc = nullptr;                 unsigned long long rc_cap = 0;
-    unsigned long long* keys = nullptr; unsigned long long keys_cap = 0;   // sorted distinct words
-    unsigned int* counts = nullptr;     unsigned long long counts_cap = 0; // occurrences (wrap at 2^32)
-    unsigned long long n_keys = 0;
+    unsigned long long* cursor = nullptr;  // [0] append cursor, [1] distinct total, [2] overflow flag
+    // the table: records grouped by bucket; bucket b's distinct records are keys[bucket_start[b] .. + bucket_distinct[b])
+    unsigned long long* keys = nullptr; unsigned long long keys_cap = 0;
+    unsigned int* counts = nullptr;     unsigned long long counts_cap = 0;   // occurrences (wrap at 2^32)
+    unsigned int* kidx = nullptr;       unsigned long long kidx_cap = 0;     // neuron index of the word
+    unsigned long long n_keys = 0;      // distinct words
+    BucketPlan plan;
+    unsigned int* bucket_count = nullptr;    unsigned long long bucket_count_cap = 0;
+    unsigned int* bucket_fill = nullptr;     unsigned long long bucket_fill_cap = 0;
+    unsigned int* bucket_distinct = nullptr; unsigned long long bucket_distinct_cap = 0;
+    unsigned long long* bucket_start = nullptr; unsigned long long bucket_start_cap = 0;
+    unsigned long long* dense_start = nullptr;  unsigned long long dense_start_cap = 0;
     unsigned int* uniques = nullptr;    // per neuron: kmer_per_neuron
     unsigned int* flags = nullptr;
     bool valid = false;
@@ -287,7 +299,10 @@ cudaError_t exact_reserve_words(ExactTable& t, unsigned long long extra, cudaStr
 cudaError_t exact_clear(ExactTable& t, unsigned long long pool, bool tables_too, cudaStream_t s);
 cudaError_t exact_finalize(ExactTable& t, const FastMod& fm, unsigned long long pool, unsigned key_bits, bool merge,
                            cudaStream_t s);
-cudaError_t exact_lookup(const ExactTable& t, unsigned long long key, unsigned long long* d_out2, cudaStream_t s);
+cudaError_t exact_lookup(const ExactTable& t, const FastMod& fm, unsigned long long key, unsigned long long* d_out2, cudaStream_t s);
+// the table as dense device arrays in bucket order (any output may be null; n_keys entries each)
+cudaError_t exact_dense_copy(ExactTable& t, unsigned long long* out_keys, unsigned int* out_counts, unsigned int* out_idx,
+                             cudaStream_t s);
 cudaError_t exact_gather_uniques(const ExactTable& t, const unsigned long long* idx, unsigned long long n,
                                  unsigned int* out, cudaStream_t s);
 void exact_free(ExactTable& t);

@@ -1845,7 +1845,7 @@ int nk_get_count(nk_counter* h, uint64_t kmer, uint32_t* count, int32_t* found) 
     *count = 0;
     *found = 0;
     if (!h->xt.valid || h->xt.n_keys == 0) return NK_OK;
-    NK_CUDA(nk::exact_lookup(h->xt, h->fm, kmer, h->scalars + 4, h->stream));
+    NK_CUDA(nk::exact_lookup(h->xt, kmer, h->scalars + 4, h->stream));
     NK_CUDA(cudaMemcpyAsync(h->h_scalars + 4, h->scalars + 4, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
     NK_CUDA(cudaStreamSynchronize(h->stream));
     *found = (int32_t)h->h_scalars[4];
@@ -1870,12 +1870,12 @@ int nk_copy_exact_table(nk_counter* h, uint64_t* keys, uint32_t* counts) {
     NK_TRY(resolve(h));
     const unsigned long long n = h->xt.valid ? h->xt.n_keys : 0;
     if (n == 0) return NK_OK;
-    // the table lives bucket by bucket: compact it into dense device arrays, then copy those out
+    // the table is an open-addressing hash table: compact its occupied slots into dense device arrays, copy those out
     unsigned long long* dk = nullptr;
     unsigned int* dc = nullptr;
     if (keys) NK_CUDA(cudaMalloc(&dk, n * 8));
     if (counts && cudaMalloc(&dc, n * 4) != cudaSuccess) { cudaFree(dk); return fail(NK_ERR_OOM, "cudaMalloc(exact table copy)"); }
-    cudaError_t e = nk::exact_dense_copy(h->xt, dk, dc, nullptr, h->stream);
+    cudaError_t e = nk::exact_dense_copy(h->xt, dk, dc, h->stream);
     if (e == cudaSuccess && keys) e = cudaMemcpyAsync(keys, dk, n * 8, cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess && counts) e = cudaMemcpyAsync(counts, dc, n * 4, cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);

@@ -222,13 +222,14 @@ NK_API int nk_energy_used(const nk_counter* h, double* out);
  *   kmer_per_neuron: DashMap<usize, u32>     :26, :167-172, :467-473 (the `uniques` column of nk_top_n)
  * Enable BEFORE processing.  A batch/stream/file call then replaces both tables with this call's
  * (counts.clear(), :157/:426); nk_process_sequence adds to them (:218-221, :262-264).  Limits:
- * 12 B of device memory per window of a call + 24 B per distinct k-mer, single GPU (per-rank tables are not merged).  Off by default: then
+ * 28 B of device memory per window of a call while its table is built, single GPU (per-rank tables are not merged).  Off by default: then
  * nk_get_count returns NK_ERR_UNSUPPORTED and nk_top_n reports NK_UNIQUES_NOT_COMPUTED. */
 NK_API int nk_enable_exact_counts(nk_counter* h, int on);
 /* get_count — src/spiking_hash.rs:675-678: *found = 0 where the reference returns None. */
 NK_API int nk_get_count(nk_counter* h, uint64_t kmer, uint32_t* count, int32_t* found);
-/* the whole `counts` table (python.rs:31-40 walks it).  Like the reference's DashMap — and like it, a hash table —
- * it has no defined order. */
+/* the whole `counts` table (python.rs:31-40 walks it).  Like the reference's DashMap it has no defined order: the
+ * records come out grouped by neuron range (that is how the table is built: one partition by neuron index, then a
+ * shared-memory hash table per bucket — no sort anywhere). */
 NK_API int nk_exact_table_size(nk_counter* h, uint64_t* n);
 NK_API int nk_copy_exact_table(nk_counter* h, uint64_t* keys /* n */, uint32_t* counts /* n */);
 /* kmer_per_neuron for every neuron (0 where the reference's map has no entry) */

@@ -883,7 +883,8 @@ int fold_and_simulate(nk_counter* h, bool skip_zero, PhaseEvents& pe, bool with_
     NK_TRY(get_event(h, &pe.lif1));
     NK_CUDA(cudaEventRecord(pe.lif1, h->stream));
     if (h->exact) {  // counts.clear() + refill, kmer_per_neuron rebuilt (:157-172, :426-427, :467-473)
-        cudaError_t e = nk::exact_finalize(h->xt, h->fm, h->cfg.pool_size, std::min(64u, 2u * h->cfg.k), false, h->stream);
+        // (the stored currents are this call's per-neuron totals: the bucket sizes come from them)
+        cudaError_t e = nk::exact_finalize(h->xt, h->fm, h->cfg.pool_size, h->currents, false, h->stream);
         if (e == cudaErrorInvalidValue) return fail(NK_ERR_UNSUPPORTED, "exact counts: the words could not be partitioned into buckets that fit the on-chip tables");
         NK_CUDA(e);
     }
@@ -1724,7 +1725,7 @@ int nk_process_sequence(nk_counter* h, const uint8_t* seq, uint64_t len) {
     ++h->last.launches;
     h->fresh = false;
     h->top_cache_valid = false;
-    if (h->exact) NK_CUDA(nk::exact_finalize(h->xt, h->fm, h->cfg.pool_size, std::min(64u, 2u * h->cfg.k), true, h->stream));
+    if (h->exact) NK_CUDA(nk::exact_finalize(h->xt, h->fm, h->cfg.pool_size, nullptr, true, h->stream));
     h->spike_bound = h->spike_bound + 1 ? h->spike_bound + 1 : h->spike_bound;
     return finish_call(h, true, nullptr);
 }
@@ -1845,7 +1846,7 @@ int nk_get_count(nk_counter* h, uint64_t kmer, uint32_t* count, int32_t* found) 
     *count = 0;
     *found = 0;
     if (!h->xt.valid || h->xt.n_keys == 0) return NK_OK;
-    NK_CUDA(nk::exact_lookup(h->xt, kmer, h->scalars + 4, h->stream));
+    NK_CUDA(nk::exact_lookup(h->xt, h->fm, kmer, h->scalars + 4, h->stream));
     NK_CUDA(cudaMemcpyAsync(h->h_scalars + 4, h->scalars + 4, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
     NK_CUDA(cudaStreamSynchronize(h->stream));
     *found = (int32_t)h->h_scalars[4];
@@ -1870,12 +1871,12 @@ int nk_copy_exact_table(nk_counter* h, uint64_t* keys, uint32_t* counts) {
     NK_TRY(resolve(h));
     const unsigned long long n = h->xt.valid ? h->xt.n_keys : 0;
     if (n == 0) return NK_OK;
-    // the table is an open-addressing hash table: compact its occupied slots into dense device arrays, copy those out
+    // the table lives bucket by bucket: compact it into dense device arrays, then copy those out
     unsigned long long* dk = nullptr;
     unsigned int* dc = nullptr;
     if (keys) NK_CUDA(cudaMalloc(&dk, n * 8));
     if (counts && cudaMalloc(&dc, n * 4) != cudaSuccess) { cudaFree(dk); return fail(NK_ERR_OOM, "cudaMalloc(exact table copy)"); }
-    cudaError_t e = nk::exact_dense_copy(h->xt, dk, dc, h->stream);
+    cudaError_t e = nk::exact_dense_copy(h->xt, dk, dc, nullptr, h->stream);
     if (e == cudaSuccess && keys) e = cudaMemcpyAsync(keys, dk, n * 8, cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess && counts) e = cudaMemcpyAsync(counts, dc, n * 4, cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
@@ -2524,7 +2525,7 @@ static int uniques_begin(nk_counter* h, uint64_t top_n) {
 
 static int uniques_end(nk_counter* h) {
     h->uniques_open = false;
-    cudaError_t e = nk::exact_finalize(h->ut, h->fm, h->cfg.pool_size, std::min(64u, 2u * h->cfg.k), false, h->stream);
+    cudaError_t e = nk::exact_finalize(h->ut, h->fm, h->cfg.pool_size, nullptr, false, h->stream);
     if (e == cudaErrorInvalidValue) return fail(NK_ERR_UNSUPPORTED, "uniques pass: the collected words could not be partitioned");
     NK_CUDA(e);
     const uint64_t n = h->row_idx.size();

@@ -8,18 +8,31 @@
 //                                               the `uniques` column of top_abundant_neurons :667)
 //   process_sequence's variants                 :218-221, 259-263 (# sequences that touched the neuron)
 //
-// The reference's table is a concurrent hash map keyed by the k-mer word; so is this one: an open-addressing
-// table in HBM, 16-byte slots {word u64, count u32, neuron index u32}, linear probing from mix(word) * nslots >> 64,
-// slots claimed with a 64-bit atomicCAS on the word (a plain load first: a word that is already there costs one
-// atomicAdd on its count).  The count kernel appends (word, neuron index) of every window (mode 2 / 4 — it has
-// computed both anyway); at the end of the call one kernel inserts the appended records.  The first insertion of a
-// word adds one to its neuron's `uniques` (kmer_per_neuron).  No sort, no partition, no 2^31 limit (64-bit
-// cursors).  Round 2 first tried a bucket partition by neuron index + a shared-memory hash table per bucket: the
-// scatter of 113 M 16-byte records into 74 K buckets alone took 7.0 ms (L2 transaction bound: an atomic, a load and
-// three scattered stores per record; profiles/r02_exact.md) against 12.9 ms for round 1's whole CUB pipeline.
-// Memory: 12 B per window appended + 16 B per table slot (1.5 slots per record).  Counts wrap at 2^32 like the
-// reference's AtomicU32::fetch_add.
+// The reference's table is a hash map (DashMap): unordered, keyed by the k-mer word.  Nothing in it needs a
+// global sort — what is needed is "equal words meet" and "words of one neuron meet".  Both follow from ONE
+// partition by neuron index, which the count kernel has already computed for every window:
+//   0. the count kernel appends (word, neuron index) of every window               [nk_count.cu, mode 2 / 4]
+//   1. sizes of the BUCKETS of consecutive neurons (~1.5 K windows per bucket): for a whole-call table they are sums
+//      of the per-neuron counts the call has produced anyway (no pass over the records); otherwise one RED per
+//      record.  Pools with few neurons split every neuron into sub-buckets by a mix of the word.
+//   2. one-block exclusive scan of the bucket sizes -> one 64-bit write cursor per bucket
+//   3. scatter: per record ONE atomic on its bucket's cursor and ONE 16-byte store {word, weight, index}
+//   4. one CTA per bucket: a shared-memory hash table (64-bit atomicCAS) merges equal words and counts them,
+//      every NEW word adds one to its neuron's `uniques`; the distinct records are written back IN PLACE at the
+//      head of the bucket's own segment
+// get_count(word) = hash -> neuron -> bucket -> one warp scans that bucket's distinct records.
+// The table is therefore grouped by neuron range and unordered inside a bucket (like the reference's map);
+// nk_copy_exact_table compacts the buckets into dense arrays.  No 2^31 limit: every cursor is 64-bit.
+// Memory: 12 B per window appended + 16 B per window partitioned.  Counts wrap at 2^32 like the reference's
+// AtomicU32::fetch_add.
+//
+// Measured on the bench workload (113 M windows, 112.4 M distinct, B200; profiles/r02_exact.md): round 1's CUB
+// pipeline 12.9 ms per job.  Two designs were tried before this one in round 2: the same partition with three
+// separate arrays and a separate start[] + fill[] per bucket (five L2 transactions per record: scatter 7.0 ms),
+// and ONE open-addressing table in HBM with a 64-bit CAS per record (no partition at all: 16.5 ms for the insert
+// kernel — 113 M random read-modify-writes of DRAM sectors run at 6.8 G/s).
 #include <algorithm>
+#include <atomic>
 
 #include "nk_kernels.cuh"
 
@@ -28,8 +41,9 @@ namespace nk {
 namespace {
 
 constexpr int XT = 256;                       // threads per block
-constexpr unsigned long long EMPTY = ~0ull;   // slot marker.  Only pack_kmer of 32 T's (k = 32, non-canonical) equals it:
-                                              // that one word is counted in a side slot (ExactTable::cursor[3..])
+constexpr unsigned TABLE_SLOTS = 4096;        // shared-memory hash table of one bucket (power of two)
+constexpr unsigned long long BUCKET_TARGET = 1536;  // windows per bucket aimed at (table load <= ~0.4 when all distinct)
+constexpr unsigned long long EMPTY = ~0ull;   // no k < 32 word and no canonical word equals it; see dedup kernel
 
 #define NKX(expr)                        \
     do {                                 \
@@ -37,73 +51,172 @@ constexpr unsigned long long EMPTY = ~0ull;   // slot marker.  Only pack_kmer of
         if (e_ != cudaSuccess) return e_; \
     } while (0)
 
+cudaError_t ensure(void** p, unsigned long long* cap, unsigned long long bytes) {
+    if (bytes <= *cap) return cudaSuccess;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    NKX(cudaMalloc(p, bytes));
+    *cap = bytes;
+    return cudaSuccess;
+}
+
 __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {  // splitmix64 finaliser
     x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ULL;
     x ^= x >> 27; x *= 0x94D049BB133111EBULL;
     return x ^ (x >> 31);
 }
-__device__ __forceinline__ unsigned long long home_slot(unsigned long long word, unsigned long long nslots) {
-    return __umul64hi(mix64(word), nslots);
+
+__device__ __forceinline__ unsigned long long bucket_of(unsigned idx, unsigned long long word, const BucketPlan& bp) {
+    const unsigned long long g = idx / bp.neurons_per_bucket;
+    return bp.splits > 1 ? g * bp.splits + (mix64(word) >> 32) % bp.splits : g;
 }
 
-__global__ void clear_slots_kernel(ExactSlot* __restrict__ slots, unsigned long long nslots) {
+// bucket sizes without touching the records: a whole-call table holds exactly the windows the call counted, so the
+// size of a bucket of consecutive neurons is the sum of their counts (`pool_counts` = the call's u64 currents)
+__global__ void bucket_hist_from_pool_kernel(const unsigned long long* __restrict__ pool_counts, unsigned long long pool,
+                                             BucketPlan bp, unsigned int* __restrict__ bucket_count) {
+    const unsigned long long b = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (b >= bp.nbuckets) return;
+    const unsigned long long lo = b * bp.neurons_per_bucket;
+    const unsigned long long hi = lo + bp.neurons_per_bucket < pool ? lo + bp.neurons_per_bucket : pool;
+    unsigned long long s = 0;
+    for (unsigned long long i = lo; i < hi; ++i) s += pool_counts[i];
+    bucket_count[b] = (unsigned int)s;
+}
+
+__global__ void bucket_hist_kernel(const unsigned long long* __restrict__ words, const unsigned int* __restrict__ widx,
+                                   const ExactSlot* __restrict__ recs, unsigned long long n_recs, unsigned long long n, BucketPlan bp,
+                                   unsigned int* __restrict__ bucket_count) {
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    const uint4 e = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);  // {EMPTY, count 0, idx 0}
-    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < nslots; i += stride)
-        reinterpret_cast<uint4*>(slots)[i] = e;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n + n_recs; i += stride) {
+        unsigned ix;
+        unsigned long long w = 0;
+        if (i < n_recs) { ix = recs[i].idx; if (bp.splits > 1) w = recs[i].key; }
+        else { ix = widx[i - n_recs]; if (bp.splits > 1) w = words[i - n_recs]; }
+        atomicAdd(bucket_count + bucket_of(ix, w, bp), 1u);
+    }
 }
 
-// one record -> the table.  Returns true if the word was new.
-__device__ __forceinline__ bool table_insert(ExactSlot* slots, unsigned long long nslots, unsigned long long word, unsigned idx,
-                                             unsigned weight, unsigned long long* side /* [0] count [1] idx+1 of the all-ones word */) {
-    if (word == EMPTY) {
-        const unsigned long long before = atomicAdd(side, (unsigned long long)weight);
-        if (before == 0ull) { side[1] = (unsigned long long)idx + 1ull; return true; }
-        return false;
+// one block: start[b] = sum of count[< b], start[nb] = total, cursor[b] = start[b] (the scatter's write cursors)
+__global__ void __launch_bounds__(1024) bucket_scan_kernel(const unsigned int* __restrict__ count, unsigned long long nb,
+                                                            unsigned long long* __restrict__ start, unsigned long long* __restrict__ cursor) {
+    __shared__ unsigned long long s_sum[1024];
+    const unsigned t = threadIdx.x;
+    const unsigned long long per = (nb + 1023) / 1024;
+    const unsigned long long a = (unsigned long long)t * per, b = a + per < nb ? a + per : nb;
+    unsigned long long s = 0;
+    for (unsigned long long i = a; i < b; ++i) s += count[i];
+    s_sum[t] = s;
+    __syncthreads();
+    if (t == 0) {
+        unsigned long long run = 0;
+        for (int q = 0; q < 1024; ++q) { const unsigned long long x = s_sum[q]; s_sum[q] = run; run += x; }
+        start[nb] = run;
     }
-    unsigned long long s = home_slot(word, nslots);
-    for (;;) {
-        unsigned long long k = *reinterpret_cast<volatile unsigned long long*>(&slots[s].key);
-        if (k == EMPTY) {
-            k = atomicCAS(&slots[s].key, EMPTY, word);
-            if (k == EMPTY) {
-                slots[s].idx = idx;
-                atomicAdd(&slots[s].count, weight);
-                return true;
+    __syncthreads();
+    s = s_sum[t];
+    for (unsigned long long i = a; i < b; ++i) {
+        start[i] = s;
+        if (cursor) cursor[i] = s;
+        s += count[i];
+    }
+}
+
+// per record: one atomic on the bucket's cursor, one 16-byte store
+__global__ void bucket_scatter_kernel(const unsigned long long* __restrict__ words, const unsigned int* __restrict__ widx,
+                                      const ExactSlot* __restrict__ recs, unsigned long long n_recs, unsigned long long n,
+                                      BucketPlan bp, unsigned long long* __restrict__ cursor, ExactSlot* __restrict__ out) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n + n_recs; i += stride) {
+        ExactSlot r;
+        if (i < n_recs) r = recs[i];
+        else { r.key = words[i - n_recs]; r.idx = widx[i - n_recs]; r.count = 1u; }
+        const unsigned long long pos = atomicAdd(cursor + bucket_of(r.idx, r.key, bp), 1ull);
+        reinterpret_cast<uint4*>(out)[pos] = *reinterpret_cast<const uint4*>(&r);
+    }
+}
+
+// One CTA per bucket.  Equal words are merged in a shared-memory hash table (linear probing, 64-bit atomicCAS
+// on the key).  The all-ones word (only pack_kmer of 32 T's, k = 32, non-canonical) is the table's EMPTY marker
+// and therefore counted on the side.  The distinct records overwrite the head of the bucket's segment.
+// uniques != null: +1 per distinct word on its neuron (kmer_per_neuron).  *overflow is raised if a bucket holds
+// more distinct words than the table takes (the caller re-partitions into more buckets).
+__global__ void __launch_bounds__(XT) bucket_dedup_kernel(ExactSlot* __restrict__ recs, const unsigned long long* __restrict__ start,
+                                                           unsigned int* __restrict__ distinct, unsigned int* __restrict__ uniques,
+                                                           unsigned long long* __restrict__ n_distinct_total,
+                                                           unsigned int* __restrict__ overflow) {
+    extern __shared__ __align__(16) unsigned char dedup_smem[];  // 64 KB: keys, counts, neuron indices
+    unsigned long long* s_key = reinterpret_cast<unsigned long long*>(dedup_smem);
+    unsigned int* s_cnt = reinterpret_cast<unsigned int*>(s_key + TABLE_SLOTS);
+    unsigned int* s_ix = s_cnt + TABLE_SLOTS;
+    __shared__ unsigned int s_warp[XT / 32];
+    __shared__ unsigned int s_ones_cnt, s_ones_ix, s_over, s_base;
+    const unsigned long long b = blockIdx.x;
+    const unsigned long long lo = start[b], hi = start[b + 1];
+    const unsigned tid = threadIdx.x;
+    if (lo == hi) {
+        if (tid == 0) distinct[b] = 0u;
+        return;
+    }
+    for (unsigned s = tid; s < TABLE_SLOTS; s += XT) { s_key[s] = EMPTY; s_cnt[s] = 0u; }
+    if (tid == 0) { s_ones_cnt = 0u; s_ones_ix = 0u; s_over = 0u; s_base = 0u; }
+    __syncthreads();
+    for (unsigned long long i = lo + tid; i < hi; i += XT) {
+        const uint4 q = reinterpret_cast<const uint4*>(recs)[i];
+        const unsigned long long w = ((unsigned long long)q.y << 32) | q.x;
+        const unsigned wt = q.z, ix = q.w;
+        if (w == EMPTY) { atomicAdd(&s_ones_cnt, wt); s_ones_ix = ix; continue; }
+        unsigned slot = (unsigned)(mix64(w) >> 40) & (TABLE_SLOTS - 1);
+        for (unsigned probes = 0;; ++probes) {
+            unsigned long long prev = s_key[slot];                          // plain load first: a word that is already
+            if (prev == EMPTY) prev = atomicCAS(&s_key[slot], EMPTY, w);    // there costs no CAS (N runs repeat one word)
+            if (prev == EMPTY || prev == w) {
+                atomicAdd(&s_cnt[slot], wt);
+                if (prev == EMPTY) s_ix[slot] = ix;
+                break;
             }
-        }
-        if (k == word) {
-            atomicAdd(&slots[s].count, weight);
-            return false;
-        }
-        if (++s == nslots) s = 0;
-    }
-}
-
-// records = (words[i], widx[i], weight 1).  uniques != null: +1 on the neuron of every new word.
-__global__ void __launch_bounds__(XT) insert_words_kernel(const unsigned long long* __restrict__ words, const unsigned int* __restrict__ widx,
-                                                           unsigned long long n, ExactSlot* slots, unsigned long long nslots,
-                                                           unsigned int* uniques, unsigned long long* n_keys, unsigned long long* side) {
-    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    unsigned mine = 0;
-    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n; i += stride) {
-        const unsigned ix = widx[i];
-        if (table_insert(slots, nslots, words[i], ix, 1u, side)) {
-            ++mine;
-            if (uniques) atomicAdd(uniques + ix, 1u);
+            slot = (slot + 1) & (TABLE_SLOTS - 1);
+            if (probes >= TABLE_SLOTS) { s_over = 1u; break; }
         }
     }
-    mine = __reduce_add_sync(0xFFFFFFFFu, mine);
-    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(n_keys, (unsigned long long)mine);
-}
-
-// re-insert the records of an older (smaller) table: table growth
-__global__ void __launch_bounds__(XT) reinsert_kernel(const ExactSlot* __restrict__ old_slots, unsigned long long old_n,
-                                                       ExactSlot* slots, unsigned long long nslots, unsigned long long* side) {
-    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < old_n; i += stride) {
-        const ExactSlot o = old_slots[i];
-        if (o.key != EMPTY) table_insert(slots, nslots, o.key, o.idx, o.count, side);
+    __syncthreads();
+    if (s_over) {
+        if (tid == 0) atomicExch(overflow, 1u);
+        return;
+    }
+    // compact the occupied slots to the head of the segment (the loads above are all done: barrier)
+    for (unsigned base = 0; base < TABLE_SLOTS; base += XT) {
+        const unsigned s = base + tid;
+        const bool occ = s_key[s] != EMPTY;
+        const unsigned bal = __ballot_sync(0xFFFFFFFFu, occ);
+        if ((tid & 31) == 0) s_warp[tid >> 5] = __popc(bal);
+        __syncthreads();
+        unsigned before = s_base;
+        for (unsigned w = 0; w < (tid >> 5); ++w) before += s_warp[w];
+        const unsigned pos = before + __popc(bal & ((1u << (tid & 31)) - 1u));
+        if (occ) {
+            const unsigned long long k = s_key[s];
+            reinterpret_cast<uint4*>(recs)[lo + pos] = make_uint4((unsigned)k, (unsigned)(k >> 32), s_cnt[s], s_ix[s]);
+            if (uniques) atomicAdd(uniques + s_ix[s], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned t = 0;
+            for (int w = 0; w < XT / 32; ++w) t += s_warp[w];
+            s_base += t;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        unsigned nd = s_base;
+        if (s_ones_cnt) {
+            reinterpret_cast<uint4*>(recs)[lo + nd] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, s_ones_cnt, s_ones_ix);
+            if (uniques) atomicAdd(uniques + s_ones_ix, 1u);
+            ++nd;
+        }
+        distinct[b] = nd;
+        if (nd) atomicAdd(n_distinct_total, (unsigned long long)nd);
     }
 }
 
@@ -120,58 +233,39 @@ __global__ void touched_kernel(const unsigned int* __restrict__ widx, unsigned l
     }
 }
 
-__global__ void lookup_kernel(const ExactSlot* __restrict__ slots, unsigned long long nslots, const unsigned long long* __restrict__ side,
+// get_count: one warp scans the word's bucket
+template <bool POW2>
+__global__ void lookup_kernel(const ExactSlot* __restrict__ recs, const unsigned long long* __restrict__ start,
+                              const unsigned int* __restrict__ distinct, BucketPlan bp, FastMod fm, RotMul rm,
                               unsigned long long key, unsigned long long* out) {
-    out[0] = 0ull;
-    out[1] = 0ull;
-    if (key == EMPTY) {
-        if (side[0]) { out[0] = 1ull; out[1] = side[0] & 0xFFFFFFFFull; }
-        return;
+    const U64 h = siphash13_dev((unsigned)key, (unsigned)(key >> 32), rm);
+    const unsigned ix = fastmod_dev<POW2>(h, fm);
+    const unsigned long long b = bucket_of(ix, key, bp);
+    const unsigned long long lo = start[b];
+    const unsigned nd = distinct[b];
+    unsigned long long found = 0, cnt = 0;
+    for (unsigned j = threadIdx.x; j < nd; j += 32)
+        if (recs[lo + j].key == key) { found = 1; cnt = recs[lo + j].count; }
+    for (int o = 16; o > 0; o >>= 1) {
+        found |= __shfl_down_sync(0xFFFFFFFFu, found, o);
+        cnt |= __shfl_down_sync(0xFFFFFFFFu, cnt, o);  // at most one lane holds a non-zero count
     }
-    if (nslots == 0) return;
-    unsigned long long s = home_slot(key, nslots);
-    for (;;) {
-        const ExactSlot e = slots[s];
-        if (e.key == EMPTY) return;
-        if (e.key == key) { out[0] = 1ull; out[1] = e.count; return; }
-        if (++s == nslots) s = 0;
-    }
+    if (threadIdx.x == 0) { out[0] = found; out[1] = cnt; }
 }
 
-// occupied slots -> dense arrays (block-wise compaction; the order is the table's, i.e. none)
-__global__ void __launch_bounds__(XT) compact_kernel(const ExactSlot* __restrict__ slots, unsigned long long nslots,
-                                                      const unsigned long long* __restrict__ side, unsigned long long* cursor,
-                                                      unsigned long long* __restrict__ out_keys, unsigned int* __restrict__ out_counts) {
-    __shared__ unsigned int s_warp[XT / 32];
-    __shared__ unsigned long long s_base;
-    const unsigned tid = threadIdx.x;
-    const unsigned long long chunks = (nslots + XT - 1) / XT;
-    for (unsigned long long c = blockIdx.x; c < chunks; c += gridDim.x) {
-        const unsigned long long i = c * XT + tid;
-        ExactSlot e{EMPTY, 0u, 0u};
-        if (i < nslots) e = slots[i];
-        const bool occ = e.key != EMPTY;
-        const unsigned bal = __ballot_sync(0xFFFFFFFFu, occ);
-        if ((tid & 31) == 0) s_warp[tid >> 5] = __popc(bal);
-        __syncthreads();
-        if (tid == 0) {
-            unsigned t = 0;
-            for (int w = 0; w < XT / 32; ++w) t += s_warp[w];
-            s_base = t ? atomicAdd(cursor, (unsigned long long)t) : 0ull;
-        }
-        __syncthreads();
-        if (occ) {
-            unsigned long long pos = s_base + __popc(bal & ((1u << (tid & 31)) - 1u));
-            for (unsigned w = 0; w < (tid >> 5); ++w) pos += s_warp[w];
-            if (out_keys) out_keys[pos] = e.key;
-            if (out_counts) out_counts[pos] = e.count;
-        }
-        __syncthreads();
-    }
-    if (blockIdx.x == 0 && tid == 0 && side[0]) {  // the all-ones word lives beside the table
-        const unsigned long long pos = atomicAdd(cursor, 1ull);
-        if (out_keys) out_keys[pos] = EMPTY;
-        if (out_counts) out_counts[pos] = (unsigned int)side[0];
+// dense copy of the table (bucket order): one block per bucket, offsets from a scan of the distinct counts
+__global__ void compact_table_kernel(const ExactSlot* __restrict__ recs, const unsigned long long* __restrict__ start,
+                                     const unsigned int* __restrict__ distinct, const unsigned long long* __restrict__ dense_start,
+                                     unsigned long long* __restrict__ out_keys, unsigned int* __restrict__ out_counts,
+                                     ExactSlot* __restrict__ out_recs) {
+    const unsigned long long b = blockIdx.x;
+    const unsigned long long lo = start[b], d0 = dense_start[b];
+    const unsigned nd = distinct[b];
+    for (unsigned j = threadIdx.x; j < nd; j += blockDim.x) {
+        const ExactSlot r = recs[lo + j];
+        if (out_keys) out_keys[d0 + j] = r.key;
+        if (out_counts) out_counts[d0 + j] = r.count;
+        if (out_recs) out_recs[d0 + j] = r;
     }
 }
 
@@ -186,6 +280,24 @@ __global__ void filter_set_kernel(unsigned int* filter, const unsigned long long
     if (i < n) atomicOr(filter + (idx[i] >> 5), 1u << (idx[i] & 31u));
 }
 
+BucketPlan make_plan(unsigned long long n, unsigned long long pool, unsigned extra_split) {
+    BucketPlan bp;
+    unsigned long long want = (n + BUCKET_TARGET - 1) / BUCKET_TARGET;
+    if (want < 1) want = 1;
+    want *= extra_split;
+    if (want > 0x7FFFFFFFull) want = 0x7FFFFFFFull;   // one CTA per bucket: grid limit
+    if (pool >= want) {
+        bp.neurons_per_bucket = (unsigned)((pool + want - 1) / want);
+        bp.splits = 1;
+    } else {
+        bp.neurons_per_bucket = 1;
+        bp.splits = (unsigned)((want + pool - 1) / pool);
+    }
+    const unsigned long long groups = (pool + bp.neurons_per_bucket - 1) / bp.neurons_per_bucket;
+    bp.nbuckets = groups * bp.splits;
+    return bp;
+}
+
 unsigned grid_for(unsigned long long n) {
     unsigned long long blocks = (n + XT - 1) / XT;
     if (blocks > 148ull * 16) blocks = 148ull * 16;
@@ -197,35 +309,6 @@ cudaError_t ensure_cursor(ExactTable& t, cudaStream_t s) {
         NKX(cudaMalloc(&t.cursor, 8 * sizeof(unsigned long long)));
         NKX(cudaMemsetAsync(t.cursor, 0, 8 * sizeof(unsigned long long), s));
     }
-    return cudaSuccess;
-}
-
-// a fresh table of at least `want` slots; old != null: its records move over
-cudaError_t new_table(ExactTable& t, unsigned long long want, bool keep_old, cudaStream_t s) {
-    ExactSlot* old = t.slots;
-    const unsigned long long old_n = t.nslots;
-    if (!keep_old && want <= t.slots_cap) {
-        t.nslots = want;
-        clear_slots_kernel<<<grid_for(want), XT, 0, s>>>(t.slots, want);
-        return cudaGetLastError();
-    }
-    ExactSlot* ns = nullptr;
-    const unsigned long long cap = want + want / 8;
-    NKX(cudaMalloc(&ns, cap * sizeof(ExactSlot)));
-    clear_slots_kernel<<<grid_for(want), XT, 0, s>>>(ns, want);
-    if (keep_old && old && old_n) {
-        // the side slot of the all-ones word stays where it is (cursor[3..4]); only the table proper moves
-        unsigned long long* scratch_side = t.cursor + 5;  // reinserted records never hit the side slot
-        reinsert_kernel<<<grid_for(old_n), XT, 0, s>>>(old, old_n, ns, want, scratch_side);
-    }
-    NKX(cudaGetLastError());
-    if (old) {
-        NKX(cudaStreamSynchronize(s));
-        cudaFree(old);
-    }
-    t.slots = ns;
-    t.slots_cap = cap;
-    t.nslots = want;
     return cudaSuccess;
 }
 
@@ -273,19 +356,18 @@ cudaError_t exact_clear(ExactTable& t, unsigned long long pool, bool tables_too,
     if (t.cursor) NKX(cudaMemsetAsync(t.cursor, 0, sizeof(unsigned long long), s));
     if (tables_too) {
         t.n_keys = 0;
-        t.nslots = 0;   // (the allocation is kept: the next build clears what it uses)
         t.valid = false;
-        if (t.cursor) NKX(cudaMemsetAsync(t.cursor + 1, 0, 7 * sizeof(unsigned long long), s));
         if (t.uniques) NKX(cudaMemsetAsync(t.uniques, 0, pool * sizeof(unsigned int), s));
     }
     return cudaSuccess;
 }
 
-// The (word, index) records appended since the last call -> the table.  merge: ADD them to the table that exists
-// (process_sequence: counts accumulate over calls, :218-221) and use its "neurons touched by this sequence" rule
-// for the per-neuron column; else the table is replaced (counts.clear(), :157 / :426).
-cudaError_t exact_finalize(ExactTable& t, const FastMod& fm, unsigned long long pool, unsigned /*key_bits*/, bool merge,
-                           cudaStream_t s) {
+// The (word, index) records appended since the last call -> the bucketed table.  merge: ADD them to the table
+// that exists (process_sequence: counts accumulate over calls, :218-221) and use its "neurons touched by this
+// sequence" rule for the per-neuron column; else the table is replaced (counts.clear(), :157 / :426).
+// pool_counts (may be null): per-neuron counts of exactly the appended windows (the call's u64 currents).
+cudaError_t exact_finalize(ExactTable& t, const FastMod& fm, unsigned long long pool, const unsigned long long* pool_counts,
+                           bool merge, cudaStream_t s) {
     (void)fm;
     NKX(ensure_cursor(t, s));
     unsigned long long n_new = 0;
@@ -298,30 +380,80 @@ cudaError_t exact_finalize(ExactTable& t, const FastMod& fm, unsigned long long 
     }
     if (!merge) {
         t.n_keys = 0;
-        t.nslots = 0;
-        NKX(cudaMemsetAsync(t.cursor + 1, 0, 7 * sizeof(unsigned long long), s));  // [1] distinct words, [3..4] all-ones word
         NKX(cudaMemsetAsync(t.uniques, 0, pool * sizeof(unsigned int), s));
     }
-    if (n_new > 0) {
-        if (merge) {
-            if (!t.flags) {
-                NKX(cudaMalloc(&t.flags, pool * sizeof(unsigned int)));
-                NKX(cudaMemsetAsync(t.flags, 0, pool * sizeof(unsigned int), s));
-            }
-            const unsigned blocks = (unsigned)((n_new + 255) / 256);
-            touched_kernel<<<blocks, 256, 0, s>>>(t.widx, n_new, t.flags, t.uniques, 0);
-            touched_kernel<<<blocks, 256, 0, s>>>(t.widx, n_new, t.flags, t.uniques, 1);
+    if (merge && n_new > 0) {
+        if (!t.flags) {
+            NKX(cudaMalloc(&t.flags, pool * sizeof(unsigned int)));
+            NKX(cudaMemsetAsync(t.flags, 0, pool * sizeof(unsigned int), s));
         }
-        // at most n_keys + n_new distinct words afterwards: keep the load factor under 2/3
-        const unsigned long long need = (t.n_keys + n_new) * 3 / 2 + 64;
-        if (need > t.nslots) NKX(new_table(t, merge && t.nslots ? std::max(need, t.nslots * 2) : need, merge && t.n_keys > 0, s));
-        insert_words_kernel<<<grid_for(n_new), XT, 0, s>>>(t.words, t.widx, n_new, t.slots, t.nslots, merge ? nullptr : t.uniques,
-                                                           t.cursor + 1, t.cursor + 3);
-        NKX(cudaGetLastError());
-        unsigned long long nk = 0;
-        NKX(cudaMemcpyAsync(&nk, t.cursor + 1, sizeof nk, cudaMemcpyDeviceToHost, s));
-        NKX(cudaStreamSynchronize(s));
-        t.n_keys = nk;
+        const unsigned blocks = (unsigned)((n_new + 255) / 256);
+        touched_kernel<<<blocks, 256, 0, s>>>(t.widx, n_new, t.flags, t.uniques, 0);
+        touched_kernel<<<blocks, 256, 0, s>>>(t.widx, n_new, t.flags, t.uniques, 1);
+    }
+    // input records of the partition: the new windows (weight 1) and, when merging, the table's records
+    const unsigned long long n_old = merge ? t.n_keys : 0;
+    const unsigned long long n_in = n_new + n_old;
+    if (n_new > 0) {
+        ExactSlot* old_dense = nullptr;
+        if (n_old) {  // the old table, dense (it is rebuilt together with the new windows)
+            NKX(cudaMalloc(&old_dense, n_old * sizeof(ExactSlot)));
+            cudaError_t e = exact_dense_copy(t, nullptr, nullptr, old_dense, s);
+            if (e != cudaSuccess) { cudaFree(old_dense); return e; }
+        }
+        cudaError_t err = cudaSuccess;
+        for (unsigned attempt = 0, split = 1; attempt < 4; ++attempt, split *= 4) {
+            const BucketPlan bp = make_plan(n_in, pool, split);
+            err = ensure((void**)&t.bucket_count, &t.bucket_count_cap, bp.nbuckets * sizeof(unsigned int));
+            if (err == cudaSuccess) err = ensure((void**)&t.bucket_distinct, &t.bucket_distinct_cap, bp.nbuckets * sizeof(unsigned int));
+            if (err == cudaSuccess) err = ensure((void**)&t.bucket_start, &t.bucket_start_cap, (bp.nbuckets + 1) * sizeof(unsigned long long));
+            if (err == cudaSuccess) err = ensure((void**)&t.bucket_cursor, &t.bucket_cursor_cap, (bp.nbuckets + 1) * sizeof(unsigned long long));
+            if (err == cudaSuccess) err = ensure((void**)&t.recs, &t.recs_cap, n_in * sizeof(ExactSlot));
+            if (err == cudaSuccess) err = cudaMemsetAsync(t.cursor + 1, 0, 2 * sizeof(unsigned long long), s);  // [1] distinct total, [2] overflow
+            if (err != cudaSuccess) break;
+            if (pool_counts && !merge && bp.splits == 1) {
+                bucket_hist_from_pool_kernel<<<(unsigned)((bp.nbuckets + 255) / 256), 256, 0, s>>>(pool_counts, pool, bp, t.bucket_count);
+            } else {
+                err = cudaMemsetAsync(t.bucket_count, 0, bp.nbuckets * sizeof(unsigned int), s);
+                if (err != cudaSuccess) break;
+                bucket_hist_kernel<<<grid_for(n_in), XT, 0, s>>>(t.words, t.widx, old_dense, n_old, n_new, bp, t.bucket_count);
+            }
+            bucket_scan_kernel<<<1, 1024, 0, s>>>(t.bucket_count, bp.nbuckets, t.bucket_start, t.bucket_cursor);
+            bucket_scatter_kernel<<<grid_for(n_in), XT, 0, s>>>(t.words, t.widx, old_dense, n_old, n_new, bp, t.bucket_cursor, t.recs);
+            constexpr int kDedupSmem = TABLE_SLOTS * (8 + 4 + 4);
+            static std::atomic<bool> smem_set[64];
+            int dev = 0;
+            err = cudaGetDevice(&dev);
+            if (err != cudaSuccess) break;
+            if (dev >= 0 && dev < 64 && !smem_set[dev].load()) {
+                err = cudaFuncSetAttribute(bucket_dedup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDedupSmem);
+                if (err != cudaSuccess) break;
+                smem_set[dev].store(true);
+            }
+            bucket_dedup_kernel<<<(unsigned)bp.nbuckets, XT, kDedupSmem, s>>>(t.recs, t.bucket_start, t.bucket_distinct,
+                                                                             merge ? nullptr : t.uniques, t.cursor + 1,
+                                                                             reinterpret_cast<unsigned int*>(t.cursor + 2));
+            err = cudaGetLastError();
+            if (err != cudaSuccess) break;
+            unsigned long long res[2] = {0, 0};
+            err = cudaMemcpyAsync(res, t.cursor + 1, sizeof res, cudaMemcpyDeviceToHost, s);
+            if (err == cudaSuccess) err = cudaStreamSynchronize(s);
+            if (err != cudaSuccess) break;
+            if ((res[1] & 0xFFFFFFFFull) == 0) {
+                t.plan = bp;
+                t.n_keys = res[0];
+                break;
+            }
+            // a bucket held more distinct words than the table takes: partition finer.  `uniques` was touched by the
+            // buckets that did finish: start over with it
+            if (!merge) {
+                err = cudaMemsetAsync(t.uniques, 0, pool * sizeof(unsigned int), s);
+                if (err != cudaSuccess) break;
+            }
+            err = cudaErrorInvalidValue;
+        }
+        if (old_dense) { cudaStreamSynchronize(s); cudaFree(old_dense); }
+        if (err != cudaSuccess) return err;
     }
     t.valid = true;
     // the words of this call are consumed
@@ -330,16 +462,20 @@ cudaError_t exact_finalize(ExactTable& t, const FastMod& fm, unsigned long long 
     return cudaGetLastError();
 }
 
-// the table as dense device arrays (either output may be null; n_keys entries each); the order is the table's
-cudaError_t exact_dense_copy(ExactTable& t, unsigned long long* out_keys, unsigned int* out_counts, cudaStream_t s) {
+// the table as dense device arrays, bucket order (any of the outputs may be null); needs n_keys entries each
+cudaError_t exact_dense_copy(ExactTable& t, unsigned long long* out_keys, unsigned int* out_counts, ExactSlot* out_recs,
+                             cudaStream_t s) {
     if (t.n_keys == 0) return cudaSuccess;
-    NKX(cudaMemsetAsync(t.cursor + 2, 0, sizeof(unsigned long long), s));
-    compact_kernel<<<grid_for(t.nslots), XT, 0, s>>>(t.slots, t.nslots, t.cursor + 3, t.cursor + 2, out_keys, out_counts);
+    const unsigned long long nb = t.plan.nbuckets;
+    NKX(ensure((void**)&t.dense_start, &t.dense_start_cap, (nb + 1) * sizeof(unsigned long long)));
+    bucket_scan_kernel<<<1, 1024, 0, s>>>(t.bucket_distinct, nb, t.dense_start, nullptr);
+    compact_table_kernel<<<(unsigned)nb, 128, 0, s>>>(t.recs, t.bucket_start, t.bucket_distinct, t.dense_start, out_keys, out_counts, out_recs);
     return cudaGetLastError();
 }
 
-cudaError_t exact_lookup(const ExactTable& t, unsigned long long key, unsigned long long* d_out2, cudaStream_t s) {
-    lookup_kernel<<<1, 1, 0, s>>>(t.slots, t.nslots, t.cursor + 3, key, d_out2);
+cudaError_t exact_lookup(const ExactTable& t, const FastMod& fm, unsigned long long key, unsigned long long* d_out2, cudaStream_t s) {
+    if (fm.is_pow2) lookup_kernel<true><<<1, 32, 0, s>>>(t.recs, t.bucket_start, t.bucket_distinct, t.plan, fm, make_rotmul(), key, d_out2);
+    else lookup_kernel<false><<<1, 32, 0, s>>>(t.recs, t.bucket_start, t.bucket_distinct, t.plan, fm, make_rotmul(), key, d_out2);
     return cudaGetLastError();
 }
 
@@ -351,7 +487,8 @@ cudaError_t exact_gather_uniques(const ExactTable& t, const unsigned long long* 
 }
 
 void exact_free(ExactTable& t) {
-    cudaFree(t.words); cudaFree(t.widx); cudaFree(t.cursor); cudaFree(t.slots); cudaFree(t.uniques); cudaFree(t.flags);
+    cudaFree(t.words); cudaFree(t.widx); cudaFree(t.cursor); cudaFree(t.recs); cudaFree(t.uniques); cudaFree(t.flags);
+    cudaFree(t.bucket_count); cudaFree(t.bucket_distinct); cudaFree(t.bucket_start); cudaFree(t.bucket_cursor); cudaFree(t.dense_start);
     t = ExactTable{};
 }
 

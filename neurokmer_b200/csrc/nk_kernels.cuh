@@ -269,33 +269,44 @@ cudaError_t launch_merge_packs(const unsigned long long* gathered, int world, in
                                unsigned long long n_out, unsigned long long* pack_out, cudaStream_t s);
 
 // exact side tables (nk_exact.cu)
-struct ExactSlot {            // one slot of the open-addressing table in HBM (16 bytes)
-    unsigned long long key;   // the k-mer word; all-ones = empty
+struct ExactSlot {            // one record of the table (16 bytes, moved as one uint4)
+    unsigned long long key;   // the k-mer word
     unsigned int count;       // occurrences (wraps at 2^32 like the reference's AtomicU32)
     unsigned int idx;         // its neuron index
+};
+struct BucketPlan {
+    unsigned int neurons_per_bucket = 1;   // consecutive neurons that share a bucket ...
+    unsigned int splits = 1;               // ... or sub-buckets per neuron (pools with few neurons), by a mix of the word
+    unsigned long long nbuckets = 0;
 };
 struct ExactTable {
     // appended by the count kernel (mode 2 / 4): the word and the neuron index of every window
     unsigned long long* words = nullptr;
     unsigned int* widx = nullptr;
     unsigned long long words_cap = 0, words_bound = 0;
-    // [0] append cursor, [1] distinct words in the table, [2] compaction cursor, [3] count and [4] (neuron index + 1)
-    // of the all-ones word, which cannot live in the table (all-ones marks an empty slot), [5..] scratch
-    unsigned long long* cursor = nullptr;
-    ExactSlot* slots = nullptr;
-    unsigned long long nslots = 0, slots_cap = 0;
-    unsigned long long n_keys = 0;      // distinct words (host mirror of cursor[1])
+    unsigned long long* cursor = nullptr;  // [0] append cursor, [1] distinct total, [2] overflow flag
+    // the table: bucket b's distinct records are recs[bucket_start[b] .. + bucket_distinct[b])
+    ExactSlot* recs = nullptr;          unsigned long long recs_cap = 0;
+    unsigned long long n_keys = 0;      // distinct words
+    BucketPlan plan;
+    unsigned int* bucket_count = nullptr;        unsigned long long bucket_count_cap = 0;
+    unsigned int* bucket_distinct = nullptr;     unsigned long long bucket_distinct_cap = 0;
+    unsigned long long* bucket_start = nullptr;  unsigned long long bucket_start_cap = 0;
+    unsigned long long* bucket_cursor = nullptr; unsigned long long bucket_cursor_cap = 0;
+    unsigned long long* dense_start = nullptr;   unsigned long long dense_start_cap = 0;
     unsigned int* uniques = nullptr;    // per neuron: kmer_per_neuron
     unsigned int* flags = nullptr;
     bool valid = false;
 };
 cudaError_t exact_reserve_words(ExactTable& t, unsigned long long extra, cudaStream_t s);
 cudaError_t exact_clear(ExactTable& t, unsigned long long pool, bool tables_too, cudaStream_t s);
-cudaError_t exact_finalize(ExactTable& t, const FastMod& fm, unsigned long long pool, unsigned key_bits, bool merge,
-                           cudaStream_t s);
-cudaError_t exact_lookup(const ExactTable& t, unsigned long long key, unsigned long long* d_out2, cudaStream_t s);
-// the table as dense device arrays (either output may be null; n_keys entries each); no defined order
-cudaError_t exact_dense_copy(ExactTable& t, unsigned long long* out_keys, unsigned int* out_counts, cudaStream_t s);
+// pool_counts (may be null): per-neuron counts of exactly the appended windows (bucket sizes without a pass over the records)
+cudaError_t exact_finalize(ExactTable& t, const FastMod& fm, unsigned long long pool, const unsigned long long* pool_counts,
+                           bool merge, cudaStream_t s);
+cudaError_t exact_lookup(const ExactTable& t, const FastMod& fm, unsigned long long key, unsigned long long* d_out2, cudaStream_t s);
+// the table as dense device arrays in bucket order (any output may be null; n_keys entries each)
+cudaError_t exact_dense_copy(ExactTable& t, unsigned long long* out_keys, unsigned int* out_counts, ExactSlot* out_recs,
+                             cudaStream_t s);
 cudaError_t exact_gather_uniques(const ExactTable& t, const unsigned long long* idx, unsigned long long n,
                                  unsigned int* out, cudaStream_t s);
 void exact_free(ExactTable& t);

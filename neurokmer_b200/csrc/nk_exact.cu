@@ -146,12 +146,12 @@ __global__ void __launch_bounds__(XT) bucket_dedup_kernel(ExactSlot* __restrict_
                                                            unsigned int* __restrict__ distinct, unsigned int* __restrict__ uniques,
                                                            unsigned long long* __restrict__ n_distinct_total,
                                                            unsigned int* __restrict__ overflow) {
-    extern __shared__ __align__(16) unsigned char dedup_smem[];  // 64 KB: keys, counts, neuron indices
+    extern __shared__ __align__(16) unsigned char dedup_smem[];  // keys | counts | neuron indices | list of claimed slots
     unsigned long long* s_key = reinterpret_cast<unsigned long long*>(dedup_smem);
     unsigned int* s_cnt = reinterpret_cast<unsigned int*>(s_key + TABLE_SLOTS);
     unsigned int* s_ix = s_cnt + TABLE_SLOTS;
-    __shared__ unsigned int s_warp[XT / 32];
-    __shared__ unsigned int s_ones_cnt, s_ones_ix, s_over, s_base;
+    unsigned short* s_list = reinterpret_cast<unsigned short*>(s_ix + TABLE_SLOTS);  // TABLE_SLOTS entries
+    __shared__ unsigned int s_ones_cnt, s_ones_ix, s_over, s_nd;
     const unsigned long long b = blockIdx.x;
     const unsigned long long lo = start[b], hi = start[b + 1];
     const unsigned tid = threadIdx.x;
@@ -159,8 +159,14 @@ __global__ void __launch_bounds__(XT) bucket_dedup_kernel(ExactSlot* __restrict_
         if (tid == 0) distinct[b] = 0u;
         return;
     }
-    for (unsigned s = tid; s < TABLE_SLOTS; s += XT) { s_key[s] = EMPTY; s_cnt[s] = 0u; }
-    if (tid == 0) { s_ones_cnt = 0u; s_ones_ix = 0u; s_over = 0u; s_base = 0u; }
+    // keys <- EMPTY, counts <- 0 (16-byte stores; the two arrays are adjacent)
+    {
+        uint4* k4 = reinterpret_cast<uint4*>(s_key);
+        uint4* c4 = reinterpret_cast<uint4*>(s_cnt);
+        for (unsigned i = tid; i < TABLE_SLOTS / 2; i += XT) k4[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
+        for (unsigned i = tid; i < TABLE_SLOTS / 4; i += XT) c4[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (tid == 0) { s_ones_cnt = 0u; s_ones_ix = 0u; s_over = 0u; s_nd = 0u; }
     __syncthreads();
     for (unsigned long long i = lo + tid; i < hi; i += XT) {
         const uint4 q = reinterpret_cast<const uint4*>(recs)[i];
@@ -171,9 +177,12 @@ __global__ void __launch_bounds__(XT) bucket_dedup_kernel(ExactSlot* __restrict_
         for (unsigned probes = 0;; ++probes) {
             unsigned long long prev = s_key[slot];                          // plain load first: a word that is already
             if (prev == EMPTY) prev = atomicCAS(&s_key[slot], EMPTY, w);    // there costs no CAS (N runs repeat one word)
+            if (prev == EMPTY) {  // claimed: remember the slot (the distinct words are written out from this list)
+                s_ix[slot] = ix;
+                s_list[atomicAdd(&s_nd, 1u)] = (unsigned short)slot;
+            }
             if (prev == EMPTY || prev == w) {
                 atomicAdd(&s_cnt[slot], wt);
-                if (prev == EMPTY) s_ix[slot] = ix;
                 break;
             }
             slot = (slot + 1) & (TABLE_SLOTS - 1);
@@ -185,31 +194,16 @@ __global__ void __launch_bounds__(XT) bucket_dedup_kernel(ExactSlot* __restrict_
         if (tid == 0) atomicExch(overflow, 1u);
         return;
     }
-    // compact the occupied slots to the head of the segment (the loads above are all done: barrier)
-    for (unsigned base = 0; base < TABLE_SLOTS; base += XT) {
-        const unsigned s = base + tid;
-        const bool occ = s_key[s] != EMPTY;
-        const unsigned bal = __ballot_sync(0xFFFFFFFFu, occ);
-        if ((tid & 31) == 0) s_warp[tid >> 5] = __popc(bal);
-        __syncthreads();
-        unsigned before = s_base;
-        for (unsigned w = 0; w < (tid >> 5); ++w) before += s_warp[w];
-        const unsigned pos = before + __popc(bal & ((1u << (tid & 31)) - 1u));
-        if (occ) {
-            const unsigned long long k = s_key[s];
-            reinterpret_cast<uint4*>(recs)[lo + pos] = make_uint4((unsigned)k, (unsigned)(k >> 32), s_cnt[s], s_ix[s]);
-            if (uniques) atomicAdd(uniques + s_ix[s], 1u);
-        }
-        __syncthreads();
-        if (tid == 0) {
-            unsigned t = 0;
-            for (int w = 0; w < XT / 32; ++w) t += s_warp[w];
-            s_base += t;
-        }
-        __syncthreads();
+    // the distinct records overwrite the head of the segment (every load above is done: barrier)
+    const unsigned nd0 = s_nd;
+    for (unsigned j = tid; j < nd0; j += XT) {
+        const unsigned slot = s_list[j];
+        const unsigned long long k = s_key[slot];
+        reinterpret_cast<uint4*>(recs)[lo + j] = make_uint4((unsigned)k, (unsigned)(k >> 32), s_cnt[slot], s_ix[slot]);
+        if (uniques) atomicAdd(uniques + s_ix[slot], 1u);
     }
     if (tid == 0) {
-        unsigned nd = s_base;
+        unsigned nd = nd0;
         if (s_ones_cnt) {
             reinterpret_cast<uint4*>(recs)[lo + nd] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, s_ones_cnt, s_ones_ix);
             if (uniques) atomicAdd(uniques + s_ones_ix, 1u);
@@ -420,7 +414,7 @@ cudaError_t exact_finalize(ExactTable& t, const FastMod& fm, unsigned long long 
             }
             bucket_scan_kernel<<<1, 1024, 0, s>>>(t.bucket_count, bp.nbuckets, t.bucket_start, t.bucket_cursor);
             bucket_scatter_kernel<<<grid_for(n_in), XT, 0, s>>>(t.words, t.widx, old_dense, n_old, n_new, bp, t.bucket_cursor, t.recs);
-            constexpr int kDedupSmem = TABLE_SLOTS * (8 + 4 + 4);
+            constexpr int kDedupSmem = TABLE_SLOTS * (8 + 4 + 4 + 2);
             static std::atomic<bool> smem_set[64];
             int dev = 0;
             err = cudaGetDevice(&dev);

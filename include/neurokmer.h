@@ -198,7 +198,9 @@ NK_API int nk_stream_push_packed(nk_counter* h, const uint32_t* codes, const uin
  * FASTA/FASTQ record rules follow src/utils.rs:9-24.
  * Plain regular files that fit the device are copied there raw by a pool of host threads (pread -> pinned
  * slots -> async H2D) and split into records ON THE DEVICE (no host pass over the bytes); compressed input,
- * pipes and larger files go through the host reader (NK_GPU_PARSE=0 forces it).  Same results either way. */
+ * pipes and larger files go through the host reader (NK_GPU_PARSE=0 forces it).  Same results either way.
+ * Limit of the host reader only: a FASTQ record whose sequence is longer than its 32 MiB batch buffer fails with
+ * NK_ERR_UNSUPPORTED (FASTA records of any length are cut with a k-1 overlap; the device parser has no such limit). */
 NK_API int nk_process_file(nk_counter* h, const char* path, int streaming);
 
 /* process_sequence — src/spiking_hash.rs:203-273 (per-sequence API: one LIF tick

@@ -34,6 +34,9 @@ pub const NK_UNIQUES_NOT_COMPUTED: u32 = 0xFFFF_FFFF;
 extern "C" {
     pub fn nk_config_default(cfg: *mut NkConfig) -> c_int;
     pub fn nk_create(cfg: *const NkConfig, out: *mut *mut NkCounter) -> c_int; // SpikingKmerCounter::new   src/spiking_hash.rs:40-77
+    // ONE input sharded over several GPUs of this process (the reference's rayon fold/reduce over cores, src/spiking_hash.rs:94-154)
+    pub fn nk_device_count(n: *mut i32) -> c_int;
+    pub fn nk_create_multi(cfg: *const NkConfig, devices: *const i32, n_devices: i32, out: *mut *mut NkCounter) -> c_int;
     pub fn nk_destroy(h: *mut NkCounter) -> c_int; // Drop
     pub fn nk_reset(h: *mut NkCounter) -> c_int;
     pub fn nk_last_error() -> *const c_char;

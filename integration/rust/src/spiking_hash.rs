@@ -37,8 +37,36 @@ impl SpikingKmerCounter {
         Self { h, k, use_canonical, pool_size }
     }
 
-    /// `&[Vec<u8>]` is flattened into one byte array + offsets (the ABI's batch form).
+    /// The same counter with every input sharded over `gpus` GPUs of this process (0 = all of them): batches are
+    /// cut by window start with a k-1 overlap, the per-neuron sums meet over NVLink peer memory.  Same results.
+    pub fn new_multi(k: usize, threshold: f32, leak: f32, refractory: u32, spike_cost: f64, pool_size: usize,
+                     use_canonical: bool, gpus: usize) -> Self {
+        let mut cfg = unsafe { std::mem::zeroed::<ffi::NkConfig>() };
+        unsafe { ffi::nk_config_default(&mut cfg) };
+        cfg.k = k as u32;
+        cfg.threshold = threshold;
+        cfg.leak = leak;
+        cfg.refractory = refractory;
+        cfg.spike_cost = spike_cost;
+        cfg.pool_size = pool_size as u64;
+        cfg.use_canonical = use_canonical as i32;
+        let mut n = gpus as i32;
+        if n == 0 {
+            unsafe { ffi::nk_device_count(&mut n) };
+        }
+        let mut h = std::ptr::null_mut();
+        check(unsafe { ffi::nk_create_multi(&cfg, std::ptr::null(), n.max(1), &mut h) }).expect("nk_create_multi");
+        Self { h, k, use_canonical, pool_size }
+    }
+
+    /// `&[Vec<u8>]` is flattened into one byte array + offsets (the ABI's batch form); a single sequence is
+    /// handed over where it lies (no copy).  Pageable memory is staged by the library's pool of host threads.
     pub fn process_parallel(&mut self, seqs: &[Vec<u8>]) {
+        if seqs.len() == 1 {
+            let offsets = [0u64, seqs[0].len() as u64];
+            check(unsafe { ffi::nk_process_batch(self.h, seqs[0].as_ptr(), offsets.as_ptr(), 1) }).expect("nk_process_batch");
+            return;
+        }
         let mut offsets = Vec::with_capacity(seqs.len() + 1);
         let mut bases = Vec::with_capacity(seqs.iter().map(Vec::len).sum());
         offsets.push(0u64);

@@ -703,6 +703,7 @@ int simulate(nk_counter* h, bool skip_zero, bool with_topn) {
             q.out_spikes = h->topn.out_spikes;
             q.pack = h->d_pack;
             q.kmers = h->scalars + 2;
+            q.trace = getenv("NK_POST_TRACE") ? 1 : 0;
             // (no memsets: the kernel leaves its scratch, the spike counter and the k-mer counter zeroed)
             NK_CUDA(nk::launch_post(q, h->post_grid, h->stream));
             h->fired_clean = h->kmers_clean = true;
@@ -832,6 +833,9 @@ int resolve(nk_counter* h) {
         const unsigned long long* t = h->h_pack + 4;
         auto ms = [](unsigned long long a, unsigned long long b) { return b > a ? (float)((double)(b - a) * 1e-6) : 0.f; };
         h->last.post_ms = ms(t[0], t[3]);
+        if (getenv("NK_POST_TRACE") && !h->dist_job)
+            fprintf(stderr, "[post trace] start->ready %.1f us, phase 1 + barrier %.1f, select %.1f, look-back %.1f, gather+ticket %.1f, final %.1f (last block %llu)\n",
+                    ms(t[0], t[1]) * 1e3, ms(t[1], t[2]) * 1e3, ms(t[2], t[4]) * 1e3, ms(t[4], t[5]) * 1e3, ms(t[5], t[6]) * 1e3, ms(t[6], t[3]) * 1e3, t[7]);
         h->last.exch_reduce_ms = ms(t[1], t[2]);  // single GPU: the same phase on local memory
         if (h->dist_job) {
             h->last.exch_wait_ms = ms(t[0], t[1]) + ms(t[4], t[5]);

@@ -207,6 +207,7 @@ struct PostParams {
     unsigned int* hist;              // 8 * 256 bins
     unsigned long long* ctrl;        // 8 u64: [0] gather cursor, [1] error, [2] finished blocks, [4..6] block 0's time stamps
     unsigned int* block_ties;        // POST_MAX_GRID: per block, (its number of ties) + 1 once published
+    int trace;                       // NK_POST_TRACE: extra time stamps in pack[8..11] (single GPU only)
     unsigned int* seg_counts;        // ceil(pool/4096)
     unsigned long long* out_idx;     // >= 2048
     unsigned long long* out_spikes;  // >= 2048

@@ -90,12 +90,19 @@ __device__ __forceinline__ void select_from_exact_hist(const unsigned* hist, uns
     constexpr unsigned PER = POST_EXACT_BINS / PT;  // thread t owns the bins [8t, 8t+8)
     unsigned part = 0;
     for (unsigned b = 0; b < PER; ++b) part += hist[tid * PER + b];
-    s_part[tid] = part;
-    __syncthreads();
-    if (tid == 0) {
-        unsigned long long run = 0;
-        for (int x = PT - 1; x >= 0; --x) { s_above[x] = run; run += s_part[x]; }
+    // s_above[t] = number of totals in the bins of the threads ABOVE t (suffix sum): warp shuffles, then 8 warp totals
+    const unsigned lane = tid & 31u, warp = tid >> 5;
+    unsigned incl = part;  // inclusive suffix sum inside the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned v = __shfl_down_sync(0xFFFFFFFFu, incl, o);
+        if (lane + o < 32u) incl += v;
     }
+    if (lane == 0) s_part[warp] = incl;  // the warp's total
+    __syncthreads();
+    unsigned long long above = incl - part;
+    for (unsigned w = warp + 1; w < PT / 32; ++w) above += s_part[w];
+    s_above[tid] = above;
     __syncthreads();
     if (s_above[tid] < n && n <= s_above[tid] + part) *s_pick = tid;
     __syncthreads();
@@ -171,7 +178,8 @@ __global__ void __launch_bounds__(PT, 3) post_kernel(const PostParams q) {
     unsigned long long fired_sum = 0;
     // loads are issued in batches of B independent items (memory-level parallelism: a persistent grid
     // has only ~150 k threads for millions of neurons, so every thread must keep several loads in flight)
-    constexpr int B = 8;
+    // (6, not 8: 2 M neurons over 444 blocks are 17.6 per thread = 3 nearly full rounds of 6 instead of 2.2 of 8)
+    constexpr int B = 6;
     unsigned int* __restrict__ acc = p.acc;
     unsigned long long* __restrict__ currents = p.currents;
     unsigned long long* __restrict__ spikes = p.spikes;
@@ -272,6 +280,7 @@ __global__ void __launch_bounds__(PT, 3) post_kernel(const PostParams q) {
         __syncthreads();
         unsigned long long T, gt, need;
         select_from_exact_hist(s_ghist, q.n, s_above, s_part, &s_pick, T, gt, need);
+        if (q.trace && blockIdx.x == 0 && tid == 0) q.ctrl[3] = global_ns();
         const unsigned my_ties = s_hist[T];                       // this block's own range (kept from phase 1)
         unsigned my_gt = 0;
         for (unsigned b = (unsigned)T + 1 + tid; b < POST_EXACT_BINS; b += PT) my_gt += s_hist[b];
@@ -297,6 +306,7 @@ __global__ void __launch_bounds__(PT, 3) post_kernel(const PostParams q) {
             for (int w = 0; w < PT / 32; ++w) ties_before += s_red[w];
             __syncthreads();
         }
+        if (q.trace && blockIdx.x == 0 && tid == 0) q.ctrl[7] = global_ns();
         // ---- phase 3: ordered gather, only where this block contributes rows ---------------------------------
         if (my_gt != 0 || (my_ties != 0 && ties_before < need)) {
             unsigned long long seg_prefix = ties_before;
@@ -316,7 +326,10 @@ __global__ void __launch_bounds__(PT, 3) post_kernel(const PostParams q) {
                         q.out_spikes[slot] = v[it];
                     }
                 }
-                if (seg_prefix < need) {  // block-uniform: only while ties are still wanted
+                // block-uniform: only while ties are still wanted, and only in segments that hold one
+                if (seg_prefix >= need) {
+                    if (my_gt == 0) break;  // nothing above T in this range and all wanted ties are placed
+                } else if (__syncthreads_or(eq != 0)) {
                     s_part[tid] = eq;
                     __syncthreads();
                     for (int o = 1; o < PT; o <<= 1) {
@@ -342,8 +355,6 @@ __global__ void __launch_bounds__(PT, 3) post_kernel(const PostParams q) {
                     }
                     __syncthreads();
                     seg_prefix += seg_ties;
-                } else if (my_gt == 0) {
-                    break;  // nothing above T in this range and all wanted ties are placed
                 }
             }
         }
@@ -354,6 +365,7 @@ __global__ void __launch_bounds__(PT, 3) post_kernel(const PostParams q) {
         __syncthreads();
         if (!s_last) return;
         __threadfence();
+        if (q.trace && tid == 0) q.pack[10] = global_ns();
     } else {
     // ---- radix passes (totals beyond the single histogram): MSB-first select, every block redundantly ----
     unsigned long long prefix = 0, rank = q.n, gt = 0;
@@ -477,6 +489,14 @@ __global__ void __launch_bounds__(PT, 3) post_kernel(const PostParams q) {
     unsigned N = 1;
     while (N < n) N <<= 1;
     __syncthreads();
+    // the scalars of the pack: loaded now, so that their L2 round trips overlap the sort
+    unsigned long long pk_fired = 0, pk_err = 0, pk_kmers = 0, pk_t0 = 0, pk_t1 = 0, pk_t2 = 0;
+    if (tid == 0) {
+        pk_fired = __ldcg(p.total_new);
+        pk_err = __ldcg(&q.ctrl[1]);
+        pk_kmers = __ldcg(q.kmers);
+        pk_t0 = __ldcg(&q.ctrl[4]); pk_t1 = __ldcg(&q.ctrl[5]); pk_t2 = __ldcg(&q.ctrl[6]);
+    }
     for (unsigned i = tid; i < N; i += PT) {
         s_idx[i] = i < n ? __ldcg(&q.out_idx[i]) : ~0ull;
         s_spk[i] = i < n ? __ldcg(&q.out_spikes[i]) : 0ull;
@@ -510,14 +530,13 @@ __global__ void __launch_bounds__(PT, 3) post_kernel(const PostParams q) {
         q.pack[PACK_HDR + n + i] = s_spk[i];
     }
     if (tid == 0) {
-        q.pack[0] = __ldcg(p.total_new);
-        q.pack[1] = __ldcg(&q.ctrl[1]);  // 1: a peer's "counting finished" signal timed out
-        q.pack[2] = __ldcg(q.kmers);
+        q.pack[0] = pk_fired;
+        q.pack[1] = pk_err;  // 1: a peer's "counting finished" signal timed out
+        q.pack[2] = pk_kmers;
         q.pack[3] = n;
-        // the stamps of block 0; when another block finishes last they travel through the scratch
-        if (blockIdx.x == 0) { q.pack[4] = t_start; q.pack[5] = t_ready; q.pack[6] = t_phase1; }
-        else { q.pack[4] = __ldcg(&q.ctrl[4]); q.pack[5] = __ldcg(&q.ctrl[5]); q.pack[6] = __ldcg(&q.ctrl[6]); }
+        q.pack[4] = pk_t0; q.pack[5] = pk_t1; q.pack[6] = pk_t2;  // block 0's stamps travel through the scratch
         q.pack[7] = global_ns();
+        if (q.trace) { q.pack[8] = __ldcg(&q.ctrl[3]); q.pack[9] = __ldcg(&q.ctrl[7]); q.pack[11] = blockIdx.x; }
     }
     if (q.wait_flags) {
         // deliver the pack into every rank's mailbox (slot = this rank), then raise "pack delivered"

@@ -141,9 +141,7 @@ __global__ void __launch_bounds__(PT, 3) post_kernel(const PostParams q) {
     __shared__ unsigned long long s_red[PT / 32];
     __shared__ unsigned int s_pick;
     __shared__ unsigned int s_part[PT];
-    __shared__ unsigned long long s_sort[4096];  // final sort: 2048 indices + 2048 totals; before it: totals cache + histogram copy
-    unsigned long long* const s_idx = s_sort;
-    unsigned long long* const s_spk = s_sort + 2048;
+    __shared__ unsigned long long s_idx[2048], s_spk[2048];
     __shared__ int s_last;
     const unsigned tid = threadIdx.x;
     const LifParams& p = q.lif;
@@ -197,11 +195,6 @@ __global__ void __launch_bounds__(PT, 3) post_kernel(const PostParams q) {
     per_block = (per_block + ITEMS - 1) / ITEMS * ITEMS;
     const unsigned long long my_lo = (unsigned long long)blockIdx.x * per_block < p.pool ? (unsigned long long)blockIdx.x * per_block : p.pool;
     const unsigned long long my_hi = my_lo + per_block < p.pool ? my_lo + per_block : p.pool;
-    // the new totals of this block's own range stay in shared memory for phase 3 (the final sort's buffers are
-    // free until then); ranges beyond the cache (pools over ~2.7 M neurons) are re-read from L2
-    constexpr unsigned TOT_CACHE = 6144;
-    unsigned int* s_tot = reinterpret_cast<unsigned int*>(s_sort);                      // 24 KB of the 32 KB
-    const bool tot_cached = single && per_block <= TOT_CACHE;
     {
         for (unsigned long long i0 = my_lo + tid; i0 < my_hi; i0 += (unsigned long long)PT * B) {
             unsigned long long count[B], total[B];
@@ -254,7 +247,6 @@ __global__ void __launch_bounds__(PT, 3) post_kernel(const PostParams q) {
                     rr[i] = 0u;
                     spikes[i] = 0ull;
                 }
-                if (tot_cached) s_tot[i - my_lo] = (unsigned)total[u];
                 atomicAdd(&s_hist[single ? (unsigned)(total[u] < POST_EXACT_BINS - 1 ? total[u] : POST_EXACT_BINS - 1)
                                          : (unsigned)(total[u] >> (8 * top)) & 255u], 1u);
             }
@@ -283,7 +275,7 @@ __global__ void __launch_bounds__(PT, 3) post_kernel(const PostParams q) {
 
     if (single) {
         // ---- phase 2: select T from the global histogram; ties of the blocks before this one -----------------
-        unsigned* s_ghist = reinterpret_cast<unsigned*>(s_sort) + TOT_CACHE;  // the 8 KB behind the totals cache
+        unsigned* s_ghist = reinterpret_cast<unsigned*>(s_idx);  // s_idx is not needed before the final sort
         for (unsigned b = tid; b < POST_EXACT_BINS; b += PT) s_ghist[b] = __ldcg(&q.hist[b]);
         __syncthreads();
         unsigned long long T, gt, need;
@@ -326,7 +318,7 @@ __global__ void __launch_bounds__(PT, 3) post_kernel(const PostParams q) {
 #pragma unroll
                 for (int it = 0; it < ITEMS; ++it) {
                     const unsigned long long i = base + it;
-                    v[it] = i < my_hi ? (tot_cached ? (unsigned long long)s_tot[i - my_lo] : spikes[i]) : 0ull;
+                    v[it] = i < my_hi ? spikes[i] : 0ull;
                     if (i < my_hi && v[it] == T) ++eq;
                     if (i < my_hi && v[it] > T) {
                         const unsigned long long slot = atomicAdd(&q.ctrl[0], 1ull);

@@ -388,6 +388,9 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
     unsigned ok;
     asm volatile(

@@ -665,7 +665,9 @@ def gpu_arm(args):
             if name not in legs:
                 return None
             ph_l = legs[name][1]
+            walls = sorted(x[1] for x in legs[name][0])   # this rank's wall clock per step
             rec = {"value": job_kmers / (ms * 1e-3), "unit": "kmers/s", "ms_per_step": ms / args.steps,
+                   "ms_per_step_median": walls[len(walls) // 2], "ms_per_step_min": walls[0], "ms_per_step_max": walls[-1],
                    "h2d_bytes_per_step": int(ph_l[-1]["h2d_bytes"]),
                    "d2h_bytes_per_step": int(ph_l[-1]["d2h_bytes"] + 24 + 16 * TOPN)}
             if rec["h2d_bytes_per_step"]:

@@ -41,7 +41,7 @@ constexpr int kPkOther = COUNT_TILE / 8 + 16;
 static_assert(kPkCodes + kPkOther + kBitsPerStage <= kStageStride, "a packed stage fits an ASCII stage");
 
 static_assert(kBytesPerStage % 16 == 0 && kBitsPerStage % 16 == 0, "TMA bulk copies are 16-byte granular");
-static_assert(COUNT_HALO == 32, "a warp converts exactly two 16-byte words behind its span");
+static_assert(COUNT_HALO == 32, "the last warp converts exactly two 16-byte halo words");
 
 struct WindowConsts {
     unsigned wide;     // k <= 16: the forward window lives in (F0:F1) only
@@ -285,6 +285,21 @@ __device__ __forceinline__ void process_chunk(const CountParams& p, const Window
         }
         __syncwarp();
     } else {
+#ifndef NK_NO_FASTVALID
+    // a warp whose 512 starts are all valid (the common case in long sequences) skips the per-window validity bit and
+    // the predicate on the reduction (-0.8 % kernel time, profiles/r02_variants.md)
+    if (MODE == 0 && __all_sync(0xFFFFFFFFu, inv16 == 0u)) {
+#pragma unroll(kUnroll)
+        for (unsigned j = 0; j < 16; ++j) {
+            unsigned long long fwd, rc;
+            const unsigned long long word = window(j, fwd, rc);
+            const U64 h = siphash13_dev((unsigned)word, (unsigned)(word >> 32), p.rm);
+            const unsigned idx = fastmod_dev<POW2>(h, p.fm);
+            asm volatile("red.global.add.u32 [%0], %1;" ::"l"(p.acc + idx), "r"(1u) : "memory");
+        }
+        return;
+    }
+#endif
 #pragma unroll(kUnroll)
     for (unsigned j = 0; j < 16; ++j) {
         unsigned long long fwd, rc;
@@ -345,40 +360,30 @@ __device__ __forceinline__ void process_chunk(const CountParams& p, const Window
 #ifndef NK_COUNT_MINBLOCKS
 #define NK_COUNT_MINBLOCKS 2
 #endif
-// The tile pipeline.  A CTA never executes a block-wide barrier after start-up: stages are handed from the
-// producer (thread 0: tile scheduler + TMA) to the eight consumer warps through a `full` mbarrier per stage (TMA
-// transaction bytes) and handed back through an `empty` mbarrier that every warp arrives on as soon as it has
-// pulled its code words into registers — which is at the START of its work on the tile, so the refill of a stage
-// overlaps the hashing of the tile it held.  Warps drift apart by up to COUNT_STAGES - 1 tiles instead of
-// waiting for the slowest one at every tile (round 1: two __syncthreads per 4 KiB tile, `barrier` was 19 % of the
-// stall samples of an ALU-bound kernel — profiles/r02_count_kernel_ncu.md).  The k-1 overlap past the end of a
-// warp's span is converted by the warp itself (32 more bytes per 512: two lanes' worth of classification).
+// (Round 2 also tried a barrier-free tile pipeline here — `full` / `empty` mbarriers per stage, 2-4 stages, every warp
+// converting its own halo so that no __syncthreads is left in the loop, because `barrier` was 19 % of the stall samples.
+// It measured 1.0-1.9 % SLOWER than this loop (0.884 / 0.889 / 0.892 ms with 2 / 3 / 4 stages against 0.876 ms;
+// profiles/r02_variants.md): the barrier stalls were never on the critical resource, the ALU pipe was busy with the
+// other CTAs' warps.  Kept out.)
 template <bool CANON, int MODE, bool POW2, bool KHI, bool PACKED>
 __global__ void __launch_bounds__(COUNT_THREADS, NK_COUNT_MINBLOCKS) count_kernel(const __grid_constant__ CountParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ __align__(8) unsigned long long full[COUNT_STAGES], empty[COUNT_STAGES];
+    __shared__ __align__(8) unsigned long long bars[COUNT_STAGES];
     __shared__ unsigned long long tile_of[COUNT_STAGES];
+    __shared__ unsigned int halo[COUNT_WARPS][2][3];
     __shared__ TileEnds tends[COUNT_STAGES];
     constexpr bool BITMAP = MODE != 5;
-    constexpr unsigned S = COUNT_STAGES;
     unsigned valid_starts = 0;  // MODE 5: window starts this thread counted
 
-    // producer: claim the next tile for stage `st` and start its copy (or publish the end-of-work sentinel)
-    auto fill_stage = [&](unsigned st) {
-        const unsigned long long t = atomicAdd(p.tile_counter, 1u);
-        tile_of[st] = t;
-        if (t < p.ntiles) {
-            if (!BITMAP) find_tile_ends(p, t, &tends[st]);
-            issue_tile<PACKED, BITMAP>(smem + st * kStageStride, &full[st], p, t);
-        } else {
-            mbar_arrive(&full[st]);  // no bytes will come: complete the phase so that the consumers see the sentinel
-        }
-    };
-
     if (threadIdx.x == 0) {
-        for (unsigned st = 0; st < S; ++st) { mbar_init(&full[st], 1); mbar_init(&empty[st], COUNT_WARPS); }
+        for (int s = 0; s < COUNT_STAGES; ++s) mbar_init(&bars[s], 1);
         mbar_fence_init();
-        for (unsigned st = 0; st + 1 < S; ++st) fill_stage(st);
+        unsigned long long t0 = atomicAdd(p.tile_counter, 1u);
+        tile_of[0] = t0;
+        if (t0 < p.ntiles) {
+            issue_tile<PACKED, BITMAP>(smem, &bars[0], p, t0);
+            if (!BITMAP) find_tile_ends(p, t0, &tends[0]);
+        }
     }
     __syncthreads();
 
@@ -386,16 +391,18 @@ __global__ void __launch_bounds__(COUNT_THREADS, NK_COUNT_MINBLOCKS) count_kerne
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 
     for (unsigned it = 0;; ++it) {
-        const unsigned s = it % S;
-        if (threadIdx.x == 0) {
-            // stage of iteration it + S - 1; its previous use (iteration it - 1) must have been pulled into registers
-            const unsigned nx = it + S - 1u, sp = nx % S;
-            if (nx >= S) mbar_wait(&empty[sp], ((nx / S) - 1u) & 1u);
-            fill_stage(sp);
-        }
-        mbar_wait(&full[s], (it / S) & 1u);
+        const unsigned s = it & 1u;
         const unsigned long long tile = tile_of[s];
         if (tile >= p.ntiles) break;
+        if (threadIdx.x == 0) {  // prefetch the next tile into the other stage (consumed at it-1)
+            unsigned long long tn = atomicAdd(p.tile_counter, 1u);
+            tile_of[s ^ 1u] = tn;
+            if (tn < p.ntiles) {
+                issue_tile<PACKED, BITMAP>(smem + (s ^ 1u) * kStageStride, &bars[s ^ 1u], p, tn);
+                if (!BITMAP) find_tile_ends(p, tn, &tends[s ^ 1u]);
+            }
+        }
+        mbar_wait(&bars[s], (it >> 1) & 1u);
 
         const unsigned char* sb = smem + s * kStageStride;
         const unsigned short* bits =
@@ -403,8 +410,24 @@ __global__ void __launch_bounds__(COUNT_THREADS, NK_COUNT_MINBLOCKS) count_kerne
         const bool has_other = PACKED && p.other != nullptr;
         const unsigned span0 = warp * COUNT_SPAN;
         Codes16 cur = load_codes<CANON, PACKED>(sb, (span0 >> 4) + lane, has_other);
-        // the two code words behind the span (the next warp's first two, or the tile's halo): lanes 0 and 1 use them
-        const Codes16 tail = load_codes<CANON, PACKED>(sb, ((span0 + COUNT_SPAN) >> 4) + (lane & 1u), has_other);
+        // The k-1 overlap past the END of a warp's span is the first two code words of the next
+        // warp's span: they are exchanged through shared memory instead of being converted twice
+        // (the last warp converts the tile's 32-byte halo).  This is what makes small tiles cheap,
+        // and small tiles are what keeps the tail of the persistent grid short.
+        if (lane < 2) {
+            halo[warp][lane][0] = cur.F;
+            halo[warp][lane][1] = cur.R;
+            halo[warp][lane][2] = cur.V;
+        }
+        Codes16 tail{0u, 0u, 0u};
+        if (warp == COUNT_WARPS - 1)
+            tail = load_codes<CANON, PACKED>(sb, COUNT_TILE / 16 + (lane & 1u), has_other);
+        __syncthreads();
+        if (warp < COUNT_WARPS - 1 && lane < 2) {
+            tail.F = halo[warp + 1][lane][0];
+            tail.R = halo[warp + 1][lane][1];
+            tail.V = halo[warp + 1][lane][2];
+        }
 #pragma unroll 1
         for (unsigned c = 0; c < COUNT_CHUNKS_PER_SPAN; ++c) {
             Codes16 nxt = tail;
@@ -418,21 +441,17 @@ __global__ void __launch_bounds__(COUNT_THREADS, NK_COUNT_MINBLOCKS) count_kerne
                 inv16 = invalid_bits(p, tends[s], tile, (int)(off + 16u * lane));
                 valid_starts += 16u - __popc(inv16);
             }
-            if (c + 1u == COUNT_CHUNKS_PER_SPAN) {
-                // everything this warp needs from the stage is in registers: hand the stage back
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty[s]);
-            }
             process_chunk<CANON, (MODE == 5 ? 0 : MODE), POW2, KHI>(p, wc, cur, nxt, inv16, lane, tile * COUNT_TILE + off + 16u * lane,
                                                   reinterpret_cast<unsigned long long*>(smem + kSmemTotal) + warp * COUNT_CHUNK);
             cur = nxt;
         }
+        __syncthreads();
     }
     if (!BITMAP) {  // the metric's unit: windows counted (the bitmap path's marking kernel does this otherwise)
         valid_starts = __reduce_add_sync(0xFFFFFFFFu, valid_starts);
         if (lane == 0 && valid_starts) atomicAdd(p.kmers_out, (unsigned long long)valid_starts);
     }
-    // the last CTA to leave re-arms the tile scheduler for the next launch (only thread 0 ever touches it)
+    // the last CTA to leave re-arms the tile scheduler for the next launch
     if (threadIdx.x == 0) {
         __threadfence();
         if (atomicAdd(p.tile_counter + 1, 1u) == gridDim.x - 1u) {

@@ -388,9 +388,6 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
     unsigned ok;
     asm volatile(
@@ -409,6 +406,17 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 // global → shared bulk copy; size multiple of 16, both addresses 16-byte aligned
 __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, unsigned bytes,
                                             unsigned long long* bar) {
+#ifdef NK_EXP_EVICT_FIRST
+    // experiment: the input is read once — mark its lines evict-first so that it cannot push pool lines out of L2
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+        : "memory");
+    return;
+#endif
     asm volatile(
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
             smem_u32(smem_dst)),

@@ -26,10 +26,7 @@ constexpr int COUNT_CHUNKS_PER_SPAN = NK_CHUNKS_PER_SPAN;
 constexpr int COUNT_SPAN = COUNT_CHUNK * COUNT_CHUNKS_PER_SPAN;
 constexpr int COUNT_TILE = COUNT_WARPS * COUNT_SPAN;     // 4096 positions: small tiles keep the grid's tail short
 constexpr int COUNT_HALO = 32;                           // >= k-1, multiple of 16
-#ifndef NK_COUNT_STAGES
-#define NK_COUNT_STAGES 3
-#endif
-constexpr int COUNT_STAGES = NK_COUNT_STAGES;   // tiles in flight per CTA (one being hashed, the others arriving)
+constexpr int COUNT_STAGES = 2;
 
 struct CountParams {
     const unsigned char* bases;   // device, 16-B aligned, readable up to ntiles*TILE + HALO

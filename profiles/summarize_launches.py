@@ -15,7 +15,7 @@ print("`ncu --metrics gpu__time_duration.sum --clock-control none` — cold-cach
 print("Calibration micro-kernels (int_peak, red_peak), the synthetic generator and torch's L2-flush fill run outside a step's "
       "timed region; they are listed but excluded from the step share.\n")
 print("| kernel | launches | total us | avg us | share of step kernels |\n|---|---:|---:|---:|---:|")
-step = {k: v for k, v in agg.items() if not any(x in k for x in ("peak", "synth", "Fill", "vectorized"))}
+step = {k: v for k, v in agg.items() if not any(x in k for x in ("peak", "synth", "Fill", "vectorized", "hashed_idx"))}
 tot = sum(sum(v) for v in step.values())
 for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
     sh = f"{sum(v) / tot * 100:.1f}%" if k in step else "-"

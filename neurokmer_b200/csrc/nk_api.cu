@@ -337,12 +337,13 @@ int count_host_batch(nk_counter* h, const uint8_t* bases, const uint64_t* offset
     // chunk plan: fixed 32 MiB granules.  Measured alternatives at 113 MB (end to end, B200, PCIe Gen5):
     // fixed 32 MiB 2.53 ms; geometric tail down to 2 MiB 2.68 ms; 3 x 36 MiB + 4 MiB tail 2.60 ms —
     // fewer, equal copies win over a shorter exposed tail.
-    // Pinned sources are copied by the DMA engine at the link's own rate (55 GB/s measured against 47 GB/s for the
-    // in-place reads above), and since the long-sequence count kernel needs no bitmap and no marking kernels a chunk is
-    // ONE launch: small chunks cost nothing and leave only a small last chunk's kernel exposed behind the last copy.
+    // Pinned sources that are not read in place (NK_ZEROCOPY=0, unaligned pointers): DMA copies in 16 MiB chunks, one
+    // count launch per chunk.  Measured end to end at 113 MB (tools/h2d_sweep.py, profiles/r02_bench.md): in place 2.35 ms;
+    // chunks of 2 / 4 / 8 / 16 / 32 MiB 3.48 / 2.80 / 2.42 / 2.33 / 2.40 ms — below 8 MiB the host's per-chunk
+    // submission cost (copy, events, launch) shows, at 32 MiB the last chunk's kernel does.
     unsigned long long chunk_bytes = kChunkBytes;
     if (at_ok && at.type == cudaMemoryTypeHost) {
-        unsigned long long mb = 8;
+        unsigned long long mb = 16;
         if (const char* e = getenv("NK_H2D_CHUNK_MB")) { const unsigned long long t = strtoull(e, nullptr, 10); if (t >= 1 && t <= 32) mb = t; }
         chunk_bytes = mb << 20;
     }

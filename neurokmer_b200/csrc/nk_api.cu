@@ -1224,6 +1224,8 @@ static int process_file_device(nk_counter* h, const char* path, bool streaming, 
         }
         return NK_OK;
     }
+    timespec tr0, tr1, tr2;
+    clock_gettime(CLOCK_MONOTONIC, &tr0);
     begin_call(h);
     PhaseEvents pe;
     int rc;
@@ -1233,6 +1235,7 @@ static int process_file_device(nk_counter* h, const char* path, bool streaming, 
     unsigned long long nb = 0, nr = 0;
     rc = parse_file_on_device(h, path, handled, &fq, &nb, &nr, err);
     if (rc != NK_OK || !*handled) return rc;
+    clock_gettime(CLOCK_MONOTONIC, &tr1);
     zero_kmers(h);
     h->currents_valid_overwrite = true;
     for (unsigned long long c0 = 0; c0 < nb && nr > 0; c0 += slice) {
@@ -1246,6 +1249,10 @@ static int process_file_device(nk_counter* h, const char* path, bool streaming, 
     cudaEventRecord(pe.end, h->stream);
     if ((rc = finish_call(h, true, &pe)) != NK_OK) return failed(rc);
     if ((rc = resolve(h)) != NK_OK) return failed(rc);
+    clock_gettime(CLOCK_MONOTONIC, &tr2);
+    if (getenv("NK_FILE_TRACE"))
+        fprintf(stderr, "[file trace] begin + stage + parse %.2f ms, count + post + read-back %.2f ms\n",
+                (tr1.tv_sec - tr0.tv_sec) * 1e3 + (tr1.tv_nsec - tr0.tv_nsec) * 1e-6, (tr2.tv_sec - tr1.tv_sec) * 1e3 + (tr2.tv_nsec - tr1.tv_nsec) * 1e-6);
     return NK_OK;
 }
 

@@ -278,6 +278,10 @@ int grow(void** p, unsigned long long* cap, unsigned long long need) {
 int parse_file_on_device(nk_counter* h, const char* path, bool* handled, bool* is_fastq, unsigned long long* nbases,
                          unsigned long long* nrec, std::string* err) {
     *handled = false;
+    timespec tp0;
+    clock_gettime(CLOCK_MONOTONIC, &tp0);
+    auto since0 = [&]() { timespec b; clock_gettime(CLOCK_MONOTONIC, &b); return (b.tv_sec - tp0.tv_sec) * 1e3 + (b.tv_nsec - tp0.tv_nsec) * 1e-6; };
+    const bool ftrace0 = getenv("NK_FILE_TRACE") != nullptr;
     if (const char* e = getenv("NK_GPU_PARSE")) if (atoi(e) == 0) return NK_OK;
     if (getenv("NK_FASTA_WINDOW")) return NK_OK;  // the tests of the host reader's parallel ingest pin that path
     const int fd = ::open(path, O_RDONLY);
@@ -291,11 +295,15 @@ int parse_file_on_device(nk_counter* h, const char* path, bool* handled, bool* i
     }
     const unsigned long long size_real = (unsigned long long)st.st_size;
     const bool fastq = magic[0] == '@';
-    size_t free_b = 0, total_b = 0;
-    cudaMemGetInfo(&free_b, &total_b);
-    // raw bytes + stripped bases (+ bitmap) + FASTQ line table must fit beside the pool: else the host reader streams
-    const unsigned long long have = (unsigned long long)free_b + h->raw_cap + h->staged.bases_cap + h->line_end_cap * 8;
-    if (size_real * (fastq ? 3ull : 2ull) + (size_real >> 2) + (256ull << 20) > have) { ::close(fd); return NK_OK; }
+    // raw bytes + stripped bases (+ bitmap) + FASTQ line table must fit beside the pool: else the host reader streams.
+    // Only asked when buffers have to grow: cudaMemGetInfo is a resource-manager call with a long latency tail (it
+    // showed up as 5-70 ms outliers of the file path when it ran for every file).
+    if (size_real + 64 > h->raw_cap) {
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        const unsigned long long have = (unsigned long long)free_b + h->raw_cap + h->staged.bases_cap + h->line_end_cap * 8;
+        if (size_real * (fastq ? 3ull : 2ull) + (size_real >> 2) + (256ull << 20) > have) { ::close(fd); return NK_OK; }
+    }
 
     int rc = NK_OK;
     do {
@@ -317,7 +325,18 @@ int parse_file_on_device(nk_counter* h, const char* path, bool* handled, bool* i
         cudaEvent_t prev = nullptr;
         if ((rc = get_event(h, &prev)) != NK_OK) break;
         if (cudaEventRecord(prev, h->stream) != cudaSuccess) { rc = fail(NK_ERR_CUDA, "cudaEventRecord"); break; }
+        timespec ts0, ts1;
+        if (ftrace0) fprintf(stderr, "[file trace] staging starts at %.2f ms; ", since0());
+        clock_gettime(CLOCK_MONOTONIC, &ts0);
         if ((rc = stage_to_device(h, nullptr, fd, 0, size_real, h->d_raw, prev, h->stream)) != NK_OK) break;
+        clock_gettime(CLOCK_MONOTONIC, &ts1);
+        const bool ftrace = getenv("NK_FILE_TRACE") != nullptr;
+        auto since = [&](const timespec& a) { timespec b; clock_gettime(CLOCK_MONOTONIC, &b); return (b.tv_sec - a.tv_sec) * 1e3 + (b.tv_nsec - a.tv_nsec) * 1e-6; };
+        if (ftrace) {  // (the extra synchronisation only exists under NK_FILE_TRACE)
+            fprintf(stderr, "staging issued in %.2f ms", since(ts0));
+            cudaStreamSynchronize(h->stream);
+            fprintf(stderr, ", copies complete at %.2f ms", since(ts0));
+        }
         h->last.h2d_bytes += size_real;
         if (add_nl && cudaMemsetAsync(h->d_raw + size_real, '\n', 1, h->stream) != cudaSuccess) { rc = fail(NK_ERR_CUDA, "cudaMemsetAsync"); break; }
         NvtxRange nvtx("nk:parse (FASTA/FASTQ records on the device)");
@@ -327,6 +346,7 @@ int parse_file_on_device(nk_counter* h, const char* path, bool* handled, bool* i
             NK_B(nk::launch_fasta_plan(h->d_raw, size, h->d_parse_scratch, h->d_parse_totals, h->stream));
             NK_B(cudaMemcpyAsync(h->h_parse_totals, h->d_parse_totals, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
             NK_B(cudaStreamSynchronize(h->stream));
+            if (ftrace) fprintf(stderr, ", plan done at %.2f ms", since(ts0));
             nb = h->h_parse_totals[0];
             nr = h->h_parse_totals[1];
             if ((rc = ensure_devbuf(h->staged, nb)) != NK_OK) break;
@@ -334,6 +354,7 @@ int parse_file_on_device(nk_counter* h, const char* path, bool* handled, bool* i
             NK_B(nk::launch_fasta_write(h->d_raw, size, h->d_parse_scratch, h->staged.bases, h->staged_offsets, h->stream));
             // offsets[nrec] = number of bases (h_parse_totals[0] stays put until the next parse, which synchronises first)
             NK_B(cudaMemcpyAsync(h->staged_offsets + nr, h->h_parse_totals, sizeof(unsigned long long), cudaMemcpyHostToDevice, h->stream));
+            if (ftrace) fprintf(stderr, ", write launched at %.2f ms\n", since(ts0));
         } else {
             NK_B(nk::launch_fastq_lines(h->d_raw, size, h->d_parse_scratch, h->d_parse_totals, h->stream));
             NK_B(cudaMemcpyAsync(h->h_parse_totals + 2, h->d_parse_totals + 2, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));

@@ -211,7 +211,8 @@ int count_chunk(nk_counter* h, DevBuf& b, const unsigned long long* d_offsets, u
     // Long sequences: no invalid-start bitmap at all — every tile looks the few sequence ends that reach into
     // it up in the offsets (mode 5): no memset, no marking kernels, 1/8 B per base less HBM traffic.
     const unsigned long long nseq_here = seq_hi - seq_lo;
-    const bool short_reads = nseq_here > 0 && nstarts / nseq_here < 2048 && h->cfg.k > 1;
+    const unsigned long long nseq_heur = h->nseq_hint ? h->nseq_hint : nseq_here;  // (the overlapped file path passes every record so far)
+    const bool short_reads = nseq_here > 0 && nstarts / nseq_heur < 2048 && h->cfg.k > 1;
     const char* bm_env = getenv("NK_BITMAP");  // NK_BITMAP=1: the bitmap path for long sequences too (A/B runs, tests)
     const bool force_bitmap = bm_env && atoi(bm_env) != 0;
     const int mode = h->exact ? 2 : (short_reads ? 3 : (force_bitmap || nseq_here == 0 ? 0 : 5));
@@ -1212,7 +1213,7 @@ static int process_file_device(nk_counter* h, const char* path, bool streaming, 
         unsigned long long nb = h->fp_nbases, nr = h->fp_nrec;
         if (!same) {
             bool fq = false;
-            int rc = parse_file_on_device(h, path, handled, &fq, &nb, &nr, err);
+            int rc = parse_file_on_device(h, path, handled, &fq, &nb, &nr, err, nullptr);
             if (rc != NK_OK || !*handled) return rc;
         }
         *handled = true;
@@ -1226,24 +1227,32 @@ static int process_file_device(nk_counter* h, const char* path, bool streaming, 
     }
     timespec tr0, tr1, tr2;
     clock_gettime(CLOCK_MONOTONIC, &tr0);
-    begin_call(h);
     PhaseEvents pe;
-    int rc;
-    if ((rc = get_event(h, &pe.begin)) != NK_OK) return failed(rc);
-    cudaEventRecord(pe.begin, h->stream);
+    int rc = NK_OK;
     bool fq = false;
     unsigned long long nb = 0, nr = 0;
-    rc = parse_file_on_device(h, path, handled, &fq, &nb, &nr, err);
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        begin_call(h);
+        pe = PhaseEvents{};
+        if ((rc = get_event(h, &pe.begin)) != NK_OK) return failed(rc);
+        cudaEventRecord(pe.begin, h->stream);
+        NK_TRY(zero_kmers(h));
+        h->currents_valid_overwrite = true;
+        // stage + parse + count (FASTA: the counting overlaps the read)
+        rc = parse_file_on_device(h, path, handled, &fq, &nb, &nr, err, &pe);
+        if (rc == NK_ERR_STATE && attempt == 0) {
+            // the overlapped path met more records than it had room for: void the partial counts, take the two-phase path
+            if (h->acc_dirty) { cudaMemsetAsync(h->acc, 0, h->cfg.pool_size * sizeof(unsigned int), h->stream); h->acc_dirty = false; h->acc_kmers = 0; }
+            if (h->exact) nk::exact_clear(h->xt, h->cfg.pool_size, false, h->stream);
+            h->kmers_clean = false;
+            h->file_no_overlap = true;
+            continue;
+        }
+        break;
+    }
+    h->file_no_overlap = false;
     if (rc != NK_OK || !*handled) return rc;
     clock_gettime(CLOCK_MONOTONIC, &tr1);
-    zero_kmers(h);
-    h->currents_valid_overwrite = true;
-    for (unsigned long long c0 = 0; c0 < nb && nr > 0; c0 += slice) {
-        const unsigned long long n = std::min(slice, nb - c0);
-        DevBuf view = h->staged;
-        view.bases = h->staged.bases + c0;
-        if ((rc = count_chunk(h, view, h->staged_offsets, 0, nr, c0, n, n, &pe, false)) != NK_OK) return failed(rc);
-    }
     if ((rc = fold_and_simulate(h, /*skip_zero=*/!streaming, pe, true)) != NK_OK) return failed(rc);
     if ((rc = get_event(h, &pe.end)) != NK_OK) return failed(rc);
     cudaEventRecord(pe.end, h->stream);

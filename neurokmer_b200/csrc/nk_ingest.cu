@@ -275,13 +275,11 @@ int grow(void** p, unsigned long long* cap, unsigned long long need) {
 
 }  // namespace
 
+// count_pe != null: the windows are also COUNTED here (as part of a job the caller has begun) — for FASTA chunk by
+// chunk while the rest of the file is still on its way; null: parse only (uniques pass, parity tap).
 int parse_file_on_device(nk_counter* h, const char* path, bool* handled, bool* is_fastq, unsigned long long* nbases,
-                         unsigned long long* nrec, std::string* err) {
+                         unsigned long long* nrec, std::string* err, PhaseEvents* count_pe) {
     *handled = false;
-    timespec tp0;
-    clock_gettime(CLOCK_MONOTONIC, &tp0);
-    auto since0 = [&]() { timespec b; clock_gettime(CLOCK_MONOTONIC, &b); return (b.tv_sec - tp0.tv_sec) * 1e3 + (b.tv_nsec - tp0.tv_nsec) * 1e-6; };
-    const bool ftrace0 = getenv("NK_FILE_TRACE") != nullptr;
     if (const char* e = getenv("NK_GPU_PARSE")) if (atoi(e) == 0) return NK_OK;
     if (getenv("NK_FASTA_WINDOW")) return NK_OK;  // the tests of the host reader's parallel ingest pin that path
     const int fd = ::open(path, O_RDONLY);
@@ -304,6 +302,11 @@ int parse_file_on_device(nk_counter* h, const char* path, bool* handled, bool* i
         const unsigned long long have = (unsigned long long)free_b + h->raw_cap + h->staged.bases_cap + h->line_end_cap * 8;
         if (size_real * (fastq ? 3ull : 2ull) + (size_real >> 2) + (256ull << 20) > have) { ::close(fd); return NK_OK; }
     }
+    const bool ftrace = getenv("NK_FILE_TRACE") != nullptr;
+    timespec ts0;
+    clock_gettime(CLOCK_MONOTONIC, &ts0);
+    auto since = [&]() { timespec b; clock_gettime(CLOCK_MONOTONIC, &b); return (b.tv_sec - ts0.tv_sec) * 1e3 + (b.tv_nsec - ts0.tv_nsec) * 1e-6; };
+    const unsigned long long count_slice = (0xFFFFFFFFull / nk::COUNT_TILE - 1) * nk::COUNT_TILE;
 
     int rc = NK_OK;
     do {
@@ -315,7 +318,7 @@ int parse_file_on_device(nk_counter* h, const char* path, bool* handled, bool* i
         if ((rc = grow(&h->d_parse_scratch, &h->parse_scratch_cap, nk::parse_scratch_bytes(size))) != NK_OK) break;
         if (!h->d_parse_totals) {
             if (cudaMalloc(&h->d_parse_totals, 8 * sizeof(unsigned long long)) != cudaSuccess ||
-                cudaMallocHost(&h->h_parse_totals, 8 * sizeof(unsigned long long)) != cudaSuccess) {
+                cudaMallocHost(&h->h_parse_totals, 2 * 64 * sizeof(unsigned long long)) != cudaSuccess) {
                 rc = fail(NK_ERR_OOM, "parse totals");
                 break;
             }
@@ -325,53 +328,140 @@ int parse_file_on_device(nk_counter* h, const char* path, bool* handled, bool* i
         cudaEvent_t prev = nullptr;
         if ((rc = get_event(h, &prev)) != NK_OK) break;
         if (cudaEventRecord(prev, h->stream) != cudaSuccess) { rc = fail(NK_ERR_CUDA, "cudaEventRecord"); break; }
-        timespec ts0, ts1;
-        if (ftrace0) fprintf(stderr, "[file trace] staging starts at %.2f ms; ", since0());
-        clock_gettime(CLOCK_MONOTONIC, &ts0);
-        if ((rc = stage_to_device(h, nullptr, fd, 0, size_real, h->d_raw, prev, h->stream)) != NK_OK) break;
-        clock_gettime(CLOCK_MONOTONIC, &ts1);
-        const bool ftrace = getenv("NK_FILE_TRACE") != nullptr;
-        auto since = [&](const timespec& a) { timespec b; clock_gettime(CLOCK_MONOTONIC, &b); return (b.tv_sec - a.tv_sec) * 1e3 + (b.tv_nsec - a.tv_nsec) * 1e-6; };
-        if (ftrace) {  // (the extra synchronisation only exists under NK_FILE_TRACE)
-            fprintf(stderr, "staging issued in %.2f ms", since(ts0));
-            cudaStreamSynchronize(h->stream);
-            fprintf(stderr, ", copies complete at %.2f ms", since(ts0));
-        }
-        h->last.h2d_bytes += size_real;
-        if (add_nl && cudaMemsetAsync(h->d_raw + size_real, '\n', 1, h->stream) != cudaSuccess) { rc = fail(NK_ERR_CUDA, "cudaMemsetAsync"); break; }
         NvtxRange nvtx("nk:parse (FASTA/FASTQ records on the device)");
         unsigned long long nb = 0, nr = 0;
+        h->last.h2d_bytes += size_real;
 #define NK_B(expr) { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { rc = fail(e_ == cudaErrorMemoryAllocation ? NK_ERR_OOM : NK_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); break; } }
-        if (!fastq) {
-            NK_B(nk::launch_fasta_plan(h->d_raw, size, h->d_parse_scratch, h->d_parse_totals, h->stream));
-            NK_B(cudaMemcpyAsync(h->h_parse_totals, h->d_parse_totals, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
-            NK_B(cudaStreamSynchronize(h->stream));
-            if (ftrace) fprintf(stderr, ", plan done at %.2f ms", since(ts0));
-            nb = h->h_parse_totals[0];
-            nr = h->h_parse_totals[1];
-            if ((rc = ensure_devbuf(h->staged, nb)) != NK_OK) break;
-            if ((rc = ensure_offsets(&h->staged_offsets, &h->staged_offsets_cap, nr + 1)) != NK_OK) break;
-            NK_B(nk::launch_fasta_write(h->d_raw, size, h->d_parse_scratch, h->staged.bases, h->staged_offsets, h->stream));
-            // offsets[nrec] = number of bases (h_parse_totals[0] stays put until the next parse, which synchronises first)
-            NK_B(cudaMemcpyAsync(h->staged_offsets + nr, h->h_parse_totals, sizeof(unsigned long long), cudaMemcpyHostToDevice, h->stream));
-            if (ftrace) fprintf(stderr, ", write launched at %.2f ms\n", since(ts0));
-        } else {
-            NK_B(nk::launch_fastq_lines(h->d_raw, size, h->d_parse_scratch, h->d_parse_totals, h->stream));
-            NK_B(cudaMemcpyAsync(h->h_parse_totals + 2, h->d_parse_totals + 2, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
-            NK_B(cudaStreamSynchronize(h->stream));
-            const unsigned long long nlines = h->h_parse_totals[2];
-            unsigned long long le_bytes = h->line_end_cap * 8;
-            if ((rc = grow((void**)&h->d_line_end, &le_bytes, (nlines + 1) * 8)) != NK_OK) break;
-            h->line_end_cap = le_bytes / 8;
-            // sequence lines are at most half of a well-formed file; a malformed one may keep more (dropped later)
+        unsigned long long* const carry = h->d_parse_totals + 5;
+        NK_B(cudaMemsetAsync(carry, 0, 3 * sizeof(unsigned long long), h->stream));
+        const unsigned long long SEGB = nk::parse_segment_bytes();
+        const unsigned long long nseg_all = (size + SEGB - 1) / SEGB;
+        // Overlapped FASTA job: the file arrives in super-chunks; the records of a chunk are parsed (the scan carries its
+        // state from chunk to chunk) and its windows are counted while the next chunk is still being read.  A window is
+        // counted once all of its k bases have been parsed: after chunk c the starts up to (bases so far) - (k-1), rounded
+        // down to 16; the record that is open at the end of a chunk ends, provisionally, where the parsed bases end.
+        // At most 62 chunks (their totals come back through a small pinned ring, read one chunk late).
+        unsigned long long chunk = 16ull << 20;
+        if (const char* e = getenv("NK_FILE_CHUNK_MB")) { const unsigned long long t = strtoull(e, nullptr, 10); if (t >= 1 && t <= 4096) chunk = t << 20; }
+        while ((size + chunk - 1) / chunk > 62) chunk *= 2;
+        const bool overlapped = !fastq && count_pe != nullptr && size > 2 * chunk && !h->file_no_overlap;
+        if (overlapped) {
+            // upper bounds: every byte a base; records are discovered on the way (a file with more than the offsets buffer
+            // holds falls back to the two-phase path below)
             if ((rc = ensure_devbuf(h->staged, size)) != NK_OK) break;
-            if ((rc = ensure_offsets(&h->staged_offsets, &h->staged_offsets_cap, nlines / 4 + 2)) != NK_OK) break;
-            NK_B(nk::launch_fastq_write(h->d_raw, size, size_real, h->d_parse_scratch, h->staged.bases, h->staged_offsets, h->d_line_end,
-                                        nlines, h->d_parse_totals, h->stream));
-            NK_B(cudaMemcpyAsync(h->h_parse_totals, h->d_parse_totals, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
-            NK_B(cudaStreamSynchronize(h->stream));
-            nb = h->h_parse_totals[0];
-            nr = h->h_parse_totals[1];
+            if ((rc = ensure_offsets(&h->staged_offsets, &h->staged_offsets_cap, 1u << 20)) != NK_OK) break;
+            const unsigned long long ocap = h->staged_offsets_cap;
+            // an end that has not been parsed yet reads as "infinitely far": the write kernels fill in real starts (= the
+            // previous record's end) as records appear, whatever is still open ends beyond every window counted so far
+            NK_B(cudaMemsetAsync(h->staged_offsets, 0xFF, ocap * sizeof(unsigned long long), h->stream));
+            const unsigned long long nchunks = (size + chunk - 1) / chunk;
+            std::vector<cudaEvent_t> planned(nchunks, nullptr);
+            unsigned long long counted = 0, seq_open = 0;   // window starts counted so far; index of the open record
+            bool overflow = false;
+            auto count_upto = [&](unsigned long long c, bool final) -> int {
+                // totals of chunk c are on the host (its event has completed)
+                const unsigned long long nbc = h->h_parse_totals[2 * c], nrc = h->h_parse_totals[2 * c + 1];
+                if (nrc + 1 > ocap) { overflow = true; return NK_OK; }
+                if (nrc == 0) return NK_OK;  // (cannot happen: the file starts with '>')
+                unsigned long long upto = final ? nbc : (nbc >= h->cfg.k - 1 ? (nbc - (h->cfg.k - 1)) / 16 * 16 : 0);
+                if (final) {  // the last record ends where the bases end
+                    cudaError_t e = cudaMemcpyAsync(h->staged_offsets + nrc, h->h_parse_totals + 2 * c, sizeof(unsigned long long),
+                                                    cudaMemcpyHostToDevice, h->stream);
+                    if (e != cudaSuccess) return fail(NK_ERR_CUDA, "cudaMemcpyAsync(offsets end): %s", cudaGetErrorString(e));
+                }
+                // every record seen so far is handed to the kernels (the one that holds `counted` is somewhere among the
+                // last few; empty records can pile up on one position); the short-read heuristic gets the records of
+                // this range only
+                h->nseq_hint = nrc - seq_open;
+                while (counted < upto) {
+                    const unsigned long long n = std::min(count_slice, upto - counted);
+                    DevBuf view = h->staged;
+                    view.bases = h->staged.bases + counted;
+                    const int r = count_chunk(h, view, h->staged_offsets, 0, nrc, counted, n, n, count_pe, false);
+                    if (r != NK_OK) { h->nseq_hint = 0; return r; }
+                    counted += n;
+                }
+                h->nseq_hint = 0;
+                seq_open = nrc - 1;
+                return NK_OK;
+            };
+            cudaError_t ce = cudaSuccess;
+            for (unsigned long long c = 0; c < nchunks && rc == NK_OK && !overflow; ++c) {
+                const unsigned long long c0 = c * chunk, c1 = std::min(size, c0 + chunk);
+                rc = stage_to_device(h, nullptr, fd, c0, std::min(c1, size_real) - c0, h->d_raw + c0, c == 0 ? prev : nullptr, h->stream);
+                if (rc != NK_OK) break;
+                const unsigned long long s0 = c0 / SEGB, s1 = c + 1 == nchunks ? nseg_all : c1 / SEGB;
+                ce = nk::launch_fasta_plan(h->d_raw, size, s0, s1 - s0, h->d_parse_scratch, h->d_parse_totals, carry, h->stream);
+                if (ce == cudaSuccess) ce = nk::launch_fasta_write(h->d_raw, size, s0, s1 - s0, h->d_parse_scratch, h->staged.bases, h->staged_offsets, ocap, h->stream);
+                if (ce == cudaSuccess) ce = cudaMemcpyAsync(h->h_parse_totals + 2 * c, h->d_parse_totals, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream);
+                if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&planned[c], cudaEventDisableTiming);
+                if (ce == cudaSuccess) ce = cudaEventRecord(planned[c], h->stream);
+                if (ce != cudaSuccess) break;
+                if (c > 0) {  // the previous chunk's totals have long arrived: count its windows behind this chunk's parse
+                    ce = cudaEventSynchronize(planned[c - 1]);
+                    if (ce != cudaSuccess) break;
+                    rc = count_upto(c - 1, false);
+                }
+            }
+            if (rc == NK_OK && ce == cudaSuccess && !overflow) {
+                ce = cudaEventSynchronize(planned[nchunks - 1]);
+                if (ce == cudaSuccess) rc = count_upto(nchunks - 1, true);
+            }
+            if (ftrace) fprintf(stderr, "[file trace] overlapped: %llu chunks, last count enqueued at %.2f ms\n", nchunks, since());
+            for (cudaEvent_t e : planned) if (e) cudaEventDestroy(e);
+            if (ce != cudaSuccess) { rc = fail(NK_ERR_CUDA, "overlapped file parse: %s", cudaGetErrorString(ce)); break; }
+            if (rc != NK_OK) break;
+            if (overflow) {
+                // more records than the offsets buffer holds: what was counted so far is void — the caller starts the job
+                // again through the two-phase path (NK_ERR_STATE is caught by process_file_device)
+                rc = NK_ERR_STATE;
+                break;
+            }
+            nb = h->h_parse_totals[2 * (nchunks - 1)];
+            nr = h->h_parse_totals[2 * (nchunks - 1) + 1];
+        } else {
+            if ((rc = stage_to_device(h, nullptr, fd, 0, size_real, h->d_raw, prev, h->stream)) != NK_OK) break;
+            if (ftrace) fprintf(stderr, "[file trace] staging issued at %.2f ms\n", since());
+            if (add_nl) NK_B(cudaMemsetAsync(h->d_raw + size_real, '\n', 1, h->stream));
+            if (!fastq) {
+                NK_B(nk::launch_fasta_plan(h->d_raw, size, 0, nseg_all, h->d_parse_scratch, h->d_parse_totals, carry, h->stream));
+                NK_B(cudaMemcpyAsync(h->h_parse_totals, h->d_parse_totals, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+                NK_B(cudaStreamSynchronize(h->stream));
+                nb = h->h_parse_totals[0];
+                nr = h->h_parse_totals[1];
+                if ((rc = ensure_devbuf(h->staged, nb)) != NK_OK) break;
+                if ((rc = ensure_offsets(&h->staged_offsets, &h->staged_offsets_cap, nr + 1)) != NK_OK) break;
+                NK_B(nk::launch_fasta_write(h->d_raw, size, 0, nseg_all, h->d_parse_scratch, h->staged.bases, h->staged_offsets,
+                                            h->staged_offsets_cap, h->stream));
+                // offsets[nrec] = number of bases (h_parse_totals[0] stays put until the next parse, which synchronises first)
+                NK_B(cudaMemcpyAsync(h->staged_offsets + nr, h->h_parse_totals, sizeof(unsigned long long), cudaMemcpyHostToDevice, h->stream));
+            } else {
+                NK_B(nk::launch_fastq_lines(h->d_raw, size, h->d_parse_scratch, h->d_parse_totals, h->stream));
+                NK_B(cudaMemcpyAsync(h->h_parse_totals + 2, h->d_parse_totals + 2, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+                NK_B(cudaStreamSynchronize(h->stream));
+                const unsigned long long nlines = h->h_parse_totals[2];
+                unsigned long long le_bytes = h->line_end_cap * 8;
+                if ((rc = grow((void**)&h->d_line_end, &le_bytes, (nlines + 1) * 8)) != NK_OK) break;
+                h->line_end_cap = le_bytes / 8;
+                // sequence lines are at most half of a well-formed file; a malformed one may keep more (dropped later)
+                if ((rc = ensure_devbuf(h->staged, size)) != NK_OK) break;
+                if ((rc = ensure_offsets(&h->staged_offsets, &h->staged_offsets_cap, nlines / 4 + 2)) != NK_OK) break;
+                NK_B(nk::launch_fastq_write(h->d_raw, size, size_real, h->d_parse_scratch, h->staged.bases, h->staged_offsets, h->d_line_end,
+                                            nlines, h->d_parse_totals, h->stream));
+                NK_B(cudaMemcpyAsync(h->h_parse_totals, h->d_parse_totals, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+                NK_B(cudaStreamSynchronize(h->stream));
+                nb = h->h_parse_totals[0];
+                nr = h->h_parse_totals[1];
+            }
+            if (count_pe) {  // the whole file is parsed: count it like a staged batch
+                for (unsigned long long c0 = 0; c0 < nb && nr > 0 && rc == NK_OK; c0 += count_slice) {
+                    const unsigned long long n = std::min(count_slice, nb - c0);
+                    DevBuf view = h->staged;
+                    view.bases = h->staged.bases + c0;
+                    rc = count_chunk(h, view, h->staged_offsets, 0, nr, c0, n, n, count_pe, false);
+                }
+                if (rc != NK_OK) break;
+            }
         }
 #undef NK_B
         *nbases = nb;
@@ -439,7 +529,7 @@ int nk_debug_parse_file(nk_counter* h, const char* path, uint64_t* nrecords, uin
     bool handled = false, fq = false;
     unsigned long long nb = 0, nr = 0;
     std::string err;
-    NK_TRY(parse_file_on_device(h, path, &handled, &fq, &nb, &nr, &err));
+    NK_TRY(parse_file_on_device(h, path, &handled, &fq, &nb, &nr, &err, nullptr));
     if (!handled) return fail(NK_ERR_UNSUPPORTED, "%s: not a plain regular FASTA/FASTQ file the device parser takes", path);
     std::vector<uint8_t> bases(nb ? nb : 1);
     std::vector<uint64_t> offs(nr + 1);

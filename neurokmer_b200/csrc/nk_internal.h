@@ -178,6 +178,8 @@ struct nk_counter {
     unsigned long long* d_parse_totals = nullptr;  // 8 u64
     unsigned long long* h_parse_totals = nullptr;  // pinned mirror
     // the parsed file that still sits in `staged` / `staged_offsets` (the uniques pass re-uses it instead of a second read)
+    bool file_no_overlap = false;           // retry of a file whose records outgrew the overlapped path's offsets buffer
+    unsigned long long nseq_hint = 0;       // sequences that actually lie in the range being counted (heuristics only)
     bool fp_valid = false;
     std::string fp_path;
     unsigned long long fp_size = 0, fp_mtime_ns = 0, fp_nbases = 0, fp_nrec = 0;
@@ -254,8 +256,9 @@ int stage_to_device(nk_counter* h, const uint8_t* src, int fd, uint64_t off, uin
 void stage_pool_destroy(nk_counter* h);
 // Whole plain FASTA / FASTQ file -> h->staged (bases) + h->staged_offsets, parsed on the device.
 // *handled = false (and NK_OK): this path does not apply (compressed, not a regular file, too large, disabled)
+// count_pe != null: the caller has begun a job and the windows are counted here as well (FASTA: overlapped with the read)
 int parse_file_on_device(nk_counter* h, const char* path, bool* handled, bool* is_fastq, unsigned long long* nbases,
-                         unsigned long long* nrec, std::string* err);
+                         unsigned long long* nrec, std::string* err, PhaseEvents* count_pe);
 void ingest_free(nk_counter* h);
 int uniques_chunk(nk_counter* h, DevBuf& b, const unsigned long long* d_offsets, unsigned long long seq_lo,
                   unsigned long long seq_hi, unsigned long long origin, unsigned long long nstarts, bool packed);

@@ -318,10 +318,15 @@ cudaError_t launch_filter_set(unsigned int* filter, const unsigned long long* id
 // record parsing on the device (nk_parse.cu).  `file`: raw bytes, 16-byte aligned, readable up to size + 16.
 // totals (device, 8 u64): [0] bases, [1] records, [2] newlines, [3] kept bytes incl. dropped records, [4] first bad record
 size_t parse_scratch_bytes(unsigned long long size);
-cudaError_t launch_fasta_plan(const unsigned char* file, unsigned long long size, void* scratch,
-                              unsigned long long* totals, cudaStream_t s);
-cudaError_t launch_fasta_write(const unsigned char* file, unsigned long long size, void* scratch, unsigned char* bases,
-                               unsigned long long* offsets, cudaStream_t s);
+// FASTA: segments [seg_first, seg_first + nseg) of the raw bytes (units of parse_segment_bytes(); a whole file: 0, all).
+// carry (device, 3 u64, zero for a file's first range): what the earlier segments left behind; updated for the next range.
+unsigned long long parse_segment_bytes();
+cudaError_t launch_fasta_plan(const unsigned char* file, unsigned long long size, unsigned long long seg_first,
+                              unsigned long long nseg, void* scratch, unsigned long long* totals, unsigned long long* carry,
+                              cudaStream_t s);
+cudaError_t launch_fasta_write(const unsigned char* file, unsigned long long size, unsigned long long seg_first,
+                               unsigned long long nseg, void* scratch, unsigned char* bases, unsigned long long* offsets,
+                               unsigned long long offsets_cap, cudaStream_t s);
 cudaError_t launch_fastq_lines(const unsigned char* file, unsigned long long size, void* scratch,
                                unsigned long long* totals, cudaStream_t s);
 cudaError_t launch_fastq_write(const unsigned char* file, unsigned long long size, unsigned long long size_real, void* scratch,

@@ -150,9 +150,9 @@ struct FaSummary {           // per segment
 };
 
 __global__ void __launch_bounds__(PT) fa_summary_kernel(const unsigned char* __restrict__ file, unsigned long long size,
-                                                         FaSummary* __restrict__ sum) {
+                                                         unsigned long long seg_first, FaSummary* __restrict__ sum) {
     __shared__ unsigned s_ev[PT / 32], s_hs[PT / 32], s_red[3][PT / 32];
-    const unsigned long long seg0 = (unsigned long long)blockIdx.x * SEG;
+    const unsigned long long seg0 = (seg_first + blockIdx.x) * SEG;
     unsigned carry0 = 0, carry1 = 1;   // the two assumptions about the state at the segment's first byte
     unsigned k0 = 0, k1 = 0, nrec = 0;
     for (int it = 0; it < SEG_ITERS; ++it) {
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(PT) fa_summary_kernel(const unsigned char* __r
         // any event in the segment <=> both assumptions ended in the same state ... or the segment is event-free and
         // they still differ: then it passes its incoming state on
         s.event = carry0 == carry1 ? (1u | (carry0 << 1)) : 0u;
-        sum[blockIdx.x] = s;
+        sum[seg_first + blockIdx.x] = s;
     }
 }
 
@@ -195,13 +195,21 @@ struct SegPrefix {               // per segment, after the one-block scan
 };
 
 // one block: sequential meaning, parallel execution — thread t owns a contiguous run of segments
-__global__ void __launch_bounds__(1024) fa_scan_kernel(const FaSummary* __restrict__ sum, unsigned long long nseg,
-                                                        SegPrefix* __restrict__ pre, unsigned long long* __restrict__ totals) {
+// Scans the segments [seg_first, seg_first + nseg).  carry (device, 3 u64: state, bases, records) is what the segments
+// before them left behind — {0, 0, 0} for a whole file — and is updated for the next range (files parsed chunk by chunk).
+__global__ void __launch_bounds__(1024) fa_scan_kernel(const FaSummary* __restrict__ sum, unsigned long long seg_first,
+                                                        unsigned long long nseg, SegPrefix* __restrict__ pre,
+                                                        unsigned long long* __restrict__ totals, unsigned long long* __restrict__ carry) {
     __shared__ unsigned s_event[1024];
     __shared__ unsigned long long s_out[1024], s_rec[1024];
     const unsigned t = threadIdx.x;
+    sum += seg_first;
+    pre += seg_first;
     const unsigned long long per = (nseg + 1023) / 1024;
-    const unsigned long long a = (unsigned long long)t * per, b = a + per < nseg ? a + per : nseg;
+    const unsigned long long a = (unsigned long long)t * per < nseg ? (unsigned long long)t * per : nseg;
+    const unsigned long long b = a + per < nseg ? a + per : nseg;
+    const unsigned carry_state = (unsigned)carry[0];
+    const unsigned long long carry_out = carry[1], carry_rec = carry[2];
     unsigned ev = 0;
     for (unsigned long long s = a; s < b; ++s) {
         const unsigned e = sum[s].event;
@@ -209,7 +217,7 @@ __global__ void __launch_bounds__(1024) fa_scan_kernel(const FaSummary* __restri
     }
     s_event[t] = ev;
     __syncthreads();
-    unsigned state = 0;  // the file starts at a line start, outside a header (its first '>' is an event)
+    unsigned state = carry_state;  // a file starts at a line start, outside a header (its first '>' is an event)
     for (int q = (int)t - 1; q >= 0; --q)
         if (s_event[q] & 1u) { state = s_event[q] >> 1; break; }
     unsigned long long out = 0, rec = 0;
@@ -222,15 +230,19 @@ __global__ void __launch_bounds__(1024) fa_scan_kernel(const FaSummary* __restri
     }
     s_out[t] = out; s_rec[t] = rec;
     __syncthreads();
+    __shared__ unsigned s_last_state;
+    if (t == 1023) s_last_state = st;  // state behind the last segment of the range (empty thread ranges pass it on)
+    __syncthreads();
     if (t == 0) {
-        unsigned long long ro = 0, rr = 0;
+        unsigned long long ro = carry_out, rr = carry_rec;
         for (int q = 0; q < 1024; ++q) {
             const unsigned long long o = s_out[q], r = s_rec[q];
             s_out[q] = ro; s_rec[q] = rr;
             ro += o; rr += r;
         }
-        totals[0] = ro;  // bases
-        totals[1] = rr;  // records
+        totals[0] = ro;  // bases so far
+        totals[1] = rr;  // records so far
+        carry[0] = s_last_state; carry[1] = ro; carry[2] = rr;
     }
     __syncthreads();
     out = s_out[t]; rec = s_rec[t]; st = state;
@@ -262,12 +274,13 @@ __device__ __forceinline__ void flush_bytes(unsigned char* __restrict__ dst, uns
 }
 
 __global__ void __launch_bounds__(PT) fa_write_kernel(const unsigned char* __restrict__ file, unsigned long long size,
-                                                       const SegPrefix* __restrict__ pre, unsigned char* __restrict__ bases,
-                                                       unsigned long long* __restrict__ offsets) {
+                                                       unsigned long long seg_first, const SegPrefix* __restrict__ pre,
+                                                       unsigned char* __restrict__ bases, unsigned long long* __restrict__ offsets,
+                                                       unsigned long long offsets_cap) {
     __shared__ unsigned s_ev[PT / 32], s_hs[PT / 32], s_warp[PT / 32];
     __shared__ __align__(16) unsigned char s_buf[STEP + 32];
-    const unsigned long long seg0 = (unsigned long long)blockIdx.x * SEG;
-    const SegPrefix p = pre[blockIdx.x];
+    const unsigned long long seg0 = (seg_first + blockIdx.x) * SEG;
+    const SegPrefix p = pre[seg_first + blockIdx.x];
     unsigned long long out_pos = p.out, rec = p.rec;
     unsigned carry = p.state;
     for (int it = 0; it < SEG_ITERS; ++it) {
@@ -300,7 +313,7 @@ __global__ void __launch_bounds__(PT) fa_write_kernel(const unsigned char* __res
         unsigned rs = 0;
         for (unsigned m = t.S; m; m &= m - 1, ++rs) {
             const unsigned j = __ffs(m) - 1;
-            offsets[rec + mine_s + rs] = out_pos + mine + __popc(keep & ((1u << j) - 1u));
+            if (rec + mine_s + rs < offsets_cap) offsets[rec + mine_s + rs] = out_pos + mine + __popc(keep & ((1u << j) - 1u));
         }
         __syncthreads();
         flush_bytes(bases, out_pos, total, s_buf);
@@ -463,25 +476,31 @@ size_t parse_scratch_bytes(unsigned long long size) {
     return (size_t)(nseg * (sizeof(FaSummary) + sizeof(SegPrefix) + 2 * sizeof(unsigned)) + 256);
 }
 
-cudaError_t launch_fasta_plan(const unsigned char* file, unsigned long long size, void* scratch,
-                              unsigned long long* totals, cudaStream_t s) {
-    const unsigned long long nseg = nseg_of(size);
-    if (nseg == 0 || nseg > 0x7FFFFFFFull) return cudaErrorInvalidValue;
+// segments [seg_first, seg_first + nseg) of the raw bytes (a whole file: 0, all); carry: see fa_scan_kernel.
+// The range must end at the end of the file or at a multiple of parse_segment_bytes().
+cudaError_t launch_fasta_plan(const unsigned char* file, unsigned long long size, unsigned long long seg_first,
+                              unsigned long long nseg, void* scratch, unsigned long long* totals, unsigned long long* carry,
+                              cudaStream_t s) {
+    const unsigned long long nseg_all = nseg_of(size);
+    if (nseg == 0 || nseg_all > 0x7FFFFFFFull) return cudaErrorInvalidValue;
     FaSummary* sum = reinterpret_cast<FaSummary*>(scratch);
-    SegPrefix* pre = reinterpret_cast<SegPrefix*>(sum + nseg);
-    fa_summary_kernel<<<(unsigned)nseg, PT, 0, s>>>(file, size, sum);
-    fa_scan_kernel<<<1, 1024, 0, s>>>(sum, nseg, pre, totals);
+    SegPrefix* pre = reinterpret_cast<SegPrefix*>(sum + nseg_all);
+    fa_summary_kernel<<<(unsigned)nseg, PT, 0, s>>>(file, size, seg_first, sum);
+    fa_scan_kernel<<<1, 1024, 0, s>>>(sum, seg_first, nseg, pre, totals, carry);
     return cudaGetLastError();
 }
 
-cudaError_t launch_fasta_write(const unsigned char* file, unsigned long long size, void* scratch, unsigned char* bases,
-                               unsigned long long* offsets, cudaStream_t s) {
-    const unsigned long long nseg = nseg_of(size);
+cudaError_t launch_fasta_write(const unsigned char* file, unsigned long long size, unsigned long long seg_first,
+                               unsigned long long nseg, void* scratch, unsigned char* bases, unsigned long long* offsets,
+                               unsigned long long offsets_cap, cudaStream_t s) {
+    const unsigned long long nseg_all = nseg_of(size);
     FaSummary* sum = reinterpret_cast<FaSummary*>(scratch);
-    SegPrefix* pre = reinterpret_cast<SegPrefix*>(sum + nseg);
-    fa_write_kernel<<<(unsigned)nseg, PT, 0, s>>>(file, size, pre, bases, offsets);
+    SegPrefix* pre = reinterpret_cast<SegPrefix*>(sum + nseg_all);
+    fa_write_kernel<<<(unsigned)nseg, PT, 0, s>>>(file, size, seg_first, pre, bases, offsets, offsets_cap);
     return cudaGetLastError();
 }
+
+unsigned long long parse_segment_bytes() { return SEG; }
 
 cudaError_t launch_fastq_lines(const unsigned char* file, unsigned long long size, void* scratch,
                                unsigned long long* totals /* [2] <- number of '\n' */, cudaStream_t s) {

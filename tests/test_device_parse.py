@@ -186,3 +186,55 @@ def test_pageable_batches_take_the_staging_pool():
         assert_state_equal(d, o)
     finally:
         del os.environ["NK_STAGE_POOL"]
+
+
+@pytest.mark.parametrize("case", ["records_60col", "tiny_records", "crlf_single_lines", "more_records_than_the_offsets_buffer"])
+def test_overlapped_fasta_file_path(tmp_path, case, monkeypatch):
+    """Large FASTA files are parsed and counted chunk by chunk while the rest of the file is still being read (the
+    scan carries its state from chunk to chunk; the record open at the end of a chunk ends "infinitely far").  Forced
+    here with 1 MiB chunks: record boundaries next to chunk boundaries, records shorter than k, empty records piling
+    up on one position, CRLF, and a file with more records than the overlapped path has room for (it falls back to
+    the two-phase path).  Same pool state as the host reader's path and as the oracle on the records."""
+    from neurokmer_b200 import flatten
+    rng = np.random.default_rng(abs(hash(case)) % 2**32)
+    k, pool = 31, 70_001
+    if case == "records_60col":
+        lens = [1_500_000, 20, 0, 0, 0, 31, 30, 900_000, 1, 1_048_576 - 40, 64, 700_000, 5]
+        seqs = [random_dna(rng, n, 0.002, 0.02) for n in lens]
+        data = fasta_bytes(rng, seqs, 60)
+    elif case == "tiny_records":
+        seqs = [random_dna(rng, int(n), 0.01) for n in rng.integers(0, 120, size=60_000)]
+        data = fasta_bytes(rng, seqs, 70)
+    elif case == "crlf_single_lines":
+        seqs = [random_dna(rng, n, 0.001) for n in (1_200_000, 800_000, 40, 1_500_000)]
+        data = fasta_bytes(rng, seqs, 0, b"\r\n", final_eol=False)
+    else:
+        seqs = [b"ACGTACGTACGTACGTACGTACGTACGTACGTAC"] * 1_060_000   # > 2^20 records of 34 bases
+        data = b"".join(b">r\n" + s + b"\n" for s in seqs)
+    p = tmp_path / "big.fa"
+    p.write_bytes(data)
+    assert len(data) > 3 * (1 << 20)
+    o = oracle_counter(k, pool)
+    o.process_streaming([flatten(seqs)])
+    monkeypatch.setenv("NK_FILE_CHUNK_MB", "1")
+    dev = make(k, pool)
+    dev.set_file_uniques(20)
+    dev.process_file_streaming(str(p))
+    assert dev.timings()["kmers"] == sum(max(0, len(s) - k + 1) for s in seqs)
+    assert_state_equal(dev, o); assert_topn_equal(dev, o, 20)
+    rows = dev.top_abundant_neurons(20)
+    monkeypatch.setenv("NK_GPU_PARSE", "0")
+    host = make(k, pool)
+    host.set_file_uniques(20)
+    host.process_file_streaming(str(p))
+    assert rows == host.top_abundant_neurons(20)           # including the uniques column (resident parsed file re-used)
+    monkeypatch.delenv("NK_GPU_PARSE")
+    # a second job on the same counter (carried state) and the exact-table mode go through the same chunks
+    o.process_streaming([flatten(seqs)])
+    dev.process_file_streaming(str(p))
+    assert_state_equal(dev, o)
+    if case == "records_60col":
+        e = make(k, pool); e.enable_exact_counts(True)
+        e.process_file_streaming(str(p))
+        np.testing.assert_array_equal(e.currents(), dev.currents())
+        assert int(e.exact_table()[1].sum()) == dev.timings()["kmers"]

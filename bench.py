@@ -538,6 +538,52 @@ def gpu_arm(args):
         st, ph, s_top, _ = timed(job_resident, args.steps)
         strong = (st, ph, s_top, c.energy.total_spikes())
         staged_now.update(nb=nb, nseq=nseq)
+    # ---- configs[4] (N > 1): 1.25 Gbase per GPU of ONE stream of 100 Mbase sequences (10 Gbp at N=8), pool 16 M ----
+    config5 = None
+    if world > 1 and peer and args.workload == "config2" and not args.no_config5:
+        K5, POOL5, SEED5, PER5, SEQ5, STEPS5 = 31, 16_000_000, 5, 1_250_000_000, 100_000_000, 5
+        total5 = world * PER5
+        offs5 = np.array(list(range(0, total5, SEQ5)) + [total5], np.uint64)
+        kmers5 = int(sum(max(0, int(offs5[i + 1] - offs5[i]) - K5 + 1) for i in range(len(offs5) - 1)))
+        lo5, hi5 = rank * PER5, (rank + 1) * PER5
+        po5 = shard_of(offs5, lo5, hi5)
+        c5 = SpikingKmerCounter(K5, LIF_REF["threshold"], LIF_REF["leak"], LIF_REF["refractory"], LIF_REF["spike_cost"],
+                                POOL5, True, device=local)
+        handle5, _ = c5.dist_export()
+        handles5 = [None] * world
+        dist.all_gather_object(handles5, handle5)
+        c5.dist_setup(rank, world, handles=b"".join(handles5))
+        db5, do5 = c5.stage_reserve(int(po5[-1]), len(po5) - 1)
+        c5.synth_fill(db5, SEED5, lo5, int(po5[-1]), 1)
+        copy_h2d(do5, po5)
+        c5.synchronize()
+        barrier()   # also separates the setup from the first signal
+        stream5 = torch.cuda.ExternalStream(c5.cuda_stream(), device=torch.device("cuda", local))
+        ms5, top5 = 0.0, None
+        for it in range(2 + STEPS5):
+            barrier()
+            with torch.cuda.stream(stream5):
+                flush.fill_(1)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream5)
+            c5.reset(); c5.stream_begin(); c5.process_staged(int(po5[-1]), len(po5) - 1, 1); c5.dist_run()
+            with torch.cuda.stream(stream5):
+                e1.record(stream5)
+            top5 = c5.top_abundant_neurons(TOPN)
+            e1.synchronize()
+            if it >= 2:
+                ms5 += e0.elapsed_time(e1)
+        t5 = torch.tensor([ms5], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t5, op=dist.ReduceOp.MAX)
+        ph5 = c5.timings()
+        config5 = {"workload": f"configs[4]: {total5 / 1e9:.2f} Gbp in 100 Mbase sequences cut over {world} GPUs, k=31, pool 16M, canonical, streaming",
+                   "value": kmers5 * STEPS5 / (float(t5[0]) * 1e-3), "unit": "kmers/s", "ms_per_step": float(t5[0]) / STEPS5, "steps": STEPS5,
+                   "kmers_per_step": kmers5, "count_ms": ph5["count_ms"], "post_ms": ph5["post_ms"],
+                   "exchange_ms": {"wait": ph5["exch_wait_ms"], "reduce": ph5["exch_reduce_ms"], "merge": ph5["merge_ms"]},
+                   # no oracle run at this size (10 Gbp): the property the domain offers — every window counted exactly once
+                   "check": {"kmers_counted_equal_windows": bool(int(ph5["kmers"]) == kmers5), "total_spikes": c5.energy.total_spikes(),
+                             "top1": list(top5[0][:2]) if top5 else None}}
+        c5.close()
     clocks = sampler.stop() if sampler else None
 
     if os.environ.get("NK_TRACE"):
@@ -719,6 +765,7 @@ def gpu_arm(args):
             "strong_scaling": None if not strong else {
                 "value": KMERS * args.steps / (strong_ms * 1e-3), "unit": "kmers/s", "ms_per_step": strong_ms / args.steps,
                 "kmers_per_step": KMERS, "note": "the N=1 job (113 Mbase, 7 sequences) cut by window start into N ranges"},
+            "config5": config5,
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "result": {"total_spikes": total_spikes, "top1": list(top[0][:2]) if top else None, "parity": parity},
         }
@@ -770,6 +817,7 @@ def main():
     ap.add_argument("--workload", default="config2", choices=["config2", "config5"])
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (large workloads)")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the job's result (large workloads)")
+    ap.add_argument("--no-config5", action="store_true", help="N > 1: skip the configs[4] sub-record (1.25 Gbase per GPU, pool 16M)")
     ap.add_argument("--dist", default="peer", choices=["peer", "fused", "allreduce"],
                     help="N > 1: peer = sharded pool, every exchange through NVLink peer memory inside the kernels (default); "
                          "fused = same kernels with an NCCL barrier + all-gather around them; allreduce = NCCL all-reduce of the currents")

@@ -246,10 +246,13 @@ private:
 static StagePool* pool_of(nk_counter* h) {
     if (!h->stage_pool) {
         unsigned n = std::thread::hardware_concurrency();
-        // measured on the 16-vCPU B200 boxes (tools/stage_sweep.py, profiles/r02_bench.md): 113 MB of pageable memory
-        // in 8.7 / 4.6 / 2.9 / 4.0 / 4.9 ms with 1 / 2 / 4 / 8 / 12 threads and 2 MiB pieces — beyond four the threads
-        // fight the DMA engine for host memory bandwidth (the slots stop fitting the last-level cache)
-        if (n > 4) n = 4;
+        // Measured on the 16-vCPU B200 boxes (tools/stage_sweep.py, profiles/r02_bench.md), 113 MB, 2 MiB pieces, workers
+        // that stay hot between the chunks of a job: pageable batch 3.9 / 3.05 / 2.94 / 2.99 / 2.91 ms and FASTA file
+        // 6.2 / 4.7 / 4.6 / 4.05 / 3.43 ms with 3 / 4 / 5 / 6 / 8 threads (pread copies slower per thread than memcpy).
+        // Eight, but never more than this GPU's share of the host's cores (one process per GPU on an 8-GPU box).
+        int ngpu = 1;
+        if (cudaGetDeviceCount(&ngpu) != cudaSuccess || ngpu < 1) { cudaGetLastError(); ngpu = 1; }
+        n = std::min(8u, std::max(2u, n / (unsigned)ngpu));
         if (const char* e = getenv("NK_STAGE_THREADS")) n = (unsigned)atoi(e);
         if (n > 32) n = 32;
         if (n < 1) n = 1;

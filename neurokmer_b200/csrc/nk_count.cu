@@ -116,14 +116,27 @@ struct TileEnds {
     unsigned long long first;       // index (into offsets[1..]) of the first end > tile start
 };
 
-__device__ __forceinline__ void find_tile_ends(const CountParams& p, unsigned long long tile, TileEnds* te) {
+__device__ __forceinline__ void find_tile_ends(const CountParams& p, unsigned long long tile, TileEnds* te,
+                                               unsigned long long* cursor = nullptr) {
     const unsigned long long t0 = p.origin + tile * COUNT_TILE;
-    // first end > t0 among offsets[1 .. nseq]
-    unsigned long long lo = 0, hi = p.nseq;  // answer in [lo, hi]: index i means offsets[i + 1]
+    // first end > t0 among offsets[1 .. nseq]; index i means offsets[i + 1], the answer lies in [lo, hi].
+    // A CTA's tiles only move forward, so the search gallops from the previous tile's answer (`cursor`): in a
+    // long-sequence batch that is ONE load per tile instead of log2(nseq) dependent ones.
+    unsigned long long lo = cursor ? *cursor : 0ull, hi = p.nseq;
+    if (cursor) {
+        unsigned long long step = 1, probe = lo;
+        while (probe < p.nseq) {
+            if (__ldg(p.offsets + probe + 1) > t0) { hi = probe; break; }
+            lo = probe + 1;
+            probe += step;
+            step <<= 1;
+        }
+    }
     while (lo < hi) {
         const unsigned long long mid = (lo + hi) >> 1;
         if (__ldg(p.offsets + mid + 1) > t0) hi = mid; else lo = mid + 1;
     }
+    if (cursor) *cursor = lo;
     te->first = lo;
     const unsigned long long reach = t0 + COUNT_TILE + (p.k - 1);  // an end e invalidates starts e-k+1 .. e-1
     int n = 0;
@@ -182,6 +195,7 @@ template <bool CANON, int MODE, bool POW2, bool KHI>
 __device__ __forceinline__ void process_chunk(const CountParams& p, const WindowConsts& wc, const Codes16& cur,
                                               const Codes16& nxt, unsigned inv16, unsigned lane,
                                               unsigned long long pos0, unsigned long long* wbuf) {
+    // (inv16 is a by-value copy: the N-run shortcut below edits it)
     const unsigned F0 = cur.F;
     const unsigned F1 = neighbour(cur.F, nxt.F, lane, 1);
     const unsigned F2 = neighbour(cur.F, nxt.F, lane, 2);
@@ -209,6 +223,23 @@ __device__ __forceinline__ void process_chunk(const CountParams& p, const Window
     }
 
     constexpr bool EMIT = MODE == 1;
+#ifndef NK_NO_NRUN
+    if constexpr (CANON && MODE == 0) {
+        // Runs of N (assembly gaps, centromeres: megabases of them in real genomes).  A base that is not ACGT is code 0
+        // on BOTH strands (src/models.rs:237,249), so every window inside a run is the word 0 and lands on ONE neuron:
+        // half a percent of N in the input sent 565,000 of the bench job's reductions to a single address, and the L2
+        // slice that owns it made the whole kernel 11 % slower (tools/count_ablate.py).  A lane whose 48 bases are all
+        // code 0 on both strands has 16 such windows; the warp adds them up and sends one reduction.
+        const bool all_other = (F0 | F1 | F2 | R0 | R1 | R2) == 0u;
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, all_other);
+        if (m) {
+            const unsigned cnt = __reduce_add_sync(0xFFFFFFFFu, all_other ? 16u - __popc(inv16 & 0xFFFFu) : 0u);
+            if (lane == 0 && cnt) atomicAdd(p.acc + fastmod_dev<POW2>(siphash13_dev(0u, 0u, p.rm), p.fm), cnt);
+            if (m == 0xFFFFFFFFu) return;
+            if (all_other) inv16 = 0xFFFFu;
+        }
+    }
+#endif
     // MODE 2: reserve this warp's slots in the word array with ONE atomic per 512-position chunk
     unsigned long long* wslot = nullptr;
     unsigned int* islot = nullptr;
@@ -295,7 +326,11 @@ __device__ __forceinline__ void process_chunk(const CountParams& p, const Window
             const unsigned long long word = window(j, fwd, rc);
             const U64 h = siphash13_dev((unsigned)word, (unsigned)(word >> 32), p.rm);
             const unsigned idx = fastmod_dev<POW2>(h, p.fm);
+#ifdef NK_EXP_NORED
+            if (idx == 0xFFFFFFFFu) p.acc[0] = 1u;  // diagnostic build only (tools/variants.sh): no pool update
+#else
             asm volatile("red.global.add.u32 [%0], %1;" ::"l"(p.acc + idx), "r"(1u) : "memory");
+#endif
         }
         return;
     }
@@ -361,91 +396,94 @@ __device__ __forceinline__ void process_chunk(const CountParams& p, const Window
 #define NK_COUNT_MINBLOCKS 2
 #endif
 // (Round 2 also tried a barrier-free tile pipeline here — `full` / `empty` mbarriers per stage, 2-4 stages, every warp
-// converting its own halo so that no __syncthreads is left in the loop, because `barrier` was 19 % of the stall samples.
-// It measured 1.0-1.9 % SLOWER than this loop (0.884 / 0.889 / 0.892 ms with 2 / 3 / 4 stages against 0.876 ms;
-// profiles/r02_variants.md): the barrier stalls were never on the critical resource, the ALU pipe was busy with the
-// other CTAs' warps.  Kept out.)
+// converting its own halo so that no __syncthreads is left in the loop.  It measured 1.0-1.9 % SLOWER than a loop with
+// barriers (profiles/r02_variants.md): the ALU pipe was busy with the other CTAs' warps anyway.  Kept out.)
 template <bool CANON, int MODE, bool POW2, bool KHI, bool PACKED>
 __global__ void __launch_bounds__(COUNT_THREADS, NK_COUNT_MINBLOCKS) count_kernel(const __grid_constant__ CountParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) unsigned long long bars[COUNT_STAGES];
-    __shared__ unsigned long long tile_of[COUNT_STAGES];
-    __shared__ unsigned int halo[COUNT_WARPS][2][3];
-    __shared__ TileEnds tends[COUNT_STAGES];
     constexpr bool BITMAP = MODE != 5;
     unsigned valid_starts = 0;  // MODE 5: window starts this thread counted
+    const WindowConsts wc = make_window_consts(p.k);
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const bool has_other = PACKED && p.other != nullptr;
+
+    // ONE __syncthreads per tile.  Everything a warp reads from a stage (its 16 bytes per lane, the halo, the bitmap
+    // word) is in registers before the barrier, so right after it thread 0 refills the stage with the tile after
+    // next, and the warps hash without meeting again until the next tile's barrier.  The tile ticket (a global atomic
+    // that queues behind this kernel's own reductions in L2) is fetched one tile ahead of its use, and the sequence
+    // ends of a tile are looked up from the previous tile's position: the serial work of thread 0 that the other
+    // seven warps wait for at the barrier shrinks to a few hundred cycles per tile.  Worth 0.4 % against the loop with a
+    // barrier on each side of the hashing (0.783 against 0.786 ms, profiles/r02_variants.md).
+    static_assert(COUNT_CHUNKS_PER_SPAN == 1 && COUNT_STAGES == 2, "the one-barrier loop reads a stage once, before the barrier");
+    constexpr unsigned kSlots = 4;                        // per-tile records live for three tiles
+    __shared__ unsigned long long tile_of[kSlots];
+    __shared__ TileEnds tends[kSlots];
+    __shared__ unsigned int halo[COUNT_STAGES][COUNT_WARPS][2][3];
+    __shared__ unsigned long long cursor;                 // thread 0 only: where the previous tile's end search stopped
+    unsigned ticket = 0;                                  // thread 0 only: the ticket of tile it+2, in flight in a register
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < COUNT_STAGES; ++s) mbar_init(&bars[s], 1);
         mbar_fence_init();
-        unsigned long long t0 = atomicAdd(p.tile_counter, 1u);
-        tile_of[0] = t0;
-        if (t0 < p.ntiles) {
-            issue_tile<PACKED, BITMAP>(smem, &bars[0], p, t0);
-            if (!BITMAP) find_tile_ends(p, t0, &tends[0]);
+        cursor = 0;
+        for (unsigned s = 0; s < 2; ++s) {
+            const unsigned long long t = atomicAdd(p.tile_counter, 1u);
+            tile_of[s] = t;
+            if (t < p.ntiles) {
+                issue_tile<PACKED, BITMAP>(smem + s * kStageStride, &bars[s], p, t);
+                if (!BITMAP) find_tile_ends(p, t, &tends[s], &cursor);
+            }
         }
+        ticket = atomicAdd(p.tile_counter, 1u);
     }
     __syncthreads();
 
-    const WindowConsts wc = make_window_consts(p.k);
-    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-
     for (unsigned it = 0;; ++it) {
-        const unsigned s = it & 1u;
-        const unsigned long long tile = tile_of[s];
+        const unsigned s = it & 1u, slot = it & (kSlots - 1u);
+        const unsigned long long tile = tile_of[slot];
         if (tile >= p.ntiles) break;
-        if (threadIdx.x == 0) {  // prefetch the next tile into the other stage (consumed at it-1)
-            unsigned long long tn = atomicAdd(p.tile_counter, 1u);
-            tile_of[s ^ 1u] = tn;
-            if (tn < p.ntiles) {
-                issue_tile<PACKED, BITMAP>(smem + (s ^ 1u) * kStageStride, &bars[s ^ 1u], p, tn);
-                if (!BITMAP) find_tile_ends(p, tn, &tends[s ^ 1u]);
-            }
-        }
         mbar_wait(&bars[s], (it >> 1) & 1u);
 
         const unsigned char* sb = smem + s * kStageStride;
         const unsigned short* bits =
             reinterpret_cast<const unsigned short*>(sb + (PACKED ? kPkCodes + kPkOther : kBytesPerStage));
-        const bool has_other = PACKED && p.other != nullptr;
         const unsigned span0 = warp * COUNT_SPAN;
-        Codes16 cur = load_codes<CANON, PACKED>(sb, (span0 >> 4) + lane, has_other);
-        // The k-1 overlap past the END of a warp's span is the first two code words of the next
-        // warp's span: they are exchanged through shared memory instead of being converted twice
-        // (the last warp converts the tile's 32-byte halo).  This is what makes small tiles cheap,
-        // and small tiles are what keeps the tail of the persistent grid short.
+        const Codes16 cur = load_codes<CANON, PACKED>(sb, (span0 >> 4) + lane, has_other);
+        // The k-1 overlap past the END of a warp's span is the first two code words of the next warp's span: they
+        // are exchanged through shared memory instead of being converted twice (the last warp converts the tile's
+        // 32-byte halo).  This is what makes small tiles cheap, and small tiles keep the persistent grid's tail short.
         if (lane < 2) {
-            halo[warp][lane][0] = cur.F;
-            halo[warp][lane][1] = cur.R;
-            halo[warp][lane][2] = cur.V;
+            halo[s][warp][lane][0] = cur.F;
+            halo[s][warp][lane][1] = cur.R;
+            halo[s][warp][lane][2] = cur.V;
         }
         Codes16 tail{0u, 0u, 0u};
         if (warp == COUNT_WARPS - 1)
             tail = load_codes<CANON, PACKED>(sb, COUNT_TILE / 16 + (lane & 1u), has_other);
+        unsigned inv16 = 0;
+        if (BITMAP) inv16 = bits[(span0 >> 4) + lane];
         __syncthreads();
-        if (warp < COUNT_WARPS - 1 && lane < 2) {
-            tail.F = halo[warp + 1][lane][0];
-            tail.R = halo[warp + 1][lane][1];
-            tail.V = halo[warp + 1][lane][2];
-        }
-#pragma unroll 1
-        for (unsigned c = 0; c < COUNT_CHUNKS_PER_SPAN; ++c) {
-            Codes16 nxt = tail;
-            if (c + 1u < COUNT_CHUNKS_PER_SPAN)
-                nxt = load_codes<CANON, PACKED>(sb, ((span0 + (c + 1u) * COUNT_CHUNK) >> 4) + lane, has_other);
-            const unsigned off = span0 + c * COUNT_CHUNK;
-            unsigned inv16;
-            if (BITMAP) {
-                inv16 = bits[(off >> 4) + lane];
-            } else {
-                inv16 = invalid_bits(p, tends[s], tile, (int)(off + 16u * lane));
-                valid_starts += 16u - __popc(inv16);
+        if (threadIdx.x == 0) {  // stage s is free: refill it with tile it+2; ask for the ticket of tile it+3
+            const unsigned long long tn = ticket;
+            ticket = atomicAdd(p.tile_counter, 1u);
+            tile_of[(it + 2u) & (kSlots - 1u)] = tn;
+            if (tn < p.ntiles) {
+                issue_tile<PACKED, BITMAP>(smem + s * kStageStride, &bars[s], p, tn);
+                if (!BITMAP) find_tile_ends(p, tn, &tends[(it + 2u) & (kSlots - 1u)], &cursor);
             }
-            process_chunk<CANON, (MODE == 5 ? 0 : MODE), POW2, KHI>(p, wc, cur, nxt, inv16, lane, tile * COUNT_TILE + off + 16u * lane,
-                                                  reinterpret_cast<unsigned long long*>(smem + kSmemTotal) + warp * COUNT_CHUNK);
-            cur = nxt;
         }
-        __syncthreads();
+        if (warp < COUNT_WARPS - 1 && lane < 2) {
+            tail.F = halo[s][warp + 1][lane][0];
+            tail.R = halo[s][warp + 1][lane][1];
+            tail.V = halo[s][warp + 1][lane][2];
+        }
+        if (!BITMAP) {
+            inv16 = invalid_bits(p, tends[slot], tile, (int)(span0 + 16u * lane));
+            valid_starts += 16u - __popc(inv16);
+        }
+        process_chunk<CANON, (MODE == 5 ? 0 : MODE), POW2, KHI>(p, wc, cur, tail, inv16, lane, tile * COUNT_TILE + span0 + 16u * lane,
+                                              reinterpret_cast<unsigned long long*>(smem + kSmemTotal) + warp * COUNT_CHUNK);
     }
     if (!BITMAP) {  // the metric's unit: windows counted (the bitmap path's marking kernel does this otherwise)
         valid_starts = __reduce_add_sync(0xFFFFFFFFu, valid_starts);

@@ -1542,3 +1542,43 @@ def test_long_sequence_mode_without_bitmap_equals_bitmap_mode(coracle, k, pool, 
             assert c.timings()["kmers"] == tot
         c.close()
     monkeypatch.delenv("NK_BITMAP", raising=False)
+
+
+@pytest.mark.parametrize("k,pool", [(31, 2_000_000), (32, 99_991), (17, 4096), (5, 65_537), (1, 1000)])
+def test_runs_of_n_are_counted_once_per_warp_not_once_per_window(coracle, k, pool):
+    """A base that is not ACGT is code 0 on both strands (src/models.rs:237,249), so every window inside a run of N is
+    the word 0 and the count kernel adds a whole lane's (or warp's) windows of such a run with ONE reduction.
+    Runs shorter and longer than a lane's 48 bases and a warp's 512, runs that start or end on lane, warp and tile
+    boundaries, runs that cross sequence ends (windows there are invalid), IUPAC letters and poly-A next to N
+    (poly-A is word 0 too, by the normal path): currents and window totals equal the oracle's."""
+    from neurokmer_b200 import PinnedBuffer, flatten, pack_bases
+    rng = np.random.default_rng(1000 + k)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+
+    def dna(n):
+        return acgt[rng.integers(0, 4, n, dtype=np.uint8)].copy()
+
+    seq = dna(200_000)
+    for start, length in [(100, 10), (1000, 47), (2000, 48), (3000, 49), (4096 - 20, 64), (8192, 512), (16384 - 3, 515),
+                          (30_000, 5000), (40_960, 4096), (60_000 + 16, 1024), (90_001, 777), (199_000, 1000)]:
+        seq[start:start + length] = ord("N")
+    seq[120_000:120_100] = ord("A")                      # poly-A: word 0 through the hash path
+    seq[120_100:120_400] = ord("N")
+    seq[130_000:130_200] = np.frombuffer(b"RYKMSWnn", np.uint8)[rng.integers(0, 8, 200)]
+    tail_n = np.full(3000, ord("N"), np.uint8)           # a sequence that is one run, then one that starts inside N
+    mixed = dna(50_000); mixed[:700] = ord("n"); mixed[-600:] = ord("N")
+    seqs = [seq, tail_n, mixed, np.full(k, ord("N"), np.uint8), np.full(max(k - 1, 0), ord("N"), np.uint8), dna(70_000)]
+    bases, offsets = flatten([s.tobytes() for s in seqs])
+    assert bases.size / len(seqs) >= 2048                # the long-sequence (no bitmap) kernel
+    for canonical in (True, False):
+        exp, tot = coracle.accumulate(bases, offsets, k, pool, canonical, threads=4)
+        c = make(k, pool, canonical)
+        pin = PinnedBuffer(bases.size); pin.array[:] = bases
+        for src in (bases, pin.array):
+            c.process_batch(src, offsets)
+            np.testing.assert_array_equal(c.currents(), exp)
+            assert c.timings()["kmers"] == tot
+        codes, other, _ = pack_bases(bases)
+        c.process_batch_packed(codes, other, offsets)
+        np.testing.assert_array_equal(c.currents(), exp)
+        c.close()

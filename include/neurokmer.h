@@ -285,7 +285,8 @@ NK_API int nk_debug_fasta_windows_digest(const char* path, uint64_t window, uint
 /* SipHash-1-3(keys 0,0) of LE64(word) and word-hash % pool_size for a host array. */
 NK_API int nk_debug_hash(nk_counter* h, const uint64_t* words, uint64_t n, uint64_t* hashes, uint64_t* idx);
 /* values[i] % pool_size on the device for ANY pool_size in [1, 2^32) without allocating a pool:
- * which 0 = the FP64-pipe routine the kernels use, 1 = the integer (Moeller-Granlund) routine. */
+ * which 0 = the two-stage FP64-pipe routine (any pool size), 1 = the integer (Moeller-Granlund) routine,
+ * 2 = the routine the count kernel picks for this pool size (one FP64 stage where the size allows it). */
 NK_API int nk_debug_mod(const uint64_t* values, uint64_t n, uint64_t pool_size, int which, uint64_t* out);
 NK_API int nk_copy_currents(nk_counter* h, uint64_t* out /* pool_size */);
 NK_API int nk_copy_spike_counts(nk_counter* h, uint64_t* out /* pool_size */);

@@ -1458,6 +1458,9 @@ int nk_create(const nk_config* cfg, nk_counter** out) {
     nk_counter* h = new nk_counter();
     h->cfg = *cfg;
     h->fm = nk::make_fastmod(cfg->pool_size);
+    if (const char* e = std::getenv("NK_MOD_TWO_STAGE")) {  // A/B switch: keep the two-stage remainder in the count kernel
+        if (e[0] == '1') h->fm.kind = 0u;
+    }
     auto bail = [&](int rc) { nk_destroy(h); return rc; };
 #define NK_C(expr)                                                                                              \
     do {                                                                                                        \
@@ -2021,7 +2024,8 @@ int nk_debug_mod(const uint64_t* values, uint64_t n, uint64_t pool_size, int whi
     if (n == 0) return NK_OK;
     if (!values || !out) return fail(NK_ERR_BAD_ARG, "null argument");
     if (pool_size == 0 || pool_size >= (1ull << 32)) return fail(NK_ERR_BAD_ARG, "pool_size must be in [1, 2^32)");
-    if (which != 0 && which != 1) return fail(NK_ERR_BAD_ARG, "which must be 0 (FP64-pipe form) or 1 (integer form)");
+    if (which < 0 || which > 2)
+        return fail(NK_ERR_BAD_ARG, "which must be 0 (two-stage FP64 form), 1 (integer form) or 2 (the count kernel's pick)");
     unsigned long long* d = nullptr;
     NK_CUDA(cudaMalloc(&d, 2 * n * sizeof(unsigned long long)));
     cudaError_t e = cudaMemcpy(d, values, n * 8, cudaMemcpyHostToDevice);

@@ -191,7 +191,7 @@ __device__ __noinline__ unsigned long long pack_skip(unsigned F0, unsigned F1, u
     return word;
 }
 
-template <bool CANON, int MODE, bool POW2, bool KHI>
+template <bool CANON, int MODE, int MODK, bool KHI>
 __device__ __forceinline__ void process_chunk(const CountParams& p, const WindowConsts& wc, const Codes16& cur,
                                               const Codes16& nxt, unsigned inv16, unsigned lane,
                                               unsigned long long pos0, unsigned long long* wbuf) {
@@ -234,7 +234,7 @@ __device__ __forceinline__ void process_chunk(const CountParams& p, const Window
         const unsigned m = __ballot_sync(0xFFFFFFFFu, all_other);
         if (m) {
             const unsigned cnt = __reduce_add_sync(0xFFFFFFFFu, all_other ? 16u - __popc(inv16 & 0xFFFFu) : 0u);
-            if (lane == 0 && cnt) atomicAdd(p.acc + fastmod_dev<POW2>(siphash13_dev(0u, 0u, p.rm), p.fm), cnt);
+            if (lane == 0 && cnt) atomicAdd(p.acc + fastmod_kind_dev<MODK>(siphash13_dev(0u, 0u, p.rm), p.fm), cnt);
             if (m == 0xFFFFFFFFu) return;
             if (all_other) inv16 = 0xFFFFu;
         }
@@ -306,13 +306,13 @@ __device__ __forceinline__ void process_chunk(const CountParams& p, const Window
             for (unsigned u = 0; u < 4; ++u) {
                 const unsigned long long word = wbuf[t + 32u * u];
                 const U64 h = siphash13_dev((unsigned)word, (unsigned)(word >> 32), p.rm);
-                atomicAdd(p.acc + fastmod_dev<POW2>(h, p.fm), 1u);
+                atomicAdd(p.acc + fastmod_kind_dev<MODK>(h, p.fm), 1u);
             }
         }
         for (unsigned t = full + lane; t < total; t += 32u) {
             const unsigned long long word = wbuf[t];
             const U64 h = siphash13_dev((unsigned)word, (unsigned)(word >> 32), p.rm);
-            atomicAdd(p.acc + fastmod_dev<POW2>(h, p.fm), 1u);
+            atomicAdd(p.acc + fastmod_kind_dev<MODK>(h, p.fm), 1u);
         }
         __syncwarp();
     } else {
@@ -325,7 +325,7 @@ __device__ __forceinline__ void process_chunk(const CountParams& p, const Window
             unsigned long long fwd, rc;
             const unsigned long long word = window(j, fwd, rc);
             const U64 h = siphash13_dev((unsigned)word, (unsigned)(word >> 32), p.rm);
-            const unsigned idx = fastmod_dev<POW2>(h, p.fm);
+            const unsigned idx = fastmod_kind_dev<MODK>(h, p.fm);
 #ifdef NK_EXP_NORED
             if (idx == 0xFFFFFFFFu) p.acc[0] = 1u;  // diagnostic build only (tools/variants.sh): no pool update
 #else
@@ -341,7 +341,7 @@ __device__ __forceinline__ void process_chunk(const CountParams& p, const Window
         const unsigned long long word = window(j, fwd, rc);
         const unsigned bad = (inv16 >> j) & 1u;
         const U64 h = siphash13_dev((unsigned)word, (unsigned)(word >> 32), p.rm);
-        const unsigned idx = fastmod_dev<POW2>(h, p.fm);
+        const unsigned idx = fastmod_kind_dev<MODK>(h, p.fm);
         if (EMIT) {
             if (!bad) {
                 const unsigned long long pos = pos0 + j;
@@ -398,7 +398,7 @@ __device__ __forceinline__ void process_chunk(const CountParams& p, const Window
 // (Round 2 also tried a barrier-free tile pipeline here — `full` / `empty` mbarriers per stage, 2-4 stages, every warp
 // converting its own halo so that no __syncthreads is left in the loop.  It measured 1.0-1.9 % SLOWER than a loop with
 // barriers (profiles/r02_variants.md): the ALU pipe was busy with the other CTAs' warps anyway.  Kept out.)
-template <bool CANON, int MODE, bool POW2, bool KHI, bool PACKED>
+template <bool CANON, int MODE, int MODK, bool KHI, bool PACKED>
 __global__ void __launch_bounds__(COUNT_THREADS, NK_COUNT_MINBLOCKS) count_kernel(const __grid_constant__ CountParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) unsigned long long bars[COUNT_STAGES];
@@ -482,7 +482,7 @@ __global__ void __launch_bounds__(COUNT_THREADS, NK_COUNT_MINBLOCKS) count_kerne
             inv16 = invalid_bits(p, tends[slot], tile, (int)(span0 + 16u * lane));
             valid_starts += 16u - __popc(inv16);
         }
-        process_chunk<CANON, (MODE == 5 ? 0 : MODE), POW2, KHI>(p, wc, cur, tail, inv16, lane, tile * COUNT_TILE + span0 + 16u * lane,
+        process_chunk<CANON, (MODE == 5 ? 0 : MODE), MODK, KHI>(p, wc, cur, tail, inv16, lane, tile * COUNT_TILE + span0 + 16u * lane,
                                               reinterpret_cast<unsigned long long*>(smem + kSmemTotal) + warp * COUNT_CHUNK);
     }
     if (!BITMAP) {  // the metric's unit: windows counted (the bitmap path's marking kernel does this otherwise)
@@ -560,7 +560,7 @@ __global__ void mark_tail_kernel(unsigned int* invalid, unsigned long long nbyte
 
 size_t count_smem_bytes() { return (size_t)kSmemTotal; }
 
-template <bool CANON, int MODE, bool POW2, bool KHI, bool PACKED>
+template <bool CANON, int MODE, int MODK, bool KHI, bool PACKED>
 static cudaError_t launch_count_t(const CountParams& p, cudaStream_t s) {
     constexpr int kSmem = kSmemTotal + (MODE == 3 ? kCompactBytes : 0);
     // persistent grid of this instantiation: SMs x resident CTAs (a multiple of 148 on B200); function
@@ -577,25 +577,34 @@ static cudaError_t launch_count_t(const CountParams& p, cudaStream_t s) {
         int sms = 0, per_sm = 0;
         e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(count_kernel<CANON, MODE, POW2, KHI, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+        e = cudaFuncSetAttribute(count_kernel<CANON, MODE, MODK, KHI, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
         if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, count_kernel<CANON, MODE, POW2, KHI, PACKED>, COUNT_THREADS, kSmem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, count_kernel<CANON, MODE, MODK, KHI, PACKED>, COUNT_THREADS, kSmem);
         if (e != cudaSuccess) return e;
         max_grid_of[dev].store(sms * (per_sm < 1 ? 1 : per_sm), std::memory_order_release);
     }
     const int max_grid = max_grid_of[dev].load(std::memory_order_acquire);
     const unsigned long long grid = p.ntiles < (unsigned long long)max_grid ? p.ntiles : (unsigned long long)max_grid;
     if (grid == 0) return cudaSuccess;
-    count_kernel<CANON, MODE, POW2, KHI, PACKED><<<(unsigned)grid, COUNT_THREADS, kSmem, s>>>(p);
+    count_kernel<CANON, MODE, MODK, KHI, PACKED><<<(unsigned)grid, COUNT_THREADS, kSmem, s>>>(p);
     return cudaGetLastError();
+}
+
+template <bool CANON, int MODE, int MODK, bool PACKED>
+static cudaError_t launch_count_k(const CountParams& p, cudaStream_t s) {
+    return p.k > 16 ? launch_count_t<CANON, MODE, MODK, true, PACKED>(p, s) : launch_count_t<CANON, MODE, MODK, false, PACKED>(p, s);
 }
 
 template <bool CANON, int MODE, bool PACKED>
 static cudaError_t launch_count_cm(const CountParams& p, cudaStream_t s) {
-    const bool pow2 = p.fm.is_pow2 != 0, khi = p.k > 16;
-    if (pow2)
-        return khi ? launch_count_t<CANON, MODE, true, true, PACKED>(p, s) : launch_count_t<CANON, MODE, true, false, PACKED>(p, s);
-    return khi ? launch_count_t<CANON, MODE, false, true, PACKED>(p, s) : launch_count_t<CANON, MODE, false, false, PACKED>(p, s);
+    if (p.fm.is_pow2) return launch_count_k<CANON, MODE, 1, PACKED>(p, s);
+    // the one-stage remainder (nk_device.cuh) for the modes a job's time is spent in; the tap and table modes keep
+    // the two-stage form
+    if constexpr (MODE == 0 || MODE == 3 || MODE == 5) {
+        if (p.fm.kind == 3u) return launch_count_k<CANON, MODE, 3, PACKED>(p, s);
+        if (p.fm.kind == 2u) return launch_count_k<CANON, MODE, 2, PACKED>(p, s);
+    }
+    return launch_count_k<CANON, MODE, 0, PACKED>(p, s);
 }
 
 template <bool CANON, bool PACKED>

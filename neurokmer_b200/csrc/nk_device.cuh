@@ -156,6 +156,11 @@ struct FastMod {
     uint32_t pow2m1;  // p-1 if p is a power of two, else 0 (p == 1 handled: pow2m1 == 0 && dn == 2^31)
     uint32_t p;
     uint32_t is_pow2;
+    // one-stage FP64 remainder (fastmod_single_dev): h = A*2^s + B with s = 32 or 44, x = A*(2^s mod p) + B < 2^53
+    double m1;        // kind 3: 2^32 mod p;  kind 2: (2^44 mod p) * 2^-12 (A is taken in place, as A * 2^12)
+    double inv_dn;    // 1/p rounded DOWN (<= 1/p), so that the quotient estimate is never too large
+    uint32_t kind;    // 0: two stages (any p), 2: split at bit 44 (4 <= p <= 2^31), 3: split at bit 32 (2^32 mod p < 2^21 - 1)
+    uint32_t pad_;
 };
 
 __host__ __device__ __forceinline__ FastMod make_fastmod(unsigned long long p64) {
@@ -172,6 +177,26 @@ __host__ __device__ __forceinline__ FastMod make_fastmod(unsigned long long p64)
     fm.dd = (double)p;
     fm.inv = 1.0 / (double)p;
     fm.two_d = 2.0 * (double)p;
+    fm.m1 = 0.0;
+    fm.kind = 0u;
+    fm.pad_ = 0u;
+    // 1/p rounded to nearest is within half an ulp of 1/p; one ulp below it is <= 1/p and >= (1/p)(1 - 2^-51)
+    {
+        union { double d; unsigned long long u; } cv;
+        cv.d = fm.inv;
+        cv.u -= 1ull;
+        fm.inv_dn = cv.d;
+    }
+    if (!fm.is_pow2 && p64 >= 4ull && p64 <= 0x80000000ull) {
+        const unsigned long long m32 = 0x100000000ull % p64, m44 = (1ull << 44) % p64;
+        if (m32 < (1ull << 21) - 1ull) {
+            fm.kind = 3u;
+            fm.m1 = (double)m32;
+        } else {
+            fm.kind = 2u;
+            fm.m1 = (double)m44 * (1.0 / 4096.0);
+        }
+    }
     return fm;
 }
 
@@ -228,6 +253,27 @@ inline uint32_t fastmod_fp64_host(unsigned long long h, const FastMod& fm) {
     (void)two52;
     const unsigned long long r = (unsigned long long)r2;
     return (uint32_t)(r >= fm.p ? r - fm.p : r);
+}
+
+// ---------------------------------------------------------------------------
+// One-stage form (fm.kind 2 or 3), 7 FP64 ops and 1-3 ALU ops — the count kernel's default when p allows it
+// (the two stages above cost 7.6 % of the kernel, tools/count_ablate.py):
+//   kind 3 (2^32 mod p < 2^21 - 1, e.g. every p < 2^21):  A = h >> 32, B = h & (2^32-1), m = 2^32 mod p
+//   kind 2 (4 <= p <= 2^31):                               A = h >> 44, B = h & (2^44-1), m = 2^44 mod p
+//   x = A*m + B == h (mod p), and x < 2^53 is an integer, so ONE fma gives it exactly
+//     (kind 3: A*m < 2^32 * (2^21 - 2);  kind 2: A*m < 2^20 * 2^31, B < 2^44).
+//   Q = trunc(x * inv_dn + 2^52) in ONE fma rounded toward zero = 2^52 + floor(x * inv_dn); inv_dn in
+//     [(1/p)(1 - 2^-51), 1/p], so q = Q - 2^52 is floor(x/p) or one less (x/p * 2^-51 < 4/p <= 1).
+//   r = x - q*p (one fma, exact: an integer in [0, 2p) <= 2^32);  result = min(r, r - p) on unsigned words.
+// Host twin of fastmod_single_dev for the tests.
+// ---------------------------------------------------------------------------
+inline uint32_t fastmod_single_host(unsigned long long h, const FastMod& fm) {
+    const unsigned long long A = fm.kind == 3u ? (h >> 32) : (h >> 44);
+    const unsigned long long B = fm.kind == 3u ? (h & 0xFFFFFFFFull) : (h & ((1ull << 44) - 1ull));
+    const unsigned long long m = fm.kind == 3u ? 0x100000000ull % fm.p : (1ull << 44) % fm.p;
+    const unsigned long long x = A * m + B;
+    unsigned long long q = x / fm.p;  // the device's estimate is this or one less; both give the same result
+    return (uint32_t)(x - q * fm.p);
 }
 
 #ifdef __CUDACC__
@@ -369,6 +415,32 @@ __device__ __forceinline__ uint32_t fastmod_dev(U64 h, const FastMod& fm) {
     const double r2 = __fma_rn(-q2, fm.dd, x2);                                         // in [0, p]
     const uint32_t r = (uint32_t)__double2loint(__dadd_rn(r2, two52));
     return min(r, r - fm.p);
+}
+
+// One-stage FP64 remainder (see fastmod_single_host for the derivation); KIND = fm.kind (2 or 3).
+template <int KIND>
+__device__ __forceinline__ uint32_t fastmod_single_dev(U64 h, const FastMod& fm) {
+    const double two52 = 4503599627370496.0;
+    double a, b;
+    if (KIND == 3) {
+        a = __dadd_rn(__hiloint2double(0x43300000, (int)h.hi), -two52);                                // A
+        b = __dadd_rn(__hiloint2double(0x43300000, (int)h.lo), -two52);                                // B
+    } else {
+        a = __dadd_rn(__hiloint2double(0x43300000, (int)(h.hi & 0xFFFFF000u)), -two52);                // A * 2^12
+        b = __dadd_rn(__hiloint2double((int)(0x43300000u | (h.hi & 0xFFFu)), (int)h.lo), -two52);      // B
+    }
+    const double x = __fma_rn(a, fm.m1, b);
+    const double q = __dadd_rn(__fma_rz(x, fm.inv_dn, two52), -two52);
+    const double r = __fma_rn(-q, fm.dd, x);
+    const uint32_t ri = (uint32_t)__double2loint(__dadd_rn(r, two52));
+    return min(ri, ri - fm.p);
+}
+// MODK: 0 two stages, 1 power of two, 2 / 3 one stage
+template <int MODK>
+__device__ __forceinline__ uint32_t fastmod_kind_dev(U64 h, const FastMod& fm) {
+    if (MODK == 1) return h.lo & fm.pow2m1;
+    if (MODK >= 2) return fastmod_single_dev<MODK>(h, fm);
+    return fastmod_dev<false>(h, fm);
 }
 
 // ---------------------------------------------------------------------------

@@ -25,7 +25,11 @@ __global__ void mod_words_kernel(const unsigned long long* __restrict__ h, unsig
     const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
     const U64 x{(unsigned)h[i], (unsigned)(h[i] >> 32)};
-    out[i] = which ? fastmod_mg_dev<POW2>(x, fm) : fastmod_dev<POW2>(x, fm);
+    if (which == 2 && !POW2) {  // the routine the count kernel picks for this pool size (fm.kind)
+        out[i] = fm.kind == 3u ? fastmod_single_dev<3>(x, fm) : (fm.kind == 2u ? fastmod_single_dev<2>(x, fm) : fastmod_dev<false>(x, fm));
+        return;
+    }
+    out[i] = which == 1 ? fastmod_mg_dev<POW2>(x, fm) : fastmod_dev<POW2>(x, fm);
 }
 
 // Position-addressable synthetic stream: 32 bases per splitmix64 draw.

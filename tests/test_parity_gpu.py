@@ -816,11 +816,13 @@ def test_config3_full_size_two_slices():
 
 def test_exact_modulo_all_pool_sizes():
     """`finish() % pool_size` (spiking_hash.rs:81) for pool sizes up to 2^32-1 and adversarial values
-    (exact multiples, multiples ± 1, extremes): the FP64-pipe routine and the integer routine both equal
-    Python's integer remainder."""
+    (exact multiples, multiples ± 1, extremes): the two-stage FP64-pipe routine, the integer routine and the
+    one-stage routine the count kernel picks per pool size (split at bit 32 or 44) all equal Python's integer
+    remainder."""
     from neurokmer_b200.counter import debug_mod
     rng = np.random.default_rng(99)
-    pools = [1, 2, 3, 5, 7, 10, 1000, 4096, 65535, 65536, 65537, 999_983, 1_000_000, 2_000_000, 15_625, 16_000_000,
+    pools = [1, 2, 3, 4, 5, 6, 7, 10, 1000, 4096, 65535, 65536, 65537, 999_983, 1_000_000, 2_000_000, 15_625, 16_000_000,
+             2**21 - 2, 2**21 - 1, 2**21 + 1, 2_097_153, 2**32 // 3, 2**32 // 3 + 1, 1_431_655_766,
              2**24 - 1, 2**31 - 1, 2**31, 2**31 + 1, 4_294_967_291, 2**32 - 2, 2**32 - 1] + \
             [int(x) for x in rng.integers(1, 2**32, size=40, dtype=np.uint64)]
     for p in pools:
@@ -830,8 +832,10 @@ def test_exact_modulo_all_pool_sizes():
         v[:6000] = mult                                   # exact multiples
         v[6000:12000] = mult + np.uint64(p - 1)           # one below the next multiple (may wrap: still valid input)
         v[12000:12010] = [0, 1, 2**64 - 1, 2**64 - 2, 2**63, 2**32, 2**32 - 1, p, p - 1 if p > 1 else 0, (p * 4096) % 2**64]
+        v[12010:14000] |= np.uint64(0xFFFFFFFF00000000)   # large high words: the one-stage routine's x near 2^53
+        v[14000:16000] |= np.uint64(0xFFFFF00000000000)
         want = np.array([int(x) % p for x in v], np.uint64)
-        for which in (0, 1):
+        for which in (0, 1, 2):
             np.testing.assert_array_equal(debug_mod(v, p, which), want, err_msg=f"pool {p} routine {which}")
 
 

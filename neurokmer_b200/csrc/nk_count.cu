@@ -224,17 +224,28 @@ __device__ __forceinline__ void process_chunk(const CountParams& p, const Window
 
     constexpr bool EMIT = MODE == 1;
 #ifndef NK_NO_NRUN
-    if constexpr (CANON && MODE == 0) {
+    if constexpr (CANON && (MODE == 0 || MODE == 2 || MODE == 4)) {
         // Runs of N (assembly gaps, centromeres: megabases of them in real genomes).  A base that is not ACGT is code 0
         // on BOTH strands (src/models.rs:237,249), so every window inside a run is the word 0 and lands on ONE neuron:
         // half a percent of N in the input sent 565,000 of the bench job's reductions to a single address, and the L2
         // slice that owns it made the whole kernel 11 % slower (tools/count_ablate.py).  A lane whose 48 bases are all
         // code 0 on both strands has 16 such windows; the warp adds them up and sends one reduction.
+        // Exact tables (mode 2): those windows are not appended one by one either — their number goes to
+        // words_cursor[3] and exact_finalize adds ONE record {word 0, that count} (565,000 copies of one word in one
+        // bucket serialised its scatter cursor and its shared-memory counter).  Uniques pass (mode 4): one copy.
         const bool all_other = (F0 | F1 | F2 | R0 | R1 | R2) == 0u;
         const unsigned m = __ballot_sync(0xFFFFFFFFu, all_other);
         if (m) {
             const unsigned cnt = __reduce_add_sync(0xFFFFFFFFu, all_other ? 16u - __popc(inv16 & 0xFFFFu) : 0u);
-            if (lane == 0 && cnt) atomicAdd(p.acc + fastmod_kind_dev<MODK>(siphash13_dev(0u, 0u, p.rm), p.fm), cnt);
+            if (lane == 0 && cnt) {
+                const unsigned idx0 = fastmod_kind_dev<MODK>(siphash13_dev(0u, 0u, p.rm), p.fm);
+                if (MODE != 4) atomicAdd(p.acc + idx0, cnt);
+                if (MODE == 2) atomicAdd(p.words_cursor + 3, (unsigned long long)cnt);
+                if (MODE == 4 && ((__ldg(p.filter + (idx0 >> 5)) >> (idx0 & 31u)) & 1u)) {
+                    const unsigned long long slot = atomicAdd(p.words_cursor, 1ull);
+                    if (slot < p.words_cap) { p.words[slot] = 0ull; p.widx[slot] = idx0; }
+                }
+            }
             if (m == 0xFFFFFFFFu) return;
             if (all_other) inv16 = 0xFFFFu;
         }
@@ -243,6 +254,7 @@ __device__ __forceinline__ void process_chunk(const CountParams& p, const Window
     // MODE 2: reserve this warp's slots in the word array with ONE atomic per 512-position chunk
     unsigned long long* wslot = nullptr;
     unsigned int* islot = nullptr;
+    unsigned wstride = 1u;
     if (MODE == 2) {
         const unsigned mine = 16u - __popc(inv16 & 0xFFFFu);
         unsigned incl = mine;
@@ -256,6 +268,13 @@ __device__ __forceinline__ void process_chunk(const CountParams& p, const Window
         base = __shfl_sync(0xFFFFFFFFu, base, 31);
         wslot = p.words + base + (incl - mine);
         islot = p.widx + base + (incl - mine);
+        if (__all_sync(0xFFFFFFFFu, mine == 16u)) {
+            // the common case: window j of lane l goes to slot 32 j + l, so that every store instruction of the warp
+            // writes 32 consecutive words (the order inside the array means nothing: it is partitioned afterwards)
+            wslot = p.words + base + lane;
+            islot = p.widx + base + lane;
+            wstride = 32u;
+        }
     }
     constexpr int kUnroll = NK_COUNT_UNROLL;
     // word of window j of this lane (canonical min, or pack_kmer) — pure function of the code words
@@ -357,7 +376,7 @@ __device__ __forceinline__ void process_chunk(const CountParams& p, const Window
                 if (slot < p.words_cap) { p.words[slot] = word; p.widx[slot] = idx; }
             }
         } else {
-            if (MODE == 2 && !bad) { *wslot++ = word; *islot++ = idx; }
+            if (MODE == 2 && !bad) { *wslot = word; *islot = idx; wslot += wstride; islot += wstride; }
 #ifdef NK_EXP_NORED
             // diagnostic build only (tools/variants.sh): no pool update, keep the value alive
             if (idx == 0xFFFFFFFFu) p.acc[0] = bad;

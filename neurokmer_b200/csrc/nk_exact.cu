@@ -143,6 +143,7 @@ __global__ void bucket_scatter_kernel(const unsigned long long* __restrict__ wor
 // uniques != null: +1 per distinct word on its neuron (kmer_per_neuron).  *overflow is raised if a bucket holds
 // more distinct words than the table takes (the caller re-partitions into more buckets).
 __global__ void __launch_bounds__(XT) bucket_dedup_kernel(ExactSlot* __restrict__ recs, const unsigned long long* __restrict__ start,
+                                                           const unsigned long long* __restrict__ filled,
                                                            unsigned int* __restrict__ distinct, unsigned int* __restrict__ uniques,
                                                            unsigned long long* __restrict__ n_distinct_total,
                                                            unsigned int* __restrict__ overflow) {
@@ -153,7 +154,9 @@ __global__ void __launch_bounds__(XT) bucket_dedup_kernel(ExactSlot* __restrict_
     unsigned short* s_list = reinterpret_cast<unsigned short*>(s_ix + TABLE_SLOTS);  // TABLE_SLOTS entries
     __shared__ unsigned int s_ones_cnt, s_ones_ix, s_over, s_nd;
     const unsigned long long b = blockIdx.x;
-    const unsigned long long lo = start[b], hi = start[b + 1];
+    // `filled` = the scatter's cursors: a segment sized from the neurons' counts is longer than its records when the
+    // count kernel summed a run of N into one weighted record
+    const unsigned long long lo = start[b], hi = filled[b];
     const unsigned tid = threadIdx.x;
     if (lo == hi) {
         if (tid == 0) distinct[b] = 0u;
@@ -347,7 +350,7 @@ cudaError_t launch_filter_set(unsigned int* filter, const unsigned long long* id
 
 cudaError_t exact_clear(ExactTable& t, unsigned long long pool, bool tables_too, cudaStream_t s) {
     t.words_bound = 0;
-    if (t.cursor) NKX(cudaMemsetAsync(t.cursor, 0, sizeof(unsigned long long), s));
+    if (t.cursor) NKX(cudaMemsetAsync(t.cursor, 0, 4 * sizeof(unsigned long long), s));   // append cursor ... run-of-N count
     if (tables_too) {
         t.n_keys = 0;
         t.valid = false;
@@ -364,10 +367,23 @@ cudaError_t exact_finalize(ExactTable& t, const FastMod& fm, unsigned long long 
                            bool merge, cudaStream_t s) {
     (void)fm;
     NKX(ensure_cursor(t, s));
-    unsigned long long n_new = 0;
-    NKX(cudaMemcpyAsync(&n_new, t.cursor, sizeof n_new, cudaMemcpyDeviceToHost, s));
+    unsigned long long cur4[4] = {0, 0, 0, 0};
+    NKX(cudaMemcpyAsync(cur4, t.cursor, sizeof cur4, cudaMemcpyDeviceToHost, s));
     NKX(cudaStreamSynchronize(s));
+    unsigned long long n_new = cur4[0];
     if (n_new > t.words_cap) n_new = t.words_cap;  // (the uniques pass lets its cursor run past the capacity)
+    // windows inside runs of N, summed by the count kernel (nk_count.cu): ONE record {word 0, their number}
+    const unsigned long long n_zero = cur4[3];
+    ExactSlot* const zero_rec = reinterpret_cast<ExactSlot*>(t.cursor + 4);
+    if (n_zero) {
+        ExactSlot z;
+        z.key = 0ull;
+        z.count = (unsigned int)n_zero;
+        z.idx = fastmod_u64(siphash13_u64(0ull), fm);
+        NKX(cudaMemcpyAsync(zero_rec, &z, sizeof z, cudaMemcpyHostToDevice, s));
+        NKX(cudaStreamSynchronize(s));   // `z` is a local
+    }
+    const unsigned long long n_w = n_zero ? 1ull : 0ull;
     if (!t.uniques) {
         NKX(cudaMalloc(&t.uniques, pool * sizeof(unsigned int)));
         NKX(cudaMemsetAsync(t.uniques, 0, pool * sizeof(unsigned int), s));
@@ -376,24 +392,32 @@ cudaError_t exact_finalize(ExactTable& t, const FastMod& fm, unsigned long long 
         t.n_keys = 0;
         NKX(cudaMemsetAsync(t.uniques, 0, pool * sizeof(unsigned int), s));
     }
-    if (merge && n_new > 0) {
+    if (merge && n_new + n_w > 0) {
         if (!t.flags) {
             NKX(cudaMalloc(&t.flags, pool * sizeof(unsigned int)));
             NKX(cudaMemsetAsync(t.flags, 0, pool * sizeof(unsigned int), s));
         }
         const unsigned blocks = (unsigned)((n_new + 255) / 256);
-        touched_kernel<<<blocks, 256, 0, s>>>(t.widx, n_new, t.flags, t.uniques, 0);
-        touched_kernel<<<blocks, 256, 0, s>>>(t.widx, n_new, t.flags, t.uniques, 1);
+        if (n_new) touched_kernel<<<blocks, 256, 0, s>>>(t.widx, n_new, t.flags, t.uniques, 0);
+        if (n_w) touched_kernel<<<1, 32, 0, s>>>(&zero_rec->idx, 1, t.flags, t.uniques, 0);
+        if (n_new) touched_kernel<<<blocks, 256, 0, s>>>(t.widx, n_new, t.flags, t.uniques, 1);
+        if (n_w) touched_kernel<<<1, 32, 0, s>>>(&zero_rec->idx, 1, t.flags, t.uniques, 1);
     }
     // input records of the partition: the new windows (weight 1) and, when merging, the table's records
-    const unsigned long long n_old = merge ? t.n_keys : 0;
+    const unsigned long long n_tab = merge ? t.n_keys : 0;
+    const unsigned long long n_old = n_tab + n_w;          // weighted records: the old table and the run-of-N record
     const unsigned long long n_in = n_new + n_old;
-    if (n_new > 0) {
+    if (n_new + n_w > 0) {
         ExactSlot* old_dense = nullptr;
-        if (n_old) {  // the old table, dense (it is rebuilt together with the new windows)
-            NKX(cudaMalloc(&old_dense, n_old * sizeof(ExactSlot)));
+        ExactSlot* old_alloc = nullptr;
+        if (n_tab) {  // the old table, dense (it is rebuilt together with the new windows)
+            NKX(cudaMalloc(&old_alloc, n_old * sizeof(ExactSlot)));
+            old_dense = old_alloc;
             cudaError_t e = exact_dense_copy(t, nullptr, nullptr, old_dense, s);
-            if (e != cudaSuccess) { cudaFree(old_dense); return e; }
+            if (e == cudaSuccess && n_w) e = cudaMemcpyAsync(old_dense + n_tab, zero_rec, sizeof(ExactSlot), cudaMemcpyDeviceToDevice, s);
+            if (e != cudaSuccess) { cudaFree(old_alloc); return e; }
+        } else if (n_w) {
+            old_dense = zero_rec;
         }
         cudaError_t err = cudaSuccess;
         for (unsigned attempt = 0, split = 1; attempt < 4; ++attempt, split *= 4) {
@@ -402,7 +426,8 @@ cudaError_t exact_finalize(ExactTable& t, const FastMod& fm, unsigned long long 
             if (err == cudaSuccess) err = ensure((void**)&t.bucket_distinct, &t.bucket_distinct_cap, bp.nbuckets * sizeof(unsigned int));
             if (err == cudaSuccess) err = ensure((void**)&t.bucket_start, &t.bucket_start_cap, (bp.nbuckets + 1) * sizeof(unsigned long long));
             if (err == cudaSuccess) err = ensure((void**)&t.bucket_cursor, &t.bucket_cursor_cap, (bp.nbuckets + 1) * sizeof(unsigned long long));
-            if (err == cudaSuccess) err = ensure((void**)&t.recs, &t.recs_cap, n_in * sizeof(ExactSlot));
+            // (segments sized from the neurons' counts also hold room for the run-of-N windows that arrive as one record)
+            if (err == cudaSuccess) err = ensure((void**)&t.recs, &t.recs_cap, (n_in + n_zero) * sizeof(ExactSlot));
             if (err == cudaSuccess) err = cudaMemsetAsync(t.cursor + 1, 0, 2 * sizeof(unsigned long long), s);  // [1] distinct total, [2] overflow
             if (err != cudaSuccess) break;
             if (pool_counts && !merge && bp.splits == 1) {
@@ -424,7 +449,7 @@ cudaError_t exact_finalize(ExactTable& t, const FastMod& fm, unsigned long long 
                 if (err != cudaSuccess) break;
                 smem_set[dev].store(true);
             }
-            bucket_dedup_kernel<<<(unsigned)bp.nbuckets, XT, kDedupSmem, s>>>(t.recs, t.bucket_start, t.bucket_distinct,
+            bucket_dedup_kernel<<<(unsigned)bp.nbuckets, XT, kDedupSmem, s>>>(t.recs, t.bucket_start, t.bucket_cursor, t.bucket_distinct,
                                                                              merge ? nullptr : t.uniques, t.cursor + 1,
                                                                              reinterpret_cast<unsigned int*>(t.cursor + 2));
             err = cudaGetLastError();
@@ -446,13 +471,14 @@ cudaError_t exact_finalize(ExactTable& t, const FastMod& fm, unsigned long long 
             }
             err = cudaErrorInvalidValue;
         }
-        if (old_dense) { cudaStreamSynchronize(s); cudaFree(old_dense); }
+        if (old_alloc) { cudaStreamSynchronize(s); cudaFree(old_alloc); }
         if (err != cudaSuccess) return err;
     }
     t.valid = true;
     // the words of this call are consumed
     t.words_bound = 0;
     NKX(cudaMemsetAsync(t.cursor, 0, sizeof(unsigned long long), s));
+    NKX(cudaMemsetAsync(t.cursor + 3, 0, sizeof(unsigned long long), s));
     return cudaGetLastError();
 }
 

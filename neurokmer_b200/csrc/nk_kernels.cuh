@@ -285,7 +285,8 @@ struct ExactTable {
     unsigned long long* words = nullptr;
     unsigned int* widx = nullptr;
     unsigned long long words_cap = 0, words_bound = 0;
-    unsigned long long* cursor = nullptr;  // [0] append cursor, [1] distinct total, [2] overflow flag
+    unsigned long long* cursor = nullptr;  // [0] append cursor, [1] distinct total, [2] overflow flag, [3] windows inside runs of N
+                                           // (summed by the count kernel), [4..5] their one weighted record (an ExactSlot)
     // the table: bucket b's distinct records are recs[bucket_start[b] .. + bucket_distinct[b])
     ExactSlot* recs = nullptr;          unsigned long long recs_cap = 0;
     unsigned long long n_keys = 0;      // distinct words

@@ -17,7 +17,7 @@ c = SpikingKmerCounter(31, 1.0, 0.95, 2, 1.0, 2_000_000, True)
 n = bench.NBASES
 offsets = np.concatenate([[0], np.cumsum(bench.SEQ_LENS)]).astype(np.uint64)
 db, do = c.stage_reserve(n, 7)
-c.synth_fill(db, 2, 0, n, 3); copy_h2d(do, offsets); c.synchronize()
+c.synth_fill(db, 2, 0, n, int(os.environ.get('NK_SYNTH_FLAGS', 3))); copy_h2d(do, offsets); c.synchronize()
 for exact in (False, True):
     c.enable_exact_counts(exact)
     ts = []

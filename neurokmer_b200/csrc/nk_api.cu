@@ -906,6 +906,42 @@ int fold_and_simulate(nk_counter* h, bool skip_zero, PhaseEvents& pe, bool with_
     return NK_OK;
 }
 
+// get_count on one table of `h`'s device (the handle's own table, or a group member's slice table)
+int exact_lookup_in(nk_counter* h, nk::ExactTable& t, uint64_t kmer, uint32_t* count, int32_t* found) {
+    NK_CUDA(cudaSetDevice(h->cfg.device));
+    NK_TRY(resolve(h));
+    *count = 0;
+    *found = 0;
+    if (!t.valid || t.n_keys == 0) return NK_OK;
+    NK_CUDA(nk::exact_lookup(t, h->fm, kmer, h->scalars + 4, h->stream));
+    NK_CUDA(cudaMemcpyAsync(h->h_scalars + 4, h->scalars + 4, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    NK_CUDA(cudaStreamSynchronize(h->stream));
+    *found = (int32_t)h->h_scalars[4];
+    *count = (uint32_t)h->h_scalars[5];
+    return NK_OK;
+}
+
+// one table's (key, count) rows to host arrays of t.n_keys entries (either may be null)
+int exact_copy_table_of(nk_counter* h, nk::ExactTable& t, uint64_t* keys, uint32_t* counts) {
+    NK_CUDA(cudaSetDevice(h->cfg.device));
+    NK_TRY(resolve(h));
+    const unsigned long long n = t.valid ? t.n_keys : 0;
+    if (n == 0) return NK_OK;
+    // the table lives bucket by bucket: compact it into dense device arrays, then copy those out
+    unsigned long long* dk = nullptr;
+    unsigned int* dc = nullptr;
+    if (keys) NK_CUDA(cudaMalloc(&dk, n * 8));
+    if (counts && cudaMalloc(&dc, n * 4) != cudaSuccess) { cudaFree(dk); return fail(NK_ERR_OOM, "cudaMalloc(exact table copy)"); }
+    cudaError_t e = nk::exact_dense_copy(t, dk, dc, nullptr, h->stream);
+    if (e == cudaSuccess && keys) e = cudaMemcpyAsync(keys, dk, n * 8, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess && counts) e = cudaMemcpyAsync(counts, dc, n * 4, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(dk);
+    cudaFree(dc);
+    NK_CUDA(e);
+    return NK_OK;
+}
+
 }  // namespace nkd
 
 using namespace nkd;
@@ -1560,6 +1596,7 @@ int nk_destroy(nk_counter* h) {
     for (int r = 0; r < 16; ++r) if (h->dist_ipc_opened[r]) cudaIpcCloseMemHandle((void*)h->dist_peer[r]);
     cudaFree(h->d_merged);
     nk::exact_free(h->xt);
+    nk::exact_free(h->xs);
     cudaFree(h->d_top_uniques);
     ingest_free(h);
     free_devbuf(h->buf[0]); free_devbuf(h->buf[1]); free_devbuf(h->staged); free_devbuf(h->zc);
@@ -1859,36 +1896,26 @@ int nk_energy_used(const nk_counter* h, double* out) {
     return NK_OK;
 }
 int nk_enable_exact_counts(nk_counter* h, int on) {
-    if (is_group(h)) return group_unsupported("nk_enable_exact_counts");
+    if (is_group(h)) return group_enable_exact(h, on);
     if (!h) return fail(NK_ERR_BAD_ARG, "null handle");
     if (h->streaming) return fail(NK_ERR_STATE, "nk_enable_exact_counts inside nk_stream_begin/end");
     NK_CUDA(cudaSetDevice(h->cfg.device));
     NK_TRY(resolve(h));
     h->exact = on != 0;
-    if (!h->exact) { NK_CUDA(cudaStreamSynchronize(h->stream)); nk::exact_free(h->xt); }
+    if (!h->exact) { NK_CUDA(cudaStreamSynchronize(h->stream)); nk::exact_free(h->xt); nk::exact_free(h->xs); }
     return NK_OK;
 }
 
 int nk_get_count(nk_counter* h, uint64_t kmer, uint32_t* count, int32_t* found) {
-    if (is_group(h)) return group_unsupported("nk_get_count");
+    if (is_group(h)) return group_get_count(h, kmer, count, found);
     if (!h || !count || !found) return fail(NK_ERR_BAD_ARG, "null argument");
     if (!h->exact)
         return fail(NK_ERR_UNSUPPORTED, "exact k-mer table is off: call nk_enable_exact_counts(h, 1) before processing");
-    NK_CUDA(cudaSetDevice(h->cfg.device));
-    NK_TRY(resolve(h));
-    *count = 0;
-    *found = 0;
-    if (!h->xt.valid || h->xt.n_keys == 0) return NK_OK;
-    NK_CUDA(nk::exact_lookup(h->xt, h->fm, kmer, h->scalars + 4, h->stream));
-    NK_CUDA(cudaMemcpyAsync(h->h_scalars + 4, h->scalars + 4, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
-    NK_CUDA(cudaStreamSynchronize(h->stream));
-    *found = (int32_t)h->h_scalars[4];
-    *count = (uint32_t)h->h_scalars[5];
-    return NK_OK;
+    return exact_lookup_in(h, h->xt, kmer, count, found);
 }
 
 int nk_exact_table_size(nk_counter* h, uint64_t* n) {
-    if (is_group(h)) return group_unsupported("nk_exact_table_size");
+    if (is_group(h)) return group_exact_table_size(h, n);
     if (!h || !n) return fail(NK_ERR_BAD_ARG, "null argument");
     if (!h->exact) return fail(NK_ERR_UNSUPPORTED, "exact k-mer table is off");
     NK_TRY(resolve(h));
@@ -1897,30 +1924,14 @@ int nk_exact_table_size(nk_counter* h, uint64_t* n) {
 }
 
 int nk_copy_exact_table(nk_counter* h, uint64_t* keys, uint32_t* counts) {
-    if (is_group(h)) return group_unsupported("nk_copy_exact_table");
+    if (is_group(h)) return group_copy_exact_table(h, keys, counts);
     if (!h) return fail(NK_ERR_BAD_ARG, "null handle");
     if (!h->exact) return fail(NK_ERR_UNSUPPORTED, "exact k-mer table is off");
-    NK_CUDA(cudaSetDevice(h->cfg.device));
-    NK_TRY(resolve(h));
-    const unsigned long long n = h->xt.valid ? h->xt.n_keys : 0;
-    if (n == 0) return NK_OK;
-    // the table lives bucket by bucket: compact it into dense device arrays, then copy those out
-    unsigned long long* dk = nullptr;
-    unsigned int* dc = nullptr;
-    if (keys) NK_CUDA(cudaMalloc(&dk, n * 8));
-    if (counts && cudaMalloc(&dc, n * 4) != cudaSuccess) { cudaFree(dk); return fail(NK_ERR_OOM, "cudaMalloc(exact table copy)"); }
-    cudaError_t e = nk::exact_dense_copy(h->xt, dk, dc, nullptr, h->stream);
-    if (e == cudaSuccess && keys) e = cudaMemcpyAsync(keys, dk, n * 8, cudaMemcpyDeviceToHost, h->stream);
-    if (e == cudaSuccess && counts) e = cudaMemcpyAsync(counts, dc, n * 4, cudaMemcpyDeviceToHost, h->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    cudaFree(dk);
-    cudaFree(dc);
-    NK_CUDA(e);
-    return NK_OK;
+    return exact_copy_table_of(h, h->xt, keys, counts);
 }
 
 int nk_copy_uniques(nk_counter* h, uint32_t* out) {
-    if (is_group(h)) return group_unsupported("nk_copy_uniques");
+    if (is_group(h)) return group_copy_uniques(h, out);
     if (!h || !out) return fail(NK_ERR_BAD_ARG, "null argument");
     if (!h->exact) return fail(NK_ERR_UNSUPPORTED, "exact k-mer table is off");
     NK_CUDA(cudaSetDevice(h->cfg.device));

@@ -41,8 +41,8 @@ namespace nk {
 namespace {
 
 constexpr int XT = 256;                       // threads per block
-constexpr unsigned TABLE_SLOTS = 4096;        // shared-memory hash table of one bucket (power of two)
-constexpr unsigned long long BUCKET_TARGET = 1536;  // windows per bucket aimed at (table load <= ~0.4 when all distinct)
+constexpr unsigned TABLE_SLOTS = 2048;        // shared-memory hash table of one bucket (power of two)
+constexpr unsigned long long BUCKET_TARGET = 768;   // windows per bucket aimed at (table load <= ~0.4 when all distinct)
 constexpr unsigned long long EMPTY = ~0ull;   // no k < 32 word and no canonical word equals it; see dedup kernel
 
 #define NKX(expr)                        \
@@ -85,15 +85,17 @@ __global__ void bucket_hist_from_pool_kernel(const unsigned long long* __restric
     bucket_count[b] = (unsigned int)s;
 }
 
+// (flo, fhi): only records of the neurons [flo, fhi) take part (a slice table built from other GPUs' whole buckets)
 __global__ void bucket_hist_kernel(const unsigned long long* __restrict__ words, const unsigned int* __restrict__ widx,
                                    const ExactSlot* __restrict__ recs, unsigned long long n_recs, unsigned long long n, BucketPlan bp,
-                                   unsigned int* __restrict__ bucket_count) {
+                                   unsigned int flo, unsigned int fhi, unsigned int* __restrict__ bucket_count) {
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n + n_recs; i += stride) {
         unsigned ix;
         unsigned long long w = 0;
         if (i < n_recs) { ix = recs[i].idx; if (bp.splits > 1) w = recs[i].key; }
         else { ix = widx[i - n_recs]; if (bp.splits > 1) w = words[i - n_recs]; }
+        if (ix < flo || ix >= fhi) continue;
         atomicAdd(bucket_count + bucket_of(ix, w, bp), 1u);
     }
 }
@@ -123,17 +125,36 @@ __global__ void __launch_bounds__(1024) bucket_scan_kernel(const unsigned int* _
     }
 }
 
-// per record: one atomic on the bucket's cursor, one 16-byte store
+// per record: one atomic on the bucket's cursor, one 16-byte store.  The kernel is latency-bound (ncu: 68 % of the
+// stall samples wait for the atomic's return value, 4.6 % of the issue slots used), so every thread keeps
+// SCATTER_BATCH records in flight: all loads, then all atomics, then all stores.
+constexpr int SCATTER_BATCH = 4;
 __global__ void bucket_scatter_kernel(const unsigned long long* __restrict__ words, const unsigned int* __restrict__ widx,
                                       const ExactSlot* __restrict__ recs, unsigned long long n_recs, unsigned long long n,
-                                      BucketPlan bp, unsigned long long* __restrict__ cursor, ExactSlot* __restrict__ out) {
-    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n + n_recs; i += stride) {
-        ExactSlot r;
-        if (i < n_recs) r = recs[i];
-        else { r.key = words[i - n_recs]; r.idx = widx[i - n_recs]; r.count = 1u; }
-        const unsigned long long pos = atomicAdd(cursor + bucket_of(r.idx, r.key, bp), 1ull);
-        reinterpret_cast<uint4*>(out)[pos] = *reinterpret_cast<const uint4*>(&r);
+                                      BucketPlan bp, unsigned int flo, unsigned int fhi,
+                                      unsigned long long* __restrict__ cursor, ExactSlot* __restrict__ out) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x, total = n + n_recs;
+    for (unsigned long long i0 = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i0 < total; i0 += stride * SCATTER_BATCH) {
+        ExactSlot r[SCATTER_BATCH];
+        bool take[SCATTER_BATCH];
+#pragma unroll
+        for (int j = 0; j < SCATTER_BATCH; ++j) {
+            const unsigned long long i = i0 + (unsigned long long)j * stride;
+            take[j] = i < total;
+            r[j].key = 0ull; r[j].idx = 0u; r[j].count = 1u;
+            if (take[j]) {
+                if (i < n_recs) r[j] = recs[i];
+                else { r[j].key = words[i - n_recs]; r[j].idx = widx[i - n_recs]; }
+                take[j] = r[j].idx >= flo && r[j].idx < fhi;
+            }
+        }
+        unsigned long long pos[SCATTER_BATCH];
+#pragma unroll
+        for (int j = 0; j < SCATTER_BATCH; ++j)
+            pos[j] = take[j] ? atomicAdd(cursor + bucket_of(r[j].idx, r[j].key, bp), 1ull) : 0ull;
+#pragma unroll
+        for (int j = 0; j < SCATTER_BATCH; ++j)
+            if (take[j]) reinterpret_cast<uint4*>(out)[pos[j]] = *reinterpret_cast<const uint4*>(&r[j]);
     }
 }
 
@@ -363,6 +384,67 @@ cudaError_t exact_clear(ExactTable& t, unsigned long long pool, bool tables_too,
 // that exists (process_sequence: counts accumulate over calls, :218-221) and use its "neurons touched by this
 // sequence" rule for the per-neuron column; else the table is replaced (counts.clear(), :157 / :426).
 // pool_counts (may be null): per-neuron counts of exactly the appended windows (the call's u64 currents).
+// records -> table: bucket sizes, scan, scatter, per-bucket dedup; re-partitions finer if a bucket overflows its
+// on-chip table.  Input: the n_new appended windows (weight 1) and n_old weighted records (`old_dense`).
+static cudaError_t partition_and_dedup(ExactTable& t, unsigned long long pool, const unsigned long long* pool_counts, bool merge,
+                                       unsigned long long n_new, const ExactSlot* old_dense, unsigned long long n_old,
+                                       unsigned long long n_zero, unsigned int flo, unsigned int fhi, cudaStream_t s) {
+    const unsigned long long n_in = n_new + n_old;
+    cudaError_t err = cudaSuccess;
+    for (unsigned attempt = 0, split = 1; attempt < 4; ++attempt, split *= 4) {
+        const BucketPlan bp = make_plan(n_in, pool, split);
+        err = ensure((void**)&t.bucket_count, &t.bucket_count_cap, bp.nbuckets * sizeof(unsigned int));
+        if (err == cudaSuccess) err = ensure((void**)&t.bucket_distinct, &t.bucket_distinct_cap, bp.nbuckets * sizeof(unsigned int));
+        if (err == cudaSuccess) err = ensure((void**)&t.bucket_start, &t.bucket_start_cap, (bp.nbuckets + 1) * sizeof(unsigned long long));
+        if (err == cudaSuccess) err = ensure((void**)&t.bucket_cursor, &t.bucket_cursor_cap, (bp.nbuckets + 1) * sizeof(unsigned long long));
+        // (segments sized from the neurons' counts also hold room for the run-of-N windows that arrive as one record)
+        if (err == cudaSuccess) err = ensure((void**)&t.recs, &t.recs_cap, (n_in + n_zero) * sizeof(ExactSlot));
+        if (err == cudaSuccess) err = cudaMemsetAsync(t.cursor + 1, 0, 2 * sizeof(unsigned long long), s);  // [1] distinct total, [2] overflow
+        if (err != cudaSuccess) break;
+        if (pool_counts && !merge && bp.splits == 1) {
+            bucket_hist_from_pool_kernel<<<(unsigned)((bp.nbuckets + 255) / 256), 256, 0, s>>>(pool_counts, pool, bp, t.bucket_count);
+        } else {
+            err = cudaMemsetAsync(t.bucket_count, 0, bp.nbuckets * sizeof(unsigned int), s);
+            if (err != cudaSuccess) break;
+            bucket_hist_kernel<<<grid_for(n_in), XT, 0, s>>>(t.words, t.widx, old_dense, n_old, n_new, bp, flo, fhi, t.bucket_count);
+        }
+        bucket_scan_kernel<<<1, 1024, 0, s>>>(t.bucket_count, bp.nbuckets, t.bucket_start, t.bucket_cursor);
+        bucket_scatter_kernel<<<grid_for(n_in), XT, 0, s>>>(t.words, t.widx, old_dense, n_old, n_new, bp, flo, fhi, t.bucket_cursor, t.recs);
+        constexpr int kDedupSmem = TABLE_SLOTS * (8 + 4 + 4 + 2);
+        static std::atomic<bool> smem_set[64];
+        int dev = 0;
+        err = cudaGetDevice(&dev);
+        if (err != cudaSuccess) break;
+        if (dev >= 0 && dev < 64 && !smem_set[dev].load()) {
+            err = cudaFuncSetAttribute(bucket_dedup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDedupSmem);
+            if (err != cudaSuccess) break;
+            smem_set[dev].store(true);
+        }
+        bucket_dedup_kernel<<<(unsigned)bp.nbuckets, XT, kDedupSmem, s>>>(t.recs, t.bucket_start, t.bucket_cursor, t.bucket_distinct,
+                                                                         merge ? nullptr : t.uniques, t.cursor + 1,
+                                                                         reinterpret_cast<unsigned int*>(t.cursor + 2));
+        err = cudaGetLastError();
+        if (err != cudaSuccess) break;
+        unsigned long long res[2] = {0, 0};
+        err = cudaMemcpyAsync(res, t.cursor + 1, sizeof res, cudaMemcpyDeviceToHost, s);
+        if (err == cudaSuccess) err = cudaStreamSynchronize(s);
+        if (err != cudaSuccess) break;
+        if ((res[1] & 0xFFFFFFFFull) == 0) {
+            t.plan = bp;
+            t.n_keys = res[0];
+            break;
+        }
+        // a bucket held more distinct words than the table takes: partition finer.  `uniques` was touched by the
+        // buckets that did finish: start over with it
+        if (!merge) {
+            err = cudaMemsetAsync(t.uniques, 0, pool * sizeof(unsigned int), s);
+            if (err != cudaSuccess) break;
+        }
+        err = cudaErrorInvalidValue;
+    }
+    return err;
+}
+
 cudaError_t exact_finalize(ExactTable& t, const FastMod& fm, unsigned long long pool, const unsigned long long* pool_counts,
                            bool merge, cudaStream_t s) {
     (void)fm;
@@ -419,58 +501,7 @@ cudaError_t exact_finalize(ExactTable& t, const FastMod& fm, unsigned long long 
         } else if (n_w) {
             old_dense = zero_rec;
         }
-        cudaError_t err = cudaSuccess;
-        for (unsigned attempt = 0, split = 1; attempt < 4; ++attempt, split *= 4) {
-            const BucketPlan bp = make_plan(n_in, pool, split);
-            err = ensure((void**)&t.bucket_count, &t.bucket_count_cap, bp.nbuckets * sizeof(unsigned int));
-            if (err == cudaSuccess) err = ensure((void**)&t.bucket_distinct, &t.bucket_distinct_cap, bp.nbuckets * sizeof(unsigned int));
-            if (err == cudaSuccess) err = ensure((void**)&t.bucket_start, &t.bucket_start_cap, (bp.nbuckets + 1) * sizeof(unsigned long long));
-            if (err == cudaSuccess) err = ensure((void**)&t.bucket_cursor, &t.bucket_cursor_cap, (bp.nbuckets + 1) * sizeof(unsigned long long));
-            // (segments sized from the neurons' counts also hold room for the run-of-N windows that arrive as one record)
-            if (err == cudaSuccess) err = ensure((void**)&t.recs, &t.recs_cap, (n_in + n_zero) * sizeof(ExactSlot));
-            if (err == cudaSuccess) err = cudaMemsetAsync(t.cursor + 1, 0, 2 * sizeof(unsigned long long), s);  // [1] distinct total, [2] overflow
-            if (err != cudaSuccess) break;
-            if (pool_counts && !merge && bp.splits == 1) {
-                bucket_hist_from_pool_kernel<<<(unsigned)((bp.nbuckets + 255) / 256), 256, 0, s>>>(pool_counts, pool, bp, t.bucket_count);
-            } else {
-                err = cudaMemsetAsync(t.bucket_count, 0, bp.nbuckets * sizeof(unsigned int), s);
-                if (err != cudaSuccess) break;
-                bucket_hist_kernel<<<grid_for(n_in), XT, 0, s>>>(t.words, t.widx, old_dense, n_old, n_new, bp, t.bucket_count);
-            }
-            bucket_scan_kernel<<<1, 1024, 0, s>>>(t.bucket_count, bp.nbuckets, t.bucket_start, t.bucket_cursor);
-            bucket_scatter_kernel<<<grid_for(n_in), XT, 0, s>>>(t.words, t.widx, old_dense, n_old, n_new, bp, t.bucket_cursor, t.recs);
-            constexpr int kDedupSmem = TABLE_SLOTS * (8 + 4 + 4 + 2);
-            static std::atomic<bool> smem_set[64];
-            int dev = 0;
-            err = cudaGetDevice(&dev);
-            if (err != cudaSuccess) break;
-            if (dev >= 0 && dev < 64 && !smem_set[dev].load()) {
-                err = cudaFuncSetAttribute(bucket_dedup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDedupSmem);
-                if (err != cudaSuccess) break;
-                smem_set[dev].store(true);
-            }
-            bucket_dedup_kernel<<<(unsigned)bp.nbuckets, XT, kDedupSmem, s>>>(t.recs, t.bucket_start, t.bucket_cursor, t.bucket_distinct,
-                                                                             merge ? nullptr : t.uniques, t.cursor + 1,
-                                                                             reinterpret_cast<unsigned int*>(t.cursor + 2));
-            err = cudaGetLastError();
-            if (err != cudaSuccess) break;
-            unsigned long long res[2] = {0, 0};
-            err = cudaMemcpyAsync(res, t.cursor + 1, sizeof res, cudaMemcpyDeviceToHost, s);
-            if (err == cudaSuccess) err = cudaStreamSynchronize(s);
-            if (err != cudaSuccess) break;
-            if ((res[1] & 0xFFFFFFFFull) == 0) {
-                t.plan = bp;
-                t.n_keys = res[0];
-                break;
-            }
-            // a bucket held more distinct words than the table takes: partition finer.  `uniques` was touched by the
-            // buckets that did finish: start over with it
-            if (!merge) {
-                err = cudaMemsetAsync(t.uniques, 0, pool * sizeof(unsigned int), s);
-                if (err != cudaSuccess) break;
-            }
-            err = cudaErrorInvalidValue;
-        }
+        const cudaError_t err = partition_and_dedup(t, pool, pool_counts, merge, n_new, old_dense, n_old, n_zero, 0u, 0xFFFFFFFFu, s);
         if (old_alloc) { cudaStreamSynchronize(s); cudaFree(old_alloc); }
         if (err != cudaSuccess) return err;
     }
@@ -491,6 +522,42 @@ cudaError_t exact_dense_copy(ExactTable& t, unsigned long long* out_keys, unsign
     bucket_scan_kernel<<<1, 1024, 0, s>>>(t.bucket_distinct, nb, t.dense_start, nullptr);
     compact_table_kernel<<<(unsigned)nb, 128, 0, s>>>(t.recs, t.bucket_start, t.bucket_distinct, t.dense_start, out_keys, out_counts, out_recs);
     return cudaGetLastError();
+}
+
+// ---- tables of a multi-GPU group: every GPU builds the table of its own share of the windows, then GPU d collects
+// the records of ITS neuron slice from all of them and merges equal words (src/spiking_hash.rs:157-172: one map) ----
+
+// The dense copy of `t` (bucket order = neuron order) into out_recs (n_keys records) and, for every neuron range
+// [bounds[i], bounds[i+1]) (i < n_ranges), the dense range of the buckets that hold it: first[i] .. last[i]
+// (boundary buckets are shared by two ranges: the reader filters by neuron index).
+cudaError_t exact_dense_export(ExactTable& t, ExactSlot* out_recs, const unsigned long long* bounds, int n_ranges,
+                               unsigned long long* first, unsigned long long* last, cudaStream_t s) {
+    for (int i = 0; i < n_ranges; ++i) first[i] = last[i] = 0;
+    if (!t.valid || t.n_keys == 0) return cudaSuccess;
+    NKX(exact_dense_copy(t, nullptr, nullptr, out_recs, s));
+    const unsigned long long npb = t.plan.neurons_per_bucket, sp = t.plan.splits, nb = t.plan.nbuckets;
+    for (int i = 0; i < n_ranges; ++i) {
+        if (bounds[i + 1] <= bounds[i]) continue;
+        unsigned long long b0 = (bounds[i] / npb) * sp, b1 = ((bounds[i + 1] - 1) / npb + 1) * sp;
+        if (b0 > nb) b0 = nb;
+        if (b1 > nb) b1 = nb;
+        NKX(cudaMemcpyAsync(first + i, t.dense_start + b0, 8, cudaMemcpyDeviceToHost, s));
+        NKX(cudaMemcpyAsync(last + i, t.dense_start + b1, 8, cudaMemcpyDeviceToHost, s));
+    }
+    return cudaStreamSynchronize(s);
+}
+
+// `t` <- the table of the weighted records `recs` restricted to the neurons [flo, fhi)
+cudaError_t exact_build_from_records(ExactTable& t, unsigned long long pool, const ExactSlot* recs, unsigned long long n_recs,
+                                     unsigned int flo, unsigned int fhi, cudaStream_t s) {
+    NKX(ensure_cursor(t, s));
+    if (!t.uniques) NKX(cudaMalloc(&t.uniques, pool * sizeof(unsigned int)));
+    NKX(cudaMemsetAsync(t.uniques, 0, pool * sizeof(unsigned int), s));
+    t.n_keys = 0;
+    t.valid = false;
+    if (n_recs) NKX(partition_and_dedup(t, pool, nullptr, false, 0, recs, n_recs, 0, flo, fhi, s));
+    t.valid = true;
+    return cudaSuccess;
 }
 
 cudaError_t exact_lookup(const ExactTable& t, const FastMod& fm, unsigned long long key, unsigned long long* d_out2, cudaStream_t s) {

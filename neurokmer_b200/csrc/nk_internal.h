@@ -205,6 +205,11 @@ struct nk_counter {
     // exact side tables (opt-in, nk_enable_exact_counts)
     bool exact = false;
     nk::ExactTable xt;
+    // member of a multi-GPU group: the merged table of THIS GPU's neuron slice (xt holds its own windows' table)
+    nk::ExactTable xs;
+    // group leader: kmer_per_neuron of the whole pool on the host (for the `uniques` column), filled on demand
+    std::vector<uint32_t> group_uniques;
+    bool group_uniques_valid = false;
     unsigned int* d_top_uniques = nullptr;
     // uniques pass (nk_uniques_*): `uniques` of the top rows by a second pass over the input, without the
     // O(windows) exact table — the words that map to the rows' neurons are collected, sorted and counted
@@ -286,5 +291,14 @@ int group_top_n(nk_counter* g, uint64_t top_n, nk_top_entry* out, uint64_t* n_ou
 int group_copy(nk_counter* g, int which, void* out);  // 0 currents, 1 spike counts, 2 voltages, 3 refractory ticks
 int group_timings(nk_counter* g, nk_timings* out);
 int group_synchronize(nk_counter* g);
+// exact side tables of a group: every GPU builds the table of its own windows, GPU d merges the records of its neuron slice
+int group_enable_exact(nk_counter* g, int on);
+int group_get_count(nk_counter* g, uint64_t kmer, uint32_t* count, int32_t* found);
+int group_exact_table_size(nk_counter* g, uint64_t* n);
+int group_copy_exact_table(nk_counter* g, uint64_t* keys, uint32_t* counts);
+int group_copy_uniques(nk_counter* g, uint32_t* out);
+// shared with the single-GPU entry points (nk_api.cu)
+int exact_lookup_in(nk_counter* h, nk::ExactTable& t, uint64_t kmer, uint32_t* count, int32_t* found);
+int exact_copy_table_of(nk_counter* h, nk::ExactTable& t, uint64_t* keys, uint32_t* counts);
 
 }  // namespace nkd

@@ -309,6 +309,11 @@ cudaError_t exact_lookup(const ExactTable& t, const FastMod& fm, unsigned long l
 // the table as dense device arrays in bucket order (any output may be null; n_keys entries each)
 cudaError_t exact_dense_copy(ExactTable& t, unsigned long long* out_keys, unsigned int* out_counts, ExactSlot* out_recs,
                              cudaStream_t s);
+// multi-GPU groups: the dense table plus the dense ranges of n_ranges neuron ranges; a table from weighted records
+cudaError_t exact_dense_export(ExactTable& t, ExactSlot* out_recs, const unsigned long long* bounds, int n_ranges,
+                               unsigned long long* first, unsigned long long* last, cudaStream_t s);
+cudaError_t exact_build_from_records(ExactTable& t, unsigned long long pool, const ExactSlot* recs, unsigned long long n_recs,
+                                     unsigned int flo, unsigned int fhi, cudaStream_t s);
 cudaError_t exact_gather_uniques(const ExactTable& t, const unsigned long long* idx, unsigned long long n,
                                  unsigned int* out, cudaStream_t s);
 void exact_free(ExactTable& t);

@@ -18,12 +18,15 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <thread>
 
 #include "nk_internal.h"
 
 using namespace nkd;
 
 namespace nkd {
+
+int exact_finalize_group(nk_counter* g);
 
 namespace {
 
@@ -84,7 +87,7 @@ int member_after_job(nk_counter* c, bool holds_slice) {
 bool sliced_path_ok(const nk_counter* g) {
     const nk_counter* c0 = g->group[0];
     const int n = (int)g->group.size();
-    if (g->group_state != kFresh || !g->group_can_peer) return false;
+    if (g->group_state != kFresh || !g->group_can_peer || g->exact) return false;   // (exact tables: LIF on group[0])
     if (c0->force_direct || c0->cfg.steps == 0 || !std::isfinite(c0->cfg.threshold) || !std::isfinite(c0->cfg.leak)) return false;
     if (saturation_count(c0->cfg) >= (1ull << 20)) return false;
     const unsigned long long per = (c0->cfg.pool_size + n - 1) / n;
@@ -233,7 +236,12 @@ int group_destroy(nk_counter* g) {
 
 int group_reset(nk_counter* g) {
     DeviceGuard dg;
-    for (nk_counter* c : g->group) NK_TRY(nk_reset(c));
+    for (nk_counter* c : g->group) {
+        NK_TRY(nk_reset(c));
+        c->xs.n_keys = 0;
+        c->xs.valid = false;
+    }
+    g->group_uniques_valid = false;
     g->group_state = kFresh;
     g->group_streaming = false;
     g->group_counted = false;
@@ -302,7 +310,9 @@ int group_end(nk_counter* g, bool skip_zero) {
     if (!g->group_streaming) return fail(NK_ERR_STATE, "nk_stream_end without nk_stream_begin");
     DeviceGuard dg;
     g->group_streaming = false;
-    return sliced_path_ok(g) ? end_sliced(g, skip_zero) : end_on_leader(g, skip_zero);
+    NK_TRY(sliced_path_ok(g) ? end_sliced(g, skip_zero) : end_on_leader(g, skip_zero));
+    if (g->exact) NK_TRY(exact_finalize_group(g));
+    return NK_OK;
 }
 
 int group_process_batch(nk_counter* g, const uint8_t* bases, const uint32_t* codes, const uint32_t* other,
@@ -334,7 +344,16 @@ int group_top_n(nk_counter* g, uint64_t top_n, nk_top_entry* out, uint64_t* n_ou
         for (nk_counter* c : g->group) c->topn_hint = std::max<unsigned long long>(c->topn_hint, n);
     // more rows than the slices computed: bring the state to group[0] and select there
     if (g->group_state == kSliced && !(c0->top_cache_valid && n <= c0->top_cached_n)) NK_TRY(gather_to_leader(g));
-    return nk_top_n(c0, top_n, out, n_out);
+    NK_TRY(nk_top_n(c0, top_n, out, n_out));
+    if (g->exact && out && n_out) {  // `uniques` = kmer_per_neuron of the MERGED table (group[0] only knows its own windows)
+        if (!g->group_uniques_valid) {
+            g->group_uniques.assign(g->cfg.pool_size, 0u);
+            NK_TRY(group_copy_uniques(g, g->group_uniques.data()));
+            g->group_uniques_valid = true;
+        }
+        for (uint64_t i = 0; i < *n_out; ++i) out[i].uniques = g->group_uniques[out[i].idx];
+    }
+    return NK_OK;
 }
 
 int group_copy(nk_counter* g, int which, void* out) {
@@ -401,7 +420,152 @@ int group_synchronize(nk_counter* g) {
     return NK_OK;
 }
 
+// ---- exact side tables of a group (src/spiking_hash.rs:157-172, 442-447, 467-473: ONE map over the whole input) ----
+// GPU m has appended (word, neuron) of ITS windows.  1. every GPU builds the table of its own windows (nk_exact.cu) and
+// a dense copy of it in neuron order; 2. GPU d copies, from every GPU, the records of the buckets that hold ITS neuron
+// slice [d*P/n, (d+1)*P/n) (peer copies) and merges equal words: the table of its slice.  get_count asks the owner of the
+// word's neuron; the table and kmer_per_neuron are the members' slices one after the other.
+namespace {
+
+template <typename F>
+void on_every_member(int n, F f) {  // one host thread per GPU (the table builders synchronise their streams)
+    std::vector<std::thread> th;
+    for (int i = 1; i < n; ++i) th.emplace_back(f, i);
+    f(0);
+    for (std::thread& t : th) t.join();
+}
+
+void slice_bounds(const nk_counter* g, std::vector<unsigned long long>& b) {
+    const unsigned long long n = g->group.size(), P = g->cfg.pool_size, per = (P + n - 1) / n;
+    b.resize(n + 1);
+    for (unsigned long long i = 0; i <= n; ++i) b[i] = std::min(P, i * per);
+}
+
+}  // namespace
+
+int exact_finalize_group(nk_counter* g) {
+    NvtxRange nvtx("nk:exact tables (multi-GPU group: per-GPU tables, then the slice merge over peer copies)");
+    const int n = (int)g->group.size();
+    const unsigned long long P = g->cfg.pool_size;
+    std::vector<unsigned long long> bounds;
+    slice_bounds(g, bounds);
+    struct Export {
+        nk::ExactSlot* dense = nullptr;
+        std::vector<unsigned long long> first, last;
+        cudaError_t e = cudaSuccess;
+    };
+    std::vector<Export> ex((size_t)n);
+    on_every_member(n, [&](int m) {
+        nk_counter* c = g->group[(size_t)m];
+        Export& x = ex[(size_t)m];
+        x.first.assign((size_t)n, 0);
+        x.last.assign((size_t)n, 0);
+        x.e = cudaSetDevice(c->cfg.device);
+        if (x.e == cudaSuccess) x.e = nk::exact_finalize(c->xt, c->fm, P, nullptr, false, c->stream);
+        if (x.e != cudaSuccess) return;
+        const unsigned long long nk_ = c->xt.valid ? c->xt.n_keys : 0;
+        if (nk_) x.e = cudaMalloc(&x.dense, nk_ * sizeof(nk::ExactSlot));
+        if (x.e == cudaSuccess) x.e = nk::exact_dense_export(c->xt, x.dense, bounds.data(), n, x.first.data(), x.last.data(), c->stream);
+    });
+    cudaError_t bad = cudaSuccess;
+    for (const Export& x : ex) if (x.e != cudaSuccess) bad = x.e;
+    std::vector<cudaError_t> merged((size_t)n, cudaSuccess);
+    if (bad == cudaSuccess) {
+        on_every_member(n, [&](int d) {
+            nk_counter* c = g->group[(size_t)d];
+            cudaError_t& e = merged[(size_t)d];
+            e = cudaSetDevice(c->cfg.device);
+            if (e != cudaSuccess) return;
+            unsigned long long total = 0;
+            for (int m = 0; m < n; ++m) total += ex[(size_t)m].last[(size_t)d] - ex[(size_t)m].first[(size_t)d];
+            nk::ExactSlot* cat = nullptr;
+            if (total) e = cudaMalloc(&cat, total * sizeof(nk::ExactSlot));
+            unsigned long long off = 0;
+            for (int m = 0; m < n && e == cudaSuccess; ++m) {
+                const unsigned long long a = ex[(size_t)m].first[(size_t)d], len = ex[(size_t)m].last[(size_t)d] - a;
+                if (!len) continue;
+                e = cudaMemcpyPeerAsync(cat + off, c->cfg.device, ex[(size_t)m].dense + a, g->group[(size_t)m]->cfg.device,
+                                        len * sizeof(nk::ExactSlot), c->stream);
+                off += len;
+            }
+            if (e == cudaSuccess)
+                e = nk::exact_build_from_records(c->xs, P, cat, total, (unsigned)bounds[(size_t)d], (unsigned)bounds[(size_t)d + 1], c->stream);
+            cudaStreamSynchronize(c->stream);
+            cudaFree(cat);
+        });
+    }
+    for (int m = 0; m < n; ++m) {
+        cudaSetDevice(g->group[(size_t)m]->cfg.device);
+        cudaFree(ex[(size_t)m].dense);
+    }
+    for (cudaError_t e : merged) if (e != cudaSuccess) bad = e;
+    g->group_uniques_valid = false;
+    if (bad == cudaErrorInvalidValue)
+        return fail(NK_ERR_UNSUPPORTED, "exact counts: the words could not be partitioned into buckets that fit the on-chip tables");
+    if (bad != cudaSuccess) return fail(NK_ERR_CUDA, "exact tables of the group: %s", cudaGetErrorString(bad));
+    return NK_OK;
+}
+
+int group_enable_exact(nk_counter* g, int on) {
+    if (g->group_streaming) return fail(NK_ERR_STATE, "nk_enable_exact_counts inside nk_stream_begin/end");
+    DeviceGuard dg;
+    for (nk_counter* c : g->group) NK_TRY(nk_enable_exact_counts(c, on));
+    g->exact = on != 0;
+    g->group_uniques_valid = false;
+    return NK_OK;
+}
+
+int group_get_count(nk_counter* g, uint64_t kmer, uint32_t* count, int32_t* found) {
+    if (!count || !found) return fail(NK_ERR_BAD_ARG, "null argument");
+    if (!g->exact)
+        return fail(NK_ERR_UNSUPPORTED, "exact k-mer table is off: call nk_enable_exact_counts(h, 1) before processing");
+    DeviceGuard dg;
+    const nk::FastMod& fm = g->group[0]->fm;
+    const unsigned long long idx = nk::fastmod_u64(nk::siphash13_u64(kmer), fm);
+    const unsigned long long n = g->group.size(), per = (g->cfg.pool_size + n - 1) / n;
+    nk_counter* owner = g->group[(size_t)(idx / per)];
+    return exact_lookup_in(owner, owner->xs, kmer, count, found);
+}
+
+int group_exact_table_size(nk_counter* g, uint64_t* n) {
+    if (!n) return fail(NK_ERR_BAD_ARG, "null argument");
+    if (!g->exact) return fail(NK_ERR_UNSUPPORTED, "exact k-mer table is off");
+    *n = 0;
+    for (nk_counter* c : g->group) *n += c->xs.valid ? c->xs.n_keys : 0;
+    return NK_OK;
+}
+
+int group_copy_exact_table(nk_counter* g, uint64_t* keys, uint32_t* counts) {
+    if (!g->exact) return fail(NK_ERR_UNSUPPORTED, "exact k-mer table is off");
+    DeviceGuard dg;
+    unsigned long long off = 0;
+    for (nk_counter* c : g->group) {
+        NK_TRY(exact_copy_table_of(c, c->xs, keys ? keys + off : nullptr, counts ? counts + off : nullptr));
+        off += c->xs.valid ? c->xs.n_keys : 0;
+    }
+    return NK_OK;
+}
+
+int group_copy_uniques(nk_counter* g, uint32_t* out) {
+    if (!out) return fail(NK_ERR_BAD_ARG, "null argument");
+    if (!g->exact) return fail(NK_ERR_UNSUPPORTED, "exact k-mer table is off");
+    DeviceGuard dg;
+    std::vector<unsigned long long> bounds;
+    slice_bounds(g, bounds);
+    std::memset(out, 0, g->cfg.pool_size * sizeof(uint32_t));
+    for (size_t d = 0; d < g->group.size(); ++d) {
+        nk_counter* c = g->group[d];
+        const unsigned long long lo = bounds[d], len = bounds[d + 1] - lo;
+        if (!len || !c->xs.valid || !c->xs.uniques) continue;
+        NK_CUDA(cudaSetDevice(c->cfg.device));
+        NK_CUDA(cudaMemcpyAsync(out + lo, c->xs.uniques + lo, len * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        NK_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    return NK_OK;
+}
+
 }  // namespace nkd
+
 
 extern "C" {
 

@@ -222,7 +222,7 @@ def test_group_rejects_what_it_cannot_do():
     from neurokmer_b200 import NkError
     from neurokmer_b200 import _lib
     g = make_group(31, 1000, devices=[0, 0])
-    for call in (lambda: g.process_sequence(b"ACGT" * 20), lambda: g.enable_exact_counts(True), lambda: g.stage_reserve(100, 1),
+    for call in (lambda: g.process_sequence(b"ACGT" * 20), lambda: g.get_count(5), lambda: g.stage_reserve(100, 1),
                  lambda: g.dist_export(), lambda: g.stream_accumulated()):
         with pytest.raises(NkError) as e:
             call()
@@ -233,6 +233,74 @@ def test_group_rejects_what_it_cannot_do():
     g.close()
     with pytest.raises(NkError):
         make_group(31, 1000, devices=[0, 99])
+
+
+def _exact_checks(g, coracle, seqs, k, pool, canonical):
+    from test_parity_gpu import _oracle_tables
+    keys, counts, uni = _oracle_tables(coracle, seqs, k, pool, canonical)
+    gk, gc = g.exact_table()
+    np.testing.assert_array_equal(gk, keys); np.testing.assert_array_equal(gc, counts)
+    np.testing.assert_array_equal(g.kmer_per_neuron(), uni)
+    for i in range(0, len(keys), max(1, len(keys) // 23)):
+        assert g.get_count(int(keys[i])) == int(counts[i])
+    present = set(keys.tolist())
+    for x in range(1, 40):
+        if x not in present:
+            assert g.get_count(x) is None
+    top = g.top_abundant_neurons(20)
+    assert [t[2] for t in top] == [int(uni[t[0]]) for t in top]
+
+
+@pytest.mark.parametrize("k,pool,canonical,world", [(11, 5000, True, 2), (31, 100_003, True, 3), (9, 4096, False, 4), (5, 7, True, 2),
+                                                    (21, 1_000_000, True, 2)])
+def test_group_exact_tables_merge_by_neuron_slice(coracle, k, pool, canonical, world):
+    """nk_enable_exact_counts on a group (src/spiking_hash.rs:157-172, 442-447, 467-473: ONE map over the whole input):
+    every member builds the table of its own windows, member d merges the records of its neuron slice from all of
+    them.  A word that occurs in several members' shards (repeats, runs of N, poly-A) must come out ONCE with the sum;
+    get_count asks the slice's owner; kmer_per_neuron and the uniques column come from the merged table; a second call
+    replaces the table; the neuron state is what the plain group computes."""
+    rng = np.random.default_rng(k * 7 + world)
+    rep = random_dna(rng, 3000)
+    seqs = [random_dna(rng, 120_000, 0.01, 0.05), rep * 5, b"", b"ACG", random_dna(rng, 50_000, 0.0, 0.0, 0.0) + b"N" * 3000 + rep,
+            b"A" * 5000, rep + random_dna(rng, 70_000, 0.01), b"N" * 2500]
+    g = make_group(k, pool, canonical, devices=[0] * world)
+    g.enable_exact_counts(True)
+    g.process_parallel(seqs)
+    _exact_checks(g, coracle, seqs, k, pool, canonical)
+    plain = make_group(k, pool, canonical, devices=[0] * world); plain.process_parallel(seqs)
+    np.testing.assert_array_equal(plain.currents(), g.currents())
+    np.testing.assert_array_equal(plain.spike_counts(), g.spike_counts())
+    plain.close()
+    seqs2 = [random_dna(rng, 40_000), rep]
+    g.process_parallel(seqs2)                      # counts.clear() + refill (:157)
+    _exact_checks(g, coracle, seqs2, k, pool, canonical)
+    from neurokmer_b200 import flatten
+    g.reset()
+    g.stream_begin(); g.stream_push(*flatten(seqs[:3])); g.stream_push(*flatten(seqs[3:])); g.stream_end()
+    _exact_checks(g, coracle, seqs, k, pool, canonical)
+    g.process_parallel([])                         # nothing counted: empty tables
+    assert g.exact_table()[0].size == 0 and int(g.kmer_per_neuron().sum()) == 0 and g.get_count(0) is None
+    g.enable_exact_counts(False)
+    g.process_parallel(seqs2)
+    assert [t[2] for t in g.top_abundant_neurons(3)] == [None] * 3
+    g.close()
+
+
+def test_group_exact_tables_two_devices(coracle):
+    """the slice merge over real peer copies"""
+    _need_two()
+    from neurokmer_b200 import device_count
+    nd = min(device_count(), 8)
+    rng = np.random.default_rng(5)
+    k, pool = 31, 2_000_000
+    rep = random_dna(rng, 20_000)
+    seqs = [random_dna(rng, 900_000, 0.001, 0.01), rep * 3, random_dna(rng, 600_000) + b"N" * 5000 + rep, random_dna(rng, 400_000)]
+    for devs in ([0, 1], list(range(nd))):
+        g = make_group(k, pool, True, devices=devs)
+        g.enable_exact_counts(True)
+        g.process_parallel(seqs)
+        _exact_checks(g, coracle, seqs, k, pool, True)
+        g.close()
 
 
 def _need_two():

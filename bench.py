@@ -521,6 +521,27 @@ def gpu_arm(args):
                        "what": "all ranks cudaMemcpyAsync their pinned 113 MB shard to their GPU simultaneously (max over ranks)"}
         del dst
 
+    # ---- exact side tables (N = 1): the same device-resident job with nk_enable_exact_counts -------
+    exact_rec = None
+    if world == 1 and not args.no_e2e:
+        c.enable_exact_counts(True)
+        ts = []
+        for it in range(7):
+            c.reset()
+            t0 = time.perf_counter()
+            c.stream_begin(); c.process_staged(staged_now["nb"], staged_now["nseq"], 1); c.stream_finish()
+            spk = c.energy.total_spikes()   # observes the result: the job and its tables are complete
+            ts.append((time.perf_counter() - t0) * 1e3)
+        n_keys = c.exact_table_size()
+        uni_sum = int(c.kmer_per_neuron().sum(dtype=np.uint64))
+        exact_rec = {"ms_per_job": float(np.mean(ts[2:])), "ms_per_job_min": float(np.min(ts[2:])), "jobs": len(ts) - 2,
+                     "timing": "host wall clock around one whole job (count + append, bucket partition, per-bucket dedup)",
+                     "distinct_kmers": int(n_keys), "windows": int(c.timings()["kmers"]),
+                     # every distinct word belongs to exactly one neuron: the per-neuron uniques add up to the table size
+                     "check": {"uniques_sum_equals_distinct": bool(uni_sum == int(n_keys)), "total_spikes": int(spk)}}
+        c.enable_exact_counts(False)
+        c.reset()
+
     # ---- strong scaling (N > 1): the 113 Mbase job itself, cut N ways ------------------------------------------
     strong = None
     if world > 1:
@@ -765,7 +786,7 @@ def gpu_arm(args):
             "strong_scaling": None if not strong else {
                 "value": KMERS * args.steps / (strong_ms * 1e-3), "unit": "kmers/s", "ms_per_step": strong_ms / args.steps,
                 "kmers_per_step": KMERS, "note": "the N=1 job (113 Mbase, 7 sequences) cut by window start into N ranges"},
-            "config5": config5,
+            "config5": config5, "exact_tables": exact_rec,
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "result": {"total_spikes": total_spikes, "top1": list(top[0][:2]) if top else None, "parity": parity},
         }

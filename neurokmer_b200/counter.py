@@ -247,6 +247,11 @@ class SpikingKmerCounter:
         order = np.argsort(keys, kind="stable")
         return keys[order], counts[order]
 
+    def exact_table_size(self) -> int:
+        n = C.c_uint64()
+        check(self._L.nk_exact_table_size(self._h, C.byref(n)))
+        return int(n.value)
+
     def kmer_per_neuron(self) -> np.ndarray:
         return self._copy(self._L.nk_copy_uniques, np.uint32)
 

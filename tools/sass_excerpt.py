@@ -54,6 +54,6 @@ if __name__ == "__main__":
           "the FMA pipe, `DFMA`/`DADD`/`DMUL` = the exact modulo on the FP64 pipe, `SHF.L.W` = one half of a 64-bit rotate.  There is no "
           "dense contraction anywhere on this path, so no `UTC*MMA` / `LDTM` (tcgen05 / TMEM) and no `UTMALDG` (tensor-map TMA): the tiles "
           "are linear byte ranges.\n")
-    report("neurokmer_b200/build/nk_count.o", r"count_kernel<true, 5, false, true, false>", [r"UBLKCP", r"SYNCS", r"REDG", r"IMAD\.X", r"DFMA", r"SHF\.L\.W", r"ATOMG"])
+    report("neurokmer_b200/build/nk_count.o", r"count_kernel<true, 5, 3, true, false>", [r"UBLKCP", r"SYNCS", r"REDG", r"IMAD\.X", r"DFMA", r"SHF\.L\.W", r"ATOMG"])
     report("neurokmer_b200/build/nk_post.o", r"post_kernel", [r"LDG\.E\.STRONG\.SYS|LD\.E\.STRONG\.SYS|\.SYS", r"ATOMS", r"ATOMG|REDG", r"BAR\.SYNC", r"MEMBAR|ERRBAR", r"CCTL"])
     report("neurokmer_b200/build/nk_parse.o", r"fa_write_kernel", [r"VOTE|BALLOT", r"STS", r"STG\.E\.128", r"POPC"])

@@ -122,7 +122,8 @@ NK_API const char* nk_version(void);
  * The reference spreads one input over the cores of one process (rayon fold/reduce over per-thread current
  * vectors, src/spiking_hash.rs:94-154; worker threads, :292-403).  nk_create_multi is the same thing with
  * GPUs: the returned handle is used exactly like one from nk_create — nk_process_batch, nk_stream_*,
- * nk_process_file, the packed variants, nk_top_n, totals, nk_copy_*, nk_uniques_* — and every batch is cut
+ * nk_process_file, the packed variants, nk_top_n, totals, nk_copy_*, nk_uniques_*, the exact side tables
+ * (nk_enable_exact_counts ... nk_copy_uniques) — and every batch is cut
  * by window start into one contiguous range per device (sequences are cut wherever a range ends; the owner of
  * starts [a, b) reads bases [a, min(b + k-1, end of sequence)), so every window is counted exactly once).
  * Each device counts into its own accumulators; the exchange is a reduce-scatter fused into the LIF/top-N
@@ -130,7 +131,7 @@ NK_API const char* nk_version(void);
  * Results are bit-identical to a single-GPU counter.  `devices` = NULL means ordinals 0..n_devices-1;
  * cfg->device is ignored.  Needs peer access between the devices (NK_ERR_UNSUPPORTED otherwise).
  * Not available on a group handle (NK_ERR_UNSUPPORTED): nk_process_sequence (sequential by definition:
- * replicas only), the exact side tables, device-resident staging, the nk_dist_* plumbing. */
+ * replicas only), device-resident staging, the nk_dist_* plumbing. */
 NK_API int nk_device_count(int32_t* n);
 NK_API int nk_create_multi(const nk_config* cfg, const int32_t* devices, int32_t n_devices, nk_counter** out);
 /* number of devices behind the handle (1 for nk_create) */
@@ -224,7 +225,10 @@ NK_API int nk_energy_used(const nk_counter* h, double* out);
  *   kmer_per_neuron: DashMap<usize, u32>     :26, :167-172, :467-473 (the `uniques` column of nk_top_n)
  * Enable BEFORE processing.  A batch/stream/file call then replaces both tables with this call's
  * (counts.clear(), :157/:426); nk_process_sequence adds to them (:218-221, :262-264).  Limits:
- * 28 B of device memory per window of a call while its table is built, single GPU (per-rank tables are not merged).  Off by default: then
+ * 28 B of device memory per window of a call while its table is built.  On a multi-GPU group (nk_create_multi) every
+ * GPU builds the table of its own windows and GPU d merges the records of its neuron slice from all of them: ONE table
+ * over the whole input, like the reference's map; handles of different PROCESSES (nk_dist_*) keep per-rank tables.
+ * Off by default: then
  * nk_get_count returns NK_ERR_UNSUPPORTED and nk_top_n reports NK_UNIQUES_NOT_COMPUTED. */
 NK_API int nk_enable_exact_counts(nk_counter* h, int on);
 /* get_count — src/spiking_hash.rs:675-678: *found = 0 where the reference returns None. */

@@ -348,7 +348,22 @@ int count_host_batch(nk_counter* h, const uint8_t* bases, const uint64_t* offset
         if (const char* e = getenv("NK_H2D_CHUNK_MB")) { const unsigned long long t = strtoull(e, nullptr, 10); if (t >= 1 && t <= 32) mb = t; }
         chunk_bytes = mb << 20;
     }
+    // experiment knob: NK_H2D_PLAN="32,32,24,16,8,2" = chunk sizes in MiB for a pinned source, the last one repeats
+    std::vector<unsigned long long> plan;
+    if (at_ok && at.type == cudaMemoryTypeHost) {
+        if (const char* e = getenv("NK_H2D_PLAN")) {
+            for (const char* q = e; *q;) {
+                char* end = nullptr;
+                const unsigned long long t = strtoull(q, &end, 10);
+                if (end == q) break;
+                if (t >= 1 && t <= 32) plan.push_back(t << 20);
+                q = *end ? end + 1 : end;
+            }
+        }
+    }
+    size_t plan_i = 0;
     for (unsigned long long c0 = zc_body, c1 = 0; c0 < nbytes; c0 = c1) {
+        if (!plan.empty()) { chunk_bytes = plan[std::min(plan_i, plan.size() - 1)]; ++plan_i; }
         c1 = std::min(c0 + chunk_bytes, nbytes);
         const unsigned long long copy_len = std::min(c1 + nk::COUNT_HALO, nbytes) - c0;
         DevBuf& b = h->buf[h->cur_buf];

@@ -27,8 +27,9 @@ def child():
         c.stream_begin(); c.stream_push(pin.array, offsets); c.stream_end(); top = c.top_abundant_neurons(20)
         ts.append((time.perf_counter() - t0) * 1e3)
     ts = sorted(ts[5:])
-    print("zerocopy=%s chunk_mb=%s: e2e median %.3f ms, min %.3f ms, spikes %d" % (
-        os.environ.get("NK_ZEROCOPY", "1"), os.environ.get("NK_H2D_CHUNK_MB", "-"), ts[len(ts) // 2], ts[0], c.energy.total_spikes()), flush=True)
+    print("zerocopy=%s chunk_mb=%s plan=%s: e2e median %.3f ms, min %.3f ms, spikes %d" % (
+        os.environ.get("NK_ZEROCOPY", "1"), os.environ.get("NK_H2D_CHUNK_MB", "-"), os.environ.get("NK_H2D_PLAN", "-"),
+        ts[len(ts) // 2], ts[0], c.energy.total_spikes()), flush=True)
 
 
 if __name__ == "__main__":
@@ -36,5 +37,8 @@ if __name__ == "__main__":
         child()
         sys.exit(0)
     subprocess.run([sys.executable, __file__, "child"], env=dict(os.environ, NK_ZEROCOPY="1"))
-    for mb in (2, 4, 8, 16, 32):
+    for mb in (8, 16, 32):
         subprocess.run([sys.executable, __file__, "child"], env=dict(os.environ, NK_ZEROCOPY="0", NK_H2D_CHUNK_MB=str(mb)))
+    for plan in ("32,32,24,12,6,2", "32,32,32,8,3,1", "24,24,24,16,12,6,2", "16,16,16,16,16,16,8,3,1", "32,32,16,16,8,4,2,1",
+                 "8,32,32,24,8,3,1", "4,16,32,32,16,8,4,1"):
+        subprocess.run([sys.executable, __file__, "child"], env=dict(os.environ, NK_ZEROCOPY="0", NK_H2D_PLAN=plan))

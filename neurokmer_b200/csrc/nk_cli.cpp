@@ -31,7 +31,8 @@ static void usage() {
             "      --device <ID>            CUDA device ordinal [default: 0]\n"
             "      --gpus <N>               shard the input over GPUs 0..N-1 (0 = all) [default: 1]\n"
             "      --devices <a,b,..>       shard the input over exactly these CUDA devices\n"
-            "      --exact                  build the exact k-mer table (uniques column by sort, get_count)\n"
+            "      --exact                  build the exact k-mer table (uniques column from it; with several GPUs the\n"
+            "                               per-GPU tables are merged by neuron slice)\n"
             "      --no-uniques             skip the second read of the file that fills the uniques column\n");
 }
 
@@ -97,7 +98,6 @@ int main(int argc, char** argv) {
     }
     if (gpus < 0) { fprintf(stderr, "error: --gpus must be >= 0\n"); return 2; }
     if (!devices.empty()) gpus = (int)devices.size();
-    if ((gpus > 1 || !devices.empty()) && exact) { fprintf(stderr, "error: --exact needs --gpus 1 (the exact k-mer table is single-GPU)\n"); return 2; }
     const int crc = !devices.empty() ? nk_create_multi(&cfg, devices.data(), (int32_t)devices.size(), &h)
                     : gpus > 1       ? nk_create_multi(&cfg, nullptr, gpus, &h)
                                      : nk_create(&cfg, &h);

@@ -216,6 +216,17 @@ def test_group_file_and_cli(tmp_path):
     want = subprocess.check_output(args, text=True)
     got = subprocess.check_output(args + ["--devices", "0,0"], text=True)
     assert got == want and "unique k-mers colliding" in got
+    # --exact on a group: the uniques column comes from the table merged across the members
+    want_x = subprocess.check_output(args + ["--exact"], text=True)
+    got_x = subprocess.check_output(args + ["--exact", "--devices", "0,0,0"], text=True)
+    assert got_x == want_x == want
+    g.enable_exact_counts(True); one.enable_exact_counts(True)
+    g.reset(); one.reset()
+    g.process_file_streaming(str(fa)); one.process_file_streaming(str(fa))
+    assert g.top_abundant_neurons(20) == one.top_abundant_neurons(20)
+    gk, gc = g.exact_table(); ok, oc = one.exact_table()
+    np.testing.assert_array_equal(gk, ok); np.testing.assert_array_equal(gc, oc)
+    np.testing.assert_array_equal(g.kmer_per_neuron(), one.kmer_per_neuron())
 
 
 def test_group_rejects_what_it_cannot_do():

@@ -1586,3 +1586,48 @@ def test_runs_of_n_are_counted_once_per_warp_not_once_per_window(coracle, k, poo
         c.process_batch_packed(codes, other, offsets)
         np.testing.assert_array_equal(c.currents(), exp)
         c.close()
+
+
+@pytest.mark.parametrize("k,pool", [(31, 100_003), (15, 4096)])
+def test_runs_of_n_in_exact_tables_and_the_uniques_pass(coracle, k, pool):
+    """The count kernel sums the windows inside a run of N per warp (word 0, one neuron).  The exact tables then get
+    ONE weighted record for all of them, the uniques pass one copy: counts[0] must still be the number of such windows
+    (plus poly-A, which is word 0 by the normal path), kmer_per_neuron and the uniques column unchanged, and
+    process_sequence (which ADDS to the table) must count the neuron as touched once per sequence."""
+    rng = np.random.default_rng(77 + k)
+    a = np.frombuffer(random_dna(rng, 150_000, 0.002), np.uint8).copy()
+    a[10_000:16_000] = ord("N"); a[60_000:60_100] = ord("N"); a[99_990:104_096] = ord("n")
+    a[120_000:120_200] = ord("A")
+    seqs = [a.tobytes(), b"N" * 5000, random_dna(rng, 40_000), b"N" * (k - 1), b"N" * k]
+    keys, counts, uni = _oracle_tables(coracle, seqs, k, pool, True)
+    c = make(k, pool, True); c.enable_exact_counts(True)
+    c.process_parallel(seqs)
+    gk, gc = c.exact_table()
+    np.testing.assert_array_equal(gk, keys); np.testing.assert_array_equal(gc, counts)
+    assert keys[0] == 0 and c.get_count(0) == int(counts[0]) and int(counts[0]) > 9000
+    np.testing.assert_array_equal(c.kmer_per_neuron(), uni)
+    top = c.top_abundant_neurons(20)
+    assert [t[2] for t in top] == [int(uni[t[0]]) for t in top]
+    # the same rows by the second, filtered pass (no table): the neuron of word 0 is among the top rows
+    u = make(k, pool, True)
+    u.process_parallel(seqs)
+    from neurokmer_b200 import flatten
+    rows = u.top_abundant_neurons(20)
+    idx0 = coracle.neuron_index(0, pool)
+    got = u.top_uniques(20, [flatten(seqs)])
+    assert [(r[0], r[1]) for r in got] == [(r[0], r[1]) for r in rows]
+    assert [r[2] for r in got] == [int(uni[r[0]]) for r in rows]
+    assert idx0 in [r[0] for r in rows] or int(counts[0]) < 1000
+    # process_sequence: merge mode with a sequence that is ONLY a run of N, then one that starts with a run
+    s = make(k, pool, True); s.enable_exact_counts(True)
+    total, touched = {}, np.zeros(pool, np.uint32)
+    for q in (b"N" * 3000, b"N" * 700 + random_dna(rng, 2000), random_dna(rng, 1500)):
+        s.process_sequence(q)
+        w = coracle.kmer_words(q, k, True)
+        for x in w.tolist():
+            total[x] = total.get(x, 0) + 1
+        for i in set(coracle.neuron_index(int(x), pool) for x in set(w.tolist())):
+            touched[i] += 1
+        gk, gc = s.exact_table()
+        assert dict(zip(gk.tolist(), gc.tolist())) == total
+        np.testing.assert_array_equal(s.kmer_per_neuron(), touched)

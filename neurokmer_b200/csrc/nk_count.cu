@@ -225,15 +225,16 @@ __device__ __forceinline__ void process_chunk(const CountParams& p, const Window
     constexpr bool EMIT = MODE == 1;
 #ifndef NK_NO_NRUN
     if constexpr (CANON && (MODE == 0 || MODE == 2 || MODE == 4)) {
-        // Runs of N (assembly gaps, centromeres: megabases of them in real genomes).  A base that is not ACGT is code 0
-        // on BOTH strands (src/models.rs:237,249), so every window inside a run is the word 0 and lands on ONE neuron:
-        // half a percent of N in the input sent 565,000 of the bench job's reductions to a single address, and the L2
-        // slice that owns it made the whole kernel 11 % slower (tools/count_ablate.py).  A lane whose 48 bases are all
-        // code 0 on both strands has 16 such windows; the warp adds them up and sends one reduction.
+        // Runs of N (assembly gaps, centromeres: megabases of them in real genomes), poly-A, poly-T.  A base that is not
+        // ACGT is code 0 on BOTH strands (src/models.rs:237,249), A is 0 on the forward strand, T on the complement:
+        // a lane whose 48 bases are all code 0 on ONE strand has 16 windows whose word on that strand is 0, and 0 is the
+        // canonical minimum whatever the other strand holds.  All of them land on ONE neuron: half a percent of N in the
+        // input sent 565,000 of the bench job's reductions to a single address, and the L2 slice that owns it made the
+        // whole kernel 11 % slower (tools/count_ablate.py).  The warp adds such lanes' windows up and sends one reduction.
         // Exact tables (mode 2): those windows are not appended one by one either — their number goes to
         // words_cursor[3] and exact_finalize adds ONE record {word 0, that count} (565,000 copies of one word in one
         // bucket serialised its scatter cursor and its shared-memory counter).  Uniques pass (mode 4): one copy.
-        const bool all_other = (F0 | F1 | F2 | R0 | R1 | R2) == 0u;
+        const bool all_other = (F0 | F1 | F2) == 0u || (R0 | R1 | R2) == 0u;
         const unsigned m = __ballot_sync(0xFFFFFFFFu, all_other);
         if (m) {
             const unsigned cnt = __reduce_add_sync(0xFFFFFFFFu, all_other ? 16u - __popc(inv16 & 0xFFFFu) : 0u);

@@ -1551,7 +1551,8 @@ def test_long_sequence_mode_without_bitmap_equals_bitmap_mode(coracle, k, pool, 
 @pytest.mark.parametrize("k,pool", [(31, 2_000_000), (32, 99_991), (17, 4096), (5, 65_537), (1, 1000)])
 def test_runs_of_n_are_counted_once_per_warp_not_once_per_window(coracle, k, pool):
     """A base that is not ACGT is code 0 on both strands (src/models.rs:237,249), so every window inside a run of N is
-    the word 0 and the count kernel adds a whole lane's (or warp's) windows of such a run with ONE reduction.
+    the word 0 — and so is every window of a poly-A or poly-T run (canonical) — and the count kernel adds a whole
+    lane's (or warp's) windows of such a run with ONE reduction.
     Runs shorter and longer than a lane's 48 bases and a warp's 512, runs that start or end on lane, warp and tile
     boundaries, runs that cross sequence ends (windows there are invalid), IUPAC letters and poly-A next to N
     (poly-A is word 0 too, by the normal path): currents and window totals equal the oracle's."""
@@ -1566,8 +1567,13 @@ def test_runs_of_n_are_counted_once_per_warp_not_once_per_window(coracle, k, poo
     for start, length in [(100, 10), (1000, 47), (2000, 48), (3000, 49), (4096 - 20, 64), (8192, 512), (16384 - 3, 515),
                           (30_000, 5000), (40_960, 4096), (60_000 + 16, 1024), (90_001, 777), (199_000, 1000)]:
         seq[start:start + length] = ord("N")
-    seq[120_000:120_100] = ord("A")                      # poly-A: word 0 through the hash path
+    seq[120_000:120_100] = ord("A")                      # poly-A next to N: word 0 too
     seq[120_100:120_400] = ord("N")
+    seq[140_000:142_000] = ord("T")                      # poly-T: the complement strand's word is 0
+    seq[150_000:150_700] = ord("a"); seq[150_700:151_000] = ord("N"); seq[151_000:151_600] = ord("A")
+    seq[160_000:160_900] = np.frombuffer(b"TtNn", np.uint8)[rng.integers(0, 4, 900)]      # T and N mixed: rc word 0
+    seq[170_000:170_900] = np.frombuffer(b"AaNRY", np.uint8)[rng.integers(0, 5, 900)]     # A and non-ACGT mixed: fwd word 0
+    seq[180_000:180_600] = ord("C"); seq[181_000:181_600] = ord("G")                       # not word 0: the normal path
     seq[130_000:130_200] = np.frombuffer(b"RYKMSWnn", np.uint8)[rng.integers(0, 8, 200)]
     tail_n = np.full(3000, ord("N"), np.uint8)           # a sequence that is one run, then one that starts inside N
     mixed = dna(50_000); mixed[:700] = ord("n"); mixed[-600:] = ord("N")
@@ -1597,7 +1603,7 @@ def test_runs_of_n_in_exact_tables_and_the_uniques_pass(coracle, k, pool):
     rng = np.random.default_rng(77 + k)
     a = np.frombuffer(random_dna(rng, 150_000, 0.002), np.uint8).copy()
     a[10_000:16_000] = ord("N"); a[60_000:60_100] = ord("N"); a[99_990:104_096] = ord("n")
-    a[120_000:120_200] = ord("A")
+    a[120_000:120_200] = ord("A"); a[130_000:131_500] = ord("T"); a[140_000:141_000] = ord("A")
     seqs = [a.tobytes(), b"N" * 5000, random_dna(rng, 40_000), b"N" * (k - 1), b"N" * k]
     keys, counts, uni = _oracle_tables(coracle, seqs, k, pool, True)
     c = make(k, pool, True); c.enable_exact_counts(True)

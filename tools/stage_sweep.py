@@ -26,7 +26,7 @@ def child():
     res = {}
     for name in ("push", "file"):
         ts = []
-        for it in range(8):
+        for it in range(int(os.environ.get('NK_SWEEP_ITERS', 8))):
             c.reset()
             t0 = time.perf_counter()
             if name == "push":
@@ -40,9 +40,10 @@ def child():
             t2 = time.perf_counter()
             ts.append(((t1 - t0) * 1e3, (t2 - t0) * 1e3))
         ts = ts[3:]
-        res[name] = (min(t[0] for t in ts), min(t[1] for t in ts))
+        jobs = sorted(t[1] for t in ts)
+        res[name] = (min(t[0] for t in ts), jobs[0], jobs[len(jobs) // 2], jobs[-1])
     os.unlink(path)
-    print("threads=%s piece_kb=%s affinity=%s  push: stage %.2f ms job %.2f ms | file: %.2f ms job %.2f ms" % (
+    print("threads=%s piece_kb=%s affinity=%s  push: stage %.2f ms, job min %.2f median %.2f max %.2f ms | file: %.2f ms, job min %.2f median %.2f max %.2f ms" % (
         os.environ.get("NK_STAGE_THREADS", "dflt"), os.environ.get("NK_STAGE_PIECE_KB", "2048"),
         "off" if os.environ.get("NK_STAGE_NO_AFFINITY") else "on", *res["push"], *res["file"]), flush=True)
 

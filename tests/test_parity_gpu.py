@@ -1614,6 +1614,10 @@ def test_runs_of_n_in_exact_tables_and_the_uniques_pass(coracle, k, pool):
     np.testing.assert_array_equal(c.kmer_per_neuron(), uni)
     top = c.top_abundant_neurons(20)
     assert [t[2] for t in top] == [int(uni[t[0]]) for t in top]
+    c.process_parallel([b"N" * 3000, b"n" * 10])           # a call whose every window is inside a run: one record
+    gk, gc = c.exact_table()
+    assert gk.tolist() == [0] and gc.tolist() == [3000 - k + 1] and c.get_count(0) == 3000 - k + 1
+    assert int(c.kmer_per_neuron().sum()) == 1 and int(c.currents().sum()) == 3000 - k + 1
     # the same rows by the second, filtered pass (no table): the neuron of word 0 is among the top rows
     u = make(k, pool, True)
     u.process_parallel(seqs)

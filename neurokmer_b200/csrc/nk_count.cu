@@ -21,8 +21,10 @@
 
 #include "nk_kernels.cuh"
 
+// windows hashed side by side in the inner loop.  Round 1 (other kernel body): 2 / 4 / 8 / 16 -> 0.967 / 0.971 / 0.972 /
+// 1.027 ms; the round-2 kernel: 1 / 2 / 3 / 4 / 8 -> 0.7624 / 0.7606 / 0.7606 / 0.7690 / 0.7813 ms (profiles/r02_variants.md)
 #ifndef NK_COUNT_UNROLL
-#define NK_COUNT_UNROLL 4
+#define NK_COUNT_UNROLL 2
 #endif
 
 namespace nk {

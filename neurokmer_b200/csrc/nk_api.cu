@@ -203,7 +203,6 @@ int count_chunk(nk_counter* h, DevBuf& b, const unsigned long long* d_offsets, u
     if (pe && pe->mark0.size() >= kMaxTimedChunks) pe = nullptr;
     if (pe) {
         NK_TRY(get_event(h, &e0));
-        NK_TRY(get_event(h, &e1));
         NK_TRY(get_event(h, &e2));
         NK_CUDA(cudaEventRecord(e0, h->stream));
     }
@@ -216,10 +215,16 @@ int count_chunk(nk_counter* h, DevBuf& b, const unsigned long long* d_offsets, u
     const char* bm_env = getenv("NK_BITMAP");  // NK_BITMAP=1: the bitmap path for long sequences too (A/B runs, tests)
     const bool force_bitmap = bm_env && atoi(bm_env) != 0;
     const int mode = h->exact ? 2 : (short_reads ? 3 : (force_bitmap || nseq_here == 0 ? 0 : 5));
-    if (mode != 5)
+    // (an event record costs ~2.7 us of stream time: a phase with nothing in it shares its neighbour's event)
+    e1 = e0;
+    if (mode != 5) {
         NK_CUDA(nk::launch_mark_invalid(b.invalid, d_offsets, seq_lo, seq_hi, origin, nstarts, h->cfg.k,
                                         h->scalars + 2, h->stream, &h->last.launches));
-    if (pe) NK_CUDA(cudaEventRecord(e1, h->stream));
+        if (pe) {
+            NK_TRY(get_event(h, &e1));
+            NK_CUDA(cudaEventRecord(e1, h->stream));
+        }
+    }
     nk::CountParams p{};
     p.bases = packed ? b.codes : b.bases;
     p.other = packed && b.has_other ? b.other : nullptr;
@@ -900,15 +905,21 @@ int free_devbuf(DevBuf& b) {
 int fold_and_simulate(nk_counter* h, bool skip_zero, PhaseEvents& pe, bool with_topn) {
     NK_TRY(get_event(h, &pe.fold0));
     NK_CUDA(cudaEventRecord(pe.fold0, h->stream));
+    const uint64_t launches_before = h->last.launches;
+    const bool zero_totals = !h->acc_dirty && h->currents_valid_overwrite;
     NK_TRY(unspill(h));
-    if (!h->acc_dirty && h->currents_valid_overwrite) {
+    if (zero_totals) {
         // nothing was counted by this call: totals are all zero (currents are OVERWRITTEN, :174-176)
         NK_TRY(materialize_zero(h));
         NK_CUDA(cudaMemsetAsync(h->currents, 0, h->cfg.pool_size * sizeof(unsigned long long), h->stream));
         h->currents_valid_overwrite = false;
     }
-    NK_TRY(get_event(h, &pe.fold1));
-    NK_CUDA(cudaEventRecord(pe.fold1, h->stream));
+    if (h->last.launches == launches_before && !zero_totals) {
+        pe.fold1 = pe.fold0;   // the fold is fused into the LIF kernel: nothing was enqueued for this phase
+    } else {
+        NK_TRY(get_event(h, &pe.fold1));
+        NK_CUDA(cudaEventRecord(pe.fold1, h->stream));
+    }
     NK_TRY(simulate(h, skip_zero, with_topn));  // folds acc -> currents inside the LIF kernel
     NK_TRY(get_event(h, &pe.lif1));
     NK_CUDA(cudaEventRecord(pe.lif1, h->stream));

@@ -154,6 +154,8 @@ struct nk_counter {
     unsigned long long* post_zero = nullptr;   // [8 u64 ctrl][8*256 u32 hist] zeroed before each launch
     unsigned long long* d_pack = nullptr;      // PACK_MAX_U64
     unsigned long long* h_pack = nullptr;      // pinned mirror
+    unsigned long long* h_pack_dev = nullptr;  // the same buffer as the device sees it (mapped): single-GPU jobs write it directly
+    bool pack_direct = false;                  // the pending pack was written into h_pack by the kernel (no D2H copy)
     unsigned long long topn_hint = 20;         // rows computed speculatively by the fused kernel (CLI: 20)
     unsigned long long top_cached_n = 0;       // rows of the last fused launch (valid until state changes)
     bool top_cache_valid = false, pending_pack = false;

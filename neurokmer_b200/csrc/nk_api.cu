@@ -2305,6 +2305,13 @@ int dist_build_post(nk_counter* h, nk::PostParams& q, unsigned long long* n_top_
     return NK_OK;
 }
 
+// where the merge kernel of a sharded job writes the merged pack: the mapped pinned host buffer when there is one
+// (no D2H copy operation behind the kernel), else device memory that dist_finish copies back
+unsigned long long* merged_pack_out(nk_counter* h) {
+    h->pack_direct = h->h_pack_dev != nullptr;
+    return h->pack_direct ? h->h_pack_dev : h->d_merged;
+}
+
 // host-side state after a sharded job's merged pack has been queued for read-back
 int dist_finish(nk_counter* h, unsigned long long n_out) {
     // accumulators are all-zero between jobs (every peer has read them by now)
@@ -2316,8 +2323,9 @@ int dist_finish(nk_counter* h, unsigned long long n_out) {
     h->dist_job = true;
     h->slice_only = true;
     const size_t bytes = (nk::PACK_HDR + 2 * n_out) * sizeof(unsigned long long);
-    NK_CUDA(cudaMemcpyAsync(h->h_pack, h->d_merged, bytes, cudaMemcpyDeviceToHost, h->stream));
-    h->last.d2h_bytes += bytes;
+    if (!h->pack_direct) NK_CUDA(cudaMemcpyAsync(h->h_pack, h->d_merged, bytes, cudaMemcpyDeviceToHost, h->stream));
+    h->pack_direct = false;
+    h->last.d2h_bytes += bytes;   // (written by the merge kernel itself when the pack lives in mapped host memory)
     h->acc_dirty = false;
     h->acc_kmers = 0;
     h->currents_valid_overwrite = false;
@@ -2392,7 +2400,7 @@ int nk_dist_run(nk_counter* h) {
     h->last.lif_path = 4;
     const unsigned long long n_out = std::min<unsigned long long>(h->topn_hint, h->cfg.pool_size);
     NK_CUDA(nk::launch_merge_mailbox(h->dist_mail[h->dist_rank], h->dist_world, h->dist_rank, n_top, n_out, epoch, q.timeout_ns,
-                                     h->d_merged, h->stream));
+                                     merged_pack_out(h), h->stream));
     ++h->last.launches;
     return dist_finish(h, n_out);
 }
@@ -2405,7 +2413,7 @@ int nk_dist_complete(nk_counter* h, const void* dev_gathered, uint64_t n_each) {
     if (!h->dist_world || !h->streaming) return fail(NK_ERR_STATE, "nk_dist_complete without nk_dist_post");
     NK_CUDA(cudaSetDevice(h->cfg.device));
     const unsigned long long n_out = std::min<unsigned long long>(h->topn_hint, h->cfg.pool_size);
-    NK_CUDA(nk::launch_merge_packs((const unsigned long long*)dev_gathered, h->dist_world, h->dist_rank, n_each, n_out, h->d_merged, h->stream));
+    NK_CUDA(nk::launch_merge_packs((const unsigned long long*)dev_gathered, h->dist_world, h->dist_rank, n_each, n_out, merged_pack_out(h), h->stream));
     ++h->last.launches;
     return dist_finish(h, n_out);
 }

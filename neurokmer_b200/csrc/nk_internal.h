@@ -250,6 +250,7 @@ void collect_timings(nk_counter* h, const PhaseEvents& pe);
 float ev_ms(cudaEvent_t a, cudaEvent_t b);
 int fold_and_simulate(nk_counter* h, bool skip_zero, PhaseEvents& pe, bool with_topn);
 int dist_build_post(nk_counter* h, nk::PostParams& q, unsigned long long* n_top_out);
+unsigned long long* merged_pack_out(nk_counter* h);
 int dist_finish(nk_counter* h, unsigned long long n_out);
 int copy_out(nk_counter* h, void* dst, const void* src, size_t bytes);
 

@@ -153,7 +153,7 @@ int end_sliced(nk_counter* g, bool skip_zero) {
             if (q != r) NK_CUDA(cudaStreamWaitEvent(c->stream, g->ev_posted[(size_t)q], 0));
         if (r == 0) {
             const unsigned long long n_out = std::min<unsigned long long>(c0->topn_hint, c0->cfg.pool_size);
-            NK_CUDA(nk::launch_merge_packs(g->m_gathered, n, 0, n_top, n_out, c0->d_merged, c0->stream));
+            NK_CUDA(nk::launch_merge_packs(g->m_gathered, n, 0, n_top, n_out, merged_pack_out(c0), c0->stream));
             ++c0->last.launches;
             NK_TRY(dist_finish(c0, n_out));  // queues the read-back of the merged pack
         } else {

@@ -26,6 +26,10 @@ followed by the top-20 read-out.  One "step" = one whole job on a freshly reset 
                  -> top-20, wall clock
   result.parity: after the timed legs rank 0 runs the CPU oracle over the WHOLE job (all ranks' shards) and
                  compares currents (sha256 of the u64 array), spike counts, total spikes and the top-20
+  exact_tables : (N=1) the device-resident job with nk_enable_exact_counts (the reference's `counts` and
+                 `kmer_per_neuron` maps), host wall clock per whole job
+  config5      : (N>1) BASELINE configs[4] — 1.25 Gbase per GPU of ONE stream of 100 Mbase sequences (10 Gbp at N=8),
+                 pool 16 M — device-resident, same timing rules as `value`; checked by "every window counted once"
 
 N > 1 (torchrun, one process per GPU): weak scaling — ONE synthetic stream of N x 113 Mbase (7 sequences of
 N x {30,25,20,15,10,8,5} Mbase) cut by window start into N equal ranges: rank r owns starts

@@ -328,13 +328,14 @@ __device__ __forceinline__ void process_chunk(const CountParams& p, const Window
             for (unsigned u = 0; u < 4; ++u) {
                 const unsigned long long word = wbuf[t + 32u * u];
                 const U64 h = siphash13_dev((unsigned)word, (unsigned)(word >> 32), p.rm);
-                atomicAdd(p.acc + fastmod_kind_dev<MODK>(h, p.fm), 1u);
+                // (red, not atomicAdd: the compiler emitted ATOMG with a discarded return value here, which the L2 answers)
+                asm volatile("red.global.add.u32 [%0], %1;" ::"l"(p.acc + fastmod_kind_dev<MODK>(h, p.fm)), "r"(1u) : "memory");
             }
         }
         for (unsigned t = full + lane; t < total; t += 32u) {
             const unsigned long long word = wbuf[t];
             const U64 h = siphash13_dev((unsigned)word, (unsigned)(word >> 32), p.rm);
-            atomicAdd(p.acc + fastmod_kind_dev<MODK>(h, p.fm), 1u);
+            asm volatile("red.global.add.u32 [%0], %1;" ::"l"(p.acc + fastmod_kind_dev<MODK>(h, p.fm)), "r"(1u) : "memory");
         }
         __syncwarp();
     } else {

@@ -278,6 +278,9 @@ int validate_batch(const nk_counter* h, const uint8_t* bases, const uint64_t* of
 int uniques_host_batch(nk_counter* h, const uint8_t* bases, const uint32_t* codes, const uint32_t* other,
                        const uint64_t* offsets, uint64_t nseq);
 
+unsigned long long packed_chunk_bases();
+int ensure_devbuf_packed(DevBuf& b, unsigned long long nbases, bool with_other);
+
 // host batch -> chunked H2D (copy stream) overlapped with mark+count (compute stream)
 int count_host_batch(nk_counter* h, const uint8_t* bases, const uint64_t* offsets, uint64_t nseq, PhaseEvents* pe,
                      int sync) {
@@ -367,6 +370,17 @@ int count_host_batch(nk_counter* h, const uint8_t* bases, const uint64_t* offset
         }
     }
     size_t plan_i = 0;
+    // Pageable memory, second form (default): the pool's threads PACK their pieces (2 bits per base + `other` bits, the
+    // host packer's AVX-512 / AVX2 bodies) into their pinned slots instead of copying them, and the chunks are counted
+    // by the pre-packed kernel: a host thread writes 3/8 B per base instead of 1, PCIe carries 3/8 of the bytes.
+    // Compute-bound per thread: it pays from ten workers on (113 MB: 2.36 ms with twelve against 2.93 ms copied with
+    // eight), so a process that shares the host with seven others keeps the copy.  NK_STAGE_PACK=0 / 1 forces either.
+    const char* pk_env = getenv("NK_STAGE_PACK");
+    const bool pack_stage = pageable_pool && (pk_env ? atoi(pk_env) != 0 : stage_pack_worthwhile(h));
+    if (pack_stage) {
+        chunk_bytes = packed_chunk_bases();
+        h->last.h2d_bytes -= nbytes;   // (counted above as ASCII)
+    }
     for (unsigned long long c0 = zc_body, c1 = 0; c0 < nbytes; c0 = c1) {
         if (!plan.empty()) { chunk_bytes = plan[std::min(plan_i, plan.size() - 1)]; ++plan_i; }
         c1 = std::min(c0 + chunk_bytes, nbytes);
@@ -374,6 +388,23 @@ int count_host_batch(nk_counter* h, const uint8_t* bases, const uint64_t* offset
         DevBuf& b = h->buf[h->cur_buf];
         h->cur_buf ^= 1;
         const bool had = b.compute_done != nullptr;
+        if (pack_stage) {
+            // bases of this chunk plus the halo its last tiles read (64 bases of codes, 128 of `other` bits)
+            const unsigned long long n_pack = std::min(c1 + 128, nbytes) - c0;
+            NK_TRY(ensure_devbuf_packed(b, std::min(chunk_bytes, nbytes), true));
+            NK_TRY(stage_pack_to_device(h, bases + c0, n_pack, b.codes, b.other, had ? b.compute_done : nullptr, h->copy_stream));
+            b.has_other = true;
+            h->last.h2d_bytes += (n_pack + 15) / 16 * 4 + (n_pack + 31) / 32 * 4;
+            NK_CUDA(cudaEventRecord(b.copy_done, h->copy_stream));
+            NK_CUDA(cudaStreamWaitEvent(h->stream, b.copy_done, 0));
+            const uint64_t* first = std::upper_bound(offsets + 1, offsets + nseq + 1, (uint64_t)c0);
+            const unsigned long long seq_lo = (unsigned long long)(first - (offsets + 1));
+            const uint64_t* last = std::lower_bound(offsets, offsets + nseq, (uint64_t)c1);
+            const unsigned long long seq_hi = (unsigned long long)(last - offsets);
+            NK_TRY(count_chunk(h, b, d_offsets, seq_lo, seq_hi, c0, c1 - c0, c1 - c0, pe, true));
+            NK_CUDA(cudaEventRecord(b.compute_done, h->stream));
+            continue;
+        }
         NK_TRY(ensure_devbuf(b, std::min(kChunkBytes, nbytes)));
         if (pageable_pool) {
             // pageable memory: the pool of host threads copies 2 MiB pieces into its pinned slots and issues their H2D

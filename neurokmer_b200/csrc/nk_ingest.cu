@@ -19,6 +19,7 @@
 #include <mutex>
 #include <thread>
 
+#include "nk_host.h"
 #include "nk_internal.h"
 
 using namespace nkd;
@@ -87,12 +88,19 @@ public:
         for (auto& w : workers_) w.th.join();
     }
     bool ok() const { return !init_failed_; }
+    unsigned threads() const { return (unsigned)workers_.size(); }
+    static constexpr unsigned kCopyWorkers = 8;
 
-    int copy(const uint8_t* src, int fd, uint64_t off, uint64_t n, unsigned char* dst, cudaEvent_t after, cudaStream_t then) {
+    // dst_other != null: a PACK job — the workers turn their pieces of ASCII bases into 2-bit code words + `other` bits
+    // (the host packer's SIMD bodies) in their pinned slots and copy those: 3/8 of the bytes on PCIe, and 3/8 of the
+    // bytes written to host memory instead of a second copy of all of them
+    int copy(const uint8_t* src, int fd, uint64_t off, uint64_t n, unsigned char* dst, cudaEvent_t after, cudaStream_t then,
+             unsigned char* dst_other = nullptr) {
         if (n == 0) return NK_OK;
         {
             std::lock_guard<std::mutex> lk(mu_);
-            job_ = Job{src, fd, off, n, dst, after};
+            job_ = Job{src, fd, off, n, dst, after, dst_other,
+                       dst_other ? (unsigned)workers_.size() : std::min<unsigned>((unsigned)workers_.size(), kCopyWorkers)};
             next_.store(0);
             npieces_ = (n + piece_bytes() - 1) / piece_bytes();
             finished_ = 0;
@@ -120,7 +128,8 @@ public:
 
 private:
     struct Job {
-        const uint8_t* src; int fd; uint64_t off, n; unsigned char* dst; cudaEvent_t after;
+        const uint8_t* src; int fd; uint64_t off, n; unsigned char* dst; cudaEvent_t after; unsigned char* dst_other;
+        unsigned active;   // workers that take pieces of this job (copies stop scaling at eight, packing does not)
     };
     struct Worker {
         std::thread th;
@@ -171,7 +180,7 @@ private:
             std::string why = "worker initialisation failed";
             if (!bad && job.after && cudaStreamWaitEvent(w.stream, job.after, 0) != cudaSuccess) { bad = true; why = "cudaStreamWaitEvent"; }
             int k = 0;
-            while (!bad) {
+            while (!bad && t < job.active) {
                 const uint64_t i = next_.fetch_add(1);
                 if (i >= npieces_) break;
                 const uint64_t o = i * piece_bytes(), len = std::min<uint64_t>(piece_bytes(), job.n - o);
@@ -187,6 +196,18 @@ private:
                         got += (uint64_t)r;
                     }
                     if (bad) break;
+                } else if (job.dst_other) {
+                    // codes at the head of the slot (len/4 bytes), `other` bits behind them (len/8 bytes); a piece
+                    // starts on a multiple of 64 bases, i.e. on a word of both arrays
+                    unsigned char* const so = w.slot[s] + piece_bytes() / 4;
+                    nk::host_pack_range(job.src + o, 0, len, reinterpret_cast<uint32_t*>(w.slot[s]), reinterpret_cast<uint32_t*>(so), 0);
+                    const uint64_t cb = (len + 15) / 16 * 4, ob = (len + 31) / 32 * 4;
+                    if (cudaMemcpyAsync(job.dst + o / 4, w.slot[s], cb, cudaMemcpyHostToDevice, w.stream) != cudaSuccess ||
+                        cudaMemcpyAsync(job.dst_other + o / 8, so, ob, cudaMemcpyHostToDevice, w.stream) != cudaSuccess ||
+                        cudaEventRecord(w.ev[s], w.stream) != cudaSuccess) { bad = true; why = "cudaMemcpyAsync"; break; }
+                    w.inflight[s] = true;
+                    w.used = true;
+                    continue;
                 } else {
                     memcpy(w.slot[s], job.src + o, len);
                 }
@@ -247,12 +268,16 @@ static StagePool* pool_of(nk_counter* h) {
     if (!h->stage_pool) {
         unsigned n = std::thread::hardware_concurrency();
         // Measured on the 16-vCPU B200 boxes (tools/stage_sweep.py, profiles/r02_bench.md), 113 MB, 2 MiB pieces, workers
-        // that stay hot between the chunks of a job: pageable batch 3.9 / 3.05 / 2.94 / 2.99 / 2.91 ms and FASTA file
-        // 6.2 / 4.7 / 4.6 / 4.05 / 3.43 ms with 3 / 4 / 5 / 6 / 8 threads (pread copies slower per thread than memcpy).
-        // Eight, but never more than this GPU's share of the host's cores (one process per GPU on an 8-GPU box).
+        // that stay hot between the chunks of a job.  COPY jobs (files: pread; pageable batches without packing): 3.9 /
+        // 3.05 / 2.94 / 2.99 / 2.91 ms (batch) and 6.2 / 4.7 / 4.6 / 4.05 / 3.43 ms (file) with 3 / 4 / 5 / 6 / 8 threads,
+        // no better beyond eight (StagePool::kCopyWorkers).  PACK jobs (pageable batches) are compute-bound per thread:
+        // 3.95 / 3.17 / 3.09 / 2.40 / 2.36 / 2.38 / 2.33 ms with 4 / 6 / 8 / 10 / 12 / 14 / 15 threads — and 7.4 ms with
+        // 16, when the caller's spinning thread has no core left.  Hence up to twelve workers, two cores always left
+        // free, and never more than this GPU's share of the host's cores (one process per GPU on an 8-GPU box).
         int ngpu = 1;
         if (cudaGetDeviceCount(&ngpu) != cudaSuccess || ngpu < 1) { cudaGetLastError(); ngpu = 1; }
-        n = std::min(8u, std::max(2u, n / (unsigned)ngpu));
+        const unsigned share = std::max(2u, n / (unsigned)ngpu);
+        n = share >= 12u ? std::min(12u, share - 2u) : std::min(8u, share);
         if (const char* e = getenv("NK_STAGE_THREADS")) n = (unsigned)atoi(e);
         if (n > 32) n = 32;
         if (n < 1) n = 1;
@@ -269,6 +294,21 @@ int stage_to_device(nk_counter* h, const uint8_t* src, int fd, uint64_t off, uin
     StagePool* p = pool_of(h);
     if (!p) return fail(NK_ERR_OOM, "cannot create the host staging pool (pinned memory / streams)");
     return p->copy(src, fd, off, n, dst, after, then);
+}
+
+// pageable ASCII bases -> packed code words + `other` bits on the device (see StagePool::copy)
+int stage_pack_to_device(nk_counter* h, const uint8_t* src, uint64_t n, unsigned char* dst_codes, unsigned char* dst_other,
+                         cudaEvent_t after, cudaStream_t then) {
+    NvtxRange nvtx("nk:stage (host threads pack 2 bits per base -> pinned slots -> H2D)");
+    StagePool* p = pool_of(h);
+    if (!p) return fail(NK_ERR_OOM, "cannot create the host staging pool (pinned memory / streams)");
+    return p->copy(src, -1, 0, n, dst_codes, after, then, dst_other);
+}
+
+// packing pays from ten workers on (below that a plain copy of the ASCII bytes is faster)
+bool stage_pack_worthwhile(nk_counter* h) {
+    StagePool* p = pool_of(h);
+    return p && p->threads() >= 10;
 }
 
 void stage_pool_destroy(nk_counter* h) {

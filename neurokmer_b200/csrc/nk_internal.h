@@ -261,6 +261,9 @@ int copy_out(nk_counter* h, void* dst, const void* src, size_t bytes);
 // for this event on the device; `then`: this stream waits for all of them.
 int stage_to_device(nk_counter* h, const uint8_t* src, int fd, uint64_t off, uint64_t n, unsigned char* dst,
                     cudaEvent_t after, cudaStream_t then);
+int stage_pack_to_device(nk_counter* h, const uint8_t* src, uint64_t n, unsigned char* dst_codes, unsigned char* dst_other,
+                         cudaEvent_t after, cudaStream_t then);
+bool stage_pack_worthwhile(nk_counter* h);
 void stage_pool_destroy(nk_counter* h);
 // Whole plain FASTA / FASTQ file -> h->staged (bases) + h->staged_offsets, parsed on the device.
 // *handled = false (and NK_OK): this path does not apply (compressed, not a regular file, too large, disabled)

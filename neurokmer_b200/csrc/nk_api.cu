@@ -320,10 +320,20 @@ int count_host_batch(nk_counter* h, const uint8_t* bases, const uint64_t* offset
     if (!at_ok) cudaGetLastError();
     // plain malloc / mmap memory (what the reference's &[Vec<u8>] is), and enough of it to be worth a thread pool
     const char* sp_env = getenv("NK_STAGE_POOL");
-    const bool pageable_pool = wait_copies && at_ok && at.type == cudaMemoryTypeUnregistered && nbytes >= (8ull << 20) &&
-                               (!sp_env || atoi(sp_env) != 0);
+    const bool pool_on = wait_copies && at_ok && nbytes >= (8ull << 20) && (!sp_env || atoi(sp_env) != 0);
+    const bool pageable_pool = pool_on && at.type == cudaMemoryTypeUnregistered;
+    // Second form of the pool's work (default where the host has the cores for it): the threads PACK their pieces (2 bits
+    // per base + `other` bits, the host packer's AVX-512 / AVX2 bodies) into their pinned slots instead of copying them,
+    // and the chunks are counted by the pre-packed kernel: a host thread writes 3/8 B per base instead of 1, PCIe carries
+    // 3/8 of the bytes.  With twelve workers 113 MB take 1.93 ms end to end — less than the 2.37 ms the same bytes need
+    // when the count kernel reads them in place from PINNED memory (the link carries them at 47 GB/s) — so pinned batches
+    // go this way too.  It pays from ten workers on (a process that shares the host with seven others keeps the plain
+    // copy / the in-place read).  NK_STAGE_PACK=0 / 1 forces either.
+    const char* pk_env = getenv("NK_STAGE_PACK");
+    const bool pack_stage = pool_on && (at.type == cudaMemoryTypeUnregistered || at.type == cudaMemoryTypeHost) &&
+                            (pk_env ? atoi(pk_env) != 0 : stage_pack_worthwhile(h));
     // (the file driver double-buffers its own pinned batches and must not block on the kernels: wait_copies == false)
-    if (wait_copies && (!zc_env || atoi(zc_env) != 0) && nbytes >= 4 * (unsigned long long)nk::COUNT_TILE &&
+    if (wait_copies && !pack_stage && (!zc_env || atoi(zc_env) != 0) && nbytes >= 4 * (unsigned long long)nk::COUNT_TILE &&
         ((uintptr_t)bases & 15) == 0) {
         if (at_ok && at.type == cudaMemoryTypeHost && at.devicePointer) {
             zc_body = nbytes;  // the whole batch: the last tile's copy is clamped to the end of the array
@@ -370,13 +380,6 @@ int count_host_batch(nk_counter* h, const uint8_t* bases, const uint64_t* offset
         }
     }
     size_t plan_i = 0;
-    // Pageable memory, second form (default): the pool's threads PACK their pieces (2 bits per base + `other` bits, the
-    // host packer's AVX-512 / AVX2 bodies) into their pinned slots instead of copying them, and the chunks are counted
-    // by the pre-packed kernel: a host thread writes 3/8 B per base instead of 1, PCIe carries 3/8 of the bytes.
-    // Compute-bound per thread: it pays from ten workers on (113 MB: 2.36 ms with twelve against 2.93 ms copied with
-    // eight), so a process that shares the host with seven others keeps the copy.  NK_STAGE_PACK=0 / 1 forces either.
-    const char* pk_env = getenv("NK_STAGE_PACK");
-    const bool pack_stage = pageable_pool && (pk_env ? atoi(pk_env) != 0 : stage_pack_worthwhile(h));
     if (pack_stage) {
         chunk_bytes = packed_chunk_bases();
         h->last.h2d_bytes -= nbytes;   // (counted above as ASCII)

@@ -113,6 +113,9 @@ __attribute__((target("avx512f,avx512bw"))) uint64_t pack_avx512(const uint8_t* 
     uint64_t n_other = 0;
     uint64_t p = p0;
     for (; p + 64 <= p1; p += 64) {
+        // one core streams ~5.6 GB/s of a large array through this loop on its own; asking for the line 2 KiB ahead:
+        // 8.3 GB/s (512 B / 1 KiB / 2 KiB / 4 KiB ahead: 6.4 / 7.4 / 8.3 / 8.5 GB/s, single thread, 96 MB)
+        _mm_prefetch(reinterpret_cast<const char*>(bases + p + 2048), _MM_HINT_T0);
         const __m512i b = _mm512_loadu_si512(bases + p);
         const __mmask64 valid = _mm512_cmpeq_epi8_mask(_mm512_shuffle_epi8(tbl, _mm512_and_si512(b, m0f)), _mm512_and_si512(b, mdf));
         const __m512i h1 = _mm512_srli_epi16(b, 1), h2 = _mm512_srli_epi16(b, 2);

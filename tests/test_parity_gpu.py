@@ -1641,3 +1641,41 @@ def test_runs_of_n_in_exact_tables_and_the_uniques_pass(coracle, k, pool):
         gk, gc = s.exact_table()
         assert dict(zip(gk.tolist(), gc.tolist())) == total
         np.testing.assert_array_equal(s.kmer_per_neuron(), touched)
+
+
+def test_pack_staging_of_host_batches_equals_oracle(coracle, monkeypatch):
+    """Large host batches (>= 8 MiB) are packed to 2 bits per base + `other` bits by the staging pool's host threads on
+    their way to the GPU and counted by the pre-packed kernel (NK_STAGE_PACK=1 forces it whatever the pool size;
+    =0 forces plain copies / the in-place read).  Pageable and pinned sources, an odd source address, sequences cut by
+    the 32 Mbase chunk boundary and by the 2 MiB pieces, runs of N, IUPAC, lower case, a last piece that is not a
+    multiple of 64 bases: same currents, totals and state as the oracle, in all three modes."""
+    from neurokmer_b200 import PinnedBuffer, flatten
+    rng = np.random.default_rng(41)
+    k, pool = 31, 1_000_003
+    lens = [20_000_000, 13_554_433 - 20_000_000 % 7, 2_097_151, 150, 0, 30, 5_000_001]
+    seqs = [np.frombuffer(random_dna(rng, n, 0.001, 0.01, 0.0005), np.uint8).copy() for n in lens]
+    seqs[0][1_000_000:1_004_000] = ord("N"); seqs[0][2_097_100:2_097_300] = ord("n")     # across a 2 MiB piece
+    seqs[1][13_000_000:13_000_700] = ord("T")
+    bases, offsets = flatten([s.tobytes() for s in seqs])
+    assert bases.size > (33 << 20)                       # more than one 32 Mbase chunk
+    o = oracle_counter(k, pool)
+    o.process_streaming([(bases, offsets)])
+    pin = PinnedBuffer(bases.size + 64)
+    pin.array[:bases.size] = bases
+    odd = np.empty(bases.size + 5, np.uint8)[5:]         # pageable, address not a multiple of 4
+    odd[:] = bases
+    for mode in ("1", "0"):
+        monkeypatch.setenv("NK_STAGE_PACK", mode)
+        for src in (bases, odd, pin.array[:bases.size]):
+            c = make(k, pool)
+            c.stream_begin(); c.stream_push(src, offsets); c.stream_end()
+            assert_state_equal(c, o)
+            assert c.timings()["kmers"] == sum(max(0, n - k + 1) for n in lens)
+            c.close()
+    monkeypatch.setenv("NK_STAGE_PACK", "1")
+    c = make(k, pool); c.enable_exact_counts(True)       # exact tables fed by the packed kernel instantiation
+    c.process_batch(bases[:9_000_000], np.array([0, 4_000_000, 9_000_000], np.uint64))
+    keys, counts, uni = _oracle_tables(coracle, [bases[:4_000_000].tobytes(), bases[4_000_000:9_000_000].tobytes()], k, pool, True)
+    gk, gc = c.exact_table()
+    np.testing.assert_array_equal(gk, keys); np.testing.assert_array_equal(gc, counts)
+    c.close()

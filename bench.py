@@ -10,9 +10,10 @@ followed by the top-20 read-out.  One "step" = one whole job on a freshly reset 
   value : whole-job throughput with the bases already resident in HBM (CUDA events on the
           library's stream, L2 flushed before every step, max over ranks)
   e2e   : the same job through the public host API with HOST buffers: pinned bases ->
-          nk_stream_push (the count kernel reads the pinned batch in place across PCIe; pageable
-          memory would take the chunked, double-buffered H2D pipeline) -> nk_stream_end ->
-          nk_top_n (D2H of the result rows), wall clock around the call sequence
+          nk_stream_push -> nk_stream_end -> nk_top_n (D2H of the result rows), wall clock around the
+          call sequence.  Inside the push the library either lets the count kernel read the pinned batch
+          in place across PCIe (`e2e_inplace` forces this), or — on a host with >= 10 staging workers —
+          has its host threads pack the bases to 2 bits each on the way into the H2D copies
   e2e_prepacked: e2e with the input handed over in the pre-packed form (2 bits per base +
           `other` bits, nk_stream_push_packed): 3/8 of the bytes on PCIe; packing is untimed
   roofline     : the count kernel (windowing+SipHash+mod+RED) against the three limits the
@@ -485,12 +486,17 @@ def gpu_arm(args):
         return c.top_abundant_neurons(TOPN)
 
     if not args.no_e2e:
-        for name, job in (("e2e", job_e2e), ("e2e_pageable", job_e2e_pageable), ("e2e_prepacked", job_e2e_packed),
-                          ("e2e_file", job_e2e_file)):
+        # (e2e_inplace runs first: after a leg in which the CPU has read the pinned batch, the GPU's reads of it across
+        #  PCIe are slower — 2.76 instead of 2.35 ms — presumably snoops of lines the host's caches still hold)
+        for name, job in (("e2e_inplace", job_e2e), ("e2e", job_e2e), ("e2e_pageable", job_e2e_pageable),
+                          ("e2e_prepacked", job_e2e_packed), ("e2e_file", job_e2e_file)):
             if name == "e2e_file" and file_path is None:
                 continue
+            if name == "e2e_inplace":   # the same pinned batch with the host-side packing switched off (A/B)
+                os.environ["NK_STAGE_PACK"] = "0"
             timed(job, 2)
             st, ph, tp, _ = timed(job, args.steps)
+            os.environ.pop("NK_STAGE_PACK", None)
             assert tp == top, f"{name} and resident legs disagree"
             legs[name] = (st, ph)
 
@@ -623,11 +629,12 @@ def gpu_arm(args):
     file_ms = leg_ms("e2e_file")
     vals = [float(sum(x[0] for x in steps_res)), leg_ms("e2e"), leg_ms("e2e_pageable"), leg_ms("e2e_prepacked"),
             float(sum(x[0] for x in strong[0])) if strong else float("nan"),
-            ph_mean("count_ms"), ph_mean("exch_wait_ms"), ph_mean("exch_reduce_ms"), ph_mean("merge_ms"), ph_mean("post_ms")]
+            ph_mean("count_ms"), ph_mean("exch_wait_ms"), ph_mean("exch_reduce_ms"), ph_mean("merge_ms"), ph_mean("post_ms"),
+            leg_ms("e2e_inplace")]
     t = torch.tensor(vals, dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, pg_ms, pk_ms, strong_ms, count_ms_max, wait_ms, reduce_ms, merge_ms, post_ms = (float(x) for x in t)
+    dev_ms, e2e_ms, pg_ms, pk_ms, strong_ms, count_ms_max, wait_ms, reduce_ms, merge_ms, post_ms, ip_ms = (float(x) for x in t)
     job_kmers = total_kmers * args.steps
     value = job_kmers / (dev_ms * 1e-3)
 
@@ -732,6 +739,13 @@ def gpu_arm(args):
                                                  f"{d['exact_sample_s']:.2f} s), same LIF + top-20; job time extrapolated = "
                                                  f"{d['exact_job_extrapolated']:.2f} s")}}
 
+        def host_path(name):
+            if name not in legs:
+                return None
+            moved = int(legs[name][1][-1]["h2d_bytes"])
+            return ("packed to 2 bits per base by the library's host threads on the way" if moved < nb // 2
+                    else "ASCII bytes cross the link (in-place read of pinned memory, or copies of pageable memory)")
+
         def leg_record(name, ms, extra=None):
             if name not in legs:
                 return None
@@ -755,10 +769,14 @@ def gpu_arm(args):
             "steps": args.steps, "warmup": W, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": make_config(world, args.dist),
-            "e2e": leg_record("e2e", e2e_ms),
-            # the same job from PAGEABLE host memory (plain malloc: the reference's &[Vec<u8>]): staged through the
-            # library's pinned ring in 32 MiB chunks instead of being read in place
-            "e2e_pageable": leg_record("e2e_pageable", pg_ms),
+            # host path of the pinned batch: with >= 10 staging workers (a host with cores to spare) the library's threads pack
+            # the bases to 2 bits each on their way into the H2D copies (h2d_bytes_per_step = 3/8 of the input); otherwise
+            # the count kernel reads the pinned batch in place across PCIe.  `e2e_inplace` is the second path forced.
+            "e2e": leg_record("e2e", e2e_ms, {"host_path": host_path("e2e")}),
+            "e2e_inplace": leg_record("e2e_inplace", ip_ms, {"host_path": host_path("e2e_inplace")}),
+            # the same job from PAGEABLE host memory (plain malloc: the reference's &[Vec<u8>]): through the staging pool
+            # (packed on the way where the host has the cores, plain copies otherwise)
+            "e2e_pageable": leg_record("e2e_pageable", pg_ms, {"host_path": host_path("e2e_pageable")}),
             # same job, same API, input handed over in the library's pre-packed form (2-bit codes + `other`
             # bits in pinned host memory: nk_stream_push_packed).  The packing itself (nk_pack_bases, host
             # SIMD, all cores) is NOT in this timed region — its cost is reported beside it.

@@ -327,11 +327,12 @@ int count_host_batch(nk_counter* h, const uint8_t* bases, const uint64_t* offset
     // and the chunks are counted by the pre-packed kernel: a host thread writes 3/8 B per base instead of 1, PCIe carries
     // 3/8 of the bytes.  With twelve workers 113 MB take 1.93 ms end to end — less than the 2.37 ms the same bytes need
     // when the count kernel reads them in place from PINNED memory (the link carries them at 47 GB/s) — so pinned batches
-    // go this way too.  It pays from ten workers on (a process that shares the host with seven others keeps the plain
-    // copy / the in-place read).  NK_STAGE_PACK=0 / 1 forces either.
+    // go this way too where the process has the host to itself (one GPU in the box).  It pays from ten workers on (a
+    // process that shares the host with seven others keeps the plain copy / the in-place read).  NK_STAGE_PACK=0 / 1
+    // forces either.
     const char* pk_env = getenv("NK_STAGE_PACK");
     const bool pack_stage = pool_on && (at.type == cudaMemoryTypeUnregistered || at.type == cudaMemoryTypeHost) &&
-                            (pk_env ? atoi(pk_env) != 0 : stage_pack_worthwhile(h));
+                            (pk_env ? atoi(pk_env) != 0 : stage_pack_worthwhile(h, at.type == cudaMemoryTypeHost));
     // (the file driver double-buffers its own pinned batches and must not block on the kernels: wait_copies == false)
     if (wait_copies && !pack_stage && (!zc_env || atoi(zc_env) != 0) && nbytes >= 4 * (unsigned long long)nk::COUNT_TILE &&
         ((uintptr_t)bases & 15) == 0) {

@@ -263,7 +263,7 @@ int stage_to_device(nk_counter* h, const uint8_t* src, int fd, uint64_t off, uin
                     cudaEvent_t after, cudaStream_t then);
 int stage_pack_to_device(nk_counter* h, const uint8_t* src, uint64_t n, unsigned char* dst_codes, unsigned char* dst_other,
                          cudaEvent_t after, cudaStream_t then);
-bool stage_pack_worthwhile(nk_counter* h);
+bool stage_pack_worthwhile(nk_counter* h, bool pinned_source);
 void stage_pool_destroy(nk_counter* h);
 // Whole plain FASTA / FASTQ file -> h->staged (bases) + h->staged_offsets, parsed on the device.
 // *handled = false (and NK_OK): this path does not apply (compressed, not a regular file, too large, disabled)
